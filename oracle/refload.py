@@ -1,0 +1,174 @@
+"""Import the LIVE reference hot-path modules from /root/reference (build container only).
+
+TEST INFRASTRUCTURE.  Used by ``oracle/make_golden.py`` and by the CPU tests that
+cross-check the oracle restatement when ``/root/reference`` is present.  Nothing
+here runs on the GPU box (the reference tree does not exist there).
+
+``import fme`` itself cannot work in this image (xarray, dacite, netCDF4, zarr,
+tensorly, torch_harmonics ... are absent), so this loads only the files on the
+hot path, unmodified, from where they lie:
+
+  * fme/fft.py                              (executed as-is)
+  * fme/sht_fix.py lines 60-226             (the two SHT classes, verbatim text)
+  * fme/ace/models/modulus/*                (imported as a package alias)
+
+and provides stand-ins for the absent third-party imports:
+``torch_harmonics`` (its RealSHT/InverseRealSHT *are* the fme classes after the
+monkey-patch at fme/sht_fix.py:228-229; its quadrature / legpoly come from the
+oracle restatement), ``torch_harmonics.distributed``, ``tensorly``, ``tltorch``.
+"""
+import os
+import sys
+import types
+
+import torch
+import torch.nn as nn
+
+REFERENCE_ROOT = os.environ.get("ACE_REFERENCE_ROOT", "/root/reference")
+
+
+def available():
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "fme", "sht_fix.py"))
+
+
+_CACHE = {}
+
+
+def load():
+    """Returns a namespace with RealSHT, InverseRealSHT, rfft, irfft, SphericalFourierNeuralOperatorNet."""
+    if "ns" in _CACHE:
+        return _CACHE["ns"]
+    if not available():
+        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
+    sys.dont_write_bytecode = True  # the reference tree is read-only
+
+    from . import legendre as _leg
+    from . import quadrature as _quad
+
+    # --- fme/fft.py, executed unmodified
+    fft_ns = {}
+    with open(os.path.join(REFERENCE_ROOT, "fme", "fft.py")) as f:
+        exec(compile(f.read(), "fme/fft.py", "exec"), fft_ns)
+
+    # --- fme/sht_fix.py:60-226 (class RealSHT .. end of InverseRealSHT.forward)
+    with open(os.path.join(REFERENCE_ROOT, "fme", "sht_fix.py")) as f:
+        lines = f.readlines()
+    start = next(i for i, ln in enumerate(lines) if ln.startswith("class RealSHT"))
+    stop = next(i for i, ln in enumerate(lines) if ln.startswith("torch_harmonics.RealSHT"))
+    src = "".join(lines[start:stop])
+
+    def _t(fn):
+        def wrapped(*a, **k):
+            out = fn(*a, **k)
+            return tuple(torch.from_numpy(o.copy()) for o in out)
+        return wrapped
+
+    sht_ns = {
+        "torch": torch,
+        "nn": nn,
+        "rfft": fft_ns["rfft"],
+        "irfft": fft_ns["irfft"],
+        "get_device": lambda: torch.device("cpu"),
+        "legendre_gauss_weights": _t(_quad.legendre_gauss_weights),
+        "lobatto_weights": _t(_quad.lobatto_weights),
+        "clenshaw_curtiss_weights": _t(_quad.clenshaw_curtiss_weights),
+        "_precompute_legpoly": lambda mmax, lmax, t, norm="ortho", inverse=False, csphase=True: _leg.precompute_legpoly(
+            mmax, lmax, t.numpy(), norm=norm, inverse=inverse, csphase=csphase
+        ),
+    }
+    exec(compile("\n" * start + src, "fme/sht_fix.py", "exec"), sht_ns)
+
+    # --- stand-ins for absent third-party packages
+    th = types.ModuleType("torch_harmonics")
+    th.RealSHT = sht_ns["RealSHT"]
+    th.InverseRealSHT = sht_ns["InverseRealSHT"]
+    thd = types.ModuleType("torch_harmonics.distributed")
+
+    class DistributedRealSHT(nn.Module):
+        pass
+
+    class DistributedInverseRealSHT(nn.Module):
+        pass
+
+    thd.DistributedRealSHT = DistributedRealSHT
+    thd.DistributedInverseRealSHT = DistributedInverseRealSHT
+    th.distributed = thd
+    tl = types.ModuleType("tensorly")
+    tl.set_backend = lambda *_a, **_k: None
+    tl.einsum = torch.einsum
+    tl.ndim = lambda t: t.ndim
+    tlt = types.ModuleType("tltorch")
+    tlt_ft = types.ModuleType("tltorch.factorized_tensors")
+    tlt_core = types.ModuleType("tltorch.factorized_tensors.core")
+
+    class FactorizedTensor:  # only used in isinstance checks on this path
+        pass
+
+    tlt_core.FactorizedTensor = FactorizedTensor
+    tlt_ft.core = tlt_core
+    tlt.factorized_tensors = tlt_ft
+    for name, mod in [
+        ("torch_harmonics", th),
+        ("torch_harmonics.distributed", thd),
+        ("tensorly", tl),
+        ("tltorch", tlt),
+        ("tltorch.factorized_tensors", tlt_ft),
+        ("tltorch.factorized_tensors.core", tlt_core),
+    ]:
+        sys.modules.setdefault(name, mod)
+
+    pkg = types.ModuleType("ace_refmod")
+    pkg.__path__ = [os.path.join(REFERENCE_ROOT, "fme", "ace", "models", "modulus")]
+    sys.modules["ace_refmod"] = pkg
+    from ace_refmod.sfnonet import SphericalFourierNeuralOperatorNet  # noqa: E402
+
+    ns = types.SimpleNamespace(
+        RealSHT=sht_ns["RealSHT"],
+        InverseRealSHT=sht_ns["InverseRealSHT"],
+        rfft=fft_ns["rfft"],
+        irfft=fft_ns["irfft"],
+        SphericalFourierNeuralOperatorNet=SphericalFourierNeuralOperatorNet,
+    )
+    _CACHE["ns"] = ns
+    return ns
+
+
+class Params:
+    """Attribute bag mirroring SphericalFourierNeuralOperatorBuilder's fields (fme/ace/registry/sfno.py:21-42)."""
+
+    def __init__(self, **kw):
+        defaults = dict(
+            spectral_transform="sht",
+            filter_type="linear",
+            operator_type="diagonal",
+            scale_factor=1,
+            residual_filter_factor=1,
+            embed_dim=256,
+            num_layers=12,
+            hard_thresholding_fraction=1.0,
+            normalization_layer="instance_norm",
+            use_mlp=True,
+            activation_function="gelu",
+            encoder_layers=1,
+            pos_embed=True,
+            big_skip=True,
+            rank=1.0,
+            factorization=None,
+            separable=False,
+            complex_network=True,
+            complex_activation="real",
+            spectral_layers=1,
+            checkpointing=0,
+            data_grid="legendre-gauss",
+        )
+        defaults.update(kw)
+        for k, v in defaults.items():
+            setattr(self, k, v)
+
+
+def build_reference_net(img_shape, in_chans, out_chans, **builder_fields):
+    """The net exactly as SphericalFourierNeuralOperatorBuilder.build makes it (fme/ace/registry/sfno.py:44-61)."""
+    ns = load()
+    return ns.SphericalFourierNeuralOperatorNet(
+        params=Params(**builder_fields), in_chans=in_chans, out_chans=out_chans, img_shape=tuple(img_shape)
+    )
