@@ -1,0 +1,166 @@
+// Library-level C ABI: errors, options, launch counter, GEMM dispatcher, development GEMM hook.
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+namespace ace {
+
+std::atomic<long long> g_launch_count{0};
+std::atomic<long long> g_umma_count{0}, g_simt_count{0};
+
+static thread_local std::string t_last_error;
+void set_last_error(const char* msg) { t_last_error = msg ? msg : ""; }
+
+Options& options() {
+  static Options o;
+  return o;
+}
+
+namespace {
+struct ProfRec {
+  std::string name;
+  cudaEvent_t start, stop;
+};
+std::vector<ProfRec> g_prof;
+}  // namespace
+
+ProfileScope::ProfileScope(const char* n, cudaStream_t s) : name(n), stream(s) {
+  if (!options().profile) return;
+  if (cudaEventCreate(&start) != cudaSuccess || cudaEventCreate(&stop) != cudaSuccess) {
+    start = stop = nullptr;
+    return;
+  }
+  cudaEventRecord(start, stream);
+}
+ProfileScope::~ProfileScope() {
+  if (!start) return;
+  cudaEventRecord(stop, stream);
+  g_prof.push_back({name, start, stop});
+}
+
+void run_gemm(const GemmOp& op, cudaStream_t stream) {
+  ProfileScope prof(op.name, stream);
+  const char* why = nullptr;
+  if (!options().force_simt && umma_eligible(op, &why)) {
+    run_gemm_umma(op, stream);
+  } else {
+    run_gemm_simt(op, stream);
+  }
+}
+
+}  // namespace ace
+
+using namespace ace;
+
+extern "C" int ace_version(void) { return 100; }
+
+extern "C" const char* ace_last_error(void) { return t_last_error.c_str(); }
+
+extern "C" int ace_set_option(const char* key, int value) {
+  ACE_API_BEGIN
+  ACE_REQUIRE(key != nullptr, "ace_set_option: null key");
+  if (!strcmp(key, "force_simt")) options().force_simt = value;
+  else if (!strcmp(key, "profile")) options().profile = value;
+  else if (!strcmp(key, "split_terms")) {
+    ACE_REQUIRE(value == 1 || value == 3, "split_terms must be 1 or 3");
+    options().split_terms = value;
+  } else if (!strcmp(key, "umma_bk")) {
+    ACE_REQUIRE(value == 32 || value == 64, "umma_bk must be 32 or 64");
+    options().umma_bk = value;
+  } else if (!strcmp(key, "umma_bn")) {
+    ACE_REQUIRE(value == 0 || value == 128 || value == 192 || value == 256, "umma_bn must be 0, 128, 192 or 256");
+    options().umma_bn = value;
+  } else ACE_REQUIRE(false, "ace_set_option: unknown option '%s'", key);
+  ACE_API_END
+}
+
+extern "C" int ace_get_option(const char* key) {
+  if (!key) return -1;
+  if (!strcmp(key, "force_simt")) return options().force_simt;
+  if (!strcmp(key, "profile")) return options().profile;
+  if (!strcmp(key, "split_terms")) return options().split_terms;
+  if (!strcmp(key, "umma_bk")) return options().umma_bk;
+  if (!strcmp(key, "count_umma")) return (int)g_umma_count.load();
+  if (!strcmp(key, "count_simt")) return (int)g_simt_count.load();
+  if (!strcmp(key, "umma_bn")) return options().umma_bn;
+  return -1;
+}
+
+extern "C" long long ace_launch_count(void) { return g_launch_count.load(); }
+
+// Synchronises the device, writes "name count total_ms\n" lines (aggregated, launch order of first
+// appearance) into buf and clears the records.  Returns the number of bytes written (excluding NUL).
+extern "C" int ace_profile_report(char* buf, int buflen) {
+  if (!buf || buflen <= 0) return 0;
+  cudaDeviceSynchronize();
+  std::vector<std::string> order;
+  std::vector<double> total;
+  std::vector<long long> count;
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.start, r.stop);
+    cudaEventDestroy(r.start);
+    cudaEventDestroy(r.stop);
+    size_t i = 0;
+    for (; i < order.size(); ++i)
+      if (order[i] == r.name) break;
+    if (i == order.size()) {
+      order.push_back(r.name);
+      total.push_back(0.0);
+      count.push_back(0);
+    }
+    total[i] += ms;
+    count[i] += 1;
+  }
+  g_prof.clear();
+  std::string out;
+  for (size_t i = 0; i < order.size(); ++i) out += strprintf("%s %lld %.6f\n", order[i].c_str(), count[i], total[i]);
+  int n = (int)std::min<size_t>(out.size(), (size_t)buflen - 1);
+  memcpy(buf, out.data(), n);
+  buf[n] = 0;
+  return n;
+}
+
+// D[z][m][n] = sum_k A[z][m][k] * B[z][n][k] through the split-plane machinery (tests only)
+extern "C" int ace_dev_gemm(const float* a_dev, const float* b_dev, float* d_dev, int m, int n, int k, int nbatch,
+                            int a_mn_major, int impl, void* stream) {
+  ACE_API_BEGIN
+  ACE_REQUIRE(a_dev && b_dev && d_dev && m > 0 && n > 0 && k > 0 && nbatch > 0, "ace_dev_gemm: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  // A planes: K-major [z][m][kp] or MN-major [z][k][mp]; B planes [z][n][kp]
+  const int kp = (int)round_up(k, 8), mp = (int)round_up(m, 8);
+  const long long a_per = a_mn_major ? (long long)k * mp : (long long)m * kp;
+  const long long b_per = (long long)n * kp;
+  DevBuf abuf, bbuf;
+  abuf.ensure(2 * (size_t)(a_per * nbatch) * sizeof(bf16));
+  bbuf.ensure(2 * (size_t)(b_per * nbatch) * sizeof(bf16));
+  if (a_mn_major) launch_split_pad(a_dev, (long long)nbatch * k, m, mp, abuf.as<bf16>(), a_per * nbatch, s);
+  else launch_split_pad(a_dev, (long long)nbatch * m, k, kp, abuf.as<bf16>(), a_per * nbatch, s);
+  launch_split_pad(b_dev, (long long)nbatch * n, k, kp, bbuf.as<bf16>(), b_per * nbatch, s);
+  GemmOp op = make_gemm_op("dev_gemm");
+  op.M = m;
+  op.N = n;
+  op.K = k;
+  op.Z2 = nbatch;
+  if (a_mn_major) op.A = {abuf.as<bf16>(), a_per * nbatch, 1, (long long)mp, 0, a_per};
+  else op.A = {abuf.as<bf16>(), a_per * nbatch, (long long)kp, 1, 0, a_per};
+  op.B = {bbuf.as<bf16>(), b_per * nbatch, (long long)kp, 1, 0, b_per};
+  op.epi.flags = EPI_OUT_F32;
+  op.epi.outf = d_dev;
+  op.epi.f_z2 = (long long)m * n;
+  op.epi.f_m0 = n;
+  op.epi.f_n = 1;
+  if (impl == 0) {
+    run_gemm_simt(op, s);
+  } else {
+    const char* why = nullptr;
+    if (!umma_eligible(op, &why)) throw Error(ACE_ERR_INVALID, std::string("ace_dev_gemm: not eligible for tcgen05 kernel: ") + (why ? why : "?"));
+    run_gemm_umma(op, s);
+  }
+  ACE_CHECK_CUDA(cudaStreamSynchronize(s));  // temporaries are freed on return
+  ACE_API_END
+}

@@ -1,0 +1,146 @@
+// Shared host/device helpers for the ace_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/ace_b200.h"
+
+namespace ace {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- errors: internal code throws, the extern "C" layer converts to code + message ----
+struct Error : public std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+inline std::string strprintf(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  return std::string(buf);
+}
+
+#define ACE_CHECK_CUDA(expr)                                                                       \
+  do {                                                                                             \
+    cudaError_t err__ = (expr);                                                                    \
+    if (err__ != cudaSuccess)                                                                      \
+      throw ::ace::Error(ACE_ERR_CUDA, ::ace::strprintf("%s failed: %s (%s:%d)", #expr,           \
+                                                        cudaGetErrorString(err__), __FILE__, __LINE__)); \
+  } while (0)
+
+#define ACE_REQUIRE(cond, ...)                                                           \
+  do {                                                                                   \
+    if (!(cond)) throw ::ace::Error(ACE_ERR_INVALID, ::ace::strprintf(__VA_ARGS__));    \
+  } while (0)
+
+// extern "C" wrappers: convert exceptions to (code, thread-local message)
+void set_last_error(const char* msg);
+#define ACE_API_BEGIN try {
+#define ACE_API_END                         \
+  }                                         \
+  catch (const ::ace::Error& e) {           \
+    ::ace::set_last_error(e.what());        \
+    return e.code;                          \
+  }                                         \
+  catch (const std::exception& e) {         \
+    ::ace::set_last_error(e.what());        \
+    return ACE_ERR_INVALID;                 \
+  }                                         \
+  return ACE_OK;
+
+// launch bookkeeping (ace_launch_count) + launch error check
+extern std::atomic<long long> g_launch_count;
+extern std::atomic<long long> g_umma_count, g_simt_count;  // GEMMs routed to each kernel
+inline void after_launch(const char* what) {
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    throw Error(ACE_ERR_CUDA, strprintf("launch of %s failed: %s", what, cudaGetErrorString(e)));
+  }
+}
+
+// Optional per-kernel timing (option "profile" = 1): CUDA events around every launch on its own stream,
+// aggregated by name in ace_profile_report().  Off by default; cannot be used under graph capture.
+struct ProfileScope {
+  const char* name;
+  cudaStream_t stream;
+  cudaEvent_t start = nullptr, stop = nullptr;
+  ProfileScope(const char* name, cudaStream_t stream);
+  ~ProfileScope();
+};
+
+// runtime options
+struct Options {
+  int profile = 0;
+  int force_simt = 0;
+  int split_terms = 3;
+  int umma_bk = 64;  // K extent of one pipeline stage of the tcgen05 kernel (64 -> 128B swizzle, 32 -> 64B)
+  int umma_bn = 0;   // 0 = choose per op; otherwise force the N tile (128 / 192 / 256)
+};
+Options& options();
+
+inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
+
+// ---- device buffer with RAII (allocations happen at create/first-use time, never per step) ----
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) {
+    o.p = nullptr;
+    o.bytes = 0;
+  }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) {
+      release();
+      p = o.p;
+      bytes = o.bytes;
+      o.p = nullptr;
+      o.bytes = 0;
+    }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  // (re)allocate zero-filled storage of at least n bytes; returns true if a new allocation was made
+  bool ensure(size_t n) {
+    if (n <= bytes && p) return false;
+    release();
+    ACE_CHECK_CUDA(cudaMalloc(&p, n));
+    ACE_CHECK_CUDA(cudaMemset(p, 0, n));
+    ACE_CHECK_CUDA(cudaDeviceSynchronize());  // allocation time only: make the zero fill visible to every stream
+    bytes = n;
+    return true;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// ---- split-bf16 representation: v ~= hi + lo, |v - (hi+lo)| <= 2^-17 |v| ----
+__host__ __device__ inline void split_bf16(float v, bf16& hi, bf16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+__host__ __device__ inline float join_bf16(bf16 hi, bf16 lo) { return __bfloat162float(hi) + __bfloat162float(lo); }
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+}  // namespace ace

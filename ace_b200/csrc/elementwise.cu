@@ -1,0 +1,289 @@
+// HBM-bound streaming kernels around the GEMMs: InstanceNorm apply + bf16 split, weight
+// re-layout, spectral layout conversions, the stepper's pack/normalise/denormalise.
+#include "kernels.cuh"
+
+namespace ace {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline int grid_for(long long work_items, int per_block, int max_blocks = 148 * 16) {
+  long long b = (work_items + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  if (b > max_blocks) b = max_blocks;
+  return (int)b;
+}
+
+// ---------------------------------------------------------------------------------------------
+// norm + split: one (b, c) row per blockIdx.y, grid-stride over HW with 4-wide vectors
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) norm_split_kernel(const float* __restrict__ src, int C, long long HW,
+                                                             const double* __restrict__ stats,
+                                                             const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, float eps,
+                                                             bf16* __restrict__ dst, long long plane, long long dst_b,
+                                                             long long dst_c) {
+  const int bc = blockIdx.y;
+  const int b = bc / C, c = bc % C;
+  float alpha = 1.f, shift = 0.f;
+  if (stats != nullptr) {
+    double s = stats[(long long)bc * 2], q = stats[(long long)bc * 2 + 1];
+    double mean = s / (double)HW;
+    double var = q / (double)HW - mean * mean;
+    if (var < 0.0) var = 0.0;
+    double invstd = 1.0 / sqrt(var + (double)eps);
+    double a = invstd * (double)gamma[c];
+    alpha = (float)a;
+    shift = (float)((double)beta[c] - mean * a);
+  }
+  const float* s = src + (long long)bc * HW;
+  bf16* dh = dst + (long long)b * dst_b + (long long)c * dst_c;
+  bf16* dl = dh + plane;
+  const bool vec = ((HW & 3) == 0) && ((((uintptr_t)s) & 15) == 0) && ((((uintptr_t)dh) & 7) == 0) &&
+                   ((((uintptr_t)dl) & 7) == 0);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  if (vec) {
+    const long long n4 = HW >> 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(s) + i);
+      float f[4] = {fmaf(v.x, alpha, shift), fmaf(v.y, alpha, shift), fmaf(v.z, alpha, shift), fmaf(v.w, alpha, shift)};
+      __align__(8) bf16 h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) split_bf16(f[j], h[j], l[j]);
+      *reinterpret_cast<uint2*>(dh + 4 * i) = *reinterpret_cast<uint2*>(h);
+      *reinterpret_cast<uint2*>(dl + 4 * i) = *reinterpret_cast<uint2*>(l);
+    }
+  } else {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += stride) {
+      bf16 h, l;
+      split_bf16(fmaf(s[i], alpha, shift), h, l);
+      dh[i] = h;
+      dl[i] = l;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) split_pad_kernel(const float* __restrict__ src, long long rows, int cols,
+                                                            int cols_pad, bf16* __restrict__ dst, long long plane) {
+  const long long total = rows * cols_pad;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i / cols_pad;
+    int c = (int)(i % cols_pad);
+    float v = (c < cols) ? src[r * cols + c] : 0.f;
+    bf16 h, l;
+    split_bf16(v, h, l);
+    dst[i] = h;
+    dst[i + plane] = l;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) prep_dhconv_kernel(const float* __restrict__ w, int Cin, int Cout, int L,
+                                                              bf16* __restrict__ dst, long long plane) {
+  // dst[l][ro*Cout + o][ri*Cin + i]
+  const long long total = (long long)L * 2 * Cout * 2 * Cin;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    int col = (int)(idx % (2 * Cin));
+    long long t = idx / (2 * Cin);
+    int row = (int)(t % (2 * Cout));
+    int l = (int)(t / (2 * Cout));
+    int ri = col / Cin, i = col % Cin, ro = row / Cout, o = row % Cout;
+    const float* p = w + (((long long)i * Cout + o) * L + l) * 2;
+    float wr = p[0], wi = p[1];
+    float v = (ro == ri) ? wr : (ro == 0 ? -wi : wi);
+    bf16 h, lo;
+    split_bf16(v, h, lo);
+    dst[idx] = h;
+    dst[idx + plane] = lo;
+  }
+}
+
+// one thread per (b, l, m, o); x is broadcast across the o threads of a warp
+__global__ void __launch_bounds__(kThreads) diagonal_contract_kernel(const bf16* __restrict__ c1, long long c1_plane,
+                                                                    const float* __restrict__ w, int B, int C, int L,
+                                                                    int M, int Lp, bf16* __restrict__ c2,
+                                                                    long long c2_plane) {
+  const long long total = (long long)B * L * M * C;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    int o = (int)(idx % C);
+    long long t = idx / C;
+    int m = (int)(t % M);
+    t /= M;
+    int l = (int)(t % L);
+    int b = (int)(t / L);
+    const bf16* x = c1 + (((long long)b * L + l) * M + m) * 2 * C;
+    float yr = 0.f, yi = 0.f;
+    for (int i = 0; i < C; ++i) {
+      float xr = __bfloat162float(x[i]) + __bfloat162float(x[i + c1_plane]);
+      float xi = __bfloat162float(x[C + i]) + __bfloat162float(x[C + i + c1_plane]);
+      const float* p = w + ((((long long)i * C + o) * L + l) * M + m) * 2;
+      float wr = p[0], wi = p[1];
+      yr = fmaf(xr, wr, fmaf(-xi, wi, yr));
+      yi = fmaf(xr, wi, fmaf(xi, wr, yi));
+    }
+    bf16* y = c2 + (((long long)b * M + m) * Lp + l) * 2 * C;
+    bf16 h, lo;
+    split_bf16(yr, h, lo);
+    y[o] = h;
+    y[o + c2_plane] = lo;
+    split_bf16(yi, h, lo);
+    y[C + o] = h;
+    y[C + o + c2_plane] = lo;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) spec_planes_to_complex_kernel(const bf16* __restrict__ c1, long long plane,
+                                                                         int C, int L, int M, float* __restrict__ out) {
+  // out[c][l][m][2]; consecutive threads walk c (coalesced plane reads); writes are strided but the
+  // standalone transform API is not on the network hot path.
+  const long long total = (long long)L * M * C;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(idx % C);
+    long long lm = idx / C;
+    const bf16* p = c1 + lm * 2 * C;
+    float re = __bfloat162float(p[c]) + __bfloat162float(p[c + plane]);
+    float im = __bfloat162float(p[C + c]) + __bfloat162float(p[C + c + plane]);
+    float2* o = reinterpret_cast<float2*>(out) + (long long)c * L * M + lm;
+    *o = make_float2(re, im);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) spec_complex_to_planes_kernel(const float* __restrict__ in, int C, int L,
+                                                                         int M, int Lp, bf16* __restrict__ c2,
+                                                                         long long plane) {
+  const long long total = (long long)M * L * C;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(idx % C);
+    long long t = idx / C;
+    int l = (int)(t % L);
+    int m = (int)(t / L);
+    float2 v = reinterpret_cast<const float2*>(in)[((long long)c * L + l) * M + m];
+    bf16* y = c2 + ((long long)m * Lp + l) * 2 * C;
+    bf16 h, lo;
+    split_bf16(v.x, h, lo);
+    y[c] = h;
+    y[c + plane] = lo;
+    split_bf16(v.y, h, lo);
+    y[C + c] = h;
+    y[C + c + plane] = lo;
+  }
+}
+
+__global__ void vec_add_kernel(const float* a, const float* b, float* out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = a[i] + b[i];
+}
+
+__global__ void __launch_bounds__(kThreads) pack_normalize_kernel(const float* __restrict__ prog,
+                                                                 const float* __restrict__ forcing, int n_prog,
+                                                                 int n_forcing, const int* __restrict__ kind,
+                                                                 const int* __restrict__ index,
+                                                                 const float* __restrict__ mean,
+                                                                 const float* __restrict__ std, int n_in, long long HW,
+                                                                 float* __restrict__ x) {
+  const int bc = blockIdx.y;
+  const int b = bc / n_in, c = bc % n_in;
+  const float* s = (kind[c] == 0) ? prog + ((long long)b * n_prog + index[c]) * HW
+                                  : forcing + ((long long)b * n_forcing + index[c]) * HW;
+  float* d = x + (long long)bc * HW;
+  const float mu = mean[c], sd = std[c];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x)
+    d[i] = (s[i] - mu) / sd;
+}
+
+__global__ void __launch_bounds__(kThreads) unpack_denormalize_kernel(const float* __restrict__ y,
+                                                                     const float* __restrict__ x_norm,
+                                                                     const int* __restrict__ out_prog_index,
+                                                                     const int* __restrict__ prog_in_chan,
+                                                                     const float* __restrict__ mean,
+                                                                     const float* __restrict__ std, int residual,
+                                                                     int n_out, int n_in, int n_prog, long long HW,
+                                                                     float* __restrict__ out,
+                                                                     float* __restrict__ next_prog) {
+  const int bc = blockIdx.y;
+  const int b = bc / n_out, c = bc % n_out;
+  const int p = out_prog_index[c];
+  const float* s = y + (long long)bc * HW;
+  const float* r = nullptr;
+  if (residual && p >= 0 && prog_in_chan[p] >= 0) r = x_norm + ((long long)b * n_in + prog_in_chan[p]) * HW;
+  float* d = out + (long long)bc * HW;
+  float* np = (p >= 0 && next_prog != nullptr) ? next_prog + ((long long)b * n_prog + p) * HW : nullptr;
+  const float mu = mean[c], sd = std[c];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
+    float v = s[i];
+    if (r) v += r[i];
+    v = v * sd + mu;
+    d[i] = v;
+    if (np) np[i] = v;
+  }
+}
+
+}  // namespace
+
+void launch_norm_split(const float* src, int B, int C, long long HW, const double* stats, const float* gamma,
+                       const float* beta, float eps, bf16* dst, long long plane, long long dst_b, long long dst_c,
+                       cudaStream_t stream) {
+  ProfileScope prof("norm_split", stream);
+  ACE_REQUIRE((long long)B * C <= 65535, "norm_split: B*C = %lld exceeds grid.y", (long long)B * C);
+  int gx = grid_for((HW + 3) / 4, kThreads, 32);
+  dim3 grid(gx, B * C);
+  norm_split_kernel<<<grid, kThreads, 0, stream>>>(src, C, HW, stats, gamma, beta, eps, dst, plane, dst_b, dst_c);
+  after_launch("norm_split");
+}
+
+void launch_split_pad(const float* src, long long rows, int cols, int cols_pad, bf16* dst, long long plane,
+                      cudaStream_t stream) {
+  ProfileScope prof("split_pad", stream);
+  split_pad_kernel<<<grid_for(rows * cols_pad, kThreads), kThreads, 0, stream>>>(src, rows, cols, cols_pad, dst, plane);
+  after_launch("split_pad");
+}
+
+void launch_prep_dhconv(const float* w, int Cin, int Cout, int L, bf16* dst, long long plane, cudaStream_t stream) {
+  ProfileScope prof("prep_dhconv", stream);
+  prep_dhconv_kernel<<<grid_for((long long)L * 4 * Cin * Cout, kThreads), kThreads, 0, stream>>>(w, Cin, Cout, L, dst, plane);
+  after_launch("prep_dhconv");
+}
+
+void launch_diagonal_contract(const bf16* c1, long long c1_plane, const float* w, int B, int C, int L, int M, int Lp,
+                              bf16* c2, long long c2_plane, cudaStream_t stream) {
+  ProfileScope prof("diagonal_contract", stream);
+  diagonal_contract_kernel<<<grid_for((long long)B * L * M * C, kThreads), kThreads, 0, stream>>>(c1, c1_plane, w, B, C, L, M, Lp, c2, c2_plane);
+  after_launch("diagonal_contract");
+}
+
+void launch_spec_planes_to_complex(const bf16* c1, long long plane, int C, int L, int M, float* out, cudaStream_t stream) {
+  ProfileScope prof("spec_planes_to_complex", stream);
+  spec_planes_to_complex_kernel<<<grid_for((long long)L * M * C, kThreads), kThreads, 0, stream>>>(c1, plane, C, L, M, out);
+  after_launch("spec_planes_to_complex");
+}
+
+void launch_spec_complex_to_planes(const float* in, int C, int L, int M, int Lp, bf16* c2, long long plane, cudaStream_t stream) {
+  ProfileScope prof("spec_complex_to_planes", stream);
+  spec_complex_to_planes_kernel<<<grid_for((long long)L * M * C, kThreads), kThreads, 0, stream>>>(in, C, L, M, Lp, c2, plane);
+  after_launch("spec_complex_to_planes");
+}
+
+void launch_vec_add(const float* a, const float* b, float* out, long long n, cudaStream_t stream) {
+  ProfileScope prof("vec_add", stream);
+  vec_add_kernel<<<grid_for(n, kThreads), kThreads, 0, stream>>>(a, b, out, n);
+  after_launch("vec_add");
+}
+
+void launch_pack_normalize(const float* prog, const float* forcing, int n_prog, int n_forcing, const int* kind,
+                           const int* index, const float* mean, const float* std, int B, int n_in, long long HW,
+                           float* x, cudaStream_t stream) {
+  ProfileScope prof("pack_normalize", stream);
+  dim3 grid(grid_for(HW, kThreads, 64), B * n_in);
+  pack_normalize_kernel<<<grid, kThreads, 0, stream>>>(prog, forcing, n_prog, n_forcing, kind, index, mean, std, n_in, HW, x);
+  after_launch("pack_normalize");
+}
+
+void launch_unpack_denormalize(const float* y, const float* x_norm, const int* out_prog_index, const int* prog_in_chan,
+                               const float* mean, const float* std, int residual, int B, int n_out, int n_in,
+                               int n_prog, long long HW, float* out, float* next_prog, cudaStream_t stream) {
+  ProfileScope prof("unpack_denormalize", stream);
+  dim3 grid(grid_for(HW, kThreads, 64), B * n_out);
+  unpack_denormalize_kernel<<<grid, kThreads, 0, stream>>>(y, x_norm, out_prog_index, prog_in_chan, mean, std, residual, n_out, n_in, n_prog, HW, out, next_prog);
+  after_launch("unpack_denormalize");
+}
+
+}  // namespace ace

@@ -1,0 +1,116 @@
+// GemmOp: the one descriptor every GEMM-shaped piece of the hot path is expressed in.
+//
+//   for z2 in [0,Z2), z1 in [0,Z1):
+//     D[m][n] = sum_{k in [k_lo, K)} A_z[m][k] * B_z[n][k]      m in [0,M), n in [n_lo, n_hi)
+//     epilogue(D[m][n]) -> bias / addend / residual / GELU / per-column statistics / stores
+//
+// Operands live in HBM as "split-bf16 planes": two bf16 arrays (hi at `ptr`, lo at
+// `ptr + plane`), value = hi + lo.  Strides are in elements.  A may be K-major
+// (s_k == 1) or MN-major (s_row == 1); B is always K-major.  Both kernels
+// (gemm_simt.cu: generic SIMT; gemm_umma.cu: TMA + tcgen05) implement exactly this
+// contract, so either can serve any op the other can (the tcgen05 one additionally
+// needs 16-byte aligned strides).
+//
+// Triangular structure of the Legendre / dhconv stages is expressed through z1:
+//   n_lo_z1: n_lo = z1      (forward Legendre: only degrees l >= m are non-zero)
+//   n_hi_z1: n_hi = z1 + 1  (dhconv at degree l: only orders m <= l are non-zero)
+//   k_lo_z1: k_lo = z1      (inverse Legendre: sum over l >= m)
+// Buffers written under these restrictions are zero-initialised once and the
+// excluded region only ever receives exact zeros, so tile-granular kernels may
+// read or write the excluded part freely.
+#pragma once
+#include "common.cuh"
+
+namespace ace {
+
+struct Operand {
+  const bf16* ptr;     // hi plane
+  long long plane;     // lo plane = ptr + plane
+  long long s_row;     // stride of m (A) / n (B)
+  long long s_k;       // stride of k
+  long long s_z1, s_z2;
+};
+
+enum EpiFlags : uint32_t {
+  EPI_COL_BIAS = 1u << 0,    // v += col_bias[z2*cb_z2 + n]
+  EPI_ADD_F32 = 1u << 1,     // v += add[z2*add_z2 + m1*add_m1 + m0*add_m0 + n*add_n]
+  EPI_RES_PLANES = 1u << 2,  // v += (res_hi + res_lo)[z2*res_z2 + m1*res_m1 + m0*res_m0 + n*res_n]
+  EPI_GELU = 1u << 3,        // v = gelu_erf(v)
+  EPI_STATS = 1u << 4,       // stats[(z2*stats_z2 + n)*2 + {0,1}] += {v, v*v}   (double atomics)
+  EPI_OUT_PLANES = 1u << 5,  // split-bf16 store
+  EPI_OUT_F32 = 1u << 6,     // fp32 store
+};
+
+// Row index m is decomposed as m1 = m / mdiv, m0 = m % mdiv so that flattened
+// (channel, latitude) rows can be scattered into padded layouts.
+struct EpiParams {
+  uint32_t flags;
+  int mdiv;
+  const float* col_bias;
+  long long cb_z2;
+  const float* add;
+  long long add_z2, add_m1, add_m0, add_n;
+  const bf16* res;
+  long long res_plane, res_z2, res_m1, res_m0, res_n;
+  double* stats;
+  long long stats_z2;
+  bf16* out;
+  long long out_plane, o_z1, o_z2, o_m1, o_m0, o_n;
+  float* outf;
+  long long f_z1, f_z2, f_m1, f_m0, f_n;
+};
+
+struct GemmOp {
+  int M, N, K;
+  int Z1, Z2;
+  Operand A, B;
+  int n_lo_z1, n_hi_z1, k_lo_z1;
+  EpiParams epi;
+  const char* name;  // for error messages / profiling
+};
+
+inline GemmOp make_gemm_op(const char* name) {
+  GemmOp op;
+  memset(&op, 0, sizeof(op));
+  op.Z1 = op.Z2 = 1;
+  op.epi.mdiv = 1 << 30;
+  op.name = name;
+  return op;
+}
+
+#ifdef __CUDACC__
+// Epilogue value: everything up to (and including) GELU.  Shared by both kernels.
+__device__ __forceinline__ float epi_value(const EpiParams& e, float acc, int m1, int m0, int n, int z2) {
+  float v = acc;
+  if (e.flags & EPI_COL_BIAS) v += __ldg(e.col_bias + (long long)z2 * e.cb_z2 + n);
+  if (e.flags & EPI_ADD_F32) v += __ldg(e.add + (long long)z2 * e.add_z2 + (long long)m1 * e.add_m1 + (long long)m0 * e.add_m0 + (long long)n * e.add_n);
+  if (e.flags & EPI_RES_PLANES) {
+    const bf16* r = e.res + (long long)z2 * e.res_z2 + (long long)m1 * e.res_m1 + (long long)m0 * e.res_m0 + (long long)n * e.res_n;
+    v += __bfloat162float(r[0]) + __bfloat162float(r[e.res_plane]);
+  }
+  if (e.flags & EPI_GELU) v = gelu_erf(v);
+  return v;
+}
+
+__device__ __forceinline__ void epi_store(const EpiParams& e, float v, int m1, int m0, int n, int z1, int z2) {
+  if (e.flags & EPI_OUT_PLANES) {
+    bf16 hi, lo;
+    split_bf16(v, hi, lo);
+    bf16* o = e.out + (long long)z1 * e.o_z1 + (long long)z2 * e.o_z2 + (long long)m1 * e.o_m1 + (long long)m0 * e.o_m0 + (long long)n * e.o_n;
+    o[0] = hi;
+    o[e.out_plane] = lo;
+  }
+  if (e.flags & EPI_OUT_F32) {
+    e.outf[(long long)z1 * e.f_z1 + (long long)z2 * e.f_z2 + (long long)m1 * e.f_m1 + (long long)m0 * e.f_m0 + (long long)n * e.f_n] = v;
+  }
+}
+#endif
+
+// Dispatcher: tcgen05 kernel when the op is eligible (and not overridden), SIMT kernel otherwise.
+void run_gemm(const GemmOp& op, cudaStream_t stream);
+void run_gemm_simt(const GemmOp& op, cudaStream_t stream);
+// returns false (with reason) if the op cannot run on the tcgen05 kernel
+bool umma_eligible(const GemmOp& op, const char** why);
+void run_gemm_umma(const GemmOp& op, cudaStream_t stream);
+
+}  // namespace ace

@@ -1,0 +1,443 @@
+// SphericalFourierNeuralOperatorNet forward (ace_sfno_*): parameter re-layout + kernel orchestration.
+//
+// Mirrors /root/reference/fme/ace/models/modulus/sfnonet.py:713-749 (net), :217-252 (block),
+// s2convolutions.py:162-197 (spectral conv) as a fixed sequence of GemmOps and streaming kernels.
+// Per block (C = embed_dim, HW = nlat*nlon):
+//
+//   h (fp32) --norm0+split--> xn --G1 DFT--> X1 --G2 Legendre--> c1 --G3 dhconv--> c2 --G4 Legendre-->
+//   g --G5 iDFT--> T (fp32) ; T <- GELU(T + Wskip xn + bskip + bfilter) [stats1] --norm1+split--> yn
+//   --fc1+GELU--> hmid --fc2 + bias + xn--> h (fp32) [stats0 of the next block]
+//
+// InstanceNorm statistics are accumulated by the epilogue of the GEMM that produces the tensor
+// (double atomics per (sample, channel)); the normalisation itself is applied in fp32 by the
+// norm+split pass so that the bf16 split never sees un-centred data.
+#include <map>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "sht.cuh"
+
+using namespace ace;
+
+namespace {
+
+struct ConvW {
+  DevBuf w;  // planes [O][Ip]
+  long long plane = 0;
+  int O = 0, I = 0, Ip = 0;
+  DevBuf bias;  // fp32 [O]
+  bool has_bias = false;
+  void init(int o, int i, bool b) {
+    O = o;
+    I = i;
+    Ip = (int)round_up(i, 8);
+    plane = (long long)O * Ip;
+    w.ensure(2 * (size_t)plane * sizeof(bf16));
+    has_bias = b;
+    if (b) bias.ensure((size_t)O * sizeof(float));
+  }
+};
+
+struct BlockW {
+  DevBuf g0, b0, g1, b1;  // InstanceNorm affine
+  DevBuf spec;            // dhconv: planes [L][2C][2C]; diagonal: fp32 [C][C][L][M][2]
+  long long spec_plane = 0;
+  DevBuf fbias;           // spectral conv bias [C]
+  DevBuf skip_total;      // inner_skip.bias + fbias
+  ConvW skip, fc1, fc2;
+};
+
+}  // namespace
+
+struct ace_sfno {
+  ace_sfno_config cfg;
+  ace_sht_plan* outer;
+  ace_sht_plan* inner;
+  long long HW;
+  int Ctot;  // channels of the concat buffer: embed_dim + in_chans
+  ConvW enc0, enc1, dec0, dec1;
+  DevBuf pos;  // fp32 [C][HW]
+  std::vector<BlockW> blocks;
+  std::map<std::string, bool> params;  // name -> set?
+  bool finalized = false;
+
+  // workspace (allocated on first use for a batch size; grows monotonically)
+  int wsB = 0;
+  DevBuf hcat, e1, h, xn, x1, c1, c2, g, T, yn, hmid, d1, stats;
+  long long p_hcat, p_act, p_x1, p_c1, p_c2, p_g, p_hmid;  // plane offsets (elements)
+};
+
+namespace {
+
+void declare_params(ace_sfno& n) {
+  auto& p = n.params;
+  const ace_sfno_config& c = n.cfg;
+  if (c.pos_embed) p["pos_embed"] = false;
+  p["encoder.0.weight"] = p["encoder.0.bias"] = p["encoder.2.weight"] = false;
+  for (int i = 0; i < c.num_layers; ++i) {
+    std::string b = "blocks." + std::to_string(i) + ".";
+    if (c.normalization == 1) p[b + "norm0.weight"] = p[b + "norm0.bias"] = p[b + "norm1.weight"] = p[b + "norm1.bias"] = false;
+    p[b + "filter.filter.weight"] = p[b + "filter.filter.bias"] = false;
+    p[b + "inner_skip.weight"] = p[b + "inner_skip.bias"] = false;
+    p[b + "mlp.fwd.0.weight"] = p[b + "mlp.fwd.0.bias"] = p[b + "mlp.fwd.2.weight"] = p[b + "mlp.fwd.2.bias"] = false;
+  }
+  p["decoder.0.weight"] = p["decoder.0.bias"] = p["decoder.2.weight"] = false;
+}
+
+void copy_f32(DevBuf& dst, const float* src, long long n, cudaStream_t s) {
+  dst.ensure((size_t)n * sizeof(float));
+  ACE_CHECK_CUDA(cudaMemcpyAsync(dst.p, src, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+}
+
+void set_conv_w(ConvW& w, const float* src, long long numel, const char* name, cudaStream_t s) {
+  ACE_REQUIRE(numel == (long long)w.O * w.I, "%s: expected %lld elements, got %lld", name, (long long)w.O * w.I, numel);
+  launch_split_pad(src, w.O, w.I, w.Ip, w.w.as<bf16>(), w.plane, s);
+}
+void set_conv_b(ConvW& w, const float* src, long long numel, const char* name, cudaStream_t s) {
+  ACE_REQUIRE(w.has_bias && numel == w.O, "%s: expected %d elements, got %lld", name, w.O, numel);
+  copy_f32(w.bias, src, numel, s);
+}
+
+void ensure_ws(ace_sfno& n, int B) {
+  if (B <= n.wsB) return;
+  const ace_sfno_config& c = n.cfg;
+  const int C = c.embed_dim;
+  const long long HW = n.HW;
+  const ace_sht_plan& p = *n.inner;  // outer has identical L, M, K, W -> identical layouts
+  n.p_hcat = (long long)B * n.Ctot * HW;
+  n.p_act = (long long)B * C * HW;
+  n.p_x1 = B * p.x1_elems(C);
+  n.p_c1 = B * p.c1_elems(C);
+  n.p_c2 = B * p.c2_elems(C);
+  n.p_g = B * p.g_elems(C);
+  n.p_hmid = (long long)B * c.mlp_hidden * HW;
+  const size_t e = sizeof(bf16);
+  n.hcat.ensure(2 * (size_t)n.p_hcat * e);
+  n.e1.ensure(2 * (size_t)n.p_act * e);
+  n.h.ensure((size_t)n.p_act * sizeof(float));
+  n.xn.ensure(2 * (size_t)n.p_act * e);
+  n.x1.ensure(2 * (size_t)n.p_x1 * e);
+  n.c1.ensure(2 * (size_t)n.p_c1 * e);
+  n.c2.ensure(2 * (size_t)n.p_c2 * e);
+  n.g.ensure(2 * (size_t)n.p_g * e);
+  n.T.ensure((size_t)n.p_act * sizeof(float));
+  n.yn.ensure(2 * (size_t)n.p_act * e);
+  n.hmid.ensure(2 * (size_t)n.p_hmid * e);
+  n.d1.ensure(2 * (size_t)n.p_act * e);
+  n.stats.ensure((size_t)2 * c.num_layers * B * C * 2 * sizeof(double));
+  n.wsB = B;
+}
+
+// 1x1 convolution as a GEMM over flattened space: D[hw][o] = sum_i x[i][hw] * W[o][i]
+GemmOp conv_op(const char* name, const bf16* x, long long x_plane, long long x_batch_stride, long long HW, int B,
+               const ConvW& w, int k_channels) {
+  GemmOp op = make_gemm_op(name);
+  op.M = (int)HW;
+  op.N = w.O;
+  op.K = k_channels;
+  op.Z2 = B;
+  op.A = {x, x_plane, 1, HW, 0, x_batch_stride};  // MN-major: space contiguous, channel stride HW
+  op.B = {w.w.as<bf16>(), w.plane, (long long)w.Ip, 1, 0, 0};
+  if (w.has_bias) {
+    op.epi.flags |= EPI_COL_BIAS;
+    op.epi.col_bias = w.bias.as<float>();
+  }
+  return op;
+}
+
+void out_planes(GemmOp& op, bf16* out, long long plane, long long batch_stride, long long HW) {
+  op.epi.flags |= EPI_OUT_PLANES;
+  op.epi.out = out;
+  op.epi.out_plane = plane;
+  op.epi.o_z2 = batch_stride;
+  op.epi.o_n = HW;
+  op.epi.o_m0 = 1;
+}
+void out_f32(GemmOp& op, float* out, long long batch_stride, long long HW) {
+  op.epi.flags |= EPI_OUT_F32;
+  op.epi.outf = out;
+  op.epi.f_z2 = batch_stride;
+  op.epi.f_n = HW;
+  op.epi.f_m0 = 1;
+}
+
+void forward(ace_sfno& n, const float* x, float* y, int B, cudaStream_t s) {
+  const ace_sfno_config& c = n.cfg;
+  const int C = c.embed_dim, Cin = c.in_chans, NL = c.num_layers;
+  const long long HW = n.HW;
+  const bool inorm = c.normalization == 1;
+  ensure_ws(n, B);
+  // plane offsets are those of the allocated capacity; per-sample strides do not depend on it
+  bf16* hcat = n.hcat.as<bf16>();
+  const long long P_hcat = n.p_hcat, P_act = n.p_act, P_x1 = n.p_x1, P_c1 = n.p_c1, P_c2 = n.p_c2, P_g = n.p_g,
+                  P_hmid = n.p_hmid;
+  const long long act_b = (long long)C * HW, cat_b = (long long)n.Ctot * HW;
+  double* stats = n.stats.as<double>();
+  const long long stats_per = (long long)B * C * 2;
+  if (inorm) ACE_CHECK_CUDA(cudaMemsetAsync(stats, 0, (size_t)2 * NL * stats_per * sizeof(double), s));
+
+  // network input -> split planes, stored in the tail channels of the concat buffer (zero-copy big skip)
+  launch_norm_split(x, B, Cin, HW, nullptr, nullptr, nullptr, 0.f, hcat + (long long)C * HW, P_hcat, cat_b, HW, s);
+
+  // encoder: Conv(Cin->C)+bias, GELU, Conv(C->C) ; + pos_embed          (sfnonet.py:566-577, :733)
+  {
+    GemmOp op = conv_op("encoder.0", hcat + (long long)C * HW, P_hcat, cat_b, HW, B, n.enc0, Cin);
+    op.epi.flags |= EPI_GELU;
+    out_planes(op, n.e1.as<bf16>(), P_act, act_b, HW);
+    run_gemm(op, s);
+  }
+  {
+    GemmOp op = conv_op("encoder.2", n.e1.as<bf16>(), P_act, act_b, HW, B, n.enc1, C);
+    if (c.pos_embed) {
+      op.epi.flags |= EPI_ADD_F32;
+      op.epi.add = n.pos.as<float>();
+      op.epi.add_z2 = 0;
+      op.epi.add_n = HW;
+      op.epi.add_m0 = 1;
+    }
+    out_f32(op, n.h.as<float>(), act_b, HW);
+    if (inorm) {
+      op.epi.flags |= EPI_STATS;
+      op.epi.stats = stats;
+      op.epi.stats_z2 = C;
+    }
+    run_gemm(op, s);
+  }
+
+  for (int i = 0; i < NL; ++i) {
+    BlockW& w = n.blocks[i];
+    const ace_sht_plan& pf = (i == 0) ? *n.outer : *n.inner;
+    const ace_sht_plan& pi = (i == NL - 1) ? *n.outer : *n.inner;
+    double* st0 = stats + (long long)(2 * i) * stats_per;
+    double* st1 = stats + (long long)(2 * i + 1) * stats_per;
+    bf16* xn = n.xn.as<bf16>();
+
+    // norm0 (sfnonet.py:218-221)
+    launch_norm_split(n.h.as<float>(), B, C, HW, inorm ? st0 : nullptr, w.g0.as<float>(), w.b0.as<float>(), c.norm_eps,
+                      xn, P_act, act_b, HW, s);
+    // spectral convolution (s2convolutions.py:162-197)
+    run_gemm(sht_op_dft_fwd(pf, xn, P_act, act_b, C, B, n.x1.as<bf16>(), P_x1), s);
+    run_gemm(sht_op_legendre_fwd(pf, n.x1.as<bf16>(), P_x1, C, B, n.c1.as<bf16>(), P_c1), s);
+    if (c.operator_type == 1) {
+      GemmOp op = make_gemm_op("dhconv");
+      op.M = 2 * C;
+      op.N = pf.M;
+      op.K = 2 * C;
+      op.Z1 = pf.L;
+      op.Z2 = B;
+      op.A = {w.spec.as<bf16>(), w.spec_plane, 2LL * C, 1, 4LL * C * C, 0};
+      op.B = {n.c1.as<bf16>(), P_c1, 2LL * C, 1, (long long)pf.M * 2 * C, pf.c1_elems(C)};
+      op.n_hi_z1 = 1;  // order m <= degree l
+      op.epi.flags = EPI_OUT_PLANES;
+      op.epi.out = n.c2.as<bf16>();
+      op.epi.out_plane = P_c2;
+      op.epi.o_z2 = pf.c2_elems(C);
+      op.epi.o_n = (long long)pf.Lp * 2 * C;
+      op.epi.o_z1 = 2LL * C;
+      op.epi.o_m0 = 1;
+      run_gemm(op, s);
+    } else {
+      launch_diagonal_contract(n.c1.as<bf16>(), P_c1, w.spec.as<float>(), B, C, pf.L, pf.M, pf.Lp, n.c2.as<bf16>(), P_c2, s);
+    }
+    run_gemm(sht_op_legendre_inv(pi, n.c2.as<bf16>(), P_c2, C, B, n.g.as<bf16>(), P_g), s);
+    run_gemm(sht_op_dft_inv(pi, n.g.as<bf16>(), P_g, C, B, n.T.as<float>(), act_b), s);
+
+    // x = GELU(filter(x_norm) + bias_f + inner_skip(x_norm)) (sfnonet.py:223-232), in place on T
+    {
+      GemmOp op = conv_op("inner_skip", xn, P_act, act_b, HW, B, w.skip, C);
+      op.epi.col_bias = w.skip_total.as<float>();
+      op.epi.flags |= EPI_ADD_F32 | EPI_GELU;
+      op.epi.add = n.T.as<float>();
+      op.epi.add_z2 = act_b;
+      op.epi.add_n = HW;
+      op.epi.add_m0 = 1;
+      out_f32(op, n.T.as<float>(), act_b, HW);
+      if (inorm) {
+        op.epi.flags |= EPI_STATS;
+        op.epi.stats = st1;
+        op.epi.stats_z2 = C;
+      }
+      run_gemm(op, s);
+    }
+    // norm1 (sfnonet.py:234-238)
+    launch_norm_split(n.T.as<float>(), B, C, HW, inorm ? st1 : nullptr, w.g1.as<float>(), w.b1.as<float>(), c.norm_eps,
+                      n.yn.as<bf16>(), P_act, act_b, HW, s);
+    // MLP (layers.py:117-124) + outer skip (identity) with residual = x_norm (sfnonet.py:249-250)
+    {
+      GemmOp op = conv_op("mlp.fc1", n.yn.as<bf16>(), P_act, act_b, HW, B, w.fc1, C);
+      op.epi.flags |= EPI_GELU;
+      out_planes(op, n.hmid.as<bf16>(), P_hmid, (long long)c.mlp_hidden * HW, HW);
+      run_gemm(op, s);
+    }
+    {
+      GemmOp op = conv_op("mlp.fc2", n.hmid.as<bf16>(), P_hmid, (long long)c.mlp_hidden * HW, HW, B, w.fc2, c.mlp_hidden);
+      op.epi.flags |= EPI_RES_PLANES;
+      op.epi.res = xn;
+      op.epi.res_plane = P_act;
+      op.epi.res_z2 = act_b;
+      op.epi.res_n = HW;
+      op.epi.res_m0 = 1;
+      if (i == NL - 1) {
+        out_planes(op, hcat, P_hcat, cat_b, HW);  // head channels of the concat buffer
+      } else {
+        out_f32(op, n.h.as<float>(), act_b, HW);
+        if (inorm) {
+          op.epi.flags |= EPI_STATS;
+          op.epi.stats = stats + (long long)(2 * i + 2) * stats_per;
+          op.epi.stats_z2 = C;
+        }
+      }
+      run_gemm(op, s);
+    }
+  }
+
+  // decoder on cat(x, input) (sfnonet.py:741-747)
+  {
+    GemmOp op = conv_op("decoder.0", hcat, P_hcat, cat_b, HW, B, n.dec0, c.big_skip ? n.Ctot : C);
+    op.epi.flags |= EPI_GELU;
+    out_planes(op, n.d1.as<bf16>(), P_act, act_b, HW);
+    run_gemm(op, s);
+  }
+  {
+    GemmOp op = conv_op("decoder.2", n.d1.as<bf16>(), P_act, act_b, HW, B, n.dec1, C);
+    out_f32(op, y, (long long)c.out_chans * HW, HW);
+    run_gemm(op, s);
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------ C ABI
+
+extern "C" int ace_sfno_create(const ace_sfno_config* cfg, ace_sht_plan* plan_outer, ace_sht_plan* plan_inner, ace_sfno** out) {
+  ACE_API_BEGIN
+  ACE_REQUIRE(cfg && plan_outer && plan_inner && out, "ace_sfno_create: null argument");
+  const ace_sfno_config& c = *cfg;
+  ACE_REQUIRE(c.img_h > 0 && c.img_w > 0 && c.in_chans > 0 && c.out_chans > 0 && c.embed_dim > 0 && c.num_layers > 0,
+              "ace_sfno_create: non-positive size");
+  ACE_REQUIRE(c.operator_type == 0 || c.operator_type == 1, "ace_sfno_create: operator_type must be 0 (diagonal) or 1 (dhconv)");
+  ACE_REQUIRE(c.normalization == 0 || c.normalization == 1, "ace_sfno_create: normalization must be 0 (none) or 1 (instance_norm)");
+  ACE_REQUIRE(c.mlp_hidden > 0, "ace_sfno_create: use_mlp=False is not supported");
+  for (ace_sht_plan* p : {plan_outer, plan_inner})
+    ACE_REQUIRE(p->K == c.img_h && p->W == c.img_w && p->L == c.lmax && p->M == c.mmax,
+                "ace_sfno_create: plan (%d,%d,%d,%d) does not match config (%d,%d,%d,%d)", p->K, p->W, p->L, p->M, c.img_h,
+                c.img_w, c.lmax, c.mmax);
+  ace_sfno* n = new ace_sfno();
+  try {
+    n->cfg = c;
+    n->outer = plan_outer;
+    n->inner = plan_inner;
+    n->HW = (long long)c.img_h * c.img_w;
+    n->Ctot = c.embed_dim + c.in_chans;
+    const int C = c.embed_dim;
+    n->enc0.init(C, c.in_chans, true);
+    n->enc1.init(C, C, false);
+    n->dec0.init(C, c.big_skip ? n->Ctot : C, true);
+    n->dec1.init(c.out_chans, C, false);
+    n->blocks.resize(c.num_layers);
+    for (BlockW& b : n->blocks) {
+      b.skip.init(C, C, true);
+      b.fc1.init(c.mlp_hidden, C, true);
+      b.fc2.init(C, c.mlp_hidden, true);
+      b.fbias.ensure((size_t)C * sizeof(float));
+      b.skip_total.ensure((size_t)C * sizeof(float));
+    }
+    declare_params(*n);
+  } catch (...) {
+    delete n;
+    throw;
+  }
+  *out = n;
+  ACE_API_END
+}
+
+extern "C" void ace_sfno_destroy(ace_sfno* net) { delete net; }
+
+extern "C" int ace_sfno_query(ace_sfno* net, int* in_chans, int* out_chans, long long* hw) {
+  ACE_API_BEGIN
+  ACE_REQUIRE(net && in_chans && out_chans && hw, "ace_sfno_query: null argument");
+  *in_chans = net->cfg.in_chans;
+  *out_chans = net->cfg.out_chans;
+  *hw = net->HW;
+  ACE_API_END
+}
+
+extern "C" int ace_sfno_set_param(ace_sfno* net, const char* name, const float* data_dev, long long numel, void* stream) {
+  ACE_API_BEGIN
+  ACE_REQUIRE(net && name && data_dev, "ace_sfno_set_param: null argument");
+  ace_sfno& n = *net;
+  cudaStream_t s = (cudaStream_t)stream;
+  const ace_sfno_config& c = n.cfg;
+  const int C = c.embed_dim;
+  std::string nm(name);
+  auto it = n.params.find(nm);
+  ACE_REQUIRE(it != n.params.end(), "ace_sfno_set_param: unexpected parameter '%s' for this configuration", name);
+  if (nm == "pos_embed") {
+    ACE_REQUIRE(numel == (long long)C * n.HW, "pos_embed: expected %lld elements, got %lld", (long long)C * n.HW, numel);
+    copy_f32(n.pos, data_dev, numel, s);
+  } else if (nm == "encoder.0.weight") set_conv_w(n.enc0, data_dev, numel, name, s);
+  else if (nm == "encoder.0.bias") set_conv_b(n.enc0, data_dev, numel, name, s);
+  else if (nm == "encoder.2.weight") set_conv_w(n.enc1, data_dev, numel, name, s);
+  else if (nm == "decoder.0.weight") set_conv_w(n.dec0, data_dev, numel, name, s);
+  else if (nm == "decoder.0.bias") set_conv_b(n.dec0, data_dev, numel, name, s);
+  else if (nm == "decoder.2.weight") set_conv_w(n.dec1, data_dev, numel, name, s);
+  else {
+    int bi = -1, consumed = 0;
+    ACE_REQUIRE(sscanf(name, "blocks.%d.%n", &bi, &consumed) == 1 && bi >= 0 && bi < c.num_layers, "bad block index in '%s'", name);
+    BlockW& b = n.blocks[bi];
+    std::string rest(name + consumed);
+    auto vecC = [&](DevBuf& d) {
+      ACE_REQUIRE(numel == C, "%s: expected %d elements, got %lld", name, C, numel);
+      copy_f32(d, data_dev, numel, s);
+    };
+    if (rest == "norm0.weight") vecC(b.g0);
+    else if (rest == "norm0.bias") vecC(b.b0);
+    else if (rest == "norm1.weight") vecC(b.g1);
+    else if (rest == "norm1.bias") vecC(b.b1);
+    else if (rest == "filter.filter.bias") vecC(b.fbias);
+    else if (rest == "filter.filter.weight") {
+      if (c.operator_type == 1) {
+        ACE_REQUIRE(numel == (long long)C * C * c.lmax * 2, "%s: expected %lld elements, got %lld", name, (long long)C * C * c.lmax * 2, numel);
+        b.spec_plane = (long long)c.lmax * 4 * C * C;
+        b.spec.ensure(2 * (size_t)b.spec_plane * sizeof(bf16));
+        launch_prep_dhconv(data_dev, C, C, c.lmax, b.spec.as<bf16>(), b.spec_plane, s);
+      } else {
+        ACE_REQUIRE(numel == (long long)C * C * c.lmax * c.mmax * 2, "%s: expected %lld elements, got %lld", name, (long long)C * C * c.lmax * c.mmax * 2, numel);
+        copy_f32(b.spec, data_dev, numel, s);
+      }
+    } else if (rest == "inner_skip.weight") set_conv_w(b.skip, data_dev, numel, name, s);
+    else if (rest == "inner_skip.bias") set_conv_b(b.skip, data_dev, numel, name, s);
+    else if (rest == "mlp.fwd.0.weight") set_conv_w(b.fc1, data_dev, numel, name, s);
+    else if (rest == "mlp.fwd.0.bias") set_conv_b(b.fc1, data_dev, numel, name, s);
+    else if (rest == "mlp.fwd.2.weight") set_conv_w(b.fc2, data_dev, numel, name, s);
+    else if (rest == "mlp.fwd.2.bias") set_conv_b(b.fc2, data_dev, numel, name, s);
+    else ACE_REQUIRE(false, "ace_sfno_set_param: unhandled parameter '%s'", name);
+    if (rest == "inner_skip.bias" || rest == "filter.filter.bias") {
+      std::string pre = "blocks." + std::to_string(bi) + ".";
+      bool other = n.params[pre + (rest == "inner_skip.bias" ? "filter.filter.bias" : "inner_skip.bias")];
+      if (other) launch_vec_add(b.skip.bias.as<float>(), b.fbias.as<float>(), b.skip_total.as<float>(), C, s);
+    }
+  }
+  it->second = true;
+  n.finalized = false;
+  ACE_API_END
+}
+
+extern "C" int ace_sfno_finalize(ace_sfno* net) {
+  ACE_API_BEGIN
+  ACE_REQUIRE(net, "ace_sfno_finalize: null argument");
+  for (auto& kv : net->params)
+    if (!kv.second) throw Error(ACE_ERR_STATE, "ace_sfno_finalize: parameter '" + kv.first + "' has not been set");
+  net->finalized = true;
+  ACE_API_END
+}
+
+extern "C" int ace_sfno_forward(ace_sfno* net, const float* x_dev, float* y_dev, int batch, void* stream) {
+  ACE_API_BEGIN
+  ACE_REQUIRE(net && x_dev && y_dev, "ace_sfno_forward: null argument");
+  ACE_REQUIRE(batch > 0, "ace_sfno_forward: batch must be positive");
+  if (!net->finalized) throw Error(ACE_ERR_STATE, "ace_sfno_forward: call ace_sfno_finalize first");
+  forward(*net, x_dev, y_dev, batch, (cudaStream_t)stream);
+  ACE_API_END
+}

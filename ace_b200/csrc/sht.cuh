@@ -1,0 +1,48 @@
+// Spherical harmonic transform plan: device tables + the four GemmOps a transform pair is made of.
+//
+//   forward  (fme/sht_fix.py:125-151):   x --G1: longitude DFT--> X1 --G2: Legendre/quadrature--> c1
+//   inverse  (fme/sht_fix.py:206-226):   c2 --G4: Legendre--> g --G5: inverse longitude DFT--> y
+//
+// Device layouts (split-bf16 planes unless noted; element counts per plane):
+//   x   [B][C][K][W]            grid-point fields (K = nlat, W = nlon)
+//   X1  [B][2M][C][Kp]          row n = 2m+reim of the DFT output, latitude contiguous (Kp = K padded to 8)
+//   c1  [B][L][M][2C]           forward coefficients, (reim, channel) contiguous
+//   c2  [B][M][Lp][2C]          inverse input (after the spectral operator), (reim, channel) contiguous
+//   g   [B][2M][C][K]           Legendre-synthesised Fourier coefficients, latitude contiguous
+//   y   fp32 [B][C][K][W]
+#pragma once
+#include "gemm.cuh"
+
+struct ace_sht_plan {
+  int K, W, L, M;      // nlat, nlon, lmax, mmax
+  int Kp, Lp, Wp, K2p; // padded strides (multiples of 8 elements = 16 bytes)
+  ace::DevBuf wt;       // planes [M][L][Kp]    P_l^m(cos th_k) w_k
+  ace::DevBuf pinv;     // planes [M][K][Lp]    P_l^m(cos th_k), l contiguous
+  ace::DevBuf fdft;     // planes [2M][Wp]      forward DFT rows (2pi/W)(cos, -sin)
+  ace::DevBuf idft;     // planes [W][K2p]      inverse DFT rows, Hermitian weights folded in
+  long long wt_plane, pinv_plane, fdft_plane, idft_plane;
+  // lazily grown workspace of the standalone transform API
+  ace::DevBuf ws_x, ws_x1, ws_c1, ws_c2, ws_g;
+  long long ws_fields = 0;         // capacity
+  long long ws_fields_layout = 0;  // field count the c1/c2 zero regions are currently valid for
+
+  long long x1_elems(int C) const { return 2LL * M * C * Kp; }
+  long long c1_elems(int C) const { return (long long)L * M * 2 * C; }
+  long long c2_elems(int C) const { return (long long)M * Lp * 2 * C; }
+  long long g_elems(int C) const { return 2LL * M * C * K; }
+};
+
+namespace ace {
+
+// All builders take per-plane element offsets (`*_plane`) and per-sample strides implied by the
+// layouts above with batch B folded as the outermost dimension.
+GemmOp sht_op_dft_fwd(const ace_sht_plan& p, const bf16* x, long long x_plane, long long x_batch_stride, int C, int B,
+                      bf16* x1, long long x1_plane);
+GemmOp sht_op_legendre_fwd(const ace_sht_plan& p, const bf16* x1, long long x1_plane, int C, int B, bf16* c1,
+                           long long c1_plane);
+GemmOp sht_op_legendre_inv(const ace_sht_plan& p, const bf16* c2, long long c2_plane, int C, int B, bf16* g,
+                           long long g_plane);
+GemmOp sht_op_dft_inv(const ace_sht_plan& p, const bf16* g, long long g_plane, int C, int B, float* y,
+                      long long y_batch_stride);
+
+}  // namespace ace

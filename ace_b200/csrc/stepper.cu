@@ -1,0 +1,97 @@
+// Fused single-module step (ace_stepper_*): the device work of
+// /root/reference/fme/core/step/single_module.py:595-665 with corrector/ocean disabled:
+//   normalise (normalizer.py:213-243) -> pack (packer.py:45-52) -> network -> unpack ->
+//   [+ normalised input for residual prediction] -> denormalise -> next prognostic state
+// in two streaming kernels around ace_sfno_forward instead of ~100 elementwise launches.
+#include <vector>
+
+#include "kernels.cuh"
+
+extern "C" int ace_sfno_forward(ace_sfno* net, const float* x_dev, float* y_dev, int batch, void* stream);
+
+struct ace_stepper {
+  ace_sfno* net;
+  int n_in, n_out, n_prog, n_forcing, residual;
+  long long HW;
+  ace::DevBuf in_kind, in_index, out_prog, prog_in_chan, in_mean, in_std, out_mean, out_std;
+  ace::DevBuf x, y;
+  int wsB = 0;
+};
+
+using namespace ace;
+
+// provided by sfno.cu
+extern "C" int ace_sfno_query(ace_sfno* net, int* in_chans, int* out_chans, long long* hw);
+
+template <class T>
+static void upload(DevBuf& d, const T* host, size_t n) {
+  d.ensure(n * sizeof(T));
+  ACE_CHECK_CUDA(cudaMemcpy(d.p, host, n * sizeof(T), cudaMemcpyHostToDevice));
+}
+
+extern "C" int ace_stepper_create(ace_sfno* net, const ace_step_config* cfg, ace_stepper** out) {
+  ACE_API_BEGIN
+  ACE_REQUIRE(net && cfg && out, "ace_stepper_create: null argument");
+  int cin = 0, cout = 0;
+  long long hw = 0;
+  ACE_REQUIRE(ace_sfno_query(net, &cin, &cout, &hw) == ACE_OK, "ace_stepper_create: bad net");
+  ACE_REQUIRE(cfg->n_in == cin && cfg->n_out == cout, "ace_stepper_create: net has %d->%d channels, step config %d->%d", cin,
+              cout, cfg->n_in, cfg->n_out);
+  ACE_REQUIRE(cfg->n_prog > 0 && cfg->n_forcing >= 0, "ace_stepper_create: bad state sizes");
+  std::vector<int> prog_in_chan(cfg->n_prog, -1);
+  for (int c = 0; c < cfg->n_in; ++c) {
+    int kind = cfg->in_kind_host[c], idx = cfg->in_index_host[c];
+    ACE_REQUIRE(kind == 0 || kind == 1, "in_kind[%d] must be 0 (prognostic) or 1 (forcing)", c);
+    ACE_REQUIRE(idx >= 0 && idx < (kind == 0 ? cfg->n_prog : cfg->n_forcing), "in_index[%d]=%d out of range", c, idx);
+    ACE_REQUIRE(cfg->in_std_host[c] != 0.f, "in_std[%d] is zero", c);
+    if (kind == 0) prog_in_chan[idx] = c;
+  }
+  for (int c = 0; c < cfg->n_out; ++c)
+    ACE_REQUIRE(cfg->out_prog_index_host[c] >= -1 && cfg->out_prog_index_host[c] < cfg->n_prog, "out_prog_index[%d] out of range", c);
+  ace_stepper* st = new ace_stepper();
+  try {
+    st->net = net;
+    st->n_in = cfg->n_in;
+    st->n_out = cfg->n_out;
+    st->n_prog = cfg->n_prog;
+    st->n_forcing = cfg->n_forcing;
+    st->residual = cfg->residual_prediction;
+    st->HW = hw;
+    upload(st->in_kind, cfg->in_kind_host, cfg->n_in);
+    upload(st->in_index, cfg->in_index_host, cfg->n_in);
+    upload(st->out_prog, cfg->out_prog_index_host, cfg->n_out);
+    upload(st->prog_in_chan, prog_in_chan.data(), prog_in_chan.size());
+    upload(st->in_mean, cfg->in_mean_host, cfg->n_in);
+    upload(st->in_std, cfg->in_std_host, cfg->n_in);
+    upload(st->out_mean, cfg->out_mean_host, cfg->n_out);
+    upload(st->out_std, cfg->out_std_host, cfg->n_out);
+  } catch (...) {
+    delete st;
+    throw;
+  }
+  *out = st;
+  ACE_API_END
+}
+
+extern "C" void ace_stepper_destroy(ace_stepper* st) { delete st; }
+
+extern "C" int ace_stepper_step(ace_stepper* st, const float* prog_dev, const float* forcing_dev, float* out_dev,
+                                float* next_prog_dev, int batch, void* stream) {
+  ACE_API_BEGIN
+  ACE_REQUIRE(st && prog_dev && out_dev && batch > 0, "ace_stepper_step: bad argument");
+  ACE_REQUIRE(forcing_dev || st->n_forcing == 0, "ace_stepper_step: forcing is null");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (batch > st->wsB) {
+    st->x.ensure((size_t)batch * st->n_in * st->HW * sizeof(float));
+    st->y.ensure((size_t)batch * st->n_out * st->HW * sizeof(float));
+    st->wsB = batch;
+  }
+  launch_pack_normalize(prog_dev, forcing_dev, st->n_prog, st->n_forcing, st->in_kind.as<int>(), st->in_index.as<int>(),
+                        st->in_mean.as<float>(), st->in_std.as<float>(), batch, st->n_in, st->HW, st->x.as<float>(), s);
+  int rc = ace_sfno_forward(st->net, st->x.as<float>(), st->y.as<float>(), batch, stream);
+  if (rc != ACE_OK) return rc;
+  launch_unpack_denormalize(st->y.as<float>(), st->x.as<float>(), st->out_prog.as<int>(), st->prog_in_chan.as<int>(),
+                            st->out_mean.as<float>(), st->out_std.as<float>(), st->residual, batch, st->n_out, st->n_in,
+                            st->n_prog, st->HW, out_dev, next_prog_dev, s);
+  ACE_API_END
+}

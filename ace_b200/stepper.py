@@ -1,0 +1,182 @@
+"""Fused single-module step + autoregressive rollout around the B200 SFNO.
+
+Device work mirrored (corrector / ocean / masking disabled, as in the throughput benchmark):
+
+* ``/root/reference/fme/core/step/single_module.py:595-665`` ``step_with_adjustments``:
+  ``normalizer.normalize`` -> ``in_packer.pack`` -> module -> ``out_packer.unpack`` ->
+  [``residual_prediction``: add normalised prognostic inputs] -> ``normalizer.denormalize``
+  (``fme/core/normalizer.py:213-243``: ``(x - mean) / std`` and ``x * std + mean`` per name,
+  ``fme/core/packer.py:45-52``: channel order = order of the name lists);
+* ``/root/reference/fme/ace/stepper/single_module.py:1124-1167`` ``predict_generator``: the state
+  fed to step t+1 is the prognostic subset of step t's output; forcing comes from the data.
+
+The reference spends ~330 small launches per step on this; here it is two streaming kernels
+around ``ace_sfno_forward`` (``ace_stepper_step`` in the C ABI), and ``rollout`` replays the
+whole step from a CUDA graph.
+"""
+import ctypes
+from typing import Dict, List, Mapping, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .sfno import SphericalFourierNeuralOperatorNet
+
+
+class FusedStepper:
+    def __init__(
+        self,
+        module: SphericalFourierNeuralOperatorNet,
+        in_names: Sequence[str],
+        out_names: Sequence[str],
+        means: Mapping[str, float],
+        stds: Mapping[str, float],
+        residual_prediction: bool = False,
+    ):
+        self.module = module
+        self.in_names: List[str] = list(in_names)
+        self.out_names: List[str] = list(out_names)
+        if len(self.in_names) != module.in_chans or len(self.out_names) != module.out_chans:
+            raise ValueError(
+                f"module has {module.in_chans}->{module.out_chans} channels, names give {len(self.in_names)}->{len(self.out_names)}"
+            )
+        # fme/core/step/single_module.py: prognostic = outputs that are also inputs; forcing = inputs only
+        self.prognostic_names = [n for n in self.out_names if n in self.in_names]
+        self.forcing_names = [n for n in self.in_names if n not in self.out_names]
+        self.diagnostic_names = [n for n in self.out_names if n not in self.in_names]
+        self.residual_prediction = bool(residual_prediction)
+        self._means = {k: float(v) for k, v in means.items()}
+        self._stds = {k: float(v) for k, v in stds.items()}
+        for n in set(self.in_names) | set(self.out_names):
+            if n not in self._means or n not in self._stds:
+                raise KeyError(f"normalization statistics missing for '{n}'")
+        self._handle = None
+        self._handle_net = None
+        self._graph = None
+        self._static = None
+
+    # ------------------------------------------------------------------ native object
+    def _ensure(self, device):
+        net = self.module.native_handle()
+        if self._handle is not None and self._handle_net is not None and net is not None and self._handle_net.value == net.value:
+            return
+        self._destroy()
+        if net is None:
+            # materialise the device net (uploads parameters) with a throw-away forward
+            with torch.no_grad():
+                self.module(torch.zeros(1, self.module.in_chans, *self.module.img_shape, device=device))
+            net = self.module.native_handle()
+        kind = np.array([0 if n in self.prognostic_names else 1 for n in self.in_names], dtype=np.int32)
+        index = np.array(
+            [self.prognostic_names.index(n) if n in self.prognostic_names else self.forcing_names.index(n) for n in self.in_names],
+            dtype=np.int32,
+        )
+        out_prog = np.array([self.prognostic_names.index(n) if n in self.prognostic_names else -1 for n in self.out_names], dtype=np.int32)
+        f32 = lambda names, d: np.array([d[n] for n in names], dtype=np.float32)  # noqa: E731
+        in_mean, in_std = f32(self.in_names, self._means), f32(self.in_names, self._stds)
+        out_mean, out_std = f32(self.out_names, self._means), f32(self.out_names, self._stds)
+        ip = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_int))  # noqa: E731
+        fp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))  # noqa: E731
+        cfg = _lib.StepConfig(
+            n_in=len(self.in_names), n_out=len(self.out_names), n_prog=len(self.prognostic_names),
+            n_forcing=len(self.forcing_names), in_kind_host=ip(kind), in_index_host=ip(index),
+            out_prog_index_host=ip(out_prog), in_mean_host=fp(in_mean), in_std_host=fp(in_std),
+            out_mean_host=fp(out_mean), out_std_host=fp(out_std), residual_prediction=int(self.residual_prediction),
+        )
+        handle = ctypes.c_void_p()
+        _lib.check(_lib.load().ace_stepper_create(net, ctypes.byref(cfg), ctypes.byref(handle)))
+        self._handle, self._handle_net = handle, net
+        self._graph = None
+
+    def _destroy(self):
+        if getattr(self, "_handle", None) is not None:
+            try:
+                _lib.load().ace_stepper_destroy(self._handle)
+            except Exception:  # noqa: BLE001
+                pass
+        self._handle = None
+        self._handle_net = None
+
+    def __del__(self):
+        self._destroy()
+
+    # ------------------------------------------------------------------ one step, packed tensors
+    def step_packed(self, prog: torch.Tensor, forcing: Optional[torch.Tensor], out: Optional[torch.Tensor] = None,
+                    next_prog: Optional[torch.Tensor] = None):
+        """prog [B, n_prog, H, W], forcing [B, n_forcing, H, W] -> (out [B, n_out, H, W], next_prog)."""
+        if not prog.is_cuda:
+            raise _lib.AceError("FusedStepper: tensors must be on a CUDA device (there is no CPU path)")
+        B = prog.shape[0]
+        H, W = self.module.img_shape
+        prog = prog.float().contiguous()
+        if forcing is not None:
+            forcing = forcing.float().contiguous()
+        if out is None:
+            out = torch.empty(B, len(self.out_names), H, W, device=prog.device, dtype=torch.float32)
+        if next_prog is None:
+            next_prog = torch.empty(B, len(self.prognostic_names), H, W, device=prog.device, dtype=torch.float32)
+        with torch.cuda.device(prog.device):
+            self._ensure(prog.device)
+            stream = _lib.current_stream_ptr()
+            self.module._sync_params(stream)
+            _lib.check(_lib.load().ace_stepper_step(
+                self._handle, ctypes.c_void_p(prog.data_ptr()),
+                ctypes.c_void_p(forcing.data_ptr()) if forcing is not None else None,
+                ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(next_prog.data_ptr()), B, stream))
+        return out, next_prog
+
+    # ------------------------------------------------------------------ one step, name dicts (reference API shape)
+    def step(self, input: Mapping[str, torch.Tensor], next_step_input_data: Optional[Mapping[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+        """``input``: every name in ``in_names`` -> [B, H, W] (denormalised).  Returns every ``out_names`` entry."""
+        prog = torch.stack([input[n] for n in self.prognostic_names], dim=1)
+        forcing = torch.stack([input[n] for n in self.forcing_names], dim=1) if self.forcing_names else None
+        out, _ = self.step_packed(prog, forcing)
+        return {n: out[:, i] for i, n in enumerate(self.out_names)}
+
+    # ------------------------------------------------------------------ rollout
+    def rollout(self, prog0: torch.Tensor, forcing_seq: Optional[torch.Tensor], n_steps: int, use_cuda_graph: bool = True,
+                keep_outputs: bool = True):
+        """Autoregressive loop (predict_generator).  forcing_seq [n_steps, B, n_forcing, H, W] resident on device.
+
+        Returns (outputs [n_steps, B, n_out, H, W] or None, final prognostic state).
+        """
+        B = prog0.shape[0]
+        H, W = self.module.img_shape
+        dev = prog0.device
+        n_out, n_prog = len(self.out_names), len(self.prognostic_names)
+        outs = torch.empty(n_steps, B, n_out, H, W, device=dev) if keep_outputs else None
+        state = prog0.float().contiguous().clone()
+        if not use_cuda_graph:
+            out_buf = torch.empty(B, n_out, H, W, device=dev)
+            nxt = torch.empty_like(state)
+            for t in range(n_steps):
+                f = forcing_seq[t] if forcing_seq is not None else None
+                self.step_packed(state, f, out_buf if outs is None else outs[t], nxt)
+                state, nxt = nxt, state
+            return outs, state
+        st = self._static
+        if self._graph is None or st is None or st["B"] != B or st["prog"].device != dev:
+            st = dict(
+                B=B, prog=torch.empty_like(state),
+                forcing=torch.empty(B, len(self.forcing_names), H, W, device=dev) if self.forcing_names else None,
+                out=torch.empty(B, n_out, H, W, device=dev), nxt=torch.empty(B, n_prog, H, W, device=dev),
+            )
+            st["prog"].copy_(state)
+            if st["forcing"] is not None:
+                st["forcing"].zero_()
+            self.step_packed(st["prog"], st["forcing"], st["out"], st["nxt"])  # warm-up: allocations, func attributes
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.step_packed(st["prog"], st["forcing"], st["out"], st["nxt"])
+                st["prog"].copy_(st["nxt"])  # feed back inside the graph
+            self._graph, self._static = g, st
+        st["prog"].copy_(state)
+        for t in range(n_steps):
+            if st["forcing"] is not None:
+                st["forcing"].copy_(forcing_seq[t], non_blocking=True)
+            self._graph.replay()
+            if outs is not None:
+                outs[t].copy_(st["out"], non_blocking=True)
+        return outs, st["prog"].clone()

@@ -1,0 +1,148 @@
+/*
+ * ace_b200 -- C ABI of the B200-native SFNO inference hot path.
+ *
+ * Drop-in boundary for the one path of ai2cm/ace (fme 2026.5.1) that this
+ * library replaces.  The reference is pure Python, so there is no existing FFI
+ * to mirror; each entry point below names the reference interface whose device
+ * work it takes over (paths relative to the reference tree):
+ *
+ *   ace_sht_*      fme/sht_fix.py:60-151 (RealSHT), :153-226 (InverseRealSHT),
+ *                  fme/fft.py:60-96 (rfft/irfft conventions)
+ *   ace_sfno_*     fme/ace/models/modulus/sfnonet.py:341-749
+ *                  (SphericalFourierNeuralOperatorNet.__init__/forward) incl.
+ *                  sfnonet.py:123-252 (block), s2convolutions.py:47-197
+ *                  (SpectralConvS2), contractions.py:170-195, layers.py:97-137,
+ *                  as built by fme/ace/registry/sfno.py:44-61 and called from
+ *                  fme/core/step/single_module.py:425-428
+ *   ace_step_*     fme/core/step/single_module.py:595-665 (normalise, pack,
+ *                  network, unpack, residual add, denormalise) and the feedback
+ *                  loop of fme/ace/stepper/single_module.py:1124-1167
+ *
+ * Conventions
+ *   - plain C types only; every pointer named *_dev is a device pointer owned
+ *     by the caller (PyTorch's allocator in practice) and only borrowed for the
+ *     duration of the call; *_host pointers are host memory.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it,
+ *     nothing synchronises the host, so calls can be captured in a CUDA graph
+ *     once workspaces exist (first call with a given batch allocates them).
+ *   - return value 0 = success; anything else is an error code and
+ *     ace_last_error() returns a thread-local message.  Nothing calls exit().
+ *   - plans / nets are immutable after finalize; one in-flight call per object.
+ *   - fp32 in, fp32 out.  Inside, GEMM-shaped work runs on tcgen05 tensor cores
+ *     as 3-term split-bf16 products (a_hi*b_hi + a_hi*b_lo + a_lo*b_hi, fp32
+ *     accumulate in TMEM); see DESIGN.md for the error budget.
+ */
+#ifndef ACE_B200_H_
+#define ACE_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACE_OK 0
+#define ACE_ERR_INVALID 1   /* bad argument / unsupported configuration */
+#define ACE_ERR_CUDA 2      /* a CUDA runtime / driver call failed */
+#define ACE_ERR_STATE 3     /* call sequence error (e.g. forward before finalize) */
+
+typedef struct ace_sht_plan ace_sht_plan;
+typedef struct ace_sfno ace_sfno;
+typedef struct ace_stepper ace_stepper;
+
+int ace_version(void);
+const char* ace_last_error(void);
+
+/* Runtime options (development / A-B testing):
+ *   "force_simt"  1 = route every GEMM through the generic SIMT CUDA kernel
+ *                 instead of the tcgen05 kernel (both are CUDA; there is no CPU path)
+ *   "split_terms" 3 (default) or 1 = plain bf16 products (fast, ~1e-2 accurate)
+ *   "profile"     1 = time every launch with CUDA events (see ace_profile_report)
+ *   "umma_bk"     64 (default) or 32: K extent per pipeline stage of the tcgen05 kernel
+ *   "umma_bn"     0 (default: per-op choice) or 128 / 192 / 256: N tile of the tcgen05 kernel
+ * Read-only counters through ace_get_option: "count_umma" / "count_simt" = GEMMs launched on the
+ * tcgen05 / SIMT kernel since load.                                                            */
+int ace_set_option(const char* key, int value);
+int ace_get_option(const char* key);
+/* Number of kernels this library has launched since load (all streams). */
+long long ace_launch_count(void);
+/* With option "profile" = 1 every launch is bracketed by CUDA events on its stream.  This call
+ * synchronises, writes one "name count total_ms" line per kernel name into buf, clears the
+ * records and returns the number of bytes written. */
+int ace_profile_report(char* buf, int buflen);
+
+/* ---- spherical harmonic transforms ---------------------------------------------------
+ * legendre_fwd_host / legendre_inv_host: float64 [mmax][lmax][nlat], the tables of
+ * fme/sht_fix.py:113-117 (P_l^m(cos theta_k) * w_k) and :195-198 (P_l^m(cos theta_k)).
+ * They are cast to fp32 exactly as the reference does before any further processing. */
+int ace_sht_plan_create(int nlat, int nlon, int lmax, int mmax,
+                        const double* legendre_fwd_host, const double* legendre_inv_host,
+                        ace_sht_plan** out);
+void ace_sht_plan_destroy(ace_sht_plan* plan);
+/* x_dev: float32 [nfields][nlat][nlon]  ->  coeffs_dev: complex64 [nfields][lmax][mmax] */
+int ace_sht_forward(ace_sht_plan* plan, const float* x_dev, float* coeffs_dev, long long nfields, void* stream);
+/* coeffs_dev: complex64 [nfields][lmax][mmax] -> x_dev: float32 [nfields][nlat][nlon] */
+int ace_sht_inverse(ace_sht_plan* plan, const float* coeffs_dev, float* x_dev, long long nfields, void* stream);
+
+/* ---- the network ------------------------------------------------------------------ */
+typedef struct ace_sfno_config {
+  int img_h, img_w;          /* nlat, nlon */
+  int in_chans, out_chans;
+  int embed_dim, num_layers;
+  int lmax, mmax;            /* modes_lat, modes_lon (sfnonet.py:471-472) */
+  int mlp_hidden;            /* int(embed_dim * mlp_ratio); 0 = no MLP */
+  int operator_type;         /* 0 = diagonal, 1 = dhconv */
+  int normalization;         /* 0 = none, 1 = instance_norm */
+  int pos_embed;             /* 0/1 */
+  int big_skip;              /* 0/1 */
+  float norm_eps;            /* 1e-6 in the reference */
+} ace_sfno_config;
+
+/* plan_outer: data-grid plan used by the first block's forward and the last block's
+ * inverse transform (trans_down / itrans_up); plan_inner: legendre-gauss plan (trans / itrans).
+ * They may be the same object.  Plans must outlive the net. */
+int ace_sfno_create(const ace_sfno_config* cfg, ace_sht_plan* plan_outer, ace_sht_plan* plan_inner, ace_sfno** out);
+void ace_sfno_destroy(ace_sfno* net);
+/* name = the reference's state_dict key (e.g. "blocks.3.filter.filter.weight"); data_dev is
+ * float32, contiguous, in the reference's shape.  Copied/re-laid-out on `stream`. */
+int ace_sfno_set_param(ace_sfno* net, const char* name, const float* data_dev, long long numel, void* stream);
+/* Verifies every parameter has been set. */
+int ace_sfno_finalize(ace_sfno* net);
+/* x_dev float32 [batch][in_chans][H][W] -> y_dev float32 [batch][out_chans][H][W] */
+int ace_sfno_forward(ace_sfno* net, const float* x_dev, float* y_dev, int batch, void* stream);
+
+/* Shape query (used by the stepper and the Python wrapper). */
+int ace_sfno_query(ace_sfno* net, int* in_chans, int* out_chans, long long* hw);
+
+/* ---- fused step: normalise -> pack -> net -> (residual) -> denormalise -> feed back ----
+ * State layout: prognostic/forcing/diagnostic fields as float32 [batch][n][H][W] tensors.
+ *   in_index_*:  for network input channel c: source kind (0 = prognostic state, 1 = forcing)
+ *                and index into that tensor
+ *   out_prog_index: for output channel c, index of the prognostic it updates, or -1 (diagnostic) */
+typedef struct ace_step_config {
+  int n_in, n_out, n_prog, n_forcing;
+  const int* in_kind_host;      /* [n_in] */
+  const int* in_index_host;     /* [n_in] */
+  const int* out_prog_index_host; /* [n_out] */
+  const float* in_mean_host;    /* [n_in]  */
+  const float* in_std_host;     /* [n_in]  */
+  const float* out_mean_host;   /* [n_out] */
+  const float* out_std_host;    /* [n_out] */
+  int residual_prediction;      /* 0/1: add normalised input of the same prognostic to the output */
+} ace_step_config;
+int ace_stepper_create(ace_sfno* net, const ace_step_config* cfg, ace_stepper** out);
+void ace_stepper_destroy(ace_stepper* st);
+/* One 6-hour step.  prog_dev [batch][n_prog][H][W] is read; out_dev [batch][n_out][H][W]
+ * receives the denormalised outputs; next_prog_dev [batch][n_prog][H][W] receives the state
+ * for the next step (outputs that are prognostic; may alias nothing). */
+int ace_stepper_step(ace_stepper* st, const float* prog_dev, const float* forcing_dev,
+                     float* out_dev, float* next_prog_dev, int batch, void* stream);
+
+/* ---- development hook: run one split-bf16 GEMM through both kernels (tests only) ------
+ * D[z][m][n] = sum_k A[z][m][k] * B[z][n][k], fp32 in/out, row-major, a_mn_major selects the
+ * A storage order ([z][k][m] when 1).  impl: 0 = SIMT kernel, 1 = tcgen05 kernel. */
+int ace_dev_gemm(const float* a_dev, const float* b_dev, float* d_dev, int m, int n, int k, int nbatch,
+                 int a_mn_major, int impl, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACE_B200_H_ */

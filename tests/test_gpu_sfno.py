@@ -1,0 +1,107 @@
+"""GPU: the SFNO forward through the module / C ABI vs committed reference vectors and the oracle."""
+import pytest
+import torch
+
+from tests.util import NET_GOLDENS, field_rel_err, golden_net_fields, golden_state_dict, load_golden
+
+pytestmark = pytest.mark.gpu
+
+# Stated tolerance (BASELINE.json north_star: "rtol 1e-4 on prognostic fields after one step"):
+# for every (sample, field):  max|y - y_ref| <= 1e-4 * max|y_ref|.
+FIELD_RTOL = 1e-4
+
+
+def _b200_net(img_shape, cin, cout, fields):
+    import ace_b200
+
+    builder = ace_b200.ModuleSelector(type="B200SphericalFourierNeuralOperatorNet", config=fields)
+    return builder.build(cin, cout, ace_b200.DatasetInfo(img_shape=tuple(img_shape))).torch_module
+
+
+@pytest.mark.parametrize("name", NET_GOLDENS)
+def test_net_matches_reference_vectors(name):
+    g = load_golden(name)
+    fields = golden_net_fields(g)
+    net = _b200_net(g["img_shape"], int(g["in_chans"]), int(g["out_chans"]), fields)
+    net.load_state_dict(golden_state_dict(g))
+    net = net.cuda().eval()
+    with torch.no_grad():
+        y = net(torch.from_numpy(g["x"]).cuda())
+    ref = torch.from_numpy(g["output"])
+    assert y.shape == ref.shape and y.dtype == torch.float32
+    assert field_rel_err(y.cpu(), ref) < FIELD_RTOL
+
+
+@pytest.mark.parametrize(
+    "img,cin,cout,embed,layers,batch",
+    [
+        ((48, 96), 6, 7, 32, 3, 2),      # every GEMM eligible for the tcgen05 kernel
+        ((180, 360), 8, 8, 16, 2, 1),    # BASELINE configs[0] grid, reduced width
+        ((64, 128), 5, 3, 64, 2, 3),
+    ],
+)
+def test_net_tcgen05_path_vs_oracle(img, cin, cout, embed, layers, batch):
+    from ace_b200 import _lib
+    from oracle import sfno as osfno
+
+    fields = dict(embed_dim=embed, num_layers=layers, operator_type="dhconv")
+    torch.manual_seed(5)
+    onet = osfno.SphericalFourierNeuralOperatorNet(img, cin, cout, **fields).eval()
+    g = torch.Generator().manual_seed(6)
+    with torch.no_grad():
+        for k, p in onet.named_parameters():
+            if k.endswith("bias") or "norm" in k:
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+            if k.endswith("filter.filter.weight"):
+                p.mul_(p.shape[0])
+    net = _b200_net(img, cin, cout, fields)
+    net.load_state_dict(onet.state_dict())
+    net = net.cuda().eval()
+    x = torch.randn(batch, cin, *img, generator=g)
+    u0, s0 = _lib.get_option("count_umma"), _lib.get_option("count_simt")
+    with torch.no_grad():
+        y = net(x.cuda())
+        ref = onet(x)
+    torch.cuda.synchronize()
+    assert _lib.get_option("count_simt") == s0, "a GEMM fell back to the SIMT kernel"
+    assert _lib.get_option("count_umma") - u0 == 4 + 9 * layers
+    assert field_rel_err(y.cpu(), ref) < FIELD_RTOL
+    # SIMT kernels on the same problem agree with the tensor-core path
+    _lib.set_option("force_simt", 1)
+    try:
+        with torch.no_grad():
+            y2 = net(x.cuda())
+    finally:
+        _lib.set_option("force_simt", 0)
+    assert field_rel_err(y2.cpu(), ref) < FIELD_RTOL
+    assert field_rel_err(y.cpu(), y2.cpu()) < FIELD_RTOL
+
+
+def test_module_contract():
+    import ace_b200
+
+    fields = dict(embed_dim=16, num_layers=2, operator_type="dhconv")
+    net = _b200_net((16, 32), 3, 4, fields)
+    with pytest.raises(ace_b200.AceError):
+        net(torch.zeros(1, 3, 16, 32))  # CPU input: no fallback
+    net = net.cuda()
+    x = torch.randn(2, 3, 16, 32, device="cuda")
+    with pytest.raises(ace_b200.AceError):
+        net(x)  # gradients enabled on trainable parameters
+    with torch.no_grad():
+        y1 = net(x)
+        # batch size may change between calls (ensemble folding); results are per-sample independent
+        y2 = net(x[:1])
+        torch.testing.assert_close(y1[:1], y2, rtol=1e-5, atol=1e-6)
+        # parameter edits are picked up (version counter) ...
+        net.decoder[2].weight.mul_(2.0)
+        y3 = net(x)
+        torch.testing.assert_close(y3, 2 * y1, rtol=1e-4, atol=1e-6)
+        # ... and so is load_state_dict
+        sd = {k: v.clone() for k, v in net.state_dict().items()}
+        sd["decoder.2.weight"] = sd["decoder.2.weight"] / 2
+        net.load_state_dict(sd)
+        torch.testing.assert_close(net(x), y1, rtol=1e-4, atol=1e-6)
+    with pytest.raises(ValueError):
+        with torch.no_grad():
+            net(torch.zeros(1, 5, 16, 32, device="cuda"))

@@ -1,0 +1,78 @@
+"""GPU: fused step (normalise/pack/net/unpack/denormalise) and rollout vs an oracle restatement."""
+import pytest
+import torch
+
+from tests.util import field_rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_step(onet, in_names, out_names, means, stds, residual, state):
+    """fme/core/step/single_module.py:648-665 with corrector/ocean off, on name dicts (CPU, fp32)."""
+    prog = [n for n in out_names if n in in_names]
+    norm = {n: (state[n] - means[n]) / stds[n] for n in in_names}
+    x = torch.stack([norm[n] for n in in_names], dim=1)  # Packer.pack (fme/core/packer.py:45-52)
+    with torch.no_grad():
+        y = onet(x)
+    out = {n: y[:, i] for i, n in enumerate(out_names)}
+    if residual:
+        for n in prog:
+            out[n] = out[n] + norm[n]
+    return {n: out[n] * stds[n] + means[n] for n in out_names}
+
+
+def _setup(residual):
+    import ace_b200
+    from oracle import sfno as osfno
+
+    img = (32, 64)
+    in_names = ["a", "b", "f1", "c", "f2"]
+    out_names = ["c", "d1", "a", "b", "d2", "d3"]
+    means = {n: 0.1 * (i - 3) for i, n in enumerate(sorted(set(in_names + out_names)))}
+    stds = {n: 0.5 + 0.25 * i for i, n in enumerate(sorted(set(in_names + out_names)))}
+    torch.manual_seed(0)
+    onet = osfno.SphericalFourierNeuralOperatorNet(img, len(in_names), len(out_names), embed_dim=16, num_layers=2, operator_type="dhconv").eval()
+    sel = ace_b200.ModuleSelector(type="B200SphericalFourierNeuralOperatorNet", config=dict(embed_dim=16, num_layers=2, operator_type="dhconv"))
+    net = sel.build(len(in_names), len(out_names), ace_b200.DatasetInfo(img_shape=img)).torch_module
+    net.load_state_dict(onet.state_dict())
+    net = net.cuda().eval().requires_grad_(False)
+    st = ace_b200.FusedStepper(net, in_names, out_names, means, stds, residual_prediction=residual)
+    return img, in_names, out_names, means, stds, onet, st
+
+
+@pytest.mark.parametrize("residual", [False, True])
+def test_step_matches_oracle(residual):
+    img, in_names, out_names, means, stds, onet, st = _setup(residual)
+    assert st.prognostic_names == ["c", "a", "b"] and st.forcing_names == ["f1", "f2"]
+    torch.manual_seed(1)
+    state = {n: torch.randn(2, *img) * stds[n] + means[n] for n in in_names}
+    ref = _oracle_step(onet, in_names, out_names, means, stds, residual, state)
+    out = st.step({n: v.cuda() for n, v in state.items()})
+    assert list(out.keys()) == out_names
+    for n in out_names:
+        # tolerance in normalised units (the denormalisation offset would otherwise hide errors)
+        a = ((out[n].cpu() - means[n]) / stds[n])[:, None]
+        b = ((ref[n] - means[n]) / stds[n])[:, None]
+        assert field_rel_err(a, b) < 1e-4, n
+
+
+def test_rollout_graph_equals_eager_and_oracle():
+    img, in_names, out_names, means, stds, onet, st = _setup(True)
+    torch.manual_seed(2)
+    T, B = 4, 2
+    prog0 = torch.randn(B, 3, *img).cuda()
+    forcing = torch.randn(T, B, 2, *img).cuda()
+    outs_e, fin_e = st.rollout(prog0, forcing, T, use_cuda_graph=False)
+    outs_g, fin_g = st.rollout(prog0, forcing, T, use_cuda_graph=True)
+    torch.testing.assert_close(outs_g, outs_e, rtol=0, atol=0)
+    torch.testing.assert_close(fin_g, fin_e, rtol=0, atol=0)
+    # oracle loop (fme/ace/stepper/single_module.py:1135-1167): feed prognostic outputs back
+    state = {n: prog0[:, i].cpu() for i, n in enumerate(st.prognostic_names)}
+    for t in range(T):
+        full = dict(state)
+        for j, n in enumerate(st.forcing_names):
+            full[n] = forcing[t, :, j].cpu()
+        out = _oracle_step(onet, in_names, out_names, means, stds, True, full)
+        ref_t = torch.stack([out[n] for n in out_names], dim=1)
+        assert field_rel_err(outs_g[t].cpu(), ref_t) < 3e-4 * (t + 1), t
+        state = {n: out[n] for n in st.prognostic_names}
