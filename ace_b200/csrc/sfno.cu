@@ -219,6 +219,13 @@ void forward(ace_sfno& n, const float* x, float* y, int B, cudaStream_t s) {
     // spectral convolution (s2convolutions.py:162-197)
     run_gemm(sht_op_dft_fwd(pf, xn, P_act, act_b, C, B, n.x1.as<bf16>(), P_x1), s);
     run_gemm(sht_op_legendre_fwd(pf, n.x1.as<bf16>(), P_x1, C, B, n.c1.as<bf16>(), P_c1), s);
+    if (pf.table_id != pi.table_id) {
+      // forward and inverse grids differ -> scale_residual (s2convolutions.py:81-85,170-173): the residual
+      // used by inner_skip and the outer skip is inverse_transform(forward_transform(x_norm)).  x_norm has
+      // been consumed by the DFT, so the round trip overwrites xn in place.
+      run_gemm(sht_op_legendre_inv_from_c1(pi, n.c1.as<bf16>(), P_c1, C, B, n.g.as<bf16>(), P_g), s);
+      run_gemm(sht_op_dft_inv_planes(pi, n.g.as<bf16>(), P_g, C, B, xn, P_act, act_b), s);
+    }
     if (c.operator_type == 1) {
       GemmOp op = make_gemm_op("dhconv");
       op.M = 2 * C;

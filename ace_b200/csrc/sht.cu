@@ -106,12 +106,46 @@ GemmOp sht_op_dft_inv(const ace_sht_plan& p, const bf16* g, long long g_plane, i
   return op;
 }
 
+GemmOp sht_op_legendre_inv_from_c1(const ace_sht_plan& p, const bf16* c1, long long c1_plane, int C, int B, bf16* g,
+                                   long long g_plane) {
+  GemmOp op = sht_op_legendre_inv(p, c1, c1_plane, C, B, g, g_plane);
+  op.name = "sht.legendre_inv_res";
+  // c1 is [B][L][M][2C]: degree l strides over M*2C, order m (z1) over 2C; entries with l < m are exact zeros
+  op.A = {c1, c1_plane, 1, (long long)p.M * 2 * C, 2LL * C, p.c1_elems(C)};
+  return op;
+}
+
+GemmOp sht_op_dft_inv_planes(const ace_sht_plan& p, const bf16* g, long long g_plane, int C, int B, bf16* y,
+                             long long y_plane, long long y_batch_stride) {
+  GemmOp op = sht_op_dft_inv(p, g, g_plane, C, B, nullptr, 0);
+  op.name = "sht.dft_inv_res";
+  op.epi.flags = EPI_OUT_PLANES;
+  op.epi.outf = nullptr;
+  op.epi.out = y;
+  op.epi.out_plane = y_plane;
+  op.epi.o_z2 = y_batch_stride;
+  op.epi.o_m0 = p.W;
+  op.epi.o_n = 1;
+  return op;
+}
+
 }  // namespace ace
 
 using namespace ace;
 
+static unsigned long long fnv1a(const void* data, size_t n, unsigned long long h) {
+  const unsigned char* p = (const unsigned char*)data;
+  for (size_t i = 0; i < n; ++i) {
+    h ^= p[i];
+    h *= 1099511628211ull;
+  }
+  return h;
+}
+
 static void plan_build(ace_sht_plan& p, const double* fwd, const double* inv) {
   const int K = p.K, W = p.W, L = p.L, M = p.M;
+  p.table_id = fnv1a(fwd, sizeof(double) * (size_t)M * L * K, 1469598103934665603ull);
+  p.table_id = fnv1a(inv, sizeof(double) * (size_t)M * L * K, p.table_id);
   p.Kp = (int)round_up(K, 8);
   p.Lp = (int)round_up(L, 8);
   p.Wp = (int)round_up(W, 8);

@@ -16,6 +16,7 @@
 struct ace_sht_plan {
   int K, W, L, M;      // nlat, nlon, lmax, mmax
   int Kp, Lp, Wp, K2p; // padded strides (multiples of 8 elements = 16 bytes)
+  unsigned long long table_id = 0;  // FNV-1a of the two host tables: equal ids <=> same grid/normalisation
   ace::DevBuf wt;       // planes [M][L][Kp]    P_l^m(cos th_k) w_k
   ace::DevBuf pinv;     // planes [M][K][Lp]    P_l^m(cos th_k), l contiguous
   ace::DevBuf fdft;     // planes [2M][Wp]      forward DFT rows (2pi/W)(cos, -sin)
@@ -44,5 +45,12 @@ GemmOp sht_op_legendre_inv(const ace_sht_plan& p, const bf16* c2, long long c2_p
                            long long g_plane);
 GemmOp sht_op_dft_inv(const ace_sht_plan& p, const bf16* g, long long g_plane, int C, int B, float* y,
                       long long y_batch_stride);
+// Round-trip residual of SpectralConvS2 when the forward and inverse grids differ
+// (s2convolutions.py:81-85,170-173): inverse Legendre stage reading the c1 layout in place ...
+GemmOp sht_op_legendre_inv_from_c1(const ace_sht_plan& p, const bf16* c1, long long c1_plane, int C, int B, bf16* g,
+                                   long long g_plane);
+// ... and the inverse DFT storing split planes [B][C][K][W] instead of fp32
+GemmOp sht_op_dft_inv_planes(const ace_sht_plan& p, const bf16* g, long long g_plane, int C, int B, bf16* y,
+                             long long y_plane, long long y_batch_stride);
 
 }  // namespace ace
