@@ -68,11 +68,8 @@ extern "C" int ace_set_option(const char* key, int value) {
   else if (!strcmp(key, "split_terms")) {
     ACE_REQUIRE(value == 1 || value == 3, "split_terms must be 1 or 3");
     options().split_terms = value;
-  } else if (!strcmp(key, "umma_bk")) {
-    ACE_REQUIRE(value == 32 || value == 64, "umma_bk must be 32 or 64");
-    options().umma_bk = value;
   } else if (!strcmp(key, "umma_bn")) {
-    ACE_REQUIRE(value == 0 || value == 128 || value == 192 || value == 256, "umma_bn must be 0, 128, 192 or 256");
+    ACE_REQUIRE(value == 0 || value == 192 || value == 256, "umma_bn must be 0, 192 or 256");
     options().umma_bn = value;
   } else ACE_REQUIRE(false, "ace_set_option: unknown option '%s'", key);
   ACE_API_END
@@ -83,7 +80,6 @@ extern "C" int ace_get_option(const char* key) {
   if (!strcmp(key, "force_simt")) return options().force_simt;
   if (!strcmp(key, "profile")) return options().profile;
   if (!strcmp(key, "split_terms")) return options().split_terms;
-  if (!strcmp(key, "umma_bk")) return options().umma_bk;
   if (!strcmp(key, "count_umma")) return (int)g_umma_count.load();
   if (!strcmp(key, "count_simt")) return (int)g_simt_count.load();
   if (!strcmp(key, "umma_bn")) return options().umma_bn;
@@ -125,30 +121,34 @@ extern "C" int ace_profile_report(char* buf, int buflen) {
   return n;
 }
 
-// D[z][m][n] = sum_k A[z][m][k] * B[z][n][k] through the split-plane machinery (tests only)
+// D[z][m][n] = sum_k A[z][m][k] * B[z][n][k] through the split-plane machinery (tests only).
+// layout bit 0: A is stored MN-major ([z][k][m]); bit 1: B is stored MN-major ([z][k][n]).
 extern "C" int ace_dev_gemm(const float* a_dev, const float* b_dev, float* d_dev, int m, int n, int k, int nbatch,
-                            int a_mn_major, int impl, void* stream) {
+                            int layout, int impl, void* stream) {
   ACE_API_BEGIN
   ACE_REQUIRE(a_dev && b_dev && d_dev && m > 0 && n > 0 && k > 0 && nbatch > 0, "ace_dev_gemm: bad argument");
+  ACE_REQUIRE(layout >= 0 && layout <= 3, "ace_dev_gemm: layout must be 0..3");
   cudaStream_t s = (cudaStream_t)stream;
-  // A planes: K-major [z][m][kp] or MN-major [z][k][mp]; B planes [z][n][kp]
-  const int kp = (int)round_up(k, 8), mp = (int)round_up(m, 8);
-  const long long a_per = a_mn_major ? (long long)k * mp : (long long)m * kp;
-  const long long b_per = (long long)n * kp;
+  const bool a_mn = layout & 1, b_mn = (layout & 2) != 0;
+  const int kp = (int)round_up(k, 8), mp = (int)round_up(m, 8), np = (int)round_up(n, 8);
+  const long long a_per = a_mn ? (long long)k * mp : (long long)m * kp;
+  const long long b_per = b_mn ? (long long)k * np : (long long)n * kp;
   DevBuf abuf, bbuf;
   abuf.ensure(2 * (size_t)(a_per * nbatch) * sizeof(bf16));
   bbuf.ensure(2 * (size_t)(b_per * nbatch) * sizeof(bf16));
-  if (a_mn_major) launch_split_pad(a_dev, (long long)nbatch * k, m, mp, abuf.as<bf16>(), a_per * nbatch, s);
+  if (a_mn) launch_split_pad(a_dev, (long long)nbatch * k, m, mp, abuf.as<bf16>(), a_per * nbatch, s);
   else launch_split_pad(a_dev, (long long)nbatch * m, k, kp, abuf.as<bf16>(), a_per * nbatch, s);
-  launch_split_pad(b_dev, (long long)nbatch * n, k, kp, bbuf.as<bf16>(), b_per * nbatch, s);
+  if (b_mn) launch_split_pad(b_dev, (long long)nbatch * k, n, np, bbuf.as<bf16>(), b_per * nbatch, s);
+  else launch_split_pad(b_dev, (long long)nbatch * n, k, kp, bbuf.as<bf16>(), b_per * nbatch, s);
   GemmOp op = make_gemm_op("dev_gemm");
   op.M = m;
   op.N = n;
   op.K = k;
   op.Z2 = nbatch;
-  if (a_mn_major) op.A = {abuf.as<bf16>(), a_per * nbatch, 1, (long long)mp, 0, a_per};
+  if (a_mn) op.A = {abuf.as<bf16>(), a_per * nbatch, 1, (long long)mp, 0, a_per};
   else op.A = {abuf.as<bf16>(), a_per * nbatch, (long long)kp, 1, 0, a_per};
-  op.B = {bbuf.as<bf16>(), b_per * nbatch, (long long)kp, 1, 0, b_per};
+  if (b_mn) op.B = {bbuf.as<bf16>(), b_per * nbatch, 1, (long long)np, 0, b_per};
+  else op.B = {bbuf.as<bf16>(), b_per * nbatch, (long long)kp, 1, 0, b_per};
   op.epi.flags = EPI_OUT_F32;
   op.epi.outf = d_dev;
   op.epi.f_z2 = (long long)m * n;

@@ -86,8 +86,7 @@ struct Options {
   int profile = 0;
   int force_simt = 0;
   int split_terms = 3;
-  int umma_bk = 64;  // K extent of one pipeline stage of the tcgen05 kernel (64 -> 128B swizzle, 32 -> 64B)
-  int umma_bn = 0;   // 0 = choose per op; otherwise force the N tile (128 / 192 / 256)
+  int umma_bn = 0;   // 0 = choose per op; otherwise force the N tile of the K-major x K-major variants (192 / 256)
 };
 Options& options();
 

@@ -5,11 +5,11 @@
 //     epilogue(D[m][n]) -> bias / addend / residual / GELU / per-column statistics / stores
 //
 // Operands live in HBM as "split-bf16 planes": two bf16 arrays (hi at `ptr`, lo at
-// `ptr + plane`), value = hi + lo.  Strides are in elements.  A may be K-major
-// (s_k == 1) or MN-major (s_row == 1); B is always K-major.  Both kernels
-// (gemm_simt.cu: generic SIMT; gemm_umma.cu: TMA + tcgen05) implement exactly this
-// contract, so either can serve any op the other can (the tcgen05 one additionally
-// needs 16-byte aligned strides).
+// `ptr + plane`), value = hi + lo.  Strides are in elements.  A and B may each be K-major
+// (s_k == 1) or MN-major (s_row == 1).  The SIMT kernel (gemm_simt.cu) implements this
+// contract for any strides and any epilogue flag combination; the tcgen05 kernel
+// (gemm_umma.cu) implements the fast subsets the network uses (16-byte aligned strides and
+// one of the epilogue shapes listed in umma_eligible()); run_gemm() routes between them.
 //
 // Triangular structure of the Legendre / dhconv stages is expressed through z1:
 //   n_lo_z1: n_lo = z1      (forward Legendre: only degrees l >= m are non-zero)
@@ -39,6 +39,8 @@ enum EpiFlags : uint32_t {
   EPI_STATS = 1u << 4,       // stats[(z2*stats_z2 + n)*2 + {0,1}] += {v, v*v}   (double atomics)
   EPI_OUT_PLANES = 1u << 5,  // split-bf16 store
   EPI_OUT_F32 = 1u << 6,     // fp32 store
+  EPI_ROW_BIAS = 1u << 7,    // v += row_bias[z2*rb_z2 + m]
+  EPI_ROW_STATS = 1u << 8,   // stats[(z2*stats_z2 + m)*2 + {0,1}] += {v, v*v}   (double atomics)
 };
 
 // Row index m is decomposed as m1 = m / mdiv, m0 = m % mdiv so that flattened
@@ -48,6 +50,8 @@ struct EpiParams {
   int mdiv;
   const float* col_bias;
   long long cb_z2;
+  const float* row_bias;
+  long long rb_z2;
   const float* add;
   long long add_z2, add_m1, add_m0, add_n;
   const bf16* res;
@@ -83,6 +87,7 @@ inline GemmOp make_gemm_op(const char* name) {
 __device__ __forceinline__ float epi_value(const EpiParams& e, float acc, int m1, int m0, int n, int z2) {
   float v = acc;
   if (e.flags & EPI_COL_BIAS) v += __ldg(e.col_bias + (long long)z2 * e.cb_z2 + n);
+  if (e.flags & EPI_ROW_BIAS) v += __ldg(e.row_bias + (long long)z2 * e.rb_z2 + (long long)m1 * e.mdiv + m0);
   if (e.flags & EPI_ADD_F32) v += __ldg(e.add + (long long)z2 * e.add_z2 + (long long)m1 * e.add_m1 + (long long)m0 * e.add_m0 + (long long)n * e.add_n);
   if (e.flags & EPI_RES_PLANES) {
     const bf16* r = e.res + (long long)z2 * e.res_z2 + (long long)m1 * e.res_m1 + (long long)m0 * e.res_m0 + (long long)n * e.res_n;

@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const __grid_constant__ G
   const bf16* A = op.A.ptr + (long long)z1 * op.A.s_z1 + (long long)z2 * op.A.s_z2;
   const bf16* B = op.B.ptr + (long long)z1 * op.B.s_z1 + (long long)z2 * op.B.s_z2;
   const bool a_kmajor = (op.A.s_k == 1);
+  const bool b_kmajor = (op.B.s_k == 1);
 
   const int tid = threadIdx.x;
   const int tx = tid % 16, ty = tid / 16;  // tx -> n, ty -> m
@@ -56,7 +57,8 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const __grid_constant__ G
 #pragma unroll
     for (int i = 0; i < BN * BK / NT; ++i) {
       int idx = tid + i * NT;
-      int kk = idx % BK, nn = idx / BK;
+      int kk, nn;
+      if (b_kmajor) { kk = idx % BK; nn = idx / BK; } else { nn = idx % BN; kk = idx / BN; }
       int n = n0 + nn, k = k0 + kk;
       float v = 0.f;
       if (n < op.N && k < op.K && k >= k_lo) {
@@ -90,6 +92,7 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const __grid_constant__ G
     int m = m0 + ty * TM + i;
     if (m >= op.M) continue;
     int m1 = m / e.mdiv, mr = m % e.mdiv;
+    float rsum = 0.f, rsq = 0.f;
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
       int n = n0 + tx * TN + j;
@@ -97,7 +100,14 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const __grid_constant__ G
       float v = epi_value(e, acc[i][j], m1, mr, n, z2);
       csum[j] += v;
       csq[j] += v * v;
+      rsum += v;
+      rsq += v * v;
       epi_store(e, v, m1, mr, n, z1, z2);
+    }
+    if (e.flags & EPI_ROW_STATS) {
+      double* st = e.stats + ((long long)z2 * e.stats_z2 + m) * 2;
+      atomicAdd(st, (double)rsum);
+      atomicAdd(st + 1, (double)rsq);
     }
   }
   if (e.flags & EPI_STATS) {
@@ -124,7 +134,6 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const __grid_constant__ G
 
 void run_gemm_simt(const GemmOp& op, cudaStream_t stream) {
   ACE_REQUIRE(op.M > 0 && op.N > 0 && op.K > 0 && op.Z1 > 0 && op.Z2 > 0, "gemm %s: empty problem", op.name);
-  ACE_REQUIRE(op.B.s_k == 1, "gemm %s: B must be K-major", op.name);
   ACE_REQUIRE(op.Z1 <= 65535 && op.Z2 <= 65535, "gemm %s: batch extent too large", op.name);
   int tiles_m = (op.M + BM - 1) / BM, tiles_n = (op.N + BN - 1) / BN;
   dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)op.Z1, (unsigned)op.Z2);

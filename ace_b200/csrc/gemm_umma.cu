@@ -1,19 +1,28 @@
-// tcgen05 / TMA implementation of the GemmOp contract (gemm.cuh) for sm_100a.
+// tcgen05 / TMA implementation of the fast subsets of the GemmOp contract (gemm.cuh) for sm_100a.
 //
-// One persistent CTA per SM, 256 threads, warp-specialised:
-//   warp 0   TMA producer   -- cp.async.bulk.tensor loads of the hi and lo bf16 planes of the A and B
-//                              tiles into a multi-stage shared-memory ring (128B/64B hardware swizzle)
-//   warp 1   MMA issuer     -- one thread issues tcgen05.mma (M=128, N<=256, K=16, bf16 x bf16 -> fp32
-//                              in TMEM); per K-step THREE products: Ahi*Bhi + Ahi*Blo + Alo*Bhi, which
-//                              reproduces an fp32 product to ~2^-17 relative (error budget)
-//   warp 2   TMEM allocator -- 2 accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1
-//   warps 4-7 epilogue      -- tcgen05.ld TMEM -> registers, bias / addend / residual / GELU, InstanceNorm
-//                              statistics via warp-shuffle transpose-reduce + double atomics, split-bf16
-//                              and/or fp32 stores straight from registers
+// One persistent CTA per SM, 384 threads, warp-specialised:
+//   warp 0    TMA producer   -- cp.async.bulk.tensor loads of the hi and lo bf16 planes of the A and B
+//                               tiles into a multi-stage shared-memory ring (hardware swizzle)
+//   warp 1    MMA issuer     -- one thread issues tcgen05.mma (M=128, N<=256, K=16, bf16 x bf16 -> fp32
+//                               in TMEM); per K-step THREE products: Ahi*Bhi + Ahi*Blo + Alo*Bhi, which
+//                               reproduces an fp32 product to ~2^-17 relative (error budget)
+//   warp 2    TMEM allocator -- 2 accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1
+//   warps 4-11 epilogue      -- two warps per TMEM lane quarter, alternating 32-column chunks:
+//                               tcgen05.ld -> registers -> fused epilogue -> global memory
 //
-// A may be K-major (rows of K contiguous) or MN-major (the M index contiguous: activations in NCHW seen
-// as [channel][space]); B is K-major.  Out-of-range parts of any tile are zero-filled by TMA, so M, N, K
-// need no padding; only 16-byte alignment of the strides is required (umma_eligible()).
+// Operand layouts: A and B may each be K-major (rows of K contiguous; 64-byte swizzle, BK = 32) or
+// MN-major (the M / N index contiguous: activations seen as [channel][space]; 128-byte swizzle atoms of
+// 64 elements).  Out-of-range parts of any tile are zero-filled by TMA, so M, N, K need no padding.
+//
+// Epilogue shapes (compile-time; everything else goes to the SIMT kernel):
+//   ROWC  output rows contiguous in memory (o_m0 == 1): thread = accumulator row, each column is a
+//         lane-coalesced 2-byte store per plane.  Used by the transposing stages of the SHT
+//         (DFT -> m-major, Legendre -> l-major, dhconv -> m-major).  Split-plane output only.
+//   NC    output columns contiguous (o_n == 1 / f_n == 1, rows affine): the 32x32 chunk a warp holds
+//         (thread = row) is transposed through a 4 KB per-warp shared-memory tile so that global loads of
+//         the fp32 addend / split-plane residual and the stores are 64-128 B coalesced per row.
+//         Compile-time flags: ADD_F32, RES_PLANES, GELU, OUT_PLANES | OUT_F32; run-time: ROW_BIAS,
+//         ROW_STATS (per-row = per-channel InstanceNorm sums, thread-local then two fp64 atomics per tile).
 //
 // Triangular ops (gemm.cuh): the N extent of the MMA shrinks to the non-zero column range of the tile
 // (UMMA N is a runtime field of the instruction descriptor) and K-chunks below k_lo are skipped.
@@ -35,39 +44,57 @@ struct UmmaParams {
   int tiles_m, tiles_n;
   int nterms;
   int a_z1_on, a_z2_on, b_z1_on, b_z2_on;  // 0 when the operand does not vary along that batch axis
+  int m_fastest;                           // tile order: consecutive tiles share the B (1) or the A (0) tile
 };
 
-template <int BN_, int BK_, bool A_MN_>
+constexpr uint32_t EF_MASK = EPI_ADD_F32 | EPI_RES_PLANES | EPI_GELU | EPI_OUT_PLANES | EPI_OUT_F32;
+constexpr int kEpiWarps = 8;
+constexpr int kThreadsUmma = 32 * (4 + kEpiWarps);
+constexpr int kStgBytesPerWarp = 4096;
+constexpr int kMaxSmem = 232448;  // 227 KB opt-in limit per CTA
+
+template <int BN_, bool A_MN_, bool B_MN_, uint32_t EF_, bool NC_>
 struct Cfg {
-  static constexpr int BM = 128, BN = BN_, BK = BK_;
-  static constexpr bool A_MN = A_MN_;
+  static constexpr int BM = 128, BN = BN_, BK = 32;
+  static constexpr bool A_MN = A_MN_, B_MN = B_MN_, NC = NC_;
+  static constexpr uint32_t EF = EF_;
   static constexpr int UMMA_K = 16;
   static constexpr int A_PLANE = BM * BK * 2;  // bytes
   static constexpr int B_PLANE = BN * BK * 2;
   static constexpr int STAGE = 2 * (A_PLANE + B_PLANE);
-  static constexpr int STAGES = (200 * 1024) / STAGE;
+  static constexpr int STG_BYTES = NC ? kEpiWarps * kStgBytesPerWarp : 0;
+  static constexpr int MAX_STAGES = 8;
+  static constexpr int BAR_BYTES = (2 * MAX_STAGES + 4) * 8 + 16;
+  static constexpr int STAGES_RAW = (kMaxSmem - 1024 - STG_BYTES - BAR_BYTES) / STAGE;
+  static constexpr int STAGES = STAGES_RAW > MAX_STAGES ? MAX_STAGES : STAGES_RAW;
   static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
-  static constexpr int K_SWZ_BYTES = BK * 2;                        // swizzle span of K-major tiles
-  static constexpr uint32_t K_LAYOUT = (K_SWZ_BYTES == 128) ? 2u : 4u;  // UMMA layout code
-  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-  static constexpr int SMEM_BYTES = STAGES * STAGE + BAR_BYTES + 1024;  // + alignment slack
-  static_assert(BK == 64 || BK == 32, "BK");
-  static_assert(BN % 32 == 0 && BN <= 256, "BN");
-  static_assert(STAGES >= 2, "pipeline too shallow");
+  static constexpr int SMEM_BYTES = STAGES * STAGE + STG_BYTES + BAR_BYTES + 1024;  // + alignment slack
+  static_assert(BN % 64 == 0 && BN <= 256, "BN");
+  static_assert(STAGES >= 3, "pipeline too shallow");
   static_assert(A_PLANE % 1024 == 0 && B_PLANE % 1024 == 0, "tiles must keep 1024B alignment");
+  static_assert(SMEM_BYTES <= kMaxSmem, "shared memory budget");
 };
 
 struct Tile {
-  int m0, n_begin, n_count, n_lo, n_end, z1, z2, k_begin, num_kc;
+  int m0, n_begin, n_count, n_end, z1, z2, k_begin, num_kc;
 };
 
 template <int BN, int BK>
 __device__ __forceinline__ bool decode_tile(const UmmaParams& p, long long t, Tile& ti) {
   const GemmOp& op = p.op;
-  int tn = (int)(t % p.tiles_n);
-  long long r = t / p.tiles_n;
-  int tm = (int)(r % p.tiles_m);
-  r /= p.tiles_m;
+  int tn, tm;
+  long long r;
+  if (p.m_fastest) {
+    tm = (int)(t % p.tiles_m);
+    r = t / p.tiles_m;
+    tn = (int)(r % p.tiles_n);
+    r /= p.tiles_n;
+  } else {
+    tn = (int)(t % p.tiles_n);
+    r = t / p.tiles_n;
+    tm = (int)(r % p.tiles_m);
+    r /= p.tiles_m;
+  }
   ti.z2 = (int)(r % op.Z2);
   ti.z1 = (int)(r / op.Z2);
   const int n_lo = op.n_lo_z1 ? ti.z1 : 0;
@@ -76,22 +103,215 @@ __device__ __forceinline__ bool decode_tile(const UmmaParams& p, long long t, Ti
   ti.m0 = tm * 128;
   ti.n_begin = max(tn * BN, (n_lo / 16) * 16);
   ti.n_end = min(tn * BN + BN, n_hi);
-  ti.n_lo = n_lo;
   ti.n_count = ti.n_end - ti.n_begin;
   ti.k_begin = (k_lo / BK) * BK;
   ti.num_kc = (op.K - ti.k_begin + BK - 1) / BK;
   return ti.n_count > 0 && ti.n_end > n_lo && ti.num_kc > 0;
 }
 
+// ---- epilogue: ROWC (lane = row, rows contiguous in memory), split-plane output only ----
 template <class C>
-__global__ void __launch_bounds__(256, 1) gemm_umma_kernel(const __grid_constant__ UmmaParams p) {
+__device__ __forceinline__ void epilogue_rowc(const UmmaParams& p, const Tile& ti, uint32_t tacc, int q, int half,
+                                              int lane) {
+  const GemmOp& op = p.op;
+  const EpiParams& e = op.epi;
+  const int row = ti.m0 + 32 * q + lane;
+  const bool row_ok = row < op.M;
+  const int m1 = row / e.mdiv, mr = row - m1 * e.mdiv;
+  bf16* base = e.out + (long long)ti.z1 * e.o_z1 + (long long)ti.z2 * e.o_z2 + (long long)m1 * e.o_m1 +
+               (long long)mr * e.o_m0 + (long long)ti.n_begin * e.o_n;
+  const long long on = e.o_n, plane = e.out_plane;
+  for (int c = half; c * 32 < ti.n_count; c += 2) {
+    float v[32];
+    ptx::tmem_ld_32x32(tacc + c * 32, v);
+    ptx::tmem_ld_wait();
+    bf16* h = base + (long long)(c * 32) * on;
+    bf16* l = h + plane;
+    const int nleft = ti.n_count - c * 32;  // columns of this chunk inside [n_begin, n_end)
+    if (row_ok) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (j < nleft) {
+          bf16 hi, lo;
+          split_bf16(v[j], hi, lo);
+          *h = hi;
+          *l = lo;
+        }
+        h += on;
+        l += on;
+      }
+    }
+  }
+}
+
+// ---- epilogue: NC (thread = row, columns contiguous in memory, transposed through shared memory) ----
+// staging tile of one warp: fp32 view [32 rows][8 x 16 B] (swizzle p ^ (r & 7)) or two split-plane views
+// [32 rows][8 x 8 B] (swizzle p ^ ((r >> 1) & 7)), hi at +0, lo at +2048 B.
+__device__ __forceinline__ int swz16(int r, int p) { return r * 8 + (p ^ (r & 7)); }
+__device__ __forceinline__ int swz8(int r, int p) { return r * 8 + (p ^ ((r >> 1) & 7)); }
+
+template <class C>
+__device__ __forceinline__ void epilogue_nc(const UmmaParams& p, const Tile& ti, uint32_t tacc, int q, int half, int lane,
+                                            uint8_t* stg_raw) {
+  constexpr uint32_t EF = C::EF;
+  const GemmOp& op = p.op;
+  const EpiParams& e = op.epi;
+  uint4* stg16 = reinterpret_cast<uint4*>(stg_raw);
+  uint2* stg8 = reinterpret_cast<uint2*>(stg_raw);
+  const int row0 = ti.m0 + 32 * q;  // first row of this warp
+  const int row = row0 + lane;
+  const bool row_ok = row < op.M;
+  const bool do_stats = (e.flags & EPI_ROW_STATS) != 0;
+  float rbias = 0.f;
+  if ((e.flags & EPI_ROW_BIAS) && row_ok) rbias = __ldg(e.row_bias + (long long)ti.z2 * e.rb_z2 + row);
+  float ssum = 0.f, ssq = 0.f;
+  // cooperative (transposed) access: lane -> (row r = it*4 + lane/8, 4-element piece pc = lane%8)
+  const int cr = lane >> 3, pc = lane & 7;
+
+  for (int c = half; c * 32 < ti.n_count; c += 2) {
+    const int n0 = ti.n_begin + c * 32;
+    const int nvalid = min(32, ti.n_end - n0);  // multiple of 4 (host-checked)
+    float v[32];
+    ptx::tmem_ld_32x32(tacc + c * 32, v);
+    ptx::tmem_ld_wait();
+    const bool pc_ok = pc * 4 < nvalid;
+
+    if (EF & EPI_ADD_F32) {
+      const float* g = e.add + (long long)ti.z2 * e.add_z2 + (long long)(row0 + cr) * e.add_m0 + n0 + pc * 4;
+      const long long step = 4 * e.add_m0;
+      uint4 t[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        t[it] = make_uint4(0u, 0u, 0u, 0u);
+        if (pc_ok && row0 + it * 4 + cr < op.M) t[it] = __ldg(reinterpret_cast<const uint4*>(g + it * step));
+      }
+#pragma unroll
+      for (int it = 0; it < 8; ++it) stg16[swz16(it * 4 + cr, pc)] = t[it];
+      __syncwarp();
+#pragma unroll
+      for (int pp = 0; pp < 8; ++pp) {
+        uint4 w = stg16[swz16(lane, pp)];
+        v[4 * pp + 0] += __uint_as_float(w.x);
+        v[4 * pp + 1] += __uint_as_float(w.y);
+        v[4 * pp + 2] += __uint_as_float(w.z);
+        v[4 * pp + 3] += __uint_as_float(w.w);
+      }
+      __syncwarp();
+    }
+    if (EF & EPI_RES_PLANES) {
+      const bf16* g = e.res + (long long)ti.z2 * e.res_z2 + (long long)(row0 + cr) * e.res_m0 + n0 + pc * 4;
+      const long long step = 4 * e.res_m0;
+      uint2 th[8], tl[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        th[it] = tl[it] = make_uint2(0u, 0u);
+        if (pc_ok && row0 + it * 4 + cr < op.M) {
+          th[it] = __ldg(reinterpret_cast<const uint2*>(g + it * step));
+          tl[it] = __ldg(reinterpret_cast<const uint2*>(g + it * step + e.res_plane));
+        }
+      }
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        stg8[swz8(it * 4 + cr, pc)] = th[it];
+        stg8[256 + swz8(it * 4 + cr, pc)] = tl[it];
+      }
+      __syncwarp();
+#pragma unroll
+      for (int pp = 0; pp < 8; ++pp) {
+        uint2 a = stg8[swz8(lane, pp)], b = stg8[256 + swz8(lane, pp)];
+        // bf16 -> fp32 is a 16-bit shift; element 2i sits in the low half of word i
+        v[4 * pp + 0] += __uint_as_float(a.x << 16) + __uint_as_float(b.x << 16);
+        v[4 * pp + 1] += __uint_as_float(a.x & 0xffff0000u) + __uint_as_float(b.x & 0xffff0000u);
+        v[4 * pp + 2] += __uint_as_float(a.y << 16) + __uint_as_float(b.y << 16);
+        v[4 * pp + 3] += __uint_as_float(a.y & 0xffff0000u) + __uint_as_float(b.y & 0xffff0000u);
+      }
+      __syncwarp();
+    }
+
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float x = v[j] + rbias;
+      if (EF & EPI_GELU) x = gelu_erf(x);
+      v[j] = x;
+    }
+    if (do_stats && row_ok) {
+      if (nvalid == 32) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          ssum += v[j];
+          ssq = fmaf(v[j], v[j], ssq);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < nvalid) {
+            ssum += v[j];
+            ssq = fmaf(v[j], v[j], ssq);
+          }
+      }
+    }
+
+    if (EF & EPI_OUT_F32) {
+#pragma unroll
+      for (int pp = 0; pp < 8; ++pp)
+        stg16[swz16(lane, pp)] = make_uint4(__float_as_uint(v[4 * pp]), __float_as_uint(v[4 * pp + 1]),
+                                            __float_as_uint(v[4 * pp + 2]), __float_as_uint(v[4 * pp + 3]));
+      __syncwarp();
+      float* g = e.outf + (long long)ti.z1 * e.f_z1 + (long long)ti.z2 * e.f_z2 + (long long)(row0 + cr) * e.f_m0 + n0 + pc * 4;
+      const long long step = 4 * e.f_m0;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        uint4 w = stg16[swz16(it * 4 + cr, pc)];
+        if (pc_ok && row0 + it * 4 + cr < op.M) *reinterpret_cast<uint4*>(g + it * step) = w;
+      }
+      __syncwarp();
+    }
+    if (EF & EPI_OUT_PLANES) {
+#pragma unroll
+      for (int pp = 0; pp < 8; ++pp) {
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float x = v[4 * pp + i];
+          const bf16 hi = __float2bfloat16_rn(x);
+          const bf16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+          hw[i] = (uint32_t)__bfloat16_as_ushort(hi);
+          lw[i] = (uint32_t)__bfloat16_as_ushort(lo);
+        }
+        stg8[swz8(lane, pp)] = make_uint2(hw[0] | (hw[1] << 16), hw[2] | (hw[3] << 16));
+        stg8[256 + swz8(lane, pp)] = make_uint2(lw[0] | (lw[1] << 16), lw[2] | (lw[3] << 16));
+      }
+      __syncwarp();
+      bf16* g = e.out + (long long)ti.z1 * e.o_z1 + (long long)ti.z2 * e.o_z2 + (long long)(row0 + cr) * e.o_m0 + n0 + pc * 4;
+      const long long step = 4 * e.o_m0;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        uint2 a = stg8[swz8(it * 4 + cr, pc)], b = stg8[256 + swz8(it * 4 + cr, pc)];
+        if (pc_ok && row0 + it * 4 + cr < op.M) {
+          *reinterpret_cast<uint2*>(g + it * step) = a;
+          *reinterpret_cast<uint2*>(g + it * step + e.out_plane) = b;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  if (do_stats && row_ok) {
+    double* st = e.stats + ((long long)ti.z2 * e.stats_z2 + row) * 2;
+    atomicAdd(st, (double)ssum);
+    atomicAdd(st + 1, (double)ssq);
+  }
+}
+
+template <class C>
+__global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid_constant__ UmmaParams p) {
   constexpr int BN = C::BN, BK = C::BK, STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
-  const uint32_t sbase = (raw + 1023u) & ~1023u;  // 128B swizzle atoms need 1024B alignment
+  const uint32_t sbase = (raw + 1023u) & ~1023u;  // swizzle atoms need 1024B alignment
   uint8_t* smem = smem_raw + (sbase - raw);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE);
-  const uint32_t bar0 = sbase + STAGES * C::STAGE;
+  uint8_t* stg_all = smem + STAGES * C::STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_all + C::STG_BYTES);
+  const uint32_t bar0 = sbase + STAGES * C::STAGE + C::STG_BYTES;
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
@@ -112,7 +332,7 @@ __global__ void __launch_bounds__(256, 1) gemm_umma_kernel(const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(tfull_bar(a), 1);
-      ptx::mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+      ptx::mbar_init(tempty_bar(a), kEpiWarps);  // one arrive per epilogue warp
     }
     ptx::fence_barrier_init();
   }
@@ -147,11 +367,18 @@ __global__ void __launch_bounds__(256, 1) gemm_umma_kernel(const __grid_constant
           if (!C::A_MN) {
             ptx::tma_load_5d(sA + pl * C::A_PLANE, &p.tmA, fb, k0, ti.m0, az1, az2, pl);
           } else {
-            // two 64-wide M atoms, each [BK rows][128 B]
-            ptx::tma_load_5d(sA + pl * C::A_PLANE, &p.tmA, fb, ti.m0, k0, az1, az2, pl);
-            ptx::tma_load_5d(sA + pl * C::A_PLANE + BK * 128, &p.tmA, fb, ti.m0 + 64, k0, az1, az2, pl);
+            // 64-wide MN atoms, each [BK rows][128 B]
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+              ptx::tma_load_5d(sA + pl * C::A_PLANE + a * BK * 128, &p.tmA, fb, ti.m0 + 64 * a, k0, az1, az2, pl);
           }
-          ptx::tma_load_5d(sB + pl * C::B_PLANE, &p.tmB, fb, k0, ti.n_begin, bz1, bz2, pl);
+          if (!C::B_MN) {
+            ptx::tma_load_5d(sB + pl * C::B_PLANE, &p.tmB, fb, k0, ti.n_begin, bz1, bz2, pl);
+          } else {
+#pragma unroll
+            for (int a = 0; a < BN / 64; ++a)
+              ptx::tma_load_5d(sB + pl * C::B_PLANE + a * BK * 128, &p.tmB, fb, ti.n_begin + 64 * a, k0, bz1, bz2, pl);
+          }
         }
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
@@ -168,7 +395,7 @@ __global__ void __launch_bounds__(256, 1) gemm_umma_kernel(const __grid_constant
       ptx::mbar_wait(tempty_bar(as), aph ^ 1u);
       ptx::tc_fence_after();
       const int n_eff = (ti.n_count + 15) & ~15;
-      const uint32_t idesc = ptx::instr_desc_bf16(128, n_eff, C::A_MN ? 1 : 0, 0);
+      const uint32_t idesc = ptx::instr_desc_bf16(128, n_eff, C::A_MN ? 1 : 0, C::B_MN ? 1 : 0);
       const uint32_t tmem_d = tmem_base + as * BN;
       for (int kc = 0; kc < ti.num_kc; ++kc) {
         ptx::mbar_wait(full_bar(stage), phase);
@@ -177,19 +404,17 @@ __global__ void __launch_bounds__(256, 1) gemm_umma_kernel(const __grid_constant
         const uint32_t sB = sA + 2 * C::A_PLANE;
 #pragma unroll
         for (int kk = 0; kk < BK / 16; ++kk) {
-          uint64_t a_hi, a_lo;
-          if (!C::A_MN) {
-            // K-major: rows of BK*2 bytes, 8-row groups SBO apart; K-step = 32 bytes inside the swizzled row
-            a_hi = ptx::smem_desc(sA + kk * 32, 0, 8 * C::K_SWZ_BYTES, C::K_LAYOUT);
-            a_lo = ptx::smem_desc(sA + C::A_PLANE + kk * 32, 0, 8 * C::K_SWZ_BYTES, C::K_LAYOUT);
-          } else {
-            // MN-major, 128B swizzle: [k][64 m] atoms; 8-k groups SBO = 1024 B apart, the second 64-m atom
-            // LBO = BK*128 B away; one K-step = 16 k-rows = 2048 B
-            a_hi = ptx::smem_desc(sA + kk * 2048, BK * 128, 1024, 2u);
-            a_lo = ptx::smem_desc(sA + C::A_PLANE + kk * 2048, BK * 128, 1024, 2u);
-          }
-          const uint64_t b_hi = ptx::smem_desc(sB + kk * 32, 0, 8 * C::K_SWZ_BYTES, C::K_LAYOUT);
-          const uint64_t b_lo = ptx::smem_desc(sB + C::B_PLANE + kk * 32, 0, 8 * C::K_SWZ_BYTES, C::K_LAYOUT);
+          // K-major (64B swizzle, BK = 32): rows of 64 bytes, 8-row groups SBO = 512 B apart; a K-step is 32
+          // bytes inside the swizzled row.  MN-major (128B swizzle): [k][64 mn] atoms, 8-k groups SBO = 1024 B
+          // apart, the next 64-mn atom LBO = BK*128 B away; a K-step is 16 k-rows = 2048 B.
+          const uint64_t a_hi = C::A_MN ? ptx::smem_desc(sA + kk * 2048, BK * 128, 1024, 2u)
+                                        : ptx::smem_desc(sA + kk * 32, 0, 8 * BK * 2, 4u);
+          const uint64_t a_lo = C::A_MN ? ptx::smem_desc(sA + C::A_PLANE + kk * 2048, BK * 128, 1024, 2u)
+                                        : ptx::smem_desc(sA + C::A_PLANE + kk * 32, 0, 8 * BK * 2, 4u);
+          const uint64_t b_hi = C::B_MN ? ptx::smem_desc(sB + kk * 2048, BK * 128, 1024, 2u)
+                                        : ptx::smem_desc(sB + kk * 32, 0, 8 * BK * 2, 4u);
+          const uint64_t b_lo = C::B_MN ? ptx::smem_desc(sB + C::B_PLANE + kk * 2048, BK * 128, 1024, 2u)
+                                        : ptx::smem_desc(sB + C::B_PLANE + kk * 32, 0, 8 * BK * 2, 4u);
           ptx::umma_bf16(tmem_d, a_hi, b_hi, idesc, (kc | kk) != 0 ? 1u : 0u);
           if (p.nterms == 3) {
             ptx::umma_bf16(tmem_d, a_hi, b_lo, idesc, 1u);
@@ -204,8 +429,9 @@ __global__ void __launch_bounds__(256, 1) gemm_umma_kernel(const __grid_constant
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int q = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may access
-    const EpiParams& e = op.epi;
+    const int q = warp & 3;          // TMEM lane quarter this warp may access (warp id % 4)
+    const int half = (warp - 4) >> 2;  // which of the two warps of the quarter
+    uint8_t* stg = stg_all + (warp - 4) * kStgBytesPerWarp;
     uint32_t it = 0;
     Tile ti;
     for (long long t = blockIdx.x; t < total; t += gridDim.x) {
@@ -213,70 +439,9 @@ __global__ void __launch_bounds__(256, 1) gemm_umma_kernel(const __grid_constant
       const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
       ptx::mbar_wait(tfull_bar(as), aph);
       ptx::tc_fence_after();
-      const int row = ti.m0 + 32 * q + lane;
-      const bool row_ok = row < op.M;
-      const int m1 = row / e.mdiv, mr = row % e.mdiv;
-      const long long off_add = (long long)ti.z2 * e.add_z2 + (long long)m1 * e.add_m1 + (long long)mr * e.add_m0;
-      const long long off_res = (long long)ti.z2 * e.res_z2 + (long long)m1 * e.res_m1 + (long long)mr * e.res_m0;
-      const long long off_out = (long long)ti.z1 * e.o_z1 + (long long)ti.z2 * e.o_z2 + (long long)m1 * e.o_m1 + (long long)mr * e.o_m0;
-      const long long off_f = (long long)ti.z1 * e.f_z1 + (long long)ti.z2 * e.f_z2 + (long long)m1 * e.f_m1 + (long long)mr * e.f_m0;
-      const float* bias = e.col_bias + (long long)ti.z2 * e.cb_z2;
-      const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(32 * q) << 16);
-      for (int c0 = 0; c0 < ti.n_count; c0 += 32) {
-        float v[32];
-        ptx::tmem_ld_32x32(taddr + c0, v);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = ti.n_begin + c0 + j;
-          const bool ok = row_ok && n >= ti.n_lo && n < ti.n_end;
-          float x = v[j];
-          if (ok) {
-            if (e.flags & EPI_COL_BIAS) x += __ldg(bias + n);
-            if (e.flags & EPI_ADD_F32) x += __ldg(e.add + off_add + (long long)n * e.add_n);
-            if (e.flags & EPI_RES_PLANES) {
-              const bf16* r = e.res + off_res + (long long)n * e.res_n;
-              x += __bfloat162float(r[0]) + __bfloat162float(r[e.res_plane]);
-            }
-            if (e.flags & EPI_GELU) x = gelu_erf(x);
-            if (e.flags & EPI_OUT_PLANES) {
-              bf16 hi, lo;
-              split_bf16(x, hi, lo);
-              bf16* o = e.out + off_out + (long long)n * e.o_n;
-              o[0] = hi;
-              o[e.out_plane] = lo;
-            }
-            if (e.flags & EPI_OUT_F32) e.outf[off_f + (long long)n * e.f_n] = x;
-          } else {
-            x = 0.f;
-          }
-          v[j] = x;
-        }
-        if (e.flags & EPI_STATS) {
-          // per-column sums over this warp's 32 rows: butterfly transpose-reduce, 31 shuffles per quantity;
-          // afterwards lane j holds the total of column c0 + j
-          float s[32], sq[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) { s[j] = v[j]; sq[j] = v[j] * v[j]; }
-#pragma unroll
-          for (int w = 16; w >= 1; w >>= 1) {
-            const bool up = (lane & w) != 0;
-#pragma unroll
-            for (int j = 0; j < w; ++j) {
-              float keep = up ? s[j + w] : s[j], send = up ? s[j] : s[j + w];
-              s[j] = keep + __shfl_xor_sync(0xffffffffu, send, w);
-              float keepq = up ? sq[j + w] : sq[j], sendq = up ? sq[j] : sq[j + w];
-              sq[j] = keepq + __shfl_xor_sync(0xffffffffu, sendq, w);
-            }
-          }
-          const int n = ti.n_begin + c0 + lane;
-          if (n >= ti.n_lo && n < ti.n_end) {
-            double* st = e.stats + ((long long)ti.z2 * e.stats_z2 + n) * 2;
-            atomicAdd(st, (double)s[0]);
-            atomicAdd(st + 1, (double)sq[0]);
-          }
-        }
-      }
+      const uint32_t tacc = tmem_base + as * BN + ((uint32_t)(32 * q) << 16);
+      if constexpr (C::NC) epilogue_nc<C>(p, ti, tacc, q, half, lane, stg);
+      else epilogue_rowc<C>(p, ti, tacc, q, half, lane);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
@@ -368,74 +533,156 @@ void launch(const GemmOp& op, cudaStream_t stream) {
   p.tiles_m = (op.M + 127) / 128;
   p.tiles_n = (op.N + C::BN - 1) / C::BN;
   p.nterms = options().split_terms;
-  const bool a_mn = C::A_MN;
-  const CUtensorMapSwizzle kswz = (C::K_SWZ_BYTES == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-  if (!a_mn)
-    make_tmap(&p.tmA, op.A, false, op.M, op.K, op.Z1, op.Z2, C::BK, 128, kswz, &p.a_z1_on, &p.a_z2_on, op.name);
+  // the operand that is re-read by neighbouring tiles should be the small one: keep the big streaming operand's
+  // tile shared by consecutive CTAs (they run concurrently, so the second reader hits L2)
+  p.m_fastest = C::B_MN ? 1 : 0;
+  if (!C::A_MN)
+    make_tmap(&p.tmA, op.A, false, op.M, op.K, op.Z1, op.Z2, C::BK, 128, CU_TENSOR_MAP_SWIZZLE_64B, &p.a_z1_on, &p.a_z2_on, op.name);
   else
     make_tmap(&p.tmA, op.A, true, op.M, op.K, op.Z1, op.Z2, 64, C::BK, CU_TENSOR_MAP_SWIZZLE_128B, &p.a_z1_on, &p.a_z2_on, op.name);
-  make_tmap(&p.tmB, op.B, false, op.N, op.K, op.Z1, op.Z2, C::BK, C::BN, kswz, &p.b_z1_on, &p.b_z2_on, op.name);
+  if (!C::B_MN)
+    make_tmap(&p.tmB, op.B, false, op.N, op.K, op.Z1, op.Z2, C::BK, C::BN, CU_TENSOR_MAP_SWIZZLE_64B, &p.b_z1_on, &p.b_z2_on, op.name);
+  else
+    make_tmap(&p.tmB, op.B, true, op.N, op.K, op.Z1, op.Z2, 64, C::BK, CU_TENSOR_MAP_SWIZZLE_128B, &p.b_z1_on, &p.b_z2_on, op.name);
   long long total = (long long)p.tiles_m * p.tiles_n * op.Z1 * op.Z2;
   int grid = (int)std::min<long long>(total, sm_count());
-  gemm_umma_kernel<C><<<grid, 256, C::SMEM_BYTES, stream>>>(p);
+  gemm_umma_kernel<C><<<grid, kThreadsUmma, C::SMEM_BYTES, stream>>>(p);
   after_launch(op.name);
   g_umma_count.fetch_add(1, std::memory_order_relaxed);
 }
 
-template <int BK, bool A_MN>
-void launch_bn(const GemmOp& op, int bn, cudaStream_t stream) {
-  switch (bn) {
-    case 128: launch<Cfg<128, BK, A_MN>>(op, stream); break;
-    case 192: launch<Cfg<192, BK, A_MN>>(op, stream); break;
-    default: launch<Cfg<256, BK, A_MN>>(op, stream); break;
-  }
-}
-
 bool aligned8(long long v) { return (v & 7) == 0; }
+bool aligned4(long long v) { return (v & 3) == 0; }
 
-}  // namespace
+// ---- which compiled variant (if any) serves this op ----
+struct Variant {
+  bool a_mn, b_mn, nc;
+  uint32_t ef;
+};
 
-bool umma_eligible(const GemmOp& op, const char** why) {
+bool classify(const GemmOp& op, Variant& v, const char** why) {
   auto fail = [&](const char* w) {
     if (why) *why = w;
     return false;
   };
-  if (op.B.s_k != 1) return fail("B is not K-major");
-  const bool a_k = op.A.s_k == 1, a_mn = op.A.s_row == 1;
+  const bool a_k = op.A.s_k == 1, a_mn = op.A.s_row == 1 && !a_k;
+  const bool b_k = op.B.s_k == 1, b_mn = op.B.s_row == 1 && !b_k;
   if (!a_k && !a_mn) return fail("A is neither K-major nor MN-major");
+  if (!b_k && !b_mn) return fail("B is neither K-major nor MN-major");
   if (a_k && !aligned8(op.A.s_row)) return fail("A row stride not 16B aligned");
-  if (!a_k && !aligned8(op.A.s_k)) return fail("A k stride not 16B aligned");
-  if (!aligned8(op.B.s_row)) return fail("B row stride not 16B aligned");
+  if (a_mn && !aligned8(op.A.s_k)) return fail("A k stride not 16B aligned");
+  if (b_k && !aligned8(op.B.s_row)) return fail("B row stride not 16B aligned");
+  if (b_mn && !aligned8(op.B.s_k)) return fail("B k stride not 16B aligned");
   if (!aligned8(op.A.plane) || !aligned8(op.B.plane)) return fail("plane offset not 16B aligned");
   if (!aligned8(op.A.s_z1) || !aligned8(op.A.s_z2) || !aligned8(op.B.s_z1) || !aligned8(op.B.s_z2)) return fail("batch stride not 16B aligned");
   if ((((uintptr_t)op.A.ptr) & 15) || (((uintptr_t)op.B.ptr) & 15)) return fail("base pointer not 16B aligned");
   if (op.M < 1 || op.N < 1 || op.K < 1) return fail("empty");
   if (op.A.plane <= 0 || op.B.plane <= 0) return fail("plane offset must be positive");
+  const EpiParams& e = op.epi;
+  const uint32_t f = e.flags;
+  if (f & (EPI_COL_BIAS | EPI_STATS)) return fail("column bias / column statistics are SIMT-only");
+  v.a_mn = a_mn;
+  v.b_mn = b_mn;
+  v.ef = f & EF_MASK;
+  const bool planes = (f & EPI_OUT_PLANES) != 0, f32 = (f & EPI_OUT_F32) != 0;
+  if (planes == f32) return fail("exactly one of OUT_PLANES / OUT_F32 is supported");
+  // ROWC: split-plane output with contiguous rows, nothing else
+  if (v.ef == EPI_OUT_PLANES && !(f & (EPI_ROW_BIAS | EPI_ROW_STATS)) && e.o_m0 == 1 && e.o_n != 1) {
+    v.nc = false;
+    return true;
+  }
+  // NC: columns contiguous, rows affine, everything 4-element aligned
+  v.nc = true;
+  if (e.mdiv < op.M) return fail("NC epilogue needs affine rows (mdiv >= M)");
+  if (!aligned4(op.N)) return fail("NC epilogue needs N % 4 == 0");
+  if (op.n_lo_z1 || op.n_hi_z1) return fail("NC epilogue does not take triangular N ranges");
+  if (planes) {
+    if (e.o_n != 1 || !aligned4(e.o_m0) || !aligned4(e.o_z1) || !aligned4(e.o_z2) || !aligned4(e.out_plane) || (((uintptr_t)e.out) & 7))
+      return fail("plane output not 8B-vectorisable");
+  } else {
+    if (e.f_n != 1 || !aligned4(e.f_m0) || !aligned4(e.f_z1) || !aligned4(e.f_z2) || (((uintptr_t)e.outf) & 15))
+      return fail("fp32 output not 16B-vectorisable");
+  }
+  if (f & EPI_ADD_F32) {
+    if (e.add_n != 1 || e.add_m1 != 0 || !aligned4(e.add_m0) || !aligned4(e.add_z2) || (((uintptr_t)e.add) & 15))
+      return fail("fp32 addend not 16B-vectorisable");
+  }
+  if (f & EPI_RES_PLANES) {
+    if (e.res_n != 1 || e.res_m1 != 0 || !aligned4(e.res_m0) || !aligned4(e.res_z2) || !aligned4(e.res_plane) || (((uintptr_t)e.res) & 7))
+      return fail("plane residual not 8B-vectorisable");
+  }
   return true;
 }
 
+constexpr uint32_t P = EPI_OUT_PLANES, F = EPI_OUT_F32, G = EPI_GELU, AD = EPI_ADD_F32, RS = EPI_RES_PLANES;
+
+template <int BN>
+bool launch_variant(const GemmOp& op, const Variant& v, cudaStream_t s) {
+  if (!v.nc) {
+    if (!v.a_mn && !v.b_mn) { launch<Cfg<BN, false, false, P, false>>(op, s); return true; }
+    return false;
+  }
+  if (v.a_mn && !v.b_mn) {  // inverse SHT stages
+    if (v.ef == P) { launch<Cfg<BN, true, false, P, true>>(op, s); return true; }
+    if (v.ef == F) { launch<Cfg<BN, true, false, F, true>>(op, s); return true; }
+    return false;
+  }
+  if (!v.a_mn && !v.b_mn) {  // generic K-major x K-major with contiguous columns (tests, forward SHT variants)
+    if (v.ef == P) { launch<Cfg<BN, false, false, P, true>>(op, s); return true; }
+    if (v.ef == F) { launch<Cfg<BN, false, false, F, true>>(op, s); return true; }
+    return false;
+  }
+  return false;
+}
+
+// 1x1 convolutions: weights (K-major) x activations (MN-major), BN = 256
+bool launch_conv(const GemmOp& op, const Variant& v, cudaStream_t s) {
+  if (!v.nc || v.a_mn || !v.b_mn) return false;
+  switch (v.ef) {
+    case G | P: launch<Cfg<256, false, true, G | P, true>>(op, s); return true;
+    case AD | F: launch<Cfg<256, false, true, AD | F, true>>(op, s); return true;
+    case AD | G | F: launch<Cfg<256, false, true, AD | G | F, true>>(op, s); return true;
+    case RS | F: launch<Cfg<256, false, true, RS | F, true>>(op, s); return true;
+    case RS | P: launch<Cfg<256, false, true, RS | P, true>>(op, s); return true;
+    case F: launch<Cfg<256, false, true, F, true>>(op, s); return true;
+    case P: launch<Cfg<256, false, true, P, true>>(op, s); return true;
+    case G | F: launch<Cfg<256, false, true, G | F, true>>(op, s); return true;
+    default: return false;
+  }
+}
+
+bool dispatch(const GemmOp& op, bool dry, cudaStream_t s, const char** why) {
+  Variant v;
+  if (!classify(op, v, why)) return false;
+  if (v.b_mn) {
+    if (v.a_mn) { if (why) *why = "MN-major x MN-major is not compiled"; return false; }
+    static const uint32_t ok[] = {G | P, AD | F, AD | G | F, RS | F, RS | P, F, P, G | F};
+    bool found = false;
+    for (uint32_t x : ok) found |= (x == v.ef);
+    if (!v.nc || !found) { if (why) *why = "epilogue combination not compiled for MN-major B"; return false; }
+    if (!dry) launch_conv(op, v, s);
+    return true;
+  }
+  const bool ok = (!v.nc && !v.a_mn) || (v.nc && (v.ef == P || v.ef == F));
+  if (!ok) { if (why) *why = "epilogue combination not compiled for K-major B"; return false; }
+  if (dry) return true;
+  // N tile: least padded columns, ties to the larger tile
+  int bn = options().umma_bn;
+  if (bn != 192 && bn != 256) {
+    long long w192 = (op.N + 191) / 192 * 192 - op.N, w256 = (op.N + 255) / 256 * 256 - op.N;
+    bn = (w192 < w256) ? 192 : 256;
+  }
+  return bn == 192 ? launch_variant<192>(op, v, s) : launch_variant<256>(op, v, s);
+}
+
+}  // namespace
+
+bool umma_eligible(const GemmOp& op, const char** why) { return dispatch(op, true, nullptr, why); }
+
 void run_gemm_umma(const GemmOp& op, cudaStream_t stream) {
   const char* why = nullptr;
-  ACE_REQUIRE(umma_eligible(op, &why), "gemm %s: not eligible for the tcgen05 kernel: %s", op.name, why);
-  // N tile: least padded columns, ties to the larger tile (fewer re-reads of A)
-  int best = 128;
-  long long best_waste = -1;
-  for (int bn : {128, 192, 256}) {
-    long long tiles = (op.N + bn - 1) / bn;
-    long long waste = tiles * bn - op.N;
-    if (best_waste < 0 || waste < best_waste || (waste == best_waste && bn > best)) {
-      best = bn;
-      best_waste = waste;
-    }
-  }
-  if (options().umma_bn) best = options().umma_bn;
-  const bool a_mn = !(op.A.s_k == 1);
-  const int bk = options().umma_bk;
-  if (bk == 32) {
-    if (a_mn) launch_bn<32, true>(op, best, stream); else launch_bn<32, false>(op, best, stream);
-  } else {
-    if (a_mn) launch_bn<64, true>(op, best, stream); else launch_bn<64, false>(op, best, stream);
-  }
+  bool ok = dispatch(op, false, stream, &why);
+  ACE_REQUIRE(ok, "gemm %s: not eligible for the tcgen05 kernel: %s", op.name, why ? why : "?");
 }
 
 }  // namespace ace

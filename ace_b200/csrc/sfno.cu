@@ -129,19 +129,21 @@ void ensure_ws(ace_sfno& n, int B) {
   n.wsB = B;
 }
 
-// 1x1 convolution as a GEMM over flattened space: D[hw][o] = sum_i x[i][hw] * W[o][i]
+// 1x1 convolution as a GEMM with channels on the accumulator rows: D[o][hw] = sum_i W[o][i] * x[i][hw].
+// A = weights (K-major), B = activations [channel][space] (MN-major: space contiguous), so the output
+// row of a thread is a channel and its columns are contiguous in memory (NC epilogue, gemm_umma.cu).
 GemmOp conv_op(const char* name, const bf16* x, long long x_plane, long long x_batch_stride, long long HW, int B,
                const ConvW& w, int k_channels) {
   GemmOp op = make_gemm_op(name);
-  op.M = (int)HW;
-  op.N = w.O;
+  op.M = w.O;
+  op.N = (int)HW;
   op.K = k_channels;
   op.Z2 = B;
-  op.A = {x, x_plane, 1, HW, 0, x_batch_stride};  // MN-major: space contiguous, channel stride HW
-  op.B = {w.w.as<bf16>(), w.plane, (long long)w.Ip, 1, 0, 0};
+  op.A = {w.w.as<bf16>(), w.plane, (long long)w.Ip, 1, 0, 0};
+  op.B = {x, x_plane, 1, HW, 0, x_batch_stride};
   if (w.has_bias) {
-    op.epi.flags |= EPI_COL_BIAS;
-    op.epi.col_bias = w.bias.as<float>();
+    op.epi.flags |= EPI_ROW_BIAS;
+    op.epi.row_bias = w.bias.as<float>();
   }
   return op;
 }
@@ -151,15 +153,27 @@ void out_planes(GemmOp& op, bf16* out, long long plane, long long batch_stride, 
   op.epi.out = out;
   op.epi.out_plane = plane;
   op.epi.o_z2 = batch_stride;
-  op.epi.o_n = HW;
-  op.epi.o_m0 = 1;
+  op.epi.o_m0 = HW;
+  op.epi.o_n = 1;
 }
 void out_f32(GemmOp& op, float* out, long long batch_stride, long long HW) {
   op.epi.flags |= EPI_OUT_F32;
   op.epi.outf = out;
   op.epi.f_z2 = batch_stride;
-  op.epi.f_n = HW;
-  op.epi.f_m0 = 1;
+  op.epi.f_m0 = HW;
+  op.epi.f_n = 1;
+}
+void add_f32(GemmOp& op, const float* add, long long batch_stride, long long HW) {
+  op.epi.flags |= EPI_ADD_F32;
+  op.epi.add = add;
+  op.epi.add_z2 = batch_stride;
+  op.epi.add_m0 = HW;
+  op.epi.add_n = 1;
+}
+void row_stats(GemmOp& op, double* stats, int C) {
+  op.epi.flags |= EPI_ROW_STATS;
+  op.epi.stats = stats;
+  op.epi.stats_z2 = C;
 }
 
 void forward(ace_sfno& n, const float* x, float* y, int B, cudaStream_t s) {
@@ -189,19 +203,9 @@ void forward(ace_sfno& n, const float* x, float* y, int B, cudaStream_t s) {
   }
   {
     GemmOp op = conv_op("encoder.2", n.e1.as<bf16>(), P_act, act_b, HW, B, n.enc1, C);
-    if (c.pos_embed) {
-      op.epi.flags |= EPI_ADD_F32;
-      op.epi.add = n.pos.as<float>();
-      op.epi.add_z2 = 0;
-      op.epi.add_n = HW;
-      op.epi.add_m0 = 1;
-    }
+    if (c.pos_embed) add_f32(op, n.pos.as<float>(), 0, HW);
     out_f32(op, n.h.as<float>(), act_b, HW);
-    if (inorm) {
-      op.epi.flags |= EPI_STATS;
-      op.epi.stats = stats;
-      op.epi.stats_z2 = C;
-    }
+    if (inorm) row_stats(op, stats, C);
     run_gemm(op, s);
   }
 
@@ -253,18 +257,11 @@ void forward(ace_sfno& n, const float* x, float* y, int B, cudaStream_t s) {
     // x = GELU(filter(x_norm) + bias_f + inner_skip(x_norm)) (sfnonet.py:223-232), in place on T
     {
       GemmOp op = conv_op("inner_skip", xn, P_act, act_b, HW, B, w.skip, C);
-      op.epi.col_bias = w.skip_total.as<float>();
-      op.epi.flags |= EPI_ADD_F32 | EPI_GELU;
-      op.epi.add = n.T.as<float>();
-      op.epi.add_z2 = act_b;
-      op.epi.add_n = HW;
-      op.epi.add_m0 = 1;
+      op.epi.row_bias = w.skip_total.as<float>();
+      op.epi.flags |= EPI_GELU;
+      add_f32(op, n.T.as<float>(), act_b, HW);
       out_f32(op, n.T.as<float>(), act_b, HW);
-      if (inorm) {
-        op.epi.flags |= EPI_STATS;
-        op.epi.stats = st1;
-        op.epi.stats_z2 = C;
-      }
+      if (inorm) row_stats(op, st1, C);
       run_gemm(op, s);
     }
     // norm1 (sfnonet.py:234-238)
@@ -283,17 +280,13 @@ void forward(ace_sfno& n, const float* x, float* y, int B, cudaStream_t s) {
       op.epi.res = xn;
       op.epi.res_plane = P_act;
       op.epi.res_z2 = act_b;
-      op.epi.res_n = HW;
-      op.epi.res_m0 = 1;
+      op.epi.res_m0 = HW;
+      op.epi.res_n = 1;
       if (i == NL - 1) {
         out_planes(op, hcat, P_hcat, cat_b, HW);  // head channels of the concat buffer
       } else {
         out_f32(op, n.h.as<float>(), act_b, HW);
-        if (inorm) {
-          op.epi.flags |= EPI_STATS;
-          op.epi.stats = stats + (long long)(2 * i + 2) * stats_per;
-          op.epi.stats_z2 = C;
-        }
+        if (inorm) row_stats(op, stats + (long long)(2 * i + 2) * stats_per, C);
       }
       run_gemm(op, s);
     }

@@ -78,12 +78,10 @@ GemmOp sht_op_legendre_inv(const ace_sht_plan& p, const bf16* c2, long long c2_p
   op.B = {p.pinv.as<bf16>(), p.pinv_plane, (long long)p.Lp, 1, (long long)p.K * p.Lp, 0};
   op.k_lo_z1 = 1;  // coefficients with l < m are zero
   op.epi.flags = EPI_OUT_PLANES;
-  op.epi.mdiv = C;  // row = reim*C + c
-  op.epi.out = g;
+  op.epi.out = g;  // row = reim*C + c  ->  g[(2m + reim)][c][k]: affine in the row index
   op.epi.out_plane = g_plane;
   op.epi.o_z2 = p.g_elems(C);
   op.epi.o_z1 = 2LL * C * p.K;
-  op.epi.o_m1 = (long long)C * p.K;
   op.epi.o_m0 = p.K;
   op.epi.o_n = 1;
   return op;

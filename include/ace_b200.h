@@ -56,8 +56,7 @@ const char* ace_last_error(void);
  *                 instead of the tcgen05 kernel (both are CUDA; there is no CPU path)
  *   "split_terms" 3 (default) or 1 = plain bf16 products (fast, ~1e-2 accurate)
  *   "profile"     1 = time every launch with CUDA events (see ace_profile_report)
- *   "umma_bk"     64 (default) or 32: K extent per pipeline stage of the tcgen05 kernel
- *   "umma_bn"     0 (default: per-op choice) or 128 / 192 / 256: N tile of the tcgen05 kernel
+ *   "umma_bn"     0 (default: per-op choice) or 192 / 256: N tile of the tcgen05 kernel (SHT stages)
  * Read-only counters through ace_get_option: "count_umma" / "count_simt" = GEMMs launched on the
  * tcgen05 / SIMT kernel since load.                                                            */
 int ace_set_option(const char* key, int value);
@@ -137,10 +136,11 @@ int ace_stepper_step(ace_stepper* st, const float* prog_dev, const float* forcin
                      float* out_dev, float* next_prog_dev, int batch, void* stream);
 
 /* ---- development hook: run one split-bf16 GEMM through both kernels (tests only) ------
- * D[z][m][n] = sum_k A[z][m][k] * B[z][n][k], fp32 in/out, row-major, a_mn_major selects the
- * A storage order ([z][k][m] when 1).  impl: 0 = SIMT kernel, 1 = tcgen05 kernel. */
+ * D[z][m][n] = sum_k A[z][m][k] * B[z][n][k], fp32 in/out.  layout bit 0: A is stored MN-major
+ * ([z][k][m]); bit 1: B is stored MN-major ([z][k][n]).  impl: 0 = SIMT kernel, 1 = tcgen05
+ * kernel (error if the shape is not eligible, e.g. n % 4 != 0 or unaligned strides). */
 int ace_dev_gemm(const float* a_dev, const float* b_dev, float* d_dev, int m, int n, int k, int nbatch,
-                 int a_mn_major, int impl, void* stream);
+                 int layout, int impl, void* stream);
 
 #ifdef __cplusplus
 }

@@ -7,93 +7,97 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _gemm(a, b, m, n, k, nb, a_mn, impl):
+def _gemm(a, b, m, n, k, nb, layout, impl):
     from ace_b200 import _lib
 
     d = torch.empty(nb, m, n, device="cuda", dtype=torch.float32)
     _lib.check(_lib.load().ace_dev_gemm(ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(b.data_ptr()),
-                                        ctypes.c_void_p(d.data_ptr()), m, n, k, nb, int(a_mn), impl, None))
+                                        ctypes.c_void_p(d.data_ptr()), m, n, k, nb, int(layout), impl, None))
     torch.cuda.synchronize()
     return d
 
 
-def _case(m, n, k, nb, a_mn, seed=0):
+def _case(m, n, k, nb, layout, seed=0):
+    """layout bit 0: A stored [z][k][m]; bit 1: B stored [z][k][n]."""
     g = torch.Generator(device="cpu").manual_seed(seed)
     a = torch.randn(nb, m, k, generator=g)
     b = torch.randn(nb, n, k, generator=g)
     truth = torch.einsum("zmk,znk->zmn", a.double(), b.double())
-    a_dev = (a.transpose(1, 2).contiguous() if a_mn else a).cuda()
-    return a_dev, b.cuda(), truth
+    a_dev = (a.transpose(1, 2).contiguous() if layout & 1 else a).cuda()
+    b_dev = (b.transpose(1, 2).contiguous() if layout & 2 else b).cuda()
+    return a_dev, b_dev, truth
 
 
 # 3-term split products: |err| <~ 3 * 2^-18 * sum|a||b|  -> relative to sqrt(k) scale ~1e-5
 TOL = 3e-5
 
 
-@pytest.mark.parametrize("a_mn", [False, True])
+@pytest.mark.parametrize("layout", [0, 1, 2, 3])
 @pytest.mark.parametrize("shape", [(70, 50, 33, 2), (128, 64, 64, 1), (300, 130, 100, 3)])
-def test_simt_gemm_matches_fp64(shape, a_mn):
+def test_simt_gemm_matches_fp64(shape, layout):
     m, n, k, nb = shape
-    a, b, truth = _case(m, n, k, nb, a_mn)
-    d = _gemm(a, b, m, n, k, nb, a_mn, impl=0)
+    a, b, truth = _case(m, n, k, nb, layout)
+    d = _gemm(a, b, m, n, k, nb, layout, impl=0)
     err = (d.double().cpu() - truth).abs().max() / truth.abs().max()
     assert err < 1e-5, err  # SIMT path multiplies the re-joined hi+lo values in fp32
 
 
-@pytest.mark.parametrize("bk", [64, 32])
-@pytest.mark.parametrize("a_mn", [False, True])
+@pytest.mark.parametrize("layout", [0, 1, 2])
 @pytest.mark.parametrize(
     "shape",
     [
-        (128, 128, 64, 1),      # one tile, one K chunk
-        (128, 128, 256, 1),     # pipeline wraps (4 / 8 chunks)
+        (128, 128, 64, 1),      # one tile, two K chunks
+        (128, 128, 256, 1),     # pipeline wraps
         (256, 192, 128, 1),     # two M tiles, N tile 192
         (1000, 384, 200, 2),    # ragged M, K tail (zero filled by TMA), batch
-        (136, 50, 40, 3),       # N < tile, K < chunk
+        (136, 52, 40, 3),       # N < tile, K tail inside a chunk
         (64800 // 8, 384, 384, 1),  # conv-like
         (520, 768, 96, 1),      # N tile 256
+        (384, 8104, 48, 2),     # conv orientation: wide N with a ragged last tile (8 valid columns)
     ],
 )
-def test_umma_gemm_matches_simt_and_fp64(shape, a_mn, bk):
-    from ace_b200 import _lib
-
+def test_umma_gemm_matches_simt_and_fp64(shape, layout):
     m, n, k, nb = shape
-    a, b, truth = _case(m, n, k, nb, a_mn, seed=1)
-    _lib.set_option("umma_bk", bk)
-    try:
-        d1 = _gemm(a, b, m, n, k, nb, a_mn, impl=1)
-    finally:
-        _lib.set_option("umma_bk", 64)
-    d0 = _gemm(a, b, m, n, k, nb, a_mn, impl=0)
+    a, b, truth = _case(m, n, k, nb, layout, seed=1)
+    d1 = _gemm(a, b, m, n, k, nb, layout, impl=1)
+    d0 = _gemm(a, b, m, n, k, nb, layout, impl=0)
     scale = truth.abs().max()
     err_truth = (d1.double().cpu() - truth).abs().max() / scale
     err_simt = (d1.double() - d0.double()).abs().max().cpu() / scale
     assert err_truth < TOL and err_simt < TOL, (float(err_truth), float(err_simt))
 
 
-@pytest.mark.parametrize("bn", [128, 192, 256])
+@pytest.mark.parametrize("bn", [192, 256])
 def test_umma_forced_n_tiles(bn):
     from ace_b200 import _lib
 
     m, n, k, nb = 384, 400, 192, 1
-    a, b, truth = _case(m, n, k, nb, True, seed=2)
+    a, b, truth = _case(m, n, k, nb, 1, seed=2)
     _lib.set_option("umma_bn", bn)
     try:
-        d1 = _gemm(a, b, m, n, k, nb, True, impl=1)
+        d1 = _gemm(a, b, m, n, k, nb, 1, impl=1)
     finally:
         _lib.set_option("umma_bn", 0)
     err = (d1.double().cpu() - truth).abs().max() / truth.abs().max()
     assert err < TOL, float(err)
 
 
+def test_umma_rejects_unaligned_shapes():
+    from ace_b200 import AceError
+
+    a, b, _ = _case(64, 50, 32, 1, 0)
+    with pytest.raises(AceError):
+        _gemm(a, b, 64, 50, 32, 1, 0, impl=1)  # n % 4 != 0: SIMT-only, the tcgen05 entry must say so
+
+
 def test_umma_single_term_is_plain_bf16():
     from ace_b200 import _lib
 
     m, n, k, nb = 256, 128, 128, 1
-    a, b, truth = _case(m, n, k, nb, False, seed=3)
+    a, b, truth = _case(m, n, k, nb, 0, seed=3)
     _lib.set_option("split_terms", 1)
     try:
-        d1 = _gemm(a, b, m, n, k, nb, False, impl=1)
+        d1 = _gemm(a, b, m, n, k, nb, 0, impl=1)
     finally:
         _lib.set_option("split_terms", 3)
     ref = torch.einsum("zmk,znk->zmn", a.bfloat16().double(), b.bfloat16().double()).cpu()
