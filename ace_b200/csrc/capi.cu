@@ -68,8 +68,13 @@ extern "C" int ace_set_option(const char* key, int value) {
   else if (!strcmp(key, "split_terms")) {
     ACE_REQUIRE(value == 1 || value == 3, "split_terms must be 1 or 3");
     options().split_terms = value;
+  } else if (!strcmp(key, "dbg")) {
+    options().dbg = value;
+  } else if (!strcmp(key, "umma_bk")) {
+    ACE_REQUIRE(value == 32 || value == 64, "umma_bk must be 32 or 64");
+    options().umma_bk = value;
   } else if (!strcmp(key, "umma_bn")) {
-    ACE_REQUIRE(value == 0 || value == 192 || value == 256, "umma_bn must be 0, 192 or 256");
+    ACE_REQUIRE(value == 0 || value == 128 || value == 192 || value == 256, "umma_bn must be 0, 128, 192 or 256");
     options().umma_bn = value;
   } else ACE_REQUIRE(false, "ace_set_option: unknown option '%s'", key);
   ACE_API_END
@@ -83,6 +88,7 @@ extern "C" int ace_get_option(const char* key) {
   if (!strcmp(key, "count_umma")) return (int)g_umma_count.load();
   if (!strcmp(key, "count_simt")) return (int)g_simt_count.load();
   if (!strcmp(key, "umma_bn")) return options().umma_bn;
+  if (!strcmp(key, "umma_bk")) return options().umma_bk;
   return -1;
 }
 

@@ -86,6 +86,8 @@ struct Options {
   int profile = 0;
   int force_simt = 0;
   int split_terms = 3;
+  int dbg = 0;       // development switches of the tcgen05 kernel (results are wrong when non-zero)
+  int umma_bk = 32;  // K extent per pipeline stage of the ROWC (forward SHT / dhconv) variants: 32 or 64
   int umma_bn = 0;   // 0 = choose per op; otherwise force the N tile of the K-major x K-major variants (192 / 256)
 };
 Options& options();
@@ -141,5 +143,27 @@ __host__ __device__ inline void split_bf16(float v, bf16& hi, bf16& lo) {
 __host__ __device__ inline float join_bf16(bf16 hi, bf16 lo) { return __bfloat162float(hi) + __bfloat162float(lo); }
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// Exact-erf GELU for the tensor-core epilogues: gelu(x) = relu(x) - 0.5 |x| erfc(|x| / sqrt 2) with
+// erfc(t) = 2^(-t Q(t)), Q a degree-9 minimax fit on [0, 4.6] (beyond it erfc < 1e-10).  Max abs error vs the
+// fp64 definition 2.4e-7 on [-8, 8] (= the fp32 rounding floor; nn.GELU's own erff path has the same size),
+// one branch-free chain of 10 FMAs + one MUFU.EX2 instead of erff's two divergent branches.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float ax = fabsf(x);
+  const float t = fminf(ax * 0.70710678118654752440f, 4.6f);
+  float q = 4.565055586e-07f;
+  q = fmaf(q, t, -1.097697806e-05f);
+  q = fmaf(q, t, 1.118192688e-04f);
+  q = fmaf(q, t, -6.078477993e-04f);
+  q = fmaf(q, t, 1.635471654e-03f);
+  q = fmaf(q, t, 8.210374325e-04f);
+  q = fmaf(q, t, -2.841062484e-02f);
+  q = fmaf(q, t, 1.485603089e-01f);
+  q = fmaf(q, t, 9.184083273e-01f);
+  q = fmaf(q, t, 1.627907927e+00f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-q * t));
+  return fmaf(-0.5f * ax, e, fmaxf(x, 0.f));
+}
 
 }  // namespace ace

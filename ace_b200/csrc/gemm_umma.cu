@@ -1,13 +1,13 @@
 // tcgen05 / TMA implementation of the fast subsets of the GemmOp contract (gemm.cuh) for sm_100a.
 //
-// One persistent CTA per SM, 384 threads, warp-specialised:
+// One persistent CTA per SM, 512 threads, warp-specialised:
 //   warp 0    TMA producer   -- cp.async.bulk.tensor loads of the hi and lo bf16 planes of the A and B
 //                               tiles into a multi-stage shared-memory ring (hardware swizzle)
 //   warp 1    MMA issuer     -- one thread issues tcgen05.mma (M=128, N<=256, K=16, bf16 x bf16 -> fp32
 //                               in TMEM); per K-step THREE products: Ahi*Bhi + Ahi*Blo + Alo*Bhi, which
 //                               reproduces an fp32 product to ~2^-17 relative (error budget)
 //   warp 2    TMEM allocator -- 2 accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1
-//   warps 4-11 epilogue      -- two warps per TMEM lane quarter, alternating 32-column chunks:
+//   warps 4-15 epilogue      -- three warps per TMEM lane quarter, interleaved 32-column chunks:
 //                               tcgen05.ld -> registers -> fused epilogue -> global memory
 //
 // Operand layouts: A and B may each be K-major (rows of K contiguous; 64-byte swizzle, BK = 32) or
@@ -44,25 +44,26 @@ struct UmmaParams {
   int tiles_m, tiles_n;
   int nterms;
   int a_z1_on, a_z2_on, b_z1_on, b_z2_on;  // 0 when the operand does not vary along that batch axis
+  int dbg;                                 // development switches (option "dbg"): 1 skip epilogue, 2 skip TMA, 4 skip MMA
   int m_fastest;                           // tile order: consecutive tiles share the B (1) or the A (0) tile
 };
 
 constexpr uint32_t EF_MASK = EPI_ADD_F32 | EPI_RES_PLANES | EPI_GELU | EPI_OUT_PLANES | EPI_OUT_F32;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 12;
 constexpr int kThreadsUmma = 32 * (4 + kEpiWarps);
-constexpr int kStgBytesPerWarp = 4096;
+constexpr int kStgBytesPerWarp = 2048;
 constexpr int kMaxSmem = 232448;  // 227 KB opt-in limit per CTA
 
-template <int BN_, bool A_MN_, bool B_MN_, uint32_t EF_, bool NC_>
+template <int BN_, bool A_MN_, bool B_MN_, uint32_t EF_, bool NC_, int BK_ = 32>
 struct Cfg {
-  static constexpr int BM = 128, BN = BN_, BK = 32;
+  static constexpr int BM = 128, BN = BN_, BK = BK_;
   static constexpr bool A_MN = A_MN_, B_MN = B_MN_, NC = NC_;
   static constexpr uint32_t EF = EF_;
   static constexpr int UMMA_K = 16;
   static constexpr int A_PLANE = BM * BK * 2;  // bytes
   static constexpr int B_PLANE = BN * BK * 2;
   static constexpr int STAGE = 2 * (A_PLANE + B_PLANE);
-  static constexpr int STG_BYTES = NC ? kEpiWarps * kStgBytesPerWarp : 0;
+  static constexpr int STG_BYTES = kEpiWarps * kStgBytesPerWarp;
   static constexpr int MAX_STAGES = 8;
   static constexpr int BAR_BYTES = (2 * MAX_STAGES + 4) * 8 + 16;
   static constexpr int STAGES_RAW = (kMaxSmem - 1024 - STG_BYTES - BAR_BYTES) / STAGE;
@@ -70,7 +71,9 @@ struct Cfg {
   static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
   static constexpr int SMEM_BYTES = STAGES * STAGE + STG_BYTES + BAR_BYTES + 1024;  // + alignment slack
   static_assert(BN % 64 == 0 && BN <= 256, "BN");
-  static_assert(STAGES >= 3, "pipeline too shallow");
+  static constexpr uint32_t K_LAYOUT = (BK == 64) ? 2u : 4u;  // K-major tiles: 128B swizzle (BK = 64) or 64B (BK = 32)
+  static_assert(BK == 32 || BK == 64, "BK");
+  static_assert(STAGES >= 2, "pipeline too shallow");
   static_assert(A_PLANE % 1024 == 0 && B_PLANE % 1024 == 0, "tiles must keep 1024B alignment");
   static_assert(SMEM_BYTES <= kMaxSmem, "shared memory budget");
 };
@@ -109,196 +112,321 @@ __device__ __forceinline__ bool decode_tile(const UmmaParams& p, long long t, Ti
   return ti.n_count > 0 && ti.n_end > n_lo && ti.num_kc > 0;
 }
 
-// ---- epilogue: ROWC (lane = row, rows contiguous in memory), split-plane output only ----
+// ---- packed fp32x2 arithmetic (sm_100: one FFMA2 / FADD2 / FMUL2 per register pair) ----
+struct f2 {
+  unsigned long long u;
+};
+__device__ __forceinline__ f2 mk2(float a, float b) {
+  f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.u) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void un2(f2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v.u)); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+  f2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d.u) : "l"(a.u), "l"(b.u), "l"(c.u));
+  return d;
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+  f2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d.u) : "l"(a.u), "l"(b.u));
+  return d;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+  f2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d.u) : "l"(a.u), "l"(b.u));
+  return d;
+}
+__device__ __forceinline__ float ex2f(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x));
+  return e;
+}
+// gelu_fast (common.cuh) on a pair: same polynomial, packed FMAs
+__device__ __forceinline__ void gelu2(float& x0, float& x1) {
+  const float a0 = fabsf(x0), a1 = fabsf(x1);
+  f2 t = mul2(mk2(a0, a1), mk2(0.70710678118654752440f, 0.70710678118654752440f));
+  float t0, t1;
+  un2(t, t0, t1);
+  t = mk2(fminf(t0, 4.6f), fminf(t1, 4.6f));
+  f2 q = mk2(4.565055586e-07f, 4.565055586e-07f);
+  q = fma2(q, t, mk2(-1.097697806e-05f, -1.097697806e-05f));
+  q = fma2(q, t, mk2(1.118192688e-04f, 1.118192688e-04f));
+  q = fma2(q, t, mk2(-6.078477993e-04f, -6.078477993e-04f));
+  q = fma2(q, t, mk2(1.635471654e-03f, 1.635471654e-03f));
+  q = fma2(q, t, mk2(8.210374325e-04f, 8.210374325e-04f));
+  q = fma2(q, t, mk2(-2.841062484e-02f, -2.841062484e-02f));
+  q = fma2(q, t, mk2(1.485603089e-01f, 1.485603089e-01f));
+  q = fma2(q, t, mk2(9.184083273e-01f, 9.184083273e-01f));
+  q = fma2(q, t, mk2(1.627907927e+00f, 1.627907927e+00f));
+  float u0, u1;
+  un2(mul2(q, t), u0, u1);
+  const f2 e = mk2(ex2f(-u0), ex2f(-u1));
+  const f2 r = fma2(mul2(mk2(a0, a1), mk2(-0.5f, -0.5f)), e, mk2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
+  un2(r, x0, x1);
+}
+
+// two fp32 -> packed bf16x2 (element 0 in the low half), round to nearest even: one F2FP instruction
+__device__ __forceinline__ uint32_t pack_bf16x2(float x0, float x1) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// split (x0, x1) into packed hi and lo words: v ~= hi + lo, |v - (hi + lo)| <= 2^-17 |v|
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  hi = pack_bf16x2(x0, x1);
+  float r0, r1;
+  un2(add2(mk2(x0, x1), mk2(-__uint_as_float(hi << 16), -__uint_as_float(hi & 0xffff0000u))), r0, r1);
+  lo = pack_bf16x2(r0, r1);
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// ---- epilogue: ROWC (rows contiguous in memory), split-plane output only ----
+// thread = accumulator row; each plane of a 32x32 chunk is transposed through the warp's 2 KB staging tile
+// ([column][32 rows x 2 B]) so that the global stores are 8 bytes per lane, 64 contiguous bytes per column.
 template <class C>
-__device__ __forceinline__ void epilogue_rowc(const UmmaParams& p, const Tile& ti, uint32_t tacc, int q, int half,
-                                              int lane) {
+__device__ __forceinline__ void epilogue_rowc(const UmmaParams& p, const Tile& ti, uint32_t tacc, int q, int sub, int lane,
+                                              uint8_t* stg_raw) {
   const GemmOp& op = p.op;
   const EpiParams& e = op.epi;
-  const int row = ti.m0 + 32 * q + lane;
-  const bool row_ok = row < op.M;
-  const int m1 = row / e.mdiv, mr = row - m1 * e.mdiv;
-  bf16* base = e.out + (long long)ti.z1 * e.o_z1 + (long long)ti.z2 * e.o_z2 + (long long)m1 * e.o_m1 +
-               (long long)mr * e.o_m0 + (long long)ti.n_begin * e.o_n;
-  const long long on = e.o_n, plane = e.out_plane;
-  for (int c = half; c * 32 < ti.n_count; c += 2) {
+  unsigned short* s2 = reinterpret_cast<unsigned short*>(stg_raw);  // [32 columns][32 rows]
+  const uint2* s8 = reinterpret_cast<const uint2*>(stg_raw);        // [32 columns][8 x (4 rows)]
+  const int row0 = ti.m0 + 32 * q;
+  // cooperative role: column cc + 4*it, rows row0 + 4*pc .. +3 (never straddles an mdiv boundary: mdiv % 4 == 0)
+  const int cc = lane >> 3, pc = lane & 7;
+  const int grow = row0 + pc * 4;
+  const bool g_ok = grow < op.M;  // M % 4 == 0 (host-checked)
+  const int m1 = grow / e.mdiv, mr = grow - m1 * e.mdiv;
+  bf16* gbase = e.out + (long long)ti.z1 * e.o_z1 + (long long)ti.z2 * e.o_z2 + (long long)m1 * e.o_m1 + mr +
+                (long long)(ti.n_begin + cc) * e.o_n;
+  const long long on4 = 4 * e.o_n;
+  for (int c = sub; c * 32 < ti.n_count; c += kEpiWarps / 4) {
     float v[32];
     ptx::tmem_ld_32x32(tacc + c * 32, v);
     ptx::tmem_ld_wait();
-    bf16* h = base + (long long)(c * 32) * on;
-    bf16* l = h + plane;
-    const int nleft = ti.n_count - c * 32;  // columns of this chunk inside [n_begin, n_end)
-    if (row_ok) {
+    uint32_t hw[16], lw[16];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (j < nleft) {
-          bf16 hi, lo;
-          split_bf16(v[j], hi, lo);
-          *h = hi;
-          *l = lo;
-        }
-        h += on;
-        l += on;
+    for (int j = 0; j < 16; ++j) split2(v[2 * j], v[2 * j + 1], hw[j], lw[j]);
+    const int nleft = ti.n_count - c * 32;  // columns of this chunk inside [n_begin, n_end)
+    bf16* g = gbase + (long long)(c * 32) * e.o_n;
+#pragma unroll
+    for (int pl = 0; pl < 2; ++pl) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const uint32_t w = pl ? lw[j] : hw[j];
+        s2[(2 * j) * 32 + lane] = (unsigned short)w;
+        s2[(2 * j + 1) * 32 + lane] = (unsigned short)(w >> 16);
       }
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const uint2 w = s8[(it * 4 + cc) * 8 + pc];
+        if (g_ok && it * 4 + cc < nleft) *reinterpret_cast<uint2*>(g + it * on4 + (pl ? e.out_plane : 0)) = w;
+      }
+      __syncwarp();
     }
   }
 }
 
 // ---- epilogue: NC (thread = row, columns contiguous in memory, transposed through shared memory) ----
-// staging tile of one warp: fp32 view [32 rows][8 x 16 B] (swizzle p ^ (r & 7)) or two split-plane views
-// [32 rows][8 x 8 B] (swizzle p ^ ((r >> 1) & 7)), hi at +0, lo at +2048 B.
-__device__ __forceinline__ int swz16(int r, int p) { return r * 8 + (p ^ (r & 7)); }
+// A warp owns a 2 KB staging tile and moves its 32x32 chunk through it in passes:
+//   fp32 pass   16 columns: [32 rows][4 x 16 B], slot = r*4 + (p ^ ((r >> 1) & 3))
+//   plane pass  32 columns of ONE plane: [32 rows][8 x 8 B], slot = r*8 + (p ^ ((r >> 1) & 7))
+// Row pitch is 64 B in both views; own-row accesses (lane = row) and cooperative accesses (lane -> (row, piece),
+// whole 64 B row segments per quarter / half warp) are bank-conflict free with these swizzles.
+__device__ __forceinline__ int swz16(int r, int p) { return r * 4 + (p ^ ((r >> 1) & 3)); }
 __device__ __forceinline__ int swz8(int r, int p) { return r * 8 + (p ^ ((r >> 1) & 7)); }
 
+// L2 prefetch of the fp32 addend / residual planes a warp will need for its chunks of this tile; issued before the
+// warp blocks on the accumulator barrier, i.e. several microseconds ahead of use.
 template <class C>
-__device__ __forceinline__ void epilogue_nc(const UmmaParams& p, const Tile& ti, uint32_t tacc, int q, int half, int lane,
-                                            uint8_t* stg_raw) {
+__device__ __forceinline__ void epilogue_nc_prefetch(const UmmaParams& p, const Tile& ti, int q, int sub, int lane) {
   constexpr uint32_t EF = C::EF;
-  const GemmOp& op = p.op;
-  const EpiParams& e = op.epi;
-  uint4* stg16 = reinterpret_cast<uint4*>(stg_raw);
-  uint2* stg8 = reinterpret_cast<uint2*>(stg_raw);
-  const int row0 = ti.m0 + 32 * q;  // first row of this warp
-  const int row = row0 + lane;
-  const bool row_ok = row < op.M;
-  const bool do_stats = (e.flags & EPI_ROW_STATS) != 0;
-  float rbias = 0.f;
-  if ((e.flags & EPI_ROW_BIAS) && row_ok) rbias = __ldg(e.row_bias + (long long)ti.z2 * e.rb_z2 + row);
-  float ssum = 0.f, ssq = 0.f;
-  // cooperative (transposed) access: lane -> (row r = it*4 + lane/8, 4-element piece pc = lane%8)
-  const int cr = lane >> 3, pc = lane & 7;
-
-  for (int c = half; c * 32 < ti.n_count; c += 2) {
-    const int n0 = ti.n_begin + c * 32;
-    const int nvalid = min(32, ti.n_end - n0);  // multiple of 4 (host-checked)
-    float v[32];
-    ptx::tmem_ld_32x32(tacc + c * 32, v);
-    ptx::tmem_ld_wait();
-    const bool pc_ok = pc * 4 < nvalid;
-
-    if (EF & EPI_ADD_F32) {
-      const float* g = e.add + (long long)ti.z2 * e.add_z2 + (long long)(row0 + cr) * e.add_m0 + n0 + pc * 4;
-      const long long step = 4 * e.add_m0;
-      uint4 t[8];
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        t[it] = make_uint4(0u, 0u, 0u, 0u);
-        if (pc_ok && row0 + it * 4 + cr < op.M) t[it] = __ldg(reinterpret_cast<const uint4*>(g + it * step));
-      }
-#pragma unroll
-      for (int it = 0; it < 8; ++it) stg16[swz16(it * 4 + cr, pc)] = t[it];
-      __syncwarp();
-#pragma unroll
-      for (int pp = 0; pp < 8; ++pp) {
-        uint4 w = stg16[swz16(lane, pp)];
-        v[4 * pp + 0] += __uint_as_float(w.x);
-        v[4 * pp + 1] += __uint_as_float(w.y);
-        v[4 * pp + 2] += __uint_as_float(w.z);
-        v[4 * pp + 3] += __uint_as_float(w.w);
-      }
-      __syncwarp();
-    }
+  if (!(EF & (EPI_ADD_F32 | EPI_RES_PLANES))) return;
+  const EpiParams& e = p.op.epi;
+  const int row = ti.m0 + 32 * q + lane;
+  if (row >= p.op.M) return;
+  for (int c = sub; c * 32 < ti.n_count; c += kEpiWarps / 4) {
+    const long long n0 = ti.n_begin + c * 32;
+    if (EF & EPI_ADD_F32) prefetch_l2(e.add + (long long)ti.z2 * e.add_z2 + (long long)row * e.add_m0 + n0);
     if (EF & EPI_RES_PLANES) {
-      const bf16* g = e.res + (long long)ti.z2 * e.res_z2 + (long long)(row0 + cr) * e.res_m0 + n0 + pc * 4;
-      const long long step = 4 * e.res_m0;
-      uint2 th[8], tl[8];
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        th[it] = tl[it] = make_uint2(0u, 0u);
-        if (pc_ok && row0 + it * 4 + cr < op.M) {
-          th[it] = __ldg(reinterpret_cast<const uint2*>(g + it * step));
-          tl[it] = __ldg(reinterpret_cast<const uint2*>(g + it * step + e.res_plane));
-        }
-      }
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        stg8[swz8(it * 4 + cr, pc)] = th[it];
-        stg8[256 + swz8(it * 4 + cr, pc)] = tl[it];
-      }
-      __syncwarp();
-#pragma unroll
-      for (int pp = 0; pp < 8; ++pp) {
-        uint2 a = stg8[swz8(lane, pp)], b = stg8[256 + swz8(lane, pp)];
-        // bf16 -> fp32 is a 16-bit shift; element 2i sits in the low half of word i
-        v[4 * pp + 0] += __uint_as_float(a.x << 16) + __uint_as_float(b.x << 16);
-        v[4 * pp + 1] += __uint_as_float(a.x & 0xffff0000u) + __uint_as_float(b.x & 0xffff0000u);
-        v[4 * pp + 2] += __uint_as_float(a.y << 16) + __uint_as_float(b.y << 16);
-        v[4 * pp + 3] += __uint_as_float(a.y & 0xffff0000u) + __uint_as_float(b.y & 0xffff0000u);
-      }
-      __syncwarp();
+      const bf16* r = e.res + (long long)ti.z2 * e.res_z2 + (long long)row * e.res_m0 + n0;
+      prefetch_l2(r);
+      prefetch_l2(r + e.res_plane);
     }
+  }
+}
 
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float x = v[j] + rbias;
-      if (EF & EPI_GELU) x = gelu_erf(x);
-      v[j] = x;
-    }
-    if (do_stats && row_ok) {
-      if (nvalid == 32) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          ssum += v[j];
-          ssq = fmaf(v[j], v[j], ssq);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < nvalid) {
-            ssum += v[j];
-            ssq = fmaf(v[j], v[j], ssq);
-          }
-      }
-    }
+template <class C, bool FULL>
+__device__ __forceinline__ void epilogue_nc_chunk(const EpiParams& e, float (&v)[32], int nvalid, int rows_valid, int lane,
+                                                  uint4* s16, uint2* s8, const float* g_add, const bf16* g_res,
+                                                  float* g_f32, bf16* g_pl, float rbias, bool do_stats, f2& ssum, f2& ssq) {
+  constexpr uint32_t EF = C::EF;
+  const int fr = lane >> 2, fp = lane & 3;  // fp32 pass: rows it*8 + fr (it < 4), 16-byte piece fp
+  const int pr = lane >> 3, pp = lane & 7;  // plane pass: rows it*4 + pr (it < 8), 8-byte piece pp
 
-    if (EF & EPI_OUT_F32) {
+  // (the operands were L2-prefetched before the accumulator barrier, so one pass of loads in flight is enough)
+  if (EF & EPI_ADD_F32) {
 #pragma unroll
-      for (int pp = 0; pp < 8; ++pp)
-        stg16[swz16(lane, pp)] = make_uint4(__float_as_uint(v[4 * pp]), __float_as_uint(v[4 * pp + 1]),
-                                            __float_as_uint(v[4 * pp + 2]), __float_as_uint(v[4 * pp + 3]));
-      __syncwarp();
-      float* g = e.outf + (long long)ti.z1 * e.f_z1 + (long long)ti.z2 * e.f_z2 + (long long)(row0 + cr) * e.f_m0 + n0 + pc * 4;
-      const long long step = 4 * e.f_m0;
+    for (int h = 0; h < 2; ++h) {
+      uint4 t[4];
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        uint4 w = stg16[swz16(it * 4 + cr, pc)];
-        if (pc_ok && row0 + it * 4 + cr < op.M) *reinterpret_cast<uint4*>(g + it * step) = w;
+      for (int it = 0; it < 4; ++it) {
+        t[it] = make_uint4(0u, 0u, 0u, 0u);
+        if (FULL || (16 * h + fp * 4 < nvalid && it * 8 + fr < rows_valid))
+          t[it] = __ldg(reinterpret_cast<const uint4*>(g_add + (long long)(it * 8) * e.add_m0 + 16 * h));
       }
+#pragma unroll
+      for (int it = 0; it < 4; ++it) s16[swz16(it * 8 + fr, fp)] = t[it];
       __syncwarp();
-    }
-    if (EF & EPI_OUT_PLANES) {
 #pragma unroll
-      for (int pp = 0; pp < 8; ++pp) {
-        uint32_t hw[4], lw[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float x = v[4 * pp + i];
-          const bf16 hi = __float2bfloat16_rn(x);
-          const bf16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
-          hw[i] = (uint32_t)__bfloat16_as_ushort(hi);
-          lw[i] = (uint32_t)__bfloat16_as_ushort(lo);
-        }
-        stg8[swz8(lane, pp)] = make_uint2(hw[0] | (hw[1] << 16), hw[2] | (hw[3] << 16));
-        stg8[256 + swz8(lane, pp)] = make_uint2(lw[0] | (lw[1] << 16), lw[2] | (lw[3] << 16));
-      }
-      __syncwarp();
-      bf16* g = e.out + (long long)ti.z1 * e.o_z1 + (long long)ti.z2 * e.o_z2 + (long long)(row0 + cr) * e.o_m0 + n0 + pc * 4;
-      const long long step = 4 * e.o_m0;
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        uint2 a = stg8[swz8(it * 4 + cr, pc)], b = stg8[256 + swz8(it * 4 + cr, pc)];
-        if (pc_ok && row0 + it * 4 + cr < op.M) {
-          *reinterpret_cast<uint2*>(g + it * step) = a;
-          *reinterpret_cast<uint2*>(g + it * step + e.out_plane) = b;
-        }
+      for (int k = 0; k < 4; ++k) {
+        const uint4 w = s16[swz16(lane, k)];
+        v[16 * h + 4 * k + 0] += __uint_as_float(w.x);
+        v[16 * h + 4 * k + 1] += __uint_as_float(w.y);
+        v[16 * h + 4 * k + 2] += __uint_as_float(w.z);
+        v[16 * h + 4 * k + 3] += __uint_as_float(w.w);
       }
       __syncwarp();
     }
   }
+  if (EF & EPI_RES_PLANES) {
+#pragma unroll
+    for (int pl = 0; pl < 2; ++pl) {
+      uint2 t[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        t[it] = make_uint2(0u, 0u);
+        if (FULL || (pp * 4 < nvalid && it * 4 + pr < rows_valid))
+          t[it] = __ldg(reinterpret_cast<const uint2*>(g_res + (long long)(it * 4) * e.res_m0 + (pl ? e.res_plane : 0)));
+      }
+#pragma unroll
+      for (int it = 0; it < 8; ++it) s8[swz8(it * 4 + pr, pp)] = t[it];
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const uint2 a = s8[swz8(lane, k)];
+        // bf16 -> fp32 is a 16-bit shift; element 2i sits in the low half of word i
+        f2 s0 = add2(mk2(v[4 * k], v[4 * k + 1]), mk2(__uint_as_float(a.x << 16), __uint_as_float(a.x & 0xffff0000u)));
+        f2 s1 = add2(mk2(v[4 * k + 2], v[4 * k + 3]), mk2(__uint_as_float(a.y << 16), __uint_as_float(a.y & 0xffff0000u)));
+        un2(s0, v[4 * k], v[4 * k + 1]);
+        un2(s1, v[4 * k + 2], v[4 * k + 3]);
+      }
+      __syncwarp();
+    }
+  }
+
+  const f2 rb = mk2(rbias, rbias);
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    f2 x = add2(mk2(v[j], v[j + 1]), rb);
+    un2(x, v[j], v[j + 1]);
+    if (EF & EPI_GELU) gelu2(v[j], v[j + 1]);
+  }
+  if (do_stats) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      const bool ok = FULL || j < nvalid;  // nvalid is even
+      const f2 x = mk2(ok ? v[j] : 0.f, ok ? v[j + 1] : 0.f);
+      ssum = add2(ssum, x);
+      ssq = fma2(x, x, ssq);
+    }
+  }
+
+  if (EF & EPI_OUT_F32) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        s16[swz16(lane, k)] = make_uint4(__float_as_uint(v[16 * h + 4 * k]), __float_as_uint(v[16 * h + 4 * k + 1]),
+                                         __float_as_uint(v[16 * h + 4 * k + 2]), __float_as_uint(v[16 * h + 4 * k + 3]));
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const uint4 w = s16[swz16(it * 8 + fr, fp)];
+        if (FULL || (16 * h + fp * 4 < nvalid && it * 8 + fr < rows_valid))
+          *reinterpret_cast<uint4*>(g_f32 + (long long)(it * 8) * e.f_m0 + 16 * h) = w;
+      }
+      __syncwarp();
+    }
+  }
+  if (EF & EPI_OUT_PLANES) {
+    // pass 0 stores the hi plane and leaves the residuals (v - hi) in v; pass 1 stores their bf16 rounding (lo)
+#pragma unroll
+    for (int pl = 0; pl < 2; ++pl) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        uint32_t w[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          float& x0 = v[4 * k + 2 * i];
+          float& x1 = v[4 * k + 2 * i + 1];
+          w[i] = pack_bf16x2(x0, x1);
+          if (pl == 0) un2(add2(mk2(x0, x1), mk2(-__uint_as_float(w[i] << 16), -__uint_as_float(w[i] & 0xffff0000u))), x0, x1);
+        }
+        s8[swz8(lane, k)] = make_uint2(w[0], w[1]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const uint2 w = s8[swz8(it * 4 + pr, pp)];
+        if (FULL || (pp * 4 < nvalid && it * 4 + pr < rows_valid))
+          *reinterpret_cast<uint2*>(g_pl + (long long)(it * 4) * e.o_m0 + (pl ? e.out_plane : 0)) = w;
+      }
+      __syncwarp();
+    }
+  }
+}
+
+template <class C>
+__device__ __forceinline__ void epilogue_nc(const UmmaParams& p, const Tile& ti, uint32_t tacc, int q, int sub, int lane,
+                                            uint8_t* stg_raw) {
+  constexpr uint32_t EF = C::EF;
+  const GemmOp& op = p.op;
+  const EpiParams& e = op.epi;
+  uint4* s16 = reinterpret_cast<uint4*>(stg_raw);
+  uint2* s8 = reinterpret_cast<uint2*>(stg_raw);
+  const int row0 = ti.m0 + 32 * q;  // first row of this warp
+  const int row = row0 + lane;
+  const bool row_ok = row < op.M;
+  const int rows_valid = op.M - row0;  // >= 32 for full tiles
+  const bool do_stats = (e.flags & EPI_ROW_STATS) != 0;
+  float rbias = 0.f;
+  if ((e.flags & EPI_ROW_BIAS) && row_ok) rbias = __ldg(e.row_bias + (long long)ti.z2 * e.rb_z2 + row);
+  f2 ssum = mk2(0.f, 0.f), ssq = mk2(0.f, 0.f);
+  const int fr = lane >> 2, fp = lane & 3, pr = lane >> 3, pp = lane & 7;
+  // per-lane global pointers at (first cooperative row, n_begin, piece)
+  const float* g_add = nullptr;
+  const bf16* g_res = nullptr;
+  float* g_f32 = nullptr;
+  bf16* g_pl = nullptr;
+  if (EF & EPI_ADD_F32) g_add = e.add + (long long)ti.z2 * e.add_z2 + (long long)(row0 + fr) * e.add_m0 + ti.n_begin + fp * 4;
+  if (EF & EPI_RES_PLANES) g_res = e.res + (long long)ti.z2 * e.res_z2 + (long long)(row0 + pr) * e.res_m0 + ti.n_begin + pp * 4;
+  if (EF & EPI_OUT_F32)
+    g_f32 = e.outf + (long long)ti.z1 * e.f_z1 + (long long)ti.z2 * e.f_z2 + (long long)(row0 + fr) * e.f_m0 + ti.n_begin + fp * 4;
+  if (EF & EPI_OUT_PLANES)
+    g_pl = e.out + (long long)ti.z1 * e.o_z1 + (long long)ti.z2 * e.o_z2 + (long long)(row0 + pr) * e.o_m0 + ti.n_begin + pp * 4;
+
+  for (int c = sub; c * 32 < ti.n_count; c += kEpiWarps / 4) {
+    const int nvalid = min(32, ti.n_count - c * 32);  // multiple of 4 (host-checked)
+    float v[32];
+    ptx::tmem_ld_32x32(tacc + c * 32, v);
+    ptx::tmem_ld_wait();
+    const int co = c * 32;
+    if (nvalid == 32 && rows_valid >= 32)
+      epilogue_nc_chunk<C, true>(e, v, nvalid, rows_valid, lane, s16, s8, g_add + co, g_res + co, g_f32 + co, g_pl + co, rbias,
+                                 do_stats, ssum, ssq);
+    else
+      epilogue_nc_chunk<C, false>(e, v, nvalid, rows_valid, lane, s16, s8, g_add + co, g_res + co, g_f32 + co, g_pl + co, rbias,
+                                  do_stats && row_ok, ssum, ssq);
+  }
   if (do_stats && row_ok) {
+    float s0, s1, q0, q1;
+    un2(ssum, s0, s1);
+    un2(ssq, q0, q1);
     double* st = e.stats + ((long long)ti.z2 * e.stats_z2 + row) * 2;
-    atomicAdd(st, (double)ssum);
-    atomicAdd(st + 1, (double)ssq);
+    atomicAdd(st, (double)(s0 + s1));
+    atomicAdd(st + 1, (double)(q0 + q1));
   }
 }
 
@@ -347,8 +475,8 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
 
   const long long total = (long long)p.tiles_m * p.tiles_n * op.Z1 * op.Z2;
 
-  if (warp == 0 && lane == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 0) {
+    // ===================== TMA producer (whole warp walks the loop, one elected lane issues) =====================
     int stage = 0;
     uint32_t phase = 0;
     Tile ti;
@@ -357,34 +485,47 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
       const int az1 = ti.z1 * p.a_z1_on, az2 = ti.z2 * p.a_z2_on, bz1 = ti.z1 * p.b_z1_on, bz2 = ti.z2 * p.b_z2_on;
       for (int kc = 0; kc < ti.num_kc; ++kc) {
         ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-        const uint32_t fb = full_bar(stage);
-        ptx::mbar_arrive_expect_tx(fb, (uint32_t)C::STAGE);
-        const uint32_t sA = sbase + stage * C::STAGE;
-        const uint32_t sB = sA + 2 * C::A_PLANE;
-        const int k0 = ti.k_begin + kc * BK;
-#pragma unroll
-        for (int pl = 0; pl < 2; ++pl) {
-          if (!C::A_MN) {
-            ptx::tma_load_5d(sA + pl * C::A_PLANE, &p.tmA, fb, k0, ti.m0, az1, az2, pl);
+        if (ptx::elect_one()) {
+          const uint32_t fb = full_bar(stage);
+          if (p.dbg & 2) {
+            ptx::mbar_arrive(fb);
           } else {
-            // 64-wide MN atoms, each [BK rows][128 B]
+            ptx::mbar_arrive_expect_tx(fb, (uint32_t)C::STAGE);
+            const uint32_t sA = sbase + stage * C::STAGE;
+            const uint32_t sB = sA + 2 * C::A_PLANE;
+            const int k0 = ti.k_begin + kc * BK;
 #pragma unroll
-            for (int a = 0; a < 2; ++a)
-              ptx::tma_load_5d(sA + pl * C::A_PLANE + a * BK * 128, &p.tmA, fb, ti.m0 + 64 * a, k0, az1, az2, pl);
-          }
-          if (!C::B_MN) {
-            ptx::tma_load_5d(sB + pl * C::B_PLANE, &p.tmB, fb, k0, ti.n_begin, bz1, bz2, pl);
-          } else {
+            for (int pl = 0; pl < 2; ++pl) {
+              if (!C::A_MN) {
+                ptx::tma_load_5d(sA + pl * C::A_PLANE, &p.tmA, fb, k0, ti.m0, az1, az2, pl);
+              } else {
+                // 64-wide MN atoms, each [BK rows][128 B]
 #pragma unroll
-            for (int a = 0; a < BN / 64; ++a)
-              ptx::tma_load_5d(sB + pl * C::B_PLANE + a * BK * 128, &p.tmB, fb, ti.n_begin + 64 * a, k0, bz1, bz2, pl);
+                for (int a = 0; a < 2; ++a)
+                  ptx::tma_load_5d(sA + pl * C::A_PLANE + a * BK * 128, &p.tmA, fb, ti.m0 + 64 * a, k0, az1, az2, pl);
+              }
+              if (!C::B_MN) {
+                ptx::tma_load_5d(sB + pl * C::B_PLANE, &p.tmB, fb, k0, ti.n_begin, bz1, bz2, pl);
+              } else {
+#pragma unroll
+                for (int a = 0; a < BN / 64; ++a)
+                  ptx::tma_load_5d(sB + pl * C::B_PLANE + a * BK * 128, &p.tmB, fb, ti.n_begin + 64 * a, k0, bz1, bz2, pl);
+              }
+            }
           }
         }
+        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1) {
+    // ===================== MMA issuer (warp-uniform control flow keeps the descriptors in uniform registers) ==========
+    // K-major (64B swizzle for BK = 32, 128B for BK = 64): rows of 2*BK bytes, 8-row groups SBO apart; a K-step is
+    // 32 bytes inside the swizzled row.  MN-major (128B swizzle): [k][64 mn] atoms, 8-k groups SBO = 1024 B apart, the next
+    // 64-mn atom LBO = BK*128 B away; a K-step is 16 k-rows = 2048 B.  Descriptor address fields are in 16-byte units.
+    const uint64_t descA0 = C::A_MN ? ptx::smem_desc(0, BK * 128, 1024, 2u) : ptx::smem_desc(0, 0, 8 * BK * 2, C::K_LAYOUT);
+    const uint64_t descB0 = C::B_MN ? ptx::smem_desc(0, BK * 128, 1024, 2u) : ptx::smem_desc(0, 0, 8 * BK * 2, C::K_LAYOUT);
+    constexpr uint32_t kstepA = (C::A_MN ? 2048 : 32) >> 4, kstepB = (C::B_MN ? 2048 : 32) >> 4;
     int stage = 0;
     uint32_t phase = 0;
     uint32_t it = 0;
@@ -400,48 +541,47 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
       for (int kc = 0; kc < ti.num_kc; ++kc) {
         ptx::mbar_wait(full_bar(stage), phase);
         ptx::tc_fence_after();
-        const uint32_t sA = sbase + stage * C::STAGE;
-        const uint32_t sB = sA + 2 * C::A_PLANE;
+        if (ptx::elect_one()) {
+          const uint32_t sA = sbase + stage * C::STAGE;
+          const uint64_t a_hi = descA0 + (uint64_t)(sA >> 4), a_lo = a_hi + (uint64_t)(C::A_PLANE >> 4);
+          const uint64_t b_hi = a_hi - descA0 + descB0 + (uint64_t)((2 * C::A_PLANE) >> 4), b_lo = b_hi + (uint64_t)(C::B_PLANE >> 4);
+          if (!(p.dbg & 4)) {
 #pragma unroll
-        for (int kk = 0; kk < BK / 16; ++kk) {
-          // K-major (64B swizzle, BK = 32): rows of 64 bytes, 8-row groups SBO = 512 B apart; a K-step is 32
-          // bytes inside the swizzled row.  MN-major (128B swizzle): [k][64 mn] atoms, 8-k groups SBO = 1024 B
-          // apart, the next 64-mn atom LBO = BK*128 B away; a K-step is 16 k-rows = 2048 B.
-          const uint64_t a_hi = C::A_MN ? ptx::smem_desc(sA + kk * 2048, BK * 128, 1024, 2u)
-                                        : ptx::smem_desc(sA + kk * 32, 0, 8 * BK * 2, 4u);
-          const uint64_t a_lo = C::A_MN ? ptx::smem_desc(sA + C::A_PLANE + kk * 2048, BK * 128, 1024, 2u)
-                                        : ptx::smem_desc(sA + C::A_PLANE + kk * 32, 0, 8 * BK * 2, 4u);
-          const uint64_t b_hi = C::B_MN ? ptx::smem_desc(sB + kk * 2048, BK * 128, 1024, 2u)
-                                        : ptx::smem_desc(sB + kk * 32, 0, 8 * BK * 2, 4u);
-          const uint64_t b_lo = C::B_MN ? ptx::smem_desc(sB + C::B_PLANE + kk * 2048, BK * 128, 1024, 2u)
-                                        : ptx::smem_desc(sB + C::B_PLANE + kk * 32, 0, 8 * BK * 2, 4u);
-          ptx::umma_bf16(tmem_d, a_hi, b_hi, idesc, (kc | kk) != 0 ? 1u : 0u);
-          if (p.nterms == 3) {
-            ptx::umma_bf16(tmem_d, a_hi, b_lo, idesc, 1u);
-            ptx::umma_bf16(tmem_d, a_lo, b_hi, idesc, 1u);
+            for (int kk = 0; kk < BK / 16; ++kk) {
+              ptx::umma_bf16(tmem_d, a_hi + kk * kstepA, b_hi + kk * kstepB, idesc, (kc | kk) != 0 ? 1u : 0u);
+              if (p.nterms == 3) {
+                ptx::umma_bf16(tmem_d, a_hi + kk * kstepA, b_lo + kk * kstepB, idesc, 1u);
+                ptx::umma_bf16(tmem_d, a_lo + kk * kstepA, b_hi + kk * kstepB, idesc, 1u);
+              }
+            }
           }
+          ptx::umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
         }
-        ptx::umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
-      ptx::umma_commit(tfull_bar(as));  // accumulator ready for the epilogue
+      if (ptx::elect_one()) ptx::umma_commit(tfull_bar(as));  // accumulator ready for the epilogue
+      __syncwarp();
       ++it;
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int q = warp & 3;          // TMEM lane quarter this warp may access (warp id % 4)
-    const int half = (warp - 4) >> 2;  // which of the two warps of the quarter
+    const int q = warp & 3;           // TMEM lane quarter this warp may access (warp id % 4)
+    const int sub = (warp - 4) >> 2;  // which of the kEpiWarps/4 warps of the quarter
     uint8_t* stg = stg_all + (warp - 4) * kStgBytesPerWarp;
     uint32_t it = 0;
     Tile ti;
     for (long long t = blockIdx.x; t < total; t += gridDim.x) {
       if (!decode_tile<BN, BK>(p, t, ti)) continue;
       const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
+      if constexpr (C::NC) epilogue_nc_prefetch<C>(p, ti, q, sub, lane);
       ptx::mbar_wait(tfull_bar(as), aph);
       ptx::tc_fence_after();
       const uint32_t tacc = tmem_base + as * BN + ((uint32_t)(32 * q) << 16);
-      if constexpr (C::NC) epilogue_nc<C>(p, ti, tacc, q, half, lane, stg);
-      else epilogue_rowc<C>(p, ti, tacc, q, half, lane);
+      if (!(p.dbg & 1)) {
+        if constexpr (C::NC) epilogue_nc<C>(p, ti, tacc, q, sub, lane, stg);
+        else epilogue_rowc<C>(p, ti, tacc, q, sub, lane, stg);
+      }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
@@ -533,15 +673,17 @@ void launch(const GemmOp& op, cudaStream_t stream) {
   p.tiles_m = (op.M + 127) / 128;
   p.tiles_n = (op.N + C::BN - 1) / C::BN;
   p.nterms = options().split_terms;
+  p.dbg = options().dbg;
   // the operand that is re-read by neighbouring tiles should be the small one: keep the big streaming operand's
   // tile shared by consecutive CTAs (they run concurrently, so the second reader hits L2)
   p.m_fastest = C::B_MN ? 1 : 0;
+  const CUtensorMapSwizzle kswz = (C::BK == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   if (!C::A_MN)
-    make_tmap(&p.tmA, op.A, false, op.M, op.K, op.Z1, op.Z2, C::BK, 128, CU_TENSOR_MAP_SWIZZLE_64B, &p.a_z1_on, &p.a_z2_on, op.name);
+    make_tmap(&p.tmA, op.A, false, op.M, op.K, op.Z1, op.Z2, C::BK, 128, kswz, &p.a_z1_on, &p.a_z2_on, op.name);
   else
     make_tmap(&p.tmA, op.A, true, op.M, op.K, op.Z1, op.Z2, 64, C::BK, CU_TENSOR_MAP_SWIZZLE_128B, &p.a_z1_on, &p.a_z2_on, op.name);
   if (!C::B_MN)
-    make_tmap(&p.tmB, op.B, false, op.N, op.K, op.Z1, op.Z2, C::BK, C::BN, CU_TENSOR_MAP_SWIZZLE_64B, &p.b_z1_on, &p.b_z2_on, op.name);
+    make_tmap(&p.tmB, op.B, false, op.N, op.K, op.Z1, op.Z2, C::BK, C::BN, kswz, &p.b_z1_on, &p.b_z2_on, op.name);
   else
     make_tmap(&p.tmB, op.B, true, op.N, op.K, op.Z1, op.Z2, 64, C::BK, CU_TENSOR_MAP_SWIZZLE_128B, &p.b_z1_on, &p.b_z2_on, op.name);
   long long total = (long long)p.tiles_m * p.tiles_n * op.Z1 * op.Z2;
@@ -589,6 +731,10 @@ bool classify(const GemmOp& op, Variant& v, const char** why) {
   // ROWC: split-plane output with contiguous rows, nothing else
   if (v.ef == EPI_OUT_PLANES && !(f & (EPI_ROW_BIAS | EPI_ROW_STATS)) && e.o_m0 == 1 && e.o_n != 1) {
     v.nc = false;
+    // transposed 8-byte stores: groups of 4 rows must be contiguous and 8-byte aligned
+    if (!aligned4(op.M) || (e.mdiv < op.M && !aligned4(e.mdiv)) || !aligned4(e.o_m1) || !aligned4(e.o_n) || !aligned4(e.o_z1) ||
+        !aligned4(e.o_z2) || !aligned4(e.out_plane) || (((uintptr_t)e.out) & 7))
+      return fail("ROWC epilogue needs 4-row groups that are contiguous and 8B aligned");
     return true;
   }
   // NC: columns contiguous, rows affine, everything 4-element aligned
@@ -619,8 +765,10 @@ constexpr uint32_t P = EPI_OUT_PLANES, F = EPI_OUT_F32, G = EPI_GELU, AD = EPI_A
 template <int BN>
 bool launch_variant(const GemmOp& op, const Variant& v, cudaStream_t s) {
   if (!v.nc) {
-    if (!v.a_mn && !v.b_mn) { launch<Cfg<BN, false, false, P, false>>(op, s); return true; }
-    return false;
+    if (v.a_mn || v.b_mn) return false;
+    if (options().umma_bk == 64) launch<Cfg<BN, false, false, P, false, 64>>(op, s);
+    else launch<Cfg<BN, false, false, P, false, 32>>(op, s);
+    return true;
   }
   if (v.a_mn && !v.b_mn) {  // inverse SHT stages
     if (v.ef == P) { launch<Cfg<BN, true, false, P, true>>(op, s); return true; }
@@ -668,6 +816,7 @@ bool dispatch(const GemmOp& op, bool dry, cudaStream_t s, const char** why) {
   if (dry) return true;
   // N tile: least padded columns, ties to the larger tile
   int bn = options().umma_bn;
+  if (bn == 128 && !v.nc) return launch_variant<128>(op, v, s);
   if (bn != 192 && bn != 256) {
     long long w192 = (op.N + 191) / 192 * 192 - op.N, w256 = (op.N + 255) / 256 * 256 - op.N;
     bn = (w192 < w256) ? 192 : 256;
