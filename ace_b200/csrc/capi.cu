@@ -71,7 +71,7 @@ extern "C" int ace_set_option(const char* key, int value) {
   } else if (!strcmp(key, "dbg")) {
     options().dbg = value;
   } else if (!strcmp(key, "umma_bk")) {
-    ACE_REQUIRE(value == 32 || value == 64, "umma_bk must be 32 or 64");
+    ACE_REQUIRE(value == 0 || value == 32 || value == 64, "umma_bk must be 0, 32 or 64");
     options().umma_bk = value;
   } else if (!strcmp(key, "umma_bn")) {
     ACE_REQUIRE(value == 0 || value == 128 || value == 192 || value == 256, "umma_bn must be 0, 128, 192 or 256");

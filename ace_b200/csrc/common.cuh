@@ -87,7 +87,7 @@ struct Options {
   int force_simt = 0;
   int split_terms = 3;
   int dbg = 0;       // development switches of the tcgen05 kernel (results are wrong when non-zero)
-  int umma_bk = 32;  // K extent per pipeline stage of the ROWC (forward SHT / dhconv) variants: 32 or 64
+  int umma_bk = 0;   // K extent per pipeline stage of the ROWC (forward SHT / dhconv) variants: 0 = per-op hint, 32, 64
   int umma_bn = 0;   // 0 = choose per op; otherwise force the N tile of the K-major x K-major variants (192 / 256)
 };
 Options& options();

@@ -169,6 +169,64 @@ __global__ void __launch_bounds__(kThreads) spec_complex_to_planes_kernel(const 
   }
 }
 
+// Deferred InstanceNorm.  From the (sum, sum of squares) statistics of h[B][C][HW], per sample b:
+//   a[c] = gamma[c] / sqrt(var_c + eps),   s[c] = beta[c] - mean_c * a[c]        (a*h + s is the normalised tensor)
+// and fold them into the 1x1 convolution that consumes it:  W (a*h + s) + bias = (W diag(a)) h + (bias + W s):
+//   wout planes [B][O][Ip] = split(W[o][i] * a[i]),   bout[B][O] = bias[o] + sum_i W[o][i] * s[i]
+// Block (0, b) also publishes a, s and shift0 = 2*pi*s (the m = 0 DFT coefficient of the constant field s).
+__global__ void __launch_bounds__(128) prep_norm_conv_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float eps, long long HW, int C,
+                                                            const float* __restrict__ w, const float* __restrict__ bias, int O,
+                                                            int Ip, bf16* __restrict__ wout, long long wplane,
+                                                            float* __restrict__ bout, float* __restrict__ a_out,
+                                                            float* __restrict__ s_out, float* __restrict__ shift0_out) {
+  extern __shared__ float sm[];  // a[C], s[C], red[128]
+  float* sa = sm;
+  float* ss = sm + C;
+  float* red = sm + 2 * C;
+  const int o = blockIdx.x, b = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double sum = stats[((long long)b * C + c) * 2], sq = stats[((long long)b * C + c) * 2 + 1];
+    const double mean = sum / (double)HW;
+    double var = sq / (double)HW - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double a = (double)gamma[c] / sqrt(var + (double)eps);
+    sa[c] = (float)a;
+    ss[c] = (float)((double)beta[c] - mean * a);
+  }
+  __syncthreads();
+  if (o == 0) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      a_out[(long long)b * C + c] = sa[c];
+      s_out[(long long)b * C + c] = ss[c];
+      shift0_out[(long long)b * C + c] = 6.283185307179586f * ss[c];
+    }
+  }
+  if (w == nullptr) return;
+  const float* wr = w + (long long)o * C;
+  bf16* wo = wout + ((long long)b * O + o) * Ip;
+  float dot = 0.f;
+  for (int i = threadIdx.x; i < Ip; i += blockDim.x) {
+    float v = 0.f;
+    if (i < C) {
+      const float wi = wr[i];
+      v = wi * sa[i];
+      dot = fmaf(wi, ss[i], dot);
+    }
+    bf16 h, l;
+    split_bf16(v, h, l);
+    wo[i] = h;
+    wo[i + wplane] = l;
+  }
+  red[threadIdx.x] = dot;
+  __syncthreads();
+  for (int st = 64; st > 0; st >>= 1) {
+    if (threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) bout[(long long)b * O + o] = (bias ? bias[o] : 0.f) + red[0];
+}
+
 __global__ void vec_add_kernel(const float* a, const float* b, float* out, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = a[i] + b[i];
 }
@@ -260,6 +318,17 @@ void launch_spec_complex_to_planes(const float* in, int C, int L, int M, int Lp,
   ProfileScope prof("spec_complex_to_planes", stream);
   spec_complex_to_planes_kernel<<<grid_for((long long)L * M * C, kThreads), kThreads, 0, stream>>>(in, C, L, M, Lp, c2, plane);
   after_launch("spec_complex_to_planes");
+}
+
+void launch_prep_norm_conv(const double* stats, const float* gamma, const float* beta, float eps, long long HW, int B, int C,
+                           const float* w, const float* bias, int O, int Ip, bf16* wout, long long wplane, float* bout,
+                           float* a_out, float* s_out, float* shift0_out, cudaStream_t stream) {
+  ProfileScope prof("prep_norm_conv", stream);
+  dim3 grid(w ? O : 1, B);
+  size_t smem = (size_t)(2 * C + 128) * sizeof(float);
+  prep_norm_conv_kernel<<<grid, 128, smem, stream>>>(stats, gamma, beta, eps, HW, C, w, bias, O, Ip, wout, wplane, bout, a_out,
+                                                     s_out, shift0_out);
+  after_launch("prep_norm_conv");
 }
 
 void launch_vec_add(const float* a, const float* b, float* out, long long n, cudaStream_t stream) {

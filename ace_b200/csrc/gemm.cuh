@@ -41,6 +41,9 @@ enum EpiFlags : uint32_t {
   EPI_OUT_F32 = 1u << 6,     // fp32 store
   EPI_ROW_BIAS = 1u << 7,    // v += row_bias[z2*rb_z2 + m]
   EPI_ROW_STATS = 1u << 8,   // stats[(z2*stats_z2 + m)*2 + {0,1}] += {v, v*v}   (double atomics)
+  // deferred InstanceNorm (sfno.cu): the operand was stored un-normalised, the affine map is applied here
+  EPI_ROW_AFFINE = 1u << 9,  // first of all: v = ra_scale[z2*ra_z2 + m1] * v + (n == 0 ? ra_shift0[z2*ra_z2 + m1] : 0)
+  EPI_RES_AFFINE = 1u << 10, // with EPI_RES_PLANES: residual r -> res_a[z2*rsa_z2 + m] * r + res_s[z2*rsa_z2 + m]
 };
 
 // Row index m is decomposed as m1 = m / mdiv, m0 = m % mdiv so that flattened
@@ -52,6 +55,12 @@ struct EpiParams {
   long long cb_z2;
   const float* row_bias;
   long long rb_z2;
+  const float* ra_scale;
+  const float* ra_shift0;
+  long long ra_z2;
+  const float* res_a;
+  const float* res_s;
+  long long rsa_z2;
   const float* add;
   long long add_z2, add_m1, add_m0, add_n;
   const bf16* res;
@@ -69,6 +78,7 @@ struct GemmOp {
   int Z1, Z2;
   Operand A, B;
   int n_lo_z1, n_hi_z1, k_lo_z1;
+  int bk_hint;  // 0 = kernel default (32); 64 = K extent per pipeline stage for K-major x K-major ops whose A streams from HBM
   EpiParams epi;
   const char* name;  // for error messages / profiling
 };
@@ -86,12 +96,21 @@ inline GemmOp make_gemm_op(const char* name) {
 // Epilogue value: everything up to (and including) GELU.  Shared by both kernels.
 __device__ __forceinline__ float epi_value(const EpiParams& e, float acc, int m1, int m0, int n, int z2) {
   float v = acc;
+  if (e.flags & EPI_ROW_AFFINE) {
+    const long long i = (long long)z2 * e.ra_z2 + m1;
+    v = __ldg(e.ra_scale + i) * v + (n == 0 ? __ldg(e.ra_shift0 + i) : 0.f);
+  }
   if (e.flags & EPI_COL_BIAS) v += __ldg(e.col_bias + (long long)z2 * e.cb_z2 + n);
   if (e.flags & EPI_ROW_BIAS) v += __ldg(e.row_bias + (long long)z2 * e.rb_z2 + (long long)m1 * e.mdiv + m0);
   if (e.flags & EPI_ADD_F32) v += __ldg(e.add + (long long)z2 * e.add_z2 + (long long)m1 * e.add_m1 + (long long)m0 * e.add_m0 + (long long)n * e.add_n);
   if (e.flags & EPI_RES_PLANES) {
     const bf16* r = e.res + (long long)z2 * e.res_z2 + (long long)m1 * e.res_m1 + (long long)m0 * e.res_m0 + (long long)n * e.res_n;
-    v += __bfloat162float(r[0]) + __bfloat162float(r[e.res_plane]);
+    float rv = __bfloat162float(r[0]) + __bfloat162float(r[e.res_plane]);
+    if (e.flags & EPI_RES_AFFINE) {
+      const long long i = (long long)z2 * e.rsa_z2 + (long long)m1 * e.mdiv + m0;
+      rv = fmaf(__ldg(e.res_a + i), rv, __ldg(e.res_s + i));
+    }
+    v += rv;
   }
   if (e.flags & EPI_GELU) v = gelu_erf(v);
   return v;

@@ -200,10 +200,23 @@ __device__ __forceinline__ void epilogue_rowc(const UmmaParams& p, const Tile& t
   bf16* gbase = e.out + (long long)ti.z1 * e.o_z1 + (long long)ti.z2 * e.o_z2 + (long long)m1 * e.o_m1 + mr +
                 (long long)(ti.n_begin + cc) * e.o_n;
   const long long on4 = 4 * e.o_n;
+  // deferred InstanceNorm of the A operand: per-row scale, constant folded into column 0 (thread = its own row)
+  float a_scale = 1.f, a_shift0 = 0.f;
+  if (e.flags & EPI_ROW_AFFINE) {
+    const int orow = min(row0 + lane, op.M - 1);
+    const long long i = (long long)ti.z2 * e.ra_z2 + orow / e.mdiv;
+    a_scale = __ldg(e.ra_scale + i);
+    a_shift0 = __ldg(e.ra_shift0 + i);
+  }
   for (int c = sub; c * 32 < ti.n_count; c += kEpiWarps / 4) {
     float v[32];
     ptx::tmem_ld_32x32(tacc + c * 32, v);
     ptx::tmem_ld_wait();
+    if (e.flags & EPI_ROW_AFFINE) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= a_scale;
+      if (ti.n_begin + c * 32 == 0) v[0] += a_shift0;
+    }
     uint32_t hw[16], lw[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) split2(v[2 * j], v[2 * j + 1], hw[j], lw[j]);
@@ -260,7 +273,8 @@ __device__ __forceinline__ void epilogue_nc_prefetch(const UmmaParams& p, const 
 template <class C, bool FULL>
 __device__ __forceinline__ void epilogue_nc_chunk(const EpiParams& e, float (&v)[32], int nvalid, int rows_valid, int lane,
                                                   uint4* s16, uint2* s8, const float* g_add, const bf16* g_res,
-                                                  float* g_f32, bf16* g_pl, float rbias, bool do_stats, f2& ssum, f2& ssq) {
+                                                  float* g_f32, bf16* g_pl, float rbias, float res_a, float res_s, bool do_stats,
+                                                  f2& ssum, f2& ssq) {
   constexpr uint32_t EF = C::EF;
   const int fr = lane >> 2, fp = lane & 3;  // fp32 pass: rows it*8 + fr (it < 4), 16-byte piece fp
   const int pr = lane >> 3, pp = lane & 7;  // plane pass: rows it*4 + pr (it < 8), 8-byte piece pp
@@ -291,6 +305,7 @@ __device__ __forceinline__ void epilogue_nc_chunk(const EpiParams& e, float (&v)
     }
   }
   if (EF & EPI_RES_PLANES) {
+    const f2 ra2 = mk2(res_a, res_a);
 #pragma unroll
     for (int pl = 0; pl < 2; ++pl) {
       uint2 t[8];
@@ -307,8 +322,8 @@ __device__ __forceinline__ void epilogue_nc_chunk(const EpiParams& e, float (&v)
       for (int k = 0; k < 8; ++k) {
         const uint2 a = s8[swz8(lane, k)];
         // bf16 -> fp32 is a 16-bit shift; element 2i sits in the low half of word i
-        f2 s0 = add2(mk2(v[4 * k], v[4 * k + 1]), mk2(__uint_as_float(a.x << 16), __uint_as_float(a.x & 0xffff0000u)));
-        f2 s1 = add2(mk2(v[4 * k + 2], v[4 * k + 3]), mk2(__uint_as_float(a.y << 16), __uint_as_float(a.y & 0xffff0000u)));
+        f2 s0 = fma2(ra2, mk2(__uint_as_float(a.x << 16), __uint_as_float(a.x & 0xffff0000u)), mk2(v[4 * k], v[4 * k + 1]));
+        f2 s1 = fma2(ra2, mk2(__uint_as_float(a.y << 16), __uint_as_float(a.y & 0xffff0000u)), mk2(v[4 * k + 2], v[4 * k + 3]));
         un2(s0, v[4 * k], v[4 * k + 1]);
         un2(s1, v[4 * k + 2], v[4 * k + 3]);
       }
@@ -316,7 +331,7 @@ __device__ __forceinline__ void epilogue_nc_chunk(const EpiParams& e, float (&v)
     }
   }
 
-  const f2 rb = mk2(rbias, rbias);
+  const f2 rb = mk2(rbias + res_s, rbias + res_s);
 #pragma unroll
   for (int j = 0; j < 32; j += 2) {
     f2 x = add2(mk2(v[j], v[j + 1]), rb);
@@ -393,6 +408,11 @@ __device__ __forceinline__ void epilogue_nc(const UmmaParams& p, const Tile& ti,
   const bool do_stats = (e.flags & EPI_ROW_STATS) != 0;
   float rbias = 0.f;
   if ((e.flags & EPI_ROW_BIAS) && row_ok) rbias = __ldg(e.row_bias + (long long)ti.z2 * e.rb_z2 + row);
+  float res_a = 1.f, res_s = 0.f;  // deferred InstanceNorm of the residual: r -> res_a * r + res_s (per row = channel)
+  if ((EF & EPI_RES_PLANES) && (e.flags & EPI_RES_AFFINE) && row_ok) {
+    res_a = __ldg(e.res_a + (long long)ti.z2 * e.rsa_z2 + row);
+    res_s = __ldg(e.res_s + (long long)ti.z2 * e.rsa_z2 + row);
+  }
   f2 ssum = mk2(0.f, 0.f), ssq = mk2(0.f, 0.f);
   const int fr = lane >> 2, fp = lane & 3, pr = lane >> 3, pp = lane & 7;
   // per-lane global pointers at (first cooperative row, n_begin, piece)
@@ -415,10 +435,10 @@ __device__ __forceinline__ void epilogue_nc(const UmmaParams& p, const Tile& ti,
     const int co = c * 32;
     if (nvalid == 32 && rows_valid >= 32)
       epilogue_nc_chunk<C, true>(e, v, nvalid, rows_valid, lane, s16, s8, g_add + co, g_res + co, g_f32 + co, g_pl + co, rbias,
-                                 do_stats, ssum, ssq);
+                                 res_a, res_s, do_stats, ssum, ssq);
     else
       epilogue_nc_chunk<C, false>(e, v, nvalid, rows_valid, lane, s16, s8, g_add + co, g_res + co, g_f32 + co, g_pl + co, rbias,
-                                  do_stats && row_ok, ssum, ssq);
+                                  res_a, res_s, do_stats && row_ok, ssum, ssq);
   }
   if (do_stats && row_ok) {
     float s0, s1, q0, q1;
@@ -729,6 +749,8 @@ bool classify(const GemmOp& op, Variant& v, const char** why) {
   const bool planes = (f & EPI_OUT_PLANES) != 0, f32 = (f & EPI_OUT_F32) != 0;
   if (planes == f32) return fail("exactly one of OUT_PLANES / OUT_F32 is supported");
   // ROWC: split-plane output with contiguous rows, nothing else
+  if ((f & EPI_ROW_AFFINE) && !(v.ef == EPI_OUT_PLANES && e.o_m0 == 1 && e.o_n != 1)) return fail("ROW_AFFINE is only compiled for the ROWC epilogue");
+  if ((f & EPI_RES_AFFINE) && !(f & EPI_RES_PLANES)) return fail("RES_AFFINE without RES_PLANES");
   if (v.ef == EPI_OUT_PLANES && !(f & (EPI_ROW_BIAS | EPI_ROW_STATS)) && e.o_m0 == 1 && e.o_n != 1) {
     v.nc = false;
     // transposed 8-byte stores: groups of 4 rows must be contiguous and 8-byte aligned
@@ -766,7 +788,7 @@ template <int BN>
 bool launch_variant(const GemmOp& op, const Variant& v, cudaStream_t s) {
   if (!v.nc) {
     if (v.a_mn || v.b_mn) return false;
-    if (options().umma_bk == 64) launch<Cfg<BN, false, false, P, false, 64>>(op, s);
+    if (options().umma_bk == 64 || (options().umma_bk == 0 && op.bk_hint == 64)) launch<Cfg<BN, false, false, P, false, 64>>(op, s);
     else launch<Cfg<BN, false, false, P, false, 32>>(op, s);
     return true;
   }
@@ -789,6 +811,8 @@ bool launch_conv(const GemmOp& op, const Variant& v, cudaStream_t s) {
   switch (v.ef) {
     case G | P: launch<Cfg<256, false, true, G | P, true>>(op, s); return true;
     case AD | F: launch<Cfg<256, false, true, AD | F, true>>(op, s); return true;
+    case AD | P: launch<Cfg<256, false, true, AD | P, true>>(op, s); return true;
+    case AD | G | P: launch<Cfg<256, false, true, AD | G | P, true>>(op, s); return true;
     case AD | G | F: launch<Cfg<256, false, true, AD | G | F, true>>(op, s); return true;
     case RS | F: launch<Cfg<256, false, true, RS | F, true>>(op, s); return true;
     case RS | P: launch<Cfg<256, false, true, RS | P, true>>(op, s); return true;
@@ -804,7 +828,7 @@ bool dispatch(const GemmOp& op, bool dry, cudaStream_t s, const char** why) {
   if (!classify(op, v, why)) return false;
   if (v.b_mn) {
     if (v.a_mn) { if (why) *why = "MN-major x MN-major is not compiled"; return false; }
-    static const uint32_t ok[] = {G | P, AD | F, AD | G | F, RS | F, RS | P, F, P, G | F};
+    static const uint32_t ok[] = {G | P, AD | F, AD | P, AD | G | P, AD | G | F, RS | F, RS | P, F, P, G | F};
     bool found = false;
     for (uint32_t x : ok) found |= (x == v.ef);
     if (!v.nc || !found) { if (why) *why = "epilogue combination not compiled for MN-major B"; return false; }

@@ -33,6 +33,12 @@ void launch_spec_planes_to_complex(const bf16* c1, long long plane, int C, int L
 // complex64 [C][L][M] -> c2 planes [M][Lp][2C]
 void launch_spec_complex_to_planes(const float* in, int C, int L, int M, int Lp, bf16* c2, long long plane, cudaStream_t stream);
 
+// Deferred InstanceNorm: statistics -> (a, s, 2*pi*s) per (sample, channel) and, when w != nullptr, the conv
+// weights / bias with the normalisation folded in (per sample): wout planes [B][O][Ip], bout [B][O].
+void launch_prep_norm_conv(const double* stats, const float* gamma, const float* beta, float eps, long long HW, int B, int C,
+                           const float* w, const float* bias, int O, int Ip, bf16* wout, long long wplane, float* bout,
+                           float* a_out, float* s_out, float* shift0_out, cudaStream_t stream);
+
 // out[i] = a[i] + b[i]
 void launch_vec_add(const float* a, const float* b, float* out, long long n, cudaStream_t stream);
 

@@ -4,13 +4,15 @@
 // s2convolutions.py:162-197 (spectral conv) as a fixed sequence of GemmOps and streaming kernels.
 // Per block (C = embed_dim, HW = nlat*nlon):
 //
-//   h (fp32) --norm0+split--> xn --G1 DFT--> X1 --G2 Legendre--> c1 --G3 dhconv--> c2 --G4 Legendre-->
-//   g --G5 iDFT--> T (fp32) ; T <- GELU(T + Wskip xn + bskip + bfilter) [stats1] --norm1+split--> yn
-//   --fc1+GELU--> hmid --fc2 + bias + xn--> h (fp32) [stats0 of the next block]
+//   hP --G1 DFT (x a0, + 2 pi s0 at m = 0)--> X1 --G2 Legendre--> c1 --G3 dhconv--> c2 --G4 Legendre-->
+//   g --G5 iDFT--> T (fp32) ; tP <- GELU(T + (Wskip a0) hP + bskip' + bfilter) [stats1]
+//   --fc1 (W1 a1, b1') + GELU--> hmid --fc2 + bias + (a0 hP + s0)--> hP (next block) [stats0 of the next block]
 //
-// InstanceNorm statistics are accumulated by the epilogue of the GEMM that produces the tensor
-// (double atomics per (sample, channel)); the normalisation itself is applied in fp32 by the
-// norm+split pass so that the bf16 split never sees un-centred data.
+// InstanceNorm is "deferred": the epilogue of the GEMM that produces a tensor stores it UN-normalised as
+// split-bf16 planes and accumulates per-(sample, channel) sums (fp64 atomics); a tiny per-block prep kernel
+// turns the sums into y = a*h + s and folds that affine map into every consumer -- the 1x1 convolution
+// weights/bias (per sample), the row scale of the DFT GEMM (the constant s only reaches the m = 0
+// coefficient) and the residual term of fc2.  No separate normalisation pass over the activations exists.
 #include <map>
 #include <string>
 #include <vector>
@@ -27,6 +29,8 @@ struct ConvW {
   long long plane = 0;
   int O = 0, I = 0, Ip = 0;
   DevBuf bias;  // fp32 [O]
+  DevBuf wf;    // fp32 [O][I] copy (only for convolutions that a deferred InstanceNorm is folded into)
+  bool keep_f32 = false;
   bool has_bias = false;
   void init(int o, int i, bool b) {
     O = o;
@@ -64,8 +68,10 @@ struct ace_sfno {
 
   // workspace (allocated on first use for a batch size; grows monotonically)
   int wsB = 0;
-  DevBuf hcat, e1, h, xn, x1, c1, c2, g, T, yn, hmid, d1, stats;
-  long long p_hcat, p_act, p_x1, p_c1, p_c2, p_g, p_hmid;  // plane offsets (elements)
+  DevBuf hcat, e1, hP, xn, x1, c1, c2, g, T, tP, hmid, d1, stats;
+  DevBuf skipW, skipB, fc1W, fc1B;   // per-sample convolution parameters with the InstanceNorm folded in
+  DevBuf na0, ns0, nsh0, na1, ns1, nsh1;  // per-(sample, channel) a, s, 2*pi*s of norm0 / norm1
+  long long p_hcat, p_act, p_x1, p_c1, p_c2, p_g, p_hmid, p_skipW, p_fc1W;  // plane offsets (elements)
 };
 
 namespace {
@@ -93,6 +99,7 @@ void copy_f32(DevBuf& dst, const float* src, long long n, cudaStream_t s) {
 void set_conv_w(ConvW& w, const float* src, long long numel, const char* name, cudaStream_t s) {
   ACE_REQUIRE(numel == (long long)w.O * w.I, "%s: expected %lld elements, got %lld", name, (long long)w.O * w.I, numel);
   launch_split_pad(src, w.O, w.I, w.Ip, w.w.as<bf16>(), w.plane, s);
+  if (w.keep_f32) copy_f32(w.wf, src, numel, s);
 }
 void set_conv_b(ConvW& w, const float* src, long long numel, const char* name, cudaStream_t s) {
   ACE_REQUIRE(w.has_bias && numel == w.O, "%s: expected %d elements, got %lld", name, w.O, numel);
@@ -115,14 +122,24 @@ void ensure_ws(ace_sfno& n, int B) {
   const size_t e = sizeof(bf16);
   n.hcat.ensure(2 * (size_t)n.p_hcat * e);
   n.e1.ensure(2 * (size_t)n.p_act * e);
-  n.h.ensure((size_t)n.p_act * sizeof(float));
+  n.hP.ensure(2 * (size_t)n.p_act * e);
   n.xn.ensure(2 * (size_t)n.p_act * e);
   n.x1.ensure(2 * (size_t)n.p_x1 * e);
   n.c1.ensure(2 * (size_t)n.p_c1 * e);
   n.c2.ensure(2 * (size_t)n.p_c2 * e);
   n.g.ensure(2 * (size_t)n.p_g * e);
   n.T.ensure((size_t)n.p_act * sizeof(float));
-  n.yn.ensure(2 * (size_t)n.p_act * e);
+  n.tP.ensure(2 * (size_t)n.p_act * e);
+  {
+    const int Cp = (int)round_up(C, 8);
+    n.p_skipW = (long long)B * C * Cp;
+    n.p_fc1W = (long long)B * c.mlp_hidden * Cp;
+    n.skipW.ensure(2 * (size_t)n.p_skipW * e);
+    n.fc1W.ensure(2 * (size_t)n.p_fc1W * e);
+    n.skipB.ensure((size_t)B * C * sizeof(float));
+    n.fc1B.ensure((size_t)B * c.mlp_hidden * sizeof(float));
+    for (DevBuf* d : {&n.na0, &n.ns0, &n.nsh0, &n.na1, &n.ns1, &n.nsh1}) d->ensure((size_t)B * C * sizeof(float));
+  }
   n.hmid.ensure(2 * (size_t)n.p_hmid * e);
   n.d1.ensure(2 * (size_t)n.p_act * e);
   n.stats.ensure((size_t)2 * c.num_layers * B * C * 2 * sizeof(double));
@@ -146,6 +163,13 @@ GemmOp conv_op(const char* name, const bf16* x, long long x_plane, long long x_b
     op.epi.row_bias = w.bias.as<float>();
   }
   return op;
+}
+// same convolution with per-sample weights / bias (InstanceNorm folded in by prep_norm_conv)
+void use_folded(GemmOp& op, const ConvW& w, const DevBuf& wfold, long long wfold_plane, const DevBuf& bfold) {
+  op.A = {wfold.as<bf16>(), wfold_plane, (long long)w.Ip, 1, 0, (long long)w.O * w.Ip};
+  op.epi.flags |= EPI_ROW_BIAS;
+  op.epi.row_bias = bfold.as<float>();
+  op.epi.rb_z2 = w.O;
 }
 
 void out_planes(GemmOp& op, bf16* out, long long plane, long long batch_stride, long long HW) {
@@ -201,10 +225,11 @@ void forward(ace_sfno& n, const float* x, float* y, int B, cudaStream_t s) {
     out_planes(op, n.e1.as<bf16>(), P_act, act_b, HW);
     run_gemm(op, s);
   }
+  bf16* hP = n.hP.as<bf16>();
   {
     GemmOp op = conv_op("encoder.2", n.e1.as<bf16>(), P_act, act_b, HW, B, n.enc1, C);
     if (c.pos_embed) add_f32(op, n.pos.as<float>(), 0, HW);
-    out_f32(op, n.h.as<float>(), act_b, HW);
+    out_planes(op, hP, P_act, act_b, HW);
     if (inorm) row_stats(op, stats, C);
     run_gemm(op, s);
   }
@@ -215,18 +240,31 @@ void forward(ace_sfno& n, const float* x, float* y, int B, cudaStream_t s) {
     const ace_sht_plan& pi = (i == NL - 1) ? *n.outer : *n.inner;
     double* st0 = stats + (long long)(2 * i) * stats_per;
     double* st1 = stats + (long long)(2 * i + 1) * stats_per;
+    // forward and inverse grids differ -> scale_residual (s2convolutions.py:81-85,170-173): the residual used by
+    // inner_skip and the outer skip is inverse_transform(forward_transform(x_norm)) instead of x_norm itself
+    const bool scale_res = pf.table_id != pi.table_id;
+    // the residual operand of inner_skip / fc2: hP (un-normalised, affine deferred) or the round trip (already normalised)
+    const bool res_deferred = inorm && !scale_res;
     bf16* xn = n.xn.as<bf16>();
 
-    // norm0 (sfnonet.py:218-221)
-    launch_norm_split(n.h.as<float>(), B, C, HW, inorm ? st0 : nullptr, w.g0.as<float>(), w.b0.as<float>(), c.norm_eps,
-                      xn, P_act, act_b, HW, s);
+    // norm0 (sfnonet.py:218-221), deferred: a0, s0 and the inner_skip weights with diag(a0) folded in
+    if (inorm)
+      launch_prep_norm_conv(st0, w.g0.as<float>(), w.b0.as<float>(), c.norm_eps, HW, B, C, res_deferred ? w.skip.wf.as<float>() : nullptr,
+                            w.skip_total.as<float>(), C, w.skip.Ip, n.skipW.as<bf16>(), n.p_skipW, n.skipB.as<float>(),
+                            n.na0.as<float>(), n.ns0.as<float>(), n.nsh0.as<float>(), s);
     // spectral convolution (s2convolutions.py:162-197)
-    run_gemm(sht_op_dft_fwd(pf, xn, P_act, act_b, C, B, n.x1.as<bf16>(), P_x1), s);
+    {
+      GemmOp op = sht_op_dft_fwd(pf, hP, P_act, act_b, C, B, n.x1.as<bf16>(), P_x1);
+      if (inorm) {
+        op.epi.flags |= EPI_ROW_AFFINE;  // DFT(a h + s) = a DFT(h) + 2 pi s [m = 0]
+        op.epi.ra_scale = n.na0.as<float>();
+        op.epi.ra_shift0 = n.nsh0.as<float>();
+        op.epi.ra_z2 = C;
+      }
+      run_gemm(op, s);
+    }
     run_gemm(sht_op_legendre_fwd(pf, n.x1.as<bf16>(), P_x1, C, B, n.c1.as<bf16>(), P_c1), s);
-    if (pf.table_id != pi.table_id) {
-      // forward and inverse grids differ -> scale_residual (s2convolutions.py:81-85,170-173): the residual
-      // used by inner_skip and the outer skip is inverse_transform(forward_transform(x_norm)).  x_norm has
-      // been consumed by the DFT, so the round trip overwrites xn in place.
+    if (scale_res) {
       run_gemm(sht_op_legendre_inv_from_c1(pi, n.c1.as<bf16>(), P_c1, C, B, n.g.as<bf16>(), P_g), s);
       run_gemm(sht_op_dft_inv_planes(pi, n.g.as<bf16>(), P_g, C, B, xn, P_act, act_b), s);
     }
@@ -254,22 +292,28 @@ void forward(ace_sfno& n, const float* x, float* y, int B, cudaStream_t s) {
     run_gemm(sht_op_legendre_inv(pi, n.c2.as<bf16>(), P_c2, C, B, n.g.as<bf16>(), P_g), s);
     run_gemm(sht_op_dft_inv(pi, n.g.as<bf16>(), P_g, C, B, n.T.as<float>(), act_b), s);
 
-    // x = GELU(filter(x_norm) + bias_f + inner_skip(x_norm)) (sfnonet.py:223-232), in place on T
+    // residual operand of this block: x_norm = a0 hP + s0 (deferred), the round trip (scale_res), or hP itself (no norm)
+    const bf16* resid = scale_res ? xn : hP;
+    // x = GELU(filter(x_norm) + bias_f + inner_skip(residual)) (sfnonet.py:223-232) -> tP (un-normalised) + stats1
     {
-      GemmOp op = conv_op("inner_skip", xn, P_act, act_b, HW, B, w.skip, C);
+      GemmOp op = conv_op("inner_skip", resid, P_act, act_b, HW, B, w.skip, C);
       op.epi.row_bias = w.skip_total.as<float>();
+      if (res_deferred) use_folded(op, w.skip, n.skipW, n.p_skipW, n.skipB);
       op.epi.flags |= EPI_GELU;
       add_f32(op, n.T.as<float>(), act_b, HW);
-      out_f32(op, n.T.as<float>(), act_b, HW);
+      out_planes(op, n.tP.as<bf16>(), P_act, act_b, HW);
       if (inorm) row_stats(op, st1, C);
       run_gemm(op, s);
     }
-    // norm1 (sfnonet.py:234-238)
-    launch_norm_split(n.T.as<float>(), B, C, HW, inorm ? st1 : nullptr, w.g1.as<float>(), w.b1.as<float>(), c.norm_eps,
-                      n.yn.as<bf16>(), P_act, act_b, HW, s);
-    // MLP (layers.py:117-124) + outer skip (identity) with residual = x_norm (sfnonet.py:249-250)
+    // norm1 (sfnonet.py:234-238), deferred into fc1
+    if (inorm)
+      launch_prep_norm_conv(st1, w.g1.as<float>(), w.b1.as<float>(), c.norm_eps, HW, B, C, w.fc1.wf.as<float>(), w.fc1.bias.as<float>(),
+                            c.mlp_hidden, w.fc1.Ip, n.fc1W.as<bf16>(), n.p_fc1W, n.fc1B.as<float>(), n.na1.as<float>(),
+                            n.ns1.as<float>(), n.nsh1.as<float>(), s);
+    // MLP (layers.py:117-124) + outer skip (identity) with the block's residual (sfnonet.py:249-250)
     {
-      GemmOp op = conv_op("mlp.fc1", n.yn.as<bf16>(), P_act, act_b, HW, B, w.fc1, C);
+      GemmOp op = conv_op("mlp.fc1", n.tP.as<bf16>(), P_act, act_b, HW, B, w.fc1, C);
+      if (inorm) use_folded(op, w.fc1, n.fc1W, n.p_fc1W, n.fc1B);
       op.epi.flags |= EPI_GELU;
       out_planes(op, n.hmid.as<bf16>(), P_hmid, (long long)c.mlp_hidden * HW, HW);
       run_gemm(op, s);
@@ -277,15 +321,21 @@ void forward(ace_sfno& n, const float* x, float* y, int B, cudaStream_t s) {
     {
       GemmOp op = conv_op("mlp.fc2", n.hmid.as<bf16>(), P_hmid, (long long)c.mlp_hidden * HW, HW, B, w.fc2, c.mlp_hidden);
       op.epi.flags |= EPI_RES_PLANES;
-      op.epi.res = xn;
+      op.epi.res = resid;
       op.epi.res_plane = P_act;
       op.epi.res_z2 = act_b;
       op.epi.res_m0 = HW;
       op.epi.res_n = 1;
+      if (res_deferred) {
+        op.epi.flags |= EPI_RES_AFFINE;
+        op.epi.res_a = n.na0.as<float>();
+        op.epi.res_s = n.ns0.as<float>();
+        op.epi.rsa_z2 = C;
+      }
       if (i == NL - 1) {
         out_planes(op, hcat, P_hcat, cat_b, HW);  // head channels of the concat buffer
       } else {
-        out_f32(op, n.h.as<float>(), act_b, HW);
+        out_planes(op, hP, P_act, act_b, HW);  // in place when resid == hP: every chunk is read before it is written
         if (inorm) row_stats(op, stats + (long long)(2 * i + 2) * stats_per, C);
       }
       run_gemm(op, s);
@@ -337,6 +387,7 @@ extern "C" int ace_sfno_create(const ace_sfno_config* cfg, ace_sht_plan* plan_ou
     n->dec1.init(c.out_chans, C, false);
     n->blocks.resize(c.num_layers);
     for (BlockW& b : n->blocks) {
+      b.skip.keep_f32 = b.fc1.keep_f32 = (c.normalization == 1);
       b.skip.init(C, C, true);
       b.fc1.init(c.mlp_hidden, C, true);
       b.fc2.init(C, c.mlp_hidden, true);

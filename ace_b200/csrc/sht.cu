@@ -28,6 +28,7 @@ void upload_planes(DevBuf& buf, const std::vector<bf16>& hi, const std::vector<b
 GemmOp sht_op_dft_fwd(const ace_sht_plan& p, const bf16* x, long long x_plane, long long x_batch_stride, int C, int B,
                       bf16* x1, long long x1_plane) {
   GemmOp op = make_gemm_op("sht.dft_fwd");
+  op.bk_hint = 64;  // 128-byte TMA rows of the streaming operand (measured: 113 -> 91 us at 180x360x384)
   op.M = C * p.K;
   op.N = 2 * p.M;
   op.K = p.W;
@@ -48,6 +49,7 @@ GemmOp sht_op_dft_fwd(const ace_sht_plan& p, const bf16* x, long long x_plane, l
 GemmOp sht_op_legendre_fwd(const ace_sht_plan& p, const bf16* x1, long long x1_plane, int C, int B, bf16* c1,
                            long long c1_plane) {
   GemmOp op = make_gemm_op("sht.legendre_fwd");
+  op.bk_hint = 64;
   op.M = 2 * C;
   op.N = p.L;
   op.K = p.K;
