@@ -1,5 +1,6 @@
 // Library-level C ABI: errors, options, launch counter, GEMM dispatcher, development GEMM hook.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -16,7 +17,11 @@ static thread_local std::string t_last_error;
 void set_last_error(const char* msg) { t_last_error = msg ? msg : ""; }
 
 Options& options() {
-  static Options o;
+  static Options o = [] {
+    Options x;
+    if (const char* e = getenv("ACE_B200_PDL")) x.pdl = atoi(e) ? 1 : 0;
+    return x;
+  }();
   return o;
 }
 
@@ -68,6 +73,11 @@ extern "C" int ace_set_option(const char* key, int value) {
   else if (!strcmp(key, "split_terms")) {
     ACE_REQUIRE(value == 1 || value == 3, "split_terms must be 1 or 3");
     options().split_terms = value;
+  } else if (!strcmp(key, "conv_bn")) {
+    ACE_REQUIRE(value == 0 || value == 192 || value == 256, "conv_bn must be 0, 192 or 256");
+    options().conv_bn = value;
+  } else if (!strcmp(key, "pdl")) {
+    options().pdl = value ? 1 : 0;
   } else if (!strcmp(key, "dbg")) {
     options().dbg = value;
   } else if (!strcmp(key, "umma_bk")) {

@@ -86,6 +86,8 @@ struct Options {
   int profile = 0;
   int force_simt = 0;
   int split_terms = 3;
+  int conv_bn = 0;   // N tile of the 1x1-convolution GEMMs: 0 = per-op choice (wave quantisation), 192, 256
+  int pdl = 0;       // programmatic dependent launch of the tcgen05 GEMM / prep kernels (prologue overlaps the previous kernel's tail)
   int dbg = 0;       // development switches of the tcgen05 kernel (results are wrong when non-zero)
   int umma_bk = 0;   // K extent per pipeline stage of the ROWC (forward SHT / dhconv) variants: 0 = per-op hint, 32, 64
   int umma_bn = 0;   // 0 = choose per op; otherwise force the N tile of the K-major x K-major variants (192 / 256)

@@ -98,6 +98,25 @@ __global__ void __launch_bounds__(kThreads) prep_dhconv_kernel(const float* __re
   }
 }
 
+// dhconv weight [Cin][Cout][L][2] (reference layout) -> planes [L][2 (re, im)][Cout][Cinp] for the complex GEMM mode
+__global__ void __launch_bounds__(kThreads) prep_dhconv_cplx_kernel(const float* __restrict__ w, int Cin, int Cout, int L,
+                                                                   int Cinp, bf16* __restrict__ dst, long long plane) {
+  const long long total = (long long)L * 2 * Cout * Cinp;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    int i = (int)(idx % Cinp);
+    long long t = idx / Cinp;
+    int o = (int)(t % Cout);
+    t /= Cout;
+    int part = (int)(t & 1);
+    int l = (int)(t >> 1);
+    float v = (i < Cin) ? w[(((long long)i * Cout + o) * L + l) * 2 + part] : 0.f;
+    bf16 h, lo;
+    split_bf16(v, h, lo);
+    dst[idx] = h;
+    dst[idx + plane] = lo;
+  }
+}
+
 // one thread per (b, l, m, o); x is broadcast across the o threads of a warp
 __global__ void __launch_bounds__(kThreads) diagonal_contract_kernel(const bf16* __restrict__ c1, long long c1_plane,
                                                                     const float* __restrict__ w, int B, int C, int L,
@@ -174,28 +193,29 @@ __global__ void __launch_bounds__(kThreads) spec_complex_to_planes_kernel(const 
 // and fold them into the 1x1 convolution that consumes it:  W (a*h + s) + bias = (W diag(a)) h + (bias + W s):
 //   wout planes [B][O][Ip] = split(W[o][i] * a[i]),   bout[B][O] = bias[o] + sum_i W[o][i] * s[i]
 // Block (0, b) also publishes a, s and shift0 = 2*pi*s (the m = 0 DFT coefficient of the constant field s).
-__global__ void __launch_bounds__(128) prep_norm_conv_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(256) prep_norm_conv_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float eps, long long HW, int C,
                                                             const float* __restrict__ w, const float* __restrict__ bias, int O,
                                                             int Ip, bf16* __restrict__ wout, long long wplane,
                                                             float* __restrict__ bout, float* __restrict__ a_out,
                                                             float* __restrict__ s_out, float* __restrict__ shift0_out) {
-  extern __shared__ float sm[];  // a[C], s[C], red[128]
+  // one warp per output row, 8 rows per block; griddepcontrol: the statistics come from the previous kernel
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  extern __shared__ float sm[];  // a[C], s[C]
   float* sa = sm;
   float* ss = sm + C;
-  float* red = sm + 2 * C;
-  const int o = blockIdx.x, b = blockIdx.y;
+  const int b = blockIdx.y;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const double sum = stats[((long long)b * C + c) * 2], sq = stats[((long long)b * C + c) * 2 + 1];
     const double mean = sum / (double)HW;
     double var = sq / (double)HW - mean * mean;
     if (var < 0.0) var = 0.0;
-    const double a = (double)gamma[c] / sqrt(var + (double)eps);
+    const double a = (double)gamma[c] * rsqrt(var + (double)eps);
     sa[c] = (float)a;
     ss[c] = (float)((double)beta[c] - mean * a);
   }
   __syncthreads();
-  if (o == 0) {
+  if (blockIdx.x == 0) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       a_out[(long long)b * C + c] = sa[c];
       s_out[(long long)b * C + c] = ss[c];
@@ -203,13 +223,16 @@ __global__ void __launch_bounds__(128) prep_norm_conv_kernel(const double* __res
     }
   }
   if (w == nullptr) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o = blockIdx.x * 8 + warp;
+  if (o >= O) return;
   const float* wr = w + (long long)o * C;
   bf16* wo = wout + ((long long)b * O + o) * Ip;
   float dot = 0.f;
-  for (int i = threadIdx.x; i < Ip; i += blockDim.x) {
+  for (int i = lane; i < Ip; i += 32) {
     float v = 0.f;
     if (i < C) {
-      const float wi = wr[i];
+      const float wi = __ldg(wr + i);
       v = wi * sa[i];
       dot = fmaf(wi, ss[i], dot);
     }
@@ -218,13 +241,9 @@ __global__ void __launch_bounds__(128) prep_norm_conv_kernel(const double* __res
     wo[i] = h;
     wo[i + wplane] = l;
   }
-  red[threadIdx.x] = dot;
-  __syncthreads();
-  for (int st = 64; st > 0; st >>= 1) {
-    if (threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) bout[(long long)b * O + o] = (bias ? bias[o] : 0.f) + red[0];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, d);
+  if (lane == 0) bout[(long long)b * O + o] = (bias ? bias[o] : 0.f) + dot;
 }
 
 __global__ void vec_add_kernel(const float* a, const float* b, float* out, long long n) {
@@ -301,6 +320,12 @@ void launch_prep_dhconv(const float* w, int Cin, int Cout, int L, bf16* dst, lon
   after_launch("prep_dhconv");
 }
 
+void launch_prep_dhconv_cplx(const float* w, int Cin, int Cout, int L, int Cinp, bf16* dst, long long plane, cudaStream_t stream) {
+  ProfileScope prof("prep_dhconv", stream);
+  prep_dhconv_cplx_kernel<<<grid_for((long long)L * 2 * Cout * Cinp, kThreads), kThreads, 0, stream>>>(w, Cin, Cout, L, Cinp, dst, plane);
+  after_launch("prep_dhconv_cplx");
+}
+
 void launch_diagonal_contract(const bf16* c1, long long c1_plane, const float* w, int B, int C, int L, int M, int Lp,
                               bf16* c2, long long c2_plane, cudaStream_t stream) {
   ProfileScope prof("diagonal_contract", stream);
@@ -324,10 +349,20 @@ void launch_prep_norm_conv(const double* stats, const float* gamma, const float*
                            const float* w, const float* bias, int O, int Ip, bf16* wout, long long wplane, float* bout,
                            float* a_out, float* s_out, float* shift0_out, cudaStream_t stream) {
   ProfileScope prof("prep_norm_conv", stream);
-  dim3 grid(w ? O : 1, B);
-  size_t smem = (size_t)(2 * C + 128) * sizeof(float);
-  prep_norm_conv_kernel<<<grid, 128, smem, stream>>>(stats, gamma, beta, eps, HW, C, w, bias, O, Ip, wout, wplane, bout, a_out,
-                                                     s_out, shift0_out);
+  dim3 grid(w ? (O + 7) / 8 : 1, B);
+  size_t smem = (size_t)(2 * C) * sizeof(float);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = options().pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ACE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, prep_norm_conv_kernel, stats, gamma, beta, eps, HW, C, w, bias, O, Ip, wout, wplane, bout,
+                                    a_out, s_out, shift0_out));
   after_launch("prep_norm_conv");
 }
 

@@ -78,6 +78,12 @@ struct GemmOp {
   int Z1, Z2;
   Operand A, B;
   int n_lo_z1, n_hi_z1, k_lo_z1;
+  // Complex mode (dhconv): A holds two real matrices Ar, Ai of M x K each (Ai = A + a_part elements), B holds
+  // [Br | Bi] along its k axis (K + K columns), and the op computes the 2M x N real result
+  //   D[0:M]  = Ar Br - Ai Bi,   D[M:2M] = Ai Br + Ar Bi        (rows M..2M-1 are stored at row index m + M)
+  // i.e. exactly the real-ified GEMM with A' = [[Ar, -Ai], [Ai, Ar]] without materialising A'.
+  int cplx;
+  long long a_part;
   int bk_hint;  // 0 = kernel default (32); 64 = K extent per pipeline stage for K-major x K-major ops whose A streams from HBM
   EpiParams epi;
   const char* name;  // for error messages / profiling

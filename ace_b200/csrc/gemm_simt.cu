@@ -49,8 +49,17 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const __grid_constant__ G
       int m = m0 + mm, k = k0 + kk;
       float v = 0.f;
       if (m < op.M && k < op.K && k >= k_lo) {
-        const bf16* p = A + (long long)m * op.A.s_row + (long long)k * op.A.s_k;
-        v = __bfloat162float(p[0]) + __bfloat162float(p[op.A.plane]);
+        if (!op.cplx) {
+          const bf16* p = A + (long long)m * op.A.s_row + (long long)k * op.A.s_k;
+          v = __bfloat162float(p[0]) + __bfloat162float(p[op.A.plane]);
+        } else {
+          // op.M / op.K are the real-ified extents here (run_gemm_simt doubled them): A'[(ro,o)][(ri,i)]
+          const int Mh = op.M >> 1, Kh = op.K >> 1;
+          const int ro = m >= Mh, o = m - ro * Mh, ri = k >= Kh, i2 = k - ri * Kh;
+          const bf16* p = A + (ro != ri ? op.a_part : 0) + (long long)o * op.A.s_row + (long long)i2 * op.A.s_k;
+          v = __bfloat162float(p[0]) + __bfloat162float(p[op.A.plane]);
+          if (ro == 0 && ri == 1) v = -v;
+        }
       }
       As[kk][mm] = v;
     }
@@ -132,7 +141,13 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const __grid_constant__ G
 
 }  // namespace
 
-void run_gemm_simt(const GemmOp& op, cudaStream_t stream) {
+void run_gemm_simt(const GemmOp& op_in, cudaStream_t stream) {
+  GemmOp op = op_in;
+  if (op.cplx) {  // the SIMT kernel walks the real-ified problem
+    ACE_REQUIRE(!op.k_lo_z1, "gemm %s: complex mode with a triangular K range is not supported", op.name);
+    op.M *= 2;
+    op.K *= 2;
+  }
   ACE_REQUIRE(op.M > 0 && op.N > 0 && op.K > 0 && op.Z1 > 0 && op.Z2 > 0, "gemm %s: empty problem", op.name);
   ACE_REQUIRE(op.Z1 <= 65535 && op.Z2 <= 65535, "gemm %s: batch extent too large", op.name);
   int tiles_m = (op.M + BM - 1) / BM, tiles_n = (op.N + BN - 1) / BN;

@@ -54,21 +54,24 @@ constexpr int kThreadsUmma = 32 * (4 + kEpiWarps);
 constexpr int kStgBytesPerWarp = 2048;
 constexpr int kMaxSmem = 232448;  // 227 KB opt-in limit per CTA
 
-template <int BN_, bool A_MN_, bool B_MN_, uint32_t EF_, bool NC_, int BK_ = 32>
+template <int BN_, bool A_MN_, bool B_MN_, uint32_t EF_, bool NC_, int BK_ = 32, bool CPLX_ = false>
 struct Cfg {
   static constexpr int BM = 128, BN = BN_, BK = BK_;
-  static constexpr bool A_MN = A_MN_, B_MN = B_MN_, NC = NC_;
+  static constexpr bool A_MN = A_MN_, B_MN = B_MN_, NC = NC_, CPLX = CPLX_;
+  static constexpr int NACC = CPLX ? 2 : 1;  // accumulators per tile (complex mode: real and imaginary rows)
   static constexpr uint32_t EF = EF_;
   static constexpr int UMMA_K = 16;
   static constexpr int A_PLANE = BM * BK * 2;  // bytes
   static constexpr int B_PLANE = BN * BK * 2;
-  static constexpr int STAGE = 2 * (A_PLANE + B_PLANE);
+  static constexpr int STAGE = 2 * NACC * (A_PLANE + B_PLANE);  // complex mode: {Ar, Ai} x {hi, lo}, then {Br, Bi} x {hi, lo}
   static constexpr int STG_BYTES = kEpiWarps * kStgBytesPerWarp;
   static constexpr int MAX_STAGES = 8;
   static constexpr int BAR_BYTES = (2 * MAX_STAGES + 4) * 8 + 16;
   static constexpr int STAGES_RAW = (kMaxSmem - 1024 - STG_BYTES - BAR_BYTES) / STAGE;
   static constexpr int STAGES = STAGES_RAW > MAX_STAGES ? MAX_STAGES : STAGES_RAW;
-  static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
+  static constexpr int TMEM_COLS = (2 * NACC * BN <= 256) ? 256 : 512;
+  static_assert(2 * NACC * BN <= 512, "TMEM budget");
+  static_assert(!CPLX || (!A_MN && !B_MN && !NC), "complex mode: K-major operands, ROWC epilogue");
   static constexpr int SMEM_BYTES = STAGES * STAGE + STG_BYTES + BAR_BYTES + 1024;  // + alignment slack
   static_assert(BN % 64 == 0 && BN <= 256, "BN");
   static constexpr uint32_t K_LAYOUT = (BK == 64) ? 2u : 4u;  // K-major tiles: 128B swizzle (BK = 64) or 64B (BK = 32)
@@ -199,6 +202,7 @@ __device__ __forceinline__ void epilogue_rowc(const UmmaParams& p, const Tile& t
   const int m1 = grow / e.mdiv, mr = grow - m1 * e.mdiv;
   bf16* gbase = e.out + (long long)ti.z1 * e.o_z1 + (long long)ti.z2 * e.o_z2 + (long long)m1 * e.o_m1 + mr +
                 (long long)(ti.n_begin + cc) * e.o_n;
+  const int nch = (ti.n_count + 31) >> 5;  // 32-column chunks per accumulator
   const long long on4 = 4 * e.o_n;
   // deferred InstanceNorm of the A operand: per-row scale, constant folded into column 0 (thread = its own row)
   float a_scale = 1.f, a_shift0 = 0.f;
@@ -208,9 +212,12 @@ __device__ __forceinline__ void epilogue_rowc(const UmmaParams& p, const Tile& t
     a_scale = __ldg(e.ra_scale + i);
     a_shift0 = __ldg(e.ra_shift0 + i);
   }
-  for (int c = sub; c * 32 < ti.n_count; c += kEpiWarps / 4) {
+  for (int cc2 = sub; cc2 < C::NACC * nch; cc2 += kEpiWarps / 4) {
+    // complex mode: the second accumulator (imaginary rows) sits BN columns further and lands op.M rows further
+    const int part = (C::NACC == 2 && cc2 >= nch) ? 1 : 0;
+    const int c = cc2 - part * nch;
     float v[32];
-    ptx::tmem_ld_32x32(tacc + c * 32, v);
+    ptx::tmem_ld_32x32(tacc + part * C::BN + c * 32, v);
     ptx::tmem_ld_wait();
     if (e.flags & EPI_ROW_AFFINE) {
 #pragma unroll
@@ -221,7 +228,7 @@ __device__ __forceinline__ void epilogue_rowc(const UmmaParams& p, const Tile& t
 #pragma unroll
     for (int j = 0; j < 16; ++j) split2(v[2 * j], v[2 * j + 1], hw[j], lw[j]);
     const int nleft = ti.n_count - c * 32;  // columns of this chunk inside [n_begin, n_end)
-    bf16* g = gbase + (long long)(c * 32) * e.o_n;
+    bf16* g = gbase + (long long)(c * 32) * e.o_n + (long long)part * op.M;
 #pragma unroll
     for (int pl = 0; pl < 2; ++pl) {
 #pragma unroll
@@ -492,6 +499,10 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: everything above overlapped the tail of the previous kernel in the stream; its
+  // results (and the buffers it was still reading) may only be touched after this point
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const long long total = (long long)p.tiles_m * p.tiles_n * op.Z1 * op.Z2;
 
@@ -514,6 +525,18 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
             const uint32_t sA = sbase + stage * C::STAGE;
             const uint32_t sB = sA + 2 * C::A_PLANE;
             const int k0 = ti.k_begin + kc * BK;
+            if constexpr (C::CPLX) {
+              // {Ar, Ai} x {hi, lo} then {Br, Bi} x {hi, lo}; the part index rides on the z2 axis of the A map and
+              // is a K offset of op.K on the B map
+              const uint32_t sBc = sA + 4 * C::A_PLANE;
+#pragma unroll
+              for (int part = 0; part < 2; ++part)
+#pragma unroll
+                for (int pl = 0; pl < 2; ++pl) {
+                  ptx::tma_load_5d(sA + (2 * part + pl) * C::A_PLANE, &p.tmA, fb, k0, ti.m0, az1, part, pl);
+                  ptx::tma_load_5d(sBc + (2 * part + pl) * C::B_PLANE, &p.tmB, fb, k0 + part * op.K, ti.n_begin, bz1, bz2, pl);
+                }
+            } else
 #pragma unroll
             for (int pl = 0; pl < 2; ++pl) {
               if (!C::A_MN) {
@@ -557,7 +580,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
       ptx::tc_fence_after();
       const int n_eff = (ti.n_count + 15) & ~15;
       const uint32_t idesc = ptx::instr_desc_bf16(128, n_eff, C::A_MN ? 1 : 0, C::B_MN ? 1 : 0);
-      const uint32_t tmem_d = tmem_base + as * BN;
+      const uint32_t tmem_d = tmem_base + as * (C::NACC * BN);
       for (int kc = 0; kc < ti.num_kc; ++kc) {
         ptx::mbar_wait(full_bar(stage), phase);
         ptx::tc_fence_after();
@@ -565,7 +588,31 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
           const uint32_t sA = sbase + stage * C::STAGE;
           const uint64_t a_hi = descA0 + (uint64_t)(sA >> 4), a_lo = a_hi + (uint64_t)(C::A_PLANE >> 4);
           const uint64_t b_hi = a_hi - descA0 + descB0 + (uint64_t)((2 * C::A_PLANE) >> 4), b_lo = b_hi + (uint64_t)(C::B_PLANE >> 4);
-          if (!(p.dbg & 4)) {
+          if constexpr (C::CPLX) {
+            // planes in the stage: Ar_hi Ar_lo Ai_hi Ai_lo | Br_hi Br_lo Bi_hi Bi_lo
+            constexpr uint64_t AP = C::A_PLANE >> 4, BP = C::B_PLANE >> 4;
+            const uint64_t b0 = a_hi - descA0 + descB0 + 4 * AP;
+            const uint32_t tmem_r = tmem_base + as * (2 * BN), tmem_i = tmem_r + BN;
+            const uint32_t ineg = idesc | (1u << 13);  // negate A: -Ai * Bi
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk) {
+              const uint64_t ar_h = a_hi + kk * kstepA, ar_l = ar_h + AP, ai_h = ar_h + 2 * AP, ai_l = ar_h + 3 * AP;
+              const uint64_t br_h = b0 + kk * kstepB, br_l = br_h + BP, bi_h = br_h + 2 * BP, bi_l = br_h + 3 * BP;
+              const uint32_t first = (kc | kk) != 0 ? 1u : 0u;
+              ptx::umma_bf16(tmem_r, ar_h, br_h, idesc, first);
+              ptx::umma_bf16(tmem_r, ar_h, br_l, idesc, 1u);
+              ptx::umma_bf16(tmem_r, ar_l, br_h, idesc, 1u);
+              ptx::umma_bf16(tmem_r, ai_h, bi_h, ineg, 1u);
+              ptx::umma_bf16(tmem_r, ai_h, bi_l, ineg, 1u);
+              ptx::umma_bf16(tmem_r, ai_l, bi_h, ineg, 1u);
+              ptx::umma_bf16(tmem_i, ai_h, br_h, idesc, first);
+              ptx::umma_bf16(tmem_i, ai_h, br_l, idesc, 1u);
+              ptx::umma_bf16(tmem_i, ai_l, br_h, idesc, 1u);
+              ptx::umma_bf16(tmem_i, ar_h, bi_h, idesc, 1u);
+              ptx::umma_bf16(tmem_i, ar_h, bi_l, idesc, 1u);
+              ptx::umma_bf16(tmem_i, ar_l, bi_h, idesc, 1u);
+            }
+          } else if (!(p.dbg & 4)) {
 #pragma unroll
             for (int kk = 0; kk < BK / 16; ++kk) {
               ptx::umma_bf16(tmem_d, a_hi + kk * kstepA, b_hi + kk * kstepB, idesc, (kc | kk) != 0 ? 1u : 0u);
@@ -597,7 +644,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
       if constexpr (C::NC) epilogue_nc_prefetch<C>(p, ti, q, sub, lane);
       ptx::mbar_wait(tfull_bar(as), aph);
       ptx::tc_fence_after();
-      const uint32_t tacc = tmem_base + as * BN + ((uint32_t)(32 * q) << 16);
+      const uint32_t tacc = tmem_base + as * (C::NACC * BN) + ((uint32_t)(32 * q) << 16);
       if (!(p.dbg & 1)) {
         if constexpr (C::NC) epilogue_nc<C>(p, ti, tacc, q, sub, lane, stg);
         else epilogue_rowc<C>(p, ti, tacc, q, sub, lane, stg);
@@ -698,17 +745,34 @@ void launch(const GemmOp& op, cudaStream_t stream) {
   // tile shared by consecutive CTAs (they run concurrently, so the second reader hits L2)
   p.m_fastest = C::B_MN ? 1 : 0;
   const CUtensorMapSwizzle kswz = (C::BK == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-  if (!C::A_MN)
+  if (C::CPLX) {
+    Operand a = op.A;
+    a.s_z2 = op.a_part;  // the {real, imaginary} matrix index rides on the z2 axis of the map
+    make_tmap(&p.tmA, a, false, op.M, op.K, op.Z1, 2, C::BK, 128, kswz, &p.a_z1_on, &p.a_z2_on, op.name);
+    Operand b = op.B;
+    make_tmap(&p.tmB, b, false, op.N, 2LL * op.K, op.Z1, op.Z2, C::BK, C::BN, kswz, &p.b_z1_on, &p.b_z2_on, op.name);
+  } else if (!C::A_MN)
     make_tmap(&p.tmA, op.A, false, op.M, op.K, op.Z1, op.Z2, C::BK, 128, kswz, &p.a_z1_on, &p.a_z2_on, op.name);
   else
     make_tmap(&p.tmA, op.A, true, op.M, op.K, op.Z1, op.Z2, 64, C::BK, CU_TENSOR_MAP_SWIZZLE_128B, &p.a_z1_on, &p.a_z2_on, op.name);
-  if (!C::B_MN)
+  if (C::CPLX) {
+  } else if (!C::B_MN)
     make_tmap(&p.tmB, op.B, false, op.N, op.K, op.Z1, op.Z2, C::BK, C::BN, kswz, &p.b_z1_on, &p.b_z2_on, op.name);
   else
     make_tmap(&p.tmB, op.B, true, op.N, op.K, op.Z1, op.Z2, 64, C::BK, CU_TENSOR_MAP_SWIZZLE_128B, &p.b_z1_on, &p.b_z2_on, op.name);
   long long total = (long long)p.tiles_m * p.tiles_n * op.Z1 * op.Z2;
   int grid = (int)std::min<long long>(total, sm_count());
-  gemm_umma_kernel<C><<<grid, kThreadsUmma, C::SMEM_BYTES, stream>>>(p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreadsUmma);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = options().pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ACE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_umma_kernel<C>, p));
   after_launch(op.name);
   g_umma_count.fetch_add(1, std::memory_order_relaxed);
 }
@@ -742,6 +806,8 @@ bool classify(const GemmOp& op, Variant& v, const char** why) {
   if (op.A.plane <= 0 || op.B.plane <= 0) return fail("plane offset must be positive");
   const EpiParams& e = op.epi;
   const uint32_t f = e.flags;
+  if (op.cplx && (!a_k || !b_k || !aligned8(op.a_part) || op.k_lo_z1 || (op.K & 7)))
+    return fail("complex mode needs K-major operands, 16B-aligned parts and K % 8 == 0");
   if (f & (EPI_COL_BIAS | EPI_STATS)) return fail("column bias / column statistics are SIMT-only");
   v.a_mn = a_mn;
   v.b_mn = b_mn;
@@ -805,22 +871,34 @@ bool launch_variant(const GemmOp& op, const Variant& v, cudaStream_t s) {
   return false;
 }
 
-// 1x1 convolutions: weights (K-major) x activations (MN-major), BN = 256
-bool launch_conv(const GemmOp& op, const Variant& v, cudaStream_t s) {
-  if (!v.nc || v.a_mn || !v.b_mn) return false;
+// 1x1 convolutions: weights (K-major) x activations (MN-major); BN = 256 (default) or 192 (option "conv_bn")
+template <int BN>
+bool launch_conv_bn(const GemmOp& op, const Variant& v, cudaStream_t s) {
   switch (v.ef) {
-    case G | P: launch<Cfg<256, false, true, G | P, true>>(op, s); return true;
-    case AD | F: launch<Cfg<256, false, true, AD | F, true>>(op, s); return true;
-    case AD | P: launch<Cfg<256, false, true, AD | P, true>>(op, s); return true;
-    case AD | G | P: launch<Cfg<256, false, true, AD | G | P, true>>(op, s); return true;
-    case AD | G | F: launch<Cfg<256, false, true, AD | G | F, true>>(op, s); return true;
-    case RS | F: launch<Cfg<256, false, true, RS | F, true>>(op, s); return true;
-    case RS | P: launch<Cfg<256, false, true, RS | P, true>>(op, s); return true;
-    case F: launch<Cfg<256, false, true, F, true>>(op, s); return true;
-    case P: launch<Cfg<256, false, true, P, true>>(op, s); return true;
-    case G | F: launch<Cfg<256, false, true, G | F, true>>(op, s); return true;
+    case G | P: launch<Cfg<BN, false, true, G | P, true>>(op, s); return true;
+    case AD | F: launch<Cfg<BN, false, true, AD | F, true>>(op, s); return true;
+    case AD | P: launch<Cfg<BN, false, true, AD | P, true>>(op, s); return true;
+    case AD | G | P: launch<Cfg<BN, false, true, AD | G | P, true>>(op, s); return true;
+    case AD | G | F: launch<Cfg<BN, false, true, AD | G | F, true>>(op, s); return true;
+    case RS | F: launch<Cfg<BN, false, true, RS | F, true>>(op, s); return true;
+    case RS | P: launch<Cfg<BN, false, true, RS | P, true>>(op, s); return true;
+    case F: launch<Cfg<BN, false, true, F, true>>(op, s); return true;
+    case P: launch<Cfg<BN, false, true, P, true>>(op, s); return true;
+    case G | F: launch<Cfg<BN, false, true, G | F, true>>(op, s); return true;
     default: return false;
   }
+}
+bool launch_conv(const GemmOp& op, const Variant& v, cudaStream_t s) {
+  if (!v.nc || v.a_mn || !v.b_mn) return false;
+  int bn = options().conv_bn;
+  if (bn != 192 && bn != 256) {
+    // whole waves of tiles over the SMs; the narrower tile re-reads the weights more often (measured ~6 %)
+    const long long tm = (op.M + 127) / 128, z = (long long)op.Z1 * op.Z2, sms = sm_count();
+    const long long w256 = (tm * ((op.N + 255) / 256) * z + sms - 1) / sms * 256;
+    const long long w192 = (tm * ((op.N + 191) / 192) * z + sms - 1) / sms * 192;
+    bn = (w192 * 106 < w256 * 100) ? 192 : 256;
+  }
+  return bn == 192 ? launch_conv_bn<192>(op, v, s) : launch_conv_bn<256>(op, v, s);
 }
 
 bool dispatch(const GemmOp& op, bool dry, cudaStream_t s, const char** why) {
@@ -833,6 +911,11 @@ bool dispatch(const GemmOp& op, bool dry, cudaStream_t s, const char** why) {
     for (uint32_t x : ok) found |= (x == v.ef);
     if (!v.nc || !found) { if (why) *why = "epilogue combination not compiled for MN-major B"; return false; }
     if (!dry) launch_conv(op, v, s);
+    return true;
+  }
+  if (op.cplx) {
+    if (v.nc || (op.epi.flags & EPI_ROW_AFFINE)) { if (why) *why = "complex mode is compiled for the plain ROWC epilogue only"; return false; }
+    if (!dry) launch<Cfg<128, false, false, P, false, 32, true>>(op, s);
     return true;
   }
   const bool ok = (!v.nc && !v.a_mn) || (v.nc && (v.ef == P || v.ef == F));

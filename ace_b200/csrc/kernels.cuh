@@ -22,6 +22,9 @@ void launch_split_pad(const float* src, long long rows, int cols, int cols_pad, 
 //   row (ro,o), col (ri,i):  [[Wr, -Wi], [Wi, Wr]]
 void launch_prep_dhconv(const float* w, int Cin, int Cout, int L, bf16* dst, long long plane, cudaStream_t stream);
 
+// dhconv weight [Cin][Cout][L][2] -> planes [L][2 (re, im)][Cout][Cinp] for the complex GEMM mode (gemm.cuh)
+void launch_prep_dhconv_cplx(const float* w, int Cin, int Cout, int L, int Cinp, bf16* dst, long long plane, cudaStream_t stream);
+
 // diagonal operator (contractions.py:170-180) on the spectral layouts:
 //   c1 [B][L][M][2C] planes -> c2 [B][M][Lp][2C] planes, w fp32 [C][C][L][M][2]
 void launch_diagonal_contract(const bf16* c1, long long c1_plane, const float* w, int B, int C, int L, int M, int Lp,

@@ -45,7 +45,7 @@ struct ConvW {
 
 struct BlockW {
   DevBuf g0, b0, g1, b1;  // InstanceNorm affine
-  DevBuf spec;            // dhconv: planes [L][2C][2C]; diagonal: fp32 [C][C][L][M][2]
+  DevBuf spec;            // dhconv: planes [L][2 (re, im)][C][Cp]; diagonal: fp32 [C][C][L][M][2]
   long long spec_plane = 0;
   DevBuf fbias;           // spectral conv bias [C]
   DevBuf skip_total;      // inner_skip.bias + fbias
@@ -269,13 +269,17 @@ void forward(ace_sfno& n, const float* x, float* y, int B, cudaStream_t s) {
       run_gemm(sht_op_dft_inv_planes(pi, n.g.as<bf16>(), P_g, C, B, xn, P_act, act_b), s);
     }
     if (c.operator_type == 1) {
+      // complex GEMM per degree l: D[(ro,o)][m] = sum_i W[l][o][i] (complex) * c1[l][m][i] (complex)  (contractions.py:184-195)
       GemmOp op = make_gemm_op("dhconv");
-      op.M = 2 * C;
+      const int Cp = (int)round_up(C, 8);
+      op.cplx = 1;
+      op.M = C;
       op.N = pf.M;
-      op.K = 2 * C;
+      op.K = C;
       op.Z1 = pf.L;
       op.Z2 = B;
-      op.A = {w.spec.as<bf16>(), w.spec_plane, 2LL * C, 1, 4LL * C * C, 0};
+      op.a_part = (long long)C * Cp;
+      op.A = {w.spec.as<bf16>(), w.spec_plane, (long long)Cp, 1, 2LL * C * Cp, 0};
       op.B = {n.c1.as<bf16>(), P_c1, 2LL * C, 1, (long long)pf.M * 2 * C, pf.c1_elems(C)};
       op.n_hi_z1 = 1;  // order m <= degree l
       op.epi.flags = EPI_OUT_PLANES;
@@ -450,9 +454,10 @@ extern "C" int ace_sfno_set_param(ace_sfno* net, const char* name, const float* 
     else if (rest == "filter.filter.weight") {
       if (c.operator_type == 1) {
         ACE_REQUIRE(numel == (long long)C * C * c.lmax * 2, "%s: expected %lld elements, got %lld", name, (long long)C * C * c.lmax * 2, numel);
-        b.spec_plane = (long long)c.lmax * 4 * C * C;
+        const int Cp = (int)round_up(C, 8);
+        b.spec_plane = (long long)c.lmax * 2 * C * Cp;
         b.spec.ensure(2 * (size_t)b.spec_plane * sizeof(bf16));
-        launch_prep_dhconv(data_dev, C, C, c.lmax, b.spec.as<bf16>(), b.spec_plane, s);
+        launch_prep_dhconv_cplx(data_dev, C, C, c.lmax, Cp, b.spec.as<bf16>(), b.spec_plane, s);
       } else {
         ACE_REQUIRE(numel == (long long)C * C * c.lmax * c.mmax * 2, "%s: expected %lld elements, got %lld", name, (long long)C * C * c.lmax * c.mmax * 2, numel);
         copy_f32(b.spec, data_dev, numel, s);

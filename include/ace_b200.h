@@ -56,7 +56,11 @@ const char* ace_last_error(void);
  *                 instead of the tcgen05 kernel (both are CUDA; there is no CPU path)
  *   "split_terms" 3 (default) or 1 = plain bf16 products (fast, ~1e-2 accurate)
  *   "profile"     1 = time every launch with CUDA events (see ace_profile_report)
- *   "umma_bn"     0 (default: per-op choice) or 192 / 256: N tile of the tcgen05 kernel (SHT stages)
+ *   "umma_bn"     0 (default: per-op choice) or 128 / 192 / 256: N tile of the tcgen05 kernel (SHT stages)
+ *   "umma_bk"     0 (default: per-op hint) or 32 / 64: K extent per pipeline stage of the forward SHT stages
+ *   "conv_bn"     0 (default: per-op choice by wave quantisation) or 192 / 256: N tile of the 1x1-conv GEMMs
+ *   "pdl"         1 = launch the tcgen05 / prep kernels with programmatic dependent launch (default 0)
+ *   "dbg"         development switches of the tcgen05 kernel (non-zero values produce wrong results)
  * Read-only counters through ace_get_option: "count_umma" / "count_simt" = GEMMs launched on the
  * tcgen05 / SIMT kernel since load.                                                            */
 int ace_set_option(const char* key, int value);
