@@ -30,6 +30,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 STEPS_PER_YEAR = 1460  # 6-hourly
+WORKLOAD = "ACE2 1deg rollout (BASELINE configs[1]): 180x360, 44in/50out, embed 384, 8 SFNO blocks (dhconv, instance_norm), 6h steps, B=1 per GPU"
 IMG = (180, 360)
 N_PROG, N_FORCING, N_DIAG = 38, 6, 12
 EMBED, LAYERS = 384, 8
@@ -127,6 +128,16 @@ def algorithmic(B):
         "sht.dft_inv": dict(flops=0.0, bytes=act + spec, bound="hbm"),
         "norm_split": dict(flops=0.0, bytes=2.0 * act, bound="hbm"),
     }
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full capture."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get(kernel)
+    except Exception:  # noqa: BLE001
+        return None
 
 
 def sht_transform_bytes(B):
@@ -229,7 +240,7 @@ def run_reference(args):
         "impl": "reference", "metric": "simulated_years_per_day", "value": sypd, "unit": "sim-years/day",
         "n_gpus": args.gpus, "steps": r["steps"], "warmup": 1, "ms_per_step": r["sec_per_step"] * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "ACE2 1deg 180x360 44in/50out embed384 8xSFNO dhconv, B=1, 6h step (CPU reference path)"},
+        "config": {"workload": WORKLOAD, "impl_note": "reference algorithm on the host CPUs (oracle port: same torch CPU ops as the fme modules)"},
         "cpu_baseline": {"value": sypd, "unit": "sim-years/day", "cores": r["cores"], "kind": "port", "sample": sample},
         "e2e": {"value": sypd, "unit": "sim-years/day", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -244,14 +255,12 @@ def run_b200(args):
     import ace_b200
     from ace_b200 import _lib
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
+    from ace_b200 import parallel
+
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    rank, world, local_rank = parallel.init_from_env(backend="nccl", device=dev)
     B = args.batch
     K, Wm = args.steps, max(args.warmup, 3)
     H, Wd = IMG
@@ -267,14 +276,15 @@ def run_b200(args):
     net = net.to(dev).eval().requires_grad_(False)
     stepper = ace_b200.FusedStepper(net, in_names, out_names, means, stds, residual_prediction=False)
 
-    g = torch.Generator().manual_seed(1 + rank)
+    # ensemble sharding: this rank advances members member_slice(world * B) of the global ensemble
+    msl = parallel.member_slice(world * B, rank, world)
+    g = torch.Generator().manual_seed(1 + msl.start)
     prog0 = (torch.randn(B, N_PROG, H, Wd, generator=g)).to(dev)
     n_forc_steps = min(K, 64)  # forcing window resident on device, cycled
     forcing_dev = torch.randn(n_forc_steps, B, N_FORCING, H, Wd, generator=g).to(dev)
 
     def barrier():
-        if world > 1:
-            dist.barrier()
+        parallel.barrier()
         torch.cuda.synchronize(dev)
 
     # ---- eager warm-up: allocations, parameter upload, launch count per step
@@ -310,22 +320,14 @@ def run_b200(args):
     ev1.record()
     barrier()
     clocks = sampler.stop()
-    ms_total = ev0.elapsed_time(ev1)
-    t_ms = torch.tensor([ms_total], device=dev)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_total = float(t_ms.item())
+    ms_total = parallel.max_over_ranks(ev0.elapsed_time(ev1), device=dev)
     ms_per_step = ms_total / K
     steps_per_s = world * B * 1e3 / ms_per_step  # every rank advances B members per step
     value = steps_per_s * 86400.0 / STEPS_PER_YEAR
 
     # diagnostics reduction: the one collective of the data-parallel rollout (after the timed region)
-    gm = static["out"].mean(dim=(2, 3))  # [B, n_out] global means of the last step
-    if world > 1:
-        gathered = [torch.empty_like(gm) for _ in range(world)]
-        dist.all_gather(gathered, gm)
-        gm = torch.cat(gathered, 0)
-    finite = bool(torch.isfinite(gm).all().item())
+    gm = parallel.gather_members(static["out"].mean(dim=(2, 3)))  # [B_global, n_out] global means of the last step
+    finite = bool(torch.isfinite(gm).all().item()) and gm.shape[0] == world * B
 
     log(f"device-resident: {ms_per_step:.3f} ms/step; end-to-end loop")
     # ---- end-to-end through the public API with HOST buffers: H2D forcing + D2H outputs every step
@@ -350,16 +352,13 @@ def run_b200(args):
         e2e_step(t)
     ev1.record()
     barrier()
-    e_ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
-    if world > 1:
-        dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
-    e2e_ms_per_step = float(e_ms.item()) / K
+    e2e_ms_per_step = parallel.max_over_ranks(ev0.elapsed_time(ev1), device=dev) / K
     e2e_value = world * B * 1e3 / e2e_ms_per_step * 86400.0 / STEPS_PER_YEAR
     h2d = B * N_FORCING * HW * 4
     d2h = B * len(out_names) * HW * 4
 
     # ---- per-kernel CUDA-event timing (eager, same steps) for the roofline of the dominant kernel
-    roofline, roofline_sht, shares = None, None, None
+    roofline, roofline_sht, shares, kernels = None, None, None, None
     log("per-kernel event timing")
     if rank == 0:
         pk = peaks()
@@ -372,6 +371,17 @@ def run_b200(args):
         total_ms = sum(ms for _, ms in rep.values())
         shares = {k: round(ms / total_ms, 4) for k, (_, ms) in sorted(rep.items(), key=lambda kv: -kv[1][1])}
         alg = algorithmic(B)
+        kernels = {}
+        for name, (cnt_k, ms_k) in rep.items():
+            a_k = alg.get(name)
+            us_k = ms_k / cnt_k * 1e3
+            ent = {"us": round(us_k, 1), "launches_per_step": cnt_k // n_prof}
+            if a_k is not None:
+                if a_k["bound"] == "tensor":
+                    ent.update(bound="tensor", frac=round(a_k["flops"] / (us_k * 1e-6) / 1e12 / pk["bf16_tflops_sustained"], 3))
+                else:
+                    ent.update(bound="hbm", frac=round(a_k["bytes"] / (us_k * 1e-6) / 1e9 / pk["hbm_gbs"], 3))
+            kernels[name] = ent
         dom = max(rep.items(), key=lambda kv: kv[1][1])[0]
         cnt, ms = rep[dom]
         avg_s = ms / cnt * 1e-3
@@ -381,7 +391,7 @@ def run_b200(args):
                 ach = a["flops"] / avg_s / 1e12
                 peak = pk["bf16_tflops_sustained"]
                 roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                            "frac": ach / peak, "traffic": None,
+                            "frac": ach / peak, "traffic": ncu_traffic(dom),
                             "note": f"algorithmic fp32-equivalent FLOPs (2MNK); the kernel issues 3 bf16 MMAs per product, "
                                     f"so the tensor pipe runs at 3x this; peak = bf16 sustained of {pk['source']} "
                                     f"MEASURED_PEAKS.json; avg of {cnt} launches {avg_s*1e6:.1f} us (CUDA events)"}
@@ -389,7 +399,7 @@ def run_b200(args):
                 ach = a["bytes"] / avg_s / 1e9
                 peak = pk["hbm_gbs"]
                 roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                            "traffic": None, "note": f"algorithmic bytes / avg of {cnt} launches ({avg_s*1e6:.1f} us); peak of {pk['source']}"}
+                            "traffic": ncu_traffic(dom), "note": f"algorithmic bytes / avg of {cnt} launches ({avg_s*1e6:.1f} us); peak of {pk['source']}"}
         # BASELINE.json second metric: SHT achieved HBM GB/s (forward transform = DFT + Legendre kernels)
         if "sht.dft_fwd" in rep and "sht.legendre_fwd" in rep:
             t_f = (rep["sht.dft_fwd"][1] + rep["sht.legendre_fwd"][1]) / rep["sht.dft_fwd"][0] * 1e-3
@@ -414,16 +424,17 @@ def run_b200(args):
             "warmup": Wm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16x3 (split-bf16 3-term products, fp32 accumulate; fp32 I/O)", "data": "synthetic",
             "config": {
-                "workload": "ACE2 1deg rollout: 180x360, 44in/50out, embed 384, 8 SFNO blocks (dhconv, instance_norm), 6h steps",
+                "workload": WORKLOAD,
                 "members_per_gpu": B, "global_members": B * world, "parallelism": f"ensemble-dp{world}",
                 "weights": "random init (reference initialisation, seed 0)",
-                "l2": "per-step working set (3.4 GB dhconv weights + activations) >> 126 MB L2; no explicit flush",
+                "l2": "inputs larger than L2: one step streams 1.7 GB of dhconv weights + ~100 MB activation tensors per kernel (L2 = 126 MB); no explicit flush",
                 "timed": "CUDA-graph replay per step, forcing window resident in HBM",
             },
             "e2e": {"value": e2e_value, "unit": "sim-years/day", "ms_per_step": e2e_ms_per_step, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "path": "FusedStepper.step_packed (C ABI ace_stepper_step), pinned host forcing in, all 50 output fields out"},
             "gpu_launches": int(launches_per_step * K), "launches_per_step": int(launches_per_step),
             "clocks": clocks, "roofline": roofline, "roofline_sht": roofline_sht, "kernel_time_shares": shares,
+            "kernels": kernels,
             "cpu_baseline": cpu_baseline, "outputs_finite": finite,
         }
         print(json.dumps(line), flush=True)
