@@ -73,6 +73,8 @@ extern "C" int ace_set_option(const char* key, int value) {
   else if (!strcmp(key, "split_terms")) {
     ACE_REQUIRE(value == 1 || value == 3, "split_terms must be 1 or 3");
     options().split_terms = value;
+  } else if (!strcmp(key, "pair")) {
+    options().pair = value ? 1 : 0;
   } else if (!strcmp(key, "conv_bn")) {
     ACE_REQUIRE(value == 0 || value == 192 || value == 256, "conv_bn must be 0, 192 or 256");
     options().conv_bn = value;
@@ -98,6 +100,7 @@ extern "C" int ace_get_option(const char* key) {
   if (!strcmp(key, "count_umma")) return (int)g_umma_count.load();
   if (!strcmp(key, "count_simt")) return (int)g_simt_count.load();
   if (!strcmp(key, "umma_bn")) return options().umma_bn;
+  if (!strcmp(key, "pair")) return options().pair;
   if (!strcmp(key, "umma_bk")) return options().umma_bk;
   return -1;
 }

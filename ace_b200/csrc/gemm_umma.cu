@@ -54,15 +54,21 @@ constexpr int kThreadsUmma = 32 * (4 + kEpiWarps);
 constexpr int kStgBytesPerWarp = 2048;
 constexpr int kMaxSmem = 232448;  // 227 KB opt-in limit per CTA
 
-template <int BN_, bool A_MN_, bool B_MN_, uint32_t EF_, bool NC_, int BK_ = 32, bool CPLX_ = false>
+template <int BN_, bool A_MN_, bool B_MN_, uint32_t EF_, bool NC_, int BK_ = 32, bool CPLX_ = false, bool PAIR_ = false>
 struct Cfg {
   static constexpr int BM = 128, BN = BN_, BK = BK_;
   static constexpr bool A_MN = A_MN_, B_MN = B_MN_, NC = NC_, CPLX = CPLX_;
+  // PAIR: two CTAs of a cluster compute one 256 x BN tile with tcgen05.mma.cta_group::2 -- each CTA stages its own 128
+  // rows of A and HALF of the B tile (the tensor cores read the other half from the peer), which cuts the shared-memory
+  // and L2->SM operand traffic per SM by a third for a 256-wide tile
+  static constexpr bool PAIR = PAIR_;
+  static constexpr int BNL = PAIR ? BN / 2 : BN;  // B columns staged by this CTA
+  static constexpr int TILE_M = PAIR ? 256 : 128;
   static constexpr int NACC = CPLX ? 2 : 1;  // accumulators per tile (complex mode: real and imaginary rows)
   static constexpr uint32_t EF = EF_;
   static constexpr int UMMA_K = 16;
   static constexpr int A_PLANE = BM * BK * 2;  // bytes
-  static constexpr int B_PLANE = BN * BK * 2;
+  static constexpr int B_PLANE = BNL * BK * 2;
   static constexpr int STAGE = 2 * NACC * (A_PLANE + B_PLANE);  // complex mode: {Ar, Ai} x {hi, lo}, then {Br, Bi} x {hi, lo}
   static constexpr int STG_BYTES = kEpiWarps * kStgBytesPerWarp;
   static constexpr int MAX_STAGES = 8;
@@ -72,6 +78,7 @@ struct Cfg {
   static constexpr int TMEM_COLS = (2 * NACC * BN <= 256) ? 256 : 512;
   static_assert(2 * NACC * BN <= 512, "TMEM budget");
   static_assert(!CPLX || (!A_MN && !B_MN && !NC), "complex mode: K-major operands, ROWC epilogue");
+  static_assert(!PAIR || (!CPLX && BNL % 64 == 0), "pair mode");
   static constexpr int SMEM_BYTES = STAGES * STAGE + STG_BYTES + BAR_BYTES + 1024;  // + alignment slack
   static_assert(BN % 64 == 0 && BN <= 256, "BN");
   static constexpr uint32_t K_LAYOUT = (BK == 64) ? 2u : 4u;  // K-major tiles: 128B swizzle (BK = 64) or 64B (BK = 32)
@@ -85,7 +92,7 @@ struct Tile {
   int m0, n_begin, n_count, n_end, z1, z2, k_begin, num_kc;
 };
 
-template <int BN, int BK>
+template <int BN, int BK, int TILE_M = 128>
 __device__ __forceinline__ bool decode_tile(const UmmaParams& p, long long t, Tile& ti) {
   const GemmOp& op = p.op;
   int tn, tm;
@@ -106,7 +113,7 @@ __device__ __forceinline__ bool decode_tile(const UmmaParams& p, long long t, Ti
   const int n_lo = op.n_lo_z1 ? ti.z1 : 0;
   const int n_hi = op.n_hi_z1 ? min(op.N, ti.z1 + 1) : op.N;
   const int k_lo = op.k_lo_z1 ? ti.z1 : 0;
-  ti.m0 = tm * 128;
+  ti.m0 = tm * TILE_M;  // pair mode: the caller adds 128 * cluster rank
   ti.n_begin = max(tn * BN, (n_lo / 16) * 16);
   ti.n_end = min(tn * BN + BN, n_hi);
   ti.n_count = ti.n_end - ti.n_begin;
@@ -475,6 +482,9 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GemmOp& op = p.op;
+  constexpr bool PAIR = C::PAIR;
+  const uint32_t crank = PAIR ? ptx::cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs), 1 = peer
+  constexpr int NCTA = PAIR ? 2 : 1;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&p.tmA);
@@ -482,21 +492,27 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(full_bar(s), NCTA);  // pair: one arrive per CTA's producer, all bytes credited to the leader
       ptx::mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(tfull_bar(a), 1);
-      ptx::mbar_init(tempty_bar(a), kEpiWarps);  // one arrive per epilogue warp
+      ptx::mbar_init(tempty_bar(a), NCTA * kEpiWarps);  // one arrive per epilogue warp (of both CTAs)
     }
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
-    ptx::tmem_alloc(ptx::smem_u32((const void*)tmem_slot), C::TMEM_COLS);
-    ptx::tmem_relinquish();
+    if constexpr (PAIR) {
+      ptx::tmem_alloc_2sm(ptx::smem_u32((const void*)tmem_slot), C::TMEM_COLS);
+      ptx::tmem_relinquish_2sm();
+    } else {
+      ptx::tmem_alloc(ptx::smem_u32((const void*)tmem_slot), C::TMEM_COLS);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) ptx::cluster_sync();  // barriers of both CTAs exist before any remote arrive / multicast commit
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // programmatic dependent launch: everything above overlapped the tail of the previous kernel in the stream; its
@@ -505,20 +521,49 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const long long total = (long long)p.tiles_m * p.tiles_n * op.Z1 * op.Z2;
+  const long long t_first = PAIR ? (blockIdx.x >> 1) : blockIdx.x, t_step = PAIR ? (gridDim.x >> 1) : gridDim.x;
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp walks the loop, one elected lane issues) =====================
     int stage = 0;
     uint32_t phase = 0;
     Tile ti;
-    for (long long t = blockIdx.x; t < total; t += gridDim.x) {
-      if (!decode_tile<BN, BK>(p, t, ti)) continue;
+    for (long long t = t_first; t < total; t += t_step) {
+      if (!decode_tile<BN, BK, C::TILE_M>(p, t, ti)) continue;
       const int az1 = ti.z1 * p.a_z1_on, az2 = ti.z2 * p.a_z2_on, bz1 = ti.z1 * p.b_z1_on, bz2 = ti.z2 * p.b_z2_on;
       for (int kc = 0; kc < ti.num_kc; ++kc) {
         ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
         if (ptx::elect_one()) {
           const uint32_t fb = full_bar(stage);
-          if (p.dbg & 2) {
+          if constexpr (PAIR) {
+            // both CTAs fill their own stage; every byte is credited to the leader's barrier, which also collects one
+            // arrive per CTA
+            if (crank == 0) ptx::mbar_arrive_expect_tx(fb, (uint32_t)(2 * C::STAGE));
+            else ptx::mbar_arrive_leader(fb);
+            const uint32_t sA = sbase + stage * C::STAGE;
+            const uint32_t sB = sA + 2 * C::A_PLANE;
+            const int k0 = ti.k_begin + kc * BK;
+            // the MMA takes the first N/2 accumulator columns from the leader's B tile and the rest from the peer's
+            const int n_eff = (ti.n_count + 15) & ~15;
+            const int mrow = ti.m0 + 128 * (int)crank, ncol = ti.n_begin + (n_eff >> 1) * (int)crank;
+#pragma unroll
+            for (int pl = 0; pl < 2; ++pl) {
+              if (!C::A_MN) {
+                ptx::tma_load_5d_2sm(sA + pl * C::A_PLANE, &p.tmA, fb, k0, mrow, az1, az2, pl);
+              } else {
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+                  ptx::tma_load_5d_2sm(sA + pl * C::A_PLANE + a * BK * 128, &p.tmA, fb, mrow + 64 * a, k0, az1, az2, pl);
+              }
+              if (!C::B_MN) {
+                ptx::tma_load_5d_2sm(sB + pl * C::B_PLANE, &p.tmB, fb, k0, ncol, bz1, bz2, pl);
+              } else {
+#pragma unroll
+                for (int a = 0; a < C::BNL / 64; ++a)
+                  ptx::tma_load_5d_2sm(sB + pl * C::B_PLANE + a * BK * 128, &p.tmB, fb, ncol + 64 * a, k0, bz1, bz2, pl);
+              }
+            }
+          } else if (p.dbg & 2) {
             ptx::mbar_arrive(fb);
           } else {
             ptx::mbar_arrive_expect_tx(fb, (uint32_t)C::STAGE);
@@ -561,7 +606,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && crank == 0) {
     // ===================== MMA issuer (warp-uniform control flow keeps the descriptors in uniform registers) ==========
     // K-major (64B swizzle for BK = 32, 128B for BK = 64): rows of 2*BK bytes, 8-row groups SBO apart; a K-step is
     // 32 bytes inside the swizzled row.  MN-major (128B swizzle): [k][64 mn] atoms, 8-k groups SBO = 1024 B apart, the next
@@ -573,13 +618,13 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
     uint32_t phase = 0;
     uint32_t it = 0;
     Tile ti;
-    for (long long t = blockIdx.x; t < total; t += gridDim.x) {
-      if (!decode_tile<BN, BK>(p, t, ti)) continue;
+    for (long long t = t_first; t < total; t += t_step) {
+      if (!decode_tile<BN, BK, C::TILE_M>(p, t, ti)) continue;
       const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
       ptx::mbar_wait(tempty_bar(as), aph ^ 1u);
       ptx::tc_fence_after();
       const int n_eff = (ti.n_count + 15) & ~15;
-      const uint32_t idesc = ptx::instr_desc_bf16(128, n_eff, C::A_MN ? 1 : 0, C::B_MN ? 1 : 0);
+      const uint32_t idesc = ptx::instr_desc_bf16(C::TILE_M, n_eff, C::A_MN ? 1 : 0, C::B_MN ? 1 : 0);
       const uint32_t tmem_d = tmem_base + as * (C::NACC * BN);
       for (int kc = 0; kc < ti.num_kc; ++kc) {
         ptx::mbar_wait(full_bar(stage), phase);
@@ -612,6 +657,13 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
               ptx::umma_bf16(tmem_i, ar_h, bi_l, idesc, 1u);
               ptx::umma_bf16(tmem_i, ar_l, bi_h, idesc, 1u);
             }
+          } else if constexpr (PAIR) {
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk) {
+              ptx::umma_bf16_2sm(tmem_d, a_hi + kk * kstepA, b_hi + kk * kstepB, idesc, (kc | kk) != 0 ? 1u : 0u);
+              ptx::umma_bf16_2sm(tmem_d, a_hi + kk * kstepA, b_lo + kk * kstepB, idesc, 1u);
+              ptx::umma_bf16_2sm(tmem_d, a_lo + kk * kstepA, b_hi + kk * kstepB, idesc, 1u);
+            }
           } else if (!(p.dbg & 4)) {
 #pragma unroll
             for (int kk = 0; kk < BK / 16; ++kk) {
@@ -622,12 +674,16 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
               }
             }
           }
-          ptx::umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+          if constexpr (PAIR) ptx::umma_commit_2sm(empty_bar(stage));  // frees the slot in both CTAs
+          else ptx::umma_commit(empty_bar(stage));                     // frees the smem slot when these MMAs retire
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
-      if (ptx::elect_one()) ptx::umma_commit(tfull_bar(as));  // accumulator ready for the epilogue
+      if (ptx::elect_one()) {  // accumulator ready for the epilogue (of both CTAs)
+        if constexpr (PAIR) ptx::umma_commit_2sm(tfull_bar(as));
+        else ptx::umma_commit(tfull_bar(as));
+      }
       __syncwarp();
       ++it;
     }
@@ -638,9 +694,10 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
     uint8_t* stg = stg_all + (warp - 4) * kStgBytesPerWarp;
     uint32_t it = 0;
     Tile ti;
-    for (long long t = blockIdx.x; t < total; t += gridDim.x) {
-      if (!decode_tile<BN, BK>(p, t, ti)) continue;
+    for (long long t = t_first; t < total; t += t_step) {
+      if (!decode_tile<BN, BK, C::TILE_M>(p, t, ti)) continue;
       const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
+      ti.m0 += 128 * (int)crank;  // pair mode: this CTA owns the second 128 rows of the 256-row tile
       if constexpr (C::NC) epilogue_nc_prefetch<C>(p, ti, q, sub, lane);
       ptx::mbar_wait(tfull_bar(as), aph);
       ptx::tc_fence_after();
@@ -651,16 +708,21 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+      if (lane == 0) {
+        if constexpr (PAIR) ptx::mbar_arrive_leader(tempty_bar(as));
+        else ptx::mbar_arrive(tempty_bar(as));
+      }
       ++it;
     }
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) ptx::cluster_sync();  // the peer may still read this CTA's B half / signal its barriers
+  else __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if constexpr (PAIR) ptx::tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
+    else ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -737,7 +799,7 @@ void launch(const GemmOp& op, cudaStream_t stream) {
   }
   UmmaParams p;
   p.op = op;
-  p.tiles_m = (op.M + 127) / 128;
+  p.tiles_m = (op.M + C::TILE_M - 1) / C::TILE_M;
   p.tiles_n = (op.N + C::BN - 1) / C::BN;
   p.nterms = options().split_terms;
   p.dbg = options().dbg;
@@ -757,21 +819,28 @@ void launch(const GemmOp& op, cudaStream_t stream) {
     make_tmap(&p.tmA, op.A, true, op.M, op.K, op.Z1, op.Z2, 64, C::BK, CU_TENSOR_MAP_SWIZZLE_128B, &p.a_z1_on, &p.a_z2_on, op.name);
   if (C::CPLX) {
   } else if (!C::B_MN)
-    make_tmap(&p.tmB, op.B, false, op.N, op.K, op.Z1, op.Z2, C::BK, C::BN, kswz, &p.b_z1_on, &p.b_z2_on, op.name);
+    make_tmap(&p.tmB, op.B, false, op.N, op.K, op.Z1, op.Z2, C::BK, C::BNL, kswz, &p.b_z1_on, &p.b_z2_on, op.name);
   else
     make_tmap(&p.tmB, op.B, true, op.N, op.K, op.Z1, op.Z2, 64, C::BK, CU_TENSOR_MAP_SWIZZLE_128B, &p.b_z1_on, &p.b_z2_on, op.name);
   long long total = (long long)p.tiles_m * p.tiles_n * op.Z1 * op.Z2;
-  int grid = (int)std::min<long long>(total, sm_count());
+  int grid = C::PAIR ? 2 * (int)std::min<long long>(total, sm_count() / 2) : (int)std::min<long long>(total, sm_count());
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kThreadsUmma);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = options().pdl ? 1 : 0;
+  attr[0].val.programmaticStreamSerializationAllowed = (options().pdl && !C::PAIR) ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (C::PAIR) {
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
+  }
   ACE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_umma_kernel<C>, p));
   after_launch(op.name);
   g_umma_count.fetch_add(1, std::memory_order_relaxed);
@@ -850,6 +919,22 @@ bool classify(const GemmOp& op, Variant& v, const char** why) {
 
 constexpr uint32_t P = EPI_OUT_PLANES, F = EPI_OUT_F32, G = EPI_GELU, AD = EPI_ADD_F32, RS = EPI_RES_PLANES;
 
+bool launch_variant_pair(const GemmOp& op, const Variant& v, cudaStream_t s) {
+  if (!v.nc) {
+    if (v.a_mn || v.b_mn) return false;
+    launch<Cfg<256, false, false, P, false, 32, false, true>>(op, s);
+    return true;
+  }
+  if (v.b_mn) return false;
+  if (v.a_mn) {
+    if (v.ef == P) { launch<Cfg<256, true, false, P, true, 32, false, true>>(op, s); return true; }
+    if (v.ef == F) { launch<Cfg<256, true, false, F, true, 32, false, true>>(op, s); return true; }
+    return false;
+  }
+  if (v.ef == P) { launch<Cfg<256, false, false, P, true, 32, false, true>>(op, s); return true; }
+  if (v.ef == F) { launch<Cfg<256, false, false, F, true, 32, false, true>>(op, s); return true; }
+  return false;
+}
 template <int BN>
 bool launch_variant(const GemmOp& op, const Variant& v, cudaStream_t s) {
   if (!v.nc) {
@@ -872,6 +957,17 @@ bool launch_variant(const GemmOp& op, const Variant& v, cudaStream_t s) {
 }
 
 // 1x1 convolutions: weights (K-major) x activations (MN-major); BN = 256 (default) or 192 (option "conv_bn")
+bool launch_conv_pair(const GemmOp& op, const Variant& v, cudaStream_t s) {
+  switch (v.ef) {
+    case G | P: launch<Cfg<256, false, true, G | P, true, 32, false, true>>(op, s); return true;
+    case AD | P: launch<Cfg<256, false, true, AD | P, true, 32, false, true>>(op, s); return true;
+    case AD | G | P: launch<Cfg<256, false, true, AD | G | P, true, 32, false, true>>(op, s); return true;
+    case RS | P: launch<Cfg<256, false, true, RS | P, true, 32, false, true>>(op, s); return true;
+    case F: launch<Cfg<256, false, true, F, true, 32, false, true>>(op, s); return true;
+    case P: launch<Cfg<256, false, true, P, true, 32, false, true>>(op, s); return true;
+    default: return false;
+  }
+}
 template <int BN>
 bool launch_conv_bn(const GemmOp& op, const Variant& v, cudaStream_t s) {
   switch (v.ef) {
@@ -890,6 +986,7 @@ bool launch_conv_bn(const GemmOp& op, const Variant& v, cudaStream_t s) {
 }
 bool launch_conv(const GemmOp& op, const Variant& v, cudaStream_t s) {
   if (!v.nc || v.a_mn || !v.b_mn) return false;
+  if (options().pair && op.M > 128 && launch_conv_pair(op, v, s)) return true;
   int bn = options().conv_bn;
   if (bn != 192 && bn != 256) {
     // whole waves of tiles over the SMs; the narrower tile re-reads the weights more often (measured ~6 %)
@@ -922,6 +1019,7 @@ bool dispatch(const GemmOp& op, bool dry, cudaStream_t s, const char** why) {
   if (!ok) { if (why) *why = "epilogue combination not compiled for K-major B"; return false; }
   if (dry) return true;
   // N tile: least padded columns, ties to the larger tile
+  if (options().pair && op.M > 128 && launch_variant_pair(op, v, s)) return true;
   int bn = options().umma_bn;
   if (bn == 128 && !v.nc) return launch_variant<128>(op, v, s);
   if (bn != 192 && bn != 256) {

@@ -104,3 +104,30 @@ def test_umma_single_term_is_plain_bf16():
     err = (d1.double().cpu() - ref).abs().max() / ref.abs().max()
     assert err < 1e-5, float(err)  # exactly the hi*hi product
     assert (d1.double().cpu() - truth).abs().max() / truth.abs().max() > 1e-4  # and visibly worse than 3-term
+
+
+@pytest.mark.parametrize("layout", [0, 1, 2])
+@pytest.mark.parametrize(
+    "shape",
+    [
+        (256, 256, 64, 1),      # exactly one pair tile
+        (256, 256, 256, 1),     # pipeline wraps
+        (384, 512, 96, 1),      # second pair tile half empty (rows 256..383 only on the leader)
+        (1000, 384, 200, 2),    # ragged M, ragged N tile (128 valid columns), batch
+        (384, 8104, 48, 2),     # conv orientation: wide N with a ragged last tile (168 valid columns)
+        (520, 776, 96, 1),      # last N tile has 8 valid columns: 4 per CTA of the pair
+    ],
+)
+def test_umma_pair_gemm_matches_fp64(shape, layout):
+    """cta_group::2 variants: two CTAs of a cluster share one 256 x 256 tile."""
+    from ace_b200 import _lib
+
+    m, n, k, nb = shape
+    a, b, truth = _case(m, n, k, nb, layout, seed=4)
+    _lib.set_option("pair", 1)
+    try:
+        d1 = _gemm(a, b, m, n, k, nb, layout, impl=1)
+    finally:
+        _lib.set_option("pair", 0)
+    err = (d1.double().cpu() - truth).abs().max() / truth.abs().max()
+    assert err < TOL, float(err)
