@@ -74,7 +74,7 @@ extern "C" int ace_set_option(const char* key, int value) {
     ACE_REQUIRE(value == 1 || value == 3, "split_terms must be 1 or 3");
     options().split_terms = value;
   } else if (!strcmp(key, "pair")) {
-    options().pair = value ? 1 : 0;
+    options().pair = value < 0 ? -1 : (value ? 1 : 0);
   } else if (!strcmp(key, "conv_bn")) {
     ACE_REQUIRE(value == 0 || value == 192 || value == 256, "conv_bn must be 0, 192 or 256");
     options().conv_bn = value;

@@ -86,7 +86,7 @@ struct Options {
   int profile = 0;
   int force_simt = 0;
   int split_terms = 3;
-  int pair = 0;      // 1 = CTA-pair (cta_group::2, 256 x 256 tiles) variants of the tcgen05 kernel where compiled
+  int pair = -1;     // CTA-pair (cta_group::2, 256 x 256 tiles) variants: -1 = per-op choice (convolutions with M % 256 == 0), 0 = never, 1 = wherever compiled
   int conv_bn = 0;   // N tile of the 1x1-convolution GEMMs: 0 = per-op choice (wave quantisation), 192, 256
   int pdl = 0;       // programmatic dependent launch of the tcgen05 GEMM / prep kernels (prologue overlaps the previous kernel's tail)
   int dbg = 0;       // development switches of the tcgen05 kernel (results are wrong when non-zero)

@@ -193,57 +193,58 @@ __global__ void __launch_bounds__(kThreads) spec_complex_to_planes_kernel(const 
 // and fold them into the 1x1 convolution that consumes it:  W (a*h + s) + bias = (W diag(a)) h + (bias + W s):
 //   wout planes [B][O][Ip] = split(W[o][i] * a[i]),   bout[B][O] = bias[o] + sum_i W[o][i] * s[i]
 // Block (0, b) also publishes a, s and shift0 = 2*pi*s (the m = 0 DFT coefficient of the constant field s).
-__global__ void __launch_bounds__(256) prep_norm_conv_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(128) prep_norm_conv_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float eps, long long HW, int C,
                                                             const float* __restrict__ w, const float* __restrict__ bias, int O,
                                                             int Ip, bf16* __restrict__ wout, long long wplane,
                                                             float* __restrict__ bout, float* __restrict__ a_out,
                                                             float* __restrict__ s_out, float* __restrict__ shift0_out) {
-  // one warp per output row, 8 rows per block; griddepcontrol: the statistics come from the previous kernel
+  // griddepcontrol: the statistics come from the previous kernel in the stream
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  extern __shared__ float sm[];  // a[C], s[C]
-  float* sa = sm;
-  float* ss = sm + C;
-  const int b = blockIdx.y;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const double sum = stats[((long long)b * C + c) * 2], sq = stats[((long long)b * C + c) * 2 + 1];
-    const double mean = sum / (double)HW;
-    double var = sq / (double)HW - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const double a = (double)gamma[c] * rsqrt(var + (double)eps);
-    sa[c] = (float)a;
-    ss[c] = (float)((double)beta[c] - mean * a);
-  }
-  __syncthreads();
-  if (blockIdx.x == 0) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      a_out[(long long)b * C + c] = sa[c];
-      s_out[(long long)b * C + c] = ss[c];
-      shift0_out[(long long)b * C + c] = 6.283185307179586f * ss[c];
-    }
-  }
-  if (w == nullptr) return;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int o = blockIdx.x * 8 + warp;
-  if (o >= O) return;
-  const float* wr = w + (long long)o * C;
-  bf16* wo = wout + ((long long)b * O + o) * Ip;
+  // one block per output row o (blockIdx.x < O) plus one extra block (blockIdx.x == O) that publishes a, s, 2*pi*s;
+  // every thread derives the a_i, s_i it needs itself (4 channels per thread at C = 384), no shared staging
+  __shared__ float red[4];
+  const int b = blockIdx.y, o = blockIdx.x;
+  const bool publish = (o == O) || (w == nullptr);
+  const float* wr = publish ? nullptr : w + (long long)o * C;
+  bf16* wo = publish ? nullptr : wout + ((long long)b * O + o) * Ip;
   float dot = 0.f;
-  for (int i = lane; i < Ip; i += 32) {
-    float v = 0.f;
+  for (int i = threadIdx.x; i < Ip; i += blockDim.x) {
+    float a = 0.f, sh = 0.f;
     if (i < C) {
-      const float wi = __ldg(wr + i);
-      v = wi * sa[i];
-      dot = fmaf(wi, ss[i], dot);
+      const double sum = stats[((long long)b * C + i) * 2], sq = stats[((long long)b * C + i) * 2 + 1];
+      const double mean = sum / (double)HW;
+      double var = sq / (double)HW - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const double ad = (double)__ldg(gamma + i) * rsqrt(var + (double)eps);
+      a = (float)ad;
+      sh = (float)((double)__ldg(beta + i) - mean * ad);
     }
-    bf16 h, l;
-    split_bf16(v, h, l);
-    wo[i] = h;
-    wo[i + wplane] = l;
+    if (publish) {
+      if (i < C) {
+        a_out[(long long)b * C + i] = a;
+        s_out[(long long)b * C + i] = sh;
+        shift0_out[(long long)b * C + i] = 6.283185307179586f * sh;
+      }
+    } else {
+      float v = 0.f;
+      if (i < C) {
+        const float wi = __ldg(wr + i);
+        v = wi * a;
+        dot = fmaf(wi, sh, dot);
+      }
+      bf16 h, l;
+      split_bf16(v, h, l);
+      wo[i] = h;
+      wo[i + wplane] = l;
+    }
   }
+  if (publish) return;
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, d);
-  if (lane == 0) bout[(long long)b * O + o] = (bias ? bias[o] : 0.f) + dot;
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+  __syncthreads();
+  if (threadIdx.x == 0) bout[(long long)b * O + o] = (bias ? bias[o] : 0.f) + red[0] + red[1] + red[2] + red[3];
 }
 
 __global__ void vec_add_kernel(const float* a, const float* b, float* out, long long n) {
@@ -349,12 +350,11 @@ void launch_prep_norm_conv(const double* stats, const float* gamma, const float*
                            const float* w, const float* bias, int O, int Ip, bf16* wout, long long wplane, float* bout,
                            float* a_out, float* s_out, float* shift0_out, cudaStream_t stream) {
   ProfileScope prof("prep_norm_conv", stream);
-  dim3 grid(w ? (O + 7) / 8 : 1, B);
-  size_t smem = (size_t)(2 * C) * sizeof(float);
+  dim3 grid(w ? O + 1 : 1, B);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
-  cfg.blockDim = dim3(256);
-  cfg.dynamicSmemBytes = smem;
+  cfg.blockDim = dim3(128);
+  cfg.dynamicSmemBytes = 0;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

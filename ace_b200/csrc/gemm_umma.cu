@@ -986,7 +986,9 @@ bool launch_conv_bn(const GemmOp& op, const Variant& v, cudaStream_t s) {
 }
 bool launch_conv(const GemmOp& op, const Variant& v, cudaStream_t s) {
   if (!v.nc || v.a_mn || !v.b_mn) return false;
-  if (options().pair && op.M > 128 && launch_conv_pair(op, v, s)) return true;
+  // CTA pairs pay off when no half tile is wasted (measured: fc1 M=768 111 -> 95 us; M=384 ops gain nothing)
+  const bool want_pair = options().pair == 1 ? op.M > 128 : (options().pair < 0 && op.M % 256 == 0);
+  if (want_pair && launch_conv_pair(op, v, s)) return true;
   int bn = options().conv_bn;
   if (bn != 192 && bn != 256) {
     // whole waves of tiles over the SMs; the narrower tile re-reads the weights more often (measured ~6 %)
@@ -1019,7 +1021,7 @@ bool dispatch(const GemmOp& op, bool dry, cudaStream_t s, const char** why) {
   if (!ok) { if (why) *why = "epilogue combination not compiled for K-major B"; return false; }
   if (dry) return true;
   // N tile: least padded columns, ties to the larger tile
-  if (options().pair && op.M > 128 && launch_variant_pair(op, v, s)) return true;
+  if (options().pair == 1 && op.M > 128 && launch_variant_pair(op, v, s)) return true;
   int bn = options().umma_bn;
   if (bn == 128 && !v.nc) return launch_variant<128>(op, v, s);
   if (bn != 192 && bn != 256) {

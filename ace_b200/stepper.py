@@ -180,3 +180,73 @@ class FusedStepper:
             if outs is not None:
                 outs[t].copy_(st["out"], non_blocking=True)
         return outs, st["prog"].clone()
+
+    def _ensure_graph(self, prog0: torch.Tensor):
+        """Capture (once per batch size / device) the CUDA graph of one fused step on static buffers."""
+        B = prog0.shape[0]
+        st = self._static
+        if self._graph is None or st is None or st["B"] != B or st["prog"].device != prog0.device:
+            self.rollout(prog0, None if not self.forcing_names else torch.zeros(
+                1, B, len(self.forcing_names), *self.module.img_shape, device=prog0.device), 1, use_cuda_graph=True, keep_outputs=False)
+        return self._static, self._graph
+
+    def rollout_host(self, prog0: torch.Tensor, forcing_host: Optional[torch.Tensor], n_steps: int,
+                     out_host: Optional[torch.Tensor] = None):
+        """Autoregressive loop with HOST-resident forcing and outputs (the inference driver's situation: forcing windows come
+        from the data loader, outputs go to the writers; ``fme/core/generics/inference.py:117-166``).
+
+        forcing_host [>= n_steps (cycled), B, n_forcing, H, W] pinned; out_host [n_steps, B, n_out, H, W] pinned (or None).
+        Every step copies its forcing host->device and its outputs device->host; both copies run on side streams and overlap the
+        neighbouring steps' compute (double-buffered staging), the step itself is one CUDA-graph replay.
+        Returns the final prognostic state (device).  The caller synchronises before reading ``out_host``.
+        """
+        dev = prog0.device
+        st, graph = self._ensure_graph(prog0)
+        cur = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_h"):
+            self._h = None
+        h = self._h
+        if h is None or h["B"] != st["B"] or h["dev"] != dev:
+            h = dict(B=st["B"], dev=dev, s_in=torch.cuda.Stream(dev), s_out=torch.cuda.Stream(dev),
+                     fst=[torch.empty_like(st["forcing"]) for _ in range(2)] if st["forcing"] is not None else None,
+                     ost=[torch.empty_like(st["out"]) for _ in range(2)])
+            self._h = h
+        ev_in = [torch.cuda.Event() for _ in range(2)]        # forcing staged on device
+        ev_used = [torch.cuda.Event() for _ in range(2)]      # forcing stage consumed by the step
+        ev_ready = [torch.cuda.Event() for _ in range(2)]     # output staged for the host copy
+        ev_done = [torch.cuda.Event() for _ in range(2)]      # host copy of the output finished
+        st["prog"].copy_(prog0)
+        nf = forcing_host.shape[0] if forcing_host is not None else 0
+
+        def stage_forcing(t):
+            b = t & 1
+            with torch.cuda.stream(h["s_in"]):
+                if t >= 2:
+                    h["s_in"].wait_event(ev_used[b])
+                h["fst"][b].copy_(forcing_host[t % nf], non_blocking=True)
+                ev_in[b].record(h["s_in"])
+
+        if h["fst"] is not None and n_steps > 0:
+            h["s_in"].wait_stream(cur)
+            stage_forcing(0)
+        for t in range(n_steps):
+            b = t & 1
+            if h["fst"] is not None:
+                if t + 1 < n_steps:
+                    stage_forcing(t + 1)
+                cur.wait_event(ev_in[b])
+                st["forcing"].copy_(h["fst"][b], non_blocking=True)
+                ev_used[b].record(cur)
+            graph.replay()
+            if out_host is not None:
+                if t >= 2:
+                    cur.wait_event(ev_done[b])
+                h["ost"][b].copy_(st["out"], non_blocking=True)
+                ev_ready[b].record(cur)
+                with torch.cuda.stream(h["s_out"]):
+                    h["s_out"].wait_event(ev_ready[b])
+                    out_host[t].copy_(h["ost"][b], non_blocking=True)
+                    ev_done[b].record(h["s_out"])
+        cur.wait_stream(h["s_out"])
+        cur.wait_stream(h["s_in"])
+        return st["prog"].clone()

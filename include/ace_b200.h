@@ -59,6 +59,7 @@ const char* ace_last_error(void);
  *   "umma_bn"     0 (default: per-op choice) or 128 / 192 / 256: N tile of the tcgen05 kernel (SHT stages)
  *   "umma_bk"     0 (default: per-op hint) or 32 / 64: K extent per pipeline stage of the forward SHT stages
  *   "conv_bn"     0 (default: per-op choice by wave quantisation) or 192 / 256: N tile of the 1x1-conv GEMMs
+ *   "pair"        -1 (default: per-op choice) / 0 / 1: CTA-pair (tcgen05 cta_group::2) variants of the GEMM kernel
  *   "pdl"         1 = launch the tcgen05 / prep kernels with programmatic dependent launch (default 0)
  *   "dbg"         development switches of the tcgen05 kernel (non-zero values produce wrong results)
  * Read-only counters through ace_get_option: "count_umma" / "count_simt" = GEMMs launched on the

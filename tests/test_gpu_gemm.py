@@ -128,6 +128,6 @@ def test_umma_pair_gemm_matches_fp64(shape, layout):
     try:
         d1 = _gemm(a, b, m, n, k, nb, layout, impl=1)
     finally:
-        _lib.set_option("pair", 0)
+        _lib.set_option("pair", -1)
     err = (d1.double().cpu() - truth).abs().max() / truth.abs().max()
     assert err < TOL, float(err)

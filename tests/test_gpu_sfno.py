@@ -38,6 +38,7 @@ def test_net_matches_reference_vectors(name):
         ((48, 96), 6, 7, 32, 3, 2),      # every GEMM eligible for the tcgen05 kernel
         ((180, 360), 8, 8, 16, 2, 1),    # BASELINE configs[0] grid, reduced width
         ((64, 128), 5, 3, 64, 2, 3),
+        ((48, 96), 4, 4, 128, 2, 2),     # mlp hidden 256 -> fc1 runs on the CTA-pair (cta_group::2) variant
     ],
 )
 def test_net_tcgen05_path_vs_oracle(img, cin, cout, embed, layers, batch):

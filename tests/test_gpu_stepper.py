@@ -76,3 +76,24 @@ def test_rollout_graph_equals_eager_and_oracle():
         ref_t = torch.stack([out[n] for n in out_names], dim=1)
         assert field_rel_err(outs_g[t].cpu(), ref_t) < 3e-4 * (t + 1), t
         state = {n: out[n] for n in st.prognostic_names}
+
+
+def test_rollout_host_pipelined_equals_device_rollout():
+    """Host-resident forcing / outputs with copies on side streams == the device-resident graph rollout."""
+    img, in_names, out_names, means, stds, onet, st = _setup(False)
+    torch.manual_seed(3)
+    T, B = 5, 2
+    prog0 = torch.randn(B, 3, *img).cuda()
+    forcing = torch.randn(T, B, 2, *img)
+    outs_d, fin_d = st.rollout(prog0, forcing.cuda(), T, use_cuda_graph=True)
+    out_host = torch.empty(T, B, len(out_names), *img).pin_memory()
+    fin_h = st.rollout_host(prog0, forcing.pin_memory(), T, out_host)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(out_host, outs_d.cpu(), rtol=0, atol=0)
+    torch.testing.assert_close(fin_h, fin_d, rtol=0, atol=0)
+    # forcing window shorter than the rollout is cycled; a second call reuses the staging buffers
+    fin_h2 = st.rollout_host(prog0, forcing[:2].pin_memory(), 4, out_host[:4])
+    torch.cuda.synchronize()
+    outs_c, fin_c = st.rollout(prog0, forcing[[0, 1, 0, 1]].cuda(), 4, use_cuda_graph=True)
+    torch.testing.assert_close(out_host[:4], outs_c.cpu(), rtol=0, atol=0)
+    torch.testing.assert_close(fin_h2, fin_c, rtol=0, atol=0)
