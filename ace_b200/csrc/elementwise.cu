@@ -78,26 +78,6 @@ __global__ void __launch_bounds__(kThreads) split_pad_kernel(const float* __rest
   }
 }
 
-__global__ void __launch_bounds__(kThreads) prep_dhconv_kernel(const float* __restrict__ w, int Cin, int Cout, int L,
-                                                              bf16* __restrict__ dst, long long plane) {
-  // dst[l][ro*Cout + o][ri*Cin + i]
-  const long long total = (long long)L * 2 * Cout * 2 * Cin;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    int col = (int)(idx % (2 * Cin));
-    long long t = idx / (2 * Cin);
-    int row = (int)(t % (2 * Cout));
-    int l = (int)(t / (2 * Cout));
-    int ri = col / Cin, i = col % Cin, ro = row / Cout, o = row % Cout;
-    const float* p = w + (((long long)i * Cout + o) * L + l) * 2;
-    float wr = p[0], wi = p[1];
-    float v = (ro == ri) ? wr : (ro == 0 ? -wi : wi);
-    bf16 h, lo;
-    split_bf16(v, h, lo);
-    dst[idx] = h;
-    dst[idx + plane] = lo;
-  }
-}
-
 // dhconv weight [Cin][Cout][L][2] (reference layout) -> planes [L][2 (re, im)][Cout][Cinp] for the complex GEMM mode
 __global__ void __launch_bounds__(kThreads) prep_dhconv_cplx_kernel(const float* __restrict__ w, int Cin, int Cout, int L,
                                                                    int Cinp, bf16* __restrict__ dst, long long plane) {
@@ -313,12 +293,6 @@ void launch_split_pad(const float* src, long long rows, int cols, int cols_pad, 
   ProfileScope prof("split_pad", stream);
   split_pad_kernel<<<grid_for(rows * cols_pad, kThreads), kThreads, 0, stream>>>(src, rows, cols, cols_pad, dst, plane);
   after_launch("split_pad");
-}
-
-void launch_prep_dhconv(const float* w, int Cin, int Cout, int L, bf16* dst, long long plane, cudaStream_t stream) {
-  ProfileScope prof("prep_dhconv", stream);
-  prep_dhconv_kernel<<<grid_for((long long)L * 4 * Cin * Cout, kThreads), kThreads, 0, stream>>>(w, Cin, Cout, L, dst, plane);
-  after_launch("prep_dhconv");
 }
 
 void launch_prep_dhconv_cplx(const float* w, int Cin, int Cout, int L, int Cinp, bf16* dst, long long plane, cudaStream_t stream) {

@@ -2,7 +2,7 @@
 //
 //   for z2 in [0,Z2), z1 in [0,Z1):
 //     D[m][n] = sum_{k in [k_lo, K)} A_z[m][k] * B_z[n][k]      m in [0,M), n in [n_lo, n_hi)
-//     epilogue(D[m][n]) -> bias / addend / residual / GELU / per-column statistics / stores
+//     epilogue(D[m][n]) -> row affine / bias / addend / residual / GELU / per-row statistics / stores
 //
 // Operands live in HBM as "split-bf16 planes": two bf16 arrays (hi at `ptr`, lo at
 // `ptr + plane`), value = hi + lo.  Strides are in elements.  A and B may each be K-major
@@ -32,11 +32,9 @@ struct Operand {
 };
 
 enum EpiFlags : uint32_t {
-  EPI_COL_BIAS = 1u << 0,    // v += col_bias[z2*cb_z2 + n]
   EPI_ADD_F32 = 1u << 1,     // v += add[z2*add_z2 + m1*add_m1 + m0*add_m0 + n*add_n]
   EPI_RES_PLANES = 1u << 2,  // v += (res_hi + res_lo)[z2*res_z2 + m1*res_m1 + m0*res_m0 + n*res_n]
-  EPI_GELU = 1u << 3,        // v = gelu_erf(v)
-  EPI_STATS = 1u << 4,       // stats[(z2*stats_z2 + n)*2 + {0,1}] += {v, v*v}   (double atomics)
+  EPI_GELU = 1u << 3,        // v = exact (erf) GELU of v
   EPI_OUT_PLANES = 1u << 5,  // split-bf16 store
   EPI_OUT_F32 = 1u << 6,     // fp32 store
   EPI_ROW_BIAS = 1u << 7,    // v += row_bias[z2*rb_z2 + m]
@@ -51,8 +49,6 @@ enum EpiFlags : uint32_t {
 struct EpiParams {
   uint32_t flags;
   int mdiv;
-  const float* col_bias;
-  long long cb_z2;
   const float* row_bias;
   long long rb_z2;
   const float* ra_scale;
@@ -106,7 +102,6 @@ __device__ __forceinline__ float epi_value(const EpiParams& e, float acc, int m1
     const long long i = (long long)z2 * e.ra_z2 + m1;
     v = __ldg(e.ra_scale + i) * v + (n == 0 ? __ldg(e.ra_shift0 + i) : 0.f);
   }
-  if (e.flags & EPI_COL_BIAS) v += __ldg(e.col_bias + (long long)z2 * e.cb_z2 + n);
   if (e.flags & EPI_ROW_BIAS) v += __ldg(e.row_bias + (long long)z2 * e.rb_z2 + (long long)m1 * e.mdiv + m0);
   if (e.flags & EPI_ADD_F32) v += __ldg(e.add + (long long)z2 * e.add_z2 + (long long)m1 * e.add_m1 + (long long)m0 * e.add_m0 + (long long)n * e.add_n);
   if (e.flags & EPI_RES_PLANES) {

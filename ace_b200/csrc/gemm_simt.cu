@@ -24,7 +24,6 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const __grid_constant__ G
 
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
-  __shared__ float red[2][NT / 16][BN];
 
   const bf16* A = op.A.ptr + (long long)z1 * op.A.s_z1 + (long long)z2 * op.A.s_z2;
   const bf16* B = op.B.ptr + (long long)z1 * op.B.s_z1 + (long long)z2 * op.B.s_z2;
@@ -93,9 +92,6 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const __grid_constant__ G
   }
 
   const EpiParams& e = op.epi;
-  float csum[TN], csq[TN];
-#pragma unroll
-  for (int j = 0; j < TN; ++j) csum[j] = csq[j] = 0.f;
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     int m = m0 + ty * TM + i;
@@ -107,8 +103,6 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const __grid_constant__ G
       int n = n0 + tx * TN + j;
       if (n < n_lo || n >= n_hi) continue;
       float v = epi_value(e, acc[i][j], m1, mr, n, z2);
-      csum[j] += v;
-      csq[j] += v * v;
       rsum += v;
       rsq += v * v;
       epi_store(e, v, m1, mr, n, z1, z2);
@@ -117,24 +111,6 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const __grid_constant__ G
       double* st = e.stats + ((long long)z2 * e.stats_z2 + m) * 2;
       atomicAdd(st, (double)rsum);
       atomicAdd(st + 1, (double)rsq);
-    }
-  }
-  if (e.flags & EPI_STATS) {
-#pragma unroll
-    for (int j = 0; j < TN; ++j) {
-      red[0][ty][tx * TN + j] = csum[j];
-      red[1][ty][tx * TN + j] = csq[j];
-    }
-    __syncthreads();
-    if (tid < BN) {
-      int n = n0 + tid;
-      if (n >= n_lo && n < n_hi) {
-        double s = 0.0, q = 0.0;
-        for (int r = 0; r < NT / 16; ++r) { s += red[0][r][tid]; q += red[1][r][tid]; }
-        double* st = e.stats + ((long long)z2 * e.stats_z2 + n) * 2;
-        atomicAdd(st, s);
-        atomicAdd(st + 1, q);
-      }
     }
   }
 }

@@ -877,7 +877,6 @@ bool classify(const GemmOp& op, Variant& v, const char** why) {
   const uint32_t f = e.flags;
   if (op.cplx && (!a_k || !b_k || !aligned8(op.a_part) || op.k_lo_z1 || (op.K & 7)))
     return fail("complex mode needs K-major operands, 16B-aligned parts and K % 8 == 0");
-  if (f & (EPI_COL_BIAS | EPI_STATS)) return fail("column bias / column statistics are SIMT-only");
   v.a_mn = a_mn;
   v.b_mn = b_mn;
   v.ef = f & EF_MASK;
@@ -922,7 +921,8 @@ constexpr uint32_t P = EPI_OUT_PLANES, F = EPI_OUT_F32, G = EPI_GELU, AD = EPI_A
 bool launch_variant_pair(const GemmOp& op, const Variant& v, cudaStream_t s) {
   if (!v.nc) {
     if (v.a_mn || v.b_mn) return false;
-    launch<Cfg<256, false, false, P, false, 32, false, true>>(op, s);
+    if (options().umma_bk == 64 || (options().umma_bk == 0 && op.bk_hint == 64)) launch<Cfg<256, false, false, P, false, 64, false, true>>(op, s);
+    else launch<Cfg<256, false, false, P, false, 32, false, true>>(op, s);
     return true;
   }
   if (v.b_mn) return false;
@@ -1021,7 +1021,9 @@ bool dispatch(const GemmOp& op, bool dry, cudaStream_t s, const char** why) {
   if (!ok) { if (why) *why = "epilogue combination not compiled for K-major B"; return false; }
   if (dry) return true;
   // N tile: least padded columns, ties to the larger tile
-  if (options().pair == 1 && op.M > 128 && launch_variant_pair(op, v, s)) return true;
+  // forward SHT stages (K-major x K-major, ROWC) gain ~4 us each from CTA pairs when no half tile is wasted
+  const bool want_pair = options().pair == 1 ? op.M > 128 : (options().pair < 0 && !v.nc && !v.a_mn && !v.b_mn && op.M % 256 == 0);
+  if (want_pair && launch_variant_pair(op, v, s)) return true;
   int bn = options().umma_bn;
   if (bn == 128 && !v.nc) return launch_variant<128>(op, v, s);
   if (bn != 192 && bn != 256) {

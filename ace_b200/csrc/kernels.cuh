@@ -18,10 +18,6 @@ void launch_norm_split(const float* src, int B, int C, long long HW, const doubl
 void launch_split_pad(const float* src, long long rows, int cols, int cols_pad, bf16* dst, long long plane,
                       cudaStream_t stream);
 
-// dhconv weight [Cin][Cout][L][2] (fp32, reference layout) -> real-ified planes [L][2*Cout][2*Cin]:
-//   row (ro,o), col (ri,i):  [[Wr, -Wi], [Wi, Wr]]
-void launch_prep_dhconv(const float* w, int Cin, int Cout, int L, bf16* dst, long long plane, cudaStream_t stream);
-
 // dhconv weight [Cin][Cout][L][2] -> planes [L][2 (re, im)][Cout][Cinp] for the complex GEMM mode (gemm.cuh)
 void launch_prep_dhconv_cplx(const float* w, int Cin, int Cout, int L, int Cinp, bf16* dst, long long plane, cudaStream_t stream);
 

@@ -106,3 +106,35 @@ def test_module_contract():
     with pytest.raises(ValueError):
         with torch.no_grad():
             net(torch.zeros(1, 5, 16, 32, device="cuda"))
+
+
+@pytest.mark.timeout(900)
+def test_baseline_config_full_size_parity():
+    """BASELINE.json configs[1] at full size: ACE2 1 degree (180x360, 44 in / 50 out, embed 384, 8 blocks, dhconv,
+    instance_norm), B=1, one step; CUDA path through the C ABI vs the CPU oracle, rtol 1e-4 per output field."""
+    from ace_b200 import _lib
+    from oracle import sfno as osfno
+
+    fields = dict(embed_dim=384, num_layers=8, operator_type="dhconv")
+    torch.manual_seed(11)
+    onet = osfno.SphericalFourierNeuralOperatorNet((180, 360), 44, 50, **fields).eval()
+    g = torch.Generator().manual_seed(12)
+    with torch.no_grad():
+        for k, p in onet.named_parameters():
+            if k.endswith("bias") or "norm" in k:
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+            if k.endswith("filter.filter.weight"):
+                p.mul_(p.shape[0])  # O(1) spectral gain so the filter branch matters at random init
+    net = _b200_net((180, 360), 44, 50, fields)
+    net.load_state_dict(onet.state_dict())
+    net = net.cuda().eval()
+    x = torch.randn(1, 44, 180, 360, generator=g)
+    s0 = _lib.get_option("count_simt")
+    torch.set_num_threads(min(16, torch.get_num_threads()))
+    with torch.no_grad():
+        y = net(x.cuda())
+        ref = onet(x)
+    torch.cuda.synchronize()
+    assert _lib.get_option("count_simt") == s0, "a GEMM fell back to the SIMT kernel at the benchmark shape"
+    err = field_rel_err(y.cpu(), ref)
+    assert err < FIELD_RTOL, err

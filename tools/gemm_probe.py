@@ -27,6 +27,7 @@ if __name__ == "__main__":
     net = build(layers=layers)
     x = torch.randn(1, 44, *IMG, device="cuda")
     variants = [dict(), dict(pair=1)]
+    only = ('sht.dft_fwd', 'sht.legendre_fwd', 'mlp.fc1', 'prep_norm_conv')
     if len(sys.argv) > 2:
         variants = [json.loads(a) for a in sys.argv[2:]]
     base = dict(split_terms=3, umma_bn=0, umma_bk=0, dbg=0, conv_bn=0, pair=0)
