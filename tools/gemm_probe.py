@@ -26,11 +26,11 @@ if __name__ == "__main__":
     layers = int(sys.argv[1]) if len(sys.argv) > 1 else 2
     net = build(layers=layers)
     x = torch.randn(1, 44, *IMG, device="cuda")
-    variants = [dict(), dict(pair=1)]
-    only = ('sht.dft_fwd', 'sht.legendre_fwd', 'mlp.fc1', 'prep_norm_conv')
+    variants = [dict()]
+
     if len(sys.argv) > 2:
         variants = [json.loads(a) for a in sys.argv[2:]]
-    base = dict(split_terms=3, umma_bn=0, umma_bk=0, dbg=0, conv_bn=0, pair=0)
+    base = dict(split_terms=3, umma_bn=0, umma_bk=0, dbg=0, conv_bn=0, pair=-1)
     for v in variants:
         for k, val in {**base, **v}.items(): _lib.set_option(k, val)
         r = run(net, x)
