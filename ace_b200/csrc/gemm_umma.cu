@@ -45,6 +45,7 @@ struct UmmaParams {
   int nterms;
   int a_z1_on, a_z2_on, b_z1_on, b_z2_on;  // 0 when the operand does not vary along that batch axis
   int dbg;                                 // development switches (option "dbg"): 1 skip epilogue, 2 skip TMA, 4 skip MMA
+  int scalar_store;                        // epilogue stores element-wise (row groups / row starts not vector-aligned, e.g. odd nlat)
   int m_fastest;                           // tile order: consecutive tiles share the B (1) or the A (0) tile
 };
 
@@ -211,6 +212,14 @@ __device__ __forceinline__ void epilogue_rowc(const UmmaParams& p, const Tile& t
                 (long long)(ti.n_begin + cc) * e.o_n;
   const int nch = (ti.n_count + 31) >> 5;  // 32-column chunks per accumulator
   const long long on4 = 4 * e.o_n;
+  // element-wise fallback (rows of a 4-row group not contiguous / not 8-byte aligned): thread = its own row
+  unsigned short* own = nullptr;
+  if (p.scalar_store) {
+    const int orow2 = min(row0 + lane, op.M - 1);
+    const int om1 = orow2 / e.mdiv, omr = orow2 - om1 * e.mdiv;
+    own = reinterpret_cast<unsigned short*>(e.out) + (long long)ti.z1 * e.o_z1 + (long long)ti.z2 * e.o_z2 + (long long)om1 * e.o_m1 + omr +
+          (long long)ti.n_begin * e.o_n;
+  }
   // deferred InstanceNorm of the A operand: per-row scale, constant folded into column 0 (thread = its own row)
   float a_scale = 1.f, a_shift0 = 0.f;
   if (e.flags & EPI_ROW_AFFINE) {
@@ -235,6 +244,24 @@ __device__ __forceinline__ void epilogue_rowc(const UmmaParams& p, const Tile& t
 #pragma unroll
     for (int j = 0; j < 16; ++j) split2(v[2 * j], v[2 * j + 1], hw[j], lw[j]);
     const int nleft = ti.n_count - c * 32;  // columns of this chunk inside [n_begin, n_end)
+    if (p.scalar_store) {
+      if (row0 + lane < op.M) {
+        unsigned short* h = own + (long long)(c * 32) * e.o_n + (long long)part * op.M;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (2 * j < nleft) {
+            h[0] = (unsigned short)hw[j];
+            h[e.out_plane] = (unsigned short)lw[j];
+          }
+          if (2 * j + 1 < nleft) {
+            h[e.o_n] = (unsigned short)(hw[j] >> 16);
+            h[e.o_n + e.out_plane] = (unsigned short)(lw[j] >> 16);
+          }
+          h += 2 * e.o_n;
+        }
+      }
+      continue;
+    }
     bf16* g = gbase + (long long)(c * 32) * e.o_n + (long long)part * op.M;
 #pragma unroll
     for (int pl = 0; pl < 2; ++pl) {
@@ -288,7 +315,7 @@ template <class C, bool FULL>
 __device__ __forceinline__ void epilogue_nc_chunk(const EpiParams& e, float (&v)[32], int nvalid, int rows_valid, int lane,
                                                   uint4* s16, uint2* s8, const float* g_add, const bf16* g_res,
                                                   float* g_f32, bf16* g_pl, float rbias, float res_a, float res_s, bool do_stats,
-                                                  f2& ssum, f2& ssq) {
+                                                  f2& ssum, f2& ssq, bool scalar_store) {
   constexpr uint32_t EF = C::EF;
   const int fr = lane >> 2, fp = lane & 3;  // fp32 pass: rows it*8 + fr (it < 4), 16-byte piece fp
   const int pr = lane >> 3, pp = lane & 7;  // plane pass: rows it*4 + pr (it < 8), 8-byte piece pp
@@ -399,7 +426,16 @@ __device__ __forceinline__ void epilogue_nc_chunk(const EpiParams& e, float (&v)
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         const uint2 w = s8[swz8(it * 4 + pr, pp)];
-        if (FULL || (pp * 4 < nvalid && it * 4 + pr < rows_valid))
+        if (!FULL && scalar_store) {
+          // row starts not 8-byte aligned / N not a multiple of 4 (odd nlat): same coalescing, 2-byte stores
+          if (it * 4 + pr < rows_valid) {
+            unsigned short* d = reinterpret_cast<unsigned short*>(g_pl + (long long)(it * 4) * e.o_m0 + (pl ? e.out_plane : 0));
+            if (pp * 4 + 0 < nvalid) d[0] = (unsigned short)w.x;
+            if (pp * 4 + 1 < nvalid) d[1] = (unsigned short)(w.x >> 16);
+            if (pp * 4 + 2 < nvalid) d[2] = (unsigned short)w.y;
+            if (pp * 4 + 3 < nvalid) d[3] = (unsigned short)(w.y >> 16);
+          }
+        } else if (FULL || (pp * 4 < nvalid && it * 4 + pr < rows_valid))
           *reinterpret_cast<uint2*>(g_pl + (long long)(it * 4) * e.o_m0 + (pl ? e.out_plane : 0)) = w;
       }
       __syncwarp();
@@ -442,17 +478,17 @@ __device__ __forceinline__ void epilogue_nc(const UmmaParams& p, const Tile& ti,
     g_pl = e.out + (long long)ti.z1 * e.o_z1 + (long long)ti.z2 * e.o_z2 + (long long)(row0 + pr) * e.o_m0 + ti.n_begin + pp * 4;
 
   for (int c = sub; c * 32 < ti.n_count; c += kEpiWarps / 4) {
-    const int nvalid = min(32, ti.n_count - c * 32);  // multiple of 4 (host-checked)
+    const int nvalid = min(32, ti.n_count - c * 32);  // multiple of 4 (host-checked) unless scalar_store
     float v[32];
     ptx::tmem_ld_32x32(tacc + c * 32, v);
     ptx::tmem_ld_wait();
     const int co = c * 32;
-    if (nvalid == 32 && rows_valid >= 32)
+    if (nvalid == 32 && rows_valid >= 32 && !p.scalar_store)
       epilogue_nc_chunk<C, true>(e, v, nvalid, rows_valid, lane, s16, s8, g_add + co, g_res + co, g_f32 + co, g_pl + co, rbias,
-                                 res_a, res_s, do_stats, ssum, ssq);
+                                 res_a, res_s, do_stats, ssum, ssq, false);
     else
       epilogue_nc_chunk<C, false>(e, v, nvalid, rows_valid, lane, s16, s8, g_add + co, g_res + co, g_f32 + co, g_pl + co, rbias,
-                                  res_a, res_s, do_stats && row_ok, ssum, ssq);
+                                  res_a, res_s, do_stats && row_ok, ssum, ssq, p.scalar_store != 0);
   }
   if (do_stats && row_ok) {
     float s0, s1, q0, q1;
@@ -790,6 +826,8 @@ void make_tmap(CUtensorMap* tm, const Operand& o, bool mn_major, long long rows,
                           box[0], box[1]));
 }
 
+thread_local int t_scalar_store = 0;  // set by dispatch() for the launch it is about to make
+
 template <class C>
 void launch(const GemmOp& op, cudaStream_t stream) {
   static bool attr_set = false;
@@ -803,6 +841,7 @@ void launch(const GemmOp& op, cudaStream_t stream) {
   p.tiles_n = (op.N + C::BN - 1) / C::BN;
   p.nterms = options().split_terms;
   p.dbg = options().dbg;
+  p.scalar_store = t_scalar_store;
   // the operand that is re-read by neighbouring tiles should be the small one: keep the big streaming operand's
   // tile shared by consecutive CTAs (they run concurrently, so the second reader hits L2)
   p.m_fastest = C::B_MN ? 1 : 0;
@@ -852,6 +891,7 @@ bool aligned4(long long v) { return (v & 3) == 0; }
 // ---- which compiled variant (if any) serves this op ----
 struct Variant {
   bool a_mn, b_mn, nc;
+  bool scalar;  // element-wise stores (alignment of the vector paths not met)
   uint32_t ef;
 };
 
@@ -887,17 +927,24 @@ bool classify(const GemmOp& op, Variant& v, const char** why) {
   if ((f & EPI_RES_AFFINE) && !(f & EPI_RES_PLANES)) return fail("RES_AFFINE without RES_PLANES");
   if (v.ef == EPI_OUT_PLANES && !(f & (EPI_ROW_BIAS | EPI_ROW_STATS)) && e.o_m0 == 1 && e.o_n != 1) {
     v.nc = false;
-    // transposed 8-byte stores: groups of 4 rows must be contiguous and 8-byte aligned
-    if (!aligned4(op.M) || (e.mdiv < op.M && !aligned4(e.mdiv)) || !aligned4(e.o_m1) || !aligned4(e.o_n) || !aligned4(e.o_z1) ||
-        !aligned4(e.o_z2) || !aligned4(e.out_plane) || (((uintptr_t)e.out) & 7))
-      return fail("ROWC epilogue needs 4-row groups that are contiguous and 8B aligned");
+    // transposed 8-byte stores need groups of 4 rows that are contiguous and 8-byte aligned; otherwise (odd nlat) the
+    // same kernel stores element-wise
+    v.scalar = !aligned4(op.M) || (e.mdiv < op.M && !aligned4(e.mdiv)) || !aligned4(e.o_m1) || !aligned4(e.o_n) || !aligned4(e.o_z1) ||
+               !aligned4(e.o_z2) || !aligned4(e.out_plane) || (((uintptr_t)e.out) & 7);
+    if (v.scalar && op.cplx) return fail("complex mode needs the vectorised ROWC stores");
     return true;
   }
   // NC: columns contiguous, rows affine, everything 4-element aligned
   v.nc = true;
+  v.scalar = false;
   if (e.mdiv < op.M) return fail("NC epilogue needs affine rows (mdiv >= M)");
-  if (!aligned4(op.N)) return fail("NC epilogue needs N % 4 == 0");
   if (op.n_lo_z1 || op.n_hi_z1) return fail("NC epilogue does not take triangular N ranges");
+  if (planes && v.ef == EPI_OUT_PLANES && e.o_n == 1 &&
+      (!aligned4(op.N) || !aligned4(e.o_m0) || !aligned4(e.o_z1) || !aligned4(e.o_z2) || !aligned4(e.out_plane) || (((uintptr_t)e.out) & 7))) {
+    v.scalar = true;  // plain plane output with unaligned row starts (inverse Legendre at odd nlat): element-wise stores
+    return true;
+  }
+  if (!aligned4(op.N)) return fail("NC epilogue needs N % 4 == 0");
   if (planes) {
     if (e.o_n != 1 || !aligned4(e.o_m0) || !aligned4(e.o_z1) || !aligned4(e.o_z2) || !aligned4(e.out_plane) || (((uintptr_t)e.out) & 7))
       return fail("plane output not 8B-vectorisable");
@@ -1002,7 +1049,9 @@ bool launch_conv(const GemmOp& op, const Variant& v, cudaStream_t s) {
 
 bool dispatch(const GemmOp& op, bool dry, cudaStream_t s, const char** why) {
   Variant v;
+  v.scalar = false;
   if (!classify(op, v, why)) return false;
+  t_scalar_store = v.scalar ? 1 : 0;
   if (v.b_mn) {
     if (v.a_mn) { if (why) *why = "MN-major x MN-major is not compiled"; return false; }
     static const uint32_t ok[] = {G | P, AD | F, AD | P, AD | G | P, AD | G | F, RS | F, RS | P, F, P, G | F};

@@ -39,6 +39,7 @@ def test_net_matches_reference_vectors(name):
         ((180, 360), 8, 8, 16, 2, 1),    # BASELINE configs[0] grid, reduced width
         ((64, 128), 5, 3, 64, 2, 3),
         ((48, 96), 4, 4, 128, 2, 2),     # mlp hidden 256 -> fc1 runs on the CTA-pair (cta_group::2) variant
+        ((45, 96), 5, 3, 32, 2, 1),      # odd nlat (as 721x1440): element-wise store variants, still no SIMT fallback
     ],
 )
 def test_net_tcgen05_path_vs_oracle(img, cin, cout, embed, layers, batch):

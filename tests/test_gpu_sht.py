@@ -45,7 +45,7 @@ def test_live_reference_vectors_all_grids():
         assert _rel(x.cpu(), torch.from_numpy(g[f"c{i}.isht"])) < RTOL_FIELD, (i, grid)
 
 
-@pytest.mark.parametrize("shape,nf", [((48, 96), 8), ((180, 360), 8), ((64, 128), 12)])
+@pytest.mark.parametrize("shape,nf", [((48, 96), 8), ((180, 360), 8), ((64, 128), 12), ((45, 96), 8)])  # odd nlat: element-wise stores
 def test_tcgen05_path_vs_oracle(shape, nf):
     """Aligned shapes: every GEMM of the transform must run on the tcgen05 kernel and match the oracle."""
     import ace_b200
