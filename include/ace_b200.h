@@ -140,6 +140,19 @@ void ace_stepper_destroy(ace_stepper* st);
 int ace_stepper_step(ace_stepper* st, const float* prog_dev, const float* forcing_dev,
                      float* out_dev, float* next_prog_dev, int batch, void* stream);
 
+/* ---- device reductions of the inference aggregators ----------
+ * fme/core/metrics.py:35-197 (weighted_sum / weighted_mean / weighted_std / weighted_mean_bias /
+ * root_mean_squared_error) as used by fme/core/gridded_ops.py:284-360 (LatLonOperations): one pass,
+ * fp64 accumulation.  x_dev, t_dev: float32 [nfields][hw] (t_dev may be NULL), weights_dev: float32 [hw];
+ * out_dev: float64 [nfields][5] = {sum w x, sum w x^2, sum w (x-t), sum w (x-t)^2, sum w}; points with
+ * zero weight contribute nothing even if NaN (metrics.py:56-58). */
+int ace_weighted_moments(const float* x_dev, const float* t_dev, const float* weights_dev, long long nfields,
+                         long long hw, double* out_dev, void* stream);
+/* zonal mean (mean over longitude; gridded_ops.py:313-315): x_dev float32 [nfields][h][w] -> out_dev [nfields][h] */
+int ace_zonal_mean(const float* x_dev, long long nfields, int h, int w, float* out_dev, void* stream);
+/* fme/core/metrics.py:388-408 spherical_power_spectrum: complex64 [nfields][lmax][mmax] -> float32 [nfields][lmax] */
+int ace_power_spectrum(const float* coeffs_dev, long long nfields, int lmax, int mmax, float* out_dev, void* stream);
+
 /* ---- development hook: run one split-bf16 GEMM through both kernels (tests only) ------
  * D[z][m][n] = sum_k A[z][m][k] * B[z][n][k], fp32 in/out.  layout bit 0: A is stored MN-major
  * ([z][k][m]); bit 1: B is stored MN-major ([z][k][n]).  impl: 0 = SIMT kernel, 1 = tcgen05

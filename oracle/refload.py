@@ -166,6 +166,34 @@ class Params:
             setattr(self, k, v)
 
 
+def load_metrics():
+    """Namespace of the reference's fme/core/metrics.py, executed unmodified with stand-ins for its two imports
+    (``torch_harmonics``: only used in a type annotation there; ``fme.core.constants``: executed from the tree)."""
+    if "metrics" in _CACHE:
+        return _CACHE["metrics"]
+    load()  # installs the torch_harmonics stand-in
+    sys.dont_write_bytecode = True
+    consts = types.ModuleType("fme.core.constants")
+    with open(os.path.join(REFERENCE_ROOT, "fme", "core", "constants.py")) as f:
+        exec(compile(f.read(), "fme/core/constants.py", "exec"), consts.__dict__)
+    saved = {k: sys.modules.get(k) for k in ("fme", "fme.core", "fme.core.constants")}
+    try:
+        pkg, core = types.ModuleType("fme"), types.ModuleType("fme.core")
+        pkg.__path__, core.__path__ = [], []
+        sys.modules.update({"fme": pkg, "fme.core": core, "fme.core.constants": consts})
+        ns = {"__name__": "fme_core_metrics"}
+        with open(os.path.join(REFERENCE_ROOT, "fme", "core", "metrics.py")) as f:
+            exec(compile(f.read(), "fme/core/metrics.py", "exec"), ns)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    _CACHE["metrics"] = types.SimpleNamespace(**{k: v for k, v in ns.items() if callable(v)})
+    return _CACHE["metrics"]
+
+
 def build_reference_net(img_shape, in_chans, out_chans, **builder_fields):
     """The net exactly as SphericalFourierNeuralOperatorBuilder.build makes it (fme/ace/registry/sfno.py:44-61)."""
     ns = load()
