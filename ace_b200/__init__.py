@@ -7,6 +7,7 @@ Public surface (mirrors the reference interfaces it replaces; see INTEGRATION.md
   ModuleSelector, DatasetInfo                  <- fme.ace.registry.sfno / fme.core.registry.module
   FusedStepper                                 <- device work of fme.core.step.single_module.step_with_adjustments
   metrics.LatLonOperations, spherical_power_spectrum <- fme.core.gridded_ops.LatLonOperations / fme.core.metrics (device reductions)
+  HealpixSHT, HealpixISHT                      <- fme.core.cuhpx.sht.SHT / iSHT (HEALPix ring-order transform)
   parallel                                     <- data-parallel surface of fme.core.distributed (ensemble sharding, one gather)
 """
 from ._lib import AceError, get_option, launch_count, set_option  # noqa: F401
@@ -22,5 +23,6 @@ from .sht import InverseRealSHT, RealSHT, patch_torch_harmonics  # noqa: F401
 from .stepper import FusedStepper  # noqa: F401
 from . import parallel  # noqa: F401
 from . import metrics  # noqa: F401
+from .healpix import HealpixISHT, HealpixSHT  # noqa: F401
 
 __version__ = "0.1.0"

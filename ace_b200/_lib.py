@@ -70,6 +70,8 @@ SIGNATURES = {
     "ace_stepper_destroy": (None, [_VP]),
     "ace_stepper_step": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _VP]),
     "ace_dev_gemm": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP]),
+    "ace_hpx_forward": (_I, [_VP, _I, _VP, _VP, _LL, _VP]),
+    "ace_hpx_inverse": (_I, [_VP, _I, _VP, _VP, _LL, _VP]),
     "ace_weighted_moments": (_I, [_VP, _VP, _VP, _LL, _LL, _VP, _VP]),
     "ace_zonal_mean": (_I, [_VP, _LL, _I, _I, _VP, _VP]),
     "ace_power_spectrum": (_I, [_VP, _LL, _I, _I, _VP, _VP]),

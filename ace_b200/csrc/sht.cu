@@ -237,6 +237,14 @@ static void plan_ensure_ws(ace_sht_plan& p, long long nf, cudaStream_t s) {
 
 // ------------------------------------------------------------------------------------ C ABI
 
+// (internal, used by healpix.cu) make the plan's standalone-transform workspaces valid for `nfields` fields
+extern "C" int ace_sht_plan_reserve(ace_sht_plan* plan, long long nfields, void* stream) {
+  ACE_API_BEGIN
+  ACE_REQUIRE(plan != nullptr, "ace_sht_plan_reserve: null plan");
+  if (nfields != plan->ws_fields_layout) plan_ensure_ws(*plan, nfields, (cudaStream_t)stream);
+  ACE_API_END
+}
+
 extern "C" int ace_sht_plan_create(int nlat, int nlon, int lmax, int mmax, const double* legendre_fwd_host,
                                    const double* legendre_inv_host, ace_sht_plan** out) {
   ACE_API_BEGIN

@@ -140,6 +140,15 @@ void ace_stepper_destroy(ace_stepper* st);
 int ace_stepper_step(ace_stepper* st, const float* prog_dev, const float* forcing_dev,
                      float* out_dev, float* next_prog_dev, int batch, void* stream);
 
+/* ---- HEALPix spherical harmonic transform ----------------------
+ * fme/core/cuhpx/sht.py:32-98 (SHT) and :101-153 (iSHT) with fme/core/cuhpx/tools.py:34-83 (per-ring rfft / irfft +
+ * phase shift).  `plan` is an ace_sht_plan created with nlat = 4*nside - 1 (the iso-latitude rings), nlon = 4*nside and
+ * the HEALPix Legendre tables [mmax][lmax][4*nside - 1] (ring quadrature weights folded into the forward table, no
+ * Condon-Shortley sign: tools.py:288-336).  Pixels in RING order.
+ * x_dev: float32 [nfields][12*nside^2]  <->  coeffs_dev: complex64 [nfields][lmax][mmax] */
+int ace_hpx_forward(ace_sht_plan* plan, int nside, const float* x_dev, float* coeffs_dev, long long nfields, void* stream);
+int ace_hpx_inverse(ace_sht_plan* plan, int nside, const float* coeffs_dev, float* x_dev, long long nfields, void* stream);
+
 /* ---- device reductions of the inference aggregators ----------
  * fme/core/metrics.py:35-197 (weighted_sum / weighted_mean / weighted_std / weighted_mean_bias /
  * root_mean_squared_error) as used by fme/core/gridded_ops.py:284-360 (LatLonOperations): one pass,

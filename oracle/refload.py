@@ -194,6 +194,39 @@ def load_metrics():
     return _CACHE["metrics"]
 
 
+def load_cuhpx():
+    """Namespace with the reference's cuHPX ``SHT`` / ``iSHT`` classes and ``apply_ring_weight`` (fme/core/cuhpx/{tools,sht}.py
+    executed unmodified; ``fme.core.device.get_device`` -> CPU; the ring-weight data files are read from the reference tree)."""
+    if "cuhpx" in _CACHE:
+        return _CACHE["cuhpx"]
+    if not available():
+        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
+    sys.dont_write_bytecode = True
+    names = ("fme", "fme.core", "fme.core.cuhpx", "fme.core.cuhpx.tools", "fme.core.device")
+    saved = {k: sys.modules.get(k) for k in names}
+    try:
+        mods = {k: types.ModuleType(k) for k in names}
+        for k in ("fme", "fme.core", "fme.core.cuhpx"):
+            mods[k].__path__ = []
+        mods["fme.core.device"].get_device = lambda: torch.device("cpu")
+        sys.modules.update(mods)
+        tools = mods["fme.core.cuhpx.tools"]
+        with open(os.path.join(REFERENCE_ROOT, "fme", "core", "cuhpx", "tools.py")) as f:
+            exec(compile(f.read(), "fme/core/cuhpx/tools.py", "exec"), tools.__dict__)
+        tools.DATAPATH = os.path.join(REFERENCE_ROOT, "fme", "core", "cuhpx", "data")
+        ns = {"__name__": "fme_core_cuhpx_sht"}
+        with open(os.path.join(REFERENCE_ROOT, "fme", "core", "cuhpx", "sht.py")) as f:
+            exec(compile(f.read(), "fme/core/cuhpx/sht.py", "exec"), ns)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    _CACHE["cuhpx"] = types.SimpleNamespace(SHT=ns["SHT"], iSHT=ns["iSHT"], apply_ring_weight=tools.apply_ring_weight)
+    return _CACHE["cuhpx"]
+
+
 def build_reference_net(img_shape, in_chans, out_chans, **builder_fields):
     """The net exactly as SphericalFourierNeuralOperatorBuilder.build makes it (fme/ace/registry/sfno.py:44-61)."""
     ns = load()
