@@ -44,6 +44,9 @@ class StepConfig(ctypes.Structure):
         ("out_mean_host", ctypes.POINTER(ctypes.c_float)),
         ("out_std_host", ctypes.POINTER(ctypes.c_float)),
         ("residual_prediction", ctypes.c_int),
+        ("out_force_positive_host", ctypes.POINTER(ctypes.c_int)),
+        ("ocean_out_index", ctypes.c_int),
+        ("ocean_interpolate", ctypes.c_int),
     ]
 
 
@@ -68,7 +71,7 @@ SIGNATURES = {
     "ace_sfno_query": (_I, [_VP, ctypes.POINTER(_I), ctypes.POINTER(_I), ctypes.POINTER(_LL)]),
     "ace_stepper_create": (_I, [_VP, ctypes.POINTER(StepConfig), ctypes.POINTER(_VP)]),
     "ace_stepper_destroy": (None, [_VP]),
-    "ace_stepper_step": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _VP]),
+    "ace_stepper_step": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _VP]),
     "ace_dev_gemm": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP]),
     "ace_hpx_forward": (_I, [_VP, _I, _VP, _VP, _LL, _VP]),
     "ace_hpx_inverse": (_I, [_VP, _I, _VP, _VP, _LL, _VP]),

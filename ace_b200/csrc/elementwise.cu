@@ -255,6 +255,8 @@ __global__ void __launch_bounds__(kThreads) unpack_denormalize_kernel(const floa
                                                                      const float* __restrict__ mean,
                                                                      const float* __restrict__ std, int residual,
                                                                      int n_out, int n_in, int n_prog, long long HW,
+                                                                     const int* __restrict__ clamp, int ocean_out,
+                                                                     int ocean_interp, const float* __restrict__ ocean,
                                                                      float* __restrict__ out,
                                                                      float* __restrict__ next_prog) {
   const int bc = blockIdx.y;
@@ -266,10 +268,18 @@ __global__ void __launch_bounds__(kThreads) unpack_denormalize_kernel(const floa
   float* d = out + (long long)bc * HW;
   float* np = (p >= 0 && next_prog != nullptr) ? next_prog + ((long long)b * n_prog + p) * HW : nullptr;
   const float mu = mean[c], sd = std[c];
+  const bool pos = clamp[c] != 0;
+  const float* om = (c == ocean_out) ? ocean + (long long)b * 2 * HW : nullptr;  // {mask, target}
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
     float v = s[i];
     if (r) v += r[i];
     v = v * sd + mu;
+    if (pos) v = (v < 0.f) ? 0.f : v;  // torch.clamp(min=0): NaN stays NaN
+    if (om) {
+      const float m = om[i], tgt = om[HW + i];
+      if (ocean_interp) v = m * tgt + (1.f - m) * v;
+      else if ((int)rintf(m) == 1) v = tgt;
+    }
     d[i] = v;
     if (np) np[i] = v;
   }
@@ -357,10 +367,11 @@ void launch_pack_normalize(const float* prog, const float* forcing, int n_prog, 
 
 void launch_unpack_denormalize(const float* y, const float* x_norm, const int* out_prog_index, const int* prog_in_chan,
                                const float* mean, const float* std, int residual, int B, int n_out, int n_in,
-                               int n_prog, long long HW, float* out, float* next_prog, cudaStream_t stream) {
+                               int n_prog, long long HW, const int* clamp, int ocean_out, int ocean_interp, const float* ocean,
+                               float* out, float* next_prog, cudaStream_t stream) {
   ProfileScope prof("unpack_denormalize", stream);
   dim3 grid(grid_for(HW, kThreads, 64), B * n_out);
-  unpack_denormalize_kernel<<<grid, kThreads, 0, stream>>>(y, x_norm, out_prog_index, prog_in_chan, mean, std, residual, n_out, n_in, n_prog, HW, out, next_prog);
+  unpack_denormalize_kernel<<<grid, kThreads, 0, stream>>>(y, x_norm, out_prog_index, prog_in_chan, mean, std, residual, n_out, n_in, n_prog, HW, clamp, ocean_out, ocean_interp, ocean, out, next_prog);
   after_launch("unpack_denormalize");
 }
 

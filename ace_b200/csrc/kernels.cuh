@@ -46,9 +46,12 @@ void launch_vec_add(const float* a, const float* b, float* out, long long n, cud
 void launch_pack_normalize(const float* prog, const float* forcing, int n_prog, int n_forcing, const int* kind,
                            const int* index, const float* mean, const float* std, int B, int n_in, long long HW,
                            float* x, cudaStream_t stream);
-// stepper: (residual add) + denormalise + scatter to next state
+// stepper: (residual add) + denormalise + ForcePositive clamp + ocean prescriber + scatter to next state
+//   clamp[c] != 0: v = max(v, 0) (corrector/utils.py:26-43); channel ocean_out: v = target where round(mask) == 1, or the
+//   linear blend when ocean_interp (prescriber.py:94-108); ocean = [B][2][HW] {mask, target}
 void launch_unpack_denormalize(const float* y, const float* x_norm, const int* out_prog_index, const int* prog_in_chan,
                                const float* mean, const float* std, int residual, int B, int n_out, int n_in,
-                               int n_prog, long long HW, float* out, float* next_prog, cudaStream_t stream);
+                               int n_prog, long long HW, const int* clamp, int ocean_out, int ocean_interp, const float* ocean,
+                               float* out, float* next_prog, cudaStream_t stream);
 
 }  // namespace ace

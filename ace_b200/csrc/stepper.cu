@@ -13,7 +13,8 @@ struct ace_stepper {
   ace_sfno* net;
   int n_in, n_out, n_prog, n_forcing, residual;
   long long HW;
-  ace::DevBuf in_kind, in_index, out_prog, prog_in_chan, in_mean, in_std, out_mean, out_std;
+  ace::DevBuf in_kind, in_index, out_prog, prog_in_chan, in_mean, in_std, out_mean, out_std, out_clamp;
+  int ocean_out = -1, ocean_interp = 0;
   ace::DevBuf x, y;
   int wsB = 0;
 };
@@ -65,6 +66,15 @@ extern "C" int ace_stepper_create(ace_sfno* net, const ace_step_config* cfg, ace
     upload(st->in_std, cfg->in_std_host, cfg->n_in);
     upload(st->out_mean, cfg->out_mean_host, cfg->n_out);
     upload(st->out_std, cfg->out_std_host, cfg->n_out);
+    {
+      std::vector<int> clamp(cfg->n_out, 0);
+      if (cfg->out_force_positive_host)
+        for (int c = 0; c < cfg->n_out; ++c) clamp[c] = cfg->out_force_positive_host[c] ? 1 : 0;
+      upload(st->out_clamp, clamp.data(), clamp.size());
+    }
+    ACE_REQUIRE(cfg->ocean_out_index >= -1 && cfg->ocean_out_index < cfg->n_out, "ocean_out_index out of range");
+    st->ocean_out = cfg->ocean_out_index;
+    st->ocean_interp = cfg->ocean_interpolate ? 1 : 0;
   } catch (...) {
     delete st;
     throw;
@@ -75,11 +85,12 @@ extern "C" int ace_stepper_create(ace_sfno* net, const ace_step_config* cfg, ace
 
 extern "C" void ace_stepper_destroy(ace_stepper* st) { delete st; }
 
-extern "C" int ace_stepper_step(ace_stepper* st, const float* prog_dev, const float* forcing_dev, float* out_dev,
-                                float* next_prog_dev, int batch, void* stream) {
+extern "C" int ace_stepper_step(ace_stepper* st, const float* prog_dev, const float* forcing_dev, const float* ocean_dev,
+                                float* out_dev, float* next_prog_dev, int batch, void* stream) {
   ACE_API_BEGIN
   ACE_REQUIRE(st && prog_dev && out_dev && batch > 0, "ace_stepper_step: bad argument");
   ACE_REQUIRE(forcing_dev || st->n_forcing == 0, "ace_stepper_step: forcing is null");
+  ACE_REQUIRE(ocean_dev || st->ocean_out < 0, "ace_stepper_step: an ocean model is configured but ocean_dev is null");
   cudaStream_t s = (cudaStream_t)stream;
   if (batch > st->wsB) {
     st->x.ensure((size_t)batch * st->n_in * st->HW * sizeof(float));
@@ -92,6 +103,6 @@ extern "C" int ace_stepper_step(ace_stepper* st, const float* prog_dev, const fl
   if (rc != ACE_OK) return rc;
   launch_unpack_denormalize(st->y.as<float>(), st->x.as<float>(), st->out_prog.as<int>(), st->prog_in_chan.as<int>(),
                             st->out_mean.as<float>(), st->out_std.as<float>(), st->residual, batch, st->n_out, st->n_in,
-                            st->n_prog, st->HW, out_dev, next_prog_dev, s);
+                            st->n_prog, st->HW, st->out_clamp.as<int>(), st->ocean_out, st->ocean_interp, ocean_dev, out_dev, next_prog_dev, s);
   ACE_API_END
 }

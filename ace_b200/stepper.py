@@ -33,7 +33,13 @@ class FusedStepper:
         means: Mapping[str, float],
         stds: Mapping[str, float],
         residual_prediction: bool = False,
+        force_positive_names: Sequence[str] = (),
+        ocean: Optional[Mapping[str, object]] = None,
     ):
+        """``force_positive_names``: outputs clamped to >= 0 after denormalisation (the corrector's ForcePositive,
+        ``fme/core/corrector/utils.py:26-43``).  ``ocean``: ``{"surface_temperature_name": ..., "interpolate": False}`` enables
+        the prescribed-SST ocean (``fme/core/ocean.py:165-215``): every step then takes ``ocean`` data ``[B, 2, H, W]`` =
+        (ocean fraction, target surface temperature) valid at the OUTPUT time."""
         self.module = module
         self.in_names: List[str] = list(in_names)
         self.out_names: List[str] = list(out_names)
@@ -46,6 +52,13 @@ class FusedStepper:
         self.forcing_names = [n for n in self.in_names if n not in self.out_names]
         self.diagnostic_names = [n for n in self.out_names if n not in self.in_names]
         self.residual_prediction = bool(residual_prediction)
+        self.force_positive_names = list(force_positive_names)
+        for n in self.force_positive_names:
+            if n not in self.out_names:
+                raise ValueError(f"force_positive name '{n}' is not an output")
+        self.ocean = dict(ocean) if ocean is not None else None
+        if self.ocean is not None and self.ocean["surface_temperature_name"] not in self.out_names:
+            raise ValueError("ocean surface_temperature_name must be an output")
         self._means = {k: float(v) for k, v in means.items()}
         self._stds = {k: float(v) for k, v in stds.items()}
         for n in set(self.in_names) | set(self.out_names):
@@ -73,6 +86,7 @@ class FusedStepper:
             dtype=np.int32,
         )
         out_prog = np.array([self.prognostic_names.index(n) if n in self.prognostic_names else -1 for n in self.out_names], dtype=np.int32)
+        clamp = np.array([1 if n in self.force_positive_names else 0 for n in self.out_names], dtype=np.int32)
         f32 = lambda names, d: np.array([d[n] for n in names], dtype=np.float32)  # noqa: E731
         in_mean, in_std = f32(self.in_names, self._means), f32(self.in_names, self._stds)
         out_mean, out_std = f32(self.out_names, self._means), f32(self.out_names, self._stds)
@@ -83,6 +97,9 @@ class FusedStepper:
             n_forcing=len(self.forcing_names), in_kind_host=ip(kind), in_index_host=ip(index),
             out_prog_index_host=ip(out_prog), in_mean_host=fp(in_mean), in_std_host=fp(in_std),
             out_mean_host=fp(out_mean), out_std_host=fp(out_std), residual_prediction=int(self.residual_prediction),
+            out_force_positive_host=ip(clamp),
+            ocean_out_index=self.out_names.index(self.ocean["surface_temperature_name"]) if self.ocean is not None else -1,
+            ocean_interpolate=int(bool(self.ocean.get("interpolate", False))) if self.ocean is not None else 0,
         )
         handle = ctypes.c_void_p()
         _lib.check(_lib.load().ace_stepper_create(net, ctypes.byref(cfg), ctypes.byref(handle)))
@@ -103,8 +120,8 @@ class FusedStepper:
 
     # ------------------------------------------------------------------ one step, packed tensors
     def step_packed(self, prog: torch.Tensor, forcing: Optional[torch.Tensor], out: Optional[torch.Tensor] = None,
-                    next_prog: Optional[torch.Tensor] = None):
-        """prog [B, n_prog, H, W], forcing [B, n_forcing, H, W] -> (out [B, n_out, H, W], next_prog)."""
+                    next_prog: Optional[torch.Tensor] = None, ocean: Optional[torch.Tensor] = None):
+        """prog [B, n_prog, H, W], forcing [B, n_forcing, H, W] (, ocean [B, 2, H, W]) -> (out [B, n_out, H, W], next_prog)."""
         if not prog.is_cuda:
             raise _lib.AceError("FusedStepper: tensors must be on a CUDA device (there is no CPU path)")
         B = prog.shape[0]
@@ -112,6 +129,12 @@ class FusedStepper:
         prog = prog.float().contiguous()
         if forcing is not None:
             forcing = forcing.float().contiguous()
+        if (self.ocean is not None) != (ocean is not None):
+            raise ValueError("ocean data must be given exactly when an ocean model is configured")
+        if ocean is not None:
+            ocean = ocean.float().contiguous()
+            if tuple(ocean.shape) != (B, 2, H, W):
+                raise ValueError(f"ocean data must be [B, 2, H, W] = (ocean fraction, target surface temperature), got {tuple(ocean.shape)}")
         if out is None:
             out = torch.empty(B, len(self.out_names), H, W, device=prog.device, dtype=torch.float32)
         if next_prog is None:
@@ -123,6 +146,7 @@ class FusedStepper:
             _lib.check(_lib.load().ace_stepper_step(
                 self._handle, ctypes.c_void_p(prog.data_ptr()),
                 ctypes.c_void_p(forcing.data_ptr()) if forcing is not None else None,
+                ctypes.c_void_p(ocean.data_ptr()) if ocean is not None else None,
                 ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(next_prog.data_ptr()), B, stream))
         return out, next_prog
 
@@ -131,12 +155,17 @@ class FusedStepper:
         """``input``: every name in ``in_names`` -> [B, H, W] (denormalised).  Returns every ``out_names`` entry."""
         prog = torch.stack([input[n] for n in self.prognostic_names], dim=1)
         forcing = torch.stack([input[n] for n in self.forcing_names], dim=1) if self.forcing_names else None
-        out, _ = self.step_packed(prog, forcing)
+        ocean = None
+        if self.ocean is not None:
+            # the reference reads both from next_step_input_data (fme/core/step/single_module.py:708-709)
+            nxt = next_step_input_data or {}
+            ocean = torch.stack([nxt[self.ocean["ocean_fraction_name"]], nxt[self.ocean["surface_temperature_name"]]], dim=1)
+        out, _ = self.step_packed(prog, forcing, ocean=ocean)
         return {n: out[:, i] for i, n in enumerate(self.out_names)}
 
     # ------------------------------------------------------------------ rollout
     def rollout(self, prog0: torch.Tensor, forcing_seq: Optional[torch.Tensor], n_steps: int, use_cuda_graph: bool = True,
-                keep_outputs: bool = True):
+                keep_outputs: bool = True, ocean_seq: Optional[torch.Tensor] = None):
         """Autoregressive loop (predict_generator).  forcing_seq [n_steps, B, n_forcing, H, W] resident on device.
 
         Returns (outputs [n_steps, B, n_out, H, W] or None, final prognostic state).
@@ -152,7 +181,7 @@ class FusedStepper:
             nxt = torch.empty_like(state)
             for t in range(n_steps):
                 f = forcing_seq[t] if forcing_seq is not None else None
-                self.step_packed(state, f, out_buf if outs is None else outs[t], nxt)
+                self.step_packed(state, f, out_buf if outs is None else outs[t], nxt, ocean=ocean_seq[t] if ocean_seq is not None else None)
                 state, nxt = nxt, state
             return outs, state
         st = self._static
@@ -161,21 +190,24 @@ class FusedStepper:
                 B=B, prog=torch.empty_like(state),
                 forcing=torch.empty(B, len(self.forcing_names), H, W, device=dev) if self.forcing_names else None,
                 out=torch.empty(B, n_out, H, W, device=dev), nxt=torch.empty(B, n_prog, H, W, device=dev),
+                ocean=torch.zeros(B, 2, H, W, device=dev) if self.ocean is not None else None,
             )
             st["prog"].copy_(state)
             if st["forcing"] is not None:
                 st["forcing"].zero_()
-            self.step_packed(st["prog"], st["forcing"], st["out"], st["nxt"])  # warm-up: allocations, func attributes
+            self.step_packed(st["prog"], st["forcing"], st["out"], st["nxt"], ocean=st["ocean"])  # warm-up: allocations, func attributes
             torch.cuda.synchronize(dev)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self.step_packed(st["prog"], st["forcing"], st["out"], st["nxt"])
+                self.step_packed(st["prog"], st["forcing"], st["out"], st["nxt"], ocean=st["ocean"])
                 st["prog"].copy_(st["nxt"])  # feed back inside the graph
             self._graph, self._static = g, st
         st["prog"].copy_(state)
         for t in range(n_steps):
             if st["forcing"] is not None:
                 st["forcing"].copy_(forcing_seq[t], non_blocking=True)
+            if st["ocean"] is not None:
+                st["ocean"].copy_(ocean_seq[t], non_blocking=True)
             self._graph.replay()
             if outs is not None:
                 outs[t].copy_(st["out"], non_blocking=True)
@@ -186,12 +218,14 @@ class FusedStepper:
         B = prog0.shape[0]
         st = self._static
         if self._graph is None or st is None or st["B"] != B or st["prog"].device != prog0.device:
-            self.rollout(prog0, None if not self.forcing_names else torch.zeros(
-                1, B, len(self.forcing_names), *self.module.img_shape, device=prog0.device), 1, use_cuda_graph=True, keep_outputs=False)
+            H, W = self.module.img_shape
+            self.rollout(prog0, torch.zeros(1, B, len(self.forcing_names), H, W, device=prog0.device) if self.forcing_names else None, 1,
+                         use_cuda_graph=True, keep_outputs=False,
+                         ocean_seq=torch.zeros(1, B, 2, H, W, device=prog0.device) if self.ocean is not None else None)
         return self._static, self._graph
 
     def rollout_host(self, prog0: torch.Tensor, forcing_host: Optional[torch.Tensor], n_steps: int,
-                     out_host: Optional[torch.Tensor] = None):
+                     out_host: Optional[torch.Tensor] = None, ocean_host: Optional[torch.Tensor] = None):
         """Autoregressive loop with HOST-resident forcing and outputs (the inference driver's situation: forcing windows come
         from the data loader, outputs go to the writers; ``fme/core/generics/inference.py:117-166``).
 
@@ -209,6 +243,7 @@ class FusedStepper:
         if h is None or h["B"] != st["B"] or h["dev"] != dev:
             h = dict(B=st["B"], dev=dev, s_in=torch.cuda.Stream(dev), s_out=torch.cuda.Stream(dev),
                      fst=[torch.empty_like(st["forcing"]) for _ in range(2)] if st["forcing"] is not None else None,
+                     cst=[torch.empty_like(st["ocean"]) for _ in range(2)] if st["ocean"] is not None else None,
                      ost=[torch.empty_like(st["out"]) for _ in range(2)])
             self._h = h
         ev_in = [torch.cuda.Event() for _ in range(2)]        # forcing staged on device
@@ -224,6 +259,8 @@ class FusedStepper:
                 if t >= 2:
                     h["s_in"].wait_event(ev_used[b])
                 h["fst"][b].copy_(forcing_host[t % nf], non_blocking=True)
+                if h["cst"] is not None:
+                    h["cst"][b].copy_(ocean_host[t % ocean_host.shape[0]], non_blocking=True)
                 ev_in[b].record(h["s_in"])
 
         if h["fst"] is not None and n_steps > 0:
@@ -236,6 +273,8 @@ class FusedStepper:
                     stage_forcing(t + 1)
                 cur.wait_event(ev_in[b])
                 st["forcing"].copy_(h["fst"][b], non_blocking=True)
+                if h["cst"] is not None:
+                    st["ocean"].copy_(h["cst"][b], non_blocking=True)
                 ev_used[b].record(cur)
             graph.replay()
             if out_host is not None:

@@ -131,13 +131,22 @@ typedef struct ace_step_config {
   const float* out_mean_host;   /* [n_out] */
   const float* out_std_host;    /* [n_out] */
   int residual_prediction;      /* 0/1: add normalised input of the same prognostic to the output */
+  /* post-step adjustments on the DENORMALISED outputs, in the reference's order (single_module.py:670-709):
+   * corrector ForcePositive (fme/core/corrector/utils.py:26-43: clamp(min=0) of the named fields), then the ocean
+   * prescriber (fme/core/ocean.py:165-215 + fme/core/prescriber.py:71-109): overwrite the surface temperature with the
+   * target where round(ocean_fraction) == 1 (fme/core/spatial_masking.py:11-30), or blend linearly when `interpolate`. */
+  const int* out_force_positive_host; /* [n_out] 0/1, or NULL */
+  int ocean_out_index;          /* output channel of the surface temperature, or -1: no ocean model */
+  int ocean_interpolate;        /* 0: replace on rounded mask == 1; 1: mask * target + (1 - mask) * generated */
 } ace_step_config;
 int ace_stepper_create(ace_sfno* net, const ace_step_config* cfg, ace_stepper** out);
 void ace_stepper_destroy(ace_stepper* st);
 /* One 6-hour step.  prog_dev [batch][n_prog][H][W] is read; out_dev [batch][n_out][H][W]
- * receives the denormalised outputs; next_prog_dev [batch][n_prog][H][W] receives the state
- * for the next step (outputs that are prognostic; may alias nothing). */
-int ace_stepper_step(ace_stepper* st, const float* prog_dev, const float* forcing_dev,
+ * receives the denormalised (and adjusted) outputs; next_prog_dev [batch][n_prog][H][W] receives the state
+ * for the next step (outputs that are prognostic; may alias nothing).  ocean_dev: float32 [batch][2][H][W] =
+ * {ocean fraction, target surface temperature} at the OUTPUT time (the reference's next_step_input_data); required
+ * iff ocean_out_index >= 0. */
+int ace_stepper_step(ace_stepper* st, const float* prog_dev, const float* forcing_dev, const float* ocean_dev,
                      float* out_dev, float* next_prog_dev, int batch, void* stream);
 
 /* ---- HEALPix spherical harmonic transform ----------------------

@@ -97,3 +97,48 @@ def test_rollout_host_pipelined_equals_device_rollout():
     outs_c, fin_c = st.rollout(prog0, forcing[[0, 1, 0, 1]].cuda(), 4, use_cuda_graph=True)
     torch.testing.assert_close(out_host[:4], outs_c.cpu(), rtol=0, atol=0)
     torch.testing.assert_close(fin_h2, fin_c, rtol=0, atol=0)
+
+
+def test_force_positive_and_prescribed_ocean_match_reference_semantics():
+    """Post-step adjustments in the reference's order (fme/core/step/single_module.py:670-709): ForcePositive clamp
+    (fme/core/corrector/utils.py:26-43), then the ocean prescriber (fme/core/prescriber.py:94-108, replace where
+    round(mask) == 1, fme/core/spatial_masking.py:25-30)."""
+    import ace_b200
+
+    img, in_names, out_names, means, stds, onet, st0 = _setup(False)
+    for interpolate in (False, True):
+        st = ace_b200.FusedStepper(st0.module, in_names, out_names, means, stds, residual_prediction=False,
+                                   force_positive_names=["d1", "a"],
+                                   ocean=dict(surface_temperature_name="c", ocean_fraction_name="f2", interpolate=interpolate))
+        torch.manual_seed(4)
+        state = {n: torch.randn(2, *img) * stds[n] + means[n] for n in in_names}
+        mask = torch.rand(2, *img)
+        target = torch.randn(2, *img) + 280.0
+        ref = _oracle_step(onet, in_names, out_names, means, stds, False, state)
+        for n in ("d1", "a"):
+            ref[n] = torch.clamp(ref[n], min=0.0)
+        if interpolate:
+            ref["c"] = mask * target + (1 - mask) * ref["c"]
+        else:
+            ref["c"] = torch.where(torch.round(mask).to(int) == 1, target, ref["c"])
+        out = st.step({n: v.cuda() for n, v in state.items()}, next_step_input_data={"f2": mask.cuda(), "c": target.cuda()})
+        for n in out_names:
+            a = ((out[n].cpu() - means[n]) / stds[n])[:, None]
+            b = ((ref[n] - means[n]) / stds[n])[:, None]
+            assert field_rel_err(a, b) < 1e-4, (n, interpolate)
+        assert (out["d1"] >= 0).all() and (out["a"] >= 0).all()
+        # rollout: graph == eager with ocean data; the prescribed field is fed back as next state
+        T = 3
+        prog0 = torch.randn(2, 3, *img).cuda()
+        forcing = torch.randn(T, 2, 2, *img).cuda()
+        ocean = torch.stack([torch.rand(T, 2, *img), torch.randn(T, 2, *img) + 280.0], dim=2).cuda()
+        oe, fe = st.rollout(prog0, forcing, T, use_cuda_graph=False, ocean_seq=ocean)
+        og, fg = st.rollout(prog0, forcing, T, use_cuda_graph=True, ocean_seq=ocean)
+        torch.testing.assert_close(og, oe, rtol=0, atol=0)
+        torch.testing.assert_close(fg, fe, rtol=0, atol=0)
+        out_host = torch.empty(T, 2, len(out_names), *img).pin_memory()
+        fh = st.rollout_host(prog0, forcing.cpu().pin_memory(), T, out_host, ocean_host=ocean.cpu().pin_memory())
+        torch.cuda.synchronize()
+        torch.testing.assert_close(out_host, og.cpu(), rtol=0, atol=0)
+        with pytest.raises(ValueError):
+            st.step_packed(prog0, forcing[0])  # ocean configured but no ocean data
