@@ -25,3 +25,25 @@ for B in (1, 8):
         us = e0.elapsed_time(e1) / 20 * 1e3
         res[name] = {"us": round(us, 1), "GBps": round(nbytes / us / 1e3, 1)}
     print(json.dumps({"B": B, "fields": 50, **res}))
+
+# HEALPix SHT (row f4) at BASELINE configs[4]'s shape: nside 64, lmax = mmax = 127, batch 4 x 50 fields
+import ace_b200
+nside, lmax = 64, 127
+fwd = ace_b200.HealpixSHT(nside, lmax=lmax, mmax=lmax, quad_weights="none")
+inv = ace_b200.HealpixISHT(nside, lmax=lmax, mmax=lmax)
+x = torch.randn(4, 50, 12 * nside**2, device="cuda")
+c = fwd(x)
+res = {}
+for name, fn in [("healpix_sht", lambda: fwd(x)), ("healpix_isht", lambda: inv(c))]:
+    for _ in range(3):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / 20 * 1e3
+    nbytes = x.numel() * 4 + c.numel() * 8
+    res[name] = {"us": round(us, 1), "GBps": round(nbytes / us / 1e3, 1)}
+print(json.dumps({"healpix": "nside 64, 4 x 50 fields, lmax = mmax = 127", **res}))
