@@ -21,6 +21,7 @@ from .registry import (  # noqa: F401
 from .sfno import SphericalFourierNeuralOperatorNet  # noqa: F401
 from .sht import InverseRealSHT, RealSHT, patch_torch_harmonics  # noqa: F401
 from .stepper import FusedStepper  # noqa: F401
+from .corrector import AtmosphereCorrector  # noqa: F401
 from . import parallel  # noqa: F401
 from . import metrics  # noqa: F401
 from .healpix import HealpixISHT, HealpixSHT  # noqa: F401

@@ -50,6 +50,25 @@ class StepConfig(ctypes.Structure):
     ]
 
 
+class CorrectorConfig(ctypes.Structure):
+    _fields_ = [
+        ("n_out", ctypes.c_int), ("n_prog", ctypes.c_int), ("nz", ctypes.c_int),
+        ("hw", ctypes.c_longlong),
+        ("area_weights_host", ctypes.POINTER(ctypes.c_float)),
+        ("ak_host", ctypes.POINTER(ctypes.c_double)),
+        ("bk_host", ctypes.POINTER(ctypes.c_double)),
+        ("out_prog_index_host", ctypes.POINTER(ctypes.c_int)),
+        ("out_ps", ctypes.c_int),
+        ("out_wat_host", ctypes.POINTER(ctypes.c_int)),
+        ("out_precip", ctypes.c_int), ("out_lhf", ctypes.c_int), ("out_adv", ctypes.c_int),
+        ("prog_ps", ctypes.c_int),
+        ("prog_wat_host", ctypes.POINTER(ctypes.c_int)),
+        ("conserve_dry_air", ctypes.c_int),
+        ("moisture_mode", ctypes.c_int),
+        ("timestep_seconds", ctypes.c_double),
+    ]
+
+
 # every symbol include/ace_b200.h declares: (restype, argtypes)
 _VP, _I, _LL, _CP = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_char_p
 SIGNATURES = {
@@ -73,6 +92,13 @@ SIGNATURES = {
     "ace_stepper_destroy": (None, [_VP]),
     "ace_stepper_step": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _VP]),
     "ace_dev_gemm": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP]),
+    "ace_corrector_create": (_I, [ctypes.POINTER(CorrectorConfig), ctypes.POINTER(_VP)]),
+    "ace_corrector_destroy": (None, [_VP]),
+    "ace_corrector_seed": (_I, [_VP, _VP, _I, _VP]),
+    "ace_corrector_reset": (_I, [_VP]),
+    "ace_corrector_is_seeded": (_I, [_VP]),
+    "ace_corrector_apply": (_I, [_VP, _VP, _VP, _VP, _I, _VP]),
+    "ace_stepper_set_corrector": (_I, [_VP, _VP]),
     "ace_hpx_forward": (_I, [_VP, _I, _VP, _VP, _LL, _VP]),
     "ace_hpx_inverse": (_I, [_VP, _I, _VP, _VP, _LL, _VP]),
     "ace_weighted_moments": (_I, [_VP, _VP, _VP, _LL, _LL, _VP, _VP]),

@@ -285,6 +285,25 @@ __global__ void __launch_bounds__(kThreads) unpack_denormalize_kernel(const floa
   }
 }
 
+__global__ void __launch_bounds__(kThreads) ocean_prescribe_kernel(float* __restrict__ out, float* __restrict__ next_prog,
+                                                                  const int* __restrict__ out_prog_index, int n_out, int n_prog,
+                                                                  long long HW, int ocean_out, int ocean_interp,
+                                                                  const float* __restrict__ ocean) {
+  const int b = blockIdx.y;
+  float* d = out + ((long long)b * n_out + ocean_out) * HW;
+  const int p = out_prog_index[ocean_out];
+  float* np = (p >= 0 && next_prog != nullptr) ? next_prog + ((long long)b * n_prog + p) * HW : nullptr;
+  const float* om = ocean + (long long)b * 2 * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
+    float v = d[i];
+    const float m = om[i], tgt = om[HW + i];
+    if (ocean_interp) v = m * tgt + (1.f - m) * v;
+    else if ((int)rintf(m) == 1) v = tgt;
+    d[i] = v;
+    if (np) np[i] = v;
+  }
+}
+
 }  // namespace
 
 void launch_norm_split(const float* src, int B, int C, long long HW, const double* stats, const float* gamma,
@@ -373,6 +392,14 @@ void launch_unpack_denormalize(const float* y, const float* x_norm, const int* o
   dim3 grid(grid_for(HW, kThreads, 64), B * n_out);
   unpack_denormalize_kernel<<<grid, kThreads, 0, stream>>>(y, x_norm, out_prog_index, prog_in_chan, mean, std, residual, n_out, n_in, n_prog, HW, clamp, ocean_out, ocean_interp, ocean, out, next_prog);
   after_launch("unpack_denormalize");
+}
+
+void launch_ocean_prescribe(float* out, float* next_prog, const int* out_prog_index, int B, int n_out, int n_prog, long long HW,
+                            int ocean_out, int ocean_interp, const float* ocean, cudaStream_t stream) {
+  ProfileScope prof("ocean_prescribe", stream);
+  dim3 grid(grid_for(HW, kThreads, 64), B);
+  ocean_prescribe_kernel<<<grid, kThreads, 0, stream>>>(out, next_prog, out_prog_index, n_out, n_prog, HW, ocean_out, ocean_interp, ocean);
+  after_launch("ocean_prescribe");
 }
 
 }  // namespace ace

@@ -54,4 +54,9 @@ void launch_unpack_denormalize(const float* y, const float* x_norm, const int* o
                                int n_prog, long long HW, const int* clamp, int ocean_out, int ocean_interp, const float* ocean,
                                float* out, float* next_prog, cudaStream_t stream);
 
+// ocean prescriber as a separate pass over the surface-temperature channel (used when conservation correctors run between
+// ForcePositive and the ocean); ocean = [B][2][HW] {mask, target}
+void launch_ocean_prescribe(float* out, float* next_prog, const int* out_prog_index, int B, int n_out, int n_prog, long long HW,
+                            int ocean_out, int ocean_interp, const float* ocean, cudaStream_t stream);
+
 }  // namespace ace

@@ -15,11 +15,17 @@ struct ace_stepper {
   long long HW;
   ace::DevBuf in_kind, in_index, out_prog, prog_in_chan, in_mean, in_std, out_mean, out_std, out_clamp;
   int ocean_out = -1, ocean_interp = 0;
+  ace_corrector* corrector = nullptr;
   ace::DevBuf x, y;
   int wsB = 0;
 };
 
 using namespace ace;
+
+// provided by corrector.cu
+extern "C" int ace_corrector_apply(ace_corrector* c, const float* prev_prog_dev, float* out_dev, float* next_prog_dev, int batch, void* stream);
+extern "C" int ace_corrector_seed(ace_corrector* c, const float* prog_dev, int batch, void* stream);
+extern "C" int ace_corrector_is_seeded(ace_corrector* c);
 
 // provided by sfno.cu
 extern "C" int ace_sfno_query(ace_sfno* net, int* in_chans, int* out_chans, long long* hw);
@@ -85,6 +91,13 @@ extern "C" int ace_stepper_create(ace_sfno* net, const ace_step_config* cfg, ace
 
 extern "C" void ace_stepper_destroy(ace_stepper* st) { delete st; }
 
+extern "C" int ace_stepper_set_corrector(ace_stepper* st, ace_corrector* c) {
+  ACE_API_BEGIN
+  ACE_REQUIRE(st, "ace_stepper_set_corrector: null stepper");
+  st->corrector = c;
+  ACE_API_END
+}
+
 extern "C" int ace_stepper_step(ace_stepper* st, const float* prog_dev, const float* forcing_dev, const float* ocean_dev,
                                 float* out_dev, float* next_prog_dev, int batch, void* stream) {
   ACE_API_BEGIN
@@ -101,8 +114,23 @@ extern "C" int ace_stepper_step(ace_stepper* st, const float* prog_dev, const fl
                         st->in_mean.as<float>(), st->in_std.as<float>(), batch, st->n_in, st->HW, st->x.as<float>(), s);
   int rc = ace_sfno_forward(st->net, st->x.as<float>(), st->y.as<float>(), batch, stream);
   if (rc != ACE_OK) return rc;
+  // reference order (single_module.py:670-709): ForcePositive -> conservation correctors -> ocean prescriber.  Without a
+  // corrector the ocean overwrite rides in the denormalisation kernel; with one it is a separate pass over its one channel.
+  const bool split = st->corrector != nullptr && st->ocean_out >= 0;
   launch_unpack_denormalize(st->y.as<float>(), st->x.as<float>(), st->out_prog.as<int>(), st->prog_in_chan.as<int>(),
                             st->out_mean.as<float>(), st->out_std.as<float>(), st->residual, batch, st->n_out, st->n_in,
-                            st->n_prog, st->HW, st->out_clamp.as<int>(), st->ocean_out, st->ocean_interp, ocean_dev, out_dev, next_prog_dev, s);
+                            st->n_prog, st->HW, st->out_clamp.as<int>(), split ? -1 : st->ocean_out, st->ocean_interp, ocean_dev, out_dev,
+                            next_prog_dev, s);
+  if (st->corrector) {
+    if (!ace_corrector_is_seeded(st->corrector)) {
+      rc = ace_corrector_seed(st->corrector, prog_dev, batch, stream);  // first step of a rollout: the input IS the initial condition
+      if (rc != ACE_OK) return rc;
+    }
+    rc = ace_corrector_apply(st->corrector, prog_dev, out_dev, next_prog_dev, batch, stream);
+    if (rc != ACE_OK) return rc;
+  }
+  if (split)
+    launch_ocean_prescribe(out_dev, next_prog_dev, st->out_prog.as<int>(), batch, st->n_out, st->n_prog, st->HW, st->ocean_out,
+                           st->ocean_interp, ocean_dev, s);
   ACE_API_END
 }

@@ -35,11 +35,19 @@ class FusedStepper:
         residual_prediction: bool = False,
         force_positive_names: Sequence[str] = (),
         ocean: Optional[Mapping[str, object]] = None,
+        corrector: Optional[Mapping[str, object]] = None,
     ):
         """``force_positive_names``: outputs clamped to >= 0 after denormalisation (the corrector's ForcePositive,
         ``fme/core/corrector/utils.py:26-43``).  ``ocean``: ``{"surface_temperature_name": ..., "interpolate": False}`` enables
         the prescribed-SST ocean (``fme/core/ocean.py:165-215``): every step then takes ``ocean`` data ``[B, 2, H, W]`` =
-        (ocean fraction, target surface temperature) valid at the OUTPUT time."""
+        (ocean fraction, target surface temperature) valid at the OUTPUT time.
+        ``corrector``: the conservation correctors of ``fme/core/corrector/atmosphere.py`` (``conserve_dry_air``,
+        ``moisture_budget_correction``), run between ForcePositive and the ocean like the reference:
+        ``dict(conserve_dry_air=True, moisture_budget_correction="advection_and_precipitation", ak=..., bk=...,
+        area_weights=[H, W], timestep_seconds=21600.0)``; field names are resolved with the reference's prefixes
+        (``fme/core/atmosphere_data.py:17-41``: ``PRESsfc``, ``specific_total_water_k``, ``PRATEsfc``, ``LHTFLsfc``,
+        ``tendency_of_total_water_path_due_to_advection``).  The dry-air reference is captured from the first state the
+        stepper sees after ``reset_corrector_state()`` (the initial condition of a rollout)."""
         self.module = module
         self.in_names: List[str] = list(in_names)
         self.out_names: List[str] = list(out_names)
@@ -64,6 +72,8 @@ class FusedStepper:
         for n in set(self.in_names) | set(self.out_names):
             if n not in self._means or n not in self._stds:
                 raise KeyError(f"normalization statistics missing for '{n}'")
+        self.corrector = dict(corrector) if corrector is not None else None
+        self._corrector_handle = None
         self._handle = None
         self._handle_net = None
         self._graph = None
@@ -105,8 +115,28 @@ class FusedStepper:
         _lib.check(_lib.load().ace_stepper_create(net, ctypes.byref(cfg), ctypes.byref(handle)))
         self._handle, self._handle_net = handle, net
         self._graph = None
+        if self.corrector is not None:
+            self._build_corrector()
+            _lib.check(_lib.load().ace_stepper_set_corrector(self._handle, self._corrector_handle))
+
+    def _build_corrector(self):
+        from .corrector import AtmosphereCorrector
+
+        self._corrector_obj = AtmosphereCorrector(self.out_names, self.prognostic_names, self.module.img_shape, **self.corrector)
+        self._corrector_handle = self._corrector_obj._handle
+
+    def reset_corrector_state(self):
+        """Forget the dry-air reference: the next step's input state is treated as the initial condition of a new rollout."""
+        if self._corrector_handle is not None:
+            _lib.check(_lib.load().ace_corrector_reset(self._corrector_handle))
+
+    def _seed_corrector(self, prog: torch.Tensor):
+        if self._corrector_handle is not None and not _lib.load().ace_corrector_is_seeded(self._corrector_handle):
+            _lib.check(_lib.load().ace_corrector_seed(self._corrector_handle, ctypes.c_void_p(prog.data_ptr()), prog.shape[0],
+                                                      _lib.current_stream_ptr()))
 
     def _destroy(self):
+        self._corrector_handle = None  # the stepper goes first (it borrows the corrector), AtmosphereCorrector frees itself
         if getattr(self, "_handle", None) is not None:
             try:
                 _lib.load().ace_stepper_destroy(self._handle)
@@ -176,6 +206,11 @@ class FusedStepper:
         n_out, n_prog = len(self.out_names), len(self.prognostic_names)
         outs = torch.empty(n_steps, B, n_out, H, W, device=dev) if keep_outputs else None
         state = prog0.float().contiguous().clone()
+        if self.corrector is not None:  # a rollout starts from an initial condition: (re)capture the dry-air reference from it
+            with torch.cuda.device(dev):
+                self._ensure(dev)
+                self.reset_corrector_state()
+                self._seed_corrector(state)
         if not use_cuda_graph:
             out_buf = torch.empty(B, n_out, H, W, device=dev)
             nxt = torch.empty_like(state)
@@ -236,6 +271,10 @@ class FusedStepper:
         """
         dev = prog0.device
         st, graph = self._ensure_graph(prog0)
+        if self.corrector is not None:
+            with torch.cuda.device(dev):
+                self.reset_corrector_state()
+                self._seed_corrector(prog0.float().contiguous())
         cur = torch.cuda.current_stream(dev)
         if not hasattr(self, "_h"):
             self._h = None

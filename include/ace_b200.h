@@ -47,6 +47,7 @@ extern "C" {
 typedef struct ace_sht_plan ace_sht_plan;
 typedef struct ace_sfno ace_sfno;
 typedef struct ace_stepper ace_stepper;
+typedef struct ace_corrector ace_corrector;
 
 int ace_version(void);
 const char* ace_last_error(void);
@@ -148,6 +149,42 @@ void ace_stepper_destroy(ace_stepper* st);
  * iff ocean_out_index >= 0. */
 int ace_stepper_step(ace_stepper* st, const float* prog_dev, const float* forcing_dev, const float* ocean_dev,
                      float* out_dev, float* next_prog_dev, int batch, void* stream);
+
+/* ---- conservation correctors of the post-step state -------------
+ * fme/core/corrector/atmosphere.py:404-463 (conserve_dry_air: pin the area-weighted global mean of ps - g * total water path
+ * to its value at the initial condition by a globally constant dry-air pressure offset, solving for ps) and :518-608
+ * (moisture_budget_correction: scale precipitation / evaporation so the global budget closes, then optionally recompute the
+ * advective tendency as the column residual).  Channel indices refer to the denormalised output tensor [batch][n_out][hw] and
+ * to the prognostic INPUT state [batch][n_prog][hw] of the step; out_prog_index maps an output channel to the prognostic it
+ * feeds (-1: diagnostic), so corrected fields also reach the next state. */
+typedef struct ace_corrector_config {
+  int n_out, n_prog, nz;             /* nz = number of vertical layers; ak / bk have nz + 1 interface values */
+  long long hw;
+  const float* area_weights_host;    /* [hw] */
+  const double* ak_host;             /* [nz + 1] hybrid sigma-pressure coefficients (fme/core/coordinates.py:241-255) */
+  const double* bk_host;
+  const int* out_prog_index_host;    /* [n_out] */
+  int out_ps;                        /* surface pressure (PRESsfc) */
+  const int* out_wat_host;           /* [nz] specific_total_water_k */
+  int out_precip, out_lhf, out_adv;  /* PRATEsfc, LHTFLsfc, tendency_of_total_water_path_due_to_advection (-1 if unused) */
+  int prog_ps;
+  const int* prog_wat_host;          /* [nz] */
+  int conserve_dry_air;              /* 0/1 */
+  int moisture_mode;                 /* 0 none, 1 precipitation, 2 advection_and_precipitation, 3 evaporation, 4 advection_and_evaporation */
+  double timestep_seconds;
+} ace_corrector_config;
+int ace_corrector_create(const ace_corrector_config* cfg, ace_corrector** out);
+void ace_corrector_destroy(ace_corrector* c);
+/* Capture the dry-air reference from the initial condition (the reference does this the first time the corrector runs,
+ * atmosphere.py:404-427); synchronises the stream once.  ace_corrector_reset forgets it (new rollout). */
+int ace_corrector_seed(ace_corrector* c, const float* prog_dev, int batch, void* stream);
+int ace_corrector_reset(ace_corrector* c);
+int ace_corrector_is_seeded(ace_corrector* c);
+/* In place on out_dev (and next_prog_dev for corrected prognostic fields); prev_prog_dev = the step's input state. */
+int ace_corrector_apply(ace_corrector* c, const float* prev_prog_dev, float* out_dev, float* next_prog_dev, int batch, void* stream);
+/* Attach (or detach with NULL) a corrector to the fused step: it then runs after ForcePositive and before the ocean
+ * prescriber, the reference's order (fme/core/step/single_module.py:670-709). */
+int ace_stepper_set_corrector(ace_stepper* st, ace_corrector* c);
 
 /* ---- HEALPix spherical harmonic transform ----------------------
  * fme/core/cuhpx/sht.py:32-98 (SHT) and :101-153 (iSHT) with fme/core/cuhpx/tools.py:34-83 (per-ring rfft / irfft +

@@ -227,6 +227,60 @@ def load_cuhpx():
     return _CACHE["cuhpx"]
 
 
+def load_corrector():
+    """The reference's AtmosphereData class and its dry-air / moisture correction FUNCTIONS, executed from the tree:
+    fme/core/{typing_,stacker,constants,metrics,atmosphere_data}.py as modules, fme/core/corrector/state.py, and the three
+    functions of fme/core/corrector/atmosphere.py extracted by name (the rest of that file needs dacite / the registries)."""
+    if "corrector" in _CACHE:
+        return _CACHE["corrector"]
+    import ast
+
+    metrics_ns = load_metrics()
+    sys.dont_write_bytecode = True
+    names = ("fme", "fme.core", "fme.core.constants", "fme.core.metrics", "fme.core.typing_", "fme.core.stacker", "fme.core.device",
+             "fme.core.atmosphere_data")
+    saved = {k: sys.modules.get(k) for k in names}
+    try:
+        mods = {k: types.ModuleType(k) for k in names}
+        for k in ("fme", "fme.core"):
+            mods[k].__path__ = []
+        mods["fme.core.device"].get_device = lambda: torch.device("cpu")
+        mods["fme.core.metrics"].__dict__.update(vars(metrics_ns))
+        mods["fme.core"].metrics = mods["fme.core.metrics"]
+        sys.modules.update(mods)
+        for name in ("constants", "typing_", "stacker", "atmosphere_data"):
+            with open(os.path.join(REFERENCE_ROOT, "fme", "core", f"{name}.py")) as f:
+                exec(compile(f.read(), f"fme/core/{name}.py", "exec"), mods[f"fme.core.{name}"].__dict__)
+        state_ns = {"__name__": "fme_core_corrector_state"}
+        with open(os.path.join(REFERENCE_ROOT, "fme", "core", "corrector", "state.py")) as f:
+            exec(compile(f.read(), "fme/core/corrector/state.py", "exec"), state_ns)
+        path = os.path.join(REFERENCE_ROOT, "fme", "core", "corrector", "atmosphere.py")
+        with open(path) as f:
+            src = f.read()
+        wanted = {"_seed_global_dry_air_mass", "_adjust_gen_dry_air_to_target", "_force_conserve_moisture"}
+        tree = ast.parse(src)
+        picked = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in wanted]
+        assert {n.name for n in picked} == wanted
+        from collections.abc import Callable
+        from typing import Literal
+
+        ad = mods["fme.core.atmosphere_data"]
+        ns = {"torch": torch, "Callable": Callable, "Literal": Literal, "AtmosphereData": ad.AtmosphereData,
+              "HasAtmosphereVerticalIntegral": ad.HasAtmosphereVerticalIntegral, "CorrectorState": state_ns["CorrectorState"],
+              "TensorMapping": dict, "TensorDict": dict, "AreaWeightedMean": object, "GRAVITY": mods["fme.core.constants"].GRAVITY}
+        exec(compile(ast.Module(body=picked, type_ignores=[]), path, "exec"), ns)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    _CACHE["corrector"] = types.SimpleNamespace(AtmosphereData=ad.AtmosphereData, CorrectorState=state_ns["CorrectorState"],
+                                                seed=ns["_seed_global_dry_air_mass"], adjust=ns["_adjust_gen_dry_air_to_target"],
+                                                conserve_moisture=ns["_force_conserve_moisture"])
+    return _CACHE["corrector"]
+
+
 def build_reference_net(img_shape, in_chans, out_chans, **builder_fields):
     """The net exactly as SphericalFourierNeuralOperatorBuilder.build makes it (fme/ace/registry/sfno.py:44-61)."""
     ns = load()

@@ -1,0 +1,238 @@
+"""GPU: conservation correctors (dry-air pin, moisture budget) vs oracle/corrector.py, alone and inside the fused step."""
+import pytest
+import torch
+
+from tests.util import field_rel_err
+
+pytestmark = pytest.mark.gpu
+
+NZ = 8
+MODES = [None, "precipitation", "advection_and_precipitation", "evaporation", "advection_and_evaporation"]
+PROG = ["PRESsfc"] + [f"specific_total_water_{k}" for k in range(NZ)]
+# deliberately shuffled: output order != prognostic order, water levels not contiguous
+OUT = ["specific_total_water_3", "PRATEsfc", "PRESsfc", "specific_total_water_0", "LHTFLsfc", "specific_total_water_7",
+       "tendency_of_total_water_path_due_to_advection", "specific_total_water_1", "specific_total_water_2", "specific_total_water_4",
+       "specific_total_water_5", "specific_total_water_6"]
+PROG_ORDER = ["specific_total_water_2", "PRESsfc"] + [f"specific_total_water_{k}" for k in (0, 1, 3, 4, 5, 6, 7)]
+
+
+def _coords(H, W):
+    ak = torch.linspace(0.0, 5000.0, NZ + 1).flip(0) * torch.linspace(1.0, 0.0, NZ + 1)
+    bk = torch.linspace(0.0, 1.0, NZ + 1)
+    lat = torch.linspace(-80, 80, H)
+    w = torch.cos(torch.deg2rad(lat))[:, None].expand(H, W).contiguous()
+    return ak, bk, w
+
+
+def _fields(g, B, H, W, ps_mean, diag):
+    d = {"PRESsfc": ps_mean + 500.0 * torch.randn(B, H, W, generator=g)}
+    for k in range(NZ):
+        d[f"specific_total_water_{k}"] = 1e-3 * (k + 1) * torch.rand(B, H, W, generator=g)
+    if diag:
+        d["PRATEsfc"] = 3e-5 * torch.rand(B, H, W, generator=g)
+        d["LHTFLsfc"] = 80.0 + 40.0 * torch.rand(B, H, W, generator=g)
+        d["tendency_of_total_water_path_due_to_advection"] = 1e-5 * torch.randn(B, H, W, generator=g)
+    return d
+
+
+def _wat(d):
+    return torch.stack([d[f"specific_total_water_{k}"] for k in range(NZ)], dim=-1)
+
+
+def _oracle_correct(inp, gen, target, w, ak, bk, dry, mode):
+    """AtmosphereCorrector.__call__ order (fme/core/corrector/atmosphere.py:349-398): dry air, then moisture."""
+    from oracle import corrector as oc
+    from oracle import metrics as om
+
+    vc = oc.VerticalCoordinate(ak, bk)
+
+    def awm(data, keepdim=False, name=None):
+        return om.weighted_mean(data, w.to(data.dtype), keepdim=keepdim)
+
+    gen = dict(gen)
+    if target is None:
+        target = oc.seed_global_dry_air_mass(inp["PRESsfc"], _wat(inp), awm, vc)
+    if dry:
+        gen["PRESsfc"] = oc.adjust_dry_air_to_target(gen["PRESsfc"], _wat(gen), target, awm, vc)
+    if mode is not None:
+        p, l, a = oc.conserve_moisture(inp["PRESsfc"], _wat(inp), gen["PRESsfc"], _wat(gen), gen["PRATEsfc"], gen["LHTFLsfc"], awm, vc,
+                                       21600.0, mode)
+        gen["PRATEsfc"], gen["LHTFLsfc"] = p, l
+        if a is not None:
+            gen["tendency_of_total_water_path_due_to_advection"] = a
+    return gen, target
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("dry", [True, False])
+def test_corrector_apply_matches_oracle(mode, dry):
+    from ace_b200.corrector import AtmosphereCorrector
+
+    B, H, W = 3, 24, 48
+    g = torch.Generator().manual_seed(11)
+    ak, bk, w = _coords(H, W)
+    ic = _fields(g, B, H, W, 1.0e5, False)       # initial condition (dry-air reference)
+    inp = _fields(g, B, H, W, 1.0002e5, False)   # the step's input state (2nd step of a rollout: differs from the IC)
+    gen = _fields(g, B, H, W, 1.0007e5, True)
+    from oracle import corrector as oc
+    from oracle import metrics as om
+
+    vc = oc.VerticalCoordinate(ak, bk)
+    target = oc.seed_global_dry_air_mass(ic["PRESsfc"], _wat(ic), lambda d, keepdim=False: om.weighted_mean(d, w.to(d.dtype), keepdim=keepdim), vc)
+    ref, _ = _oracle_correct(inp, gen, target, w, ak, bk, dry, mode)
+    dbl = lambda d: {k: v.double() for k, v in d.items()}  # noqa: E731
+    ref64, _ = _oracle_correct(dbl(inp), dbl(gen), target, w.double(), ak.double(), bk.double(), dry, mode)  # same algorithm, fp64
+
+    c = AtmosphereCorrector(OUT, PROG_ORDER, (H, W), ak, bk, w, 21600.0, conserve_dry_air=dry, moisture_budget_correction=mode)
+    pack = lambda d, names: torch.stack([d[n] for n in names], dim=1).contiguous().cuda()  # noqa: E731
+    out, prev, nxt = pack(gen, OUT), pack(inp, PROG_ORDER), pack(gen, PROG_ORDER)
+    with pytest.raises(Exception):
+        c.apply(prev, out.clone(), nxt.clone())      # not seeded
+    c.seed(pack(ic, PROG_ORDER))
+    assert c.seeded
+    c.apply(prev, out, nxt)
+    for i, n in enumerate(OUT):
+        got, want = out[:, i].cpu(), ref[n]
+        if torch.equal(want, gen[n]):
+            assert torch.equal(got, want), f"{n}: field the reference leaves alone was modified"
+        else:
+            # The reference evaluates the column integrals and the budget's global means in fp32; the budget ratio
+            # (<E> - <dTWP/dt>) / <P> amplifies that rounding (dTWP/dt is a difference of two ~20 kg/m2 columns) to ~1e-5
+            # relative.  The device accumulates columns and means in fp64, so it must (1) agree with the fp32 reference to
+            # that conditioning noise and (2) sit within fp32 output rounding of the same algorithm evaluated in fp64.
+            e32 = field_rel_err(got[:, None], want[:, None])
+            e64 = field_rel_err(got[:, None].double(), ref64[n][:, None])
+            r64 = field_rel_err(want[:, None].double(), ref64[n][:, None])
+            assert e32 < 3e-5, (n, mode, dry, e32)
+            assert e64 < 2e-6 and e64 <= r64 + 2e-7, (n, mode, dry, e64, r64)
+    for i, n in enumerate(PROG_ORDER):  # corrected prognostic fields are fed back identically
+        assert torch.equal(nxt[:, i], out[:, OUT.index(n)]), n
+    if dry:  # the pin holds on the device result: global dry-air mean == target to fp32 resolution of ps
+        o = {n: out[:, i].cpu() for i, n in enumerate(OUT)}
+        achieved = om.weighted_mean(oc.dry_air(o["PRESsfc"], _wat(o), vc).double(), w.double(), keepdim=True)
+        assert float((achieved - target).abs().max()) < 0.02  # Pa
+    if mode is not None:  # and the budget closes: <dTWP/dt> = <E> - <P> (+ <adv> = 0 when advection is the residual)
+        o = {n: out[:, i].cpu().double() for i, n in enumerate(OUT)}
+        twp1 = oc.VerticalCoordinate(ak.double(), bk.double()).vertical_integral(_wat(o), o["PRESsfc"])
+        twp0 = oc.VerticalCoordinate(ak.double(), bk.double()).vertical_integral(_wat(inp).double(), inp["PRESsfc"].double())
+        mean = lambda d: om.weighted_mean(d, w.double())  # noqa: E731
+        resid = mean((twp1 - twp0) / 21600.0) - mean(o["LHTFLsfc"] / 2.5e6) + mean(o["PRATEsfc"])
+        assert float(resid.abs().max()) < 1e-9, float(resid.abs().max())
+
+
+def test_unsupported_options_raise():
+    from ace_b200.corrector import AtmosphereCorrector
+
+    ak, bk, w = _coords(8, 16)
+    with pytest.raises(NotImplementedError):
+        AtmosphereCorrector(OUT, PROG_ORDER, (8, 16), ak, bk, w, total_energy_budget_correction={"method": "constant_temperature"})
+    with pytest.raises(ValueError):
+        AtmosphereCorrector(OUT, PROG_ORDER, (8, 16), ak[:-1], bk[:-1], w)
+
+
+def _stepper(mode, ocean):
+    import ace_b200
+    from oracle import sfno as osfno
+
+    img = (32, 64)
+    in_names = PROG_ORDER + ["forcing_a", "ocean_fraction"]
+    out_names = OUT + ["surface_temperature_diag"]
+    allnames = sorted(set(in_names + out_names))
+    means = {n: 0.0 for n in allnames}
+    stds = {n: 1.0 for n in allnames}
+    means["PRESsfc"], stds["PRESsfc"] = 1.0e5, 800.0
+    for k in range(NZ):
+        means[f"specific_total_water_{k}"], stds[f"specific_total_water_{k}"] = 1e-3 * (k + 1), 4e-4 * (k + 1)
+    means["PRATEsfc"], stds["PRATEsfc"] = 3e-5, 1.5e-5
+    means["LHTFLsfc"], stds["LHTFLsfc"] = 90.0, 30.0
+    stds["tendency_of_total_water_path_due_to_advection"] = 1e-5
+    means["surface_temperature_diag"], stds["surface_temperature_diag"] = 285.0, 10.0
+    torch.manual_seed(0)
+    onet = osfno.SphericalFourierNeuralOperatorNet(img, len(in_names), len(out_names), embed_dim=16, num_layers=2, operator_type="dhconv").eval()
+    sel = ace_b200.ModuleSelector(type="B200SphericalFourierNeuralOperatorNet", config=dict(embed_dim=16, num_layers=2, operator_type="dhconv"))
+    net = sel.build(len(in_names), len(out_names), ace_b200.DatasetInfo(img_shape=img)).torch_module
+    net.load_state_dict(onet.state_dict())
+    net = net.cuda().eval().requires_grad_(False)
+    ak, bk, w = _coords(*img)
+    fp = [f"specific_total_water_{k}" for k in range(NZ)] + ["PRATEsfc"]
+    st = ace_b200.FusedStepper(
+        net, in_names, out_names, means, stds, residual_prediction=True, force_positive_names=fp,
+        ocean=dict(surface_temperature_name="surface_temperature_diag", ocean_fraction_name="ocean_fraction", interpolate=False) if ocean else None,
+        corrector=dict(conserve_dry_air=True, moisture_budget_correction=mode, ak=ak, bk=bk, area_weights=w, timestep_seconds=21600.0))
+    return img, in_names, out_names, means, stds, onet, st, (ak, bk, w), fp
+
+
+@pytest.mark.parametrize("mode", ["advection_and_precipitation", "evaporation"])
+def test_fused_step_with_corrector_matches_oracle_sequence(mode):
+    """Two chained steps through the reference's sequence (fme/core/step/single_module.py:648-709): network, denormalise,
+    ForcePositive, dry air + moisture corrector (reference captured at the first step's input), ocean prescriber."""
+    from tests.test_gpu_stepper import _oracle_step
+
+    img, in_names, out_names, means, stds, onet, st, (ak, bk, w), fp = _stepper(mode, ocean=True)
+    B = 2
+    g = torch.Generator().manual_seed(5)
+    state = {n: torch.randn(B, *img, generator=g) * stds[n] + means[n] for n in in_names}
+    for k in range(NZ):
+        state[f"specific_total_water_{k}"] = state[f"specific_total_water_{k}"].clamp(min=0)
+    target = None
+    dev_state = {n: v.cuda() for n, v in state.items()}
+    st.reset_corrector_state()
+    for step in range(2):
+        mask = torch.rand(B, *img, generator=g)
+        sst = 280.0 + torch.randn(B, *img, generator=g)
+        ref = _oracle_step(onet, in_names, out_names, means, stds, True, state)
+        for n in fp:
+            ref[n] = torch.clamp(ref[n], min=0.0)
+        ref, target = _oracle_correct(state, ref, target, w, ak, bk, True, mode)
+        ref["surface_temperature_diag"] = torch.where(torch.round(mask).to(int) == 1, sst, ref["surface_temperature_diag"])
+        out = st.step(dev_state, next_step_input_data={"ocean_fraction": mask.cuda(), "surface_temperature_diag": sst.cuda()})
+        for n in out_names:
+            a = ((out[n].cpu() - means[n]) / stds[n])[:, None]
+            b = ((ref[n] - means[n]) / stds[n])[:, None]
+            # the advective tendency is (TWP_out - TWP_in) / dt - (E - P): two ~20 kg/m2 columns that differ by ~1e-3 of
+            # themselves here, so the 1e-4 agreement of the network outputs is a 1e-3 agreement of this residual
+            tol = 1e-3 if n == "tendency_of_total_water_path_due_to_advection" else 1e-4
+            assert field_rel_err(a, b) < tol, (n, step)
+        # both sides advance on their own outputs (errors would compound, not hide)
+        new_forcing = {n: torch.randn(B, *img, generator=g) for n in ("forcing_a", "ocean_fraction")}
+        state = {**{n: ref[n] for n in PROG_ORDER}, **new_forcing}
+        dev_state = {**{n: out[n] for n in PROG_ORDER}, **{n: v.cuda() for n, v in new_forcing.items()}}
+
+
+def test_rollout_with_corrector_graph_equals_eager_and_reseeds():
+    img, in_names, out_names, means, stds, onet, st, _, _ = _stepper("advection_and_precipitation", ocean=False)
+    B, T = 2, 4
+    g = torch.Generator().manual_seed(9)
+    n_prog, n_f = len(st.prognostic_names), len(st.forcing_names)
+    pm = torch.tensor([means[n] for n in st.prognostic_names])[None, :, None, None]
+    ps = torch.tensor([stds[n] for n in st.prognostic_names])[None, :, None, None]
+    prog0 = (torch.randn(B, n_prog, *img, generator=g) * ps + pm).cuda()
+    prog1 = (torch.randn(B, n_prog, *img, generator=g) * ps + pm + 0.3 * ps).cuda()
+    forcing = torch.randn(T, B, n_f, *img, generator=g).cuda()
+    oe, fe = st.rollout(prog0, forcing, T, use_cuda_graph=False)
+    og, fg = st.rollout(prog0, forcing, T, use_cuda_graph=True)
+    torch.testing.assert_close(og, oe, rtol=0, atol=0)
+    torch.testing.assert_close(fg, fe, rtol=0, atol=0)
+    # a second rollout from another initial condition re-captures the dry-air reference (graph replays read it from the device)
+    oe1, _ = st.rollout(prog1, forcing, T, use_cuda_graph=False)
+    og1, _ = st.rollout(prog1, forcing, T, use_cuda_graph=True)
+    torch.testing.assert_close(og1, oe1, rtol=0, atol=0)
+    assert not torch.equal(og1, og)
+    out_host = torch.empty(T, B, len(out_names), *img).pin_memory()
+    st.rollout_host(prog0, forcing.cpu().pin_memory(), T, out_host)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(out_host, og.cpu(), rtol=0, atol=0)
+    # the invariant itself: the global dry-air mean of every step's output equals the initial condition's
+    from oracle import corrector as oc
+    from oracle import metrics as om
+
+    ak, bk, w = _coords(*img)
+    vc = oc.VerticalCoordinate(ak, bk)
+
+    def dry_mean(d):
+        return om.weighted_mean(oc.dry_air(d["PRESsfc"], _wat(d), vc).double(), w.double())
+
+    ic = {n: prog0[:, i].cpu() for i, n in enumerate(st.prognostic_names)}
+    for t in range(T):
+        o = {n: og[t, :, i].cpu() for i, n in enumerate(out_names)}
+        assert float((dry_mean(o) - dry_mean(ic)).abs().max()) < 0.05, t
