@@ -66,6 +66,16 @@ class CorrectorConfig(ctypes.Structure):
         ("conserve_dry_air", ctypes.c_int),
         ("moisture_mode", ctypes.c_int),
         ("timestep_seconds", ctypes.c_double),
+        ("zero_global_mean_moisture_advection", ctypes.c_int),
+        ("out_frozen", ctypes.c_int),
+        ("clip_frozen_precipitation", ctypes.c_int),
+        ("energy_mode", ctypes.c_int),
+        ("unaccounted_heating", ctypes.c_double),
+        ("out_temp_host", ctypes.POINTER(ctypes.c_int)),
+        ("prog_temp_host", ctypes.POINTER(ctypes.c_int)),
+        ("n_forcing", ctypes.c_int), ("forcing_hgt", ctypes.c_int),
+        ("out_dlw_sfc", ctypes.c_int), ("out_ulw_sfc", ctypes.c_int), ("out_dsw_sfc", ctypes.c_int), ("out_usw_sfc", ctypes.c_int),
+        ("out_shf", ctypes.c_int), ("out_usw_toa", ctypes.c_int), ("out_ulw_toa", ctypes.c_int),
     ]
 
 
@@ -90,14 +100,15 @@ SIGNATURES = {
     "ace_sfno_query": (_I, [_VP, ctypes.POINTER(_I), ctypes.POINTER(_I), ctypes.POINTER(_LL)]),
     "ace_stepper_create": (_I, [_VP, ctypes.POINTER(StepConfig), ctypes.POINTER(_VP)]),
     "ace_stepper_destroy": (None, [_VP]),
-    "ace_stepper_step": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _VP]),
+    "ace_stepper_step": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _VP]),
     "ace_dev_gemm": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP]),
     "ace_corrector_create": (_I, [ctypes.POINTER(CorrectorConfig), ctypes.POINTER(_VP)]),
     "ace_corrector_destroy": (None, [_VP]),
     "ace_corrector_seed": (_I, [_VP, _VP, _I, _VP]),
     "ace_corrector_reset": (_I, [_VP]),
     "ace_corrector_is_seeded": (_I, [_VP]),
-    "ace_corrector_apply": (_I, [_VP, _VP, _VP, _VP, _I, _VP]),
+    "ace_corrector_needs_next": (_I, [_VP]),
+    "ace_corrector_apply": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _VP]),
     "ace_stepper_set_corrector": (_I, [_VP, _VP]),
     "ace_hpx_forward": (_I, [_VP, _I, _VP, _VP, _LL, _VP]),
     "ace_hpx_inverse": (_I, [_VP, _I, _VP, _VP, _LL, _VP]),

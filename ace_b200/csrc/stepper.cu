@@ -23,7 +23,9 @@ struct ace_stepper {
 using namespace ace;
 
 // provided by corrector.cu
-extern "C" int ace_corrector_apply(ace_corrector* c, const float* prev_prog_dev, float* out_dev, float* next_prog_dev, int batch, void* stream);
+extern "C" int ace_corrector_apply(ace_corrector* c, const float* prev_prog_dev, const float* prev_forcing_dev, const float* next_dev,
+                                   float* out_dev, float* next_prog_dev, int batch, void* stream);
+extern "C" int ace_corrector_needs_next(ace_corrector* c);
 extern "C" int ace_corrector_seed(ace_corrector* c, const float* prog_dev, int batch, void* stream);
 extern "C" int ace_corrector_is_seeded(ace_corrector* c);
 
@@ -99,11 +101,13 @@ extern "C" int ace_stepper_set_corrector(ace_stepper* st, ace_corrector* c) {
 }
 
 extern "C" int ace_stepper_step(ace_stepper* st, const float* prog_dev, const float* forcing_dev, const float* ocean_dev,
-                                float* out_dev, float* next_prog_dev, int batch, void* stream) {
+                                const float* corrector_next_dev, float* out_dev, float* next_prog_dev, int batch, void* stream) {
   ACE_API_BEGIN
   ACE_REQUIRE(st && prog_dev && out_dev && batch > 0, "ace_stepper_step: bad argument");
   ACE_REQUIRE(forcing_dev || st->n_forcing == 0, "ace_stepper_step: forcing is null");
   ACE_REQUIRE(ocean_dev || st->ocean_out < 0, "ace_stepper_step: an ocean model is configured but ocean_dev is null");
+  ACE_REQUIRE(corrector_next_dev || !ace_corrector_needs_next(st->corrector),
+              "ace_stepper_step: the corrector's energy budget correction needs corrector_next_dev");
   cudaStream_t s = (cudaStream_t)stream;
   if (batch > st->wsB) {
     st->x.ensure((size_t)batch * st->n_in * st->HW * sizeof(float));
@@ -126,7 +130,7 @@ extern "C" int ace_stepper_step(ace_stepper* st, const float* prog_dev, const fl
       rc = ace_corrector_seed(st->corrector, prog_dev, batch, stream);  // first step of a rollout: the input IS the initial condition
       if (rc != ACE_OK) return rc;
     }
-    rc = ace_corrector_apply(st->corrector, prog_dev, out_dev, next_prog_dev, batch, stream);
+    rc = ace_corrector_apply(st->corrector, prog_dev, forcing_dev, corrector_next_dev, out_dev, next_prog_dev, batch, stream);
     if (rc != ACE_OK) return rc;
   }
   if (split)

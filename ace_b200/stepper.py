@@ -122,8 +122,22 @@ class FusedStepper:
     def _build_corrector(self):
         from .corrector import AtmosphereCorrector
 
-        self._corrector_obj = AtmosphereCorrector(self.out_names, self.prognostic_names, self.module.img_shape, **self.corrector)
+        self._corrector_obj = AtmosphereCorrector(self.out_names, self.prognostic_names, self.module.img_shape,
+                                                  forcing_names=self.forcing_names, **self.corrector)
         self._corrector_handle = self._corrector_obj._handle
+
+    @property
+    def corrector_needs_next(self) -> bool:
+        """True when every step also needs (DSWRFtoa, HGTsfc) at the output time (total-energy budget correction)."""
+        c = self.corrector or {}
+        return c.get("total_energy_budget_correction") is not None
+
+    def corrector_next_from_forcing(self, forcing_next: torch.Tensor) -> torch.Tensor:
+        """Select the two next-step fields the energy correction reads from a forcing tensor [..., n_forcing, H, W]."""
+        from .corrector import next_step_names
+
+        a, b = next_step_names(self.forcing_names)
+        return forcing_next[..., [self.forcing_names.index(a), self.forcing_names.index(b)], :, :].contiguous()
 
     def reset_corrector_state(self):
         """Forget the dry-air reference: the next step's input state is treated as the initial condition of a new rollout."""
@@ -150,8 +164,10 @@ class FusedStepper:
 
     # ------------------------------------------------------------------ one step, packed tensors
     def step_packed(self, prog: torch.Tensor, forcing: Optional[torch.Tensor], out: Optional[torch.Tensor] = None,
-                    next_prog: Optional[torch.Tensor] = None, ocean: Optional[torch.Tensor] = None):
-        """prog [B, n_prog, H, W], forcing [B, n_forcing, H, W] (, ocean [B, 2, H, W]) -> (out [B, n_out, H, W], next_prog)."""
+                    next_prog: Optional[torch.Tensor] = None, ocean: Optional[torch.Tensor] = None,
+                    corrector_next: Optional[torch.Tensor] = None):
+        """prog [B, n_prog, H, W], forcing [B, n_forcing, H, W] (, ocean [B, 2, H, W]) (, corrector_next [B, 2, H, W] =
+        (DSWRFtoa, HGTsfc) at the output time) -> (out [B, n_out, H, W], next_prog)."""
         if not prog.is_cuda:
             raise _lib.AceError("FusedStepper: tensors must be on a CUDA device (there is no CPU path)")
         B = prog.shape[0]
@@ -165,6 +181,13 @@ class FusedStepper:
             ocean = ocean.float().contiguous()
             if tuple(ocean.shape) != (B, 2, H, W):
                 raise ValueError(f"ocean data must be [B, 2, H, W] = (ocean fraction, target surface temperature), got {tuple(ocean.shape)}")
+        if self.corrector_needs_next != (corrector_next is not None):
+            raise ValueError("corrector_next = (DSWRFtoa, HGTsfc) at the output time must be given exactly when the energy budget "
+                             "correction is configured")
+        if corrector_next is not None:
+            corrector_next = corrector_next.float().contiguous()
+            if tuple(corrector_next.shape) != (B, 2, H, W):
+                raise ValueError(f"corrector_next must be [B, 2, H, W], got {tuple(corrector_next.shape)}")
         if out is None:
             out = torch.empty(B, len(self.out_names), H, W, device=prog.device, dtype=torch.float32)
         if next_prog is None:
@@ -177,6 +200,7 @@ class FusedStepper:
                 self._handle, ctypes.c_void_p(prog.data_ptr()),
                 ctypes.c_void_p(forcing.data_ptr()) if forcing is not None else None,
                 ctypes.c_void_p(ocean.data_ptr()) if ocean is not None else None,
+                ctypes.c_void_p(corrector_next.data_ptr()) if corrector_next is not None else None,
                 ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(next_prog.data_ptr()), B, stream))
         return out, next_prog
 
@@ -190,13 +214,21 @@ class FusedStepper:
             # the reference reads both from next_step_input_data (fme/core/step/single_module.py:708-709)
             nxt = next_step_input_data or {}
             ocean = torch.stack([nxt[self.ocean["ocean_fraction_name"]], nxt[self.ocean["surface_temperature_name"]]], dim=1)
-        out, _ = self.step_packed(prog, forcing, ocean=ocean)
+        cnext = None
+        if self.corrector_needs_next:
+            from .corrector import next_step_names
+
+            nxt = next_step_input_data or {}
+            cnext = torch.stack([nxt[n] for n in next_step_names(self.forcing_names)], dim=1)
+        out, _ = self.step_packed(prog, forcing, ocean=ocean, corrector_next=cnext)
         return {n: out[:, i] for i, n in enumerate(self.out_names)}
 
     # ------------------------------------------------------------------ rollout
     def rollout(self, prog0: torch.Tensor, forcing_seq: Optional[torch.Tensor], n_steps: int, use_cuda_graph: bool = True,
                 keep_outputs: bool = True, ocean_seq: Optional[torch.Tensor] = None):
-        """Autoregressive loop (predict_generator).  forcing_seq [n_steps, B, n_forcing, H, W] resident on device.
+        """Autoregressive loop (predict_generator).  forcing_seq [n_steps, B, n_forcing, H, W] resident on device
+        ([n_steps + 1, ...] with the energy budget correction, which reads DSWRFtoa / HGTsfc of the output time, like the
+        reference's forcing windows of n + 1 times).
 
         Returns (outputs [n_steps, B, n_out, H, W] or None, final prognostic state).
         """
@@ -211,12 +243,16 @@ class FusedStepper:
                 self._ensure(dev)
                 self.reset_corrector_state()
                 self._seed_corrector(state)
+        needs_next = self.corrector_needs_next
+        if needs_next and (forcing_seq is None or forcing_seq.shape[0] < n_steps + 1):
+            raise ValueError("the energy budget correction needs forcing at n_steps + 1 times")
         if not use_cuda_graph:
             out_buf = torch.empty(B, n_out, H, W, device=dev)
             nxt = torch.empty_like(state)
             for t in range(n_steps):
                 f = forcing_seq[t] if forcing_seq is not None else None
-                self.step_packed(state, f, out_buf if outs is None else outs[t], nxt, ocean=ocean_seq[t] if ocean_seq is not None else None)
+                self.step_packed(state, f, out_buf if outs is None else outs[t], nxt, ocean=ocean_seq[t] if ocean_seq is not None else None,
+                                 corrector_next=self.corrector_next_from_forcing(forcing_seq[t + 1]) if needs_next else None)
                 state, nxt = nxt, state
             return outs, state
         st = self._static
@@ -226,15 +262,16 @@ class FusedStepper:
                 forcing=torch.empty(B, len(self.forcing_names), H, W, device=dev) if self.forcing_names else None,
                 out=torch.empty(B, n_out, H, W, device=dev), nxt=torch.empty(B, n_prog, H, W, device=dev),
                 ocean=torch.zeros(B, 2, H, W, device=dev) if self.ocean is not None else None,
+                cnext=torch.zeros(B, 2, H, W, device=dev) if needs_next else None,
             )
             st["prog"].copy_(state)
             if st["forcing"] is not None:
                 st["forcing"].zero_()
-            self.step_packed(st["prog"], st["forcing"], st["out"], st["nxt"], ocean=st["ocean"])  # warm-up: allocations, func attributes
+            self.step_packed(st["prog"], st["forcing"], st["out"], st["nxt"], ocean=st["ocean"], corrector_next=st["cnext"])  # warm-up: allocations, func attributes
             torch.cuda.synchronize(dev)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self.step_packed(st["prog"], st["forcing"], st["out"], st["nxt"], ocean=st["ocean"])
+                self.step_packed(st["prog"], st["forcing"], st["out"], st["nxt"], ocean=st["ocean"], corrector_next=st["cnext"])
                 st["prog"].copy_(st["nxt"])  # feed back inside the graph
             self._graph, self._static = g, st
         st["prog"].copy_(state)
@@ -243,6 +280,8 @@ class FusedStepper:
                 st["forcing"].copy_(forcing_seq[t], non_blocking=True)
             if st["ocean"] is not None:
                 st["ocean"].copy_(ocean_seq[t], non_blocking=True)
+            if st["cnext"] is not None:
+                st["cnext"].copy_(self.corrector_next_from_forcing(forcing_seq[t + 1]), non_blocking=True)
             self._graph.replay()
             if outs is not None:
                 outs[t].copy_(st["out"], non_blocking=True)
@@ -254,7 +293,8 @@ class FusedStepper:
         st = self._static
         if self._graph is None or st is None or st["B"] != B or st["prog"].device != prog0.device:
             H, W = self.module.img_shape
-            self.rollout(prog0, torch.zeros(1, B, len(self.forcing_names), H, W, device=prog0.device) if self.forcing_names else None, 1,
+            nt = 2 if self.corrector_needs_next else 1
+            self.rollout(prog0, torch.zeros(nt, B, len(self.forcing_names), H, W, device=prog0.device) if self.forcing_names else None, 1,
                          use_cuda_graph=True, keep_outputs=False,
                          ocean_seq=torch.zeros(1, B, 2, H, W, device=prog0.device) if self.ocean is not None else None)
         return self._static, self._graph
@@ -265,6 +305,7 @@ class FusedStepper:
         from the data loader, outputs go to the writers; ``fme/core/generics/inference.py:117-166``).
 
         forcing_host [>= n_steps (cycled), B, n_forcing, H, W] pinned; out_host [n_steps, B, n_out, H, W] pinned (or None).
+        With the energy budget correction the (DSWRFtoa, HGTsfc) pair of the output time is taken from ``forcing_host[(t + 1) % n]``.
         Every step copies its forcing host->device and its outputs device->host; both copies run on side streams and overlap the
         neighbouring steps' compute (double-buffered staging), the step itself is one CUDA-graph replay.
         Returns the final prognostic state (device).  The caller synchronises before reading ``out_host``.
@@ -283,6 +324,7 @@ class FusedStepper:
             h = dict(B=st["B"], dev=dev, s_in=torch.cuda.Stream(dev), s_out=torch.cuda.Stream(dev),
                      fst=[torch.empty_like(st["forcing"]) for _ in range(2)] if st["forcing"] is not None else None,
                      cst=[torch.empty_like(st["ocean"]) for _ in range(2)] if st["ocean"] is not None else None,
+                     nst=[torch.empty_like(st["forcing"]) for _ in range(2)] if st["cnext"] is not None else None,
                      ost=[torch.empty_like(st["out"]) for _ in range(2)])
             self._h = h
         ev_in = [torch.cuda.Event() for _ in range(2)]        # forcing staged on device
@@ -300,6 +342,8 @@ class FusedStepper:
                 h["fst"][b].copy_(forcing_host[t % nf], non_blocking=True)
                 if h["cst"] is not None:
                     h["cst"][b].copy_(ocean_host[t % ocean_host.shape[0]], non_blocking=True)
+                if h["nst"] is not None:
+                    h["nst"][b].copy_(forcing_host[(t + 1) % nf], non_blocking=True)
                 ev_in[b].record(h["s_in"])
 
         if h["fst"] is not None and n_steps > 0:
@@ -314,6 +358,8 @@ class FusedStepper:
                 st["forcing"].copy_(h["fst"][b], non_blocking=True)
                 if h["cst"] is not None:
                     st["ocean"].copy_(h["cst"][b], non_blocking=True)
+                if h["nst"] is not None:
+                    st["cnext"].copy_(self.corrector_next_from_forcing(h["nst"][b]), non_blocking=True)
                 ev_used[b].record(cur)
             graph.replay()
             if out_host is not None:

@@ -146,9 +146,10 @@ void ace_stepper_destroy(ace_stepper* st);
  * receives the denormalised (and adjusted) outputs; next_prog_dev [batch][n_prog][H][W] receives the state
  * for the next step (outputs that are prognostic; may alias nothing).  ocean_dev: float32 [batch][2][H][W] =
  * {ocean fraction, target surface temperature} at the OUTPUT time (the reference's next_step_input_data); required
- * iff ocean_out_index >= 0. */
+ * iff ocean_out_index >= 0.  corrector_next_dev: float32 [batch][2][H][W] = {DSWRFtoa, HGTsfc} at the OUTPUT time; required
+ * iff the attached corrector has its energy budget correction on (ace_corrector_needs_next). */
 int ace_stepper_step(ace_stepper* st, const float* prog_dev, const float* forcing_dev, const float* ocean_dev,
-                     float* out_dev, float* next_prog_dev, int batch, void* stream);
+                     const float* corrector_next_dev, float* out_dev, float* next_prog_dev, int batch, void* stream);
 
 /* ---- conservation correctors of the post-step state -------------
  * fme/core/corrector/atmosphere.py:404-463 (conserve_dry_air: pin the area-weighted global mean of ps - g * total water path
@@ -172,6 +173,16 @@ typedef struct ace_corrector_config {
   int conserve_dry_air;              /* 0/1 */
   int moisture_mode;                 /* 0 none, 1 precipitation, 2 advection_and_precipitation, 3 evaporation, 4 advection_and_evaporation */
   double timestep_seconds;
+  /* the remaining corrections of the reference's sequence (atmosphere.py:349-398); zero / -1 = off */
+  int zero_global_mean_moisture_advection; /* 0/1: subtract the global mean of out_adv (:467-490), before the moisture budget */
+  int out_frozen;                    /* total_frozen_precipitation_rate, or -1 (enters the surface energy flux) */
+  int clip_frozen_precipitation;     /* 0/1: frozen = min(frozen, corrected precipitation) (:493-515); needs moisture_mode != 0 */
+  int energy_mode;                   /* 0 none, 1 constant_temperature (:611-695) */
+  double unaccounted_heating;        /* W/m2 (constant_unaccounted_heating) */
+  const int* out_temp_host;          /* [nz] air_temperature_k in out (energy_mode only) */
+  const int* prog_temp_host;         /* [nz] in the prognostic state */
+  int n_forcing, forcing_hgt;        /* the step's forcing input [batch][n_forcing][hw] and its surface height channel (HGTsfc) */
+  int out_dlw_sfc, out_ulw_sfc, out_dsw_sfc, out_usw_sfc, out_shf, out_usw_toa, out_ulw_toa; /* DLWRFsfc ULWRFsfc DSWRFsfc USWRFsfc SHTFLsfc USWRFtoa ULWRFtoa */
 } ace_corrector_config;
 int ace_corrector_create(const ace_corrector_config* cfg, ace_corrector** out);
 void ace_corrector_destroy(ace_corrector* c);
@@ -180,8 +191,13 @@ void ace_corrector_destroy(ace_corrector* c);
 int ace_corrector_seed(ace_corrector* c, const float* prog_dev, int batch, void* stream);
 int ace_corrector_reset(ace_corrector* c);
 int ace_corrector_is_seeded(ace_corrector* c);
-/* In place on out_dev (and next_prog_dev for corrected prognostic fields); prev_prog_dev = the step's input state. */
-int ace_corrector_apply(ace_corrector* c, const float* prev_prog_dev, float* out_dev, float* next_prog_dev, int batch, void* stream);
+/* 1 when ace_corrector_apply needs prev_forcing_dev and next_dev (energy budget correction). */
+int ace_corrector_needs_next(ace_corrector* c);
+/* In place on out_dev (and next_prog_dev for corrected prognostic fields); prev_prog_dev / prev_forcing_dev = the step's input
+ * state and forcing; next_dev [batch][2][hw] = (TOA downward shortwave DSWRFtoa, surface height HGTsfc) valid at the OUTPUT time
+ * (the reference reads them from next_step_input_data, atmosphere.py:626-633).  The last two may be NULL unless energy_mode. */
+int ace_corrector_apply(ace_corrector* c, const float* prev_prog_dev, const float* prev_forcing_dev, const float* next_dev,
+                        float* out_dev, float* next_prog_dev, int batch, void* stream);
 /* Attach (or detach with NULL) a corrector to the fused step: it then runs after ForcePositive and before the ocean
  * prescriber, the reference's order (fme/core/step/single_module.py:670-709). */
 int ace_stepper_set_corrector(ace_stepper* st, ace_corrector* c);

@@ -64,3 +64,72 @@ def conserve_moisture(ps_in, wat_in, ps, wat, precip, lhf, area_weighted_mean, v
         evap = lhf / LATENT_HEAT_OF_VAPORIZATION  # ... and evaporation_rate is re-derived from it (atmosphere_data.py:270-279)
     adv = tend - (evap - precip) if terms_to_modify.startswith("advection") else None
     return precip, lhf, adv
+
+
+# ---- the remaining corrections of the sequence (atmosphere.py:349-398 builds it in this order: ForcePositive, dry air,
+# zero-mean moisture advection, moisture budget (+ frozen-precipitation clip), total energy budget) -----------------------------
+LATENT_HEAT_OF_FREEZING = 334000.0
+SPECIFIC_HEAT_OF_DRY_AIR_CONST_PRESSURE = 1004.6
+RVGAS = 461.5
+RDGAS = 287.05
+SPECIFIC_HEAT_OF_DRY_AIR_CONST_VOLUME = SPECIFIC_HEAT_OF_DRY_AIR_CONST_PRESSURE - RDGAS
+
+
+def zero_global_mean_moisture_advection(adv, area_weighted_mean):
+    """atmosphere.py:467-490: subtract the global mean from the advective tendency."""
+    return adv - area_weighted_mean(adv)[..., None, None]
+
+
+def clip_frozen_precipitation(frozen, precip):
+    """atmosphere.py:493-515."""
+    return torch.minimum(frozen, precip)
+
+
+def layer_thickness(p_int, temp, wat):
+    """atmosphere_data.py:376-393 (hydrostatic, virtual temperature from total water, TOA pressure clamped to 1 Pa)."""
+    tv = temp * (1 + (RVGAS / RDGAS - 1.0) * wat)
+    dlogp = torch.log(torch.clamp(p_int, min=1.0)).diff(dim=-1)
+    return dlogp * RDGAS * tv / GRAVITY
+
+
+def _rev_cumsum(x):
+    return torch.cumsum(x.flip(dims=(-1,)), dim=-1).flip(dims=(-1,))
+
+
+def total_energy_ace2_path(ps, temp, wat, hgt, vc):
+    """atmosphere_data.py:310-326,341-365,396-418: cv T + Lv q + g z_mid, integrated over the column."""
+    thick = layer_thickness(vc.interface_pressure(ps), temp, wat)
+    hsfc = torch.where(hgt < 0.0, 0, hgt).reshape(*hgt.shape, 1)
+    cum = _rev_cumsum(thick)
+    h_int = torch.concat([cum + hsfc.broadcast_to(cum.shape), hsfc], dim=-1)
+    h_mid = 0.5 * (h_int[..., :-1] + h_int[..., 1:])
+    te = temp * SPECIFIC_HEAT_OF_DRY_AIR_CONST_VOLUME + wat * LATENT_HEAT_OF_VAPORIZATION + h_mid * GRAVITY
+    return vc.vertical_integral(te, ps)
+
+
+def net_energy_flux_into_atmosphere(f):
+    """atmosphere_data.py:228-250 + metrics.py:299-352; ``f``: dict of the nine flux fields (frozen precipitation may be None)."""
+    frozen = f["frozen"] * LATENT_HEAT_OF_FREEZING if f.get("frozen") is not None else 0.0
+    rad = f["dsw_sfc"] - f["usw_sfc"] + f["dlw_sfc"] - f["ulw_sfc"]
+    turb = -f["lhf"] - f["shf"]
+    sfc = rad + turb - frozen
+    toa = f["dsw_toa"] - f["usw_toa"] - f["ulw_toa"]
+    return toa - sfc
+
+
+def energy_correction_factor(ps, temp, wat, vc):
+    """atmosphere.py:668-695."""
+    q_times_dlogp = layer_thickness(vc.interface_pressure(ps), temp, wat) * GRAVITY / temp
+    integrand = SPECIFIC_HEAT_OF_DRY_AIR_CONST_VOLUME - 0.5 * q_times_dlogp + _rev_cumsum(q_times_dlogp)
+    return vc.vertical_integral(integrand, ps)
+
+
+def conserve_total_energy(ps_in, temp_in, wat_in, hgt_in, ps, temp, wat, hgt_next, fluxes, area_weighted_mean, vc, timestep_seconds,
+                          unaccounted_heating=0.0):
+    """atmosphere.py:611-665 (method constant_temperature).  Returns the corrected air temperature [..., nz]."""
+    e_gen = area_weighted_mean(total_energy_ace2_path(ps, temp, wat, hgt_next, vc), keepdim=True)
+    e_in = area_weighted_mean(total_energy_ace2_path(ps_in, temp_in, wat_in, hgt_in, vc), keepdim=True)
+    flux = area_weighted_mean(net_energy_flux_into_atmosphere(fluxes), keepdim=True)
+    desired = e_in + (flux + unaccounted_heating) * timestep_seconds
+    factor = area_weighted_mean(energy_correction_factor(ps, temp, wat, vc), True)
+    return temp + ((desired - e_gen) / factor)[..., None]

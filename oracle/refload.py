@@ -229,8 +229,8 @@ def load_cuhpx():
 
 def load_corrector():
     """The reference's AtmosphereData class and its dry-air / moisture correction FUNCTIONS, executed from the tree:
-    fme/core/{typing_,stacker,constants,metrics,atmosphere_data}.py as modules, fme/core/corrector/state.py, and the three
-    functions of fme/core/corrector/atmosphere.py extracted by name (the rest of that file needs dacite / the registries)."""
+    fme/core/{typing_,stacker,constants,metrics,atmosphere_data}.py as modules, fme/core/corrector/state.py, and the
+    correction functions of fme/core/corrector/atmosphere.py extracted by name (the rest of that file needs dacite / the registries)."""
     if "corrector" in _CACHE:
         return _CACHE["corrector"]
     import ast
@@ -257,7 +257,9 @@ def load_corrector():
         path = os.path.join(REFERENCE_ROOT, "fme", "core", "corrector", "atmosphere.py")
         with open(path) as f:
             src = f.read()
-        wanted = {"_seed_global_dry_air_mass", "_adjust_gen_dry_air_to_target", "_force_conserve_moisture"}
+        wanted = {"_seed_global_dry_air_mass", "_adjust_gen_dry_air_to_target", "_force_conserve_moisture",
+                  "_force_zero_global_mean_moisture_advection", "_clip_frozen_precipitation", "_force_conserve_total_energy",
+                  "_energy_correction_factor"}
         tree = ast.parse(src)
         picked = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in wanted]
         assert {n.name for n in picked} == wanted
@@ -267,7 +269,9 @@ def load_corrector():
         ad = mods["fme.core.atmosphere_data"]
         ns = {"torch": torch, "Callable": Callable, "Literal": Literal, "AtmosphereData": ad.AtmosphereData,
               "HasAtmosphereVerticalIntegral": ad.HasAtmosphereVerticalIntegral, "CorrectorState": state_ns["CorrectorState"],
-              "TensorMapping": dict, "TensorDict": dict, "AreaWeightedMean": object, "GRAVITY": mods["fme.core.constants"].GRAVITY}
+              "TensorMapping": dict, "TensorDict": dict, "AreaWeightedMean": object, "GRAVITY": mods["fme.core.constants"].GRAVITY,
+              "SPECIFIC_HEAT_OF_DRY_AIR_CONST_VOLUME": mods["fme.core.constants"].SPECIFIC_HEAT_OF_DRY_AIR_CONST_VOLUME,
+              "compute_layer_thickness": ad.compute_layer_thickness}
         exec(compile(ast.Module(body=picked, type_ignores=[]), path, "exec"), ns)
     finally:
         for k, v in saved.items():
@@ -277,7 +281,10 @@ def load_corrector():
                 sys.modules[k] = v
     _CACHE["corrector"] = types.SimpleNamespace(AtmosphereData=ad.AtmosphereData, CorrectorState=state_ns["CorrectorState"],
                                                 seed=ns["_seed_global_dry_air_mass"], adjust=ns["_adjust_gen_dry_air_to_target"],
-                                                conserve_moisture=ns["_force_conserve_moisture"])
+                                                conserve_moisture=ns["_force_conserve_moisture"],
+                                                zero_mean_advection=ns["_force_zero_global_mean_moisture_advection"],
+                                                clip_frozen=ns["_clip_frozen_precipitation"],
+                                                conserve_energy=ns["_force_conserve_total_energy"])
     return _CACHE["corrector"]
 
 

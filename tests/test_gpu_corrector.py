@@ -120,12 +120,14 @@ def test_corrector_apply_matches_oracle(mode, dry):
         assert float(resid.abs().max()) < 1e-9, float(resid.abs().max())
 
 
-def test_unsupported_options_raise():
+def test_bad_options_raise():
     from ace_b200.corrector import AtmosphereCorrector
 
     ak, bk, w = _coords(8, 16)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):  # no air temperature / flux fields among these outputs
         AtmosphereCorrector(OUT, PROG_ORDER, (8, 16), ak, bk, w, total_energy_budget_correction={"method": "constant_temperature"})
+    with pytest.raises(NotImplementedError):
+        AtmosphereCorrector(OUT, PROG_ORDER, (8, 16), ak, bk, w, total_energy_budget_correction={"method": "something_else"})
     with pytest.raises(ValueError):
         AtmosphereCorrector(OUT, PROG_ORDER, (8, 16), ak[:-1], bk[:-1], w)
 
@@ -236,3 +238,206 @@ def test_rollout_with_corrector_graph_equals_eager_and_reseeds():
     for t in range(T):
         o = {n: og[t, :, i].cpu() for i, n in enumerate(out_names)}
         assert float((dry_mean(o) - dry_mean(ic)).abs().max()) < 0.05, t
+
+
+# ---- the rest of the reference's sequence: zero-mean advection, frozen-precipitation clip, total energy budget ----------------
+FLUXES = ["DLWRFsfc", "ULWRFsfc", "DSWRFsfc", "USWRFsfc", "SHTFLsfc", "USWRFtoa", "ULWRFtoa"]
+TEMPS = [f"air_temperature_{k}" for k in range(NZ)]
+PROG_E = PROG_ORDER[:3] + TEMPS[::-1] + PROG_ORDER[3:]                  # temperatures interleaved, reversed order
+OUT_E = OUT[:5] + TEMPS[4:] + FLUXES[:3] + OUT[5:] + TEMPS[:4] + FLUXES[3:] + ["total_frozen_precipitation_rate"]
+FORCING_E = ["land_fraction", "DSWRFtoa", "HGTsfc"]
+
+
+def _energy_fields(g, B, H, W):
+    ic = _fields(g, B, H, W, 1.0e5, False)
+    inp = _fields(g, B, H, W, 1.0002e5, False)
+    gen = _fields(g, B, H, W, 1.0007e5, True)
+    for d in (ic, inp, gen):
+        for k in range(NZ):
+            d[f"air_temperature_{k}"] = 210.0 + 10.0 * k + 3.0 * torch.randn(B, H, W, generator=g)
+    for n, m in zip(FLUXES, [340.0, 390.0, 190.0, 30.0, 20.0, 100.0, 240.0]):
+        gen[n] = m + 20.0 * torch.randn(B, H, W, generator=g)
+    gen["total_frozen_precipitation_rate"] = gen["PRATEsfc"] * 2.0 * torch.rand(B, H, W, generator=g)
+    forcing = {"land_fraction": torch.rand(B, H, W, generator=g), "DSWRFtoa": 300.0 + 80.0 * torch.rand(B, H, W, generator=g),
+               "HGTsfc": 800.0 * torch.randn(B, H, W, generator=g)}
+    nxt = {"DSWRFtoa": 340.0 + 100.0 * torch.rand(B, H, W, generator=g), "HGTsfc": forcing["HGTsfc"] + 1.0}  # distinguishable
+    return ic, inp, gen, forcing, nxt
+
+
+def _temp(d):
+    return torch.stack([d[f"air_temperature_{k}"] for k in range(NZ)], dim=-1)
+
+
+def _oracle_full(inp, forcing, nxt, gen, target, w, ak, bk, mode, zero_adv, clip, heating):
+    """The whole sequence of fme/core/corrector/atmosphere.py:349-398 after ForcePositive."""
+    from oracle import corrector as oc
+    from oracle import metrics as om
+
+    vc = oc.VerticalCoordinate(ak, bk)
+
+    def awm(data, keepdim=False, name=None):
+        return om.weighted_mean(data, w.to(data.dtype), keepdim=keepdim)
+
+    gen = dict(gen)
+    adv = "tendency_of_total_water_path_due_to_advection"
+    gen["PRESsfc"] = oc.adjust_dry_air_to_target(gen["PRESsfc"], _wat(gen), target, awm, vc)
+    if zero_adv:
+        gen[adv] = oc.zero_global_mean_moisture_advection(gen[adv], awm)
+    if mode is not None:
+        p, l, a = oc.conserve_moisture(inp["PRESsfc"], _wat(inp), gen["PRESsfc"], _wat(gen), gen["PRATEsfc"], gen["LHTFLsfc"], awm, vc, 21600.0, mode)
+        gen["PRATEsfc"], gen["LHTFLsfc"] = p, l
+        if a is not None:
+            gen[adv] = a
+        if clip:
+            gen["total_frozen_precipitation_rate"] = oc.clip_frozen_precipitation(gen["total_frozen_precipitation_rate"], gen["PRATEsfc"])
+    if heating is not None:
+        fl = dict(dsw_toa=nxt["DSWRFtoa"], usw_toa=gen["USWRFtoa"], ulw_toa=gen["ULWRFtoa"], dlw_sfc=gen["DLWRFsfc"], ulw_sfc=gen["ULWRFsfc"],
+                  dsw_sfc=gen["DSWRFsfc"], usw_sfc=gen["USWRFsfc"], lhf=gen["LHTFLsfc"], shf=gen["SHTFLsfc"], frozen=gen["total_frozen_precipitation_rate"])
+        t = oc.conserve_total_energy(inp["PRESsfc"], _temp(inp), _wat(inp), forcing["HGTsfc"], gen["PRESsfc"], _temp(gen), _wat(gen), nxt["HGTsfc"],
+                                     fl, awm, vc, 21600.0, heating)
+        for k in range(NZ):
+            gen[f"air_temperature_{k}"] = t[..., k]
+    return gen
+
+
+@pytest.mark.parametrize("mode,zero_adv,clip,heating", [
+    ("advection_and_precipitation", False, True, 0.0),   # configs/baselines/era5/ace-train-config-1-step-pretrain.yaml:119-124
+    ("advection_and_precipitation", False, False, 1.14),  # configs/baselines/shield-som/ace-train-config.yaml:140-145
+    ("evaporation", True, True, 0.0),                     # corrected LHF and clipped frozen precipitation feed the energy flux
+    ("precipitation", True, False, None),                 # zero-mean advection survives (the mode does not recompute advection)
+    (None, True, False, 0.5),
+])
+def test_full_corrector_sequence_matches_oracle(mode, zero_adv, clip, heating):
+    from ace_b200.corrector import AtmosphereCorrector
+    from oracle import corrector as oc
+    from oracle import metrics as om
+
+    B, H, W = 2, 24, 48
+    g = torch.Generator().manual_seed(21)
+    ak, bk, w = _coords(H, W)
+    ic, inp, gen, forcing, nxt = _energy_fields(g, B, H, W)
+    vc = oc.VerticalCoordinate(ak, bk)
+    target = oc.seed_global_dry_air_mass(ic["PRESsfc"], _wat(ic), lambda d, keepdim=False: om.weighted_mean(d, w.to(d.dtype), keepdim=keepdim), vc)
+    ref = _oracle_full(inp, forcing, nxt, gen, target, w, ak, bk, mode, zero_adv, clip, heating)
+    dbl = lambda d: {k: v.double() for k, v in d.items()}  # noqa: E731
+    ref64 = _oracle_full(dbl(inp), dbl(forcing), dbl(nxt), dbl(gen), target, w.double(), ak.double(), bk.double(), mode, zero_adv, clip, heating)
+
+    c = AtmosphereCorrector(OUT_E, PROG_E, (H, W), ak, bk, w, 21600.0, conserve_dry_air=True, moisture_budget_correction=mode,
+                            zero_global_mean_moisture_advection=zero_adv, clip_frozen_precipitation=clip,
+                            total_energy_budget_correction=None if heating is None else dict(method="constant_temperature", constant_unaccounted_heating=heating),
+                            forcing_names=FORCING_E)
+    pack = lambda d, names: torch.stack([d[n] for n in names], dim=1).contiguous().cuda()  # noqa: E731
+    out, prev, nprog = pack(gen, OUT_E), pack(inp, PROG_E), pack(gen, PROG_E)
+    c.seed(pack(ic, PROG_E))
+    if heating is not None:
+        with pytest.raises(ValueError):
+            c.apply(prev, out.clone(), nprog.clone())
+    c.apply(prev, out, nprog, prev_forcing=pack(forcing, FORCING_E), next_step=pack(nxt, ["DSWRFtoa", "HGTsfc"]))
+    changed = set()
+    for i, n in enumerate(OUT_E):
+        got, want = out[:, i].cpu(), ref[n]
+        if torch.equal(want, gen[n]):
+            assert torch.equal(got, want), f"{n}: field the reference leaves alone was modified"
+            continue
+        changed.add(n)
+        e32 = field_rel_err(got[:, None], want[:, None])
+        e64 = field_rel_err(got[:, None].double(), ref64[n][:, None])
+        r64 = field_rel_err(want[:, None].double(), ref64[n][:, None])
+        assert e32 < 3e-5, (n, e32)
+        assert e64 < 2e-6 and e64 <= r64 + 2e-7, (n, e64, r64)
+    if heating is not None:
+        assert set(TEMPS) <= changed
+        # the temperature offset itself (a global-mean energy difference of ~1e9 J/m2 columns): compare the offsets, not T
+        d_dev = (out[:, OUT_E.index("air_temperature_3")].cpu().double() - gen["air_temperature_3"].double()).mean(dim=(-1, -2))
+        d_64 = (ref64["air_temperature_3"] - gen["air_temperature_3"].double()).mean(dim=(-1, -2))
+        d_32 = (ref["air_temperature_3"].double() - gen["air_temperature_3"].double()).mean(dim=(-1, -2))
+        assert float((d_dev - d_64).abs().max()) <= float((d_32 - d_64).abs().max()) + 2e-5, (d_dev, d_32, d_64)
+        assert float(d_64.abs().min()) > 1e-3
+    if clip and mode is not None:
+        assert "total_frozen_precipitation_rate" in changed
+    if zero_adv and mode in (None, "precipitation", "evaporation"):
+        assert "tendency_of_total_water_path_due_to_advection" in changed
+    for i, n in enumerate(PROG_E):
+        assert torch.equal(nprog[:, i], out[:, OUT_E.index(n)]), n
+
+
+def test_fused_rollout_with_full_corrector_graph_equals_eager_and_oracle_step():
+    """FusedStepper with the ERA5 baseline's corrector block: one step against the oracle sequence, then graph == eager and
+    rollout_host == rollout over 3 steps (the energy correction reads DSWRFtoa / HGTsfc of the next forcing time)."""
+    import ace_b200
+    from oracle import sfno as osfno
+    from tests.test_gpu_stepper import _oracle_step
+
+    img = (32, 64)
+    in_names = PROG_E + FORCING_E
+    out_names = OUT_E
+    allnames = sorted(set(in_names + out_names))
+    means, stds = {n: 0.0 for n in allnames}, {n: 1.0 for n in allnames}
+    means["PRESsfc"], stds["PRESsfc"] = 1.0e5, 800.0
+    for k in range(NZ):
+        means[f"specific_total_water_{k}"], stds[f"specific_total_water_{k}"] = 1e-3 * (k + 1), 4e-4 * (k + 1)
+        means[f"air_temperature_{k}"], stds[f"air_temperature_{k}"] = 210.0 + 10.0 * k, 4.0
+    for n, m in zip(FLUXES, [340.0, 390.0, 190.0, 30.0, 20.0, 100.0, 240.0]):
+        means[n], stds[n] = m, 20.0
+    means["PRATEsfc"], stds["PRATEsfc"] = 3e-5, 1.5e-5
+    means["total_frozen_precipitation_rate"], stds["total_frozen_precipitation_rate"] = 3e-5, 3e-5
+    means["LHTFLsfc"], stds["LHTFLsfc"] = 90.0, 30.0
+    stds["tendency_of_total_water_path_due_to_advection"] = 1e-5
+    means["DSWRFtoa"], stds["DSWRFtoa"] = 340.0, 100.0
+    means["HGTsfc"], stds["HGTsfc"] = 400.0, 800.0
+    torch.manual_seed(0)
+    onet = osfno.SphericalFourierNeuralOperatorNet(img, len(in_names), len(out_names), embed_dim=16, num_layers=2, operator_type="dhconv").eval()
+    sel = ace_b200.ModuleSelector(type="B200SphericalFourierNeuralOperatorNet", config=dict(embed_dim=16, num_layers=2, operator_type="dhconv"))
+    net = sel.build(len(in_names), len(out_names), ace_b200.DatasetInfo(img_shape=img)).torch_module
+    net.load_state_dict(onet.state_dict())
+    net = net.cuda().eval().requires_grad_(False)
+    ak, bk, w = _coords(*img)
+    fp = [f"specific_total_water_{k}" for k in range(NZ)] + ["PRATEsfc", "total_frozen_precipitation_rate"]
+    st = ace_b200.FusedStepper(
+        net, in_names, out_names, means, stds, residual_prediction=True, force_positive_names=fp,
+        corrector=dict(conserve_dry_air=True, moisture_budget_correction="advection_and_precipitation", clip_frozen_precipitation=True,
+                       total_energy_budget_correction=dict(method="constant_temperature", constant_unaccounted_heating=1.14),
+                       ak=ak, bk=bk, area_weights=w, timestep_seconds=21600.0))
+    assert st.forcing_names == FORCING_E and st.corrector_needs_next
+    B, T = 2, 3
+    g = torch.Generator().manual_seed(13)
+    state = {n: torch.randn(B, *img, generator=g) * stds[n] + means[n] for n in in_names}
+    for k in range(NZ):
+        state[f"specific_total_water_{k}"] = state[f"specific_total_water_{k}"].clamp(min=0)
+    nxt = {"DSWRFtoa": 340.0 + 100.0 * torch.rand(B, *img, generator=g), "HGTsfc": state["HGTsfc"]}
+    # one step vs the oracle sequence
+    from oracle import corrector as oc
+    from oracle import metrics as om
+
+    vc = oc.VerticalCoordinate(ak, bk)
+    ref = _oracle_step(onet, in_names, out_names, means, stds, True, state)
+    for n in fp:
+        ref[n] = torch.clamp(ref[n], min=0.0)
+    target = oc.seed_global_dry_air_mass(state["PRESsfc"], _wat(state), lambda d, keepdim=False: om.weighted_mean(d, w.to(d.dtype), keepdim=keepdim), vc)
+    ref = _oracle_full(state, state, nxt, ref, target, w, ak, bk, "advection_and_precipitation", False, True, 1.14)
+    st.reset_corrector_state()
+    out = st.step({n: v.cuda() for n, v in state.items()}, next_step_input_data={n: v.cuda() for n, v in nxt.items()})
+    for n in out_names:
+        a = ((out[n].cpu() - means[n]) / stds[n])[:, None]
+        b = ((ref[n] - means[n]) / stds[n])[:, None]
+        tol = 1e-3 if n == "tendency_of_total_water_path_due_to_advection" else 1e-4  # see the moisture test above
+        # both sides hold the DENORMALISED field in fp32: with |mean| = 17..70 std here (fluxes, temperatures) one ulp of the field
+        # is up to 4e-6 std, which is not small against a random-init network's 1e-2-std outputs; allow two ulps of the field
+        ulp = 2.0 * 2.0 ** -23 * (abs(means[n]) + float(b.abs().max()) * stds[n]) / stds[n]
+        err = float((a - b).abs().amax())
+        assert err < tol * float(b.abs().amax()) + ulp, (n, err, float(b.abs().amax()), ulp)
+    # rollouts: forcing at T + 1 times
+    prog0 = torch.stack([state[n] for n in st.prognostic_names], dim=1).cuda()
+    fm = torch.tensor([means[n] for n in FORCING_E])[None, None, :, None, None]
+    fs = torch.tensor([stds[n] for n in FORCING_E])[None, None, :, None, None]
+    forcing = (torch.randn(T + 1, B, len(FORCING_E), *img, generator=g) * fs + fm).cuda()
+    with pytest.raises(ValueError):
+        st.rollout(prog0, forcing[:T], T, use_cuda_graph=False)
+    oe, fe = st.rollout(prog0, forcing, T, use_cuda_graph=False)
+    og, fg = st.rollout(prog0, forcing, T, use_cuda_graph=True)
+    torch.testing.assert_close(og, oe, rtol=0, atol=0)
+    torch.testing.assert_close(fg, fe, rtol=0, atol=0)
+    out_host = torch.empty(T, B, len(out_names), *img).pin_memory()
+    st.rollout_host(prog0, forcing.cpu().pin_memory(), T, out_host)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(out_host, og.cpu(), rtol=0, atol=0)

@@ -68,3 +68,56 @@ def test_oracle_corrector_equals_reference(mode):
         assert torch.equal(r["tendency_of_total_water_path_due_to_advection"], adv)
     else:
         assert adv is None and "tendency_of_total_water_path_due_to_advection" not in r
+
+
+def _temp(d):
+    return torch.stack([d[f"air_temperature_{k}"] for k in range(NZ)], dim=-1)
+
+
+def energy_state(seed, B=2, H=12, W=24):
+    ak, bk, w, inp, gen = synthetic_state(seed, B, H, W)
+    g = torch.Generator().manual_seed(seed + 100)
+    for d in (inp, gen):
+        for k in range(NZ):
+            d[f"air_temperature_{k}"] = 210.0 + 10.0 * k + 3.0 * torch.randn(B, H, W, generator=g)
+    inp["HGTsfc"] = 800.0 * torch.randn(B, H, W, generator=g)  # negative heights are clamped to 0 by the reference
+    forcing = {"HGTsfc": inp["HGTsfc"], "DSWRFtoa": 340.0 + 100.0 * torch.rand(B, H, W, generator=g)}
+    for n, m in [("DLWRFsfc", 340.0), ("ULWRFsfc", 390.0), ("DSWRFsfc", 190.0), ("USWRFsfc", 30.0), ("SHTFLsfc", 20.0),
+                 ("USWRFtoa", 100.0), ("ULWRFtoa", 240.0)]:
+        gen[n] = m + 20.0 * torch.randn(B, H, W, generator=g)
+    return ak, bk, w, inp, gen, forcing
+
+
+@pytest.mark.parametrize("frozen", [False, True])
+def test_oracle_energy_and_small_corrections_equal_reference(frozen):
+    ref = refload.load_corrector()
+    ak, bk, w, inp, gen, forcing = energy_state(3)
+    vc = oc.VerticalCoordinate(ak, bk)
+    if frozen:
+        gen["total_frozen_precipitation_rate"] = gen["PRATEsfc"] * 2.0 * torch.rand(gen["PRATEsfc"].shape, generator=torch.Generator().manual_seed(8))
+
+    def awm(data, keepdim=False, name=None):
+        return om.weighted_mean(data, w.to(data.dtype), keepdim=keepdim)
+
+    # zero-mean advection (atmosphere.py:467-490) and frozen-precipitation clip (:493-515)
+    r = ref.zero_mean_advection(dict(gen), awm)
+    name = "tendency_of_total_water_path_due_to_advection"
+    assert set(r) == {name} and torch.equal(r[name], oc.zero_global_mean_moisture_advection(gen[name], awm))
+    r = ref.clip_frozen(dict(gen))
+    if frozen:
+        assert torch.equal(r["total_frozen_precipitation_rate"], oc.clip_frozen_precipitation(gen["total_frozen_precipitation_rate"], gen["PRATEsfc"]))
+        assert not torch.equal(r["total_frozen_precipitation_rate"], gen["total_frozen_precipitation_rate"])
+    else:
+        assert r == {}
+    # total energy budget (atmosphere.py:611-695)
+    for heating in (0.0, 1.14):
+        r = ref.conserve_energy(inp, dict(gen), forcing, awm, vc, 21600.0, "constant_temperature", heating)
+        fl = dict(dsw_toa=forcing["DSWRFtoa"], usw_toa=gen["USWRFtoa"], ulw_toa=gen["ULWRFtoa"], dlw_sfc=gen["DLWRFsfc"], ulw_sfc=gen["ULWRFsfc"],
+                  dsw_sfc=gen["DSWRFsfc"], usw_sfc=gen["USWRFsfc"], lhf=gen["LHTFLsfc"], shf=gen["SHTFLsfc"],
+                  frozen=gen.get("total_frozen_precipitation_rate"))
+        t = oc.conserve_total_energy(inp["PRESsfc"], _temp(inp), _wat(inp), inp["HGTsfc"], gen["PRESsfc"], _temp(gen), _wat(gen),
+                                     forcing["HGTsfc"], fl, awm, vc, 21600.0, heating)
+        assert set(r) == {f"air_temperature_{k}" for k in range(NZ)}
+        for k in range(NZ):
+            assert torch.equal(r[f"air_temperature_{k}"], t[..., k]), k
+        assert float((t - _temp(gen)).abs().max()) > 1e-3  # the correction is not a no-op on this state
