@@ -294,3 +294,88 @@ def build_reference_net(img_shape, in_chans, out_chans, **builder_fields):
     return ns.SphericalFourierNeuralOperatorNet(
         params=Params(**builder_fields), in_chans=in_chans, out_chans=out_chans, img_shape=tuple(img_shape)
     )
+
+
+def load_csfno():
+    """The reference's conditional SFNO package (fme/core/models/conditional_sfno/*), imported from the tree under its own
+    dotted name with stand-ins for the two fme imports it makes: ``fme.core.distributed`` (a non-distributed ``Distributed``
+    whose ``get_sht`` / ``get_isht`` return the reference's own RealSHT / InverseRealSHT from ``load()``) and
+    ``fme.core.benchmark.timer`` (executed from the tree).  Also ``isotropic_noise`` of fme/ace/registry/stochastic_sfno.py,
+    extracted by name (the rest of that file needs the registries).  Returns a namespace with get_lat_lon_sfnonet, SFNONetConfig,
+    ContextConfig, Context, FourierNeuralOperatorBlock, isotropic_noise."""
+    if "csfno" in _CACHE:
+        return _CACHE["csfno"]
+    import ast
+    import importlib
+
+    base = load()
+    sys.dont_write_bytecode = True
+
+    class _Distributed:
+        _inst = None
+
+        @classmethod
+        def get_instance(cls):
+            if cls._inst is None:
+                cls._inst = cls()
+            return cls._inst
+
+        def get_local_slices(self, shape, *a, **k):
+            return tuple(slice(None, n) for n in shape)
+
+        def get_sht(self, nlat, nlon, lmax=None, mmax=None, grid="legendre-gauss"):
+            return base.RealSHT(nlat, nlon, lmax=lmax, mmax=mmax, grid=grid)
+
+        def get_isht(self, nlat, nlon, lmax=None, mmax=None, grid="legendre-gauss"):
+            return base.InverseRealSHT(nlat, nlon, lmax=lmax, mmax=mmax, grid=grid)
+
+        def reduce_min(self, t):
+            return t
+
+        def reduce_max(self, t):
+            return t
+
+    names = ("fme", "fme.core", "fme.core.distributed", "fme.core.distributed.distributed", "fme.core.benchmark",
+             "fme.core.benchmark.timer", "fme.core.models", "fme.core.models.conditional_sfno")
+    saved = {k: sys.modules.get(k) for k in names}
+    try:
+        mods = {k: types.ModuleType(k) for k in names}
+        for k in ("fme", "fme.core", "fme.core.distributed", "fme.core.benchmark", "fme.core.models"):
+            mods[k].__path__ = []
+        mods["fme.core.models.conditional_sfno"].__path__ = [os.path.join(REFERENCE_ROOT, "fme", "core", "models", "conditional_sfno")]
+        mods["fme.core.distributed"].Distributed = _Distributed
+        mods["fme.core.distributed.distributed"].Distributed = _Distributed
+        mods["fme.core"].distributed = mods["fme.core.distributed"]
+        sys.modules.update(mods)
+        with open(os.path.join(REFERENCE_ROOT, "fme", "core", "benchmark", "timer.py")) as f:
+            exec(compile(f.read(), "fme/core/benchmark/timer.py", "exec"), mods["fme.core.benchmark.timer"].__dict__)
+        for k in list(sys.modules):  # a fresh import of the package's submodules
+            if k.startswith("fme.core.models.conditional_sfno."):
+                del sys.modules[k]
+        net = importlib.import_module("fme.core.models.conditional_sfno.sfnonet")
+        layers = importlib.import_module("fme.core.models.conditional_sfno.layers")
+        path = os.path.join(REFERENCE_ROOT, "fme", "ace", "registry", "stochastic_sfno.py")
+        with open(path) as f:
+            tree = ast.parse(f.read())
+        picked = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "isotropic_noise"]
+        assert len(picked) == 1
+        import math
+        from collections.abc import Callable
+
+        ns = {"torch": torch, "math": math, "Callable": Callable, "Distributed": _Distributed,
+              "randn": lambda shape, dtype=None, device=None: torch.randn(shape, dtype=dtype, device=device)}
+        exec(compile(ast.Module(body=picked, type_ignores=[]), path, "exec"), ns)
+    finally:
+        loaded = {k: v for k, v in sys.modules.items() if k.startswith("fme.core.models.conditional_sfno.")}
+        for k in loaded:
+            del sys.modules[k]
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    _CACHE["csfno"] = types.SimpleNamespace(
+        get_lat_lon_sfnonet=net.get_lat_lon_sfnonet, SFNONetConfig=net.SFNONetConfig, ContextConfig=layers.ContextConfig,
+        Context=layers.Context, FourierNeuralOperatorBlock=net.FourierNeuralOperatorBlock, isotropic_noise=ns["isotropic_noise"],
+        RealSHT=base.RealSHT, InverseRealSHT=base.InverseRealSHT)
+    return _CACHE["csfno"]

@@ -6,6 +6,7 @@ import numpy as np
 import torch
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLDEN_DIR = GOLDEN
 
 
 def load_golden(name):
@@ -50,3 +51,30 @@ NET_GOLDENS = [
     "ref_live_net_ace2like_48x96.npz",
     "ref_stored_sfnonet_output_is_unchanged.npz",
 ]
+
+
+CSFNO_GOLDENS = [
+    "ref_stored_csfno_output_is_unchanged.npz",
+    "ref_stored_csfno_checkpoint.npz",
+    "ref_live_csfno_era5like_24x48.npz",
+    "ref_live_csfno_noaffine_pos_17x32.npz",
+    "ref_live_csfno_nonoise_12x24.npz",
+]
+
+
+def load_csfno_case(name):
+    """A conditional-SFNO golden: returns (net kwargs, context dims, state_dict, x, context dict, y)."""
+    import torch
+
+    d = np.load(os.path.join(GOLDEN_DIR, name))
+    state = {k[2:]: torch.from_numpy(d[k]) for k in d.files if k.startswith("p:")}
+    ctx = {k: None for k in ("embedding_scalar", "embedding_pos", "labels", "noise")}
+    ctx.update({k[4:]: torch.from_numpy(d[k]) for k in d.files if k.startswith("ctx:")})
+    meta = {k[5:]: d[k].item() for k in d.files if k.startswith("meta:")}
+    x, y = torch.from_numpy(d["x"]), torch.from_numpy(d["y"])
+    dims = dict(embed_dim_scalar=0 if ctx["embedding_scalar"] is None else ctx["embedding_scalar"].shape[-1],
+                embed_dim_labels=0 if ctx["labels"] is None else ctx["labels"].shape[-1],
+                embed_dim_noise=0 if ctx["noise"] is None else ctx["noise"].shape[-3],
+                embed_dim_pos=0 if ctx["embedding_pos"] is None else ctx["embedding_pos"].shape[-3])
+    kwargs = dict(img_shape=tuple(x.shape[-2:]), in_chans=x.shape[1], out_chans=y.shape[1], **meta)
+    return kwargs, dims, state, x, ctx, y
