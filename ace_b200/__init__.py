@@ -27,3 +27,5 @@ from . import metrics  # noqa: F401
 from .healpix import HealpixISHT, HealpixSHT  # noqa: F401
 
 __version__ = "0.1.0"
+from . import csfno  # noqa: F401
+from .csfno import NoiseConditionedModel, NoiseConditionedSFNO  # noqa: F401

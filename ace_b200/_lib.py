@@ -50,6 +50,13 @@ class StepConfig(ctypes.Structure):
     ]
 
 
+class CsfnoConfig(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in (
+        "img_h", "img_w", "in_chans", "out_chans", "embed_dim", "num_layers", "lmax", "mmax", "mlp_hidden", "pos_embed", "big_skip",
+        "normalize_big_skip", "affine_norms", "embed_dim_scalar", "embed_dim_labels", "embed_dim_noise", "embed_dim_pos")] + [
+        ("norm_eps", ctypes.c_float)]
+
+
 class CorrectorConfig(ctypes.Structure):
     _fields_ = [
         ("n_out", ctypes.c_int), ("n_prog", ctypes.c_int), ("nz", ctypes.c_int),
@@ -102,6 +109,12 @@ SIGNATURES = {
     "ace_stepper_destroy": (None, [_VP]),
     "ace_stepper_step": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _VP]),
     "ace_dev_gemm": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP]),
+    "ace_csfno_create": (_I, [ctypes.POINTER(CsfnoConfig), _VP, _VP, ctypes.POINTER(_VP)]),
+    "ace_csfno_destroy": (None, [_VP]),
+    "ace_csfno_set_param": (_I, [_VP, _CP, _VP, _LL, _VP]),
+    "ace_csfno_finalize": (_I, [_VP, _VP]),
+    "ace_csfno_forward": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _VP]),
+    "ace_isotropic_noise": (_I, [_VP, _VP, _VP, _VP, _VP, _LL, _VP]),
     "ace_corrector_create": (_I, [ctypes.POINTER(CorrectorConfig), ctypes.POINTER(_VP)]),
     "ace_corrector_destroy": (None, [_VP]),
     "ace_corrector_seed": (_I, [_VP, _VP, _I, _VP]),

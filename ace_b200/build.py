@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libace_b200.so")
-SOURCES = ["capi.cu", "gemm_simt.cu", "gemm_umma.cu", "elementwise.cu", "sht.cu", "sfno.cu", "stepper.cu", "metrics.cu", "healpix.cu", "corrector.cu"]
+SOURCES = ["capi.cu", "gemm_simt.cu", "gemm_umma.cu", "elementwise.cu", "sht.cu", "sfno.cu", "stepper.cu", "metrics.cu", "healpix.cu", "corrector.cu", "cln.cu", "csfno.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "--expt-relaxed-constexpr",

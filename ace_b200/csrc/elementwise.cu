@@ -80,7 +80,8 @@ __global__ void __launch_bounds__(kThreads) split_pad_kernel(const float* __rest
 
 // dhconv weight [Cin][Cout][L][2] (reference layout) -> planes [L][2 (re, im)][Cout][Cinp] for the complex GEMM mode
 __global__ void __launch_bounds__(kThreads) prep_dhconv_cplx_kernel(const float* __restrict__ w, int Cin, int Cout, int L,
-                                                                   int Cinp, bf16* __restrict__ dst, long long plane) {
+                                                                   long long s_l, long long s_o, long long s_i, int Cinp,
+                                                                   bf16* __restrict__ dst, long long plane) {
   const long long total = (long long)L * 2 * Cout * Cinp;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     int i = (int)(idx % Cinp);
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(kThreads) prep_dhconv_cplx_kernel(const float*
     t /= Cout;
     int part = (int)(t & 1);
     int l = (int)(t >> 1);
-    float v = (i < Cin) ? w[(((long long)i * Cout + o) * L + l) * 2 + part] : 0.f;
+    float v = (i < Cin) ? w[(l * s_l + o * s_o + i * s_i) * 2 + part] : 0.f;
     bf16 h, lo;
     split_bf16(v, h, lo);
     dst[idx] = h;
@@ -326,7 +327,16 @@ void launch_split_pad(const float* src, long long rows, int cols, int cols_pad, 
 
 void launch_prep_dhconv_cplx(const float* w, int Cin, int Cout, int L, int Cinp, bf16* dst, long long plane, cudaStream_t stream) {
   ProfileScope prof("prep_dhconv", stream);
-  prep_dhconv_cplx_kernel<<<grid_for((long long)L * 2 * Cout * Cinp, kThreads), kThreads, 0, stream>>>(w, Cin, Cout, L, Cinp, dst, plane);
+  prep_dhconv_cplx_kernel<<<grid_for((long long)L * 2 * Cout * Cinp, kThreads), kThreads, 0, stream>>>(w, Cin, Cout, L, 1, L, (long long)Cout * L,
+                                                                                                       Cinp, dst, plane);
+  after_launch("prep_dhconv_cplx");
+}
+
+void launch_prep_dhconv_cplx_strided(const float* w, int Cin, int Cout, int L, long long s_l, long long s_o, long long s_i, int Cinp, bf16* dst,
+                                     long long plane, cudaStream_t stream) {
+  ProfileScope prof("prep_dhconv", stream);
+  prep_dhconv_cplx_kernel<<<grid_for((long long)L * 2 * Cout * Cinp, kThreads), kThreads, 0, stream>>>(w, Cin, Cout, L, s_l, s_o, s_i, Cinp, dst,
+                                                                                                       plane);
   after_launch("prep_dhconv_cplx");
 }
 

@@ -60,3 +60,29 @@ void launch_ocean_prescribe(float* out, float* next_prog, const int* out_prog_in
                             int ocean_out, int ocean_interp, const float* ocean, cudaStream_t stream);
 
 }  // namespace ace
+
+namespace ace {
+
+// ---- noise-conditioned SFNO (cln.cu) ----
+// ConditionalLayerNorm (conditional_sfno/layers.py:95-141,285-320) on split planes [B][C][HW]:
+//   y = ((x - mean) rsqrt(var + eps) lnw[c] + lnb[c]) * (sb0[b][c].s + sum_e w2[c][e].s ctx[b][e][hw]) + (sb0[b][c].b + sum_e w2[c][e].b ctx[b][e][hw])
+// mean / var over the C channels of the pixel (biased); lnw/lnb, sb0 may be null (1, 0); Ep in {0, 8, 16, 32, 64}.
+void launch_cond_layer_norm(const bf16* x, long long x_plane, long long x_b, int B, int C, long long HW, const float* lnw, const float* lnb,
+                            const float* sb0, const float* w2, const float* ctx, int Ep, float eps, bf16* out, long long o_plane,
+                            long long o_b, cudaStream_t stream);
+// smallest supported padded context width >= E, or -1
+int cln_padded_context(int E);
+// sb0 [B][C][2]: the Linear maps of the per-sample context vectors (scalar embedding, labels) incl. their biases
+void launch_cln_vector_terms(const float* scalar, int Es, const float* labels, int El, const float* Ws, const float* bs, const float* Wb,
+                             const float* bb, const float* Wsl, const float* bsl, const float* Wbl, const float* bbl, int B, int C, float* sb0,
+                             cudaStream_t stream);
+// ctx [B][Ep][HW] = concat(noise [B][En][HW], pos [B][Epos][HW], zero padding)
+void launch_concat_ctx(const float* noise, int En, const float* pos, int Epos, int B, long long HW, int Ep, float* ctx, cudaStream_t stream);
+// w2 [C][Ep][2] from the 1x1-convolution weights W_scale_2d / W_bias_2d [C][En] and W_scale_pos / W_bias_pos [C][Epos]
+void launch_build_cln_w2(const float* ws_n, const float* wb_n, int En, const float* ws_p, const float* wb_p, int Epos, int C, int Ep, float* w2,
+                         cudaStream_t stream);
+// dhconv weight with element (l, o, i, part) at w[(l*s_l + o*s_o + i*s_i)*2 + part] -> planes [L][2 (re, im)][Cout][Cinp]
+void launch_prep_dhconv_cplx_strided(const float* w, int Cin, int Cout, int L, long long s_l, long long s_o, long long s_i, int Cinp, bf16* dst,
+                                     long long plane, cudaStream_t stream);
+
+}  // namespace ace

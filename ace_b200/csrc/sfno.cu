@@ -17,31 +17,11 @@
 #include <string>
 #include <vector>
 
-#include "kernels.cuh"
-#include "sht.cuh"
+#include "netops.cuh"
 
 using namespace ace;
 
 namespace {
-
-struct ConvW {
-  DevBuf w;  // planes [O][Ip]
-  long long plane = 0;
-  int O = 0, I = 0, Ip = 0;
-  DevBuf bias;  // fp32 [O]
-  DevBuf wf;    // fp32 [O][I] copy (only for convolutions that a deferred InstanceNorm is folded into)
-  bool keep_f32 = false;
-  bool has_bias = false;
-  void init(int o, int i, bool b) {
-    O = o;
-    I = i;
-    Ip = (int)round_up(i, 8);
-    plane = (long long)O * Ip;
-    w.ensure(2 * (size_t)plane * sizeof(bf16));
-    has_bias = b;
-    if (b) bias.ensure((size_t)O * sizeof(float));
-  }
-};
 
 struct BlockW {
   DevBuf g0, b0, g1, b1;  // InstanceNorm affine
@@ -91,21 +71,6 @@ void declare_params(ace_sfno& n) {
   p["decoder.0.weight"] = p["decoder.0.bias"] = p["decoder.2.weight"] = false;
 }
 
-void copy_f32(DevBuf& dst, const float* src, long long n, cudaStream_t s) {
-  dst.ensure((size_t)n * sizeof(float));
-  ACE_CHECK_CUDA(cudaMemcpyAsync(dst.p, src, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, s));
-}
-
-void set_conv_w(ConvW& w, const float* src, long long numel, const char* name, cudaStream_t s) {
-  ACE_REQUIRE(numel == (long long)w.O * w.I, "%s: expected %lld elements, got %lld", name, (long long)w.O * w.I, numel);
-  launch_split_pad(src, w.O, w.I, w.Ip, w.w.as<bf16>(), w.plane, s);
-  if (w.keep_f32) copy_f32(w.wf, src, numel, s);
-}
-void set_conv_b(ConvW& w, const float* src, long long numel, const char* name, cudaStream_t s) {
-  ACE_REQUIRE(w.has_bias && numel == w.O, "%s: expected %d elements, got %lld", name, w.O, numel);
-  copy_f32(w.bias, src, numel, s);
-}
-
 void ensure_ws(ace_sfno& n, int B) {
   if (B <= n.wsB) return;
   const ace_sfno_config& c = n.cfg;
@@ -144,60 +109,6 @@ void ensure_ws(ace_sfno& n, int B) {
   n.d1.ensure(2 * (size_t)n.p_act * e);
   n.stats.ensure((size_t)2 * c.num_layers * B * C * 2 * sizeof(double));
   n.wsB = B;
-}
-
-// 1x1 convolution as a GEMM with channels on the accumulator rows: D[o][hw] = sum_i W[o][i] * x[i][hw].
-// A = weights (K-major), B = activations [channel][space] (MN-major: space contiguous), so the output
-// row of a thread is a channel and its columns are contiguous in memory (NC epilogue, gemm_umma.cu).
-GemmOp conv_op(const char* name, const bf16* x, long long x_plane, long long x_batch_stride, long long HW, int B,
-               const ConvW& w, int k_channels) {
-  GemmOp op = make_gemm_op(name);
-  op.M = w.O;
-  op.N = (int)HW;
-  op.K = k_channels;
-  op.Z2 = B;
-  op.A = {w.w.as<bf16>(), w.plane, (long long)w.Ip, 1, 0, 0};
-  op.B = {x, x_plane, 1, HW, 0, x_batch_stride};
-  if (w.has_bias) {
-    op.epi.flags |= EPI_ROW_BIAS;
-    op.epi.row_bias = w.bias.as<float>();
-  }
-  return op;
-}
-// same convolution with per-sample weights / bias (InstanceNorm folded in by prep_norm_conv)
-void use_folded(GemmOp& op, const ConvW& w, const DevBuf& wfold, long long wfold_plane, const DevBuf& bfold) {
-  op.A = {wfold.as<bf16>(), wfold_plane, (long long)w.Ip, 1, 0, (long long)w.O * w.Ip};
-  op.epi.flags |= EPI_ROW_BIAS;
-  op.epi.row_bias = bfold.as<float>();
-  op.epi.rb_z2 = w.O;
-}
-
-void out_planes(GemmOp& op, bf16* out, long long plane, long long batch_stride, long long HW) {
-  op.epi.flags |= EPI_OUT_PLANES;
-  op.epi.out = out;
-  op.epi.out_plane = plane;
-  op.epi.o_z2 = batch_stride;
-  op.epi.o_m0 = HW;
-  op.epi.o_n = 1;
-}
-void out_f32(GemmOp& op, float* out, long long batch_stride, long long HW) {
-  op.epi.flags |= EPI_OUT_F32;
-  op.epi.outf = out;
-  op.epi.f_z2 = batch_stride;
-  op.epi.f_m0 = HW;
-  op.epi.f_n = 1;
-}
-void add_f32(GemmOp& op, const float* add, long long batch_stride, long long HW) {
-  op.epi.flags |= EPI_ADD_F32;
-  op.epi.add = add;
-  op.epi.add_z2 = batch_stride;
-  op.epi.add_m0 = HW;
-  op.epi.add_n = 1;
-}
-void row_stats(GemmOp& op, double* stats, int C) {
-  op.epi.flags |= EPI_ROW_STATS;
-  op.epi.stats = stats;
-  op.epi.stats_z2 = C;
 }
 
 void forward(ace_sfno& n, const float* x, float* y, int B, cudaStream_t s) {

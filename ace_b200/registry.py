@@ -178,4 +178,89 @@ def install_into_fme(override: bool = False):
     FmeModuleSelector.register(B200_TYPE_NAME)(cls)
     if override:
         FmeModuleSelector.register(REFERENCE_TYPE_NAME)(cls)
+    nfields = [(f.name, f.type, f) for f in dataclasses.fields(B200NoiseConditionedSFNOBuilder)]
+    ncls = dataclasses.make_dataclass(
+        "B200NoiseConditionedSFNOBuilder", nfields, bases=(FmeModuleConfig,),
+        namespace={"build": B200NoiseConditionedSFNOBuilder.build, "__post_init__": B200NoiseConditionedSFNOBuilder.__post_init__},
+    )
+    FmeModuleSelector.register(B200_NOISE_TYPE_NAME)(ncls)
+    if override:
+        FmeModuleSelector.register(REFERENCE_NOISE_TYPE_NAME)(ncls)
     return cls
+
+
+B200_NOISE_TYPE_NAME = "B200NoiseConditionedSFNO"
+REFERENCE_NOISE_TYPE_NAME = "NoiseConditionedSFNO"
+
+
+@ModuleSelector.register(B200_NOISE_TYPE_NAME)
+@dataclasses.dataclass
+class B200NoiseConditionedSFNOBuilder(ModuleConfig):
+    """Same fields and defaults as ``NoiseConditionedSFNOBuilder`` (fme/ace/registry/stochastic_sfno.py:181-397)."""
+
+    spectral_transform: str = "sht"
+    filter_type: str = "linear"
+    operator_type: str = "dhconv"
+    residual_filter_factor: int = 1
+    embed_dim: int = 256
+    noise_embed_dim: int = 256
+    context_pos_embed_dim: int = 0
+    label_embed_dim: int = 0
+    noise_type: Literal["isotropic", "gaussian"] = "gaussian"
+    global_layer_norm: bool = False
+    num_layers: int = 12
+    use_mlp: bool = True
+    mlp_ratio: float = 2.0
+    activation_function: str = "gelu"
+    encoder_layers: int = 1
+    pos_embed: bool = True
+    big_skip: bool = True
+    rank: float = 1.0
+    factorization: None = None
+    separable: bool = False
+    complex_network: bool = True
+    complex_activation: str = "real"
+    spectral_layers: int = 1
+    checkpointing: int = 0
+    data_grid: Literal["legendre-gauss", "equiangular"] = "legendre-gauss"
+    filter_residual: bool = False
+    filter_output: bool = False
+    local_blocks: list | None = None
+    normalize_big_skip: bool = False
+    affine_norms: bool = False
+    filter_num_groups: int = 1
+    lora_rank: int = 0
+    lora_alpha: float | None = None
+    spectral_lora_rank: int = 0
+    spectral_lora_alpha: float | None = None
+    filter_preserves_global_mean: bool = False
+    spectral_ratio: float = 1.0
+    clip_latent_global_means: bool = False
+
+    def __post_init__(self):
+        # stochastic_sfno.py:300-318
+        if self.context_pos_embed_dim > 0 and self.pos_embed:
+            raise ValueError("context_pos_embed_dim and pos_embed should not both be set")
+        if self.factorization is not None:
+            raise ValueError("The 'factorization' parameter is no longer supported.")
+        if self.separable:
+            raise ValueError("The 'separable' parameter is no longer supported.")
+        if self.operator_type != "dhconv":
+            raise ValueError("Only 'dhconv' operator_type is supported for NoiseConditionedSFNO models.")
+
+    def build(self, n_in_channels: int, n_out_channels: int, dataset_info):
+        from .csfno import ContextConfig, NoiseConditionedModel, SFNONetConfig, get_lat_lon_sfnonet  # noqa: PLC0415
+
+        n_labels = len(dataset_info.all_labels)
+        effective_label_dim = self.label_embed_dim if self.label_embed_dim > 0 else n_labels
+        names = {f.name for f in dataclasses.fields(SFNONetConfig)}
+        cfg = SFNONetConfig(**{k: v for k, v in dataclasses.asdict(self).items() if k in names})
+        net = get_lat_lon_sfnonet(
+            params=cfg, in_chans=n_in_channels, out_chans=n_out_channels, img_shape=dataset_info.img_shape, data_grid=self.data_grid,
+            context_config=ContextConfig(embed_dim_scalar=0, embed_dim_pos=self.context_pos_embed_dim, embed_dim_noise=self.noise_embed_dim,
+                                         embed_dim_labels=effective_label_dim))
+        isotropic = self.noise_type == "isotropic"
+        return NoiseConditionedModel(
+            net, img_shape=dataset_info.img_shape, embed_dim_noise=self.noise_embed_dim, embed_dim_pos=self.context_pos_embed_dim,
+            n_labels=n_labels, label_embed_dim=self.label_embed_dim, inverse_sht=net.itrans_up if isotropic else None,
+            lmax=net.itrans_up.lmax if isotropic else 0, mmax=net.itrans_up.mmax if isotropic else 0)

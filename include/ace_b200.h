@@ -48,6 +48,7 @@ typedef struct ace_sht_plan ace_sht_plan;
 typedef struct ace_sfno ace_sfno;
 typedef struct ace_stepper ace_stepper;
 typedef struct ace_corrector ace_corrector;
+typedef struct ace_csfno ace_csfno;
 
 int ace_version(void);
 const char* ace_last_error(void);
@@ -116,6 +117,44 @@ int ace_sfno_forward(ace_sfno* net, const float* x_dev, float* y_dev, int batch,
 
 /* Shape query (used by the stepper and the Python wrapper). */
 int ace_sfno_query(ace_sfno* net, int* in_chans, int* out_chans, long long* hw);
+
+/* ---- the noise-conditioned network -------------------------------
+ * fme/core/models/conditional_sfno/sfnonet.py:496-824 (SphericalFourierNeuralOperatorNet with a Context) as built by
+ * get_lat_lon_sfnonet (:443-493) for fme/ace/registry/stochastic_sfno.py:181-397 ("NoiseConditionedSFNO"): filter_type
+ * "linear" (dhconv weights [1][L][O][I][2]), one filter group, scale_factor 1, encoder_layers 1, GELU, MLP, identity outer
+ * skip, ConditionalLayerNorm (layers.py:143-320, channel LayerNorm per pixel, eps 1e-5) conditioned on any of: a scalar
+ * embedding [batch][embed_dim_scalar], labels [batch][embed_dim_labels], a noise field [batch][embed_dim_noise][H][W], a
+ * positional embedding [batch][embed_dim_pos][H][W].  embed_dim_noise + embed_dim_pos <= 64. */
+typedef struct ace_csfno_config {
+  int img_h, img_w;
+  int in_chans, out_chans;
+  int embed_dim, num_layers;
+  int lmax, mmax;
+  int mlp_hidden;            /* int(embed_dim * mlp_ratio) */
+  int pos_embed;             /* 0/1 learned additive position embedding after the encoder */
+  int big_skip;              /* 0/1 */
+  int normalize_big_skip;    /* 0/1: ConditionalLayerNorm on the big-skip copy of the input (sfnonet.py:738-747) */
+  int affine_norms;          /* 0/1: elementwise affine of the channel LayerNorms (norm.weight / norm.bias) */
+  int embed_dim_scalar, embed_dim_labels, embed_dim_noise, embed_dim_pos; /* ContextConfig (layers.py:33-43) */
+  float norm_eps;            /* 1e-5 in the reference */
+} ace_csfno_config;
+/* plan_outer / plan_inner as for ace_sfno_create (trans_down + itrans_up on the data grid, trans + itrans on Legendre-Gauss). */
+int ace_csfno_create(const ace_csfno_config* cfg, ace_sht_plan* plan_outer, ace_sht_plan* plan_inner, ace_csfno** out);
+void ace_csfno_destroy(ace_csfno* net);
+/* name = the reference's state_dict key (e.g. "blocks.0.norm0.W_scale_2d.weight", "norm_big_skip.norm.bias"). */
+int ace_csfno_set_param(ace_csfno* net, const char* name, const float* data_dev, long long numel, void* stream);
+/* Verifies every parameter has been set and builds the derived tables on `stream`. */
+int ace_csfno_finalize(ace_csfno* net, void* stream);
+/* x_dev float32 [batch][in_chans][H][W] + Context (pointers may be NULL when the corresponding width is 0)
+ * -> y_dev float32 [batch][out_chans][H][W].  Enqueue-only, graph-capturable after the first call for a batch size. */
+int ace_csfno_forward(ace_csfno* net, const float* x_dev, const float* scalar_dev, const float* labels_dev, const float* noise_dev,
+                      const float* pos_dev, float* y_dev, int batch, void* stream);
+/* Isotropic Gaussian noise fields of unit pointwise variance (fme/ace/registry/stochastic_sfno.py:21-47) from the caller's two
+ * N(0,1) draws real_dev / imag_dev float32 [nfields][lmax][mmax]: Im(a_l0) = 0, Re / Im of m > 0 divided by sqrt(2), all scaled
+ * by sqrt(4 pi) / lmax, then the inverse SHT of `plan` -> noise_dev float32 [nfields][nlat][nlon].
+ * coeffs_scratch_dev: complex64 [nfields][lmax][mmax]. */
+int ace_isotropic_noise(ace_sht_plan* plan, const float* real_dev, const float* imag_dev, float* coeffs_scratch_dev, float* noise_dev,
+                        long long nfields, void* stream);
 
 /* ---- fused step: normalise -> pack -> net -> (residual) -> denormalise -> feed back ----
  * State layout: prognostic/forcing/diagnostic fields as float32 [batch][n][H][W] tensors.
