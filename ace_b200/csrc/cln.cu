@@ -10,11 +10,14 @@
 // channels (noise, then positional) are concatenated once per forward into ctx [B][E][HW], and ONE streaming kernel per norm
 // does statistics, normalisation, the two E-term dot products per output element and the split-bf16 store.
 //
-// Kernel shape: one thread per pixel (coalesced along the pixel axis for every channel row), 128 pixels per block, grid
-// (ceil(HW / 128), B).  Pass 1 reads the C channel values of the pixel and accumulates sum / sum of squares in fp64; pass 2
-// re-reads them (L2), with the pixel's E context values in registers and the (scale, bias) weight pairs of 16 channels at a
-// time staged in shared memory (read as warp-uniform broadcasts).  Algorithmic traffic per norm: 2 reads + 1 write of the
-// [C][HW] planes (4 B per element each) + E * HW * 4 B of context.
+// Kernel shape (cond_layer_norm_kernel2, HW even): a block of 8 warps owns 64 consecutive pixels; lane l of EVERY warp holds
+// pixels 2l, 2l+1 (bf16x2 loads / stores: 128 B per warp and channel row) and warp w takes the channels c = w (mod 8), so a
+// sample offers HW/64 * 8 warps of parallelism (8 100 at 1 degree).  Pass 1: per-warp partial sums / sums of squares in fp64,
+// combined through shared memory.  Pass 2 re-reads the tile (L2) with the two pixels' E context values in fp32x2 register
+// pairs; the (scale, bias) weights of 32 channels at a time sit in shared memory and every warp-uniform read of one context
+// channel's pair feeds two FFMA2 (both pixels' scale and bias accumulators).  Algorithmic traffic per norm:
+// 2 reads + 1 write of the [C][HW] planes (4 B per element each) + E * HW * 4 B of context; 2 * E FMA per element.
+// cond_layer_norm_kernel (one thread per pixel) is the generic path for odd HW.
 #include "kernels.cuh"
 
 namespace ace {
@@ -81,6 +84,169 @@ __global__ void __launch_bounds__(kPix) cond_layer_norm_kernel(const bf16* __res
       ob[(long long)c * HW] = hi;
       ob[(long long)c * HW + o_plane] = lo;
     }
+  }
+}
+
+struct f2 {
+  unsigned long long u;
+};
+__device__ __forceinline__ f2 mk2(float a, float b) {
+  f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.u) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void un2(f2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v.u)); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+  f2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d.u) : "l"(a.u), "l"(b.u), "l"(c.u));
+  return d;
+}
+
+constexpr int kWarps = 8;     // warps per block = channel interleave
+constexpr int kPix2 = 64;     // pixels per block (2 per lane)
+constexpr int kCh2 = 32;      // channels per shared-memory weight chunk
+
+__device__ __forceinline__ void load_pair(const bf16* p, long long plane, float& v0, float& v1) {
+  const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(p);
+  const __nv_bfloat162 l = *reinterpret_cast<const __nv_bfloat162*>(p + plane);
+  v0 = __low2float(h) + __low2float(l);
+  v1 = __high2float(h) + __high2float(l);
+}
+
+template <int E>
+__global__ void __launch_bounds__(kWarps * 32) cond_layer_norm_kernel2(const bf16* __restrict__ x, long long x_plane, long long x_b, int C,
+                                                                      long long HW, const float* __restrict__ lnw,
+                                                                      const float* __restrict__ lnb, const float* __restrict__ sb0,
+                                                                      const float* __restrict__ w2, const float* __restrict__ ctx, float eps,
+                                                                      bf16* __restrict__ out, long long o_plane, long long o_b) {
+  __shared__ __align__(16) float wsm[2 * kCh2 * (E > 0 ? E : 1) * 2];  // two buffers of [channel][e] -> (ws, wb)
+  __shared__ double red[kWarps][32][4];
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long p = (long long)blockIdx.x * kPix2 + 2 * lane;  // HW is even: a pair is live or dead as a whole
+  const bool live = p < HW;
+  const bf16* xb = x + (long long)b * x_b + p;
+  // ---- pass 1: statistics over the channel axis
+  double s0 = 0, q0 = 0, s1 = 0, q1 = 0;
+  if (live) {
+#pragma unroll 8
+    for (int c = warp; c < C; c += kWarps) {
+      float v0, v1;
+      load_pair(xb + (long long)c * HW, x_plane, v0, v1);
+      s0 += (double)v0;
+      q0 += (double)v0 * (double)v0;
+      s1 += (double)v1;
+      q1 += (double)v1 * (double)v1;
+    }
+  }
+  red[warp][lane][0] = s0;
+  red[warp][lane][1] = q0;
+  red[warp][lane][2] = s1;
+  red[warp][lane][3] = q1;
+  __syncthreads();
+  s0 = q0 = s1 = q1 = 0;
+#pragma unroll
+  for (int w = 0; w < kWarps; ++w) {
+    s0 += red[w][lane][0];
+    q0 += red[w][lane][1];
+    s1 += red[w][lane][2];
+    q1 += red[w][lane][3];
+  }
+  const double m0 = s0 / C, m1 = s1 / C;
+  const float mean0 = (float)m0, mean1 = (float)m1;
+  const float rstd0 = rsqrtf((float)fmax(q0 / C - m0 * m0, 0.0) + eps), rstd1 = rsqrtf((float)fmax(q1 / C - m1 * m1, 0.0) + eps);
+  // ---- the two pixels' context values as (v, v) pairs: ptxas turns them into the scalar-broadcast operand of FFMA2, so the
+  // (ws, wb) weight pair of a context channel -- 8 bytes of a warp-uniform shared-memory read -- feeds both pixels'
+  // (scale, bias) accumulators with two FFMA2.
+  f2 cx[E > 0 ? 2 * E : 1];
+  if (E > 0) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      float2 v = make_float2(0.f, 0.f);
+      if (live) v = __ldg(reinterpret_cast<const float2*>(ctx + ((long long)b * E + e) * HW + p));
+      cx[2 * e] = mk2(v.x, v.x);
+      cx[2 * e + 1] = mk2(v.y, v.y);
+    }
+  }
+  bf16* ob = out + (long long)b * o_b + p;
+  // ---- pass 2: normalise, conditional affine map, split store.  The weights of 32 channels at a time are double-buffered
+  // in shared memory with cp.async so that the next chunk's global loads overlap this chunk's arithmetic.
+  constexpr int kChunkVec = kCh2 * (E > 0 ? E : 1) / 2;  // 16-byte vectors per chunk ((ws, wb) pairs of two context channels)
+  auto stage = [&](int c0, int buf) {
+    if (E > 0) {
+      const int nvec = min(kCh2, C - c0) * E / 2;
+      const float4* src = reinterpret_cast<const float4*>(w2 + (long long)c0 * E * 2);
+      float4* dst = reinterpret_cast<float4*>(wsm) + buf * kChunkVec;
+      for (int i = threadIdx.x; i < nvec; i += kWarps * 32) {
+        const unsigned saddr = (unsigned)__cvta_generic_to_shared(dst + i);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(src + i) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  stage(0, 0);
+  // software pipeline of the tile re-read: the (hi, lo) words of this warp's next two channels are always in flight, so the
+  // L2 latency hides behind two channels' worth of FFMA2 instead of stalling every iteration
+  auto ldraw = [&](int c, unsigned& h, unsigned& l) {
+    if (live && c < C) {
+      h = __ldg(reinterpret_cast<const unsigned*>(xb + (long long)c * HW));
+      l = __ldg(reinterpret_cast<const unsigned*>(xb + (long long)c * HW + x_plane));
+    }
+  };
+  auto unpack = [](unsigned h, unsigned l, float& v0, float& v1) {
+    v0 = __uint_as_float(h << 16) + __uint_as_float(l << 16);  // bf16 -> fp32 is a 16-bit shift
+    v1 = __uint_as_float(h & 0xffff0000u) + __uint_as_float(l & 0xffff0000u);
+  };
+  unsigned hA = 0, lA = 0, hB = 0, lB = 0, hC = 0, lC = 0;
+  ldraw(warp, hA, lA);
+  ldraw(warp + kWarps, hB, lB);
+  int buf = 0;
+  for (int c0 = 0; c0 < C; c0 += kCh2, buf ^= 1) {
+    const int nch = min(kCh2, C - c0);
+    if (c0 + kCh2 < C) {
+      stage(c0 + kCh2, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();  // chunk `buf` has landed for every thread
+    if (live) {
+      for (int cc = warp; cc < nch; cc += kWarps) {
+        const int c = c0 + cc;
+        ldraw(c + 2 * kWarps, hC, lC);
+        const float sc_i = sb0 ? __ldg(sb0 + ((long long)b * C + c) * 2) : 1.f;
+        const float bi_i = sb0 ? __ldg(sb0 + ((long long)b * C + c) * 2 + 1) : 0.f;
+        f2 a0 = mk2(sc_i, bi_i), a1 = a0;  // (scale, bias) of pixel 0 / pixel 1
+        if (E > 0) {
+          const float2* wp = reinterpret_cast<const float2*>(wsm) + (buf * kCh2 + cc) * E;
+#pragma unroll
+          for (int e = 0; e < E; ++e) {
+            const float2 w = wp[e];
+            const f2 wv = mk2(w.x, w.y);
+            a0 = fma2(wv, cx[2 * e], a0);
+            a1 = fma2(wv, cx[2 * e + 1], a1);
+          }
+        }
+        float v0, v1, sc0, sc1, bi0, bi1;
+        unpack(hA, lA, v0, v1);
+        hA = hB, lA = lB, hB = hC, lB = lC;
+        un2(a0, sc0, bi0);
+        un2(a1, sc1, bi1);
+        float y0 = (v0 - mean0) * rstd0, y1 = (v1 - mean1) * rstd1;
+        if (lnw) {
+          const float g = __ldg(lnw + c), h = __ldg(lnb + c);
+          y0 = fmaf(y0, g, h);
+          y1 = fmaf(y1, g, h);
+        }
+        y0 = fmaf(y0, sc0, bi0);
+        y1 = fmaf(y1, sc1, bi1);
+        bf16 h0, l0, h1, l1;
+        split_bf16(y0, h0, l0);
+        split_bf16(y1, h1, l1);
+        *reinterpret_cast<__nv_bfloat162*>(ob + (long long)c * HW) = __halves2bfloat162(h0, h1);
+        *reinterpret_cast<__nv_bfloat162*>(ob + (long long)c * HW + o_plane) = __halves2bfloat162(l0, l1);
+      }
+    }
+    __syncthreads();  // everyone is done with chunk `buf` before it is refilled two iterations later
   }
 }
 
@@ -165,8 +331,17 @@ void launch_cond_layer_norm(const bf16* x, long long x_plane, long long x_b, int
                             const float* sb0, const float* w2, const float* ctx, int Ep, float eps, bf16* out, long long o_plane,
                             long long o_b, cudaStream_t stream) {
   ProfileScope prof("cond_layer_norm", stream);
-  const dim3 grid((unsigned)((HW + kPix - 1) / kPix), (unsigned)B);
-#define ACE_CLN(E) cond_layer_norm_kernel<E><<<grid, kPix, 0, stream>>>(x, x_plane, x_b, C, HW, lnw, lnb, sb0, w2, ctx, eps, out, o_plane, o_b)
+  // the paired kernel needs 4-byte aligned bf16x2 / 8-byte aligned context pairs at every channel row of every sample
+  const bool paired = (HW % 2 == 0) && (x_plane % 2 == 0) && (x_b % 2 == 0) && (o_plane % 2 == 0) && (o_b % 2 == 0) &&
+                      ((uintptr_t)x % 4 == 0) && ((uintptr_t)out % 4 == 0) && ((uintptr_t)ctx % 8 == 0) && !options().force_simt;
+  const dim3 grid(paired ? (unsigned)((HW + kPix2 - 1) / kPix2) : (unsigned)((HW + kPix - 1) / kPix), (unsigned)B);
+#define ACE_CLN(E)                                                                                                                      \
+  do {                                                                                                                                  \
+    if (paired)                                                                                                                         \
+      cond_layer_norm_kernel2<E><<<grid, kWarps * 32, 0, stream>>>(x, x_plane, x_b, C, HW, lnw, lnb, sb0, w2, ctx, eps, out, o_plane, o_b); \
+    else                                                                                                                                \
+      cond_layer_norm_kernel<E><<<grid, kPix, 0, stream>>>(x, x_plane, x_b, C, HW, lnw, lnb, sb0, w2, ctx, eps, out, o_plane, o_b);      \
+  } while (0)
   switch (Ep) {
     case 0: ACE_CLN(0); break;
     case 8: ACE_CLN(8); break;
