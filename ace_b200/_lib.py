@@ -112,6 +112,9 @@ SIGNATURES = {
     "ace_csfno_create": (_I, [ctypes.POINTER(CsfnoConfig), _VP, _VP, ctypes.POINTER(_VP)]),
     "ace_csfno_destroy": (None, [_VP]),
     "ace_csfno_set_param": (_I, [_VP, _CP, _VP, _LL, _VP]),
+    "ace_csfno_query": (_I, [_VP, ctypes.POINTER(_I), ctypes.POINTER(_I), ctypes.POINTER(_LL)]),
+    "ace_stepper_create_conditional": (_I, [_VP, ctypes.POINTER(StepConfig), ctypes.POINTER(_VP)]),
+    "ace_stepper_set_context": (_I, [_VP, _VP, _VP]),
     "ace_csfno_finalize": (_I, [_VP, _VP]),
     "ace_csfno_forward": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _VP]),
     "ace_isotropic_noise": (_I, [_VP, _VP, _VP, _VP, _VP, _LL, _VP]),

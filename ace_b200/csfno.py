@@ -335,6 +335,14 @@ class SphericalFourierNeuralOperatorNet(nn.Module):
         return y.to(dtype)
 
 
+def _native_handle(self):
+    """The ace_csfno* behind this module (after at least one forward); used by the fused stepper."""
+    return self._net
+
+
+SphericalFourierNeuralOperatorNet.native_handle = _native_handle
+
+
 def get_lat_lon_sfnonet(params: SFNONetConfig, in_chans: int, out_chans: int, img_shape: Tuple[int, int], data_grid: str = "equiangular",
                         context_config: ContextConfig = ContextConfig()) -> SphericalFourierNeuralOperatorNet:
     """sfnonet.py:443-493."""

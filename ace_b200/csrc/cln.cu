@@ -199,6 +199,11 @@ __global__ void __launch_bounds__(kWarps * 32) cond_layer_norm_kernel2(const bf1
   unsigned hA = 0, lA = 0, hB = 0, lB = 0, hC = 0, lC = 0;
   ldraw(warp, hA, lA);
   ldraw(warp + kWarps, hB, lB);
+  // running pointers (the per-iteration strides are loop constants: no 64-bit multiplies on the FMA pipe inside the loop)
+  const long long cstep = (long long)kWarps * HW;
+  const unsigned* xpre = reinterpret_cast<const unsigned*>(xb + (long long)(warp + 2 * kWarps) * HW);  // bf16x2 words
+  bf16* op = ob + (long long)warp * HW;
+  const float* sbp = sb0 ? sb0 + ((long long)b * C + warp) * 2 : nullptr;
   int buf = 0;
   for (int c0 = 0; c0 < C; c0 += kCh2, buf ^= 1) {
     const int nch = min(kCh2, C - c0);
@@ -210,14 +215,21 @@ __global__ void __launch_bounds__(kWarps * 32) cond_layer_norm_kernel2(const bf1
     }
     __syncthreads();  // chunk `buf` has landed for every thread
     if (live) {
-      for (int cc = warp; cc < nch; cc += kWarps) {
+      const float2* wp = reinterpret_cast<const float2*>(wsm) + (buf * kCh2 + warp) * E;
+      for (int cc = warp; cc < nch; cc += kWarps, wp += kWarps * E, xpre += cstep / 2, op += cstep) {
         const int c = c0 + cc;
-        ldraw(c + 2 * kWarps, hC, lC);
-        const float sc_i = sb0 ? __ldg(sb0 + ((long long)b * C + c) * 2) : 1.f;
-        const float bi_i = sb0 ? __ldg(sb0 + ((long long)b * C + c) * 2 + 1) : 0.f;
+        if (c + 2 * kWarps < C) {
+          hC = __ldg(xpre);
+          lC = __ldg(xpre + x_plane / 2);
+        }
+        float sc_i = 1.f, bi_i = 0.f;
+        if (sbp) {
+          sc_i = __ldg(sbp);
+          bi_i = __ldg(sbp + 1);
+          sbp += 2 * kWarps;
+        }
         f2 a0 = mk2(sc_i, bi_i), a1 = a0;  // (scale, bias) of pixel 0 / pixel 1
         if (E > 0) {
-          const float2* wp = reinterpret_cast<const float2*>(wsm) + (buf * kCh2 + cc) * E;
 #pragma unroll
           for (int e = 0; e < E; ++e) {
             const float2 w = wp[e];
@@ -239,11 +251,11 @@ __global__ void __launch_bounds__(kWarps * 32) cond_layer_norm_kernel2(const bf1
         }
         y0 = fmaf(y0, sc0, bi0);
         y1 = fmaf(y1, sc1, bi1);
-        bf16 h0, l0, h1, l1;
-        split_bf16(y0, h0, l0);
-        split_bf16(y1, h1, l1);
-        *reinterpret_cast<__nv_bfloat162*>(ob + (long long)c * HW) = __halves2bfloat162(h0, h1);
-        *reinterpret_cast<__nv_bfloat162*>(ob + (long long)c * HW + o_plane) = __halves2bfloat162(l0, l1);
+        // split-bf16 store: hi = round-to-nearest bf16 of y, lo = bf16 of the remainder; two pixels per 32-bit word
+        const __nv_bfloat162 hi = __floats2bfloat162_rn(y0, y1);
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(y0 - __low2float(hi), y1 - __high2float(hi));
+        *reinterpret_cast<__nv_bfloat162*>(op) = hi;
+        *reinterpret_cast<__nv_bfloat162*>(op + o_plane) = lo;
       }
     }
     __syncthreads();  // everyone is done with chunk `buf` before it is refilled two iterations later

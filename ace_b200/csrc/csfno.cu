@@ -347,6 +347,15 @@ extern "C" int ace_csfno_create(const ace_csfno_config* cfg, ace_sht_plan* plan_
 
 extern "C" void ace_csfno_destroy(ace_csfno* net) { delete net; }
 
+extern "C" int ace_csfno_query(ace_csfno* net, int* in_chans, int* out_chans, long long* hw) {
+  ACE_API_BEGIN
+  ACE_REQUIRE(net && in_chans && out_chans && hw, "ace_csfno_query: null argument");
+  *in_chans = net->cfg.in_chans;
+  *out_chans = net->cfg.out_chans;
+  *hw = net->HW;
+  ACE_API_END
+}
+
 extern "C" int ace_csfno_set_param(ace_csfno* net, const char* name, const float* data_dev, long long numel, void* stream) {
   ACE_API_BEGIN
   ACE_REQUIRE(net && name && data_dev, "ace_csfno_set_param: null argument");

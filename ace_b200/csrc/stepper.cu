@@ -8,9 +8,15 @@
 #include "kernels.cuh"
 
 extern "C" int ace_sfno_forward(ace_sfno* net, const float* x_dev, float* y_dev, int batch, void* stream);
+extern "C" int ace_csfno_forward(ace_csfno* net, const float* x_dev, const float* scalar_dev, const float* labels_dev, const float* noise_dev,
+                                 const float* pos_dev, float* y_dev, int batch, void* stream);
+extern "C" int ace_csfno_query(ace_csfno* net, int* in_chans, int* out_chans, long long* hw);
 
 struct ace_stepper {
-  ace_sfno* net;
+  ace_sfno* net = nullptr;
+  ace_csfno* cnet = nullptr;               // noise-conditioned network instead of `net`
+  const float* noise = nullptr;            // its context fields: persistent device addresses the caller refills before each step
+  const float* pos = nullptr;
   int n_in, n_out, n_prog, n_forcing, residual;
   long long HW;
   ace::DevBuf in_kind, in_index, out_prog, prog_in_chan, in_mean, in_std, out_mean, out_std, out_clamp;
@@ -38,12 +44,41 @@ static void upload(DevBuf& d, const T* host, size_t n) {
   ACE_CHECK_CUDA(cudaMemcpy(d.p, host, n * sizeof(T), cudaMemcpyHostToDevice));
 }
 
+static ace_stepper* make_stepper(int cin, int cout, long long hw, const ace_step_config* cfg);
+
 extern "C" int ace_stepper_create(ace_sfno* net, const ace_step_config* cfg, ace_stepper** out) {
   ACE_API_BEGIN
   ACE_REQUIRE(net && cfg && out, "ace_stepper_create: null argument");
   int cin = 0, cout = 0;
   long long hw = 0;
   ACE_REQUIRE(ace_sfno_query(net, &cin, &cout, &hw) == ACE_OK, "ace_stepper_create: bad net");
+  ace_stepper* st = make_stepper(cin, cout, hw, cfg);
+  st->net = net;
+  *out = st;
+  ACE_API_END
+}
+
+extern "C" int ace_stepper_create_conditional(ace_csfno* net, const ace_step_config* cfg, ace_stepper** out) {
+  ACE_API_BEGIN
+  ACE_REQUIRE(net && cfg && out, "ace_stepper_create_conditional: null argument");
+  int cin = 0, cout = 0;
+  long long hw = 0;
+  ACE_REQUIRE(ace_csfno_query(net, &cin, &cout, &hw) == ACE_OK, "ace_stepper_create_conditional: bad net");
+  ace_stepper* st = make_stepper(cin, cout, hw, cfg);
+  st->cnet = net;
+  *out = st;
+  ACE_API_END
+}
+
+extern "C" int ace_stepper_set_context(ace_stepper* st, const float* noise_dev, const float* pos_dev) {
+  ACE_API_BEGIN
+  ACE_REQUIRE(st && st->cnet, "ace_stepper_set_context: the stepper does not drive a noise-conditioned network");
+  st->noise = noise_dev;
+  st->pos = pos_dev;
+  ACE_API_END
+}
+
+static ace_stepper* make_stepper(int cin, int cout, long long hw, const ace_step_config* cfg) {
   ACE_REQUIRE(cfg->n_in == cin && cfg->n_out == cout, "ace_stepper_create: net has %d->%d channels, step config %d->%d", cin,
               cout, cfg->n_in, cfg->n_out);
   ACE_REQUIRE(cfg->n_prog > 0 && cfg->n_forcing >= 0, "ace_stepper_create: bad state sizes");
@@ -59,7 +94,6 @@ extern "C" int ace_stepper_create(ace_sfno* net, const ace_step_config* cfg, ace
     ACE_REQUIRE(cfg->out_prog_index_host[c] >= -1 && cfg->out_prog_index_host[c] < cfg->n_prog, "out_prog_index[%d] out of range", c);
   ace_stepper* st = new ace_stepper();
   try {
-    st->net = net;
     st->n_in = cfg->n_in;
     st->n_out = cfg->n_out;
     st->n_prog = cfg->n_prog;
@@ -87,8 +121,7 @@ extern "C" int ace_stepper_create(ace_sfno* net, const ace_step_config* cfg, ace
     delete st;
     throw;
   }
-  *out = st;
-  ACE_API_END
+  return st;
 }
 
 extern "C" void ace_stepper_destroy(ace_stepper* st) { delete st; }
@@ -116,7 +149,8 @@ extern "C" int ace_stepper_step(ace_stepper* st, const float* prog_dev, const fl
   }
   launch_pack_normalize(prog_dev, forcing_dev, st->n_prog, st->n_forcing, st->in_kind.as<int>(), st->in_index.as<int>(),
                         st->in_mean.as<float>(), st->in_std.as<float>(), batch, st->n_in, st->HW, st->x.as<float>(), s);
-  int rc = ace_sfno_forward(st->net, st->x.as<float>(), st->y.as<float>(), batch, stream);
+  int rc = st->cnet ? ace_csfno_forward(st->cnet, st->x.as<float>(), nullptr, nullptr, st->noise, st->pos, st->y.as<float>(), batch, stream)
+                    : ace_sfno_forward(st->net, st->x.as<float>(), st->y.as<float>(), batch, stream);
   if (rc != ACE_OK) return rc;
   // reference order (single_module.py:670-709): ForcePositive -> conservation correctors -> ocean prescriber.  Without a
   // corrector the ocean overwrite rides in the denormalisation kernel; with one it is a separate pass over its one channel.

@@ -49,6 +49,14 @@ class FusedStepper:
         ``tendency_of_total_water_path_due_to_advection``).  The dry-air reference is captured from the first state the
         stepper sees after ``reset_corrector_state()`` (the initial condition of a rollout)."""
         self.module = module
+        # a NoiseConditionedModel wrapper (ace_b200/csfno.py): the step drives its conditional network and draws fresh noise per step
+        self._wrapper = module if hasattr(module, "conditional_model") else None
+        if self._wrapper is not None:
+            module = self.module = self._wrapper.conditional_model
+            cc = module.context_config
+            if cc.embed_dim_scalar or cc.embed_dim_labels:
+                raise NotImplementedError("FusedStepper: scalar / label conditioning is not supported in the fused step")
+        self._ctx = None
         self.in_names: List[str] = list(in_names)
         self.out_names: List[str] = list(out_names)
         if len(self.in_names) != module.in_chans or len(self.out_names) != module.out_chans:
@@ -88,7 +96,7 @@ class FusedStepper:
         if net is None:
             # materialise the device net (uploads parameters) with a throw-away forward
             with torch.no_grad():
-                self.module(torch.zeros(1, self.module.in_chans, *self.module.img_shape, device=device))
+                (self._wrapper or self.module)(torch.zeros(1, self.module.in_chans, *self.module.img_shape, device=device))
             net = self.module.native_handle()
         kind = np.array([0 if n in self.prognostic_names else 1 for n in self.in_names], dtype=np.int32)
         index = np.array(
@@ -112,9 +120,11 @@ class FusedStepper:
             ocean_interpolate=int(bool(self.ocean.get("interpolate", False))) if self.ocean is not None else 0,
         )
         handle = ctypes.c_void_p()
-        _lib.check(_lib.load().ace_stepper_create(net, ctypes.byref(cfg), ctypes.byref(handle)))
+        create = _lib.load().ace_stepper_create_conditional if self._wrapper is not None else _lib.load().ace_stepper_create
+        _lib.check(create(net, ctypes.byref(cfg), ctypes.byref(handle)))
         self._handle, self._handle_net = handle, net
         self._graph = None
+        self._ctx = None
         if self.corrector is not None:
             self._build_corrector()
             _lib.check(_lib.load().ace_stepper_set_corrector(self._handle, self._corrector_handle))
@@ -138,6 +148,20 @@ class FusedStepper:
 
         a, b = next_step_names(self.forcing_names)
         return forcing_next[..., [self.forcing_names.index(a), self.forcing_names.index(b)], :, :].contiguous()
+
+    def _refresh_context(self, B: int, device, noise: Optional[torch.Tensor]):
+        """Noise-conditioned network: (re)fill the persistent context buffers the native step reads -- a fresh noise draw per step
+        (``fme/ace/registry/stochastic_sfno.py:128-146``), or ``noise`` when the caller injects it (parity tests)."""
+        w = self._wrapper
+        H, Wd = self.module.img_shape
+        if self._ctx is None or self._ctx["B"] != B or self._ctx["device"] != device:
+            nz = torch.empty(B, w.embed_dim, H, Wd, device=device) if w.embed_dim > 0 else None
+            pos = w.pos_embed.detach().float().expand(B, -1, -1, -1).contiguous() if w.pos_embed is not None else None
+            self._ctx = dict(B=B, device=device, noise=nz, pos=pos)
+            _lib.check(_lib.load().ace_stepper_set_context(
+                self._handle, ctypes.c_void_p(nz.data_ptr()) if nz is not None else None, ctypes.c_void_p(pos.data_ptr()) if pos is not None else None))
+        if self._ctx["noise"] is not None:
+            self._ctx["noise"].copy_(noise if noise is not None else w.draw_noise(B, device))
 
     def reset_corrector_state(self):
         """Forget the dry-air reference: the next step's input state is treated as the initial condition of a new rollout."""
@@ -165,7 +189,7 @@ class FusedStepper:
     # ------------------------------------------------------------------ one step, packed tensors
     def step_packed(self, prog: torch.Tensor, forcing: Optional[torch.Tensor], out: Optional[torch.Tensor] = None,
                     next_prog: Optional[torch.Tensor] = None, ocean: Optional[torch.Tensor] = None,
-                    corrector_next: Optional[torch.Tensor] = None):
+                    corrector_next: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None):
         """prog [B, n_prog, H, W], forcing [B, n_forcing, H, W] (, ocean [B, 2, H, W]) (, corrector_next [B, 2, H, W] =
         (DSWRFtoa, HGTsfc) at the output time) -> (out [B, n_out, H, W], next_prog)."""
         if not prog.is_cuda:
@@ -196,6 +220,8 @@ class FusedStepper:
             self._ensure(prog.device)
             stream = _lib.current_stream_ptr()
             self.module._sync_params(stream)
+            if self._wrapper is not None:
+                self._refresh_context(B, prog.device, noise)
             _lib.check(_lib.load().ace_stepper_step(
                 self._handle, ctypes.c_void_p(prog.data_ptr()),
                 ctypes.c_void_p(forcing.data_ptr()) if forcing is not None else None,

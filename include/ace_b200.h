@@ -149,6 +149,7 @@ int ace_csfno_finalize(ace_csfno* net, void* stream);
  * -> y_dev float32 [batch][out_chans][H][W].  Enqueue-only, graph-capturable after the first call for a batch size. */
 int ace_csfno_forward(ace_csfno* net, const float* x_dev, const float* scalar_dev, const float* labels_dev, const float* noise_dev,
                       const float* pos_dev, float* y_dev, int batch, void* stream);
+int ace_csfno_query(ace_csfno* net, int* in_chans, int* out_chans, long long* hw);
 /* Isotropic Gaussian noise fields of unit pointwise variance (fme/ace/registry/stochastic_sfno.py:21-47) from the caller's two
  * N(0,1) draws real_dev / imag_dev float32 [nfields][lmax][mmax]: Im(a_l0) = 0, Re / Im of m > 0 divided by sqrt(2), all scaled
  * by sqrt(4 pi) / lmax, then the inverse SHT of `plan` -> noise_dev float32 [nfields][nlat][nlon].
@@ -187,6 +188,11 @@ void ace_stepper_destroy(ace_stepper* st);
  * {ocean fraction, target surface temperature} at the OUTPUT time (the reference's next_step_input_data); required
  * iff ocean_out_index >= 0.  corrector_next_dev: float32 [batch][2][H][W] = {DSWRFtoa, HGTsfc} at the OUTPUT time; required
  * iff the attached corrector has its energy budget correction on (ace_corrector_needs_next). */
+/* The same fused step around a noise-conditioned network (scalar / label contexts are not supported here).  Its context fields are
+ * read from persistent device buffers the caller refills before every step: noise_dev float32 [batch][embed_dim_noise][H][W] (a
+ * fresh draw per step, fme/ace/registry/stochastic_sfno.py:128-146) and pos_dev [batch][embed_dim_pos][H][W] (or NULL). */
+int ace_stepper_create_conditional(ace_csfno* net, const ace_step_config* cfg, ace_stepper** out);
+int ace_stepper_set_context(ace_stepper* st, const float* noise_dev, const float* pos_dev);
 int ace_stepper_step(ace_stepper* st, const float* prog_dev, const float* forcing_dev, const float* ocean_dev,
                      const float* corrector_next_dev, float* out_dev, float* next_prog_dev, int batch, void* stream);
 

@@ -133,3 +133,60 @@ def test_isotropic_noise_matches_reference_vector_and_wrapper():
     assert drawn.shape == (64, 8, *img) and abs(float(drawn.var()) - 1.0) < 0.05
     y1, y2 = model(x.cuda()), model(x.cuda())
     assert y1.shape == (2, 4, *img) and not torch.equal(y1, y2)  # stochastic: a fresh draw per call
+
+
+def test_fused_stepper_drives_noise_conditioned_network():
+    """FusedStepper around a NoiseConditionedModel: one step with injected noise vs the oracle chain (normalise, conditional net,
+    residual, denormalise), then stochastic CUDA-graph rollouts (a fresh isotropic draw per step, reproducible under a seed)."""
+    import ace_b200
+    from oracle import csfno as oc
+
+    img = (24, 48)
+    in_names = ["a", "b", "f1", "c", "f2"]
+    out_names = ["c", "d1", "a", "b", "d2", "d3"]
+    names = sorted(set(in_names + out_names))
+    means = {n: 0.1 * (i - 3) for i, n in enumerate(names)}
+    stds = {n: 0.5 + 0.25 * i for i, n in enumerate(names)}
+    sel = ace_b200.ModuleSelector(type="B200NoiseConditionedSFNO", config=dict(embed_dim=32, num_layers=2, noise_embed_dim=8, noise_type="isotropic",
+                                                                                affine_norms=True, normalize_big_skip=True))
+    torch.manual_seed(4)
+    model = sel.build(len(in_names), len(out_names), ace_b200.DatasetInfo(img_shape=img)).torch_module
+    torch.manual_seed(4)
+    onet = oc.SphericalFourierNeuralOperatorNet(img, len(in_names), len(out_names), oc.ContextConfig(embed_dim_noise=8), embed_dim=32, num_layers=2,
+                                                affine_norms=True, normalize_big_skip=True, data_grid="legendre-gauss").eval()
+    with torch.no_grad():
+        for k, p in onet.named_parameters():
+            if "W_scale" in k or "W_bias" in k:
+                p.add_(0.3 * torch.randn_like(p))
+    model.conditional_model.load_state_dict(onet.state_dict())
+    model = model.cuda().eval().requires_grad_(False)
+    st = ace_b200.FusedStepper(model, in_names, out_names, means, stds, residual_prediction=True)
+    assert st.prognostic_names == ["c", "a", "b"] and st.forcing_names == ["f1", "f2"]
+    B = 2
+    state = {n: torch.randn(B, *img) * stds[n] + means[n] for n in in_names}
+    noise = oc.NoiseConditionedModel(onet, img, embed_dim_noise=8, isotropic=True).draw_noise(B)
+    norm = {n: (state[n] - means[n]) / stds[n] for n in in_names}
+    with torch.no_grad():
+        y = onet(torch.stack([norm[n] for n in in_names], dim=1), oc.Context(noise=noise))
+    ref = {n: y[:, i] for i, n in enumerate(out_names)}
+    for n in st.prognostic_names:
+        ref[n] = ref[n] + norm[n]
+    prog = torch.stack([state[n] for n in st.prognostic_names], dim=1).cuda()
+    forcing = torch.stack([state[n] for n in st.forcing_names], dim=1).cuda()
+    out, nxt = st.step_packed(prog, forcing, noise=noise.cuda())
+    for i, n in enumerate(out_names):
+        assert field_rel_err(((out[:, i].cpu() - means[n]) / stds[n])[:, None], ref[n][:, None]) < 1e-4, n
+    # rollouts: every step draws its own noise; same seed + same call sequence -> same trajectory; members differ
+    T = 3
+    fseq = torch.randn(T, B, 2, *img).cuda()
+    prog0 = prog[:1].expand(B, -1, -1, -1).contiguous()  # identical members: only the noise separates them
+    st.rollout(prog0, fseq, 1)  # capture
+    torch.manual_seed(9)
+    o1, f1 = st.rollout(prog0, fseq, T)
+    torch.manual_seed(9)
+    o2, f2 = st.rollout(prog0, fseq, T)
+    torch.testing.assert_close(o1, o2, rtol=0, atol=0)
+    o3, _ = st.rollout(prog0, fseq, T)
+    assert not torch.equal(o1, o3)
+    assert not torch.equal(o1[:, 0], o1[:, 1])
+    assert torch.isfinite(o1).all()
