@@ -50,6 +50,11 @@ class StepConfig(ctypes.Structure):
     ]
 
 
+class SlabOceanConfig(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in ("prog_sst", "out_dlw_sfc", "out_ulw_sfc", "out_dsw_sfc", "out_usw_sfc", "out_lhf", "out_shf")] + [
+        ("timestep_seconds", ctypes.c_double)]
+
+
 class CsfnoConfig(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in (
         "img_h", "img_w", "in_chans", "out_chans", "embed_dim", "num_layers", "lmax", "mmax", "mlp_hidden", "pos_embed", "big_skip",
@@ -114,6 +119,7 @@ SIGNATURES = {
     "ace_csfno_set_param": (_I, [_VP, _CP, _VP, _LL, _VP]),
     "ace_csfno_query": (_I, [_VP, ctypes.POINTER(_I), ctypes.POINTER(_I), ctypes.POINTER(_LL)]),
     "ace_stepper_create_conditional": (_I, [_VP, ctypes.POINTER(StepConfig), ctypes.POINTER(_VP)]),
+    "ace_stepper_set_slab_ocean": (_I, [_VP, ctypes.POINTER(SlabOceanConfig)]),
     "ace_stepper_set_context": (_I, [_VP, _VP, _VP]),
     "ace_csfno_finalize": (_I, [_VP, _VP]),
     "ace_csfno_forward": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _VP]),

@@ -305,6 +305,36 @@ __global__ void __launch_bounds__(kThreads) ocean_prescribe_kernel(float* __rest
   }
 }
 
+// slab ocean (fme/core/ocean.py:64-88,223-243): target = T_in + (F_net + Q) / (rho * depth * c_p) * dt with F_net the net surface
+// energy flux of the generated (corrected) fields without frozen precipitation (metrics.py:299-334), then the prescriber.
+// ocean = [B][3][HW] {mask, q_flux, mixed layer depth}
+__global__ void __launch_bounds__(kThreads) ocean_slab_kernel(float* __restrict__ out, float* __restrict__ next_prog,
+                                                             const float* __restrict__ prev_prog, const int* __restrict__ out_prog_index,
+                                                             int n_out, int n_prog, long long HW, int ocean_out, int ocean_interp,
+                                                             const float* __restrict__ ocean, SlabOceanIdx ix) {
+  const int b = blockIdx.y;
+  float* ob = out + (long long)b * n_out * HW;
+  float* d = ob + (long long)ocean_out * HW;
+  const int p = out_prog_index[ocean_out];
+  float* np = (p >= 0 && next_prog != nullptr) ? next_prog + ((long long)b * n_prog + p) * HW : nullptr;
+  const float* om = ocean + (long long)b * 3 * HW;
+  const float* tin = prev_prog + ((long long)b * n_prog + ix.prog_sst) * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
+    auto o = [&](int c) { return ob[(long long)c * HW + i]; };
+    const float rad = o(ix.dsw) - o(ix.usw) + o(ix.dlw) - o(ix.ulw);
+    const float turb = -o(ix.lhf) - o(ix.shf);
+    const float fnet = rad + turb - 0.f;
+    const float tend = (fnet + om[HW + i]) / (1000.f * om[2 * HW + i] * 4000.f);  // DENSITY_OF_WATER, SPECIFIC_HEAT_OF_WATER
+    const float tgt = tin[i] + tend * ix.dt;
+    float v = d[i];
+    const float m = om[i];
+    if (ocean_interp) v = m * tgt + (1.f - m) * v;
+    else if ((int)rintf(m) == 1) v = tgt;
+    d[i] = v;
+    if (np) np[i] = v;
+  }
+}
+
 }  // namespace
 
 void launch_norm_split(const float* src, int B, int C, long long HW, const double* stats, const float* gamma,
@@ -410,6 +440,14 @@ void launch_ocean_prescribe(float* out, float* next_prog, const int* out_prog_in
   dim3 grid(grid_for(HW, kThreads, 64), B);
   ocean_prescribe_kernel<<<grid, kThreads, 0, stream>>>(out, next_prog, out_prog_index, n_out, n_prog, HW, ocean_out, ocean_interp, ocean);
   after_launch("ocean_prescribe");
+}
+
+void launch_ocean_slab(float* out, float* next_prog, const float* prev_prog, const int* out_prog_index, int B, int n_out, int n_prog, long long HW,
+                       int ocean_out, int ocean_interp, const float* ocean, const SlabOceanIdx& ix, cudaStream_t stream) {
+  ProfileScope prof("ocean_slab", stream);
+  dim3 grid(grid_for(HW, kThreads, 64), B);
+  ocean_slab_kernel<<<grid, kThreads, 0, stream>>>(out, next_prog, prev_prog, out_prog_index, n_out, n_prog, HW, ocean_out, ocean_interp, ocean, ix);
+  after_launch("ocean_slab");
 }
 
 }  // namespace ace

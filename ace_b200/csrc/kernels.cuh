@@ -59,6 +59,15 @@ void launch_unpack_denormalize(const float* y, const float* x_norm, const int* o
 void launch_ocean_prescribe(float* out, float* next_prog, const int* out_prog_index, int B, int n_out, int n_prog, long long HW,
                             int ocean_out, int ocean_interp, const float* ocean, cudaStream_t stream);
 
+// slab ocean instead of the prescribed target: ocean = [B][3][HW] {mask, q_flux, mixed layer depth}; target = T_in + (F_net + Q) /
+// (rho depth c_p) dt (fme/core/ocean.py:64-88,223-243); channel indices into out (fluxes) / the prognostic input state (T_in)
+struct SlabOceanIdx {
+  int prog_sst, dlw, ulw, dsw, usw, lhf, shf;
+  float dt;
+};
+void launch_ocean_slab(float* out, float* next_prog, const float* prev_prog, const int* out_prog_index, int B, int n_out, int n_prog, long long HW,
+                       int ocean_out, int ocean_interp, const float* ocean, const SlabOceanIdx& ix, cudaStream_t stream);
+
 }  // namespace ace
 
 namespace ace {

@@ -21,6 +21,8 @@ struct ace_stepper {
   long long HW;
   ace::DevBuf in_kind, in_index, out_prog, prog_in_chan, in_mean, in_std, out_mean, out_std, out_clamp;
   int ocean_out = -1, ocean_interp = 0;
+  bool slab = false;
+  ace::SlabOceanIdx slab_ix;
   ace_corrector* corrector = nullptr;
   ace::DevBuf x, y;
   int wsB = 0;
@@ -124,6 +126,25 @@ static ace_stepper* make_stepper(int cin, int cout, long long hw, const ace_step
   return st;
 }
 
+extern "C" int ace_stepper_set_slab_ocean(ace_stepper* st, const ace_slab_ocean_config* cfg) {
+  ACE_API_BEGIN
+  ACE_REQUIRE(st, "ace_stepper_set_slab_ocean: null stepper");
+  if (!cfg) {
+    st->slab = false;
+    return ACE_OK;
+  }
+  ACE_REQUIRE(st->ocean_out >= 0, "ace_stepper_set_slab_ocean: the step has no ocean surface temperature channel (ocean_out_index)");
+  auto ok = [&](int c, int n) { return c >= 0 && c < n; };
+  ACE_REQUIRE(ok(cfg->prog_sst, st->n_prog), "ace_stepper_set_slab_ocean: surface temperature must be a prognostic input");
+  const int fl[6] = {cfg->out_dlw_sfc, cfg->out_ulw_sfc, cfg->out_dsw_sfc, cfg->out_usw_sfc, cfg->out_lhf, cfg->out_shf};
+  for (int k = 0; k < 6; ++k) ACE_REQUIRE(ok(fl[k], st->n_out), "ace_stepper_set_slab_ocean: flux channel %d out of range", k);
+  ACE_REQUIRE(cfg->timestep_seconds > 0, "ace_stepper_set_slab_ocean: timestep must be positive");
+  st->slab_ix = {cfg->prog_sst, cfg->out_dlw_sfc, cfg->out_ulw_sfc, cfg->out_dsw_sfc, cfg->out_usw_sfc, cfg->out_lhf, cfg->out_shf,
+                 (float)cfg->timestep_seconds};
+  st->slab = true;
+  ACE_API_END
+}
+
 extern "C" void ace_stepper_destroy(ace_stepper* st) { delete st; }
 
 extern "C" int ace_stepper_set_corrector(ace_stepper* st, ace_corrector* c) {
@@ -154,7 +175,7 @@ extern "C" int ace_stepper_step(ace_stepper* st, const float* prog_dev, const fl
   if (rc != ACE_OK) return rc;
   // reference order (single_module.py:670-709): ForcePositive -> conservation correctors -> ocean prescriber.  Without a
   // corrector the ocean overwrite rides in the denormalisation kernel; with one it is a separate pass over its one channel.
-  const bool split = st->corrector != nullptr && st->ocean_out >= 0;
+  const bool split = (st->corrector != nullptr || st->slab) && st->ocean_out >= 0;
   launch_unpack_denormalize(st->y.as<float>(), st->x.as<float>(), st->out_prog.as<int>(), st->prog_in_chan.as<int>(),
                             st->out_mean.as<float>(), st->out_std.as<float>(), st->residual, batch, st->n_out, st->n_in,
                             st->n_prog, st->HW, st->out_clamp.as<int>(), split ? -1 : st->ocean_out, st->ocean_interp, ocean_dev, out_dev,
@@ -167,7 +188,10 @@ extern "C" int ace_stepper_step(ace_stepper* st, const float* prog_dev, const fl
     rc = ace_corrector_apply(st->corrector, prog_dev, forcing_dev, corrector_next_dev, out_dev, next_prog_dev, batch, stream);
     if (rc != ACE_OK) return rc;
   }
-  if (split)
+  if (split && st->slab)
+    launch_ocean_slab(out_dev, next_prog_dev, prog_dev, st->out_prog.as<int>(), batch, st->n_out, st->n_prog, st->HW, st->ocean_out,
+                      st->ocean_interp, ocean_dev, st->slab_ix, s);
+  else if (split)
     launch_ocean_prescribe(out_dev, next_prog_dev, st->out_prog.as<int>(), batch, st->n_out, st->n_prog, st->HW, st->ocean_out,
                            st->ocean_interp, ocean_dev, s);
   ACE_API_END

@@ -40,7 +40,10 @@ class FusedStepper:
         """``force_positive_names``: outputs clamped to >= 0 after denormalisation (the corrector's ForcePositive,
         ``fme/core/corrector/utils.py:26-43``).  ``ocean``: ``{"surface_temperature_name": ..., "interpolate": False}`` enables
         the prescribed-SST ocean (``fme/core/ocean.py:165-215``): every step then takes ``ocean`` data ``[B, 2, H, W]`` =
-        (ocean fraction, target surface temperature) valid at the OUTPUT time.
+        (ocean fraction, target surface temperature) valid at the OUTPUT time.  With ``"slab": {"mixed_layer_depth_name": ...,
+        "q_flux_name": ..., "timestep_seconds": 21600.0}`` the target is the slab-ocean prediction instead (``fme/core/ocean.py:64-88``:
+        input surface temperature + (net surface energy flux of the corrected outputs + q-flux) / (rho depth c_p) dt) and the ocean
+        data is ``[B, 3, H, W]`` = (ocean fraction, q-flux, mixed layer depth).
         ``corrector``: the conservation correctors of ``fme/core/corrector/atmosphere.py`` (``conserve_dry_air``,
         ``moisture_budget_correction``), run between ForcePositive and the ocean like the reference:
         ``dict(conserve_dry_air=True, moisture_budget_correction="advection_and_precipitation", ak=..., bk=...,
@@ -75,6 +78,10 @@ class FusedStepper:
         self.ocean = dict(ocean) if ocean is not None else None
         if self.ocean is not None and self.ocean["surface_temperature_name"] not in self.out_names:
             raise ValueError("ocean surface_temperature_name must be an output")
+        self._slab = dict(self.ocean["slab"]) if self.ocean is not None and self.ocean.get("slab") else None
+        self.n_ocean = 0 if self.ocean is None else (3 if self._slab else 2)
+        if self._slab is not None and self.ocean["surface_temperature_name"] not in self.in_names:
+            raise ValueError("slab ocean: the surface temperature must be a prognostic variable (input and output)")
         self._means = {k: float(v) for k, v in means.items()}
         self._stds = {k: float(v) for k, v in stds.items()}
         for n in set(self.in_names) | set(self.out_names):
@@ -125,6 +132,18 @@ class FusedStepper:
         self._handle, self._handle_net = handle, net
         self._graph = None
         self._ctx = None
+        if self._slab is not None:
+            from .corrector import _find  # the reference's field-name prefixes (fme/core/atmosphere_data.py:17-41)
+
+            keys = dict(out_dlw_sfc="sfc_down_lw_radiative_flux", out_ulw_sfc="sfc_up_lw_radiative_flux", out_dsw_sfc="sfc_down_sw_radiative_flux",
+                        out_usw_sfc="sfc_up_sw_radiative_flux", out_lhf="latent_heat_flux", out_shf="sensible_heat_flux")
+            idx = {k: _find(self.out_names, v) for k, v in keys.items()}
+            missing = [keys[k] for k, i in idx.items() if i < 0]
+            if missing:
+                raise ValueError(f"slab ocean: no output field for {missing}")
+            scfg = _lib.SlabOceanConfig(prog_sst=self.prognostic_names.index(self.ocean["surface_temperature_name"]),
+                                        timestep_seconds=float(self._slab.get("timestep_seconds", 21600.0)), **idx)
+            _lib.check(_lib.load().ace_stepper_set_slab_ocean(self._handle, ctypes.byref(scfg)))
         if self.corrector is not None:
             self._build_corrector()
             _lib.check(_lib.load().ace_stepper_set_corrector(self._handle, self._corrector_handle))
@@ -203,8 +222,9 @@ class FusedStepper:
             raise ValueError("ocean data must be given exactly when an ocean model is configured")
         if ocean is not None:
             ocean = ocean.float().contiguous()
-            if tuple(ocean.shape) != (B, 2, H, W):
-                raise ValueError(f"ocean data must be [B, 2, H, W] = (ocean fraction, target surface temperature), got {tuple(ocean.shape)}")
+            if tuple(ocean.shape) != (B, self.n_ocean, H, W):
+                raise ValueError(f"ocean data must be [B, {self.n_ocean}, H, W] = (ocean fraction, "
+                                 f"{'q-flux, mixed layer depth' if self._slab else 'target surface temperature'}), got {tuple(ocean.shape)}")
         if self.corrector_needs_next != (corrector_next is not None):
             raise ValueError("corrector_next = (DSWRFtoa, HGTsfc) at the output time must be given exactly when the energy budget "
                              "correction is configured")
@@ -239,7 +259,11 @@ class FusedStepper:
         if self.ocean is not None:
             # the reference reads both from next_step_input_data (fme/core/step/single_module.py:708-709)
             nxt = next_step_input_data or {}
-            ocean = torch.stack([nxt[self.ocean["ocean_fraction_name"]], nxt[self.ocean["surface_temperature_name"]]], dim=1)
+            if self._slab is not None:
+                ocean = torch.stack([nxt[self.ocean["ocean_fraction_name"]], nxt[self._slab["q_flux_name"]],
+                                     nxt[self._slab["mixed_layer_depth_name"]]], dim=1)
+            else:
+                ocean = torch.stack([nxt[self.ocean["ocean_fraction_name"]], nxt[self.ocean["surface_temperature_name"]]], dim=1)
         cnext = None
         if self.corrector_needs_next:
             from .corrector import next_step_names
@@ -287,7 +311,7 @@ class FusedStepper:
                 B=B, prog=torch.empty_like(state),
                 forcing=torch.empty(B, len(self.forcing_names), H, W, device=dev) if self.forcing_names else None,
                 out=torch.empty(B, n_out, H, W, device=dev), nxt=torch.empty(B, n_prog, H, W, device=dev),
-                ocean=torch.zeros(B, 2, H, W, device=dev) if self.ocean is not None else None,
+                ocean=torch.ones(B, self.n_ocean, H, W, device=dev) if self.ocean is not None else None,
                 cnext=torch.zeros(B, 2, H, W, device=dev) if needs_next else None,
             )
             st["prog"].copy_(state)
@@ -322,7 +346,7 @@ class FusedStepper:
             nt = 2 if self.corrector_needs_next else 1
             self.rollout(prog0, torch.zeros(nt, B, len(self.forcing_names), H, W, device=prog0.device) if self.forcing_names else None, 1,
                          use_cuda_graph=True, keep_outputs=False,
-                         ocean_seq=torch.zeros(1, B, 2, H, W, device=prog0.device) if self.ocean is not None else None)
+                         ocean_seq=torch.ones(1, B, self.n_ocean, H, W, device=prog0.device) if self.ocean is not None else None)
         return self._static, self._graph
 
     def rollout_host(self, prog0: torch.Tensor, forcing_host: Optional[torch.Tensor], n_steps: int,

@@ -196,6 +196,18 @@ int ace_stepper_set_context(ace_stepper* st, const float* noise_dev, const float
 int ace_stepper_step(ace_stepper* st, const float* prog_dev, const float* forcing_dev, const float* ocean_dev,
                      const float* corrector_next_dev, float* out_dev, float* next_prog_dev, int batch, void* stream);
 
+/* Slab ocean instead of a prescribed target (fme/core/ocean.py:64-88,223-243; configs/baselines/shield-som): the surface
+ * temperature written where the mask selects ocean is T_in + (F_net + Q) / (rho depth c_p) dt, F_net = net surface energy flux of
+ * the generated fields (after the correctors) without frozen precipitation (fme/core/metrics.py:299-334).  ocean_dev of
+ * ace_stepper_step is then float32 [batch][3][H][W] = {ocean fraction, q_flux, mixed layer depth} at the OUTPUT time.  NULL: back
+ * to the prescribed target. */
+typedef struct ace_slab_ocean_config {
+  int prog_sst;                      /* surface temperature in the prognostic INPUT state */
+  int out_dlw_sfc, out_ulw_sfc, out_dsw_sfc, out_usw_sfc, out_lhf, out_shf; /* DLWRFsfc ULWRFsfc DSWRFsfc USWRFsfc LHTFLsfc SHTFLsfc */
+  double timestep_seconds;
+} ace_slab_ocean_config;
+int ace_stepper_set_slab_ocean(ace_stepper* st, const ace_slab_ocean_config* cfg);
+
 /* ---- conservation correctors of the post-step state -------------
  * fme/core/corrector/atmosphere.py:404-463 (conserve_dry_air: pin the area-weighted global mean of ps - g * total water path
  * to its value at the initial condition by a globally constant dry-air pressure offset, solving for ps) and :518-608

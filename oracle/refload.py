@@ -279,7 +279,15 @@ def load_corrector():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
-    _CACHE["corrector"] = types.SimpleNamespace(AtmosphereData=ad.AtmosphereData, CorrectorState=state_ns["CorrectorState"],
+    # fme/core/ocean.py: mixed_layer_temperature_tendency, by name (the file's other imports need the prescriber / registries)
+    with open(os.path.join(REFERENCE_ROOT, "fme", "core", "ocean.py")) as f:
+        otree = ast.parse(f.read())
+    opick = [n for n in otree.body if isinstance(n, ast.FunctionDef) and n.name == "mixed_layer_temperature_tendency"]
+    assert len(opick) == 1
+    ons = {"torch": torch, "DENSITY_OF_WATER": mods["fme.core.constants"].DENSITY_OF_WATER,
+           "SPECIFIC_HEAT_OF_WATER": mods["fme.core.constants"].SPECIFIC_HEAT_OF_WATER}
+    exec(compile(ast.Module(body=opick, type_ignores=[]), "fme/core/ocean.py", "exec"), ons)
+    _CACHE["corrector"] = types.SimpleNamespace(AtmosphereData=ad.AtmosphereData, mixed_layer_temperature_tendency=ons["mixed_layer_temperature_tendency"], CorrectorState=state_ns["CorrectorState"],
                                                 seed=ns["_seed_global_dry_air_mass"], adjust=ns["_adjust_gen_dry_air_to_target"],
                                                 conserve_moisture=ns["_force_conserve_moisture"],
                                                 zero_mean_advection=ns["_force_zero_global_mean_moisture_advection"],

@@ -441,3 +441,96 @@ def test_fused_rollout_with_full_corrector_graph_equals_eager_and_oracle_step():
     st.rollout_host(prog0, forcing.cpu().pin_memory(), T, out_host)
     torch.cuda.synchronize()
     torch.testing.assert_close(out_host, og.cpu(), rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("interpolate", [True, False])
+def test_fused_step_with_slab_ocean_matches_oracle(interpolate):
+    """The SHiELD-SOM baseline's post-step block (configs/baselines/shield-som/ace-train-config.yaml:133-146): full corrector
+    sequence, then the slab ocean (fme/core/ocean.py:64-88) through the prescriber; graph rollout == eager."""
+    import ace_b200
+    from oracle import corrector as oc
+    from oracle import metrics as om
+    from oracle import ocean as oo
+    from oracle import sfno as osfno
+    from tests.test_gpu_stepper import _oracle_step
+
+    img = (32, 64)
+    sst = "surface_temperature"
+    forcing_names = FORCING_E + ["ocean_fraction"]
+    in_names = PROG_E + [sst] + forcing_names
+    out_names = OUT_E + [sst]
+    allnames = sorted(set(in_names + out_names))
+    means, stds = {n: 0.0 for n in allnames}, {n: 1.0 for n in allnames}
+    means["PRESsfc"], stds["PRESsfc"] = 1.0e5, 800.0
+    for k in range(NZ):
+        means[f"specific_total_water_{k}"], stds[f"specific_total_water_{k}"] = 1e-3 * (k + 1), 4e-4 * (k + 1)
+        means[f"air_temperature_{k}"], stds[f"air_temperature_{k}"] = 210.0 + 10.0 * k, 4.0
+    for n, m in zip(FLUXES, [340.0, 390.0, 190.0, 30.0, 20.0, 100.0, 240.0]):
+        means[n], stds[n] = m, 20.0
+    means["PRATEsfc"], stds["PRATEsfc"] = 3e-5, 1.5e-5
+    means["total_frozen_precipitation_rate"], stds["total_frozen_precipitation_rate"] = 3e-5, 3e-5
+    means["LHTFLsfc"], stds["LHTFLsfc"] = 90.0, 30.0
+    stds["tendency_of_total_water_path_due_to_advection"] = 1e-5
+    means["DSWRFtoa"], stds["DSWRFtoa"] = 340.0, 100.0
+    means["HGTsfc"], stds["HGTsfc"] = 400.0, 800.0
+    means[sst], stds[sst] = 288.0, 12.0
+    torch.manual_seed(0)
+    onet = osfno.SphericalFourierNeuralOperatorNet(img, len(in_names), len(out_names), embed_dim=16, num_layers=2, operator_type="dhconv").eval()
+    sel = ace_b200.ModuleSelector(type="B200SphericalFourierNeuralOperatorNet", config=dict(embed_dim=16, num_layers=2, operator_type="dhconv"))
+    net = sel.build(len(in_names), len(out_names), ace_b200.DatasetInfo(img_shape=img)).torch_module
+    net.load_state_dict(onet.state_dict())
+    net = net.cuda().eval().requires_grad_(False)
+    ak, bk, w = _coords(*img)
+    fp = [f"specific_total_water_{k}" for k in range(NZ)] + ["PRATEsfc", "total_frozen_precipitation_rate"]
+    st = ace_b200.FusedStepper(
+        net, in_names, out_names, means, stds, residual_prediction=True, force_positive_names=fp,
+        ocean=dict(surface_temperature_name=sst, ocean_fraction_name="ocean_fraction", interpolate=interpolate,
+                   slab=dict(mixed_layer_depth_name="prescribed_mixed_layer_depth", q_flux_name="prescribed_qflux", timestep_seconds=21600.0)),
+        corrector=dict(conserve_dry_air=True, moisture_budget_correction="advection_and_precipitation",
+                       total_energy_budget_correction=dict(method="constant_temperature", constant_unaccounted_heating=1.14),
+                       ak=ak, bk=bk, area_weights=w, timestep_seconds=21600.0))
+    assert st.n_ocean == 3
+    B = 2
+    g = torch.Generator().manual_seed(17)
+    state = {n: torch.randn(B, *img, generator=g) * stds[n] + means[n] for n in in_names}
+    for k in range(NZ):
+        state[f"specific_total_water_{k}"] = state[f"specific_total_water_{k}"].clamp(min=0)
+    nxt = {"DSWRFtoa": 340.0 + 100.0 * torch.rand(B, *img, generator=g), "HGTsfc": state["HGTsfc"],
+           "ocean_fraction": torch.rand(B, *img, generator=g), "prescribed_qflux": 30.0 * torch.randn(B, *img, generator=g),
+           "prescribed_mixed_layer_depth": 20.0 + 60.0 * torch.rand(B, *img, generator=g)}
+    vc = oc.VerticalCoordinate(ak, bk)
+    ref = _oracle_step(onet, in_names, out_names, means, stds, True, state)
+    for n in fp:
+        ref[n] = torch.clamp(ref[n], min=0.0)
+    target = oc.seed_global_dry_air_mass(state["PRESsfc"], _wat(state), lambda d, keepdim=False: om.weighted_mean(d, w.to(d.dtype), keepdim=keepdim), vc)
+    ref = _oracle_full(state, state, nxt, ref, target, w, ak, bk, "advection_and_precipitation", False, False, 1.14)
+    f_net = oo.net_surface_energy_flux_without_frozen_precip(ref["DLWRFsfc"], ref["ULWRFsfc"], ref["DSWRFsfc"], ref["USWRFsfc"], ref["LHTFLsfc"],
+                                                             ref["SHTFLsfc"])
+    t_slab = oo.slab_surface_temperature(state[sst], f_net, nxt["prescribed_qflux"], nxt["prescribed_mixed_layer_depth"], 21600.0)
+    ref[sst] = oo.prescribe(nxt["ocean_fraction"], ref[sst], t_slab, interpolate)
+    st.reset_corrector_state()
+    out = st.step({n: v.cuda() for n, v in state.items()}, next_step_input_data={n: v.cuda() for n, v in nxt.items()})
+    for n in out_names:
+        a = ((out[n].cpu() - means[n]) / stds[n])[:, None]
+        b = ((ref[n] - means[n]) / stds[n])[:, None]
+        tol = 1e-3 if n == "tendency_of_total_water_path_due_to_advection" else 1e-4
+        ulp = 2.0 * 2.0 ** -23 * (abs(means[n]) + float(b.abs().max()) * stds[n]) / stds[n]
+        err = float((a - b).abs().amax())
+        assert err < tol * float(b.abs().amax()) + ulp, (n, err, float(b.abs().amax()), ulp)
+    assert float((ref[sst] - _oracle_step(onet, in_names, out_names, means, stds, True, state)[sst]).abs().max()) > 0.1  # the ocean acted
+    # rollouts: graph == eager, host-pipelined == device
+    T = 3
+    prog0 = torch.stack([state[n] for n in st.prognostic_names], dim=1).cuda()
+    fm = torch.tensor([means[n] for n in st.forcing_names])[None, None, :, None, None]
+    fs = torch.tensor([stds[n] for n in st.forcing_names])[None, None, :, None, None]
+    forcing = (torch.randn(T + 1, B, len(st.forcing_names), *img, generator=g) * fs + fm).cuda()
+    ocean = torch.stack([torch.rand(T, B, *img, generator=g), 30.0 * torch.randn(T, B, *img, generator=g),
+                         20.0 + 60.0 * torch.rand(T, B, *img, generator=g)], dim=2).cuda()
+    oe, fe = st.rollout(prog0, forcing, T, use_cuda_graph=False, ocean_seq=ocean)
+    og, fg = st.rollout(prog0, forcing, T, use_cuda_graph=True, ocean_seq=ocean)
+    torch.testing.assert_close(og, oe, rtol=0, atol=0)
+    torch.testing.assert_close(fg, fe, rtol=0, atol=0)
+    out_host = torch.empty(T, B, len(out_names), *img).pin_memory()
+    st.rollout_host(prog0, forcing.cpu().pin_memory(), T, out_host, ocean_host=ocean.cpu().pin_memory())
+    torch.cuda.synchronize()
+    torch.testing.assert_close(out_host, og.cpu(), rtol=0, atol=0)

@@ -121,3 +121,18 @@ def test_oracle_energy_and_small_corrections_equal_reference(frozen):
         for k in range(NZ):
             assert torch.equal(r[f"air_temperature_{k}"], t[..., k]), k
         assert float((t - _temp(gen)).abs().max()) > 1e-3  # the correction is not a no-op on this state
+
+
+def test_oracle_slab_ocean_equals_reference():
+    from oracle import ocean as oo
+
+    ref = refload.load_corrector()
+    ak, bk, w, inp, gen, forcing = energy_state(5)
+    g = torch.Generator().manual_seed(1)
+    q = 30.0 * torch.randn(gen["PRESsfc"].shape, generator=g)
+    depth = 20.0 + 60.0 * torch.rand(gen["PRESsfc"].shape, generator=g)
+    f_ref = ref.AtmosphereData(gen).net_surface_energy_flux_without_frozen_precip
+    f = oo.net_surface_energy_flux_without_frozen_precip(gen["DLWRFsfc"], gen["ULWRFsfc"], gen["DSWRFsfc"], gen["USWRFsfc"], gen["LHTFLsfc"],
+                                                         gen["SHTFLsfc"])
+    assert torch.equal(f, f_ref)
+    assert torch.equal(oo.mixed_layer_temperature_tendency(f, q, depth), ref.mixed_layer_temperature_tendency(f_ref, q, depth))
