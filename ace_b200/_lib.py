@@ -59,7 +59,7 @@ class CsfnoConfig(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in (
         "img_h", "img_w", "in_chans", "out_chans", "embed_dim", "num_layers", "lmax", "mmax", "mlp_hidden", "pos_embed", "big_skip",
         "normalize_big_skip", "affine_norms", "embed_dim_scalar", "embed_dim_labels", "embed_dim_noise", "embed_dim_pos")] + [
-        ("norm_eps", ctypes.c_float)]
+        ("norm_eps", ctypes.c_float), ("filter_residual", ctypes.c_int), ("filter_output", ctypes.c_int)]
 
 
 class CorrectorConfig(ctypes.Structure):
@@ -122,6 +122,8 @@ SIGNATURES = {
     "ace_stepper_set_slab_ocean": (_I, [_VP, ctypes.POINTER(SlabOceanConfig)]),
     "ace_stepper_set_context": (_I, [_VP, _VP, _VP]),
     "ace_csfno_finalize": (_I, [_VP, _VP]),
+    "ace_label_embed": (_I, [_VP, _VP, _VP, _I, _I, _I, _VP, _VP]),
+    "ace_label_pos_embed": (_I, [_VP, _VP, _VP, _I, _I, _LL, _VP, _VP]),
     "ace_csfno_forward": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _VP]),
     "ace_isotropic_noise": (_I, [_VP, _VP, _VP, _VP, _VP, _LL, _VP]),
     "ace_corrector_create": (_I, [ctypes.POINTER(CorrectorConfig), ctypes.POINTER(_VP)]),

@@ -15,11 +15,22 @@ keeps its own re-laid-out copy, refreshed when a parameter's storage or version 
 Random draws (the N(0,1) numbers behind the noise) come from ``torch.randn`` on the input's device, as the reference's come
 from ``fme.core.rand.randn``; everything downstream (isotropic scaling, inverse SHT, the network) runs in the library.
 
+Options that only re-parameterise the per-degree spectral operator or a 1x1 convolution are folded into the parameters the
+device library receives (``_sync_params``; exact identities, evaluated in fp64 once per parameter change, never per step):
+
+* ``filter_num_groups = G``      -> block-diagonal dense ``[L, C, C]`` operator (s2convolutions.py:229-236, :388);
+* ``spectral_lora_rank``         -> ``W_l + (alpha / r) B_l A_l``                  (s2convolutions.py:94-115, :393-410);
+* ``filter_preserves_global_mean`` -> ``W_0 = I``                                  (s2convolutions.py:411-418);
+* ``spectral_ratio < 1``         -> ``Q W'_l P`` with the pre / post projections  (s2convolutions.py:210-228: channel-wise linear
+  maps commute with the transforms; the transform then runs at full width, i.e. the option's speed-up is not realised);
+* ``lora_rank`` (``LoRAConv2d``) -> ``W + (alpha / r) W_up W_down``                (lora.py:131-141).
+
+``filter_residual`` / ``filter_output`` (SHT round trips of the residual streams / the output) run on the device.
+
 Unsupported reference options raise ``NotImplementedError`` at construction (no fallback): ``filter_type`` other than
-``"linear"``, ``filter_num_groups != 1``, ``global_layer_norm``, ``filter_residual`` / ``filter_output``, local (DISCO) blocks,
-LoRA, ``spectral_ratio != 1``, ``filter_preserves_global_mean``, ``clip_latent_global_means``, ``use_mlp=False``,
-``encoder_layers != 1``, dropout, activation other than GELU, noise + positional context wider than 64 channels, learned label
-embeddings / label-position interaction.
+``"linear"``, ``global_layer_norm``, local (DISCO) blocks, ``spectral_ratio < 1`` together with a round-trip residual
+(``filter_residual`` or a non-Gaussian data grid), ``clip_latent_global_means``, ``use_mlp=False``, ``encoder_layers != 1``,
+dropout, activation other than GELU, noise + positional context wider than 64 channels.
 """
 import ctypes
 import dataclasses
@@ -127,15 +138,65 @@ class _ConditionalLayerNorm(nn.Module):
                     getattr(self, name).weight.zero_()
 
 
-class _SpectralConvS2(nn.Module):
-    """Holder for SpectralConvS2 (s2convolutions.py:162-280): ``weight`` [1, L, C, C, 2] and ``bias`` [1, C, 1, 1]."""
+def _lora_scaling(rank, alpha):
+    return (float(alpha) if alpha is not None else float(rank)) / float(rank)
 
-    def __init__(self, channels, modes_lat):
+
+class _LoRAConv2d(nn.Conv2d):
+    """Holder for LoRAConv2d (lora.py:9-141), 1x1: ``weight``, ``bias``, ``lora_down.weight``, ``lora_up.weight`` created and
+    initialised in the reference's order (base conv, down, up, then Kaiming re-draw of down and zeroed up)."""
+
+    def __init__(self, in_channels, out_channels, bias=True, lora_rank=0, lora_alpha=None):
+        super().__init__(in_channels, out_channels, 1, 1, bias=bias)
+        if lora_rank < 0:
+            raise ValueError(f"lora_rank must be >= 0, got {lora_rank}")
+        self.lora_rank = int(lora_rank)
+        self.lora_scaling = 0.0
+        if self.lora_rank > 0:
+            self.lora_down = nn.Conv2d(in_channels, self.lora_rank, 1, bias=False)
+            self.lora_up = nn.Conv2d(self.lora_rank, out_channels, 1, 1, bias=False)
+            self.lora_scaling = _lora_scaling(lora_rank, lora_alpha)
+            nn.init.kaiming_uniform_(self.lora_down.weight, a=math.sqrt(5))
+            nn.init.zeros_(self.lora_up.weight)
+
+    def sources(self):
+        return [self.weight, self.lora_down.weight, self.lora_up.weight]
+
+    def effective_weight(self):
+        """``W + (alpha / r) W_up W_down`` [O, I, 1, 1] fp32: lora.py:131-141 is linear in x, so the update merges exactly."""
+        with torch.no_grad():
+            up, down = self.lora_up.weight.double().flatten(1), self.lora_down.weight.double().flatten(1)
+            w = self.weight.double().flatten(1) + self.lora_scaling * (up @ down)
+            return w.float().reshape(self.weight.shape).contiguous()
+
+
+class _SpectralConvS2(nn.Module):
+    """Holder for SpectralConvS2 (s2convolutions.py:138-280): ``pre_proj`` / ``post_proj`` (``spectral_ratio < 1``), ``weight``
+    [G, L, C_s/G, C_s/G, 2], ``lora_A`` / ``lora_B``, ``bias`` [1, C, 1, 1], in the reference's creation order."""
+
+    def __init__(self, channels, modes_lat, num_groups=1, lora_rank=0, lora_alpha=None, preserve_global_mean=False, spectral_ratio=1.0):
         super().__init__()
-        self.modes_lat, self.channels = modes_lat, channels
-        scale = math.sqrt(1 / channels) * torch.ones(modes_lat, 1, 1, 2)
+        sc = validate_spectral_ratio(spectral_ratio, channels, num_groups, channels_name="in_channels", num_groups_name="num_groups")
+        if channels % num_groups != 0:
+            raise ValueError(f"in_channels={channels} is not divisible by num_groups={num_groups}")
+        self.modes_lat, self.channels, self.spectral_channels, self.num_groups = modes_lat, channels, sc, num_groups
+        self.preserve_global_mean = bool(preserve_global_mean)
+        if spectral_ratio < 1.0:
+            self.pre_proj = nn.Conv2d(channels, sc, kernel_size=1, bias=False)
+            self.post_proj = nn.Conv2d(sc, channels, kernel_size=1, bias=False)
+        else:
+            self.pre_proj = self.post_proj = None
+        scale = math.sqrt(1 / sc) * torch.ones(modes_lat, 1, 1, 2)
         scale[0, :] *= math.sqrt(2.0)
-        self.weight = nn.Parameter(scale * torch.randn(1, modes_lat, channels, channels, 2))
+        self.weight = nn.Parameter(scale * torch.randn(num_groups, modes_lat, sc // num_groups, sc // num_groups, 2))
+        self.lora_rank = int(lora_rank)
+        if self.lora_rank > 0:
+            self.lora_A = nn.Parameter(scale * torch.randn(num_groups, modes_lat, lora_rank, sc // num_groups, 2))
+            self.lora_B = nn.Parameter(torch.zeros(num_groups, modes_lat, sc // num_groups, lora_rank, 2))
+            self.lora_scaling = _lora_scaling(lora_rank, lora_alpha)
+        else:
+            self.lora_A = self.lora_B = None
+            self.lora_scaling = 0.0
         self.bias = nn.Parameter(torch.zeros(1, channels, 1, 1))
         self.register_load_state_dict_pre_hook(self._upgrade_old_weight_layouts)
 
@@ -146,36 +207,96 @@ class _SpectralConvS2(nn.Module):
         w = state_dict.get(key)
         if w is None:
             return
-        c, lat = module.channels, module.modes_lat
-        if tuple(w.shape) == (c, c, lat, 2):
-            w = w.view(1, c, c, lat, 2)
-        if tuple(w.shape) == (1, c, c, lat, 2) and tuple(w.shape) != tuple(module.weight.shape):
+        g, lat, c = module.num_groups, module.modes_lat, module.weight.shape[2]
+        if tuple(w.shape) == (c * g, c * g, lat, 2):
+            w = w.view(1, *w.shape)
+        if w.ndim == 5 and tuple(w.shape) == (g, c, c, lat, 2) and tuple(w.shape) != tuple(module.weight.shape):
             w = w.permute(0, 3, 2, 1, 4)
         state_dict[key] = w
 
+    @property
+    def is_plain(self):
+        """True when ``weight`` already is the dense [1, L, C, C, 2] operator the device library takes."""
+        return self.num_groups == 1 and self.lora_rank == 0 and not self.preserve_global_mean and self.pre_proj is None
+
+    def sources(self):
+        return [p for p in (self.weight, self.lora_A, self.lora_B, getattr(self.pre_proj, "weight", None),
+                            getattr(self.post_proj, "weight", None)) if p is not None]
+
+    def effective_weight(self):
+        """The dense per-degree operator [1, L, C, C, 2] fp32 equivalent to this layer's grouped / LoRA / mean-preserving /
+        bottlenecked contraction (module docstring); fp64 arithmetic, a few degrees at a time to bound the scratch memory."""
+        G, L, cg = self.num_groups, self.modes_lat, self.spectral_channels // self.num_groups
+        C, sc = self.channels, self.spectral_channels
+        with torch.no_grad():
+            dev = self.weight.device
+            out = torch.empty(L, C, C, 2, dtype=torch.float32, device=dev)
+            P = self.pre_proj.weight.double().flatten(1).to(torch.complex128) if self.pre_proj is not None else None    # [sc, C]
+            Q = self.post_proj.weight.double().flatten(1).to(torch.complex128) if self.post_proj is not None else None  # [C, sc]
+            step = max(1, min(L, (1 << 22) // max(1, C * C)))
+            for l0 in range(0, L, step):
+                l1 = min(L, l0 + step)
+                w = torch.view_as_complex(self.weight[:, l0:l1].double().contiguous())  # [G, l, o, i]
+                if self.lora_rank > 0:
+                    a = torch.view_as_complex(self.lora_A[:, l0:l1].double().contiguous())  # [G, l, r, i]
+                    b = torch.view_as_complex(self.lora_B[:, l0:l1].double().contiguous())  # [G, l, o, r]
+                    w = w + self.lora_scaling * torch.einsum("gxor,gxri->gxoi", b, a)
+                dense = torch.zeros(l1 - l0, sc, sc, dtype=torch.complex128, device=dev)
+                for g in range(G):
+                    dense[:, g * cg:(g + 1) * cg, g * cg:(g + 1) * cg] = w[g]
+                if self.preserve_global_mean and l0 == 0:
+                    dense[0] = torch.eye(sc, dtype=torch.complex128, device=dev)
+                if P is not None:
+                    dense = Q @ dense @ P
+                out[l0:l1] = torch.view_as_real(dense).float()
+            return out.unsqueeze(0).contiguous()
+
+
+def validate_spectral_ratio(spectral_ratio, channels, num_groups, *, channels_name="embed_dim", num_groups_name="filter_num_groups",
+                            filter_type=None, local_blocks=False):
+    """s2convolutions.py:34-91: the spectral channel count ``round(channels * spectral_ratio)`` and the reference's errors."""
+    if not 0.0 < spectral_ratio <= 1.0:
+        raise ValueError(f"spectral_ratio must be in (0, 1], got {spectral_ratio}.")
+    spectral_channels = round(channels * spectral_ratio)
+    if spectral_ratio < 1.0:
+        if filter_type is not None and filter_type != "linear":
+            raise NotImplementedError(f"spectral_ratio < 1 is only supported for filter_type='linear', got filter_type='{filter_type}'.")
+        if local_blocks:
+            raise NotImplementedError("spectral_ratio < 1 is not supported with local_blocks, since local (DISCO) blocks have no "
+                                      "spectral filter to bottleneck.")
+        if spectral_channels < 1:
+            raise ValueError(f"spectral_ratio={spectral_ratio} with {channels_name}={channels} produces fewer than 1 spectral channel.")
+        if spectral_channels % num_groups != 0:
+            raise ValueError(f"spectral_ratio={spectral_ratio} with {channels_name}={channels} yields {spectral_channels} spectral "
+                             f"channels, which is not divisible by {num_groups_name}={num_groups}.")
+    return spectral_channels
+
 
 class _FilterLayer(nn.Module):
-    def __init__(self, channels, modes_lat):
+    def __init__(self, channels, modes_lat, **kw):
         super().__init__()
-        self.filter = _SpectralConvS2(channels, modes_lat)
+        self.filter = _SpectralConvS2(channels, modes_lat, **kw)
 
 
 class _MLP(nn.Module):
-    def __init__(self, channels, hidden):
+    def __init__(self, channels, hidden, lora_rank=0, lora_alpha=None):
         super().__init__()
-        self.fwd = nn.Sequential(nn.Conv2d(channels, hidden, 1, bias=True), nn.GELU(), nn.Conv2d(hidden, channels, 1, bias=True))
+        self.fwd = nn.Sequential(_LoRAConv2d(channels, hidden, True, lora_rank, lora_alpha), nn.GELU(),
+                                 _LoRAConv2d(hidden, channels, True, lora_rank, lora_alpha))
 
 
 class _Block(nn.Module):
     """Holder for FourierNeuralOperatorBlock (sfnonet.py:262-374), same registration order."""
 
-    def __init__(self, channels, hidden, modes_lat, cc, affine_norms):
+    def __init__(self, channels, hidden, modes_lat, cc, p):
         super().__init__()
-        self.norm0 = _ConditionalLayerNorm(channels, cc, affine_norms)
-        self.filter = _FilterLayer(channels, modes_lat)
-        self.inner_skip = nn.Conv2d(channels, channels, 1, 1)
-        self.norm1 = _ConditionalLayerNorm(channels, cc, affine_norms)
-        self.mlp = _MLP(channels, hidden)
+        self.norm0 = _ConditionalLayerNorm(channels, cc, p.affine_norms)
+        self.filter = _FilterLayer(channels, modes_lat, num_groups=p.filter_num_groups, lora_rank=p.spectral_lora_rank,
+                                   lora_alpha=p.spectral_lora_alpha, preserve_global_mean=p.filter_preserves_global_mean,
+                                   spectral_ratio=p.spectral_ratio)
+        self.inner_skip = _LoRAConv2d(channels, channels, True, p.lora_rank, p.lora_alpha)
+        self.norm1 = _ConditionalLayerNorm(channels, cc, p.affine_norms)
+        self.mlp = _MLP(channels, hidden, p.lora_rank, p.lora_alpha)
 
 
 # ---------------------------------------------------------------------------------------------- the conditional network
@@ -191,14 +312,16 @@ class SphericalFourierNeuralOperatorNet(nn.Module):
             unsupported.append(f"filter_type={p.filter_type!r}")
         if p.scale_factor != 1:
             raise NotImplementedError("scale factor must be 1 as it is not implemented for conditional layer normalization")
-        for name, off in (("global_layer_norm", False), ("filter_residual", False), ("filter_output", False), ("lora_rank", 0),
-                          ("spectral_lora_rank", 0), ("filter_preserves_global_mean", False), ("clip_latent_global_means", False),
-                          ("filter_num_groups", 1), ("spectral_ratio", 1.0), ("encoder_layers", 1), ("drop_rate", 0.0),
+        validate_spectral_ratio(p.spectral_ratio, p.embed_dim, p.filter_num_groups, filter_type=p.filter_type,
+                                local_blocks=bool(p.local_blocks))  # SFNONetConfig.__post_init__ (sfnonet.py:139-146)
+        for name, off in (("global_layer_norm", False), ("clip_latent_global_means", False), ("encoder_layers", 1), ("drop_rate", 0.0),
                           ("drop_path_rate", 0.0), ("use_mlp", True)):
             if getattr(p, name) != off:
                 unsupported.append(f"{name}={getattr(p, name)!r}")
         if p.local_blocks:
             unsupported.append("local_blocks")
+        if p.spectral_ratio < 1.0 and (p.filter_residual or data_grid != "legendre-gauss"):
+            unsupported.append("spectral_ratio < 1 with a round-trip residual (filter_residual or a non-Gaussian data grid)")
         if p.activation_function != "gelu":
             if p.activation_function not in ("relu", "silu"):
                 raise ValueError(f"Unknown activation function {p.activation_function}")
@@ -211,6 +334,7 @@ class SphericalFourierNeuralOperatorNet(nn.Module):
         self.img_shape = tuple(img_shape)
         self.in_chans, self.out_chans, self.embed_dim, self.num_layers = in_chans, out_chans, p.embed_dim, p.num_layers
         self.big_skip, self.affine_norms = p.big_skip, p.affine_norms
+        self.filter_residual, self.filter_output = bool(p.filter_residual), bool(p.filter_output)
         h, w = self.img_shape
         self.modes_lat = int(h * p.hard_thresholding_fraction)
         self.modes_lon = int((w // 2 + 1) * p.hard_thresholding_fraction)
@@ -221,9 +345,10 @@ class SphericalFourierNeuralOperatorNet(nn.Module):
         self.trans = RealSHT(h, w, grid="legendre-gauss", **kw)
         self.itrans = InverseRealSHT(h, w, grid="legendre-gauss", **kw)
         C = p.embed_dim
-        self.encoder = nn.Sequential(nn.Conv2d(in_chans, C, 1, bias=True), nn.GELU(), nn.Conv2d(C, C, 1, bias=False))
-        self.blocks = nn.ModuleList([_Block(C, self.mlp_hidden, self.modes_lat, context_config, p.affine_norms) for _ in range(p.num_layers)])
-        self.decoder = nn.Sequential(nn.Conv2d(C + p.big_skip * in_chans, C, 1, bias=True), nn.GELU(), nn.Conv2d(C, out_chans, 1, bias=False))
+        lora = (p.lora_rank, p.lora_alpha)
+        self.encoder = nn.Sequential(_LoRAConv2d(in_chans, C, True, *lora), nn.GELU(), _LoRAConv2d(C, C, False, *lora))
+        self.blocks = nn.ModuleList([_Block(C, self.mlp_hidden, self.modes_lat, context_config, p) for _ in range(p.num_layers)])
+        self.decoder = nn.Sequential(_LoRAConv2d(C + p.big_skip * in_chans, C, True, *lora), nn.GELU(), _LoRAConv2d(C, out_chans, False, *lora))
         if p.pos_embed:
             self.pos_embed = nn.Parameter(torch.zeros(1, C, h, w))
             self.pos_embed.is_shared_mp = ["matmul"]
@@ -245,7 +370,8 @@ class SphericalFourierNeuralOperatorNet(nn.Module):
             num_layers=self.num_layers, lmax=self.modes_lat, mmax=self.modes_lon, mlp_hidden=self.mlp_hidden,
             pos_embed=int(self.pos_embed is not None), big_skip=int(bool(self.big_skip)), normalize_big_skip=int(hasattr(self, "norm_big_skip")),
             affine_norms=int(bool(self.affine_norms)), embed_dim_scalar=cc.embed_dim_scalar, embed_dim_labels=cc.embed_dim_labels,
-            embed_dim_noise=cc.embed_dim_noise, embed_dim_pos=cc.embed_dim_pos, norm_eps=1e-5)
+            embed_dim_noise=cc.embed_dim_noise, embed_dim_pos=cc.embed_dim_pos, norm_eps=1e-5,
+            filter_residual=int(self.filter_residual), filter_output=int(self.filter_output))
 
     def _release(self):
         if getattr(self, "_net", None) is not None:
@@ -272,19 +398,38 @@ class SphericalFourierNeuralOperatorNet(nn.Module):
         _lib.check(_lib.load().ace_csfno_create(ctypes.byref(cfg), outer.handle, inner.handle, ctypes.byref(handle)))
         self._net, self._net_device, self._plans = handle, device, (outer, inner)
 
+    def device_parameters(self):
+        """``[(key, sources, build)]``: every parameter the device library takes, under the reference's ``state_dict`` key of the
+        un-adapted layer, with the torch parameters it is derived from.  ``build`` is ``None`` when the single source is passed
+        as stored; otherwise it returns the folded fp32 tensor (module docstring: LoRA merges, grouped / mean-preserving /
+        bottlenecked spectral operators)."""
+        derived, hidden = {}, set()
+        for prefix, mod in self.named_modules():
+            if isinstance(mod, _LoRAConv2d) and mod.lora_rank > 0:
+                derived[prefix + ".weight"] = (mod.sources(), mod.effective_weight)
+                hidden.update((prefix + ".lora_down.weight", prefix + ".lora_up.weight"))
+            elif isinstance(mod, _SpectralConvS2) and not mod.is_plain:
+                derived[prefix + ".weight"] = (mod.sources(), mod.effective_weight)
+                hidden.update(prefix + "." + n for n in ("lora_A", "lora_B", "pre_proj.weight", "post_proj.weight"))
+        out = []
+        for name, prm in self.named_parameters():
+            if name in hidden or (not self.big_skip and name.startswith("norm_big_skip.")):
+                continue  # (the reference still creates norm_big_skip without a big skip; it is never used)
+            sources, build = derived.get(name, ([prm], None))
+            out.append((name, sources, build))
+        return out
+
     def _sync_params(self, stream):
         lib = _lib.load()
         dirty = False
-        skip_big = not self.big_skip  # the reference still creates norm_big_skip without a big skip; it is never used
-        for name, prm in self.named_parameters():
-            if skip_big and name.startswith("norm_big_skip."):
-                continue
-            key = (prm.data_ptr(), prm._version)
+        for name, sources, build in self.device_parameters():
+            key = tuple((p.data_ptr(), p._version) for p in sources)
             if self._uploaded.get(name) == key:
                 continue
-            if prm.device != self._net_device:
-                raise _lib.AceError(f"parameter {name} is on {prm.device}, input is on {self._net_device}")
-            t = prm.detach()
+            for p in sources:
+                if p.device != self._net_device:
+                    raise _lib.AceError(f"parameter {name} is on {p.device}, input is on {self._net_device}")
+            t = sources[0].detach() if build is None else build()
             if t.dtype != torch.float32 or not t.is_contiguous():
                 t = t.float().contiguous()
             _lib.check(lib.ace_csfno_set_param(self._net, name.encode(), ctypes.c_void_p(t.data_ptr()), t.numel(), stream))
@@ -382,18 +527,24 @@ class NoiseConditionedModel(nn.Module):
     def __init__(self, conditional_model: nn.Module, img_shape: Tuple[int, int], embed_dim_noise: int = 256, embed_dim_pos: int = 0,
                  n_labels: int = 0, label_embed_dim: int = 0, inverse_sht=None, lmax: int = 0, mmax: int = 0):
         super().__init__()
-        if label_embed_dim > 0:
-            raise NotImplementedError("ace_b200 NoiseConditionedSFNO does not implement learned label embeddings (label_embed_dim > 0)")
-        if embed_dim_pos != 0 and n_labels > 0:
-            raise NotImplementedError("ace_b200 NoiseConditionedSFNO does not implement the label-position interaction embedding")
         self.conditional_model = conditional_model
         self.embed_dim, self.img_shape = embed_dim_noise, tuple(img_shape)
         self._inverse_sht, self._lmax, self._mmax = inverse_sht, lmax, mmax
-        self.label_embedding = None
+        if label_embed_dim > 0 and n_labels == 0:
+            raise ValueError("label_embed_dim > 0 requires n_labels > 0")
+        if label_embed_dim > 0:
+            self.label_embedding = nn.Linear(n_labels, label_embed_dim)
+            effective_label_dim = label_embed_dim
+        else:
+            self.label_embedding = None
+            effective_label_dim = n_labels
         self.label_pos_embed = None
         if embed_dim_pos != 0:
             self.pos_embed = nn.Parameter(torch.zeros(1, embed_dim_pos, *self.img_shape))
             nn.init.trunc_normal_(self.pos_embed, std=0.02)
+            if effective_label_dim > 0:
+                self.label_pos_embed = nn.Parameter(torch.zeros(effective_label_dim, embed_dim_pos, *self.img_shape))
+                nn.init.trunc_normal_(self.label_pos_embed, std=0.02)
         else:
             self.pos_embed = None
 
@@ -404,9 +555,38 @@ class NoiseConditionedModel(nn.Module):
 
     def forward(self, x: torch.Tensor, labels: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
         x = x.reshape(-1, *x.shape[-3:])
+        B = x.shape[0]
         if noise is None and self.embed_dim > 0:
-            noise = self.draw_noise(x.shape[0], x.device)
-        pos = self.pos_embed.expand(x.shape[0], -1, -1, -1) if self.pos_embed is not None else None
+            noise = self.draw_noise(B, x.device)
+        lib, vp = _lib.load(), ctypes.c_void_p
+        if labels is not None and (self.label_embedding is not None or self.label_pos_embed is not None):
+            if not x.is_cuda:
+                raise _lib.AceError("ace_b200 NoiseConditionedSFNO: input must be a CUDA tensor (there is no CPU path)")
+            labels = labels.to(device=x.device, dtype=torch.float32).contiguous()
+        if labels is not None and self.label_embedding is not None and B > 0:
+            lin = self.label_embedding  # stochastic_sfno.py:152-153
+            if labels.dim() != 2 or labels.shape != (B, lin.in_features):
+                raise ValueError(f"labels: expected {(B, lin.in_features)}, got {tuple(labels.shape)}")
+            w, b = lin.weight.detach().float().contiguous(), lin.bias.detach().float().contiguous()
+            emb = torch.empty(B, lin.out_features, dtype=torch.float32, device=x.device)
+            with torch.cuda.device(x.device):
+                _lib.check(lib.ace_label_embed(vp(labels.data_ptr()), vp(w.data_ptr()), vp(b.data_ptr()), B, lin.in_features, lin.out_features,
+                                               vp(emb.data_ptr()), _lib.current_stream_ptr()))
+            labels = emb
+        pos = None
+        if self.pos_embed is not None:
+            if self.label_pos_embed is not None and labels is not None and B > 0:  # stochastic_sfno.py:157-165
+                n = self.label_pos_embed.shape[0]
+                if labels.dim() != 2 or labels.shape != (B, n):
+                    raise ValueError(f"labels: expected {(B, n)}, got {tuple(labels.shape)}")
+                base = self.pos_embed.detach().float().contiguous()
+                lpe = self.label_pos_embed.detach().float().contiguous()
+                pos = torch.empty(B, *base.shape[1:], dtype=torch.float32, device=x.device)
+                with torch.cuda.device(x.device):
+                    _lib.check(lib.ace_label_pos_embed(vp(base.data_ptr()), vp(labels.data_ptr()), vp(lpe.data_ptr()), B, n, base.numel(),
+                                                       vp(pos.data_ptr()), _lib.current_stream_ptr()))
+            else:
+                pos = self.pos_embed.expand(B, -1, -1, -1)
         return self.conditional_model(x, Context(embedding_scalar=None, embedding_pos=pos, labels=labels, noise=noise if self.embed_dim > 0 else None))
 
 

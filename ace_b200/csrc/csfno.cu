@@ -7,7 +7,13 @@
 //
 //   h --CLN0(ctx)--> xn --G1 DFT--> X1 --G2 Legendre--> c1 --G3 dhconv--> c2 --G4 Legendre--> g --G5 iDFT--> T (fp32)
 //   r = xn, or iSHT(SHT(xn)) when the block's forward / inverse grids differ (first / last block on an equiangular data grid)
+//       (or in every block with filter_residual)
 //   t = GELU(T + b_filter + W_skip r + b_skip) --CLN1(ctx)--> tn --fc1 + GELU--> hmid --fc2 + b + r--> h (next block)
+//
+// filter_residual also passes the big-skip copy of the input through trans_down -> itrans_up, filter_output the network output
+// (sfnonet.py:581-591,775-778,822): four GemmOps each on the data-grid plan with their own (zero-initialised) spectral buffers.
+// Grouped / LoRA / mean-preserving / bottlenecked spectral operators arrive as the equivalent dense [L][C][C] operator
+// (ace_b200/csfno.py folds them when a parameter changes), so the filter is always the one complex GEMM per degree below.
 //
 // Unlike the InstanceNorm of the deterministic SFNO (sfno.cu), the conditional layer norm is per PIXEL over channels with a
 // per-pixel, per-channel affine map (functions of the noise field), so it cannot be folded into the neighbouring GEMMs'
@@ -29,6 +35,24 @@ struct ClnW {
   DevBuf Ws, bs, Wb, bb, Wsl, bsl, Wbl, bbl;  // Linear layers on the scalar embedding / labels
   DevBuf ws_n, wb_n, ws_p, wb_p;            // 1x1-conv weights on the noise / positional context, fp32 as given
   DevBuf w2;                                // [C][Ep][2] built by finalize
+};
+
+// buffers of one outer-grid SHT round trip at a fixed channel count (the never-written l < m region of c1 must stay zero, so
+// round trips of different widths do not share them)
+struct RtBuf {
+  DevBuf x1, c1, g;
+  long long p_x1 = 0, p_c1 = 0, p_g = 0;
+  int B = 0;
+  void ensure(const ace_sht_plan& p, int C, int batch) {
+    if (batch <= B) return;
+    p_x1 = batch * p.x1_elems(C);
+    p_c1 = batch * p.c1_elems(C);
+    p_g = batch * p.g_elems(C);
+    x1.ensure(2 * (size_t)p_x1 * sizeof(bf16));
+    c1.ensure(2 * (size_t)p_c1 * sizeof(bf16));
+    g.ensure(2 * (size_t)p_g * sizeof(bf16));
+    B = batch;
+  }
 };
 
 struct CBlockW {
@@ -57,6 +81,9 @@ struct ace_csfno {
   int wsB = 0;
   DevBuf xin, hcat, e1, hP, xn, rr, x1, c1, c2, g, T, tP, tn, hmid, d1, ctx, sb0;
   long long p_xin, p_hcat, p_act, p_x1, p_c1, p_c2, p_g, p_hmid;
+  RtBuf rt_in, rt_out;  // filter_residual on the big skip (in_chans wide) / filter_output (out_chans wide)
+  DevBuf xrt, yP;       // planes [B][in_chans][HW]: filtered input ahead of norm_big_skip; [B][out_chans][HW]: unfiltered output
+  long long p_yP = 0;
 };
 
 namespace {
@@ -144,6 +171,15 @@ void ensure_ws(ace_csfno& n, int B) {
   n.T.ensure((size_t)n.p_act * sizeof(float));
   n.hmid.ensure(2 * (size_t)n.p_hmid * e);
   if (n.Ep > 0) n.ctx.ensure((size_t)B * n.Ep * HW * sizeof(float));
+  if (c.big_skip && c.filter_residual) {
+    n.rt_in.ensure(*n.outer, c.in_chans, B);
+    if (c.normalize_big_skip) n.xrt.ensure(2 * (size_t)n.p_xin * e);
+  }
+  if (c.filter_output) {
+    n.rt_out.ensure(*n.outer, c.out_chans, B);
+    n.p_yP = (long long)B * c.out_chans * HW;
+    n.yP.ensure(2 * (size_t)n.p_yP * e);
+  }
   n.sb0.ensure((size_t)B * std::max(C, c.in_chans) * 2 * sizeof(float));
   n.wsB = B;
 }
@@ -163,6 +199,17 @@ void run_cln(ace_csfno& n, const ClnW& w, const bf16* x, long long x_plane, long
                          o_b, s);
 }
 
+// itrans_up(trans_down(x)) for `Cc` channels of split planes -> split planes `out`, or fp32 `outf` when given
+void round_trip_outer(ace_csfno& n, RtBuf& r, const bf16* x, long long x_plane, long long x_b, int Cc, int B, bf16* out, long long o_plane,
+                      long long o_b, float* outf, long long f_b, cudaStream_t s) {
+  const ace_sht_plan& p = *n.outer;
+  run_gemm(sht_op_dft_fwd(p, x, x_plane, x_b, Cc, B, r.x1.as<bf16>(), r.p_x1), s);
+  run_gemm(sht_op_legendre_fwd(p, r.x1.as<bf16>(), r.p_x1, Cc, B, r.c1.as<bf16>(), r.p_c1), s);
+  run_gemm(sht_op_legendre_inv_from_c1(p, r.c1.as<bf16>(), r.p_c1, Cc, B, r.g.as<bf16>(), r.p_g), s);
+  if (outf) run_gemm(sht_op_dft_inv(p, r.g.as<bf16>(), r.p_g, Cc, B, outf, f_b), s);
+  else run_gemm(sht_op_dft_inv_planes(p, r.g.as<bf16>(), r.p_g, Cc, B, out, o_plane, o_b), s);
+}
+
 void forward(ace_csfno& n, const float* x, const float* scalar, const float* labels, const float* noise, const float* posctx, float* y, int B,
              cudaStream_t s) {
   const ace_csfno_config& c = n.cfg;
@@ -180,9 +227,11 @@ void forward(ace_csfno& n, const float* x, const float* scalar, const float* lab
   // of the concat buffer (sfnonet.py:775-778)
   const bf16* enc_in;
   long long enc_plane, enc_b;
-  if (c.big_skip && !c.normalize_big_skip) {
-    launch_norm_split(x, B, Cin, HW, nullptr, nullptr, nullptr, 0.f, hcat + (long long)C * HW, P_hcat, cat_b, HW, s);
-    enc_in = hcat + (long long)C * HW;
+  bf16* const skip_dst = hcat + (long long)C * HW;
+  const bool rt_skip = c.big_skip && c.filter_residual;  // residual = itrans_up(trans_down(x)); the encoder still reads x itself
+  if (c.big_skip && !c.normalize_big_skip && !rt_skip) {
+    launch_norm_split(x, B, Cin, HW, nullptr, nullptr, nullptr, 0.f, skip_dst, P_hcat, cat_b, HW, s);
+    enc_in = skip_dst;
     enc_plane = P_hcat;
     enc_b = cat_b;
   } else {
@@ -190,7 +239,16 @@ void forward(ace_csfno& n, const float* x, const float* scalar, const float* lab
     enc_in = n.xin.as<bf16>();
     enc_plane = P_xin;
     enc_b = in_b;
-    if (c.big_skip) run_cln(n, n.nbs, enc_in, P_xin, in_b, scalar, labels, B, hcat + (long long)C * HW, P_hcat, cat_b, s);
+    if (rt_skip && !c.normalize_big_skip) {
+      round_trip_outer(n, n.rt_in, enc_in, P_xin, in_b, Cin, B, skip_dst, P_hcat, cat_b, nullptr, 0, s);
+    } else if (c.big_skip) {
+      const bf16* src = enc_in;
+      if (rt_skip) {
+        round_trip_outer(n, n.rt_in, enc_in, P_xin, in_b, Cin, B, n.xrt.as<bf16>(), P_xin, in_b, nullptr, 0, s);
+        src = n.xrt.as<bf16>();
+      }
+      run_cln(n, n.nbs, src, P_xin, in_b, scalar, labels, B, skip_dst, P_hcat, cat_b, s);
+    }
   }
 
   // encoder: Conv(Cin->C)+bias, GELU, Conv(C->C) ; + pos_embed          (sfnonet.py:613-640, :785-786)
@@ -212,7 +270,7 @@ void forward(ace_csfno& n, const float* x, const float* scalar, const float* lab
     CBlockW& w = n.blocks[i];
     const ace_sht_plan& pf = (i == 0) ? *n.outer : *n.inner;
     const ace_sht_plan& pi = (i == NL - 1) ? *n.outer : *n.inner;
-    const bool round_trip = pf.table_id != pi.table_id;  // s2convolutions.py:195-199
+    const bool round_trip = c.filter_residual || pf.table_id != pi.table_id;  // s2convolutions.py:195-199
     bf16* xn = n.xn.as<bf16>();
     run_cln(n, w.n0, hP, P_act, act_b, scalar, labels, B, xn, P_act, act_b, s);
     run_gemm(sht_op_dft_fwd(pf, xn, P_act, act_b, C, B, n.x1.as<bf16>(), P_x1), s);
@@ -287,9 +345,12 @@ void forward(ace_csfno& n, const float* x, const float* scalar, const float* lab
     run_gemm(op, s);
   }
   {
+    const long long out_b = (long long)c.out_chans * HW;
     GemmOp op = conv_op("decoder.2", n.d1.as<bf16>(), P_act, act_b, HW, B, n.dec1, C);
-    out_f32(op, y, (long long)c.out_chans * HW, HW);
+    if (c.filter_output) out_planes(op, n.yP.as<bf16>(), n.p_yP, out_b, HW);
+    else out_f32(op, y, out_b, HW);
     run_gemm(op, s);
+    if (c.filter_output) round_trip_outer(n, n.rt_out, n.yP.as<bf16>(), n.p_yP, out_b, c.out_chans, B, nullptr, 0, 0, y, out_b, s);
   }
 }
 
@@ -440,6 +501,57 @@ extern "C" int ace_csfno_forward(ace_csfno* net, const float* x_dev, const float
   ACE_REQUIRE(noise_dev || c.embed_dim_noise == 0, "ace_csfno_forward: noise must be provided");
   ACE_REQUIRE(pos_dev || c.embed_dim_pos == 0, "ace_csfno_forward: embedding_pos must be provided");
   forward(*net, x_dev, scalar_dev, labels_dev, noise_dev, pos_dev, y_dev, batch, (cudaStream_t)stream);
+  ACE_API_END
+}
+
+// ------------------------------------------------------------------------------------ label conditioning of the wrapper
+// fme/ace/registry/stochastic_sfno.py:152-165: labels -> Linear(n_labels, label_embed_dim); positional context per sample =
+// pos_embed + einsum("bl,lpxy->bpxy", labels, label_pos_embed).  Tiny streaming kernels (a few kB .. MB per step).
+namespace {
+__global__ void small_linear_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int n_in, int n_out,
+                                    long long total, float* __restrict__ y) {
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long b = idx / n_out;
+    const int o = (int)(idx % n_out);
+    float acc = 0.f;
+    for (int i = 0; i < n_in; ++i) acc = fmaf(x[b * n_in + i], w[(long long)o * n_in + i], acc);
+    y[idx] = acc + (bias ? bias[o] : 0.f);
+  }
+}
+__global__ void label_pos_embed_kernel(const float* __restrict__ base, const float* __restrict__ labels, const float* __restrict__ lpe, int n_labels,
+                                       long long phw, long long total, float* __restrict__ out) {
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long b = idx / phw, r = idx % phw;
+    float acc = 0.f;
+    for (int l = 0; l < n_labels; ++l) acc = fmaf(labels[b * n_labels + l], lpe[(long long)l * phw + r], acc);
+    out[idx] = base[r] + acc;
+  }
+}
+}  // namespace
+
+extern "C" int ace_label_embed(const float* labels_dev, const float* weight_dev, const float* bias_dev, int batch, int n_labels, int embed_dim,
+                               float* out_dev, void* stream) {
+  ACE_API_BEGIN
+  ACE_REQUIRE(labels_dev && weight_dev && out_dev && batch > 0 && n_labels > 0 && embed_dim > 0, "ace_label_embed: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long total = (long long)batch * embed_dim;
+  ProfileScope prof("label_embed", s);
+  small_linear_kernel<<<(unsigned)std::min<long long>((total + 127) / 128, 148 * 8), 128, 0, s>>>(labels_dev, weight_dev, bias_dev, n_labels, embed_dim,
+                                                                                             total, out_dev);
+  after_launch("label_embed");
+  ACE_API_END
+}
+
+extern "C" int ace_label_pos_embed(const float* pos_dev, const float* labels_dev, const float* label_pos_dev, int batch, int n_labels, long long phw,
+                                   float* out_dev, void* stream) {
+  ACE_API_BEGIN
+  ACE_REQUIRE(pos_dev && labels_dev && label_pos_dev && out_dev && batch > 0 && n_labels > 0 && phw > 0, "ace_label_pos_embed: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long total = (long long)batch * phw;
+  ProfileScope prof("label_pos_embed", s);
+  label_pos_embed_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, s>>>(pos_dev, labels_dev, label_pos_dev, n_labels,
+                                                                                                 phw, total, out_dev);
+  after_launch("label_pos_embed");
   ACE_API_END
 }
 

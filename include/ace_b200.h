@@ -137,6 +137,9 @@ typedef struct ace_csfno_config {
   int affine_norms;          /* 0/1: elementwise affine of the channel LayerNorms (norm.weight / norm.bias) */
   int embed_dim_scalar, embed_dim_labels, embed_dim_noise, embed_dim_pos; /* ContextConfig (layers.py:33-43) */
   float norm_eps;            /* 1e-5 in the reference */
+  int filter_residual;       /* 0/1: every block's residual and the big skip are SHT round trips (s2convolutions.py:195-199,
+                                sfnonet.py:581-586,775-778) */
+  int filter_output;         /* 0/1: the network output is passed through trans_down -> itrans_up (sfnonet.py:586-591,822) */
 } ace_csfno_config;
 /* plan_outer / plan_inner as for ace_sfno_create (trans_down + itrans_up on the data grid, trans + itrans on Legendre-Gauss). */
 int ace_csfno_create(const ace_csfno_config* cfg, ace_sht_plan* plan_outer, ace_sht_plan* plan_inner, ace_csfno** out);
@@ -156,6 +159,15 @@ int ace_csfno_query(ace_csfno* net, int* in_chans, int* out_chans, long long* hw
  * coeffs_scratch_dev: complex64 [nfields][lmax][mmax]. */
 int ace_isotropic_noise(ace_sht_plan* plan, const float* real_dev, const float* imag_dev, float* coeffs_scratch_dev, float* noise_dev,
                         long long nfields, void* stream);
+/* Label conditioning of NoiseConditionedModel (fme/ace/registry/stochastic_sfno.py:96-103,152-165).
+ * ace_label_embed: out[batch][embed_dim] = labels[batch][n_labels] * weight[embed_dim][n_labels]^T + bias[embed_dim] (bias may be
+ * NULL) -- the learned label embedding, torch.nn.Linear(n_labels, label_embed_dim).
+ * ace_label_pos_embed: out[batch][phw] = pos[phw] + sum_l labels[batch][l] * label_pos[l][phw], phw = embed_dim_pos * H * W -- the
+ * per-sample positional context "pos_embed + einsum('bl,lpxy->bpxy', labels, label_pos_embed)". */
+int ace_label_embed(const float* labels_dev, const float* weight_dev, const float* bias_dev, int batch, int n_labels, int embed_dim,
+                    float* out_dev, void* stream);
+int ace_label_pos_embed(const float* pos_dev, const float* labels_dev, const float* label_pos_dev, int batch, int n_labels, long long phw,
+                        float* out_dev, void* stream);
 
 /* ---- fused step: normalise -> pack -> net -> (residual) -> denormalise -> feed back ----
  * State layout: prognostic/forcing/diagnostic fields as float32 [batch][n][H][W] tensors.

@@ -1,12 +1,13 @@
 """Noise-conditioned SFNO (``NoiseConditionedSFNO``) -- oracle restatement on torch-CPU.  TEST INFRASTRUCTURE.
 
-Restates, for the configuration family the ACE2-ERA5 / stochastic baselines use (filter_type="linear", scale_factor=1,
-no LoRA, no local (DISCO) blocks, no dropout, spectral_ratio=1):
+Restates, for filter_type="linear" and scale_factor=1 (no local (DISCO) blocks, no dropout) -- i.e. the configuration family
+of the ACE2-ERA5 / stochastic baselines plus the grouped, LoRA, global-mean-preserving and spectral_ratio variants:
 
   /root/reference/fme/core/models/conditional_sfno/layers.py:33-95     ContextConfig / Context
   /root/reference/fme/core/models/conditional_sfno/layers.py:95-141    ChannelLayerNorm
   /root/reference/fme/core/models/conditional_sfno/layers.py:143-320   ConditionalLayerNorm
   /root/reference/fme/core/models/conditional_sfno/layers.py:363-415   MLP
+  /root/reference/fme/core/models/conditional_sfno/lora.py:9-141       LoRAConv2d
   /root/reference/fme/core/models/conditional_sfno/s2convolutions.py:118-433  _contract_dhconv, SpectralConvS2
   /root/reference/fme/core/models/conditional_sfno/sfnonet.py:262-436  FourierNeuralOperatorBlock
   /root/reference/fme/core/models/conditional_sfno/sfnonet.py:443-824  get_lat_lon_sfnonet, SphericalFourierNeuralOperatorNet
@@ -113,35 +114,79 @@ class ConditionalLayerNorm(nn.Module):
         return self.norm(x) * scale + bias
 
 
+class LoRAConv2d(nn.Conv2d):
+    """lora.py:9-141 for 1x1, ungrouped, dropout-free convolutions: y = conv(x) + (alpha / r) * up(down(x)).
+
+    Construction order (it fixes the seeded draws): the base Conv2d, ``lora_down``, ``lora_up`` (each with torch's default
+    initialisation), then ``reset_lora_parameters`` re-draws ``lora_down`` (Kaiming) and zeroes ``lora_up``."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=1, stride=1, bias=True, lora_rank=0, lora_alpha=None):
+        super().__init__(in_channels, out_channels, kernel_size, stride, bias=bias)
+        self.lora_rank = int(lora_rank)
+        self.lora_scaling = 0.0
+        if self.lora_rank > 0:
+            self.lora_down = nn.Conv2d(in_channels, self.lora_rank, 1, bias=False)
+            self.lora_up = nn.Conv2d(self.lora_rank, out_channels, kernel_size, stride, bias=False)
+            self.lora_scaling = (float(lora_alpha) if lora_alpha is not None else float(lora_rank)) / float(self.lora_rank)
+            nn.init.kaiming_uniform_(self.lora_down.weight, a=math.sqrt(5))
+            nn.init.zeros_(self.lora_up.weight)
+
+    def forward(self, x):
+        y = super().forward(x)
+        if self.lora_rank == 0:
+            return y
+        return y + self.lora_up(self.lora_down(x)) * self.lora_scaling
+
+
 class MLP(nn.Module):
     """layers.py:363-415 without dropout / checkpointing: fc1 (bias), activation, fc2 (bias)."""
 
-    def __init__(self, in_features, hidden_features, act_layer=nn.GELU):
+    def __init__(self, in_features, hidden_features, act_layer=nn.GELU, lora_rank=0, lora_alpha=None):
         super().__init__()
-        self.fwd = nn.Sequential(nn.Conv2d(in_features, hidden_features, 1, bias=True), act_layer(),
-                                 nn.Conv2d(hidden_features, in_features, 1, bias=True))
+        self.fwd = nn.Sequential(LoRAConv2d(in_features, hidden_features, 1, bias=True, lora_rank=lora_rank, lora_alpha=lora_alpha),
+                                 act_layer(),
+                                 LoRAConv2d(hidden_features, in_features, 1, bias=True, lora_rank=lora_rank, lora_alpha=lora_alpha))
 
     def forward(self, x):
         return self.fwd(x)
 
 
 class SpectralConvS2(nn.Module):
-    """s2convolutions.py:138-433, dense weights [G, L, O/G, I/G, 2]; out[b,g,o,l,m] = sum_i x[b,g,i,l,m] w[g,l,o,i]."""
+    """s2convolutions.py:138-433, dense weights [G, L, O/G, I/G, 2]; out[b,g,o,l,m] = sum_i x[b,g,i,l,m] w[g,l,o,i]
+    (+ the LoRA update B A x, the l = 0 pass-through of ``preserve_global_mean``, the pre / post projections of
+    ``spectral_ratio < 1``)."""
 
     def __init__(self, forward_transform, inverse_transform, channels, num_groups=1, bias=True, filter_residual=False,
-                 preserve_global_mean=False):
+                 preserve_global_mean=False, lora_rank=0, lora_alpha=None, spectral_ratio=1.0):
         super().__init__()
+        if not 0.0 < spectral_ratio <= 1.0:
+            raise ValueError(f"spectral_ratio must be in (0, 1], got {spectral_ratio}.")
+        sc = round(channels * spectral_ratio)  # validate_spectral_ratio (s2convolutions.py:34-91)
+        if spectral_ratio < 1.0 and (sc < 1 or sc % num_groups != 0):
+            raise ValueError(f"spectral_ratio={spectral_ratio} with in_channels={channels} yields {sc} spectral channels")
         assert channels % num_groups == 0
-        self.num_groups = num_groups
+        self.num_groups, self.spectral_channels = num_groups, sc
         self.forward_transform, self.inverse_transform = forward_transform, inverse_transform
         self.modes_lat, self.modes_lon = inverse_transform.lmax, inverse_transform.mmax
         self._round_trip_residual = filter_residual or (
             forward_transform.nlat != inverse_transform.nlat or forward_transform.nlon != inverse_transform.nlon
             or forward_transform.grid != inverse_transform.grid)
         self._preserve_global_mean = preserve_global_mean
-        scale = math.sqrt(1 / channels) * torch.ones(self.modes_lat, 1, 1, 2)
+        if spectral_ratio < 1.0:
+            self.pre_proj = nn.Conv2d(channels, sc, kernel_size=1, bias=False)
+            self.post_proj = nn.Conv2d(sc, channels, kernel_size=1, bias=False)
+        else:
+            self.pre_proj = self.post_proj = None
+        scale = math.sqrt(1 / sc) * torch.ones(self.modes_lat, 1, 1, 2)
         scale[0, :] *= math.sqrt(2.0)
-        self.weight = nn.Parameter(scale * torch.randn(num_groups, self.modes_lat, channels // num_groups, channels // num_groups, 2))
+        self.weight = nn.Parameter(scale * torch.randn(num_groups, self.modes_lat, sc // num_groups, sc // num_groups, 2))
+        self.lora_scaling = 0.0
+        if lora_rank > 0:
+            self.lora_A = nn.Parameter(scale * torch.randn(num_groups, self.modes_lat, lora_rank, sc // num_groups, 2))
+            self.lora_B = nn.Parameter(torch.zeros(num_groups, self.modes_lat, sc // num_groups, lora_rank, 2))
+            self.lora_scaling = (lora_alpha if lora_alpha is not None else lora_rank) / lora_rank
+        else:
+            self.lora_A = self.lora_B = None
         if bias:
             self.bias = nn.Parameter(torch.zeros(1, channels, 1, 1))
         self.register_load_state_dict_pre_hook(self._upgrade_old_weight_layouts)
@@ -162,17 +207,27 @@ class SpectralConvS2(nn.Module):
 
     def forward(self, x):
         residual = x
-        x = self.forward_transform(x.float())
+        x = x.float()
+        if self.pre_proj is not None:
+            x = self.pre_proj(x)
+        x = self.forward_transform(x)
         if self._round_trip_residual:
             residual = self.inverse_transform(x.contiguous())
+            if self.post_proj is not None:
+                residual = self.post_proj(residual)
         B, C, H, W = x.shape
         x = x.reshape(B, self.num_groups, C // self.num_groups, H, W)
+        xs = x[..., : self.modes_lat, : self.modes_lon]
         xp = torch.zeros_like(x)
-        xp[..., : self.modes_lat, : self.modes_lon] = torch.einsum(
-            "bgixy,gxoi->bgoxy", x[..., : self.modes_lat, : self.modes_lon], torch.view_as_complex(self.weight))
+        xp[..., : self.modes_lat, : self.modes_lon] = torch.einsum("bgixy,gxoi->bgoxy", xs, torch.view_as_complex(self.weight))
+        if self.lora_A is not None:
+            tmp = torch.einsum("gxri,bgixy->bgxry", torch.view_as_complex(self.lora_A), xs)
+            xp = xp + self.lora_scaling * torch.einsum("gxor,bgxry->bgoxy", torch.view_as_complex(self.lora_B), tmp)
         if self._preserve_global_mean:
             xp = torch.cat([x[..., :1, :], xp[..., 1:, :]], dim=-2)
         x = self.inverse_transform(xp.reshape(B, C, H, W).contiguous())
+        if self.post_proj is not None:
+            x = self.post_proj(x)
         if hasattr(self, "bias"):
             x = x + self.bias
         return x, residual
@@ -195,16 +250,18 @@ class FourierNeuralOperatorBlock(nn.Module):
 
     def __init__(self, forward_transform, inverse_transform, embed_dim, img_shape, context_config, global_layer_norm=False,
                  mlp_ratio=2.0, act_layer=nn.GELU, use_mlp=True, filter_residual=False, affine_norms=False, filter_num_groups=1,
-                 filter_preserves_global_mean=False):
+                 filter_preserves_global_mean=False, lora_rank=0, lora_alpha=None, spectral_lora_rank=0, spectral_lora_alpha=None,
+                 spectral_ratio=1.0):
         super().__init__()
         self.norm0 = ConditionalLayerNorm(embed_dim, img_shape, context_config, global_layer_norm, elementwise_affine=affine_norms)
         self.filter = _Filter(SpectralConvS2(forward_transform, inverse_transform, embed_dim, num_groups=filter_num_groups, bias=True,
-                                             filter_residual=filter_residual, preserve_global_mean=filter_preserves_global_mean))
-        self.inner_skip = nn.Conv2d(embed_dim, embed_dim, 1, 1)
+                                             filter_residual=filter_residual, preserve_global_mean=filter_preserves_global_mean,
+                                             lora_rank=spectral_lora_rank, lora_alpha=spectral_lora_alpha, spectral_ratio=spectral_ratio))
+        self.inner_skip = LoRAConv2d(embed_dim, embed_dim, 1, 1, lora_rank=lora_rank, lora_alpha=lora_alpha)
         self.act_layer = act_layer()
         self.norm1 = ConditionalLayerNorm(embed_dim, img_shape, context_config, global_layer_norm, elementwise_affine=affine_norms)
         if use_mlp:
-            self.mlp = MLP(embed_dim, int(embed_dim * mlp_ratio), act_layer)
+            self.mlp = MLP(embed_dim, int(embed_dim * mlp_ratio), act_layer, lora_rank, lora_alpha)
         self.outer_skip = nn.Identity()
 
     def forward(self, x, context):
@@ -222,7 +279,8 @@ class SphericalFourierNeuralOperatorNet(nn.Module):
     def __init__(self, img_shape, in_chans, out_chans, context_config=ContextConfig(), embed_dim=256, num_layers=12,
                  global_layer_norm=False, use_mlp=True, mlp_ratio=2.0, activation_function="gelu", encoder_layers=1, pos_embed=True,
                  big_skip=True, filter_residual=False, filter_output=False, normalize_big_skip=False, affine_norms=False,
-                 filter_num_groups=1, filter_preserves_global_mean=False, data_grid="equiangular", hard_thresholding_fraction=1.0):
+                 filter_num_groups=1, filter_preserves_global_mean=False, data_grid="equiangular", hard_thresholding_fraction=1.0,
+                 lora_rank=0, lora_alpha=None, spectral_lora_rank=0, spectral_lora_alpha=None, spectral_ratio=1.0):
         super().__init__()
         h, w = img_shape
         modes_lat, modes_lon = int(h * hard_thresholding_fraction), int((w // 2 + 1) * hard_thresholding_fraction)
@@ -237,16 +295,17 @@ class SphericalFourierNeuralOperatorNet(nn.Module):
         def stack(cin, cout):
             mods, cur = [], cin
             for _ in range(encoder_layers):
-                mods += [nn.Conv2d(cur, embed_dim, 1, bias=True), act_layer()]
+                mods += [LoRAConv2d(cur, embed_dim, 1, bias=True, lora_rank=lora_rank, lora_alpha=lora_alpha), act_layer()]
                 cur = embed_dim
-            mods.append(nn.Conv2d(cur, cout, 1, bias=False))
+            mods.append(LoRAConv2d(cur, cout, 1, bias=False, lora_rank=lora_rank, lora_alpha=lora_alpha))
             return nn.Sequential(*mods)
 
         self.encoder = stack(in_chans, embed_dim)
         self.blocks = nn.ModuleList([
             FourierNeuralOperatorBlock(self.trans_down if i == 0 else self.trans, self.itrans_up if i == num_layers - 1 else self.itrans,
                                        embed_dim, img_shape, context_config, global_layer_norm, mlp_ratio, act_layer, use_mlp,
-                                       filter_residual, affine_norms, filter_num_groups, filter_preserves_global_mean)
+                                       filter_residual, affine_norms, filter_num_groups, filter_preserves_global_mean, lora_rank,
+                                       lora_alpha, spectral_lora_rank, spectral_lora_alpha, spectral_ratio)
             for i in range(num_layers)])
         self.decoder = stack(embed_dim + big_skip * in_chans, out_chans)
         if pos_embed:

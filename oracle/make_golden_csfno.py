@@ -43,9 +43,19 @@ def _reference_setup(r):
     return model, x, ctx
 
 
-def main():
+def main(only=()):
+    """``only``: names of live cases to (re)generate; empty = everything, including the conversions of the stored goldens."""
     r = refload.load_csfno()
     os.makedirs(OUT, exist_ok=True)
+    if only:
+        return _live_cases(r, only)
+    _stored_cases(r)
+    _live_cases(r, only)
+    _noise_case(r)
+    print("wrote csfno goldens to", OUT)
+
+
+def _stored_cases(r):
     # 1. test_sfnonet_output_is_unchanged.pt (test_sfnonet.py:151-159)
     model, x, ctx = _reference_setup(r)
     with torch.no_grad():
@@ -63,31 +73,48 @@ def main():
         y2 = model(x2, r.Context(**ctx2))
     assert torch.allclose(y2, stored2, rtol=1e-5, atol=1e-6), float((y2 - stored2).abs().max())
     np.savez(os.path.join(OUT, "ref_stored_csfno_checkpoint.npz"), **_pack(ck, x2, ctx2, stored2, embed_dim=16, num_layers=2, data_grid="equiangular"))
+
+
+def _live_cases(r, only):
     # 3. live: the ERA5 baseline's option set at toy size (configs/baselines/era5/ace-train-config-1-step-pretrain.yaml:94-108:
     #    noise conditioning only, affine_norms, normalize_big_skip, legendre-gauss data grid), non-trivial conditioning weights
     for name, kw, cc, shape in [
         ("era5like_24x48", dict(embed_dim=32, num_layers=3, affine_norms=True, normalize_big_skip=True), dict(embed_dim_noise=8), (24, 48)),
         ("noaffine_pos_17x32", dict(embed_dim=24, num_layers=2, mlp_ratio=1.5), dict(embed_dim_noise=4, embed_dim_pos=2), (17, 32)),
         ("nonoise_12x24", dict(embed_dim=16, num_layers=2, affine_norms=True, big_skip=False, pos_embed=False), dict(), (12, 24)),
+        # grouped filter + spectral / conv LoRA + bottlenecked spectral width + l = 0 pass-through, every parameter randomised
+        ("grouped_lora_bottleneck_16x32", dict(embed_dim=32, num_layers=2, affine_norms=True, normalize_big_skip=True, filter_num_groups=2,
+                                               spectral_ratio=0.5, spectral_lora_rank=2, spectral_lora_alpha=3.0, lora_rank=2,
+                                               filter_preserves_global_mean=True), dict(embed_dim_noise=6, embed_dim_labels=2), (16, 32)),
+        # SHT round trips of every residual, the big skip and the output, on the equiangular data grid
+        ("filtered_20x40", dict(embed_dim=24, num_layers=2, affine_norms=True, normalize_big_skip=True, filter_num_groups=4,
+                                filter_residual=True, filter_output=True), dict(embed_dim_noise=4, embed_dim_pos=3), (20, 40)),
     ]:
+        if only and name not in only:
+            continue
         torch.manual_seed(7)
         cfg = dict(embed_dim_scalar=0, embed_dim_labels=0, embed_dim_noise=0, embed_dim_pos=0)
         cfg.update(cc)
-        grid = "legendre-gauss" if name.startswith("era5") else "equiangular"
+        grid = "legendre-gauss" if name.startswith(("era5", "grouped")) else "equiangular"
         m = r.get_lat_lon_sfnonet(params=r.SFNONetConfig(filter_type="linear", **kw), img_shape=shape, in_chans=5, out_chans=4,
                                   data_grid=grid, context_config=r.ContextConfig(**cfg))
         with torch.no_grad():
             for k, p in m.named_parameters():  # conditioning and affine parameters start at identity: randomise them
                 if "W_scale" in k or "W_bias" in k or ".norm." in k or k.endswith("filter.filter.bias"):
                     p.add_(0.3 * torch.randn_like(p))
+                elif "lora" in k:  # lora_B / lora_up start at zero
+                    p.add_(0.2 * torch.randn_like(p))
         B = 2
         x = torch.randn(B, 5, *shape)
-        ctx = dict(embedding_scalar=None, labels=None,
+        ctx = dict(embedding_scalar=None, labels=torch.randn(B, cfg["embed_dim_labels"]) if cfg["embed_dim_labels"] else None,
                    noise=torch.randn(B, cfg["embed_dim_noise"], *shape) if cfg["embed_dim_noise"] else None,
                    embedding_pos=torch.randn(B, cfg["embed_dim_pos"], *shape) if cfg["embed_dim_pos"] else None)
         with torch.no_grad():
             y = m(x, r.Context(**ctx))
         np.savez(os.path.join(OUT, f"ref_live_csfno_{name}.npz"), **_pack(m.state_dict(), x, ctx, y, data_grid=grid, **kw))
+
+
+def _noise_case(r):
     # 4. isotropic noise (stochastic_sfno.py:21-47) through the reference's InverseRealSHT, seeded draws stored
     torch.manual_seed(3)
     isht = r.InverseRealSHT(12, 24, lmax=12, mmax=13, grid="legendre-gauss")
@@ -96,8 +123,9 @@ def main():
     torch.set_rng_state(state)
     real, imag = torch.randn(2, 3, 12, 13), torch.randn(2, 3, 12, 13)
     np.savez(os.path.join(OUT, "ref_live_isotropic_noise.npz"), real=_np(real), imag=_np(imag), noise=_np(noise))
-    print("wrote csfno goldens to", OUT)
 
 
 if __name__ == "__main__":
-    main()
+    import sys
+
+    main(tuple(sys.argv[1:]))

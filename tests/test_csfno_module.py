@@ -38,12 +38,69 @@ def test_reference_checkpoints_load(name):
     net = _b200_from_case(kwargs, dims)
     res = net.load_state_dict(state)  # incl. the [G, I, O, L, 2] layout of the stored checkpoint golden
     assert not res.missing_keys and not res.unexpected_keys
-    assert tuple(net.blocks[0].filter.filter.weight.shape) == (1, net.modes_lat, net.embed_dim, net.embed_dim, 2)
+    conv = net.blocks[0].filter.filter
+    cg = conv.spectral_channels // conv.num_groups
+    assert tuple(conv.weight.shape) == (conv.num_groups, net.modes_lat, cg, cg, 2)
+    dense = dict((k, b) for k, _, b in net.device_parameters())["blocks.0.filter.filter.weight"]
+    if dense is not None:  # what the device library receives is always the dense per-degree operator
+        assert tuple(dense().shape) == (1, net.modes_lat, net.embed_dim, net.embed_dim, 2)
+
+
+FOLDED_CASES = [
+    dict(filter_num_groups=4),
+    dict(filter_num_groups=2, filter_preserves_global_mean=True),
+    dict(spectral_lora_rank=3, spectral_lora_alpha=5.0, lora_rank=2),
+    dict(filter_num_groups=2, spectral_ratio=0.5, spectral_lora_rank=2, lora_rank=3, lora_alpha=1.5, filter_preserves_global_mean=True),
+    dict(filter_residual=True, filter_output=True, filter_num_groups=2),
+]
+
+
+@pytest.mark.parametrize("extra", FOLDED_CASES)
+def test_folded_parameters_reproduce_the_adapted_network(extra):
+    """Grouped / LoRA / mean-preserving / bottlenecked layers are handed to the device library as plain dense parameters
+    (csfno.py ``device_parameters``).  The fold is checked here without a GPU: the oracle network WITH the options (bit-identical
+    to the reference, tests/test_oracle_csfno.py) against the oracle network WITHOUT them carrying the folded parameters."""
+    cc = dict(embed_dim_noise=5, embed_dim_pos=2, embed_dim_labels=2)
+    kw = dict(embed_dim=16, num_layers=2, affine_norms=True, normalize_big_skip=True, **extra)
+    torch.manual_seed(11)
+    full = oc.SphericalFourierNeuralOperatorNet((10, 20), 3, 2, oc.ContextConfig(**cc), data_grid="legendre-gauss", **kw).eval()
+    torch.manual_seed(11)
+    mod = bc.get_lat_lon_sfnonet(bc.SFNONetConfig(**kw), 3, 2, (10, 20), "legendre-gauss", bc.ContextConfig(**cc))
+    sm, so = mod.state_dict(), full.state_dict()
+    assert list(sm.keys()) == list(so.keys())
+    for k in so:
+        assert torch.equal(sm[k], so[k]), k  # same construction order -> same seeded draws
+    with torch.no_grad():
+        for prm in full.parameters():
+            prm.add_(0.2 * torch.randn_like(prm))  # lora_B / lora_up start at zero
+    mod.load_state_dict(full.state_dict())
+    plain_kw = {k: v for k, v in kw.items() if k in ("embed_dim", "num_layers", "affine_norms", "normalize_big_skip", "filter_residual", "filter_output")}
+    plain = oc.SphericalFourierNeuralOperatorNet((10, 20), 3, 2, oc.ContextConfig(**cc), data_grid="legendre-gauss", **plain_kw).eval()
+    folded = {}
+    for key, sources, build in mod.device_parameters():
+        folded[key] = sources[0].detach().clone() if build is None else build()
+        assert folded[key].dtype == torch.float32 and folded[key].is_contiguous()
+    assert sorted(folded) == sorted(plain.state_dict())  # exactly the keys the un-adapted network (and the device library) takes
+    plain.load_state_dict(folded)
+    x = torch.randn(2, 3, 10, 20)
+    ctx = dict(labels=torch.randn(2, 2), noise=torch.randn(2, 5, 10, 20), embedding_pos=torch.randn(2, 2, 10, 20))
+    with torch.no_grad():
+        want, got = full(x, oc.Context(**ctx)), plain(x, oc.Context(**ctx))
+    assert float((want - got).abs().max() / want.abs().max()) < 2e-6
+
+
+def test_spectral_ratio_validation_is_the_references():
+    with pytest.raises(ValueError, match="must be in"):
+        bc.get_lat_lon_sfnonet(bc.SFNONetConfig(embed_dim=8, num_layers=1, spectral_ratio=0.0), 2, 2, (8, 16), "legendre-gauss")
+    with pytest.raises(ValueError, match="not divisible"):
+        bc.get_lat_lon_sfnonet(bc.SFNONetConfig(embed_dim=8, num_layers=1, spectral_ratio=0.75, filter_num_groups=4), 2, 2, (8, 16), "legendre-gauss")
+    with pytest.raises(NotImplementedError, match="round-trip"):  # the fold cannot express post_proj(isht(sht(pre_proj(x)))) as a residual
+        bc.get_lat_lon_sfnonet(bc.SFNONetConfig(embed_dim=8, num_layers=1, spectral_ratio=0.5, filter_residual=True), 2, 2, (8, 16), "legendre-gauss")
 
 
 def test_unsupported_options_raise_and_cpu_input_is_rejected():
-    for kw in (dict(filter_num_groups=2), dict(global_layer_norm=True), dict(filter_type="makani-linear"), dict(spectral_ratio=0.5),
-               dict(filter_residual=True), dict(lora_rank=2), dict(activation_function="relu")):
+    for kw in (dict(global_layer_norm=True), dict(filter_type="makani-linear"), dict(clip_latent_global_means=True), dict(local_blocks=[0]),
+               dict(use_mlp=False), dict(activation_function="relu")):
         with pytest.raises(NotImplementedError):
             bc.get_lat_lon_sfnonet(bc.SFNONetConfig(embed_dim=8, num_layers=1, **kw), 2, 2, (8, 16))
     with pytest.raises(NotImplementedError):

@@ -74,6 +74,83 @@ def test_matches_oracle_tcgen05_path(img, embed, noise, pos, grid):
         assert ace_b200.get_option("count_umma") - u0 == 4 + 8 * 2  # encoder 2 + decoder 2 + 8 per block
 
 
+@pytest.mark.parametrize("img,embed,grid,extra", [
+    ((48, 96), 128, "legendre-gauss", dict(filter_num_groups=8)),                                      # the reference's 8-group benchmark option
+    ((48, 96), 64, "legendre-gauss", dict(filter_num_groups=2, filter_preserves_global_mean=True, spectral_lora_rank=4, lora_rank=4)),
+    ((32, 64), 64, "legendre-gauss", dict(spectral_ratio=0.5, filter_num_groups=2, spectral_lora_rank=2)),
+    ((48, 96), 64, "legendre-gauss", dict(filter_residual=True, filter_output=True)),                  # round trips on the tcgen05 path
+    ((45, 96), 64, "equiangular", dict(filter_residual=True, filter_output=True, normalize_big_skip=False)),
+    ((24, 48), 32, "equiangular", dict(filter_residual=True, big_skip=False)),
+])
+def test_folded_and_filtered_options_match_oracle(img, embed, grid, extra):
+    """Options folded into dense parameters on the host (groups, LoRA, l = 0 pass-through, spectral_ratio) and the device-side
+    SHT round trips of filter_residual / filter_output, against the oracle running the reference's own formulation."""
+    from oracle import csfno as oc
+
+    dims = dict(embed_dim_noise=8, embed_dim_labels=3)
+    kw = dict(embed_dim=embed, num_layers=2, affine_norms=True, normalize_big_skip=True)
+    kw.update(extra)
+    onet, net = _oracle_and_b200(img, 7, 6, dims, grid, 13, **kw)
+    with torch.no_grad():
+        for k, p in onet.named_parameters():
+            if "lora" in k:
+                p.add_(0.2 * torch.randn_like(p))
+    net.load_state_dict(onet.state_dict())
+    B = 2
+    x = torch.randn(B, 7, *img)
+    ctx = dict(noise=torch.randn(B, 8, *img), labels=torch.randn(B, 3), embedding_pos=None, embedding_scalar=None)
+    with torch.no_grad():
+        ref = onet(x, oc.Context(**ctx))
+    out = net(x.cuda(), _cuda_ctx(ctx)).cpu()
+    assert field_rel_err(out, ref) < 1e-4, field_rel_err(out, ref)
+    # a LoRA / projection parameter edited in place must reach the device copy of the folded weight
+    names = [k for k, _ in onet.named_parameters() if "lora" in k or "_proj" in k]
+    if names:
+        with torch.no_grad():
+            for k in names:
+                onet.get_parameter(k).mul_(1.5)
+                net.get_parameter(k).mul_(1.5)
+            ref2 = onet(x, oc.Context(**ctx))
+        assert field_rel_err(ref2, ref) > 1e-3  # the edit matters ...
+        assert field_rel_err(net(x.cuda(), _cuda_ctx(ctx)).cpu(), ref2) < 1e-4  # ... and is followed
+
+
+def test_label_embedding_and_label_position_interaction():
+    """NoiseConditionedModel with a learned label embedding and the label-position interaction (stochastic_sfno.py:96-125,152-165):
+    ace_label_embed / ace_label_pos_embed feeding the conditional network, vs the oracle wrapper."""
+    import ace_b200
+    from oracle import csfno as oc
+
+    img, n_labels, led, pos = (24, 48), 3, 5, 4
+    sel = ace_b200.ModuleSelector(type="B200NoiseConditionedSFNO", config=dict(
+        embed_dim=32, num_layers=2, noise_embed_dim=8, context_pos_embed_dim=pos, pos_embed=False, label_embed_dim=led, affine_norms=True))
+    torch.manual_seed(6)
+    model = sel.build(5, 4, ace_b200.DatasetInfo(img_shape=img, all_labels=["a", "b", "c"])).torch_module
+    assert model.label_embedding.weight.shape == (led, n_labels) and model.label_pos_embed.shape == (led, pos, *img)
+    torch.manual_seed(6)
+    onet = oc.SphericalFourierNeuralOperatorNet(img, 5, 4, oc.ContextConfig(embed_dim_noise=8, embed_dim_pos=pos, embed_dim_labels=led), embed_dim=32,
+                                                num_layers=2, affine_norms=True, pos_embed=False, data_grid="legendre-gauss")
+    owrap = oc.NoiseConditionedModel(onet, img, embed_dim_noise=8, embed_dim_pos=pos, n_labels=n_labels, label_embed_dim=led).eval()
+    so, sm = owrap.state_dict(), model.state_dict()
+    assert list(so.keys()) == list(sm.keys())
+    for k in so:
+        assert torch.equal(so[k], sm[k]), k
+    with torch.no_grad():
+        for k, p in owrap.named_parameters():
+            if "W_scale" in k or "W_bias" in k or "label" in k:
+                p.add_(0.3 * torch.randn_like(p))
+    model.load_state_dict(owrap.state_dict())
+    model = model.cuda().eval().requires_grad_(False)
+    B = 3
+    x, noise = torch.randn(B, 5, *img), torch.randn(B, 8, *img)
+    labels = torch.eye(n_labels)[[0, 2, 1]] + 0.1 * torch.randn(B, n_labels)
+    with torch.no_grad():
+        ref = owrap(x, labels=labels, noise=noise)
+        ref_nolabel = owrap(x, labels=torch.zeros(B, n_labels), noise=noise)
+    assert field_rel_err(ref_nolabel, ref) > 1e-3  # the labels matter
+    assert field_rel_err(model(x.cuda(), labels=labels.cuda(), noise=noise.cuda()).cpu(), ref) < 1e-4
+
+
 def test_module_contract_batch_sizes_and_param_refresh():
     from oracle import csfno as oc
 

@@ -56,12 +56,16 @@ def test_noise_conditioned_model_context_wiring():
 
 
 @pytest.mark.skipif(not refload.available(), reason="/root/reference not present (GPU box)")
-@pytest.mark.parametrize("groups,preserve,filter_residual", [(1, False, False), (4, True, False), (1, False, True)])
-def test_oracle_equals_live_reference(groups, preserve, filter_residual):
+@pytest.mark.parametrize("groups,preserve,filter_residual,extra", [
+    (1, False, False, {}), (4, True, False, {}), (1, False, True, {}),
+    (2, False, False, dict(spectral_lora_rank=3, spectral_lora_alpha=5.0, lora_rank=2)),
+    (2, True, True, dict(spectral_ratio=0.5, spectral_lora_rank=2, lora_rank=3, lora_alpha=1.5)),
+])
+def test_oracle_equals_live_reference(groups, preserve, filter_residual, extra):
     r = refload.load_csfno()
     cc = dict(embed_dim_scalar=3, embed_dim_labels=2, embed_dim_noise=5, embed_dim_pos=2)
     kw = dict(embed_dim=16, num_layers=2, affine_norms=True, normalize_big_skip=True, filter_num_groups=groups,
-              filter_preserves_global_mean=preserve, filter_residual=filter_residual, filter_output=filter_residual)
+              filter_preserves_global_mean=preserve, filter_residual=filter_residual, filter_output=filter_residual, **extra)
     torch.manual_seed(5)
     ref = r.get_lat_lon_sfnonet(params=r.SFNONetConfig(filter_type="linear", **kw), img_shape=(10, 20), in_chans=3, out_chans=2,
                                 data_grid="legendre-gauss", context_config=r.ContextConfig(**cc)).eval()

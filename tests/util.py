@@ -59,6 +59,8 @@ CSFNO_GOLDENS = [
     "ref_live_csfno_era5like_24x48.npz",
     "ref_live_csfno_noaffine_pos_17x32.npz",
     "ref_live_csfno_nonoise_12x24.npz",
+    "ref_live_csfno_grouped_lora_bottleneck_16x32.npz",
+    "ref_live_csfno_filtered_20x40.npz",
 ]
 
 
