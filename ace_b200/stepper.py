@@ -36,8 +36,13 @@ class FusedStepper:
         force_positive_names: Sequence[str] = (),
         ocean: Optional[Mapping[str, object]] = None,
         corrector: Optional[Mapping[str, object]] = None,
+        next_step_forcing_names: Sequence[str] = (),
+        prescribed_prognostic_names: Sequence[str] = (),
     ):
-        """``force_positive_names``: outputs clamped to >= 0 after denormalisation (the corrector's ForcePositive,
+        """``next_step_forcing_names`` / ``prescribed_prognostic_names``: ``SingleModuleStepConfig``'s fields of the same names
+        (``fme/core/step/single_module.py:64-66,92-93,103-117``): input-only variables read from the OUTPUT time by ``predict*``,
+        and outputs overwritten from the next-step data after the ocean step (``:709-714``).
+        ``force_positive_names``: outputs clamped to >= 0 after denormalisation (the corrector's ForcePositive,
         ``fme/core/corrector/utils.py:26-43``).  ``ocean``: ``{"surface_temperature_name": ..., "interpolate": False}`` enables
         the prescribed-SST ocean (``fme/core/ocean.py:165-215``): every step then takes ``ocean`` data ``[B, 2, H, W]`` =
         (ocean fraction, target surface temperature) valid at the OUTPUT time.  With ``"slab": {"mixed_layer_depth_name": ...,
@@ -88,6 +93,16 @@ class FusedStepper:
             if n not in self._means or n not in self._stds:
                 raise KeyError(f"normalization statistics missing for '{n}'")
         self.corrector = dict(corrector) if corrector is not None else None
+        self.next_step_forcing_names = list(next_step_forcing_names)
+        for n in self.next_step_forcing_names:
+            if n not in self.in_names:
+                raise ValueError(f"next_step_forcing_name '{n}' not in in_names: {self.in_names}")
+            if n in self.out_names:
+                raise ValueError(f"next_step_forcing_name is an output variable: '{n}'")
+        self.prescribed_prognostic_names = list(prescribed_prognostic_names)
+        for n in self.prescribed_prognostic_names:
+            if n not in self.out_names:
+                raise ValueError(f"prescribed_prognostic_name '{n}' must be in out_names: {self.out_names}")
         self._corrector_handle = None
         self._handle = None
         self._handle_net = None
@@ -208,11 +223,11 @@ class FusedStepper:
     # ------------------------------------------------------------------ one step, packed tensors
     def step_packed(self, prog: torch.Tensor, forcing: Optional[torch.Tensor], out: Optional[torch.Tensor] = None,
                     next_prog: Optional[torch.Tensor] = None, ocean: Optional[torch.Tensor] = None,
-                    corrector_next: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None):
+                    corrector_next: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None,
+                    prescribed: Optional[torch.Tensor] = None):
         """prog [B, n_prog, H, W], forcing [B, n_forcing, H, W] (, ocean [B, 2, H, W]) (, corrector_next [B, 2, H, W] =
-        (DSWRFtoa, HGTsfc) at the output time) -> (out [B, n_out, H, W], next_prog)."""
-        if not prog.is_cuda:
-            raise _lib.AceError("FusedStepper: tensors must be on a CUDA device (there is no CPU path)")
+        (DSWRFtoa, HGTsfc) at the output time) (, prescribed [B, n_prescribed, H, W] = the ``prescribed_prognostic_names`` at the
+        output time) -> (out [B, n_out, H, W], next_prog)."""
         B = prog.shape[0]
         H, W = self.module.img_shape
         prog = prog.float().contiguous()
@@ -232,10 +247,27 @@ class FusedStepper:
             corrector_next = corrector_next.float().contiguous()
             if tuple(corrector_next.shape) != (B, 2, H, W):
                 raise ValueError(f"corrector_next must be [B, 2, H, W], got {tuple(corrector_next.shape)}")
+        if bool(self.prescribed_prognostic_names) != (prescribed is not None):
+            raise ValueError("prescribed data must be given exactly when prescribed_prognostic_names is configured")
+        if prescribed is not None and tuple(prescribed.shape) != (B, len(self.prescribed_prognostic_names), H, W):
+            raise ValueError(f"prescribed must be [B, {len(self.prescribed_prognostic_names)}, H, W], got {tuple(prescribed.shape)}")
         if out is None:
             out = torch.empty(B, len(self.out_names), H, W, device=prog.device, dtype=torch.float32)
         if next_prog is None:
             next_prog = torch.empty(B, len(self.prognostic_names), H, W, device=prog.device, dtype=torch.float32)
+        self._native_step(prog, forcing, ocean, corrector_next, noise, out, next_prog)
+        # prescribed overwrite, last of all (fme/core/step/single_module.py:709-714): device-to-device copies on the same stream
+        for j, n in enumerate(self.prescribed_prognostic_names):
+            out[:, self.out_names.index(n)].copy_(prescribed[:, j])
+            if n in self.prognostic_names:
+                next_prog[:, self.prognostic_names.index(n)].copy_(prescribed[:, j])
+        return out, next_prog
+
+    def _native_step(self, prog, forcing, ocean, corrector_next, noise, out, next_prog):
+        """``ace_stepper_step`` on validated, contiguous fp32 device tensors (the one place the fused step enters the library)."""
+        if not prog.is_cuda:
+            raise _lib.AceError("FusedStepper: tensors must be on a CUDA device (there is no CPU path)")
+        B = prog.shape[0]
         with torch.cuda.device(prog.device):
             self._ensure(prog.device)
             stream = _lib.current_stream_ptr()
@@ -248,7 +280,6 @@ class FusedStepper:
                 ctypes.c_void_p(ocean.data_ptr()) if ocean is not None else None,
                 ctypes.c_void_p(corrector_next.data_ptr()) if corrector_next is not None else None,
                 ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(next_prog.data_ptr()), B, stream))
-        return out, next_prog
 
     # ------------------------------------------------------------------ one step, name dicts (reference API shape)
     def step(self, input: Mapping[str, torch.Tensor], next_step_input_data: Optional[Mapping[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
@@ -270,23 +301,46 @@ class FusedStepper:
 
             nxt = next_step_input_data or {}
             cnext = torch.stack([nxt[n] for n in next_step_names(self.forcing_names)], dim=1)
-        out, _ = self.step_packed(prog, forcing, ocean=ocean, corrector_next=cnext)
+        presc = None
+        if self.prescribed_prognostic_names:
+            nxt = next_step_input_data or {}
+            for n in self.prescribed_prognostic_names:
+                if n not in nxt:
+                    raise ValueError(f"prescribed_prognostic_name '{n}' not in next_step_input_data")
+            presc = torch.stack([nxt[n] for n in self.prescribed_prognostic_names], dim=1).float()
+        out, _ = self.step_packed(prog, forcing, ocean=ocean, corrector_next=cnext, prescribed=presc)
         return {n: out[:, i] for i, n in enumerate(self.out_names)}
 
     # ------------------------------------------------------------------ rollout
     def rollout(self, prog0: torch.Tensor, forcing_seq: Optional[torch.Tensor], n_steps: int, use_cuda_graph: bool = True,
-                keep_outputs: bool = True, ocean_seq: Optional[torch.Tensor] = None):
+                keep_outputs: bool = True, ocean_seq: Optional[torch.Tensor] = None, prescribed_seq: Optional[torch.Tensor] = None,
+                corrector_next_seq: Optional[torch.Tensor] = None):
         """Autoregressive loop (predict_generator).  forcing_seq [n_steps, B, n_forcing, H, W] resident on device
         ([n_steps + 1, ...] with the energy budget correction, which reads DSWRFtoa / HGTsfc of the output time, like the
-        reference's forcing windows of n + 1 times).
+        reference's forcing windows of n + 1 times; ``corrector_next_seq`` [n_steps, B, 2, H, W] overrides that selection).
+        ocean_seq [n_steps, B, n_ocean, H, W] / prescribed_seq [n_steps, B, n_prescribed, H, W]: data of the OUTPUT time of each step.
 
         Returns (outputs [n_steps, B, n_out, H, W] or None, final prognostic state).
         """
         B = prog0.shape[0]
         H, W = self.module.img_shape
+        outs = torch.empty(n_steps, B, len(self.out_names), H, W, device=prog0.device) if keep_outputs else None
+        state = None
+        for t, out, state in self._iter_steps(prog0, forcing_seq, n_steps, use_cuda_graph, ocean_seq, prescribed_seq, corrector_next_seq,
+                                              out_bufs=outs):
+            if outs is not None and out.data_ptr() != outs[t].data_ptr():
+                outs[t].copy_(out, non_blocking=True)
+        if state is None:  # n_steps == 0
+            return outs, prog0.float().contiguous().clone()
+        return outs, state.clone()
+
+    def _iter_steps(self, prog0, forcing_seq, n_steps, use_cuda_graph, ocean_seq, prescribed_seq, corrector_next_seq, out_bufs=None):
+        """Generator behind ``rollout`` / ``predict_generator``: yields ``(t, out, state)`` after every step, where ``out``
+        [B, n_out, H, W] and ``state`` [B, n_prog, H, W] are buffers that the next iteration overwrites (copy what must survive)."""
+        B = prog0.shape[0]
+        H, W = self.module.img_shape
         dev = prog0.device
-        n_out, n_prog = len(self.out_names), len(self.prognostic_names)
-        outs = torch.empty(n_steps, B, n_out, H, W, device=dev) if keep_outputs else None
+        n_out, n_prog, n_presc = len(self.out_names), len(self.prognostic_names), len(self.prescribed_prognostic_names)
         state = prog0.float().contiguous().clone()
         if self.corrector is not None:  # a rollout starts from an initial condition: (re)capture the dry-air reference from it
             with torch.cuda.device(dev):
@@ -294,17 +348,27 @@ class FusedStepper:
                 self.reset_corrector_state()
                 self._seed_corrector(state)
         needs_next = self.corrector_needs_next
-        if needs_next and (forcing_seq is None or forcing_seq.shape[0] < n_steps + 1):
+        if needs_next and corrector_next_seq is None and (forcing_seq is None or forcing_seq.shape[0] < n_steps + 1):
             raise ValueError("the energy budget correction needs forcing at n_steps + 1 times")
+        if n_presc and (prescribed_seq is None or prescribed_seq.shape[0] < n_steps):
+            raise ValueError("prescribed_prognostic_names is configured: prescribed_seq [n_steps, B, n_prescribed, H, W] is required")
+
+        def cnext_at(t):
+            if not needs_next:
+                return None
+            return corrector_next_seq[t] if corrector_next_seq is not None else self.corrector_next_from_forcing(forcing_seq[t + 1])
+
         if not use_cuda_graph:
             out_buf = torch.empty(B, n_out, H, W, device=dev)
             nxt = torch.empty_like(state)
             for t in range(n_steps):
                 f = forcing_seq[t] if forcing_seq is not None else None
-                self.step_packed(state, f, out_buf if outs is None else outs[t], nxt, ocean=ocean_seq[t] if ocean_seq is not None else None,
-                                 corrector_next=self.corrector_next_from_forcing(forcing_seq[t + 1]) if needs_next else None)
+                o = out_buf if out_bufs is None else out_bufs[t]
+                self.step_packed(state, f, o, nxt, ocean=ocean_seq[t] if ocean_seq is not None else None, corrector_next=cnext_at(t),
+                                 prescribed=prescribed_seq[t] if n_presc else None)
                 state, nxt = nxt, state
-            return outs, state
+                yield t, o, state
+            return
         st = self._static
         if self._graph is None or st is None or st["B"] != B or st["prog"].device != dev:
             st = dict(
@@ -313,15 +377,17 @@ class FusedStepper:
                 out=torch.empty(B, n_out, H, W, device=dev), nxt=torch.empty(B, n_prog, H, W, device=dev),
                 ocean=torch.ones(B, self.n_ocean, H, W, device=dev) if self.ocean is not None else None,
                 cnext=torch.zeros(B, 2, H, W, device=dev) if needs_next else None,
+                presc=torch.zeros(B, n_presc, H, W, device=dev) if n_presc else None,
             )
             st["prog"].copy_(state)
             if st["forcing"] is not None:
                 st["forcing"].zero_()
-            self.step_packed(st["prog"], st["forcing"], st["out"], st["nxt"], ocean=st["ocean"], corrector_next=st["cnext"])  # warm-up: allocations, func attributes
+            kw = dict(ocean=st["ocean"], corrector_next=st["cnext"], prescribed=st["presc"])
+            self.step_packed(st["prog"], st["forcing"], st["out"], st["nxt"], **kw)  # warm-up: allocations, func attributes
             torch.cuda.synchronize(dev)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self.step_packed(st["prog"], st["forcing"], st["out"], st["nxt"], ocean=st["ocean"], corrector_next=st["cnext"])
+                self.step_packed(st["prog"], st["forcing"], st["out"], st["nxt"], **kw)
                 st["prog"].copy_(st["nxt"])  # feed back inside the graph
             self._graph, self._static = g, st
         st["prog"].copy_(state)
@@ -331,11 +397,89 @@ class FusedStepper:
             if st["ocean"] is not None:
                 st["ocean"].copy_(ocean_seq[t], non_blocking=True)
             if st["cnext"] is not None:
-                st["cnext"].copy_(self.corrector_next_from_forcing(forcing_seq[t + 1]), non_blocking=True)
+                st["cnext"].copy_(cnext_at(t), non_blocking=True)
+            if st["presc"] is not None:
+                st["presc"].copy_(prescribed_seq[t], non_blocking=True)
             self._graph.replay()
-            if outs is not None:
-                outs[t].copy_(st["out"], non_blocking=True)
-        return outs, st["prog"].clone()
+            yield t, st["out"], st["prog"]
+
+    # ------------------------------------------------------------------ the reference Stepper's prediction API, TensorMapping level
+    TIME_DIM = 1  # fme/ace/stepper/single_module.py: tensors are [n_batch, n_time, n_lat, n_lon]
+
+    @property
+    def next_step_input_names(self) -> List[str]:
+        """fme/core/step/single_module.py:191-199: what ``next_step_input_data`` carries (input-only names, the ocean's forcing
+        names, the prescribed prognostic names)."""
+        names = list(self.forcing_names)
+        if self.ocean is not None:
+            extra = [self.ocean["ocean_fraction_name"]]
+            extra += [self._slab["q_flux_name"], self._slab["mixed_layer_depth_name"]] if self._slab else [self.ocean["surface_temperature_name"]]
+            names += [n for n in extra if n not in names]
+        names += [n for n in self.prescribed_prognostic_names if n not in names]
+        return names
+
+    def _window_tensors(self, forcing_dict: Mapping[str, torch.Tensor], n_forward_steps: int, device):
+        """The per-step device sequences of one forcing window: inputs of step t come from time t (time t + 1 for
+        ``next_step_forcing_names``), ocean / prescribed / corrector data from time t + 1 (single_module.py:1136-1147)."""
+        T = n_forward_steps
+
+        def at(name, shift):
+            v = forcing_dict[name]
+            if v.shape[self.TIME_DIM] < T + 1:
+                raise ValueError(f"forcing '{name}' has {v.shape[self.TIME_DIM]} times, {T + 1} are needed for {T} forward steps")
+            return v[:, shift:shift + T].to(device=device, dtype=torch.float32)
+
+        def seq(names, shift_of):  # -> [T, B, len(names), H, W]
+            return torch.stack([at(n, shift_of(n)) for n in names], dim=2).transpose(0, 1).contiguous()
+
+        fseq = seq(self.forcing_names, lambda n: 1 if n in self.next_step_forcing_names else 0) if self.forcing_names else None
+        oseq = None
+        if self.ocean is not None:
+            frac = self.ocean["ocean_fraction_name"]
+            names = [frac, self._slab["q_flux_name"], self._slab["mixed_layer_depth_name"]] if self._slab else \
+                [frac, self.ocean["surface_temperature_name"]]
+            oseq = seq(names, lambda n: 1)
+        pseq = seq(self.prescribed_prognostic_names, lambda n: 1) if self.prescribed_prognostic_names else None
+        cseq = None
+        if self.corrector_needs_next:
+            from .corrector import next_step_names
+
+            cseq = seq(list(next_step_names(self.forcing_names)), lambda n: 1)
+        return fseq, oseq, pseq, cseq
+
+    def predict_generator(self, ic_dict: Mapping[str, torch.Tensor], forcing_dict: Mapping[str, torch.Tensor], n_forward_steps: int,
+                          use_cuda_graph: bool = True):
+        """``Stepper.predict_generator`` (fme/ace/stepper/single_module.py:1124-1167) on name -> tensor mappings:
+        ``ic_dict[name]`` [B, 1, H, W] for every prognostic name, ``forcing_dict[name]`` [B, n_forward_steps + 1, H, W] for the
+        names in ``next_step_input_names``.  Yields, per step, the dict of all ``out_names`` -> [B, H, W] (fresh tensors); the
+        prognostic subset is fed back as the next state on the device (one CUDA-graph replay per step)."""
+        missing = [n for n in self.prognostic_names if n not in ic_dict]
+        if missing:
+            raise KeyError(f"initial condition lacks prognostic variables {missing}")
+        prog0 = torch.stack([ic_dict[n].squeeze(self.TIME_DIM) for n in self.prognostic_names], dim=1)
+        fseq, oseq, pseq, cseq = self._window_tensors(forcing_dict, n_forward_steps, prog0.device)
+        for _, out, _ in self._iter_steps(prog0, fseq, n_forward_steps, use_cuda_graph, oseq, pseq, cseq):
+            snap = out.clone()
+            yield {n: snap[:, i] for i, n in enumerate(self.out_names)}
+
+    def predict(self, initial_condition: Mapping[str, torch.Tensor], forcing: Mapping[str, torch.Tensor], use_cuda_graph: bool = True):
+        """``Stepper.predict`` (fme/ace/stepper/single_module.py:1169-1262) on name -> tensor mappings, without derived variables:
+        returns ``(data, new_initial_condition)`` with ``data[name]`` [B, n_forward_steps, H, W] for every output name and
+        ``new_initial_condition[name]`` [B, 1, H, W] for every prognostic name (the last predicted time, usable as the next
+        window's initial condition).  ``n_forward_steps`` = forcing times - 1, as in the reference."""
+        names = self.next_step_input_names
+        if not names:
+            raise ValueError("predict: the number of forward steps is taken from the forcing data, which is empty")
+        for n in self.prognostic_names:
+            if initial_condition[n].shape[self.TIME_DIM] != 1:
+                raise ValueError(f"Initial condition must have 1 timesteps, got {initial_condition[n].shape[self.TIME_DIM]}.")
+        n_forward_steps = forcing[names[0]].shape[self.TIME_DIM] - 1
+        prog0 = torch.stack([initial_condition[n].squeeze(self.TIME_DIM) for n in self.prognostic_names], dim=1)
+        fseq, oseq, pseq, cseq = self._window_tensors(forcing, n_forward_steps, prog0.device)
+        outs, final = self.rollout(prog0, fseq, n_forward_steps, use_cuda_graph, True, oseq, pseq, cseq)
+        data = {n: outs[:, :, i].transpose(0, 1) for i, n in enumerate(self.out_names)}
+        new_ic = {n: final[:, i].unsqueeze(self.TIME_DIM) for i, n in enumerate(self.prognostic_names)}
+        return data, new_ic
 
     def _ensure_graph(self, prog0: torch.Tensor):
         """Capture (once per batch size / device) the CUDA graph of one fused step on static buffers."""
@@ -344,23 +488,31 @@ class FusedStepper:
         if self._graph is None or st is None or st["B"] != B or st["prog"].device != prog0.device:
             H, W = self.module.img_shape
             nt = 2 if self.corrector_needs_next else 1
+            n_presc = len(self.prescribed_prognostic_names)
             self.rollout(prog0, torch.zeros(nt, B, len(self.forcing_names), H, W, device=prog0.device) if self.forcing_names else None, 1,
                          use_cuda_graph=True, keep_outputs=False,
-                         ocean_seq=torch.ones(1, B, self.n_ocean, H, W, device=prog0.device) if self.ocean is not None else None)
+                         ocean_seq=torch.ones(1, B, self.n_ocean, H, W, device=prog0.device) if self.ocean is not None else None,
+                         prescribed_seq=torch.zeros(1, B, n_presc, H, W, device=prog0.device) if n_presc else None)
         return self._static, self._graph
 
     def rollout_host(self, prog0: torch.Tensor, forcing_host: Optional[torch.Tensor], n_steps: int,
-                     out_host: Optional[torch.Tensor] = None, ocean_host: Optional[torch.Tensor] = None):
+                     out_host: Optional[torch.Tensor] = None, ocean_host: Optional[torch.Tensor] = None,
+                     prescribed_host: Optional[torch.Tensor] = None):
         """Autoregressive loop with HOST-resident forcing and outputs (the inference driver's situation: forcing windows come
         from the data loader, outputs go to the writers; ``fme/core/generics/inference.py:117-166``).
 
-        forcing_host [>= n_steps (cycled), B, n_forcing, H, W] pinned; out_host [n_steps, B, n_out, H, W] pinned (or None).
+        forcing_host [>= n_steps (cycled), B, n_forcing, H, W] pinned; out_host [n_steps, B, n_out, H, W] pinned (or None);
+        ocean_host / prescribed_host [>= n_steps (cycled), B, n, H, W] pinned: data of each step's OUTPUT time.
         With the energy budget correction the (DSWRFtoa, HGTsfc) pair of the output time is taken from ``forcing_host[(t + 1) % n]``.
         Every step copies its forcing host->device and its outputs device->host; both copies run on side streams and overlap the
         neighbouring steps' compute (double-buffered staging), the step itself is one CUDA-graph replay.
         Returns the final prognostic state (device).  The caller synchronises before reading ``out_host``.
         """
         dev = prog0.device
+        if bool(self.prescribed_prognostic_names) != (prescribed_host is not None):
+            raise ValueError("prescribed_host must be given exactly when prescribed_prognostic_names is configured")
+        if prescribed_host is not None and not self.forcing_names:
+            raise NotImplementedError("rollout_host: prescribed data is staged alongside the forcing; a network without forcing inputs is not handled")
         st, graph = self._ensure_graph(prog0)
         if self.corrector is not None:
             with torch.cuda.device(dev):
@@ -375,6 +527,7 @@ class FusedStepper:
                      fst=[torch.empty_like(st["forcing"]) for _ in range(2)] if st["forcing"] is not None else None,
                      cst=[torch.empty_like(st["ocean"]) for _ in range(2)] if st["ocean"] is not None else None,
                      nst=[torch.empty_like(st["forcing"]) for _ in range(2)] if st["cnext"] is not None else None,
+                     pst=[torch.empty_like(st["presc"]) for _ in range(2)] if st["presc"] is not None else None,
                      ost=[torch.empty_like(st["out"]) for _ in range(2)])
             self._h = h
         ev_in = [torch.cuda.Event() for _ in range(2)]        # forcing staged on device
@@ -394,6 +547,8 @@ class FusedStepper:
                     h["cst"][b].copy_(ocean_host[t % ocean_host.shape[0]], non_blocking=True)
                 if h["nst"] is not None:
                     h["nst"][b].copy_(forcing_host[(t + 1) % nf], non_blocking=True)
+                if h["pst"] is not None:
+                    h["pst"][b].copy_(prescribed_host[t % prescribed_host.shape[0]], non_blocking=True)
                 ev_in[b].record(h["s_in"])
 
         if h["fst"] is not None and n_steps > 0:
@@ -410,6 +565,8 @@ class FusedStepper:
                     st["ocean"].copy_(h["cst"][b], non_blocking=True)
                 if h["nst"] is not None:
                     st["cnext"].copy_(self.corrector_next_from_forcing(h["nst"][b]), non_blocking=True)
+                if h["pst"] is not None:
+                    st["presc"].copy_(h["pst"][b], non_blocking=True)
                 ev_used[b].record(cur)
             graph.replay()
             if out_host is not None:

@@ -142,3 +142,59 @@ def test_force_positive_and_prescribed_ocean_match_reference_semantics():
         torch.testing.assert_close(out_host, og.cpu(), rtol=0, atol=0)
         with pytest.raises(ValueError):
             st.step_packed(prog0, forcing[0])  # ocean configured but no ocean data
+
+
+def test_predict_with_next_step_forcing_and_prescribed_prognostics():
+    """``predict`` / ``predict_generator`` (the reference Stepper's API on name -> tensor mappings) through the C ABI and the CUDA
+    graph: forcing windows, ``next_step_forcing_names`` read from the output time, ``prescribed_prognostic_names`` overwritten
+    after the step; against the reference loop (fme/ace/stepper/single_module.py:1136-1167) on the oracle."""
+    import ace_b200
+
+    img, in_names, out_names, means, stds, onet, st0 = _setup(True)
+    st = ace_b200.FusedStepper(st0.module, in_names, out_names, means, stds, residual_prediction=True,
+                               next_step_forcing_names=["f2"], prescribed_prognostic_names=["b", "d1"])
+    T, B = 3, 2
+    torch.manual_seed(4)
+    ic = {n: torch.randn(B, 1, *img) * stds[n] + means[n] for n in st.prognostic_names}
+    forcing = {n: torch.randn(B, T + 1, *img) * stds[n] + means[n] for n in st.next_step_input_names}
+    assert st.next_step_input_names == ["f1", "f2", "b", "d1"]
+    # reference loop
+    state = {n: ic[n][:, 0] for n in st.prognostic_names}
+    ref = []
+    for t in range(T):
+        full = dict(state)
+        full["f1"], full["f2"] = forcing["f1"][:, t], forcing["f2"][:, t + 1]
+        out = _oracle_step(onet, in_names, out_names, means, stds, True, full)
+        out["b"], out["d1"] = forcing["b"][:, t + 1], forcing["d1"][:, t + 1]
+        ref.append(out)
+        state = {n: out[n] for n in st.prognostic_names}
+    cu = lambda d: {k: v.cuda() for k, v in d.items()}  # noqa: E731
+    data, new_ic = st.predict(cu(ic), cu(forcing))
+    data_e, new_ic_e = st.predict(cu(ic), cu(forcing), use_cuda_graph=False)
+    for n in out_names:
+        assert data[n].shape == (B, T, *img)
+        torch.testing.assert_close(data[n], data_e[n], rtol=0, atol=0)  # graph replay == eager launches
+        for t in range(T):
+            a = ((data[n][:, t].cpu() - means[n]) / stds[n])[:, None]
+            b = ((ref[t][n] - means[n]) / stds[n])[:, None]
+            assert field_rel_err(a, b) < 3e-4 * (t + 1), (n, t)
+    for n in ("b", "d1"):
+        assert torch.equal(data[n].cpu(), forcing[n][:, 1:])
+    for n in st.prognostic_names:
+        torch.testing.assert_close(new_ic[n], data[n][:, -1:], rtol=0, atol=0)
+        torch.testing.assert_close(new_ic[n], new_ic_e[n], rtol=0, atol=0)
+    gen = list(st.predict_generator(cu(ic), cu(forcing), T))
+    for t in range(T):
+        for n in out_names:
+            torch.testing.assert_close(gen[t][n], data[n][:, t], rtol=0, atol=0)
+    # host-pipelined rollout with the same data: prescribed fields staged alongside the forcing
+    prog0 = torch.stack([ic[n][:, 0] for n in st.prognostic_names], dim=1).cuda()
+    fh = torch.stack([forcing["f1"][:, :T], forcing["f2"][:, 1:T + 1]], dim=2).transpose(0, 1).contiguous().pin_memory()
+    ph = torch.stack([forcing["b"][:, 1:], forcing["d1"][:, 1:]], dim=2).transpose(0, 1).contiguous().pin_memory()
+    oh = torch.empty(T, B, len(out_names), *img).pin_memory()
+    fin = st.rollout_host(prog0, fh, T, out_host=oh, prescribed_host=ph)
+    torch.cuda.synchronize()
+    for i, n in enumerate(out_names):
+        torch.testing.assert_close(oh[:, :, i].transpose(0, 1), data[n].cpu(), rtol=0, atol=0)
+    for i, n in enumerate(st.prognostic_names):
+        torch.testing.assert_close(fin[:, i], new_ic[n][:, 0], rtol=0, atol=0)
