@@ -59,7 +59,8 @@ class CsfnoConfig(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in (
         "img_h", "img_w", "in_chans", "out_chans", "embed_dim", "num_layers", "lmax", "mmax", "mlp_hidden", "pos_embed", "big_skip",
         "normalize_big_skip", "affine_norms", "embed_dim_scalar", "embed_dim_labels", "embed_dim_noise", "embed_dim_pos")] + [
-        ("norm_eps", ctypes.c_float), ("filter_residual", ctypes.c_int), ("filter_output", ctypes.c_int)]
+        ("norm_eps", ctypes.c_float), ("filter_residual", ctypes.c_int), ("filter_output", ctypes.c_int),
+        ("clip_latent_global_means", ctypes.c_int)]
 
 
 class CorrectorConfig(ctypes.Structure):

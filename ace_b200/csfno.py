@@ -25,11 +25,13 @@ device library receives (``_sync_params``; exact identities, evaluated in fp64 o
   maps commute with the transforms; the transform then runs at full width, i.e. the option's speed-up is not realised);
 * ``lora_rank`` (``LoRAConv2d``) -> ``W + (alpha / r) W_up W_down``                (lora.py:131-141).
 
-``filter_residual`` / ``filter_output`` (SHT round trips of the residual streams / the output) run on the device.
+``filter_residual`` / ``filter_output`` (SHT round trips of the residual streams / the output) and the eval branch of
+``clip_latent_global_means`` (the latent's per-channel mean clamped into the ``_gm_min`` / ``_gm_max`` envelope buffers of the
+checkpoint, sfnonet.py:792-812; the envelope itself is only updated by training, which this module does not do) run on the device.
 
 Unsupported reference options raise ``NotImplementedError`` at construction (no fallback): ``filter_type`` other than
 ``"linear"``, ``global_layer_norm``, local (DISCO) blocks, ``spectral_ratio < 1`` together with a round-trip residual
-(``filter_residual`` or a non-Gaussian data grid), ``clip_latent_global_means``, ``use_mlp=False``, ``encoder_layers != 1``,
+(``filter_residual`` or a non-Gaussian data grid), ``use_mlp=False``, ``encoder_layers != 1``,
 dropout, activation other than GELU, noise + positional context wider than 64 channels.
 """
 import ctypes
@@ -314,7 +316,7 @@ class SphericalFourierNeuralOperatorNet(nn.Module):
             raise NotImplementedError("scale factor must be 1 as it is not implemented for conditional layer normalization")
         validate_spectral_ratio(p.spectral_ratio, p.embed_dim, p.filter_num_groups, filter_type=p.filter_type,
                                 local_blocks=bool(p.local_blocks))  # SFNONetConfig.__post_init__ (sfnonet.py:139-146)
-        for name, off in (("global_layer_norm", False), ("clip_latent_global_means", False), ("encoder_layers", 1), ("drop_rate", 0.0),
+        for name, off in (("global_layer_norm", False), ("encoder_layers", 1), ("drop_rate", 0.0),
                           ("drop_path_rate", 0.0), ("use_mlp", True)):
             if getattr(p, name) != off:
                 unsupported.append(f"{name}={getattr(p, name)!r}")
@@ -357,6 +359,10 @@ class SphericalFourierNeuralOperatorNet(nn.Module):
             self.pos_embed = None
         if p.normalize_big_skip:
             self.norm_big_skip = _ConditionalLayerNorm(in_chans, context_config, p.affine_norms)
+        self.clip_latent_global_means = bool(p.clip_latent_global_means)
+        if self.clip_latent_global_means:  # sfnonet.py:730-746: the envelope travels in the checkpoint as two buffers
+            self.register_buffer("_gm_min", torch.full((1, C, 1, 1), float("inf")))
+            self.register_buffer("_gm_max", torch.full((1, C, 1, 1), float("-inf")))
         self._net = None
         self._net_device = None
         self._plans = None
@@ -371,7 +377,8 @@ class SphericalFourierNeuralOperatorNet(nn.Module):
             pos_embed=int(self.pos_embed is not None), big_skip=int(bool(self.big_skip)), normalize_big_skip=int(hasattr(self, "norm_big_skip")),
             affine_norms=int(bool(self.affine_norms)), embed_dim_scalar=cc.embed_dim_scalar, embed_dim_labels=cc.embed_dim_labels,
             embed_dim_noise=cc.embed_dim_noise, embed_dim_pos=cc.embed_dim_pos, norm_eps=1e-5,
-            filter_residual=int(self.filter_residual), filter_output=int(self.filter_output))
+            filter_residual=int(self.filter_residual), filter_output=int(self.filter_output),
+            clip_latent_global_means=int(self.clip_latent_global_means))
 
     def _release(self):
         if getattr(self, "_net", None) is not None:
@@ -417,7 +424,11 @@ class SphericalFourierNeuralOperatorNet(nn.Module):
                 continue  # (the reference still creates norm_big_skip without a big skip; it is never used)
             sources, build = derived.get(name, ([prm], None))
             out.append((name, sources, build))
+        out += [(name, [buf], None) for name, buf in self.named_buffers() if name in ("_gm_min", "_gm_max")]
         return out
+
+    def request_latent_global_mean_envelope_reset(self) -> None:
+        """sfnonet.py:754-762: asks the next TRAINING forward to restart the envelope; inference never updates it, so nothing to do."""
 
     def _sync_params(self, stream):
         lib = _lib.load()

@@ -84,6 +84,7 @@ struct ace_csfno {
   RtBuf rt_in, rt_out;  // filter_residual on the big skip (in_chans wide) / filter_output (out_chans wide)
   DevBuf xrt, yP;       // planes [B][in_chans][HW]: filtered input ahead of norm_big_skip; [B][out_chans][HW]: unfiltered output
   long long p_yP = 0;
+  DevBuf gm_min, gm_max, gm_stats;  // clip_latent_global_means: envelope [C] each; per-(sample, channel) {sum, sum of squares} (double)
 };
 
 namespace {
@@ -112,6 +113,30 @@ void declare_params(ace_csfno& n) {
   }
   p["decoder.0.weight"] = p["decoder.0.bias"] = p["decoder.2.weight"] = false;
   if (c.big_skip && c.normalize_big_skip) declare_cln(p, "norm_big_skip.", c);
+  if (c.clip_latent_global_means) p["_gm_min"] = p["_gm_max"] = false;
+}
+
+// clip_latent_global_means, eval branch (sfnonet.py:803-812): x[b][c] += clamp(mean, lo[c], hi[c]) - mean with mean the plain
+// spatial mean of channel c of sample b (from the producing GEMM's row statistics); nothing happens while any hi[] is non-finite.
+// grid (chunks of the plane, B * C); a block whose channel needs no shift returns before touching the plane.
+__global__ void __launch_bounds__(256) clip_latent_means_kernel(const double* __restrict__ stats, const float* __restrict__ lo,
+                                                               const float* __restrict__ hi, int C, long long HW, bf16* __restrict__ x,
+                                                               long long plane, long long x_b) {
+  int ok = 1;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) ok &= isfinite(hi[i]) ? 1 : 0;
+  if (!__syncthreads_and(ok)) return;
+  const int b = blockIdx.y / C, c = blockIdx.y % C;
+  const float mean = (float)(stats[((long long)b * C + c) * 2] / (double)HW);
+  const float shift = fminf(fmaxf(mean, lo[c]), hi[c]) - mean;
+  if (shift == 0.f) return;
+  bf16* p = x + (long long)b * x_b + (long long)c * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
+    const float v = __bfloat162float(p[i]) + __bfloat162float(p[i + plane]) + shift;
+    bf16 h, l;
+    split_bf16(v, h, l);
+    p[i] = h;
+    p[i + plane] = l;
+  }
 }
 
 // returns true if `rest` (the key below the norm's prefix) named one of this norm's parameters
@@ -181,6 +206,7 @@ void ensure_ws(ace_csfno& n, int B) {
     n.yP.ensure(2 * (size_t)n.p_yP * e);
   }
   n.sb0.ensure((size_t)B * std::max(C, c.in_chans) * 2 * sizeof(float));
+  if (c.clip_latent_global_means) n.gm_stats.ensure((size_t)B * C * 2 * sizeof(double));
   n.wsB = B;
 }
 
@@ -263,7 +289,18 @@ void forward(ace_csfno& n, const float* x, const float* scalar, const float* lab
     GemmOp op = conv_op("encoder.2", n.e1.as<bf16>(), P_act, act_b, HW, B, n.enc1, C);
     if (c.pos_embed) add_f32(op, n.pos.as<float>(), 0, HW);
     out_planes(op, hP, P_act, act_b, HW);
+    if (c.clip_latent_global_means) {
+      ACE_CHECK_CUDA(cudaMemsetAsync(n.gm_stats.p, 0, (size_t)B * C * 2 * sizeof(double), s));
+      row_stats(op, n.gm_stats.as<double>(), C);
+    }
     run_gemm(op, s);
+    if (c.clip_latent_global_means) {
+      ACE_REQUIRE((long long)B * C <= 65535, "clip_latent_global_means: batch * embed_dim = %lld exceeds the grid limit 65535", (long long)B * C);
+      ProfileScope prof("clip_latent_means", s);
+      dim3 grid((unsigned)std::min<long long>((HW + 255) / 256, 64), (unsigned)(B * C));
+      clip_latent_means_kernel<<<grid, 256, 0, s>>>(n.gm_stats.as<double>(), n.gm_min.as<float>(), n.gm_max.as<float>(), C, HW, hP, P_act, act_b);
+      after_launch("clip_latent_means");
+    }
   }
 
   for (int i = 0; i < NL; ++i) {
@@ -430,6 +467,9 @@ extern "C" int ace_csfno_set_param(ace_csfno* net, const char* name, const float
   if (nm == "pos_embed") {
     ACE_REQUIRE(numel == (long long)C * n.HW, "pos_embed: expected %lld elements, got %lld", (long long)C * n.HW, numel);
     copy_f32(n.pos, data_dev, numel, s);
+  } else if (nm == "_gm_min" || nm == "_gm_max") {
+    ACE_REQUIRE(numel == C, "%s: expected %d elements, got %lld", name, C, numel);
+    copy_f32(nm == "_gm_min" ? n.gm_min : n.gm_max, data_dev, numel, s);
   } else if (nm == "encoder.0.weight") set_conv_w(n.enc0, data_dev, numel, name, s);
   else if (nm == "encoder.0.bias") set_conv_b(n.enc0, data_dev, numel, name, s);
   else if (nm == "encoder.2.weight") set_conv_w(n.enc1, data_dev, numel, name, s);

@@ -140,6 +140,9 @@ typedef struct ace_csfno_config {
   int filter_residual;       /* 0/1: every block's residual and the big skip are SHT round trips (s2convolutions.py:195-199,
                                 sfnonet.py:581-586,775-778) */
   int filter_output;         /* 0/1: the network output is passed through trans_down -> itrans_up (sfnonet.py:586-591,822) */
+  int clip_latent_global_means; /* 0/1: eval branch of sfnonet.py:792-812 -- the per-channel spatial mean of the post-encoder latent
+                                is clamped into the envelope buffers "_gm_min" / "_gm_max" (set like parameters, [embed_dim] each);
+                                a no-op while any "_gm_max" entry is non-finite (envelope never trained) */
 } ace_csfno_config;
 /* plan_outer / plan_inner as for ace_sfno_create (trans_down + itrans_up on the data grid, trans + itrans on Legendre-Gauss). */
 int ace_csfno_create(const ace_csfno_config* cfg, ace_sht_plan* plan_outer, ace_sht_plan* plan_inner, ace_csfno** out);

@@ -274,13 +274,14 @@ class FourierNeuralOperatorBlock(nn.Module):
 
 
 class SphericalFourierNeuralOperatorNet(nn.Module):
-    """sfnonet.py:496-824 (eval path; ``clip_latent_global_means`` is not restated)."""
+    """sfnonet.py:496-824, eval path (``clip_latent_global_means``: the envelope buffers are only applied, never updated)."""
 
     def __init__(self, img_shape, in_chans, out_chans, context_config=ContextConfig(), embed_dim=256, num_layers=12,
                  global_layer_norm=False, use_mlp=True, mlp_ratio=2.0, activation_function="gelu", encoder_layers=1, pos_embed=True,
                  big_skip=True, filter_residual=False, filter_output=False, normalize_big_skip=False, affine_norms=False,
                  filter_num_groups=1, filter_preserves_global_mean=False, data_grid="equiangular", hard_thresholding_fraction=1.0,
-                 lora_rank=0, lora_alpha=None, spectral_lora_rank=0, spectral_lora_alpha=None, spectral_ratio=1.0):
+                 lora_rank=0, lora_alpha=None, spectral_lora_rank=0, spectral_lora_alpha=None, spectral_ratio=1.0,
+                 clip_latent_global_means=False):
         super().__init__()
         h, w = img_shape
         modes_lat, modes_lon = int(h * hard_thresholding_fraction), int((w // 2 + 1) * hard_thresholding_fraction)
@@ -317,6 +318,10 @@ class SphericalFourierNeuralOperatorNet(nn.Module):
             self.norm_big_skip = ConditionalLayerNorm(in_chans, img_shape, context_config, global_layer_norm, elementwise_affine=affine_norms)
         else:
             self.norm_big_skip = None
+        self._clip_latent_global_means = clip_latent_global_means
+        if clip_latent_global_means:  # sfnonet.py:730-746
+            self.register_buffer("_gm_min", torch.full((1, embed_dim, 1, 1), float("inf")))
+            self.register_buffer("_gm_max", torch.full((1, embed_dim, 1, 1), float("-inf")))
 
     def forward(self, x, context):
         if self.big_skip:
@@ -326,6 +331,9 @@ class SphericalFourierNeuralOperatorNet(nn.Module):
         x = self.encoder(x)
         if self.pos_embed is not None:
             x = x + self.pos_embed
+        if self._clip_latent_global_means and torch.isfinite(self._gm_max).all():  # eval branch of sfnonet.py:792-812
+            global_means = x.mean(dim=(-2, -1), keepdim=True)
+            x = x + (torch.clamp(global_means, min=self._gm_min, max=self._gm_max) - global_means)
         for blk in self.blocks:
             x = blk(x, context)
         if self.big_skip:

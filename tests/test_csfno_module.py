@@ -98,8 +98,23 @@ def test_spectral_ratio_validation_is_the_references():
         bc.get_lat_lon_sfnonet(bc.SFNONetConfig(embed_dim=8, num_layers=1, spectral_ratio=0.5, filter_residual=True), 2, 2, (8, 16), "legendre-gauss")
 
 
+def test_clip_latent_global_means_buffers_follow_the_checkpoint():
+    kw = dict(embed_dim=8, num_layers=1, clip_latent_global_means=True)
+    o = oc.SphericalFourierNeuralOperatorNet((8, 16), 2, 2, data_grid="legendre-gauss", **kw)
+    m = bc.get_lat_lon_sfnonet(bc.SFNONetConfig(**kw), 2, 2, (8, 16), "legendre-gauss")
+    assert list(m.state_dict().keys()) == list(o.state_dict().keys())
+    assert torch.isinf(m._gm_min).all() and torch.isinf(m._gm_max).all()  # fresh envelope: the device kernel stays a no-op
+    with torch.no_grad():
+        o._gm_min.fill_(-0.5)
+        o._gm_max.fill_(0.25)
+    m.load_state_dict(o.state_dict())
+    keys = [k for k, _, _ in m.device_parameters()]
+    assert keys[-2:] == ["_gm_min", "_gm_max"] and float(m._gm_max.max()) == 0.25
+    m.request_latent_global_mean_envelope_reset()  # API of the reference; inference never updates the envelope
+
+
 def test_unsupported_options_raise_and_cpu_input_is_rejected():
-    for kw in (dict(global_layer_norm=True), dict(filter_type="makani-linear"), dict(clip_latent_global_means=True), dict(local_blocks=[0]),
+    for kw in (dict(global_layer_norm=True), dict(filter_type="makani-linear"), dict(local_blocks=[0]),
                dict(use_mlp=False), dict(activation_function="relu")):
         with pytest.raises(NotImplementedError):
             bc.get_lat_lon_sfnonet(bc.SFNONetConfig(embed_dim=8, num_layers=1, **kw), 2, 2, (8, 16))

@@ -115,6 +115,41 @@ def test_folded_and_filtered_options_match_oracle(img, embed, grid, extra):
         assert field_rel_err(net(x.cuda(), _cuda_ctx(ctx)).cpu(), ref2) < 1e-4  # ... and is followed
 
 
+def test_clip_latent_global_means():
+    """Eval branch of sfnonet.py:792-812 on the device (row statistics of encoder.2 + one shift kernel) vs the oracle: no-op with a
+    fresh envelope, per-channel shift once the envelope buffers are finite, ignored again when one entry is not finite."""
+    from oracle import csfno as oc
+
+    img = (48, 96)
+    dims = dict(embed_dim_noise=8)
+    onet, net = _oracle_and_b200(img, 7, 6, dims, "legendre-gauss", 17, embed_dim=64, num_layers=2, affine_norms=True, clip_latent_global_means=True)
+    B = 2
+    x = torch.randn(B, 7, *img)
+    ctx = dict(noise=torch.randn(B, 8, *img), labels=None, embedding_pos=None, embedding_scalar=None)
+
+    def both():
+        with torch.no_grad():
+            ref = onet(x, oc.Context(**ctx))
+        return ref, net(x.cuda(), _cuda_ctx(ctx)).cpu()
+
+    ref0, out0 = both()
+    assert field_rel_err(out0, ref0) < 1e-4
+    with torch.no_grad():
+        lat = onet.encoder(x) + onet.pos_embed
+        m = lat.mean(dim=(-2, -1), keepdim=True)
+        onet._gm_min.copy_(m.amin(0, keepdim=True) + 0.02)  # tighter than the data on the low side, looser on the high side
+        onet._gm_max.copy_(m.amax(0, keepdim=True) + 0.05)
+    net.load_state_dict(onet.state_dict())
+    ref1, out1 = both()
+    assert field_rel_err(ref1, ref0) > 1e-3  # the clip matters ...
+    assert field_rel_err(out1, ref1) < 1e-4  # ... and the device applies the same shift
+    with torch.no_grad():
+        onet._gm_max[0, 3] = float("inf")
+    net.load_state_dict(onet.state_dict())
+    ref2, out2 = both()
+    assert torch.equal(ref2, ref0) and field_rel_err(out2, ref0) < 1e-4
+
+
 def test_label_embedding_and_label_position_interaction():
     """NoiseConditionedModel with a learned label embedding and the label-position interaction (stochastic_sfno.py:96-125,152-165):
     ace_label_embed / ace_label_pos_embed feeding the conditional network, vs the oracle wrapper."""

@@ -85,3 +85,31 @@ def test_oracle_equals_live_reference(groups, preserve, filter_residual, extra):
         yr = ref(x, r.Context(**ctx))
         yo = ora(x, oc.Context(**ctx))
     assert torch.equal(yr, yo)
+
+
+@pytest.mark.skipif(not refload.available(), reason="/root/reference not present (GPU box)")
+def test_clip_latent_global_means_equals_live_reference():
+    """Eval path of ``clip_latent_global_means`` (sfnonet.py:792-812): no-op with the fresh (infinite) envelope, a per-channel
+    shift of the latent once the envelope buffers are finite."""
+    r = refload.load_csfno()
+    kw = dict(embed_dim=16, num_layers=2, clip_latent_global_means=True)
+    torch.manual_seed(8)
+    ref = r.get_lat_lon_sfnonet(params=r.SFNONetConfig(filter_type="linear", **kw), img_shape=(10, 20), in_chans=3, out_chans=2,
+                                data_grid="legendre-gauss",
+                                context_config=r.ContextConfig(embed_dim_scalar=0, embed_dim_labels=0, embed_dim_noise=4, embed_dim_pos=0)).eval()
+    torch.manual_seed(8)
+    ora = oc.SphericalFourierNeuralOperatorNet((10, 20), 3, 2, oc.ContextConfig(embed_dim_noise=4), data_grid="legendre-gauss", **kw).eval()
+    assert list(ref.state_dict().keys()) == list(ora.state_dict().keys())
+    x = torch.randn(2, 3, 10, 20)
+    ctx = dict(embedding_scalar=None, embedding_pos=None, labels=None, noise=torch.randn(2, 4, 10, 20))
+    with torch.no_grad():
+        y_open = ref(x, r.Context(**ctx))
+        assert torch.equal(y_open, ora(x, oc.Context(**ctx)))
+        lat = ref.encoder(x) + ref.pos_embed
+        m = lat.mean(dim=(-2, -1), keepdim=True)
+        ref._gm_min.copy_(m.amin(0, keepdim=True) + 0.01)  # tighter than the data on one side: some channels get shifted
+        ref._gm_max.copy_(m.amax(0, keepdim=True) + 0.02)
+        ora.load_state_dict(ref.state_dict())
+        y_clip = ref(x, r.Context(**ctx))
+        assert not torch.equal(y_clip, y_open)
+        assert torch.equal(y_clip, ora(x, oc.Context(**ctx)))
