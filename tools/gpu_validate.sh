@@ -8,7 +8,7 @@ mkdir -p gpurun_out
 date > gpurun_out/validate_start.txt
 nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv > gpurun_out/gpu.txt 2>&1
 # 1. the whole -m gpu suite, 6 worker processes (the CPU oracle is the slow side of most tests)
-timeout 330 python -m pytest tests -m gpu -q -n 6 -p no:cacheprovider --durations=12 > gpurun_out/tests_gpu.log 2>&1
+timeout 360 python -m pytest tests -m gpu -q -n 6 -p no:cacheprovider --timeout 150 -rf --durations=12 > gpurun_out/tests_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/tests_gpu.log
 tail -5 gpurun_out/tests_gpu.log
 # 2. smoke (what the driver runs)
