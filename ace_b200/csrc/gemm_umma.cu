@@ -272,11 +272,14 @@ __device__ __forceinline__ void epilogue_rowc(const UmmaParams& p, const Tile& t
         s2[(2 * j + 1) * 32 + lane] = (unsigned short)(w >> 16);
       }
       __syncwarp();
+      // all eight shared-memory reads first, then the stores: issued pairwise (as ptxas orders the lo-plane pass when the
+      // loads sit inside the predicated store loop) every STG waits for its own LDS
+      uint2 w[8];
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const uint2 w = s8[(it * 4 + cc) * 8 + pc];
-        if (g_ok && it * 4 + cc < nleft) *reinterpret_cast<uint2*>(g + it * on4 + (pl ? e.out_plane : 0)) = w;
-      }
+      for (int it = 0; it < 8; ++it) w[it] = s8[(it * 4 + cc) * 8 + pc];
+#pragma unroll
+      for (int it = 0; it < 8; ++it)
+        if (g_ok && it * 4 + cc < nleft) *reinterpret_cast<uint2*>(g + it * on4 + (pl ? e.out_plane : 0)) = w[it];
       __syncwarp();
     }
   }

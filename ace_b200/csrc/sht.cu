@@ -26,17 +26,18 @@ void upload_planes(DevBuf& buf, const std::vector<bf16>& hi, const std::vector<b
 }  // namespace
 
 GemmOp sht_op_dft_fwd(const ace_sht_plan& p, const bf16* x, long long x_plane, long long x_batch_stride, int C, int B,
-                      bf16* x1, long long x1_plane) {
+                      bf16* x1, long long x1_plane, int rows_per_channel) {
   GemmOp op = make_gemm_op("sht.dft_fwd");
+  const int Kq = rows_per_channel > 0 ? rows_per_channel : p.K;
   op.bk_hint = 64;  // 128-byte TMA rows of the streaming operand (measured: 113 -> 91 us at 180x360x384)
-  op.M = C * p.K;
+  op.M = C * Kq;
   op.N = 2 * p.M;
   op.K = p.W;
   op.Z2 = B;
   op.A = {x, x_plane, (long long)p.W, 1, 0, x_batch_stride};
   op.B = {p.fdft.as<bf16>(), p.fdft_plane, (long long)p.Wp, 1, 0, 0};
   op.epi.flags = EPI_OUT_PLANES;
-  op.epi.mdiv = p.K;
+  op.epi.mdiv = Kq;
   op.epi.out = x1;
   op.epi.out_plane = x1_plane;
   op.epi.o_z2 = p.x1_elems(C);
@@ -56,7 +57,7 @@ GemmOp sht_op_legendre_fwd(const ace_sht_plan& p, const bf16* x1, long long x1_p
   op.Z1 = p.M;
   op.Z2 = B;
   op.A = {x1, x1_plane, (long long)p.Kp, 1, 2LL * C * p.Kp, p.x1_elems(C)};
-  op.B = {p.wt.as<bf16>(), p.wt_plane, (long long)p.Kp, 1, (long long)p.L * p.Kp, 0};
+  op.B = {p.wt.as<bf16>(), p.wt_plane, (long long)p.Kt, 1, (long long)p.L * p.Kt, 0};
   op.n_lo_z1 = 1;  // P_l^m = 0 for l < m
   op.epi.flags = EPI_OUT_PLANES;
   op.epi.out = c1;
@@ -77,7 +78,7 @@ GemmOp sht_op_legendre_inv(const ace_sht_plan& p, const bf16* c2, long long c2_p
   op.Z1 = p.M;
   op.Z2 = B;
   op.A = {c2, c2_plane, 1, 2LL * C, (long long)p.Lp * 2 * C, p.c2_elems(C)};  // MN-major
-  op.B = {p.pinv.as<bf16>(), p.pinv_plane, (long long)p.Lp, 1, (long long)p.K * p.Lp, 0};
+  op.B = {p.pinv.as<bf16>(), p.pinv_plane, (long long)p.Lt, 1, (long long)p.K * p.Lt, 0};
   op.k_lo_z1 = 1;  // coefficients with l < m are zero
   op.epi.flags = EPI_OUT_PLANES;
   op.epi.out = g;  // row = reim*C + c  ->  g[(2m + reim)][c][k]: affine in the row index
@@ -146,26 +147,32 @@ static void plan_build(ace_sht_plan& p, const double* fwd, const double* inv) {
   const int K = p.K, W = p.W, L = p.L, M = p.M;
   p.table_id = fnv1a(fwd, sizeof(double) * (size_t)M * L * K, 1469598103934665603ull);
   p.table_id = fnv1a(inv, sizeof(double) * (size_t)M * L * K, p.table_id);
+  // K-major rows that TMA fetches in 128-byte boxes (X1 and the forward table along k, the inverse table along l) get a pitch of
+  // whole 128-byte lines; Lp only counts the (zero) pad rows of c2 and stays at the 16-byte granularity
   p.Kp = (int)round_up(K, 8);
   p.Lp = (int)round_up(L, 8);
-  p.Wp = (int)round_up(W, 8);
-  p.K2p = (int)round_up(2 * M, 8);
+  p.Kt = (int)round_up(K, 64);
+  p.Lt = (int)round_up(L, 64);
+  // row pitch of the DFT matrices: whole 128-byte lines, so that every 128-byte TMA box row (BK = 64) is one aligned L2 line
+  // (a pitch of 8 elements leaves most rows straddling two lines: 5 sectors and 2 tag look-ups per box row instead of 4 / 1)
+  p.Wp = (int)round_up(W, 64);
+  p.K2p = (int)round_up(2 * M, 64);
   {
-    std::vector<bf16> hi((size_t)M * L * p.Kp, __float2bfloat16(0.f)), lo(hi.size(), __float2bfloat16(0.f));
+    std::vector<bf16> hi((size_t)M * L * p.Kt, __float2bfloat16(0.f)), lo(hi.size(), __float2bfloat16(0.f));
     for (int m = 0; m < M; ++m)
       for (int l = 0; l < L; ++l)
         for (int k = 0; k < K; ++k) {
-          size_t d = ((size_t)m * L + l) * p.Kp + k;
+          size_t d = ((size_t)m * L + l) * p.Kt + k;
           host_split(fwd[((size_t)m * L + l) * K + k], hi[d], lo[d]);
         }
     upload_planes(p.wt, hi, lo, p.wt_plane);
   }
   {
-    std::vector<bf16> hi((size_t)M * K * p.Lp, __float2bfloat16(0.f)), lo(hi.size(), __float2bfloat16(0.f));
+    std::vector<bf16> hi((size_t)M * K * p.Lt, __float2bfloat16(0.f)), lo(hi.size(), __float2bfloat16(0.f));
     for (int m = 0; m < M; ++m)
       for (int l = 0; l < L; ++l)
         for (int k = 0; k < K; ++k) {
-          size_t d = ((size_t)m * K + k) * p.Lp + l;
+          size_t d = ((size_t)m * K + k) * p.Lt + l;
           host_split(inv[((size_t)m * L + l) * K + k], hi[d], lo[d]);
         }
     upload_planes(p.pinv, hi, lo, p.pinv_plane);

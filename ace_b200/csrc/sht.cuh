@@ -15,10 +15,11 @@
 
 struct ace_sht_plan {
   int K, W, L, M;      // nlat, nlon, lmax, mmax
-  int Kp, Lp, Wp, K2p; // padded strides (multiples of 8 elements = 16 bytes)
+  int Kp, Lp, Wp, K2p; // padded strides (Lp: multiple of 8 elements = 16 bytes; Kp, Wp, K2p: of 64 elements = one 128-byte line)
+  int Kt, Lt;          // row pitches of the forward / inverse Legendre tables (multiples of 64 elements)
   unsigned long long table_id = 0;  // FNV-1a of the two host tables: equal ids <=> same grid/normalisation
-  ace::DevBuf wt;       // planes [M][L][Kp]    P_l^m(cos th_k) w_k
-  ace::DevBuf pinv;     // planes [M][K][Lp]    P_l^m(cos th_k), l contiguous
+  ace::DevBuf wt;       // planes [M][L][Kt]    P_l^m(cos th_k) w_k
+  ace::DevBuf pinv;     // planes [M][K][Lt]    P_l^m(cos th_k), l contiguous
   ace::DevBuf fdft;     // planes [2M][Wp]      forward DFT rows (2pi/W)(cos, -sin)
   ace::DevBuf idft;     // planes [W][K2p]      inverse DFT rows, Hermitian weights folded in
   long long wt_plane, pinv_plane, fdft_plane, idft_plane;
@@ -37,8 +38,11 @@ namespace ace {
 
 // All builders take per-plane element offsets (`*_plane`) and per-sample strides implied by the
 // layouts above with batch B folded as the outermost dimension.
+// rows_per_channel (0 = nlat): the grid-point buffer may carry pad rows after each channel's nlat latitude rows (channel pitch =
+// rows_per_channel * nlon, rows_per_channel <= Kp); pad rows must hold finite values, their transforms land in the pad slots of
+// X1 that the Legendre stage never reads.  With rows_per_channel == Kp the X1 stores of a tile are one contiguous run per column.
 GemmOp sht_op_dft_fwd(const ace_sht_plan& p, const bf16* x, long long x_plane, long long x_batch_stride, int C, int B,
-                      bf16* x1, long long x1_plane);
+                      bf16* x1, long long x1_plane, int rows_per_channel = 0);
 GemmOp sht_op_legendre_fwd(const ace_sht_plan& p, const bf16* x1, long long x1_plane, int C, int B, bf16* c1,
                            long long c1_plane);
 GemmOp sht_op_legendre_inv(const ace_sht_plan& p, const bf16* c2, long long c2_plane, int C, int B, bf16* g,

@@ -5,7 +5,7 @@ import torch
 import ace_b200
 from ace_b200 import _lib
 
-IMG = (180, 360)
+IMG = tuple(int(v) for v in os.environ.get("ACE_PROBE_IMG", "180x360").split("x"))
 def build(embed=384, layers=8, cin=44, cout=50):
     torch.manual_seed(0)
     fields = dict(embed_dim=embed, num_layers=layers, operator_type="dhconv", data_grid="legendre-gauss")
