@@ -49,3 +49,34 @@ def test_library_contains_blackwell_instructions():
     assert "sm_100a" in sass
     for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG"):
         assert mnemonic in sass, mnemonic
+
+
+def test_header_is_plain_c_and_links_from_a_c_host(tmp_path):
+    """The drop-in boundary is a C ABI: include/ace_b200.h must compile as C99 (no C++ / torch types in any signature) and a C
+    host must link against libace_b200.so and reach the error-reporting entry points without a GPU."""
+    import shutil
+    import subprocess
+
+    from ace_b200 import _lib
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        import pytest
+
+        pytest.skip("gcc not available")
+    src = tmp_path / "host.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <string.h>\n#include "ace_b200.h"\n'
+        "int main(void) {\n"
+        "  if (ace_version() < 100) return 1;\n"
+        '  if (ace_set_option("no_such_option", 1) == 0) return 2;\n'
+        '  if (strstr(ace_last_error(), "unknown option") == NULL) return 3;\n'
+        '  printf("%d\\n", ace_version());\n  return 0;\n}\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, str(src)], check=True)
+    exe = tmp_path / "host"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run([gcc, "-std=c99", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-lace_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert int(out.stdout.strip()) >= 100
