@@ -251,7 +251,7 @@ class FourierNeuralOperatorBlock(nn.Module):
     def __init__(self, forward_transform, inverse_transform, embed_dim, img_shape, context_config, global_layer_norm=False,
                  mlp_ratio=2.0, act_layer=nn.GELU, use_mlp=True, filter_residual=False, affine_norms=False, filter_num_groups=1,
                  filter_preserves_global_mean=False, lora_rank=0, lora_alpha=None, spectral_lora_rank=0, spectral_lora_alpha=None,
-                 spectral_ratio=1.0):
+                 spectral_ratio=1.0, outer_skip="identity"):
         super().__init__()
         self.norm0 = ConditionalLayerNorm(embed_dim, img_shape, context_config, global_layer_norm, elementwise_affine=affine_norms)
         self.filter = _Filter(SpectralConvS2(forward_transform, inverse_transform, embed_dim, num_groups=filter_num_groups, bias=True,
@@ -262,7 +262,10 @@ class FourierNeuralOperatorBlock(nn.Module):
         self.norm1 = ConditionalLayerNorm(embed_dim, img_shape, context_config, global_layer_norm, elementwise_affine=affine_norms)
         if use_mlp:
             self.mlp = MLP(embed_dim, int(embed_dim * mlp_ratio), act_layer, lora_rank, lora_alpha)
-        self.outer_skip = nn.Identity()
+        if outer_skip == "identity":  # the network's choice (sfnonet.py:648); the block's own default is None (:283): no outer skip
+            self.outer_skip = nn.Identity()
+        elif outer_skip is not None:
+            raise NotImplementedError(f"outer_skip={outer_skip!r}")
 
     def forward(self, x, context):
         x, residual = self.filter(self.norm0(x, context))
@@ -270,7 +273,9 @@ class FourierNeuralOperatorBlock(nn.Module):
         x = self.norm1(x, context)
         if hasattr(self, "mlp"):
             x = self.mlp(x)
-        return x + self.outer_skip(residual)
+        if hasattr(self, "outer_skip"):
+            x = x + self.outer_skip(residual)
+        return x
 
 
 class SphericalFourierNeuralOperatorNet(nn.Module):

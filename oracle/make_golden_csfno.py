@@ -47,9 +47,12 @@ def main(only=()):
     """``only``: names of live cases to (re)generate; empty = everything, including the conversions of the stored goldens."""
     r = refload.load_csfno()
     os.makedirs(OUT, exist_ok=True)
+    if only == ("blocks",):
+        return _block_cases(r)
     if only:
         return _live_cases(r, only)
     _stored_cases(r)
+    _block_cases(r)
     _live_cases(r, only)
     _noise_case(r)
     print("wrote csfno goldens to", OUT)
@@ -73,6 +76,34 @@ def _stored_cases(r):
         y2 = model(x2, r.Context(**ctx2))
     assert torch.allclose(y2, stored2, rtol=1e-5, atol=1e-6), float((y2 - stored2).abs().max())
     np.savez(os.path.join(OUT, "ref_stored_csfno_checkpoint.npz"), **_pack(ck, x2, ctx2, stored2, embed_dim=16, num_layers=2, data_grid="equiangular"))
+
+
+def _block_cases(r):
+    """fme/core/benchmark/testdata/csfno_block{,_8_groups}-regression.pt: ONE FourierNeuralOperatorBlock (no outer skip, default
+    lobatto transforms, noise + labels + positional conditioning; 1 and 8 filter groups) as
+    fme/core/models/conditional_sfno/benchmark.py:106-121 builds it under fme.core.rand.set_seed(0)
+    (fme/core/benchmark/test_benchmark.py:44-60): numpy seed 1, random seed 2, torch seed 3."""
+    import random
+
+    base = refload.load()
+    for name, groups in (("csfno_block", 1), ("csfno_block_8_groups", 8)):
+        np.random.seed(1)
+        random.seed(2)
+        torch.manual_seed(3)
+        B, C, H, L = 1, 16, 9, 18
+        noise, labels, pos = torch.randn(B, 4, H, L), torch.randn(B, 3), torch.randn(B, 2, H, L)
+        x = torch.randn(B, C, H, L)
+        blk = r.FourierNeuralOperatorBlock(
+            forward_transform=base.RealSHT(nlat=H, nlon=L), inverse_transform=base.InverseRealSHT(nlat=H, nlon=L), img_shape=(H, L),
+            embed_dim=C, filter_type="linear", use_mlp=True, filter_num_groups=groups,
+            context_config=r.ContextConfig(embed_dim_scalar=0, embed_dim_noise=4, embed_dim_labels=3, embed_dim_pos=2))
+        ctx = dict(embedding_scalar=None, embedding_pos=pos, noise=noise, labels=labels)
+        with torch.no_grad():
+            y = blk(x, r.Context(**ctx))
+        stored = torch.load(os.path.join(refload.REFERENCE_ROOT, "fme", "core", "benchmark", "testdata", f"{name}-regression.pt"),
+                            map_location="cpu")["output"]
+        assert torch.allclose(y, stored, rtol=1e-5, atol=1e-6), float((y - stored).abs().max())
+        np.savez(os.path.join(OUT, f"ref_stored_{name}.npz"), **_pack(blk.state_dict(), x, ctx, stored, embed_dim=C, filter_num_groups=groups))
 
 
 def _live_cases(r, only):

@@ -125,3 +125,30 @@ def test_unsupported_options_raise_and_cpu_input_is_rejected():
     net = bc.get_lat_lon_sfnonet(bc.SFNONetConfig(embed_dim=8, num_layers=1), 2, 2, (8, 16)).requires_grad_(False)
     with pytest.raises(ace_b200.AceError):
         net(torch.zeros(1, 2, 8, 16), bc.Context())
+
+
+def test_folded_group_weights_reproduce_the_references_stored_8_group_block_golden():
+    """The dense per-degree operator the device library receives for a grouped filter (``_SpectralConvS2.effective_weight``),
+    loaded into an UNGROUPED oracle block, reproduces the reference's stored 8-group block golden
+    (fme/core/benchmark/testdata/csfno_block_8_groups-regression.pt)."""
+    import os
+
+    import numpy as np
+
+    from oracle.sht import InverseRealSHT, RealSHT
+    from tests.util import GOLDEN_DIR
+
+    d = np.load(os.path.join(GOLDEN_DIR, "ref_stored_csfno_block_8_groups.npz"))
+    state = {k[2:]: torch.from_numpy(d[k]) for k in d.files if k.startswith("p:")}
+    ctx = {k[4:]: torch.from_numpy(d[k]) for k in d.files if k.startswith("ctx:")}
+    holder = bc._SpectralConvS2(16, 8, num_groups=8)
+    holder.load_state_dict({"weight": state["filter.filter.weight"], "bias": state["filter.filter.bias"]})
+    dense = holder.effective_weight()
+    assert tuple(dense.shape) == (1, 8, 16, 16, 2)
+    blk = oc.FourierNeuralOperatorBlock(RealSHT(9, 18), InverseRealSHT(9, 18), 16, (9, 18),
+                                        oc.ContextConfig(embed_dim_noise=4, embed_dim_labels=3, embed_dim_pos=2),
+                                        filter_num_groups=1, outer_skip=None).eval()
+    blk.load_state_dict({**state, "filter.filter.weight": dense})
+    with torch.no_grad():
+        out = blk(torch.from_numpy(d["x"]), oc.Context(**ctx))
+    torch.testing.assert_close(out, torch.from_numpy(d["y"]), rtol=1e-5, atol=2e-6)

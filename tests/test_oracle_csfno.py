@@ -113,3 +113,28 @@ def test_clip_latent_global_means_equals_live_reference():
         y_clip = ref(x, r.Context(**ctx))
         assert not torch.equal(y_clip, y_open)
         assert torch.equal(y_clip, ora(x, oc.Context(**ctx)))
+
+
+@pytest.mark.parametrize("name,groups", [("ref_stored_csfno_block.npz", 1), ("ref_stored_csfno_block_8_groups.npz", 8)])
+def test_oracle_block_reproduces_the_references_stored_block_goldens(name, groups):
+    """fme/core/benchmark/testdata/csfno_block{,_8_groups}-regression.pt (the reference's own regression targets of its
+    conditional-SFNO block benchmarks, fme/core/models/conditional_sfno/benchmark.py): one FourierNeuralOperatorBlock without outer
+    skip on default (lobatto) transforms, conditioned on noise + labels + position, with 1 and with 8 filter groups."""
+    import os
+
+    from oracle.sht import InverseRealSHT, RealSHT
+
+    d = np.load(os.path.join(GOLDEN_DIR, name))
+    state = {k[2:]: torch.from_numpy(d[k]) for k in d.files if k.startswith("p:")}
+    ctx = {k[4:]: torch.from_numpy(d[k]) for k in d.files if k.startswith("ctx:")}
+    x, y = torch.from_numpy(d["x"]), torch.from_numpy(d["y"])
+    assert int(d["meta:filter_num_groups"]) == groups
+    blk = oc.FourierNeuralOperatorBlock(RealSHT(9, 18), InverseRealSHT(9, 18), 16, (9, 18),
+                                        oc.ContextConfig(embed_dim_noise=4, embed_dim_labels=3, embed_dim_pos=2),
+                                        filter_num_groups=groups, outer_skip=None).eval()
+    assert tuple(blk.filter.filter.weight.shape) == (groups, 8, 16 // groups, 16 // groups, 2)  # lobatto: lmax = nlat - 1
+    res = blk.load_state_dict(state)
+    assert not res.missing_keys and not res.unexpected_keys
+    with torch.no_grad():
+        out = blk(x, oc.Context(**ctx))
+    torch.testing.assert_close(out, y, rtol=1e-5, atol=2e-6)
