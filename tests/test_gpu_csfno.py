@@ -120,7 +120,7 @@ def test_clip_latent_global_means():
     fresh envelope, per-channel shift once the envelope buffers are finite, ignored again when one entry is not finite."""
     from oracle import csfno as oc
 
-    img = (48, 96)
+    img = (32, 64)
     dims = dict(embed_dim_noise=8)
     onet, net = _oracle_and_b200(img, 7, 6, dims, "legendre-gauss", 17, embed_dim=64, num_layers=2, affine_norms=True, clip_latent_global_means=True)
     B = 2
