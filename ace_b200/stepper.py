@@ -405,6 +405,7 @@ class FusedStepper:
 
     # ------------------------------------------------------------------ the reference Stepper's prediction API, TensorMapping level
     TIME_DIM = 1  # fme/ace/stepper/single_module.py: tensors are [n_batch, n_time, n_lat, n_lon]
+    n_ic_timesteps = 1  # Stepper.n_ic_timesteps for a single_module step
 
     @property
     def next_step_input_names(self) -> List[str]:
@@ -480,6 +481,14 @@ class FusedStepper:
         data = {n: outs[:, :, i].transpose(0, 1) for i, n in enumerate(self.out_names)}
         new_ic = {n: final[:, i].unsqueeze(self.TIME_DIM) for i, n in enumerate(self.prognostic_names)}
         return data, new_ic
+
+    def predict_paired(self, initial_condition: Mapping[str, torch.Tensor], forcing: Mapping[str, torch.Tensor], use_cuda_graph: bool = True):
+        """``Stepper.predict_paired`` (fme/ace/stepper/single_module.py:1261-1311) on name -> tensor mappings: the prediction paired
+        with the reference ("target / forcing") values of every variable of ``forcing`` at the predicted times, i.e. the time axis
+        without the initial-condition time (``get_forward_data``, :1313-1327).  Returns ``(prediction, reference), new_ic``."""
+        prediction, new_ic = self.predict(initial_condition, forcing, use_cuda_graph)
+        reference = {n: v[:, self.n_ic_timesteps:] for n, v in forcing.items()}
+        return (prediction, reference), new_ic
 
     def _ensure_graph(self, prog0: torch.Tensor):
         """Capture (once per batch size / device) the CUDA graph of one fused step on static buffers."""

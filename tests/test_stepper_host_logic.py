@@ -97,6 +97,9 @@ def test_predict_follows_the_reference_loop(next_step_forcing, prescribed):
         torch.testing.assert_close(new_ic[n][:, 0], ref[-1][n], rtol=1e-6, atol=1e-6)
     for n in prescribed:  # the overwrite is exact
         assert torch.equal(data[n], forcing[n][:, 1:])
+    (pred, reference), new_ic2 = st.predict_paired(ic, forcing, use_cuda_graph=False)
+    assert all(torch.equal(pred[n], data[n]) for n in OUT_NAMES) and all(torch.equal(new_ic2[n], new_ic[n]) for n in new_ic)
+    assert list(reference) == list(forcing) and all(torch.equal(reference[n], forcing[n][:, 1:]) for n in forcing)
     # the generator yields the same steps; a second window continues from the returned state
     gen = list(st.predict_generator(ic, forcing, T, use_cuda_graph=False))
     assert len(gen) == T
