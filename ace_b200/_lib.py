@@ -132,6 +132,8 @@ SIGNATURES = {
     "ace_corrector_seed": (_I, [_VP, _VP, _I, _VP]),
     "ace_corrector_reset": (_I, [_VP]),
     "ace_corrector_is_seeded": (_I, [_VP]),
+    "ace_corrector_get_state": (_I, [_VP, _VP, _I, _VP]),
+    "ace_corrector_set_state": (_I, [_VP, _VP, _I, _VP]),
     "ace_corrector_needs_next": (_I, [_VP]),
     "ace_corrector_apply": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _VP]),
     "ace_stepper_set_corrector": (_I, [_VP, _VP]),

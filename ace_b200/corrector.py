@@ -161,6 +161,22 @@ class AtmosphereCorrector:
     def seeded(self) -> bool:
         return bool(_lib.load().ace_corrector_is_seeded(self._handle))
 
+    def get_state(self, batch: int) -> torch.Tensor:
+        """``CorrectorState.global_dry_air_mass`` (fme/core/corrector/state.py:15-29): the fp64 dry-air target of each sample,
+        shape ``(batch, 1, 1)`` on the host.  Raises ``AceError`` when no reference has been seeded."""
+        import numpy as np
+
+        buf = np.empty(batch, dtype=np.float64)
+        _lib.check(_lib.load().ace_corrector_get_state(self._handle, buf.ctypes.data_as(ctypes.c_void_p), batch, _lib.current_stream_ptr()))
+        return torch.from_numpy(buf).view(batch, 1, 1)
+
+    def set_state(self, global_dry_air_mass: torch.Tensor):
+        """Install a dry-air target carried over from an earlier window; the next step does not re-seed from its input."""
+        import numpy as np
+
+        buf = np.ascontiguousarray(global_dry_air_mass.detach().double().cpu().reshape(-1).numpy())
+        _lib.check(_lib.load().ace_corrector_set_state(self._handle, buf.ctypes.data_as(ctypes.c_void_p), buf.shape[0], _lib.current_stream_ptr()))
+
     def seed(self, prog: torch.Tensor):
         """Capture the global dry-air mass of the initial condition ``prog [B, n_prog, H, W]`` (atmosphere.py:404-427)."""
         self._check(prog, len(self.prognostic_names))

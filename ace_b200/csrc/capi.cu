@@ -82,6 +82,8 @@ extern "C" int ace_set_option(const char* key, int value) {
     options().pdl = value ? 1 : 0;
   } else if (!strcmp(key, "dbg")) {
     options().dbg = value;
+  } else if (!strcmp(key, "dhconv_t")) {
+    options().dhconv_t = value ? 1 : 0;
   } else if (!strcmp(key, "umma_bk")) {
     ACE_REQUIRE(value == 0 || value == 32 || value == 64, "umma_bk must be 0, 32 or 64");
     options().umma_bk = value;
@@ -102,6 +104,7 @@ extern "C" int ace_get_option(const char* key) {
   if (!strcmp(key, "umma_bn")) return options().umma_bn;
   if (!strcmp(key, "pair")) return options().pair;
   if (!strcmp(key, "umma_bk")) return options().umma_bk;
+  if (!strcmp(key, "dhconv_t")) return options().dhconv_t;
   return -1;
 }
 

@@ -92,6 +92,7 @@ struct Options {
   int pdl = 0;       // programmatic dependent launch of the tcgen05 GEMM / prep kernels (prologue overlaps the previous kernel's tail)
   int dbg = 0;       // development switches of the tcgen05 kernel (results are wrong when non-zero)
   int umma_bk = 0;   // K extent per pipeline stage of the ROWC (forward SHT / dhconv) variants: 0 = per-op hint, 32, 64
+  int dhconv_t = 1;  // dhconv orientation: 1 = orders on the rows / output channels on the columns (128 x 128 MMAs, NC epilogue), 0 = weights on the rows
   int umma_bn = 0;   // 0 = choose per op; otherwise force the N tile of the K-major x K-major variants (192 / 256)
 };
 Options& options();

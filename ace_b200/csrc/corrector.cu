@@ -422,6 +422,35 @@ extern "C" int ace_corrector_seed(ace_corrector* c, const float* prog_dev, int b
 
 extern "C" int ace_corrector_is_seeded(ace_corrector* c) { return (c && c->seeded) ? 1 : 0; }
 
+// The reference threads the dry-air target through CorrectorState.global_dry_air_mass (fme/core/corrector/state.py:15-29) from
+// one prediction window to the next; these two calls read / install it (fp64, one value per sample, host memory).
+extern "C" int ace_corrector_get_state(ace_corrector* c, double* target_host, int batch, void* stream) {
+  ACE_API_BEGIN
+  ACE_REQUIRE(c && target_host && batch > 0, "ace_corrector_get_state: bad argument");
+  if (!c->seeded || batch > c->cap_b) throw Error(ACE_ERR_STATE, "ace_corrector_get_state: the corrector holds no state for this batch size");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (c->conserve_dry_air) {
+    ACE_CHECK_CUDA(cudaMemcpyAsync(target_host, c->target.p, (size_t)batch * sizeof(double), cudaMemcpyDeviceToHost, s));
+    ACE_CHECK_CUDA(cudaStreamSynchronize(s));
+  } else {
+    for (int b = 0; b < batch; ++b) target_host[b] = 0.0;
+  }
+  ACE_API_END
+}
+
+extern "C" int ace_corrector_set_state(ace_corrector* c, const double* target_host, int batch, void* stream) {
+  ACE_API_BEGIN
+  ACE_REQUIRE(c && target_host && batch > 0, "ace_corrector_set_state: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  ensure_batch(*c, batch);
+  if (c->conserve_dry_air) {
+    ACE_CHECK_CUDA(cudaMemcpyAsync(c->target.p, target_host, (size_t)batch * sizeof(double), cudaMemcpyHostToDevice, s));
+    ACE_CHECK_CUDA(cudaStreamSynchronize(s));  // target_host may be a temporary of the caller
+  }
+  c->seeded = true;
+  ACE_API_END
+}
+
 extern "C" int ace_corrector_needs_next(ace_corrector* c) { return (c && c->energy_mode) ? 1 : 0; }
 
 extern "C" int ace_corrector_apply(ace_corrector* c, const float* prev_prog_dev, const float* prev_forcing_dev, const float* next_dev,

@@ -318,29 +318,8 @@ void forward(ace_csfno& n, const float* x, const float* scalar, const float* lab
       run_gemm(sht_op_dft_inv_planes(pi, n.g.as<bf16>(), P_g, C, B, n.rr.as<bf16>(), P_act, act_b), s);
       resid = n.rr.as<bf16>();
     }
-    {
-      // complex GEMM per degree l: D[o][m] = sum_i W[l][o][i] * c1[l][m][i]   (s2convolutions.py:118-136)
-      GemmOp op = make_gemm_op("dhconv");
-      const int Cp = (int)round_up(C, 8);
-      op.cplx = 1;
-      op.M = C;
-      op.N = pf.M;
-      op.K = C;
-      op.Z1 = pf.L;
-      op.Z2 = B;
-      op.a_part = (long long)C * Cp;
-      op.A = {w.spec.as<bf16>(), w.spec_plane, (long long)Cp, 1, 2LL * C * Cp, 0};
-      op.B = {n.c1.as<bf16>(), P_c1, 2LL * C, 1, (long long)pf.M * 2 * C, pf.c1_elems(C)};
-      op.n_hi_z1 = 1;  // order m <= degree l
-      op.epi.flags = EPI_OUT_PLANES;
-      op.epi.out = n.c2.as<bf16>();
-      op.epi.out_plane = P_c2;
-      op.epi.o_z2 = pf.c2_elems(C);
-      op.epi.o_n = (long long)pf.Lp * 2 * C;
-      op.epi.o_z1 = 2LL * C;
-      op.epi.o_m0 = 1;
-      run_gemm(op, s);
-    }
+    // complex GEMM per degree l over the orders m <= l (s2convolutions.py:118-136)
+    run_gemm(dhconv_op(n.c1.as<bf16>(), P_c1, w.spec.as<bf16>(), w.spec_plane, pf, C, C, B, n.c2.as<bf16>(), P_c2), s);
     run_gemm(sht_op_legendre_inv(pi, n.c2.as<bf16>(), P_c2, C, B, n.g.as<bf16>(), P_g), s);
     run_gemm(sht_op_dft_inv(pi, n.g.as<bf16>(), P_g, C, B, n.T.as<float>(), act_b), s);
     // x = GELU(filter(xn) + b_filter + inner_skip(residual))   (sfnonet.py:387-399)

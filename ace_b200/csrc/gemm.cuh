@@ -15,6 +15,7 @@
 //   n_lo_z1: n_lo = z1      (forward Legendre: only degrees l >= m are non-zero)
 //   n_hi_z1: n_hi = z1 + 1  (dhconv at degree l: only orders m <= l are non-zero)
 //   k_lo_z1: k_lo = z1      (inverse Legendre: sum over l >= m)
+//   m_hi_z1: m_hi = z1 + 1  (dhconv at degree l with the orders on the rows)
 // Buffers written under these restrictions are zero-initialised once and the
 // excluded region only ever receives exact zeros, so tile-granular kernels may
 // read or write the excluded part freely.
@@ -74,12 +75,17 @@ struct GemmOp {
   int Z1, Z2;
   Operand A, B;
   int n_lo_z1, n_hi_z1, k_lo_z1;
+  int m_hi_z1;  // rows m > z1 are excluded (dhconv with the modes on the rows: only orders m <= degree l exist)
   // Complex mode (dhconv): A holds two real matrices Ar, Ai of M x K each (Ai = A + a_part elements), B holds
   // [Br | Bi] along its k axis (K + K columns), and the op computes the 2M x N real result
   //   D[0:M]  = Ar Br - Ai Bi,   D[M:2M] = Ai Br + Ar Bi        (rows M..2M-1 are stored at row index m + M)
   // i.e. exactly the real-ified GEMM with A' = [[Ar, -Ai], [Ai, Ar]] without materialising A'.
+  // cplx == 2 is the same complex product with the operand roles exchanged (columns contiguous in the output):
+  //   A holds [Ar | Ai] along its k axis (K + K columns), B holds two real matrices Br, Bi of N x K each (Bi = B + b_part
+  //   elements), and the op computes the M x 2N real result   D[:, 0:N] = Ar Br - Ai Bi,   D[:, N:2N] = Ar Bi + Ai Br
+  //   (column n of the imaginary part is stored at column index n + N).
   int cplx;
-  long long a_part;
+  long long a_part, b_part;
   int bk_hint;  // 0 = kernel default (32); 64 = K extent per pipeline stage for K-major x K-major ops whose A streams from HBM
   EpiParams epi;
   const char* name;  // for error messages / profiling

@@ -20,7 +20,8 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const __grid_constant__ G
   const int n_lo = op.n_lo_z1 ? z1 : 0;
   const int n_hi = op.n_hi_z1 ? min(op.N, z1 + 1) : op.N;
   const int k_lo = op.k_lo_z1 ? z1 : 0;
-  if (n0 >= n_hi || n0 + BN <= n_lo) return;
+  const int m_hi = op.m_hi_z1 ? min(op.M, z1 + 1) : op.M;
+  if (n0 >= n_hi || n0 + BN <= n_lo || m0 >= m_hi) return;
 
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
@@ -48,7 +49,8 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const __grid_constant__ G
       int m = m0 + mm, k = k0 + kk;
       float v = 0.f;
       if (m < op.M && k < op.K && k >= k_lo) {
-        if (!op.cplx) {
+        if (op.cplx != 1) {
+          // (cplx == 2: A is [Ar | Ai] along k, i.e. a plain matrix of the doubled K extent)
           const bf16* p = A + (long long)m * op.A.s_row + (long long)k * op.A.s_k;
           v = __bfloat162float(p[0]) + __bfloat162float(p[op.A.plane]);
         } else {
@@ -70,8 +72,17 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const __grid_constant__ G
       int n = n0 + nn, k = k0 + kk;
       float v = 0.f;
       if (n < op.N && k < op.K && k >= k_lo) {
-        const bf16* p = B + (long long)n * op.B.s_row + (long long)k * op.B.s_k;
-        v = __bfloat162float(p[0]) + __bfloat162float(p[op.B.plane]);
+        if (op.cplx != 2) {
+          const bf16* p = B + (long long)n * op.B.s_row + (long long)k * op.B.s_k;
+          v = __bfloat162float(p[0]) + __bfloat162float(p[op.B.plane]);
+        } else {
+          // op.N / op.K are the real-ified extents (run_gemm_simt doubled them): B'[(ro,o)][(ri,i)] = [[Br, -Bi], [Bi, Br]]
+          const int Nh = op.N >> 1, Kh = op.K >> 1;
+          const int ro = n >= Nh, o = n - ro * Nh, ri = k >= Kh, i2 = k - ri * Kh;
+          const bf16* p = B + (ro != ri ? op.b_part : 0) + (long long)o * op.B.s_row + (long long)i2 * op.B.s_k;
+          v = __bfloat162float(p[0]) + __bfloat162float(p[op.B.plane]);
+          if (ro == 0 && ri == 1) v = -v;
+        }
       }
       Bs[kk][nn] = v;
     }
@@ -95,7 +106,7 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const __grid_constant__ G
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     int m = m0 + ty * TM + i;
-    if (m >= op.M) continue;
+    if (m >= m_hi) continue;
     int m1 = m / e.mdiv, mr = m % e.mdiv;
     float rsum = 0.f, rsq = 0.f;
 #pragma unroll
@@ -121,7 +132,14 @@ void run_gemm_simt(const GemmOp& op_in, cudaStream_t stream) {
   GemmOp op = op_in;
   if (op.cplx) {  // the SIMT kernel walks the real-ified problem
     ACE_REQUIRE(!op.k_lo_z1, "gemm %s: complex mode with a triangular K range is not supported", op.name);
-    op.M *= 2;
+    ACE_REQUIRE(op.cplx == 1 || op.cplx == 2, "gemm %s: bad complex mode %d", op.name, op.cplx);
+    if (op.cplx == 1) {
+      ACE_REQUIRE(!op.m_hi_z1, "gemm %s: complex mode 1 takes no triangular M range", op.name);
+      op.M *= 2;
+    } else {
+      ACE_REQUIRE(!op.n_lo_z1 && !op.n_hi_z1, "gemm %s: complex mode 2 takes no triangular N range", op.name);
+      op.N *= 2;
+    }
     op.K *= 2;
   }
   ACE_REQUIRE(op.M > 0 && op.N > 0 && op.K > 0 && op.Z1 > 0 && op.Z2 > 0, "gemm %s: empty problem", op.name);

@@ -59,6 +59,9 @@ template <int BN_, bool A_MN_, bool B_MN_, uint32_t EF_, bool NC_, int BK_ = 32,
 struct Cfg {
   static constexpr int BM = 128, BN = BN_, BK = BK_;
   static constexpr bool A_MN = A_MN_, B_MN = B_MN_, NC = NC_, CPLX = CPLX_;
+  // complex mode with the NC epilogue = GemmOp::cplx == 2: [Ar | Ai] along the k axis of A, {Br, Bi} as two matrices, the
+  // imaginary accumulator lands N columns further (dhconv with the orders m on the rows and the output channels on the columns)
+  static constexpr bool CT = CPLX_ && NC_;
   // PAIR: two CTAs of a cluster compute one 256 x BN tile with tcgen05.mma.cta_group::2 -- each CTA stages its own 128
   // rows of A and HALF of the B tile (the tensor cores read the other half from the peer), which cuts the shared-memory
   // and L2->SM operand traffic per SM by a third for a 256-wide tile
@@ -78,7 +81,8 @@ struct Cfg {
   static constexpr int STAGES = STAGES_RAW > MAX_STAGES ? MAX_STAGES : STAGES_RAW;
   static constexpr int TMEM_COLS = (2 * NACC * BN <= 256) ? 256 : 512;
   static_assert(2 * NACC * BN <= 512, "TMEM budget");
-  static_assert(!CPLX || (!A_MN && !B_MN && !NC), "complex mode: K-major operands, ROWC epilogue");
+  static_assert(!CPLX || (!A_MN && !B_MN), "complex mode: K-major operands");
+  static_assert(!CT || EF_ == EPI_OUT_PLANES, "complex mode with the NC epilogue: plain split-plane output");
   static_assert(!PAIR || (!CPLX && BNL % 64 == 0), "pair mode");
   static constexpr int SMEM_BYTES = STAGES * STAGE + STG_BYTES + BAR_BYTES + 1024;  // + alignment slack
   static_assert(BN % 64 == 0 && BN <= 256, "BN");
@@ -120,6 +124,7 @@ __device__ __forceinline__ bool decode_tile(const UmmaParams& p, long long t, Ti
   ti.n_count = ti.n_end - ti.n_begin;
   ti.k_begin = (k_lo / BK) * BK;
   ti.num_kc = (op.K - ti.k_begin + BK - 1) / BK;
+  if (op.m_hi_z1 && ti.m0 > ti.z1) return false;  // all rows of the tile are orders m > degree z1
   return ti.n_count > 0 && ti.n_end > n_lo && ti.num_kc > 0;
 }
 
@@ -456,8 +461,9 @@ __device__ __forceinline__ void epilogue_nc(const UmmaParams& p, const Tile& ti,
   uint2* s8 = reinterpret_cast<uint2*>(stg_raw);
   const int row0 = ti.m0 + 32 * q;  // first row of this warp
   const int row = row0 + lane;
-  const bool row_ok = row < op.M;
-  const int rows_valid = op.M - row0;  // >= 32 for full tiles
+  const int m_hi = op.m_hi_z1 ? min(op.M, ti.z1 + 1) : op.M;
+  const bool row_ok = row < m_hi;
+  const int rows_valid = m_hi - row0;  // >= 32 for full tiles
   const bool do_stats = (e.flags & EPI_ROW_STATS) != 0;
   float rbias = 0.f;
   if ((e.flags & EPI_ROW_BIAS) && row_ok) rbias = __ldg(e.row_bias + (long long)ti.z2 * e.rb_z2 + row);
@@ -480,12 +486,17 @@ __device__ __forceinline__ void epilogue_nc(const UmmaParams& p, const Tile& ti,
   if (EF & EPI_OUT_PLANES)
     g_pl = e.out + (long long)ti.z1 * e.o_z1 + (long long)ti.z2 * e.o_z2 + (long long)(row0 + pr) * e.o_m0 + ti.n_begin + pp * 4;
 
-  for (int c = sub; c * 32 < ti.n_count; c += kEpiWarps / 4) {
+  const int nch = (ti.n_count + 31) >> 5;
+  for (int cc2 = sub; cc2 < C::NACC * nch; cc2 += kEpiWarps / 4) {
+    // complex mode: the second accumulator (imaginary part) sits BN TMEM columns further and lands op.N columns further
+    const int part = (C::NACC == 2 && cc2 >= nch) ? 1 : 0;
+    const int c = cc2 - part * nch;
+    if (rows_valid <= 0) break;  // (triangular M range) nothing of this warp's rows exists
     const int nvalid = min(32, ti.n_count - c * 32);  // multiple of 4 (host-checked) unless scalar_store
     float v[32];
-    ptx::tmem_ld_32x32(tacc + c * 32, v);
+    ptx::tmem_ld_32x32(tacc + part * C::BN + c * 32, v);
     ptx::tmem_ld_wait();
-    const int co = c * 32;
+    const int co = c * 32 + part * op.N;
     if (nvalid == 32 && rows_valid >= 32 && !p.scalar_store)
       epilogue_nc_chunk<C, true>(e, v, nvalid, rows_valid, lane, s16, s8, g_add + co, g_res + co, g_f32 + co, g_pl + co, rbias,
                                  res_a, res_s, do_stats, ssum, ssq, false);
@@ -617,8 +628,13 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
               for (int part = 0; part < 2; ++part)
 #pragma unroll
                 for (int pl = 0; pl < 2; ++pl) {
-                  ptx::tma_load_5d(sA + (2 * part + pl) * C::A_PLANE, &p.tmA, fb, k0, ti.m0, az1, part, pl);
-                  ptx::tma_load_5d(sBc + (2 * part + pl) * C::B_PLANE, &p.tmB, fb, k0 + part * op.K, ti.n_begin, bz1, bz2, pl);
+                  if constexpr (C::CT) {
+                    ptx::tma_load_5d(sA + (2 * part + pl) * C::A_PLANE, &p.tmA, fb, k0 + part * op.K, ti.m0, az1, az2, pl);
+                    ptx::tma_load_5d(sBc + (2 * part + pl) * C::B_PLANE, &p.tmB, fb, k0, ti.n_begin, bz1, part, pl);
+                  } else {
+                    ptx::tma_load_5d(sA + (2 * part + pl) * C::A_PLANE, &p.tmA, fb, k0, ti.m0, az1, part, pl);
+                    ptx::tma_load_5d(sBc + (2 * part + pl) * C::B_PLANE, &p.tmB, fb, k0 + part * op.K, ti.n_begin, bz1, bz2, pl);
+                  }
                 }
             } else
 #pragma unroll
@@ -847,9 +863,15 @@ void launch(const GemmOp& op, cudaStream_t stream) {
   p.scalar_store = t_scalar_store;
   // the operand that is re-read by neighbouring tiles should be the small one: keep the big streaming operand's
   // tile shared by consecutive CTAs (they run concurrently, so the second reader hits L2)
-  p.m_fastest = C::B_MN ? 1 : 0;
+  p.m_fastest = (C::B_MN || C::CT) ? 1 : 0;
   const CUtensorMapSwizzle kswz = (C::BK == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-  if (C::CPLX) {
+  if (C::CT) {
+    // [Ar | Ai] along k: one map over 2K columns; {Br, Bi}: the part index rides on the z2 axis of the B map
+    make_tmap(&p.tmA, op.A, false, op.M, 2LL * op.K, op.Z1, op.Z2, C::BK, 128, kswz, &p.a_z1_on, &p.a_z2_on, op.name);
+    Operand b = op.B;
+    b.s_z2 = op.b_part;
+    make_tmap(&p.tmB, b, false, op.N, op.K, op.Z1, 2, C::BK, C::BN, kswz, &p.b_z1_on, &p.b_z2_on, op.name);
+  } else if (C::CPLX) {
     Operand a = op.A;
     a.s_z2 = op.a_part;  // the {real, imaginary} matrix index rides on the z2 axis of the map
     make_tmap(&p.tmA, a, false, op.M, op.K, op.Z1, 2, C::BK, 128, kswz, &p.a_z1_on, &p.a_z2_on, op.name);
@@ -918,8 +940,23 @@ bool classify(const GemmOp& op, Variant& v, const char** why) {
   if (op.A.plane <= 0 || op.B.plane <= 0) return fail("plane offset must be positive");
   const EpiParams& e = op.epi;
   const uint32_t f = e.flags;
-  if (op.cplx && (!a_k || !b_k || !aligned8(op.a_part) || op.k_lo_z1 || (op.K & 7)))
+  if (op.cplx && (!a_k || !b_k || !aligned8(op.a_part) || !aligned8(op.b_part) || op.k_lo_z1 || (op.K & 7)))
     return fail("complex mode needs K-major operands, 16B-aligned parts and K % 8 == 0");
+  if (op.cplx == 2) {
+    // roles exchanged: NC epilogue, plain split-plane output with the imaginary part N columns further
+    if ((f & ~(uint32_t)EPI_OUT_PLANES) != 0 || !(f & EPI_OUT_PLANES)) return fail("complex mode 2 takes the plain split-plane output only");
+    if (op.n_lo_z1 || op.n_hi_z1) return fail("complex mode 2 takes no triangular N range");
+    if (e.mdiv < op.M) return fail("complex mode 2 needs affine rows");
+    if (e.o_n != 1 || !aligned4(op.N) || !aligned4(e.o_m0) || !aligned4(e.o_z1) || !aligned4(e.o_z2) || !aligned4(e.out_plane) || (((uintptr_t)e.out) & 7))
+      return fail("complex mode 2: plane output not 8B-vectorisable");
+    if (op.B.s_z2 != 0) return fail("complex mode 2: B must not vary along z2 (the axis carries the {re, im} index)");
+    v.a_mn = v.b_mn = false;
+    v.nc = true;
+    v.scalar = false;
+    v.ef = EPI_OUT_PLANES;
+    return true;
+  }
+  if (op.m_hi_z1) return fail("a triangular M range is only compiled for complex mode 2");
   v.a_mn = a_mn;
   v.b_mn = b_mn;
   v.ef = f & EF_MASK;
@@ -1062,6 +1099,10 @@ bool dispatch(const GemmOp& op, bool dry, cudaStream_t s, const char** why) {
     for (uint32_t x : ok) found |= (x == v.ef);
     if (!v.nc || !found) { if (why) *why = "epilogue combination not compiled for MN-major B"; return false; }
     if (!dry) launch_conv(op, v, s);
+    return true;
+  }
+  if (op.cplx == 2) {
+    if (!dry) launch<Cfg<128, false, false, P, true, 32, true>>(op, s);
     return true;
   }
   if (op.cplx) {

@@ -88,6 +88,47 @@ inline void add_f32(GemmOp& op, const float* add, long long batch_stride, long l
   op.epi.add_m0 = HW;
   op.epi.add_n = 1;
 }
+// dhconv (contractions.py:184-195): per degree l a complex GEMM  c2[m][l][o] = sum_i c1[l][m][i] * W[l][o][i]  over the orders
+// m <= l.  Weights: planes [L][2 (re, im)][Cout][Cinp]; c1: [B][L][M][2 Cin]; c2: [B][M][Lp][2 Cout].
+//   option dhconv_t = 1 (default): orders on the accumulator rows, output channels on the columns (GemmOp::cplx == 2) -- every
+//     MMA is 128 x 128, the output is stored along its contiguous (re/im, channel) axis (NC epilogue);
+//   option dhconv_t = 0: weights on the accumulator rows, the l + 1 orders on the columns (cplx == 1, ROWC epilogue).
+inline GemmOp dhconv_op(const bf16* c1, long long c1_plane, const bf16* w, long long w_plane, const ace_sht_plan& p, int Cin, int Cout,
+                        int B, bf16* c2, long long c2_plane) {
+  GemmOp op = make_gemm_op("dhconv");
+  const int Cp = (int)round_up(Cin, 8);
+  op.K = Cin;
+  op.Z1 = p.L;
+  op.Z2 = B;
+  op.epi.flags = EPI_OUT_PLANES;
+  op.epi.out = c2;
+  op.epi.out_plane = c2_plane;
+  op.epi.o_z2 = (long long)p.M * p.Lp * 2 * Cout;
+  op.epi.o_z1 = 2LL * Cout;
+  if (options().dhconv_t && Cin % 8 == 0) {
+    op.cplx = 2;
+    op.M = p.M;
+    op.N = Cout;
+    op.m_hi_z1 = 1;  // order m <= degree l
+    op.A = {c1, c1_plane, 2LL * Cin, 1, (long long)p.M * 2 * Cin, (long long)p.L * p.M * 2 * Cin};
+    op.B = {w, w_plane, (long long)Cp, 1, 2LL * Cout * Cp, 0};
+    op.b_part = (long long)Cout * Cp;
+    op.epi.o_m0 = (long long)p.Lp * 2 * Cout;
+    op.epi.o_n = 1;
+  } else {
+    op.cplx = 1;
+    op.M = Cout;
+    op.N = p.M;
+    op.a_part = (long long)Cout * Cp;
+    op.A = {w, w_plane, (long long)Cp, 1, 2LL * Cout * Cp, 0};
+    op.B = {c1, c1_plane, 2LL * Cin, 1, (long long)p.M * 2 * Cin, (long long)p.L * p.M * 2 * Cin};
+    op.n_hi_z1 = 1;  // order m <= degree l
+    op.epi.o_n = (long long)p.Lp * 2 * Cout;
+    op.epi.o_m0 = 1;
+  }
+  return op;
+}
+
 inline void row_stats(GemmOp& op, double* stats, int C) {
   op.epi.flags |= EPI_ROW_STATS;
   op.epi.stats = stats;

@@ -195,26 +195,7 @@ void forward(ace_sfno& n, const float* x, float* y, int B, cudaStream_t s) {
     }
     if (c.operator_type == 1) {
       // complex GEMM per degree l: D[(ro,o)][m] = sum_i W[l][o][i] (complex) * c1[l][m][i] (complex)  (contractions.py:184-195)
-      GemmOp op = make_gemm_op("dhconv");
-      const int Cp = (int)round_up(C, 8);
-      op.cplx = 1;
-      op.M = C;
-      op.N = pf.M;
-      op.K = C;
-      op.Z1 = pf.L;
-      op.Z2 = B;
-      op.a_part = (long long)C * Cp;
-      op.A = {w.spec.as<bf16>(), w.spec_plane, (long long)Cp, 1, 2LL * C * Cp, 0};
-      op.B = {n.c1.as<bf16>(), P_c1, 2LL * C, 1, (long long)pf.M * 2 * C, pf.c1_elems(C)};
-      op.n_hi_z1 = 1;  // order m <= degree l
-      op.epi.flags = EPI_OUT_PLANES;
-      op.epi.out = n.c2.as<bf16>();
-      op.epi.out_plane = P_c2;
-      op.epi.o_z2 = pf.c2_elems(C);
-      op.epi.o_n = (long long)pf.Lp * 2 * C;
-      op.epi.o_z1 = 2LL * C;
-      op.epi.o_m0 = 1;
-      run_gemm(op, s);
+      run_gemm(dhconv_op(n.c1.as<bf16>(), P_c1, w.spec.as<bf16>(), w.spec_plane, pf, C, C, B, n.c2.as<bf16>(), P_c2), s);
     } else {
       launch_diagonal_contract(n.c1.as<bf16>(), P_c1, w.spec.as<float>(), B, C, pf.L, pf.M, pf.Lp, n.c2.as<bf16>(), P_c2, s);
     }

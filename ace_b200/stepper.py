@@ -24,6 +24,13 @@ from . import _lib
 from .sfno import SphericalFourierNeuralOperatorNet
 
 
+class PrognosticDict(dict):
+    """name -> [B, 1, H, W] of the prognostic variables plus the terminal ``stepper_state`` of the window that produced it
+    (the reference's ``PrognosticState`` carries it the same way, fme/ace/stepper/single_module.py:507-521)."""
+
+    stepper_state = None
+
+
 class FusedStepper:
     def __init__(
         self,
@@ -188,19 +195,61 @@ class FusedStepper:
         (``fme/ace/registry/stochastic_sfno.py:128-146``), or ``noise`` when the caller injects it (parity tests)."""
         w = self._wrapper
         H, Wd = self.module.img_shape
+        pkey = None if w.pos_embed is None else (w.pos_embed.data_ptr(), w.pos_embed._version)
+        if self._ctx is not None and self._ctx["B"] == B and self._ctx["device"] == device:
+            self._refresh_pos()
         if self._ctx is None or self._ctx["B"] != B or self._ctx["device"] != device:
             nz = torch.empty(B, w.embed_dim, H, Wd, device=device) if w.embed_dim > 0 else None
             pos = w.pos_embed.detach().float().expand(B, -1, -1, -1).contiguous() if w.pos_embed is not None else None
-            self._ctx = dict(B=B, device=device, noise=nz, pos=pos)
+            self._ctx = dict(B=B, device=device, noise=nz, pos=pos, pkey=pkey)
             _lib.check(_lib.load().ace_stepper_set_context(
                 self._handle, ctypes.c_void_p(nz.data_ptr()) if nz is not None else None, ctypes.c_void_p(pos.data_ptr()) if pos is not None else None))
         if self._ctx["noise"] is not None:
             self._ctx["noise"].copy_(noise if noise is not None else w.draw_noise(B, device))
 
+    def _refresh_pos(self):
+        """pos_embed edited / reloaded since it was cached: refresh the copy IN PLACE (a captured graph reads this buffer)."""
+        w, c = self._wrapper, self._ctx
+        if w is None or c is None or w.pos_embed is None:
+            return
+        pkey = (w.pos_embed.data_ptr(), w.pos_embed._version)
+        if c["pkey"] != pkey:
+            c["pos"].copy_(w.pos_embed.detach().float().expand(c["B"], -1, -1, -1))
+            c["pkey"] = pkey
+
     def reset_corrector_state(self):
         """Forget the dry-air reference: the next step's input state is treated as the initial condition of a new rollout."""
         if self._corrector_handle is not None:
             _lib.check(_lib.load().ace_corrector_reset(self._corrector_handle))
+
+    def get_stepper_state(self, batch: int):
+        """The per-sample state the reference threads from one ``predict`` window to the next (``StepperState.corrector_state``,
+        fme/core/stepper_state.py; ``CorrectorState.global_dry_air_mass``, fme/core/corrector/state.py:15-29) as a plain dict
+        ``{"corrector_state": {"global_dry_air_mass": fp64 [batch, 1, 1]}}``, or None when there is no corrector / nothing seeded."""
+        if self._corrector_handle is None or not _lib.load().ace_corrector_is_seeded(self._corrector_handle):
+            return None
+        return {"corrector_state": {"global_dry_air_mass": self._corrector_obj.get_state(batch)}}
+
+    def _begin_window(self, state: torch.Tensor, stepper_state):
+        """Start of a rollout / prediction window (fme/core/corrector/atmosphere.py:404-427): with ``stepper_state`` carrying a
+        dry-air target the corrector keeps it (the mass stays pinned to the very first initial condition, as the reference's
+        ``predict -> prognostic_state -> next initial condition`` chain does); otherwise the target is seeded from ``state``."""
+        if self.corrector is None:
+            return
+        with torch.cuda.device(state.device):
+            self._ensure(state.device)
+            gm = None
+            if stepper_state is not None:
+                cs = stepper_state.get("corrector_state") if isinstance(stepper_state, Mapping) else getattr(stepper_state, "corrector_state", None)
+                if cs is not None:
+                    gm = cs.get("global_dry_air_mass") if isinstance(cs, Mapping) else getattr(cs, "global_dry_air_mass", None)
+            if gm is not None:
+                if gm.numel() != state.shape[0]:
+                    raise ValueError(f"stepper_state carries {gm.numel()} samples, the state has {state.shape[0]}")
+                self._corrector_obj.set_state(gm)
+            else:
+                self.reset_corrector_state()
+                self._seed_corrector(state)
 
     def _seed_corrector(self, prog: torch.Tensor):
         if self._corrector_handle is not None and not _lib.load().ace_corrector_is_seeded(self._corrector_handle):
@@ -251,10 +300,21 @@ class FusedStepper:
             raise ValueError("prescribed data must be given exactly when prescribed_prognostic_names is configured")
         if prescribed is not None and tuple(prescribed.shape) != (B, len(self.prescribed_prognostic_names), H, W):
             raise ValueError(f"prescribed must be [B, {len(self.prescribed_prognostic_names)}, H, W], got {tuple(prescribed.shape)}")
+        if prescribed is not None:
+            prescribed = prescribed.to(device=prog.device, dtype=torch.float32)
         if out is None:
             out = torch.empty(B, len(self.out_names), H, W, device=prog.device, dtype=torch.float32)
         if next_prog is None:
             next_prog = torch.empty(B, len(self.prognostic_names), H, W, device=prog.device, dtype=torch.float32)
+        # the library receives raw pointers: a view, a half / double buffer or another device would be silent corruption
+        for nm, t, c in (("prog", prog, len(self.prognostic_names)), ("forcing", forcing, len(self.forcing_names)),
+                         ("out", out, len(self.out_names)), ("next_prog", next_prog, len(self.prognostic_names)),
+                         ("ocean", ocean, self.n_ocean), ("corrector_next", corrector_next, 2)):
+            if t is None:
+                continue
+            if t.device != prog.device or t.dtype != torch.float32 or not t.is_contiguous() or tuple(t.shape) != (B, c, H, W):
+                raise ValueError(f"FusedStepper.step_packed: `{nm}` must be a contiguous fp32 tensor [{B}, {c}, {H}, {W}] on {prog.device}, "
+                                 f"got {t.dtype} {tuple(t.shape)} on {t.device}{'' if t.is_contiguous() else ' (non-contiguous)'}")
         self._native_step(prog, forcing, ocean, corrector_next, noise, out, next_prog)
         # prescribed overwrite, last of all (fme/core/step/single_module.py:709-714): device-to-device copies on the same stream
         for j, n in enumerate(self.prescribed_prognostic_names):
@@ -281,10 +341,25 @@ class FusedStepper:
                 ctypes.c_void_p(corrector_next.data_ptr()) if corrector_next is not None else None,
                 ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(next_prog.data_ptr()), B, stream))
 
+    def _sync_before_replay(self, device):
+        """A graph replay never passes through ``_native_step``: push edited / reloaded parameters (``load_state_dict``,
+        in-place updates; version-counter tracked by the module) to the device buffers the captured kernels read, OUTSIDE
+        capture.  The uploads reuse the same device buffers, so the captured graph stays valid; a rebuilt native net
+        (``_ensure`` drops the graph) is re-captured by the caller."""
+        with torch.cuda.device(device):
+            self._ensure(device)
+            self.module._sync_params(_lib.current_stream_ptr())
+            self._refresh_pos()
+
     # ------------------------------------------------------------------ one step, name dicts (reference API shape)
-    def step(self, input: Mapping[str, torch.Tensor], next_step_input_data: Optional[Mapping[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
-        """``input``: every name in ``in_names`` -> [B, H, W] (denormalised).  Returns every ``out_names`` entry."""
+    def step(self, input: Mapping[str, torch.Tensor], next_step_input_data: Optional[Mapping[str, torch.Tensor]] = None,
+             stepper_state=None) -> Dict[str, torch.Tensor]:
+        """``input``: every name in ``in_names`` -> [B, H, W] (denormalised).  Returns every ``out_names`` entry.
+        Like the reference's ``step`` (fme/core/step/single_module.py:670-690) the corrector's dry-air target comes from
+        ``stepper_state`` when given and is seeded from THIS call's input otherwise; the updated state is
+        ``get_stepper_state(B)`` afterwards."""
         prog = torch.stack([input[n] for n in self.prognostic_names], dim=1)
+        self._begin_window(prog.float().contiguous(), stepper_state)
         forcing = torch.stack([input[n] for n in self.forcing_names], dim=1) if self.forcing_names else None
         ocean = None
         if self.ocean is not None:
@@ -314,11 +389,14 @@ class FusedStepper:
     # ------------------------------------------------------------------ rollout
     def rollout(self, prog0: torch.Tensor, forcing_seq: Optional[torch.Tensor], n_steps: int, use_cuda_graph: bool = True,
                 keep_outputs: bool = True, ocean_seq: Optional[torch.Tensor] = None, prescribed_seq: Optional[torch.Tensor] = None,
-                corrector_next_seq: Optional[torch.Tensor] = None):
+                corrector_next_seq: Optional[torch.Tensor] = None, stepper_state=None):
         """Autoregressive loop (predict_generator).  forcing_seq [n_steps, B, n_forcing, H, W] resident on device
         ([n_steps + 1, ...] with the energy budget correction, which reads DSWRFtoa / HGTsfc of the output time, like the
         reference's forcing windows of n + 1 times; ``corrector_next_seq`` [n_steps, B, 2, H, W] overrides that selection).
         ocean_seq [n_steps, B, n_ocean, H, W] / prescribed_seq [n_steps, B, n_prescribed, H, W]: data of the OUTPUT time of each step.
+
+        ``stepper_state``: what ``get_stepper_state`` returned after the previous window (the dry-air target stays pinned to the
+        first initial condition across windows, fme/ace/stepper/single_module.py:1160-1165); None = ``prog0`` is a new initial condition.
 
         Returns (outputs [n_steps, B, n_out, H, W] or None, final prognostic state).
         """
@@ -327,14 +405,15 @@ class FusedStepper:
         outs = torch.empty(n_steps, B, len(self.out_names), H, W, device=prog0.device) if keep_outputs else None
         state = None
         for t, out, state in self._iter_steps(prog0, forcing_seq, n_steps, use_cuda_graph, ocean_seq, prescribed_seq, corrector_next_seq,
-                                              out_bufs=outs):
+                                              out_bufs=outs, stepper_state=stepper_state):
             if outs is not None and out.data_ptr() != outs[t].data_ptr():
                 outs[t].copy_(out, non_blocking=True)
         if state is None:  # n_steps == 0
             return outs, prog0.float().contiguous().clone()
         return outs, state.clone()
 
-    def _iter_steps(self, prog0, forcing_seq, n_steps, use_cuda_graph, ocean_seq, prescribed_seq, corrector_next_seq, out_bufs=None):
+    def _iter_steps(self, prog0, forcing_seq, n_steps, use_cuda_graph, ocean_seq, prescribed_seq, corrector_next_seq, out_bufs=None,
+                    stepper_state=None):
         """Generator behind ``rollout`` / ``predict_generator``: yields ``(t, out, state)`` after every step, where ``out``
         [B, n_out, H, W] and ``state`` [B, n_prog, H, W] are buffers that the next iteration overwrites (copy what must survive)."""
         B = prog0.shape[0]
@@ -342,11 +421,8 @@ class FusedStepper:
         dev = prog0.device
         n_out, n_prog, n_presc = len(self.out_names), len(self.prognostic_names), len(self.prescribed_prognostic_names)
         state = prog0.float().contiguous().clone()
-        if self.corrector is not None:  # a rollout starts from an initial condition: (re)capture the dry-air reference from it
-            with torch.cuda.device(dev):
-                self._ensure(dev)
-                self.reset_corrector_state()
-                self._seed_corrector(state)
+        # a rollout starts from an initial condition (capture the dry-air reference from it) or continues a carried state
+        self._begin_window(state, stepper_state)
         needs_next = self.corrector_needs_next
         if needs_next and corrector_next_seq is None and (forcing_seq is None or forcing_seq.shape[0] < n_steps + 1):
             raise ValueError("the energy budget correction needs forcing at n_steps + 1 times")
@@ -369,6 +445,7 @@ class FusedStepper:
                 state, nxt = nxt, state
                 yield t, o, state
             return
+        self._sync_before_replay(dev)
         st = self._static
         if self._graph is None or st is None or st["B"] != B or st["prog"].device != dev:
             st = dict(
@@ -449,7 +526,7 @@ class FusedStepper:
         return fseq, oseq, pseq, cseq
 
     def predict_generator(self, ic_dict: Mapping[str, torch.Tensor], forcing_dict: Mapping[str, torch.Tensor], n_forward_steps: int,
-                          use_cuda_graph: bool = True):
+                          use_cuda_graph: bool = True, stepper_state=None):
         """``Stepper.predict_generator`` (fme/ace/stepper/single_module.py:1124-1167) on name -> tensor mappings:
         ``ic_dict[name]`` [B, 1, H, W] for every prognostic name, ``forcing_dict[name]`` [B, n_forward_steps + 1, H, W] for the
         names in ``next_step_input_names``.  Yields, per step, the dict of all ``out_names`` -> [B, H, W] (fresh tensors); the
@@ -459,15 +536,19 @@ class FusedStepper:
             raise KeyError(f"initial condition lacks prognostic variables {missing}")
         prog0 = torch.stack([ic_dict[n].squeeze(self.TIME_DIM) for n in self.prognostic_names], dim=1)
         fseq, oseq, pseq, cseq = self._window_tensors(forcing_dict, n_forward_steps, prog0.device)
-        for _, out, _ in self._iter_steps(prog0, fseq, n_forward_steps, use_cuda_graph, oseq, pseq, cseq):
+        for _, out, _ in self._iter_steps(prog0, fseq, n_forward_steps, use_cuda_graph, oseq, pseq, cseq, stepper_state=stepper_state):
             snap = out.clone()
             yield {n: snap[:, i] for i, n in enumerate(self.out_names)}
 
-    def predict(self, initial_condition: Mapping[str, torch.Tensor], forcing: Mapping[str, torch.Tensor], use_cuda_graph: bool = True):
+    def predict(self, initial_condition: Mapping[str, torch.Tensor], forcing: Mapping[str, torch.Tensor], use_cuda_graph: bool = True,
+                stepper_state=None):
         """``Stepper.predict`` (fme/ace/stepper/single_module.py:1169-1262) on name -> tensor mappings, without derived variables:
         returns ``(data, new_initial_condition)`` with ``data[name]`` [B, n_forward_steps, H, W] for every output name and
         ``new_initial_condition[name]`` [B, 1, H, W] for every prognostic name (the last predicted time, usable as the next
-        window's initial condition).  ``n_forward_steps`` = forcing times - 1, as in the reference."""
+        window's initial condition).  ``n_forward_steps`` = forcing times - 1, as in the reference.  The reference attaches the
+        terminal ``stepper_state`` to the returned prognostic state (:507-521); here ``new_initial_condition`` is a dict subclass
+        whose ``.stepper_state`` attribute holds it -- pass it as ``stepper_state=`` of the next window so the dry-air target stays
+        pinned to the FIRST initial condition."""
         names = self.next_step_input_names
         if not names:
             raise ValueError("predict: the number of forward steps is taken from the forcing data, which is empty")
@@ -475,18 +556,24 @@ class FusedStepper:
             if initial_condition[n].shape[self.TIME_DIM] != 1:
                 raise ValueError(f"Initial condition must have 1 timesteps, got {initial_condition[n].shape[self.TIME_DIM]}.")
         n_forward_steps = forcing[names[0]].shape[self.TIME_DIM] - 1
+        if stepper_state is None:
+            stepper_state = getattr(initial_condition, "stepper_state", None)
         prog0 = torch.stack([initial_condition[n].squeeze(self.TIME_DIM) for n in self.prognostic_names], dim=1)
         fseq, oseq, pseq, cseq = self._window_tensors(forcing, n_forward_steps, prog0.device)
-        outs, final = self.rollout(prog0, fseq, n_forward_steps, use_cuda_graph, True, oseq, pseq, cseq)
+        outs, final = self.rollout(prog0, fseq, n_forward_steps, use_cuda_graph, True, oseq, pseq, cseq, stepper_state=stepper_state)
         data = {n: outs[:, :, i].transpose(0, 1) for i, n in enumerate(self.out_names)}
-        new_ic = {n: final[:, i].unsqueeze(self.TIME_DIM) for i, n in enumerate(self.prognostic_names)}
+        new_ic = PrognosticDict({n: final[:, i].unsqueeze(self.TIME_DIM) for i, n in enumerate(self.prognostic_names)})
+        new_ic.stepper_state = self.get_stepper_state(prog0.shape[0])
         return data, new_ic
 
-    def predict_paired(self, initial_condition: Mapping[str, torch.Tensor], forcing: Mapping[str, torch.Tensor], use_cuda_graph: bool = True):
+    def predict_paired(self, initial_condition: Mapping[str, torch.Tensor], forcing: Mapping[str, torch.Tensor], use_cuda_graph: bool = True,
+                       stepper_state=None):
         """``Stepper.predict_paired`` (fme/ace/stepper/single_module.py:1261-1311) on name -> tensor mappings: the prediction paired
         with the reference ("target / forcing") values of every variable of ``forcing`` at the predicted times, i.e. the time axis
         without the initial-condition time (``get_forward_data``, :1313-1327).  Returns ``(prediction, reference), new_ic``."""
-        prediction, new_ic = self.predict(initial_condition, forcing, use_cuda_graph)
+        if stepper_state is None:
+            stepper_state = getattr(initial_condition, "stepper_state", None)
+        prediction, new_ic = self.predict(initial_condition, forcing, use_cuda_graph, stepper_state=stepper_state)
         reference = {n: v[:, self.n_ic_timesteps:] for n, v in forcing.items()}
         return (prediction, reference), new_ic
 
@@ -506,13 +593,18 @@ class FusedStepper:
 
     def rollout_host(self, prog0: torch.Tensor, forcing_host: Optional[torch.Tensor], n_steps: int,
                      out_host: Optional[torch.Tensor] = None, ocean_host: Optional[torch.Tensor] = None,
-                     prescribed_host: Optional[torch.Tensor] = None):
+                     prescribed_host: Optional[torch.Tensor] = None, corrector_next_host: Optional[torch.Tensor] = None,
+                     stepper_state=None):
         """Autoregressive loop with HOST-resident forcing and outputs (the inference driver's situation: forcing windows come
         from the data loader, outputs go to the writers; ``fme/core/generics/inference.py:117-166``).
 
         forcing_host [>= n_steps (cycled), B, n_forcing, H, W] pinned; out_host [n_steps, B, n_out, H, W] pinned (or None);
         ocean_host / prescribed_host [>= n_steps (cycled), B, n, H, W] pinned: data of each step's OUTPUT time.
-        With the energy budget correction the (DSWRFtoa, HGTsfc) pair of the output time is taken from ``forcing_host[(t + 1) % n]``.
+        The packed host forcing must already carry the ``next_step_forcing_names`` shift (the value of such a channel at index t is
+        the one of time t + 1), as ``_window_tensors`` produces it.
+        With the energy budget correction the (DSWRFtoa, HGTsfc) pair of the OUTPUT time is taken from ``corrector_next_host[t]``
+        ([>= n_steps, B, 2, H, W] pinned) when given, else from ``forcing_host[t + 1]`` -- which then needs ``n_steps + 1`` forcing
+        times (no wrap-around: silently re-using time 0 as the next-time insolation would be wrong; ``rollout`` raises likewise).
         Every step copies its forcing host->device and its outputs device->host; both copies run on side streams and overlap the
         neighbouring steps' compute (double-buffered staging), the step itself is one CUDA-graph replay.
         Returns the final prognostic state (device).  The caller synchronises before reading ``out_host``.
@@ -522,11 +614,12 @@ class FusedStepper:
             raise ValueError("prescribed_host must be given exactly when prescribed_prognostic_names is configured")
         if prescribed_host is not None and not self.forcing_names:
             raise NotImplementedError("rollout_host: prescribed data is staged alongside the forcing; a network without forcing inputs is not handled")
+        if self.corrector_needs_next and corrector_next_host is None and (forcing_host is None or forcing_host.shape[0] < n_steps + 1):
+            raise ValueError("the energy budget correction reads (DSWRFtoa, HGTsfc) at the output time: give forcing_host with "
+                             "n_steps + 1 times or corrector_next_host [n_steps, B, 2, H, W]")
+        self._sync_before_replay(dev)
         st, graph = self._ensure_graph(prog0)
-        if self.corrector is not None:
-            with torch.cuda.device(dev):
-                self.reset_corrector_state()
-                self._seed_corrector(prog0.float().contiguous())
+        self._begin_window(prog0.float().contiguous(), stepper_state)
         cur = torch.cuda.current_stream(dev)
         if not hasattr(self, "_h"):
             self._h = None
@@ -535,7 +628,7 @@ class FusedStepper:
             h = dict(B=st["B"], dev=dev, s_in=torch.cuda.Stream(dev), s_out=torch.cuda.Stream(dev),
                      fst=[torch.empty_like(st["forcing"]) for _ in range(2)] if st["forcing"] is not None else None,
                      cst=[torch.empty_like(st["ocean"]) for _ in range(2)] if st["ocean"] is not None else None,
-                     nst=[torch.empty_like(st["forcing"]) for _ in range(2)] if st["cnext"] is not None else None,
+                     nst=[torch.empty_like(st["cnext"]) for _ in range(2)] if st["cnext"] is not None else None,
                      pst=[torch.empty_like(st["presc"]) for _ in range(2)] if st["presc"] is not None else None,
                      ost=[torch.empty_like(st["out"]) for _ in range(2)])
             self._h = h
@@ -555,7 +648,10 @@ class FusedStepper:
                 if h["cst"] is not None:
                     h["cst"][b].copy_(ocean_host[t % ocean_host.shape[0]], non_blocking=True)
                 if h["nst"] is not None:
-                    h["nst"][b].copy_(forcing_host[(t + 1) % nf], non_blocking=True)
+                    if corrector_next_host is not None:
+                        h["nst"][b].copy_(corrector_next_host[t % corrector_next_host.shape[0]], non_blocking=True)
+                    else:
+                        h["nst"][b].copy_(self.corrector_next_from_forcing(forcing_host[t + 1]), non_blocking=True)
                 if h["pst"] is not None:
                     h["pst"][b].copy_(prescribed_host[t % prescribed_host.shape[0]], non_blocking=True)
                 ev_in[b].record(h["s_in"])
@@ -573,7 +669,7 @@ class FusedStepper:
                 if h["cst"] is not None:
                     st["ocean"].copy_(h["cst"][b], non_blocking=True)
                 if h["nst"] is not None:
-                    st["cnext"].copy_(self.corrector_next_from_forcing(h["nst"][b]), non_blocking=True)
+                    st["cnext"].copy_(h["nst"][b], non_blocking=True)
                 if h["pst"] is not None:
                     st["presc"].copy_(h["pst"][b], non_blocking=True)
                 ev_used[b].record(cur)

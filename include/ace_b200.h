@@ -263,6 +263,12 @@ void ace_corrector_destroy(ace_corrector* c);
 int ace_corrector_seed(ace_corrector* c, const float* prog_dev, int batch, void* stream);
 int ace_corrector_reset(ace_corrector* c);
 int ace_corrector_is_seeded(ace_corrector* c);
+/* CorrectorState.global_dry_air_mass (fme/core/corrector/state.py:15-29): the reference carries the dry-air target from one
+ * prediction window to the next inside stepper_state (fme/ace/stepper/single_module.py:1160-1165).  get: copy the fp64 target of
+ * each sample to host memory (ACE_ERR_STATE when unseeded); set: install it and mark the corrector seeded, so that the next
+ * step does NOT re-seed from its input.  Both synchronise `stream` once. */
+int ace_corrector_get_state(ace_corrector* c, double* target_host, int batch, void* stream);
+int ace_corrector_set_state(ace_corrector* c, const double* target_host, int batch, void* stream);
 /* 1 when ace_corrector_apply needs prev_forcing_dev and next_dev (energy budget correction). */
 int ace_corrector_needs_next(ace_corrector* c);
 /* In place on out_dev (and next_prog_dev for corrected prognostic fields); prev_prog_dev / prev_forcing_dev = the step's input

@@ -240,6 +240,50 @@ def test_rollout_with_corrector_graph_equals_eager_and_reseeds():
         assert float((dry_mean(o) - dry_mean(ic)).abs().max()) < 0.05, t
 
 
+def test_corrector_state_is_carried_across_windows_and_step_seeds_from_its_own_input():
+    """(a) two chained windows with the carried ``stepper_state`` equal ONE rollout of both windows (the dry-air
+    target stays pinned to the first initial condition, fme/ace/stepper/single_module.py:1160-1165), while a window started
+    without the state re-pins it; (b) ``step()`` without a state seeds from each call's own input (fme/core/corrector/atmosphere.py:404-427)."""
+    img, in_names, out_names, means, stds, onet, st, _, _ = _stepper("advection_and_precipitation", ocean=False)
+    B, T = 2, 4
+    g = torch.Generator().manual_seed(19)
+    n_prog, n_f = len(st.prognostic_names), len(st.forcing_names)
+    pm = torch.tensor([means[n] for n in st.prognostic_names])[None, :, None, None]
+    ps = torch.tensor([stds[n] for n in st.prognostic_names])[None, :, None, None]
+    prog0 = (torch.randn(B, n_prog, *img, generator=g) * ps + pm).cuda()
+    forcing = torch.randn(2 * T, B, n_f, *img, generator=g).cuda()
+    for graph in (False, True):
+        o_all, f_all = st.rollout(prog0, forcing, 2 * T, use_cuda_graph=graph)
+        o1, f1 = st.rollout(prog0, forcing[:T], T, use_cuda_graph=graph)
+        state = st.get_stepper_state(B)
+        gm = state["corrector_state"]["global_dry_air_mass"]
+        assert gm.shape == (B, 1, 1) and gm.dtype == torch.float64
+        o2, f2 = st.rollout(f1, forcing[T:], T, use_cuda_graph=graph, stepper_state=state)
+        torch.testing.assert_close(torch.cat([o1, o2]), o_all, rtol=0, atol=0)
+        torch.testing.assert_close(f2, f_all, rtol=0, atol=0)
+        # without the carried state the second window re-pins the mass to ITS first state: the corrected pressure differs
+        o2r, _ = st.rollout(f1, forcing[T:], T, use_cuda_graph=graph)
+        gm2 = st.get_stepper_state(B)["corrector_state"]["global_dry_air_mass"]
+        assert float((gm2 - gm).abs().max()) > 0  # the drifted state has a (slightly) different dry-air mean
+    # (b) independent single steps on different inputs: each seeds from its own input
+    s0 = {n: (torch.randn(B, *img, generator=g) * stds[n] + means[n]).cuda() for n in in_names}
+    s1 = {n: v + 0.2 * stds[n] for n, v in s0.items()}
+    for k in range(NZ):
+        for d in (s0, s1):
+            d[f"specific_total_water_{k}"] = d[f"specific_total_water_{k}"].clamp(min=0)
+    a1 = st.step(s1)
+    t1 = st.get_stepper_state(B)["corrector_state"]["global_dry_air_mass"].clone()
+    st.step(s0)
+    t0 = st.get_stepper_state(B)["corrector_state"]["global_dry_air_mass"].clone()
+    assert float((t1 - t0).abs().min()) > 0
+    b1 = st.step(s1)  # same result as the first call on s1: no memory of s0's target
+    for n in out_names:
+        torch.testing.assert_close(b1[n], a1[n], rtol=0, atol=0)
+    # ... and with an explicit state the target is the given one
+    c1 = st.step(s1, stepper_state={"corrector_state": {"global_dry_air_mass": t0}})
+    assert not torch.equal(c1["PRESsfc"], a1["PRESsfc"])
+
+
 # ---- the rest of the reference's sequence: zero-mean advection, frozen-precipitation clip, total energy budget ----------------
 FLUXES = ["DLWRFsfc", "ULWRFsfc", "DSWRFsfc", "USWRFsfc", "SHTFLsfc", "USWRFtoa", "ULWRFtoa"]
 TEMPS = [f"air_temperature_{k}" for k in range(NZ)]

@@ -79,6 +79,40 @@ def test_net_tcgen05_path_vs_oracle(img, cin, cout, embed, layers, batch):
     assert field_rel_err(y.cpu(), y2.cpu()) < FIELD_RTOL
 
 
+@pytest.mark.parametrize("embed,img", [(32, (48, 96)), (136, (40, 80)), (384, (24, 48))])
+def test_dhconv_orientations_agree(embed, img):
+    """Both dhconv GEMM orientations (orders on the rows = cplx 2 / weights on the rows = cplx 1) against the oracle."""
+    from ace_b200 import _lib
+    from oracle import sfno as osfno
+
+    fields = dict(embed_dim=embed, num_layers=2, operator_type="dhconv")
+    torch.manual_seed(21)
+    onet = osfno.SphericalFourierNeuralOperatorNet(img, 5, 4, **fields).eval()
+    with torch.no_grad():
+        for k, p in onet.named_parameters():
+            if k.endswith("filter.filter.weight"):
+                p.mul_(p.shape[0])
+    net = _b200_net(img, 5, 4, fields)
+    net.load_state_dict(onet.state_dict())
+    net = net.cuda().eval()
+    x = torch.randn(2, 5, *img)
+    with torch.no_grad():
+        ref = onet(x)
+    outs = []
+    s0 = _lib.get_option("count_simt")
+    try:
+        for t in (1, 0):
+            _lib.set_option("dhconv_t", t)
+            with torch.no_grad():
+                outs.append(net(x.cuda()).cpu())
+    finally:
+        _lib.set_option("dhconv_t", 1)
+    assert _lib.get_option("count_simt") == s0
+    for y in outs:
+        assert field_rel_err(y, ref) < FIELD_RTOL
+    assert field_rel_err(outs[0], outs[1]) < FIELD_RTOL
+
+
 def test_module_contract():
     import ace_b200
 

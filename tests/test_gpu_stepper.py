@@ -78,6 +78,51 @@ def test_rollout_graph_equals_eager_and_oracle():
         state = {n: out[n] for n in st.prognostic_names}
 
 
+def test_graph_replay_picks_up_weight_changes():
+    """parameters edited / reloaded after the CUDA graph was captured must reach the replays (the graph is cached
+    on (B, device) only and a replay never passes through the eager upload path)."""
+    img, in_names, out_names, means, stds, onet, st = _setup(False)
+    torch.manual_seed(3)
+    T, B = 3, 2
+    prog0 = torch.randn(B, 3, *img).cuda()
+    forcing = torch.randn(T, B, 2, *img).cuda()
+    og0, _ = st.rollout(prog0, forcing, T, use_cuda_graph=True)  # captures
+    net = st.module
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    sd["decoder.2.weight"] = sd["decoder.2.weight"] * 1.5
+    sd["blocks.0.filter.filter.weight"] = sd["blocks.0.filter.filter.weight"] * 0.5
+    sd["pos_embed"] = sd["pos_embed"] + 0.01
+    net.load_state_dict(sd)
+    og1, fg1 = st.rollout(prog0, forcing, T, use_cuda_graph=True)   # replays of the cached graph
+    oe1, fe1 = st.rollout(prog0, forcing, T, use_cuda_graph=False)  # eager: uploads on every step
+    assert not torch.equal(og1, og0)
+    torch.testing.assert_close(og1, oe1, rtol=0, atol=0)
+    torch.testing.assert_close(fg1, fe1, rtol=0, atol=0)
+    with torch.no_grad():
+        net.encoder[0].bias.add_(0.05)  # in-place edit (version counter)
+    out_host = torch.empty(T, B, len(out_names), *img).pin_memory()
+    st.rollout_host(prog0, forcing.cpu().pin_memory(), T, out_host)
+    oe2, _ = st.rollout(prog0, forcing, T, use_cuda_graph=False)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(out_host, oe2.cpu(), rtol=0, atol=0)
+    assert not torch.equal(oe2, oe1)
+
+
+def test_step_packed_rejects_bad_buffers():
+    img, in_names, out_names, means, stds, onet, st = _setup(False)
+    B = 2
+    prog = torch.randn(B, 3, *img).cuda()
+    forcing = torch.randn(B, 2, *img).cuda()
+    with pytest.raises(ValueError):
+        st.step_packed(prog, forcing, out=torch.empty(B, len(out_names), *img, device="cuda", dtype=torch.float16))
+    with pytest.raises(ValueError):
+        st.step_packed(prog, forcing, out=torch.empty(B, len(out_names) + 1, *img, device="cuda")[:, 1:])
+    with pytest.raises(ValueError):
+        st.step_packed(prog, forcing, next_prog=torch.empty(B, 3, img[0], 2 * img[1], device="cuda")[..., ::2])
+    with pytest.raises(ValueError):
+        st.step_packed(prog, forcing, out=torch.empty(B, len(out_names), *img))  # CPU buffer
+
+
 def test_rollout_host_pipelined_equals_device_rollout():
     """Host-resident forcing / outputs with copies on side streams == the device-resident graph rollout."""
     img, in_names, out_names, means, stds, onet, st = _setup(False)
