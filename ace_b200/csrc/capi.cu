@@ -52,6 +52,8 @@ void run_gemm(const GemmOp& op, cudaStream_t stream) {
   const char* why = nullptr;
   if (!options().force_simt && umma_eligible(op, &why)) {
     run_gemm_umma(op, stream);
+  } else if (op.bfly && !options().force_simt && umma_eligible(bfly_dense(op), &why)) {
+    run_gemm_umma(bfly_dense(op), stream);  // the butterfly variant is not compiled for this shape: same result, twice the MMAs
   } else {
     run_gemm_simt(op, stream);
   }
@@ -82,6 +84,10 @@ extern "C" int ace_set_option(const char* key, int value) {
     options().pdl = value ? 1 : 0;
   } else if (!strcmp(key, "dbg")) {
     options().dbg = value;
+  } else if (!strcmp(key, "inv2")) {
+    options().inv2 = value ? 1 : 0;
+  } else if (!strcmp(key, "tile_list")) {
+    options().tile_list = value ? 1 : 0;
   } else if (!strcmp(key, "dhconv_t")) {
     options().dhconv_t = value ? 1 : 0;
   } else if (!strcmp(key, "umma_bk")) {
@@ -105,6 +111,8 @@ extern "C" int ace_get_option(const char* key) {
   if (!strcmp(key, "pair")) return options().pair;
   if (!strcmp(key, "umma_bk")) return options().umma_bk;
   if (!strcmp(key, "dhconv_t")) return options().dhconv_t;
+  if (!strcmp(key, "tile_list")) return options().tile_list;
+  if (!strcmp(key, "inv2")) return options().inv2;
   return -1;
 }
 

@@ -92,7 +92,10 @@ struct Options {
   int pdl = 0;       // programmatic dependent launch of the tcgen05 GEMM / prep kernels (prologue overlaps the previous kernel's tail)
   int dbg = 0;       // development switches of the tcgen05 kernel (results are wrong when non-zero)
   int umma_bk = 0;   // K extent per pipeline stage of the ROWC (forward SHT / dhconv) variants: 0 = per-op hint, 32, 64
-  int dhconv_t = 1;  // dhconv orientation: 1 = orders on the rows / output channels on the columns (128 x 128 MMAs, NC epilogue), 0 = weights on the rows
+  int tile_list = 1; // triangular GEMMs walk a host-built list of their non-empty tiles, heaviest first (0: implicit round-robin walk of the full tile box)
+  int inv2 = 1;      // networks use the padded / parity-split inverse Legendre stage + butterfly inverse DFT (sht.cuh); 0: first-generation pair
+  int dhconv_t = 0;  // dhconv orientation: 0 = weights on the rows, the l + 1 orders on the columns (fewest multiplications: measured 83 vs 89 us);
+                     // 1 = orders on the rows / output channels on the columns (128 x 128 MMAs, NC epilogue)
   int umma_bn = 0;   // 0 = choose per op; otherwise force the N tile of the K-major x K-major variants (192 / 256)
 };
 Options& options();

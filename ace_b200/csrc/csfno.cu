@@ -79,8 +79,8 @@ struct ace_csfno {
   bool finalized = false;
 
   int wsB = 0;
-  DevBuf xin, hcat, e1, hP, xn, rr, x1, c1, c2, g, T, tP, tn, hmid, d1, ctx, sb0;
-  long long p_xin, p_hcat, p_act, p_x1, p_c1, p_c2, p_g, p_hmid;
+  DevBuf xin, hcat, e1, hP, xn, rr, x1, c1, c2, g, g2, T, tP, tn, hmid, d1, ctx, sb0;
+  long long p_xin, p_hcat, p_act, p_x1, p_c1, p_c2, p_g, p_g2, p_hmid;
   RtBuf rt_in, rt_out;  // filter_residual on the big skip (in_chans wide) / filter_output (out_chans wide)
   DevBuf xrt, yP;       // planes [B][in_chans][HW]: filtered input ahead of norm_big_skip; [B][out_chans][HW]: unfiltered output
   long long p_yP = 0;
@@ -184,6 +184,7 @@ void ensure_ws(ace_csfno& n, int B) {
   n.p_c1 = B * p.c1_elems(C);
   n.p_c2 = B * p.c2_elems(C);
   n.p_g = B * p.g_elems(C);
+  n.p_g2 = B * p.g2_elems(C);
   n.p_hmid = (long long)B * c.mlp_hidden * HW;
   const size_t e = sizeof(bf16);
   n.xin.ensure(2 * (size_t)n.p_xin * e);
@@ -193,6 +194,7 @@ void ensure_ws(ace_csfno& n, int B) {
   n.c1.ensure(2 * (size_t)n.p_c1 * e);
   n.c2.ensure(2 * (size_t)n.p_c2 * e);
   n.g.ensure(2 * (size_t)n.p_g * e);
+  n.g2.ensure(2 * (size_t)n.p_g2 * e);
   n.T.ensure((size_t)n.p_act * sizeof(float));
   n.hmid.ensure(2 * (size_t)n.p_hmid * e);
   if (n.Ep > 0) n.ctx.ensure((size_t)B * n.Ep * HW * sizeof(float));
@@ -320,8 +322,13 @@ void forward(ace_csfno& n, const float* x, const float* scalar, const float* lab
     }
     // complex GEMM per degree l over the orders m <= l (s2convolutions.py:118-136)
     run_gemm(dhconv_op(n.c1.as<bf16>(), P_c1, w.spec.as<bf16>(), w.spec_plane, pf, C, C, B, n.c2.as<bf16>(), P_c2), s);
-    run_gemm(sht_op_legendre_inv(pi, n.c2.as<bf16>(), P_c2, C, B, n.g.as<bf16>(), P_g), s);
-    run_gemm(sht_op_dft_inv(pi, n.g.as<bf16>(), P_g, C, B, n.T.as<float>(), act_b), s);
+    if (options().inv2) {
+      run_gemm(sht_op_legendre_inv2(pi, n.c2.as<bf16>(), P_c2, C, B, n.g2.as<bf16>(), n.p_g2), s);
+      run_gemm(sht_op_dft_inv2(pi, n.g2.as<bf16>(), n.p_g2, C, B, n.T.as<float>(), act_b), s);
+    } else {
+      run_gemm(sht_op_legendre_inv(pi, n.c2.as<bf16>(), P_c2, C, B, n.g.as<bf16>(), P_g), s);
+      run_gemm(sht_op_dft_inv(pi, n.g.as<bf16>(), P_g, C, B, n.T.as<float>(), act_b), s);
+    }
     // x = GELU(filter(xn) + b_filter + inner_skip(residual))   (sfnonet.py:387-399)
     {
       GemmOp op = conv_op("inner_skip", resid, P_act, act_b, HW, B, w.skip, C);

@@ -50,6 +50,7 @@ enum EpiFlags : uint32_t {
 struct EpiParams {
   uint32_t flags;
   int mdiv;
+  int mrows;  // 0 = every row exists; otherwise rows with m0 >= mrows are padding: computed, never stored (mdiv > mrows)
   const float* row_bias;
   long long rb_z2;
   const float* ra_scale;
@@ -66,6 +67,9 @@ struct EpiParams {
   long long stats_z2;
   bf16* out;
   long long out_plane, o_z1, o_z2, o_m1, o_m0, o_n;
+  // o_z1b != 0: the z1 axis is stored split by parity -- offset = (z1 >> 1) * o_z1 + (z1 & 1) * o_z1b (inverse Legendre stage:
+  // even orders m first, then the odd ones, which is the k order the butterfly inverse DFT wants)
+  long long o_z1b;
   float* outf;
   long long f_z1, f_z2, f_m1, f_m0, f_n;
 };
@@ -86,6 +90,12 @@ struct GemmOp {
   //   (column n of the imaginary part is stored at column index n + N).
   int cplx;
   long long a_part, b_part;
+  // Butterfly mode (inverse longitude DFT of an even-length grid, sht.cu): the k axis is split at k_split,
+  //   E[m][n] = sum_{k < k_split} A[m][k] B[n][k],   O[m][n] = sum_{k >= k_split} A[m][k] B[n][k],     n in [0, N)
+  //   D[m][n] = E + O,   D[m][n + N] = E - O
+  // B holds 2N rows; rows [N, 2N) equal rows [0, N) with the k >= k_split part negated, so the op is the plain GEMM with
+  // 2N columns at half the multiplications (run_gemm falls back to exactly that when the butterfly kernel is not eligible).
+  int bfly, k_split;
   int bk_hint;  // 0 = kernel default (32); 64 = K extent per pipeline stage for K-major x K-major ops whose A streams from HBM
   EpiParams epi;
   const char* name;  // for error messages / profiling
@@ -123,11 +133,16 @@ __device__ __forceinline__ float epi_value(const EpiParams& e, float acc, int m1
   return v;
 }
 
+__device__ __forceinline__ long long epi_z1_off(const EpiParams& e, int z1) {
+  return e.o_z1b ? (long long)(z1 >> 1) * e.o_z1 + (long long)(z1 & 1) * e.o_z1b : (long long)z1 * e.o_z1;
+}
+
 __device__ __forceinline__ void epi_store(const EpiParams& e, float v, int m1, int m0, int n, int z1, int z2) {
+  if (e.mrows && m0 >= e.mrows) return;
   if (e.flags & EPI_OUT_PLANES) {
     bf16 hi, lo;
     split_bf16(v, hi, lo);
-    bf16* o = e.out + (long long)z1 * e.o_z1 + (long long)z2 * e.o_z2 + (long long)m1 * e.o_m1 + (long long)m0 * e.o_m0 + (long long)n * e.o_n;
+    bf16* o = e.out + epi_z1_off(e, z1) + (long long)z2 * e.o_z2 + (long long)m1 * e.o_m1 + (long long)m0 * e.o_m0 + (long long)n * e.o_n;
     o[0] = hi;
     o[e.out_plane] = lo;
   }
@@ -136,6 +151,15 @@ __device__ __forceinline__ void epi_store(const EpiParams& e, float v, int m1, i
   }
 }
 #endif
+
+// the plain 2N-column GEMM a butterfly op is shorthand for
+inline GemmOp bfly_dense(const GemmOp& op) {
+  GemmOp d = op;
+  d.N = 2 * op.N;
+  d.bfly = 0;
+  d.k_split = 0;
+  return d;
+}
 
 // Dispatcher: tcgen05 kernel when the op is eligible (and not overridden), SIMT kernel otherwise.
 void run_gemm(const GemmOp& op, cudaStream_t stream);

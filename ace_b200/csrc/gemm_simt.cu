@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const __grid_constant__ G
 }  // namespace
 
 void run_gemm_simt(const GemmOp& op_in, cudaStream_t stream) {
-  GemmOp op = op_in;
+  GemmOp op = op_in.bfly ? bfly_dense(op_in) : op_in;
   if (op.cplx) {  // the SIMT kernel walks the real-ified problem
     ACE_REQUIRE(!op.k_lo_z1, "gemm %s: complex mode with a triangular K range is not supported", op.name);
     ACE_REQUIRE(op.cplx == 1 || op.cplx == 2, "gemm %s: bad complex mode %d", op.name, op.cplx);

@@ -28,7 +28,11 @@
 // (UMMA N is a runtime field of the instruction descriptor) and K-chunks below k_lo are skipped.
 #include <cuda.h>
 
+#include <algorithm>
+#include <cstring>
+#include <map>
 #include <mutex>
+#include <vector>
 
 #include "gemm.cuh"
 #include "ptx.cuh"
@@ -47,6 +51,12 @@ struct UmmaParams {
   int dbg;                                 // development switches (option "dbg"): 1 skip epilogue, 2 skip TMA, 4 skip MMA
   int scalar_store;                        // epilogue stores element-wise (row groups / row starts not vector-aligned, e.g. odd nlat)
   int m_fastest;                           // tile order: consecutive tiles share the B (1) or the A (0) tile
+  // Triangular ops: explicit list of the NON-EMPTY tiles {tm, tn, z1, z2}, heaviest first (host-built, cached per shape).
+  // Walking the full tm x tn x z1 x z2 box round-robin leaves CTAs idle whenever the empty slots correlate with the CTA
+  // index (dhconv: for l < 128 every odd slot is empty and the grid size is even -> half the SMs idled for 70 % of the
+  // kernel) and gives every CTA a different amount of work when the tile cost depends on z1 (Legendre stages).
+  const int4* tiles;
+  long long n_listed;
 };
 
 constexpr uint32_t EF_MASK = EPI_ADD_F32 | EPI_RES_PLANES | EPI_GELU | EPI_OUT_PLANES | EPI_OUT_F32;
@@ -55,7 +65,7 @@ constexpr int kThreadsUmma = 32 * (4 + kEpiWarps);
 constexpr int kStgBytesPerWarp = 2048;
 constexpr int kMaxSmem = 232448;  // 227 KB opt-in limit per CTA
 
-template <int BN_, bool A_MN_, bool B_MN_, uint32_t EF_, bool NC_, int BK_ = 32, bool CPLX_ = false, bool PAIR_ = false>
+template <int BN_, bool A_MN_, bool B_MN_, uint32_t EF_, bool NC_, int BK_ = 32, bool CPLX_ = false, bool PAIR_ = false, bool BFLY_ = false>
 struct Cfg {
   static constexpr int BM = 128, BN = BN_, BK = BK_;
   static constexpr bool A_MN = A_MN_, B_MN = B_MN_, NC = NC_, CPLX = CPLX_;
@@ -68,12 +78,15 @@ struct Cfg {
   static constexpr bool PAIR = PAIR_;
   static constexpr int BNL = PAIR ? BN / 2 : BN;  // B columns staged by this CTA
   static constexpr int TILE_M = PAIR ? 256 : 128;
-  static constexpr int NACC = CPLX ? 2 : 1;  // accumulators per tile (complex mode: real and imaginary rows)
+  // butterfly mode (GemmOp::bfly): K-chunks below / from k_split accumulate into two accumulators E, O; the epilogue stores
+  // E + O at column n and E - O at column n + N
+  static constexpr bool BFLY = BFLY_;
+  static constexpr int NACC = (CPLX || BFLY) ? 2 : 1;  // accumulators per tile (complex mode: real and imaginary part)
   static constexpr uint32_t EF = EF_;
   static constexpr int UMMA_K = 16;
   static constexpr int A_PLANE = BM * BK * 2;  // bytes
   static constexpr int B_PLANE = BNL * BK * 2;
-  static constexpr int STAGE = 2 * NACC * (A_PLANE + B_PLANE);  // complex mode: {Ar, Ai} x {hi, lo}, then {Br, Bi} x {hi, lo}
+  static constexpr int STAGE = 2 * (CPLX ? 2 : 1) * (A_PLANE + B_PLANE);  // complex mode: {Ar, Ai} x {hi, lo}, then {Br, Bi} x {hi, lo}
   static constexpr int STG_BYTES = kEpiWarps * kStgBytesPerWarp;
   static constexpr int MAX_STAGES = 8;
   static constexpr int BAR_BYTES = (2 * MAX_STAGES + 4) * 8 + 16;
@@ -85,7 +98,8 @@ struct Cfg {
   static_assert(!CT || EF_ == EPI_OUT_PLANES, "complex mode with the NC epilogue: plain split-plane output");
   static_assert(!PAIR || (!CPLX && BNL % 64 == 0), "pair mode");
   static constexpr int SMEM_BYTES = STAGES * STAGE + STG_BYTES + BAR_BYTES + 1024;  // + alignment slack
-  static_assert(BN % 64 == 0 && BN <= 256, "BN");
+  static_assert(BN % (B_MN_ ? 64 : 32) == 0 && BN <= 256, "BN");
+  static_assert(!BFLY || (NC && !CPLX && !PAIR && !B_MN), "butterfly mode: NC epilogue, K-major B");
   static constexpr uint32_t K_LAYOUT = (BK == 64) ? 2u : 4u;  // K-major tiles: 128B swizzle (BK = 64) or 64B (BK = 32)
   static_assert(BK == 32 || BK == 64, "BK");
   static_assert(STAGES >= 2, "pipeline too shallow");
@@ -102,7 +116,12 @@ __device__ __forceinline__ bool decode_tile(const UmmaParams& p, long long t, Ti
   const GemmOp& op = p.op;
   int tn, tm;
   long long r;
-  if (p.m_fastest) {
+  if (p.tiles) {
+    const int4 e = __ldg(p.tiles + t);
+    tm = e.x;
+    tn = e.y;
+    r = (long long)e.z * op.Z2 + e.w;
+  } else if (p.m_fastest) {
     tm = (int)(t % p.tiles_m);
     r = t / p.tiles_m;
     tn = (int)(r % p.tiles_n);
@@ -213,7 +232,7 @@ __device__ __forceinline__ void epilogue_rowc(const UmmaParams& p, const Tile& t
   const int grow = row0 + pc * 4;
   const bool g_ok = grow < op.M;  // M % 4 == 0 (host-checked)
   const int m1 = grow / e.mdiv, mr = grow - m1 * e.mdiv;
-  bf16* gbase = e.out + (long long)ti.z1 * e.o_z1 + (long long)ti.z2 * e.o_z2 + (long long)m1 * e.o_m1 + mr +
+  bf16* gbase = e.out + epi_z1_off(e, ti.z1) + (long long)ti.z2 * e.o_z2 + (long long)m1 * e.o_m1 + mr +
                 (long long)(ti.n_begin + cc) * e.o_n;
   const int nch = (ti.n_count + 31) >> 5;  // 32-column chunks per accumulator
   const long long on4 = 4 * e.o_n;
@@ -222,7 +241,7 @@ __device__ __forceinline__ void epilogue_rowc(const UmmaParams& p, const Tile& t
   if (p.scalar_store) {
     const int orow2 = min(row0 + lane, op.M - 1);
     const int om1 = orow2 / e.mdiv, omr = orow2 - om1 * e.mdiv;
-    own = reinterpret_cast<unsigned short*>(e.out) + (long long)ti.z1 * e.o_z1 + (long long)ti.z2 * e.o_z2 + (long long)om1 * e.o_m1 + omr +
+    own = reinterpret_cast<unsigned short*>(e.out) + epi_z1_off(e, ti.z1) + (long long)ti.z2 * e.o_z2 + (long long)om1 * e.o_m1 + omr +
           (long long)ti.n_begin * e.o_n;
   }
   // deferred InstanceNorm of the A operand: per-row scale, constant folded into column 0 (thread = its own row)
@@ -308,11 +327,12 @@ __device__ __forceinline__ void epilogue_nc_prefetch(const UmmaParams& p, const 
   const EpiParams& e = p.op.epi;
   const int row = ti.m0 + 32 * q + lane;
   if (row >= p.op.M) return;
+  const int pm1 = row / e.mdiv, pm0 = row - pm1 * e.mdiv;
   for (int c = sub; c * 32 < ti.n_count; c += kEpiWarps / 4) {
     const long long n0 = ti.n_begin + c * 32;
-    if (EF & EPI_ADD_F32) prefetch_l2(e.add + (long long)ti.z2 * e.add_z2 + (long long)row * e.add_m0 + n0);
+    if (EF & EPI_ADD_F32) prefetch_l2(e.add + (long long)ti.z2 * e.add_z2 + (long long)pm1 * e.add_m1 + (long long)pm0 * e.add_m0 + n0);
     if (EF & EPI_RES_PLANES) {
-      const bf16* r = e.res + (long long)ti.z2 * e.res_z2 + (long long)row * e.res_m0 + n0;
+      const bf16* r = e.res + (long long)ti.z2 * e.res_z2 + (long long)pm1 * e.res_m1 + (long long)pm0 * e.res_m0 + n0;
       prefetch_l2(r);
       prefetch_l2(r + e.res_plane);
     }
@@ -463,7 +483,12 @@ __device__ __forceinline__ void epilogue_nc(const UmmaParams& p, const Tile& ti,
   const int row = row0 + lane;
   const int m_hi = op.m_hi_z1 ? min(op.M, ti.z1 + 1) : op.M;
   const bool row_ok = row < m_hi;
-  const int rows_valid = m_hi - row0;  // >= 32 for full tiles
+  int rows_valid = m_hi - row0;  // >= 32 for full tiles
+  // rows flattened as (m1, m0) with m0 < mdiv (mdiv % 32 == 0, host-checked: a warp's 32 rows share m1) and rows
+  // m0 >= mrows being padding that is never stored
+  const int rm1 = row0 / e.mdiv, rm0 = row0 - rm1 * e.mdiv;
+  if (e.mrows) rows_valid = min(rows_valid, e.mrows - rm0);
+  const long long z1off = epi_z1_off(e, ti.z1);
   const bool do_stats = (e.flags & EPI_ROW_STATS) != 0;
   float rbias = 0.f;
   if ((e.flags & EPI_ROW_BIAS) && row_ok) rbias = __ldg(e.row_bias + (long long)ti.z2 * e.rb_z2 + row);
@@ -479,23 +504,37 @@ __device__ __forceinline__ void epilogue_nc(const UmmaParams& p, const Tile& ti,
   const bf16* g_res = nullptr;
   float* g_f32 = nullptr;
   bf16* g_pl = nullptr;
-  if (EF & EPI_ADD_F32) g_add = e.add + (long long)ti.z2 * e.add_z2 + (long long)(row0 + fr) * e.add_m0 + ti.n_begin + fp * 4;
-  if (EF & EPI_RES_PLANES) g_res = e.res + (long long)ti.z2 * e.res_z2 + (long long)(row0 + pr) * e.res_m0 + ti.n_begin + pp * 4;
+  if (EF & EPI_ADD_F32)
+    g_add = e.add + (long long)ti.z2 * e.add_z2 + (long long)rm1 * e.add_m1 + (long long)(rm0 + fr) * e.add_m0 + ti.n_begin + fp * 4;
+  if (EF & EPI_RES_PLANES)
+    g_res = e.res + (long long)ti.z2 * e.res_z2 + (long long)rm1 * e.res_m1 + (long long)(rm0 + pr) * e.res_m0 + ti.n_begin + pp * 4;
   if (EF & EPI_OUT_F32)
-    g_f32 = e.outf + (long long)ti.z1 * e.f_z1 + (long long)ti.z2 * e.f_z2 + (long long)(row0 + fr) * e.f_m0 + ti.n_begin + fp * 4;
+    g_f32 = e.outf + (long long)ti.z1 * e.f_z1 + (long long)ti.z2 * e.f_z2 + (long long)rm1 * e.f_m1 + (long long)(rm0 + fr) * e.f_m0 +
+            ti.n_begin + fp * 4;
   if (EF & EPI_OUT_PLANES)
-    g_pl = e.out + (long long)ti.z1 * e.o_z1 + (long long)ti.z2 * e.o_z2 + (long long)(row0 + pr) * e.o_m0 + ti.n_begin + pp * 4;
+    g_pl = e.out + z1off + (long long)ti.z2 * e.o_z2 + (long long)rm1 * e.o_m1 + (long long)(rm0 + pr) * e.o_m0 + ti.n_begin + pp * 4;
 
   const int nch = (ti.n_count + 31) >> 5;
   for (int cc2 = sub; cc2 < C::NACC * nch; cc2 += kEpiWarps / 4) {
-    // complex mode: the second accumulator (imaginary part) sits BN TMEM columns further and lands op.N columns further
+    // complex mode: the second accumulator (imaginary part) sits BN TMEM columns further and lands op.N columns further;
+    // butterfly mode: pass 0 stores E + O at column n, pass 1 stores E - O at column n + N
     const int part = (C::NACC == 2 && cc2 >= nch) ? 1 : 0;
     const int c = cc2 - part * nch;
-    if (rows_valid <= 0) break;  // (triangular M range) nothing of this warp's rows exists
+    if (rows_valid <= 0) break;  // (triangular M range / padding rows) nothing of this warp's rows exists
     const int nvalid = min(32, ti.n_count - c * 32);  // multiple of 4 (host-checked) unless scalar_store
     float v[32];
-    ptx::tmem_ld_32x32(tacc + part * C::BN + c * 32, v);
-    ptx::tmem_ld_wait();
+    if constexpr (C::BFLY) {
+      float u[32];
+      ptx::tmem_ld_32x32(tacc + c * 32, v);
+      ptx::tmem_ld_32x32(tacc + C::BN + c * 32, u);
+      ptx::tmem_ld_wait();
+      const f2 sgn = part ? mk2(-1.f, -1.f) : mk2(1.f, 1.f);
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) un2(fma2(sgn, mk2(u[j], u[j + 1]), mk2(v[j], v[j + 1])), v[j], v[j + 1]);
+    } else {
+      ptx::tmem_ld_32x32(tacc + part * C::BN + c * 32, v);
+      ptx::tmem_ld_wait();
+    }
     const int co = c * 32 + part * op.N;
     if (nvalid == 32 && rows_valid >= 32 && !p.scalar_store)
       epilogue_nc_chunk<C, true>(e, v, nvalid, rows_valid, lane, s16, s8, g_add + co, g_res + co, g_f32 + co, g_pl + co, rbias,
@@ -570,7 +609,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-  const long long total = (long long)p.tiles_m * p.tiles_n * op.Z1 * op.Z2;
+  const long long total = p.tiles ? p.n_listed : (long long)p.tiles_m * p.tiles_n * op.Z1 * op.Z2;
   const long long t_first = PAIR ? (blockIdx.x >> 1) : blockIdx.x, t_step = PAIR ? (gridDim.x >> 1) : gridDim.x;
 
   if (warp == 0) {
@@ -720,12 +759,17 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
               ptx::umma_bf16_2sm(tmem_d, a_lo + kk * kstepA, b_hi + kk * kstepB, idesc, 1u);
             }
           } else if (!(p.dbg & 4)) {
+            // butterfly mode: the chunks from k_split on go to the second accumulator (k_split is a multiple of BK)
+            const int k0 = ti.k_begin + kc * BK;
+            const bool second = C::BFLY && k0 >= op.k_split;
+            const uint32_t tmem_t = tmem_d + (second ? BN : 0);
+            const bool fresh = kc == 0 || (C::BFLY && k0 == op.k_split);
 #pragma unroll
             for (int kk = 0; kk < BK / 16; ++kk) {
-              ptx::umma_bf16(tmem_d, a_hi + kk * kstepA, b_hi + kk * kstepB, idesc, (kc | kk) != 0 ? 1u : 0u);
+              ptx::umma_bf16(tmem_t, a_hi + kk * kstepA, b_hi + kk * kstepB, idesc, (fresh && kk == 0) ? 0u : 1u);
               if (p.nterms == 3) {
-                ptx::umma_bf16(tmem_d, a_hi + kk * kstepA, b_lo + kk * kstepB, idesc, 1u);
-                ptx::umma_bf16(tmem_d, a_lo + kk * kstepA, b_hi + kk * kstepB, idesc, 1u);
+                ptx::umma_bf16(tmem_t, a_hi + kk * kstepA, b_lo + kk * kstepB, idesc, 1u);
+                ptx::umma_bf16(tmem_t, a_lo + kk * kstepA, b_hi + kk * kstepB, idesc, 1u);
               }
             }
           }
@@ -847,6 +891,55 @@ void make_tmap(CUtensorMap* tm, const Operand& o, bool mn_major, long long rows,
 
 thread_local int t_scalar_store = 0;  // set by dispatch() for the launch it is about to make
 
+// ---- tile lists of the triangular ops (see UmmaParams::tiles) ----
+struct TileKey {
+  int M, N, K, Z1, Z2, flags, tile_m, bn, bk, m_fastest;
+  bool operator<(const TileKey& o) const { return memcmp(this, &o, sizeof(TileKey)) < 0; }
+};
+struct TileList {
+  DevBuf buf;
+  long long n = 0;
+};
+
+const TileList& tile_list(const GemmOp& op, int tile_m, int bn, int bk, int m_fastest) {
+  static std::mutex mu;
+  static std::map<TileKey, TileList> cache;
+  TileKey key;
+  memset(&key, 0, sizeof(key));
+  key.M = op.M; key.N = op.N; key.K = op.K; key.Z1 = op.Z1; key.Z2 = op.Z2;
+  key.flags = (op.n_lo_z1 ? 1 : 0) | (op.n_hi_z1 ? 2 : 0) | (op.k_lo_z1 ? 4 : 0) | (op.m_hi_z1 ? 8 : 0);
+  key.tile_m = tile_m; key.bn = bn; key.bk = bk; key.m_fastest = m_fastest;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  const int tiles_m = (op.M + tile_m - 1) / tile_m, tiles_n = (op.N + bn - 1) / bn;
+  struct Ent { int4 t; long long cost; long long order; };
+  std::vector<Ent> ents;
+  long long order = 0;
+  // same enumeration order as the implicit walk (locality: neighbouring entries share an operand tile), then a stable
+  // sort by descending cost: CTA b takes entries b, b + G, b + 2G, ... = one tile of every cost stratum
+  for (int z1 = 0; z1 < op.Z1; ++z1)
+    for (int z2 = 0; z2 < op.Z2; ++z2)
+      for (int o = 0; o < tiles_m * tiles_n; ++o) {
+        const int tm = m_fastest ? o % tiles_m : o / tiles_n, tn = m_fastest ? o / tiles_m : o % tiles_n;
+        const int n_lo = op.n_lo_z1 ? z1 : 0, n_hi = op.n_hi_z1 ? std::min(op.N, z1 + 1) : op.N, k_lo = op.k_lo_z1 ? z1 : 0;
+        const int n_begin = std::max(tn * bn, (n_lo / 16) * 16), n_end = std::min(tn * bn + bn, n_hi);
+        const int k_begin = (k_lo / bk) * bk, num_kc = (op.K - k_begin + bk - 1) / bk;
+        if (op.m_hi_z1 && tm * tile_m > z1) continue;
+        if (!(n_end - n_begin > 0 && n_end > n_lo && num_kc > 0)) continue;
+        const long long n_eff = std::max(64, (n_end - n_begin + 15) & ~15);  // MMAs narrower than ~64 columns cost the same
+        ents.push_back({make_int4(tm, tn, z1, z2), n_eff * num_kc, order++});
+      }
+  std::stable_sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b) { return a.cost > b.cost; });
+  TileList& tl = cache[key];
+  tl.n = (long long)ents.size();
+  std::vector<int4> host(ents.size());
+  for (size_t i = 0; i < ents.size(); ++i) host[i] = ents[i].t;
+  tl.buf.ensure(std::max<size_t>(16, host.size() * sizeof(int4)));
+  if (!host.empty()) ACE_CHECK_CUDA(cudaMemcpy(tl.buf.p, host.data(), host.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  return tl;
+}
+
 template <class C>
 void launch(const GemmOp& op, cudaStream_t stream) {
   static bool attr_set = false;
@@ -887,6 +980,14 @@ void launch(const GemmOp& op, cudaStream_t stream) {
   else
     make_tmap(&p.tmB, op.B, true, op.N, op.K, op.Z1, op.Z2, 64, C::BK, CU_TENSOR_MAP_SWIZZLE_128B, &p.b_z1_on, &p.b_z2_on, op.name);
   long long total = (long long)p.tiles_m * p.tiles_n * op.Z1 * op.Z2;
+  p.tiles = nullptr;
+  p.n_listed = 0;
+  if ((op.n_lo_z1 || op.n_hi_z1 || op.k_lo_z1 || op.m_hi_z1) && options().tile_list) {
+    const TileList& tl = tile_list(op, C::TILE_M, C::BN, C::BK, p.m_fastest);
+    if (tl.n == 0) return;  // nothing to compute
+    p.tiles = tl.buf.as<int4>();
+    p.n_listed = total = tl.n;
+  }
   int grid = C::PAIR ? 2 * (int)std::min<long long>(total, sm_count() / 2) : (int)std::min<long long>(total, sm_count());
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
@@ -957,6 +1058,7 @@ bool classify(const GemmOp& op, Variant& v, const char** why) {
     return true;
   }
   if (op.m_hi_z1) return fail("a triangular M range is only compiled for complex mode 2");
+  if (op.bfly && (e.o_m0 == 1 && e.o_n != 1 && (f & EPI_OUT_PLANES))) return fail("butterfly mode needs the NC epilogue");
   v.a_mn = a_mn;
   v.b_mn = b_mn;
   v.ef = f & EF_MASK;
@@ -977,8 +1079,17 @@ bool classify(const GemmOp& op, Variant& v, const char** why) {
   // NC: columns contiguous, rows affine, everything 4-element aligned
   v.nc = true;
   v.scalar = false;
-  if (e.mdiv < op.M) return fail("NC epilogue needs affine rows (mdiv >= M)");
+  const bool remap = e.mdiv < op.M;  // rows flattened as (m1, m0): a warp's 32 rows must share m1
+  if (remap && (e.mdiv % 32 != 0 || (f & (EPI_ROW_BIAS | EPI_ROW_STATS | EPI_RES_AFFINE)))) return fail("NC epilogue: row remapping needs mdiv % 32 == 0 and no per-row vectors");
+  if (remap && ((planes && !aligned4(e.o_m1)) || (f32 && !aligned4(e.f_m1)) || ((f & EPI_ADD_F32) && !aligned4(e.add_m1)) ||
+                ((f & EPI_RES_PLANES) && !aligned4(e.res_m1))))
+    return fail("NC epilogue: m1 strides not vectorisable");
+  if (e.mrows && !remap && e.mrows < op.M) return fail("mrows without row remapping");
   if (op.n_lo_z1 || op.n_hi_z1) return fail("NC epilogue does not take triangular N ranges");
+  if (op.bfly) {
+    if (op.cplx || !b_k || v.ef != EPI_OUT_F32 || (f & ~(uint32_t)EPI_OUT_F32) || op.k_lo_z1 || op.k_split <= 0 || op.k_split >= op.K || (op.k_split % 32) != 0)
+      return fail("butterfly mode: K-major B, plain fp32 output, 0 < k_split < K, k_split % 32 == 0");
+  }
   if (planes && v.ef == EPI_OUT_PLANES && e.o_n == 1 &&
       (!aligned4(op.N) || !aligned4(e.o_m0) || !aligned4(e.o_z1) || !aligned4(e.o_z2) || !aligned4(e.out_plane) || (((uintptr_t)e.out) & 7))) {
     v.scalar = true;  // plain plane output with unaligned row starts (inverse Legendre at odd nlat): element-wise stores
@@ -993,11 +1104,11 @@ bool classify(const GemmOp& op, Variant& v, const char** why) {
       return fail("fp32 output not 16B-vectorisable");
   }
   if (f & EPI_ADD_F32) {
-    if (e.add_n != 1 || e.add_m1 != 0 || !aligned4(e.add_m0) || !aligned4(e.add_z2) || (((uintptr_t)e.add) & 15))
+    if (e.add_n != 1 || !aligned4(e.add_m0) || !aligned4(e.add_z2) || (((uintptr_t)e.add) & 15))
       return fail("fp32 addend not 16B-vectorisable");
   }
   if (f & EPI_RES_PLANES) {
-    if (e.res_n != 1 || e.res_m1 != 0 || !aligned4(e.res_m0) || !aligned4(e.res_z2) || !aligned4(e.res_plane) || (((uintptr_t)e.res) & 7))
+    if (e.res_n != 1 || !aligned4(e.res_m0) || !aligned4(e.res_z2) || !aligned4(e.res_plane) || (((uintptr_t)e.res) & 7))
       return fail("plane residual not 8B-vectorisable");
   }
   return true;
@@ -1108,6 +1219,11 @@ bool dispatch(const GemmOp& op, bool dry, cudaStream_t s, const char** why) {
   if (op.cplx) {
     if (v.nc || (op.epi.flags & EPI_ROW_AFFINE)) { if (why) *why = "complex mode is compiled for the plain ROWC epilogue only"; return false; }
     if (!dry) launch<Cfg<128, false, false, P, false, 32, true>>(op, s);
+    return true;
+  }
+  if (op.bfly) {
+    if (!(v.nc && v.a_mn && v.ef == F)) { if (why) *why = "butterfly mode is compiled for MN-major A with fp32 output"; return false; }
+    if (!dry) launch<Cfg<96, true, false, F, true, 32, false, false, true>>(op, s);
     return true;
   }
   const bool ok = (!v.nc && !v.a_mn) || (v.nc && (v.ef == P || v.ef == F));

@@ -90,9 +90,10 @@ inline void add_f32(GemmOp& op, const float* add, long long batch_stride, long l
 }
 // dhconv (contractions.py:184-195): per degree l a complex GEMM  c2[m][l][o] = sum_i c1[l][m][i] * W[l][o][i]  over the orders
 // m <= l.  Weights: planes [L][2 (re, im)][Cout][Cinp]; c1: [B][L][M][2 Cin]; c2: [B][M][Lp][2 Cout].
-//   option dhconv_t = 1 (default): orders on the accumulator rows, output channels on the columns (GemmOp::cplx == 2) -- every
-//     MMA is 128 x 128, the output is stored along its contiguous (re/im, channel) axis (NC epilogue);
-//   option dhconv_t = 0: weights on the accumulator rows, the l + 1 orders on the columns (cplx == 1, ROWC epilogue).
+//   option dhconv_t = 0 (default): weights on the accumulator rows, the l + 1 orders on the columns (cplx == 1, ROWC epilogue):
+//     the fewest multiplications -- under the power cap that wins (83 vs 89 us at ACE2 size, profiles/r02_probe2.jsonl);
+//   option dhconv_t = 1: orders on the accumulator rows, output channels on the columns (GemmOp::cplx == 2) -- every MMA is
+//     128 x 128, the output is stored along its contiguous (re/im, channel) axis (NC epilogue).
 inline GemmOp dhconv_op(const bf16* c1, long long c1_plane, const bf16* w, long long w_plane, const ace_sht_plan& p, int Cin, int Cout,
                         int B, bf16* c2, long long c2_plane) {
   GemmOp op = make_gemm_op("dhconv");

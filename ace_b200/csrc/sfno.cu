@@ -48,10 +48,10 @@ struct ace_sfno {
 
   // workspace (allocated on first use for a batch size; grows monotonically)
   int wsB = 0;
-  DevBuf hcat, e1, hP, xn, x1, c1, c2, g, T, tP, hmid, d1, stats;
+  DevBuf hcat, e1, hP, xn, x1, c1, c2, g, g2, T, tP, hmid, d1, stats;
   DevBuf skipW, skipB, fc1W, fc1B;   // per-sample convolution parameters with the InstanceNorm folded in
   DevBuf na0, ns0, nsh0, na1, ns1, nsh1;  // per-(sample, channel) a, s, 2*pi*s of norm0 / norm1
-  long long p_hcat, p_act, p_x1, p_c1, p_c2, p_g, p_hmid, p_skipW, p_fc1W;  // plane offsets (elements)
+  long long p_hcat, p_act, p_x1, p_c1, p_c2, p_g, p_g2, p_hmid, p_skipW, p_fc1W;  // plane offsets (elements)
   // tP and hmid are only ever 1x1-convolution operands (MN-major B: one TMA box row = 64 pixels = 128 bytes of one channel), so
   // their channel pitch is padded to whole 128-byte lines: with the natural pitch H*W*2 B (= 1012.5 lines at 180x360) every odd
   // channel's box rows straddle two L2 lines.  xn / hcat keep the natural pitch.
@@ -92,6 +92,7 @@ void ensure_ws(ace_sfno& n, int B) {
   n.p_c1 = B * p.c1_elems(C);
   n.p_c2 = B * p.c2_elems(C);
   n.p_g = B * p.g_elems(C);
+  n.p_g2 = B * p.g2_elems(C);
   n.HWp = round_up(HW, 64);
   n.HWq = (long long)p.Kp * p.W;
   n.p_hp = (long long)B * C * n.HWq;
@@ -106,6 +107,7 @@ void ensure_ws(ace_sfno& n, int B) {
   n.c1.ensure(2 * (size_t)n.p_c1 * e);
   n.c2.ensure(2 * (size_t)n.p_c2 * e);
   n.g.ensure(2 * (size_t)n.p_g * e);
+  n.g2.ensure(2 * (size_t)n.p_g2 * e);
   n.T.ensure((size_t)n.p_act * sizeof(float));
   n.tP.ensure(2 * (size_t)n.p_tp * e);
   {
@@ -199,8 +201,13 @@ void forward(ace_sfno& n, const float* x, float* y, int B, cudaStream_t s) {
     } else {
       launch_diagonal_contract(n.c1.as<bf16>(), P_c1, w.spec.as<float>(), B, C, pf.L, pf.M, pf.Lp, n.c2.as<bf16>(), P_c2, s);
     }
-    run_gemm(sht_op_legendre_inv(pi, n.c2.as<bf16>(), P_c2, C, B, n.g.as<bf16>(), P_g), s);
-    run_gemm(sht_op_dft_inv(pi, n.g.as<bf16>(), P_g, C, B, n.T.as<float>(), act_b), s);
+    if (options().inv2) {
+      run_gemm(sht_op_legendre_inv2(pi, n.c2.as<bf16>(), P_c2, C, B, n.g2.as<bf16>(), n.p_g2), s);
+      run_gemm(sht_op_dft_inv2(pi, n.g2.as<bf16>(), n.p_g2, C, B, n.T.as<float>(), act_b), s);
+    } else {
+      run_gemm(sht_op_legendre_inv(pi, n.c2.as<bf16>(), P_c2, C, B, n.g.as<bf16>(), P_g), s);
+      run_gemm(sht_op_dft_inv(pi, n.g.as<bf16>(), P_g, C, B, n.T.as<float>(), act_b), s);
+    }
 
     // residual operand of this block: x_norm = a0 hP + s0 (deferred), the round trip (scale_res), or hP itself (no norm)
     const bf16* resid = scale_res ? xn : hP;

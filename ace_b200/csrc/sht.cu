@@ -78,7 +78,7 @@ GemmOp sht_op_legendre_inv(const ace_sht_plan& p, const bf16* c2, long long c2_p
   op.Z1 = p.M;
   op.Z2 = B;
   op.A = {c2, c2_plane, 1, 2LL * C, (long long)p.Lp * 2 * C, p.c2_elems(C)};  // MN-major
-  op.B = {p.pinv.as<bf16>(), p.pinv_plane, (long long)p.Lt, 1, (long long)p.K * p.Lt, 0};
+  op.B = {p.pinv.as<bf16>(), p.pinv_plane, (long long)p.Lt, 1, (long long)p.Kg * p.Lt, 0};
   op.k_lo_z1 = 1;  // coefficients with l < m are zero
   op.epi.flags = EPI_OUT_PLANES;
   op.epi.out = g;  // row = reim*C + c  ->  g[(2m + reim)][c][k]: affine in the row index
@@ -102,6 +102,41 @@ GemmOp sht_op_dft_inv(const ace_sht_plan& p, const bf16* g, long long g_plane, i
   op.epi.flags = EPI_OUT_F32;
   op.epi.outf = y;
   op.epi.f_z2 = y_batch_stride;
+  op.epi.f_m0 = p.W;
+  op.epi.f_n = 1;
+  return op;
+}
+
+GemmOp sht_op_legendre_inv2(const ace_sht_plan& p, const bf16* c2, long long c2_plane, int C, int B, bf16* g2, long long g2_plane) {
+  GemmOp op = sht_op_legendre_inv(p, c2, c2_plane, C, B, g2, g2_plane);
+  op.N = p.Kg;  // the table's rows k >= K are zero: the pad columns of g2 receive exact zeros and every epilogue chunk is full
+  op.epi.o_z2 = p.g2_elems(C);
+  op.epi.o_z1 = 2LL * C * p.Kg;              // even orders: k index 2 (m / 2) + reim
+  op.epi.o_z1b = (long long)p.Ke * C * p.Kg;  // odd orders start at k index Ke
+  op.epi.o_m0 = p.Kg;
+  return op;
+}
+
+GemmOp sht_op_dft_inv2(const ace_sht_plan& p, const bf16* g2, long long g2_plane, int C, int B, float* y, long long y_batch_stride) {
+  GemmOp op = make_gemm_op("sht.dft_inv");
+  op.M = C * p.Kg;
+  op.K = p.K2;
+  op.Z2 = B;
+  op.A = {g2, g2_plane, 1, (long long)C * p.Kg, 0, p.g2_elems(C)};  // MN-major
+  op.B = {p.idft2.as<bf16>(), p.idft2_plane, (long long)p.K2q, 1, 0, 0};
+  if (p.W % 2 == 0 && p.M > 1) {
+    op.N = p.W / 2;
+    op.bfly = 1;
+    op.k_split = p.Ke;
+  } else {
+    op.N = p.W;
+  }
+  op.epi.flags = EPI_OUT_F32;
+  op.epi.mdiv = p.Kg;  // row = c * Kg + k; rows k >= K are padding
+  op.epi.mrows = p.K;
+  op.epi.outf = y;
+  op.epi.f_z2 = y_batch_stride;
+  op.epi.f_m1 = (long long)p.K * p.W;
   op.epi.f_m0 = p.W;
   op.epi.f_n = 1;
   return op;
@@ -157,6 +192,14 @@ static void plan_build(ace_sht_plan& p, const double* fwd, const double* inv) {
   // (a pitch of 8 elements leaves most rows straddling two lines: 5 sectors and 2 tag look-ups per box row instead of 4 / 1)
   p.Wp = (int)round_up(W, 64);
   p.K2p = (int)round_up(2 * M, 64);
+  p.Kg = (int)round_up(K, 64);
+  {
+    const int Me = (M + 1) / 2, Mo = M / 2;
+    p.Ke = (int)round_up(2 * Me, 64);
+    p.K2 = p.Ke + 2 * Mo;
+    p.K2a = (int)round_up(p.K2, 8);
+    p.K2q = (int)round_up(p.K2, 64);
+  }
   {
     std::vector<bf16> hi((size_t)M * L * p.Kt, __float2bfloat16(0.f)), lo(hi.size(), __float2bfloat16(0.f));
     for (int m = 0; m < M; ++m)
@@ -168,11 +211,11 @@ static void plan_build(ace_sht_plan& p, const double* fwd, const double* inv) {
     upload_planes(p.wt, hi, lo, p.wt_plane);
   }
   {
-    std::vector<bf16> hi((size_t)M * K * p.Lt, __float2bfloat16(0.f)), lo(hi.size(), __float2bfloat16(0.f));
+    std::vector<bf16> hi((size_t)M * p.Kg * p.Lt, __float2bfloat16(0.f)), lo(hi.size(), __float2bfloat16(0.f));
     for (int m = 0; m < M; ++m)
       for (int l = 0; l < L; ++l)
         for (int k = 0; k < K; ++k) {
-          size_t d = ((size_t)m * K + k) * p.Lt + l;
+          size_t d = ((size_t)m * p.Kg + k) * p.Lt + l;
           host_split(inv[((size_t)m * L + l) * K + k], hi[d], lo[d]);
         }
     upload_planes(p.pinv, hi, lo, p.pinv_plane);
@@ -220,6 +263,25 @@ static void plan_build(ace_sht_plan& p, const double* fwd, const double* inv) {
         lo[d + 1] = __float2bfloat16_rn((float)(im - (double)__bfloat162float(h)));
       }
     upload_planes(p.idft, hi, lo, p.idft_plane);
+  }
+  {
+    // the same rows with the k axis split by the parity of m: k = 2 (m / 2) + reim for even m, Ke + 2 (m / 2) + reim for odd m
+    std::vector<bf16> hi((size_t)W * p.K2q, __float2bfloat16(0.f)), lo(hi.size(), __float2bfloat16(0.f));
+    for (int j = 0; j < W; ++j)
+      for (int m = 0; m < M && m <= W / 2; ++m) {
+        double wm = (m == 0 || m == nyq) ? 1.0 : 2.0;
+        double ang = two_pi * (double)(((long long)j * m) % W) / (double)W;
+        double re = wm * std::cos(ang);
+        double im = (m == 0 || m == nyq) ? 0.0 : -wm * std::sin(ang);
+        size_t d = (size_t)j * p.K2q + ((m & 1) ? p.Ke : 0) + 2 * (m >> 1);
+        bf16 h = __float2bfloat16_rn((float)re);
+        hi[d] = h;
+        lo[d] = __float2bfloat16_rn((float)(re - (double)__bfloat162float(h)));
+        h = __float2bfloat16_rn((float)im);
+        hi[d + 1] = h;
+        lo[d + 1] = __float2bfloat16_rn((float)(im - (double)__bfloat162float(h)));
+      }
+    upload_planes(p.idft2, hi, lo, p.idft2_plane);
   }
 }
 

@@ -17,9 +17,16 @@ struct ace_sht_plan {
   int K, W, L, M;      // nlat, nlon, lmax, mmax
   int Kp, Lp, Wp, K2p; // padded strides (Lp: multiple of 8 elements = 16 bytes; Kp, Wp, K2p: of 64 elements = one 128-byte line)
   int Kt, Lt;          // row pitches of the forward / inverse Legendre tables (multiples of 64 elements)
+  // inverse pair, second generation (sht_op_legendre_inv2 / sht_op_dft_inv2):
+  //   g2  [B][K2a][C][Kg]   Kg = nlat padded to 64 rows per channel (128-byte rows, no ragged chunk in the Legendre epilogue);
+  //                         k index of the inverse DFT = even orders first (2 (m / 2) + reim), odd orders from Ke on
+  //   idft2 planes [W][K2q] inverse DFT rows in that k order (rows j and j + W/2 differ only in the sign of the odd part)
+  int Kg, Ke, K2, K2a, K2q;
   unsigned long long table_id = 0;  // FNV-1a of the two host tables: equal ids <=> same grid/normalisation
   ace::DevBuf wt;       // planes [M][L][Kt]    P_l^m(cos th_k) w_k
-  ace::DevBuf pinv;     // planes [M][K][Lt]    P_l^m(cos th_k), l contiguous
+  ace::DevBuf pinv;     // planes [M][Kg][Lt]   P_l^m(cos th_k), l contiguous (rows k >= K are zero)
+  ace::DevBuf idft2;
+  long long idft2_plane;
   ace::DevBuf fdft;     // planes [2M][Wp]      forward DFT rows (2pi/W)(cos, -sin)
   ace::DevBuf idft;     // planes [W][K2p]      inverse DFT rows, Hermitian weights folded in
   long long wt_plane, pinv_plane, fdft_plane, idft_plane;
@@ -32,6 +39,7 @@ struct ace_sht_plan {
   long long c1_elems(int C) const { return (long long)L * M * 2 * C; }
   long long c2_elems(int C) const { return (long long)M * Lp * 2 * C; }
   long long g_elems(int C) const { return 2LL * M * C * K; }
+  long long g2_elems(int C) const { return (long long)K2a * C * Kg; }
 };
 
 namespace ace {
@@ -49,6 +57,10 @@ GemmOp sht_op_legendre_inv(const ace_sht_plan& p, const bf16* c2, long long c2_p
                            long long g_plane);
 GemmOp sht_op_dft_inv(const ace_sht_plan& p, const bf16* g, long long g_plane, int C, int B, float* y,
                       long long y_batch_stride);
+// Second-generation inverse pair (the networks' main path): padded, parity-split g2 and the butterfly inverse DFT
+//   y[j] = E[j] + O[j],  y[j + W/2] = E[j] - O[j]   (E / O = contributions of the even / odd orders m: half the multiplications)
+GemmOp sht_op_legendre_inv2(const ace_sht_plan& p, const bf16* c2, long long c2_plane, int C, int B, bf16* g2, long long g2_plane);
+GemmOp sht_op_dft_inv2(const ace_sht_plan& p, const bf16* g2, long long g2_plane, int C, int B, float* y, long long y_batch_stride);
 // Round-trip residual of SpectralConvS2 when the forward and inverse grids differ
 // (s2convolutions.py:81-85,170-173): inverse Legendre stage reading the c1 layout in place ...
 GemmOp sht_op_legendre_inv_from_c1(const ace_sht_plan& p, const bf16* c1, long long c1_plane, int C, int B, bf16* g,

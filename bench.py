@@ -11,7 +11,16 @@ Metric: simulated-years/day = steps/s * 86400 / 1460.
 
 N > 1 (torchrun, one rank per GPU): every rank advances its own ensemble member(s) -- the rollout is
 embarrassingly parallel -- and the only collective is one all_gather of the
-per-member global-mean diagnostics after the timed region; "scaling": "weak".
+per-member area-weighted global-mean diagnostics per 40-step window,
+INSIDE the timed region; "scaling": "weak".
+
+The timed region is repeated (--repeats, default 3; `ms_per_step` = median, all samples in `repeats`), a `sustained`
+leg times one simulated year (1460 steps) with the SM clock sampled, `step_roofline` gives the whole-step fractions
+of the measured HBM / bf16 peaks, and `gpu_eager_baseline` times the reference algorithm as PyTorch eager on the SAME
+GPU (cuFFT + cuBLAS + ATen: the oracle port moved to CUDA, TF32 off and on) -- SURVEY.md section 2.3's bar.
+
+--workload sht / inverse_sht: the reference's own micro-benchmark shapes (fme/sht_fix.py:232-327: 1024 fields of
+180x360, default lobatto grid) through ace_b200.RealSHT / InverseRealSHT, reported as HBM GB/s against the roofline.
 
 --impl reference times the reference algorithm's CPU path (the oracle port of the reference modules;
 the reference is pure Python and `import fme` is impossible in this image) on the host
@@ -126,18 +135,22 @@ def algorithmic(B):
         "sht.legendre_fwd": dict(flops=4.0 * B * C * M * L * K, bytes=2.0 * spec + leg, bound="hbm"),
         "sht.legendre_inv": dict(flops=4.0 * B * C * M * L * K, bytes=2.0 * spec + leg, bound="hbm"),
         "sht.dft_inv": dict(flops=0.0, bytes=act + spec, bound="hbm"),
-        "norm_split": dict(flops=0.0, bytes=2.0 * act, bound="hbm"),
+        "norm_split": dict(flops=0.0, bytes=2.0 * B * 44 * HW * 4, bound="hbm"),  # 44 input channels: fp32 read + split-plane write
     }
 
 
 def ncu_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full capture."""
-    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    try:
-        with open(path) as f:
-            return json.load(f).get(kernel)
-    except Exception:  # noqa: BLE001
-        return None
+    for name in ("r02_ncu_traffic.json", "ncu_traffic.json"):  # this round's capture first
+        path = os.path.join(ROOT, "profiles", name)
+        try:
+            with open(path) as f:
+                v = json.load(f).get(kernel)
+            if v is not None:
+                return v, name
+        except Exception:  # noqa: BLE001
+            continue
+    return None, None
 
 
 def sht_transform_bytes(B):
@@ -247,6 +260,151 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def time_gpu_eager(dev, in_names, out_names, means, stds, n_steps=5):
+    """The reference algorithm as PyTorch eager on the same GPU: the oracle port's modules moved to CUDA, i.e. exactly the torch
+    ops of the fme modules (torch.fft.rfft/irfft -> cuFFT, einsum / Conv2d -> cuBLAS / cuDNN, InstanceNorm2d, GELU -> ATen), with
+    TF32 off (fp32 FFMA GEMMs: the parity reference's arithmetic) and on (TORCH_ALLOW_TF32_CUBLAS_OVERRIDE=1 is what the
+    reference's own image runs, docker/Dockerfile:5).  A baseline measurement: none of this repository's kernels run here."""
+    import torch
+
+    log("gpu eager baseline: building the oracle net on the GPU")
+    onet = build_oracle_net().to(dev)
+    mi = torch.tensor([means[n] for n in in_names], device=dev).view(1, -1, 1, 1)
+    si = torch.tensor([stds[n] for n in in_names], device=dev).view(1, -1, 1, 1)
+    mo = torch.tensor([means[n] for n in out_names], device=dev).view(1, -1, 1, 1)
+    so = torch.tensor([stds[n] for n in out_names], device=dev).view(1, -1, 1, 1)
+    torch.manual_seed(1)
+    x0 = torch.randn(1, 44, *IMG, device=dev)
+    out = {}
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    try:
+        for label, tf32 in (("fp32", False), ("tf32", True)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            x = x0.clone()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.no_grad():
+                for it in range(2 + n_steps):
+                    if it == 2:
+                        ev0.record()
+                    y = onet((x - mi) / si) * so + mo
+                    x = torch.cat([x[:, :N_FORCING], y[:, :N_PROG]], dim=1)
+                ev1.record()
+            torch.cuda.synchronize(dev)
+            ms = ev0.elapsed_time(ev1) / n_steps
+            out[label] = {"ms_per_step": ms, "value": 86400.0 / (ms * 1e-3) / STEPS_PER_YEAR, "unit": "sim-years/day"}
+            log(f"gpu eager baseline ({label}): {ms:.2f} ms/step")
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    out["what"] = (f"reference algorithm (oracle port of the fme modules) as PyTorch eager on this GPU, B=1, {n_steps} steps after 2 warm-up, "
+                   "CUDA events; cuFFT + cuBLAS/cuDNN + ATen kernels only")
+    del onet
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_sht_workload(args):
+    """The reference's `sht` / `inverse_sht` micro-benchmarks (fme/sht_fix.py:232-327: RealSHT(180, 360) -- default lobatto grid,
+    lmax 179, mmax 181 -- on randn(1024, 180, 360); 10 iterations after 1 warm-up in the reference, CUDA events) through
+    ace_b200.RealSHT / InverseRealSHT (C ABI ace_sht_forward / ace_sht_inverse), plus the same op as PyTorch eager on this GPU."""
+    import torch
+
+    import ace_b200
+    from ace_b200 import _lib
+
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    nb, nlat, nlon = 1024, IMG[0], IMG[1]
+    K, Wm = args.steps, max(args.warmup, 3)
+    sht = ace_b200.RealSHT(nlat, nlon)
+    isht = ace_b200.InverseRealSHT(nlat, nlon)
+    L, M = sht.lmax, sht.mmax
+    torch.manual_seed(0)
+    x = torch.randn(nb, nlat, nlon, device=dev)
+    xh = sht(x)
+    inverse = args.workload == "inverse_sht"
+    fn, arg = (isht, xh) if inverse else (sht, x)
+    for _ in range(Wm):
+        fn(arg)
+    torch.cuda.synchronize()
+    l0 = _lib.launch_count()
+    fn(arg)
+    launches = _lib.launch_count() - l0
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    samples = []
+    for r in range(max(1, args.repeats)):
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(K):
+            y = fn(arg)
+        ev1.record()
+        torch.cuda.synchronize()
+        samples.append(ev0.elapsed_time(ev1) / K)
+    clocks = sampler.stop()
+    ms = sorted(samples)[len(samples) // 2]
+    by = nb * (nlat * nlon * 4 + L * M * 8) + M * L * nlat * 4  # SURVEY.md section 8(d): fields in + coefficients out + one table
+    pk = peaks()
+    # per-kernel split
+    _lib.set_option("profile", 1)
+    _lib.profile_report()
+    for _ in range(3):
+        fn(arg)
+    rep = _lib.profile_report()
+    _lib.set_option("profile", 0)
+    kernels = {k: round(t / c * 1e3, 1) for k, (c, t) in rep.items()}
+    # the same op as PyTorch eager on this GPU (oracle port moved to CUDA)
+    from oracle import sht as osht
+
+    o = osht.InverseRealSHT(nlat, nlon) if inverse else osht.RealSHT(nlat, nlon)
+    eager = {}
+    old = torch.backends.cuda.matmul.allow_tf32
+    try:
+        for label, tf32 in (("fp32", False), ("tf32", True)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            with torch.no_grad():
+                for _ in range(2):
+                    o(arg)
+                ev0.record()
+                for _ in range(5):
+                    o(arg)
+                ev1.record()
+            torch.cuda.synchronize()
+            t = ev0.elapsed_time(ev1) / 5
+            eager[label] = {"ms": t, "GBps": by / (t * 1e-3) / 1e9}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    # e2e: host fields in, host coefficients out
+    xh_host = (xh.cpu() if inverse else x.cpu()).pin_memory()
+    out_host = torch.empty_like(y, device="cpu").pin_memory()
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(3):
+        out_host.copy_(fn(xh_host.to(dev, non_blocking=True)), non_blocking=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    e2e_ms = ev0.elapsed_time(ev1) / 3
+    line = {
+        "metric": "sht_hbm_gbps", "value": by / (ms * 1e-3) / 1e9, "unit": "GB/s", "n_gpus": 1, "steps": K, "warmup": Wm, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16x3 (split-bf16 3-term products, fp32 accumulate; fp32 / complex64 I/O)", "data": "synthetic",
+        "config": {"workload": f"reference micro-benchmark `{args.workload}` (fme/sht_fix.py:232-327): 1024 fields of 180x360, lobatto grid, "
+                               f"lmax {L}, mmax {M}", "l2": "inputs larger than L2 (265 MB of fields per call)"},
+        "e2e": {"value": by / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(xh_host.numel() * xh_host.element_size()),
+                "d2h_bytes_per_step": int(out_host.numel() * out_host.element_size())},
+        "gpu_launches": int(launches * K), "launches_per_step": int(launches), "clocks": clocks,
+        "repeats": {"n": len(samples), "ms_per_step": [round(v, 4) for v in samples]},
+        "roofline": {"bound": "hbm", "achieved": by / (ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                     "frac": by / (ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None, "algorithmic_bytes": by,
+                     "note": "whole transform (layout conversion + DFT + Legendre kernels); peak of " + pk["source"]},
+        "kernels_us": kernels, "gpu_eager_baseline": eager, "cpu_baseline": None,
+    }
+    print(json.dumps(line), flush=True)
+
+
 # --------------------------------------------------------------------------------------------- B200 arm
 def run_b200(args):
     import torch
@@ -297,6 +455,7 @@ def run_b200(args):
     torch.cuda.synchronize(dev)
     launches_per_step = _lib.launch_count() - l1
     del l0
+    diag_launches_per_window = 1  # ace_weighted_moments (the all_gather is NCCL's kernel, not counted)
 
     # ---- device-resident timed region (CUDA graph replay per step, forcing already in HBM)
     log("graph capture + warm-up")
@@ -308,26 +467,66 @@ def run_b200(args):
     for t in range(Wm):
         static["forcing"].copy_(forcing_dev[t % n_forc_steps])
         graph.replay()
-    sampler = ClockSampler(local_rank)
-    barrier()
-    log(f"timed region: {K} steps")
-    sampler.start()
+    # per-window diagnostics: area-weighted global means of every output field of the window's
+    # last step (one ace_weighted_moments launch) and ONE all_gather of [B_local, n_out] across the ranks, every WINDOW steps
+    from ace_b200 import legendre as _leg
+    from ace_b200.metrics import LatLonOperations
+
+    _, wq, _ = _leg.nodes_and_weights("legendre-gauss", H)
+    area = torch.as_tensor(wq, dtype=torch.float32)[:, None].expand(H, Wd).contiguous()
+    ops = LatLonOperations(area)
+    WINDOW = 40
+    diag = {"n": 0, "last": None}
+
+    def window_diagnostics():
+        gm_local = ops.area_weighted_mean(static["out"])       # [B, n_out], one reduction kernel
+        diag["last"] = parallel.gather_members(gm_local)        # the rollout's only collective
+        diag["n"] += 1
+
+    def timed_steps(n):
+        """n steps on the current stream: forcing copy + CUDA-graph replay per step, diagnostics gather per window."""
+        for t in range(n):
+            static["forcing"].copy_(forcing_dev[t % n_forc_steps])
+            graph.replay()
+            if (t + 1) % WINDOW == 0 or t + 1 == n:
+                window_diagnostics()
+
+    window_diagnostics()  # warm-up of the reduction kernel / NCCL communicator, outside every timed region
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for t in range(K):
-        static["forcing"].copy_(forcing_dev[t % n_forc_steps])
-        graph.replay()
-    ev1.record()
-    barrier()
+    sampler = ClockSampler(local_rank)
+    samples = []
+    log(f"timed region: {args.repeats} x {K} steps")
+    sampler.start()
+    for r in range(max(1, args.repeats)):
+        barrier()
+        ev0.record()
+        timed_steps(K)
+        ev1.record()
+        barrier()
+        samples.append(parallel.max_over_ranks(ev0.elapsed_time(ev1), device=dev) / K)
     clocks = sampler.stop()
-    ms_total = parallel.max_over_ranks(ev0.elapsed_time(ev1), device=dev)
-    ms_per_step = ms_total / K
+    ms_sorted = sorted(samples)
+    ms_per_step = ms_sorted[len(ms_sorted) // 2]  # median of the repeats; every repeat times exactly K steps
     steps_per_s = world * B * 1e3 / ms_per_step  # every rank advances B members per step
     value = steps_per_s * 86400.0 / STEPS_PER_YEAR
-
-    # diagnostics reduction: the one collective of the data-parallel rollout (after the timed region)
-    gm = parallel.gather_members(static["out"].mean(dim=(2, 3)))  # [B_global, n_out] global means of the last step
+    gm = diag["last"]
     finite = bool(torch.isfinite(gm).all().item()) and gm.shape[0] == world * B
+
+    # ---- sustained leg: one simulated year (1460 steps) back to back, the clock the power cap settles at
+    sustained = None
+    if args.sustained_steps > 0:
+        log(f"sustained leg: {args.sustained_steps} steps")
+        s2 = ClockSampler(local_rank)
+        barrier()
+        s2.start()
+        ev0.record()
+        timed_steps(args.sustained_steps)
+        ev1.record()
+        barrier()
+        c2 = s2.stop()
+        ms_s = parallel.max_over_ranks(ev0.elapsed_time(ev1), device=dev) / args.sustained_steps
+        sustained = {"steps": args.sustained_steps, "ms_per_step": ms_s, "value": world * B * 1e3 / ms_s * 86400.0 / STEPS_PER_YEAR,
+                     "unit": "sim-years/day", "clocks": c2, "windows_gathered": args.sustained_steps // WINDOW}
 
     log(f"device-resident: {ms_per_step:.3f} ms/step; end-to-end loop")
     # ---- end-to-end through the public API with HOST buffers: H2D forcing + D2H outputs every step
@@ -345,12 +544,15 @@ def run_b200(args):
             done += m
 
     e2e_run(Wm)
-    barrier()
-    ev0.record()
-    e2e_run(K)
-    ev1.record()
-    barrier()
-    e2e_ms_per_step = parallel.max_over_ranks(ev0.elapsed_time(ev1), device=dev) / K
+    e2e_samples = []
+    for r in range(max(1, args.repeats)):
+        barrier()
+        ev0.record()
+        e2e_run(K)
+        ev1.record()
+        barrier()
+        e2e_samples.append(parallel.max_over_ranks(ev0.elapsed_time(ev1), device=dev) / K)
+    e2e_ms_per_step = sorted(e2e_samples)[len(e2e_samples) // 2]
     e2e_value = world * B * 1e3 / e2e_ms_per_step * 86400.0 / STEPS_PER_YEAR
     h2d = B * N_FORCING * HW * 4
     d2h = B * len(out_names) * HW * 4
@@ -389,7 +591,7 @@ def run_b200(args):
                 ach = a["flops"] / avg_s / 1e12
                 peak = pk["bf16_tflops_sustained"]
                 roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                            "frac": ach / peak, "traffic": ncu_traffic(dom),
+                            "frac": ach / peak, "traffic": ncu_traffic(dom)[0], "traffic_source": ncu_traffic(dom)[1],
                             "note": f"algorithmic fp32-equivalent FLOPs (2MNK); the kernel issues 3 bf16 MMAs per product, "
                                     f"so the tensor pipe runs at 3x this; peak = bf16 sustained of {pk['source']} "
                                     f"MEASURED_PEAKS.json; avg of {cnt} launches {avg_s*1e6:.1f} us (CUDA events)"}
@@ -397,7 +599,7 @@ def run_b200(args):
                 ach = a["bytes"] / avg_s / 1e9
                 peak = pk["hbm_gbs"]
                 roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                            "traffic": ncu_traffic(dom), "note": f"algorithmic bytes / avg of {cnt} launches ({avg_s*1e6:.1f} us); peak of {pk['source']}"}
+                            "traffic": ncu_traffic(dom)[0], "traffic_source": ncu_traffic(dom)[1], "note": f"algorithmic bytes / avg of {cnt} launches ({avg_s*1e6:.1f} us); peak of {pk['source']}"}
         # BASELINE.json second metric: SHT achieved HBM GB/s (forward transform = DFT + Legendre kernels)
         if "sht.dft_fwd" in rep and "sht.legendre_fwd" in rep:
             t_f = (rep["sht.dft_fwd"][1] + rep["sht.legendre_fwd"][1]) / rep["sht.dft_fwd"][0] * 1e-3
@@ -406,6 +608,29 @@ def run_b200(args):
             roofline_sht = {"bound": "hbm", "unit": "GB/s", "peak": pk["hbm_gbs"], "algorithmic_bytes": by,
                             "forward": {"achieved": by / t_f / 1e9, "frac": by / t_f / 1e9 / pk["hbm_gbs"], "us": t_f * 1e6},
                             "inverse": {"achieved": by / t_i / 1e9, "frac": by / t_i / 1e9 / pk["hbm_gbs"], "us": t_i * 1e6}}
+
+    # ---- whole-step roofline: the stable headline (3.70 GB and 1.26 TFLOP per B = 1 step)
+    step_roofline = None
+    if rank == 0:
+        pk = peaks()
+        step_bytes, step_flops = 3.70e9 * B, 1.26e12 * B
+        t_s = ms_per_step * 1e-3
+        step_roofline = {
+            "algorithmic_bytes": step_bytes, "algorithmic_flops": step_flops,
+            "hbm_frac": step_bytes / t_s / 1e9 / pk["hbm_gbs"], "hbm_peak_gbs": pk["hbm_gbs"],
+            "tensor_frac_fp32_equivalent": step_flops / t_s / 1e12 / pk["bf16_tflops_sustained"],
+            "tensor_frac_issued_mmas": 3.0 * step_flops / t_s / 1e12 / pk["bf16_tflops_sustained"],
+            "bf16_peak_tflops_sustained": pk["bf16_tflops_sustained"], "peaks": pk["source"],
+            "note": "per-GPU; issued MMAs = 3 bf16 products per fp32-equivalent product (split-bf16), DFT-as-GEMM work not counted",
+        }
+
+    # ---- PyTorch eager on the same GPU (rank 0, N = 1 only): the reference algorithm through cuFFT + cuBLAS + ATen
+    gpu_eager = None
+    if rank == 0 and world == 1 and not args.no_gpu_eager_baseline:
+        try:
+            gpu_eager = time_gpu_eager(dev, in_names, out_names, means, stds)
+        except Exception as e:  # noqa: BLE001  (a baseline must not take the bench line down)
+            gpu_eager = {"error": repr(e)[:300]}
 
     # ---- CPU baseline (rank 0, N = 1 only): reference algorithm on the host cores, bounded sample
     cpu_baseline = None
@@ -426,14 +651,21 @@ def run_b200(args):
                 "members_per_gpu": B, "global_members": B * world, "parallelism": f"ensemble-dp{world}",
                 "weights": "random init (reference initialisation, seed 0)",
                 "l2": "inputs larger than L2: one step streams 1.7 GB of dhconv weights + ~100 MB activation tensors per kernel (L2 = 126 MB); no explicit flush",
-                "timed": "CUDA-graph replay per step, forcing window resident in HBM",
+                "timed": "CUDA-graph replay per step, forcing window resident in HBM; per 40-step window one area-weighted-mean "
+                         "reduction of the outputs + one all_gather of [members, 50] diagnostics inside the timed region; "
+                         "value = median of the repeats",
             },
             "e2e": {"value": e2e_value, "unit": "sim-years/day", "ms_per_step": e2e_ms_per_step, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "path": "FusedStepper.rollout_host (C ABI ace_stepper_step per step): pinned host forcing in and all 50 output fields out every step, copies on side streams overlapping compute"},
-            "gpu_launches": int(launches_per_step * K), "launches_per_step": int(launches_per_step),
+            "gpu_launches": int((launches_per_step + 0) * K + diag_launches_per_window * ((K + WINDOW - 1) // WINDOW)),
+            "launches_per_step": int(launches_per_step),
+            "repeats": {"n": len(samples), "ms_per_step": [round(v, 4) for v in samples], "min": ms_sorted[0], "median": ms_per_step,
+                        "e2e_ms_per_step": [round(v, 4) for v in e2e_samples]},
+            "sustained": sustained, "step_roofline": step_roofline,
             "clocks": clocks, "roofline": roofline, "roofline_sht": roofline_sht, "kernel_time_shares": shares,
             "kernels": kernels,
-            "cpu_baseline": cpu_baseline, "outputs_finite": finite,
+            "gpu_eager_baseline": gpu_eager,
+            "cpu_baseline": cpu_baseline, "outputs_finite": finite, "diagnostic_windows": diag["n"],
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -448,9 +680,15 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=1, help="ensemble members per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager-baseline", action="store_true")
+    ap.add_argument("--repeats", type=int, default=3, help="repeats of the K-step timed region (median reported)")
+    ap.add_argument("--sustained-steps", type=int, default=STEPS_PER_YEAR, help="length of the sustained leg (0 = skip)")
+    ap.add_argument("--workload", default="rollout", choices=["rollout", "sht", "inverse_sht"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload in ("sht", "inverse_sht"):
+        run_sht_workload(args)
     else:
         run_b200(args)
 

@@ -72,6 +72,16 @@ class RealSHT(torch.nn.Module):
         self.nlat, self.nlon, self.grid, self.norm, self.csphase = nlat, nlon, grid, norm, csphase
         table, self.lmax, self.mmax = forward_table(nlat, nlon, lmax, mmax, grid, norm, csphase)
         self.weights = torch.from_numpy(table).float()
+        self._dev_tables = {}
+
+    def _table(self, device):
+        # plain attribute like fme/sht_fix.py:117 (which places it on get_device()); cached per device so that the GPU-eager
+        # baseline of bench.py does not re-upload it per call
+        if device.type == "cpu":
+            return self.weights
+        if device not in self._dev_tables:
+            self._dev_tables[device] = self.weights.to(device)
+        return self._dev_tables[device]
 
     def forward(self, x):
         assert x.shape[-2] == self.nlat and x.shape[-1] == self.nlon
@@ -81,8 +91,8 @@ class RealSHT(torch.nn.Module):
         out_shape = list(x.size())
         out_shape[-3] = self.lmax
         out_shape[-2] = self.mmax
-        xout = torch.zeros(out_shape, dtype=x.dtype)
-        w = self.weights.to(x.dtype)
+        xout = torch.zeros(out_shape, dtype=x.dtype, device=x.device)
+        w = self._table(x.device).to(x.dtype)
         xout[..., 0] = torch.einsum("...mk,mlk->...lm", x[..., : self.mmax, :, 0], w)
         xout[..., 1] = torch.einsum("...mk,mlk->...lm", x[..., : self.mmax, :, 1], w)
         return torch.view_as_complex(xout)
@@ -96,11 +106,19 @@ class InverseRealSHT(torch.nn.Module):
         self.nlat, self.nlon, self.grid, self.norm, self.csphase = nlat, nlon, grid, norm, csphase
         table, self.lmax, self.mmax = inverse_table(nlat, nlon, lmax, mmax, grid, norm, csphase)
         self.pct = torch.from_numpy(table).float()
+        self._dev_tables = {}
+
+    def _table(self, device):
+        if device.type == "cpu":
+            return self.pct
+        if device not in self._dev_tables:
+            self._dev_tables[device] = self.pct.to(device)
+        return self._dev_tables[device]
 
     def forward(self, x):
         assert x.shape[-2] == self.lmax and x.shape[-1] == self.mmax
         x = torch.view_as_real(x.transpose(-1, -2).contiguous()).float()
-        pct = self.pct.to(x.dtype)
+        pct = self._table(x.device).to(x.dtype)
         rl = torch.einsum("...ml,mlk->...km", x[..., 0], pct)
         im = torch.einsum("...ml,mlk->...km", x[..., 1], pct)
         x = torch.view_as_complex(torch.stack((rl, im), -1))
