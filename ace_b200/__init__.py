@@ -6,6 +6,7 @@ Public surface (mirrors the reference interfaces it replaces; see INTEGRATION.md
   B200SphericalFourierNeuralOperatorBuilder,
   ModuleSelector, DatasetInfo                  <- fme.ace.registry.sfno / fme.core.registry.module
   FusedStepper                                 <- device work of fme.core.step.single_module.step_with_adjustments
+  install_step_into_fme                        <- a StepSelector-registered SingleModuleStepConfig whose step is the fused library call
   metrics.LatLonOperations, spherical_power_spectrum <- fme.core.gridded_ops.LatLonOperations / fme.core.metrics (device reductions)
   HealpixSHT, HealpixISHT                      <- fme.core.cuhpx.sht.SHT / iSHT (HEALPix ring-order transform)
   parallel                                     <- data-parallel surface of fme.core.distributed (ensemble sharding, one gather)
@@ -21,6 +22,7 @@ from .registry import (  # noqa: F401
 from .sfno import SphericalFourierNeuralOperatorNet  # noqa: F401
 from .sht import InverseRealSHT, RealSHT, patch_torch_harmonics  # noqa: F401
 from .stepper import FusedStepper  # noqa: F401
+from .fme_step import install_step_into_fme  # noqa: F401
 from .corrector import AtmosphereCorrector  # noqa: F401
 from . import parallel  # noqa: F401
 from . import metrics  # noqa: F401
