@@ -141,6 +141,7 @@ SIGNATURES = {
     "ace_hpx_inverse": (_I, [_VP, _I, _VP, _VP, _LL, _VP]),
     "ace_weighted_moments": (_I, [_VP, _VP, _VP, _LL, _LL, _VP, _VP]),
     "ace_zonal_mean": (_I, [_VP, _LL, _I, _I, _VP, _VP]),
+    "ace_time_sum": (_I, [_VP, _I, _LL, _I, _LL, _LL, _VP, _VP]),
     "ace_power_spectrum": (_I, [_VP, _LL, _I, _I, _VP, _VP]),
 }
 

@@ -80,10 +80,39 @@ __global__ void __launch_bounds__(kT) power_spectrum_kernel(const float2* __rest
   if ((threadIdx.x & 31) == 0) out[row] = (float)s;
 }
 
+// acc[i] += sum over (a, b) of x[a * stride_a + b * stride_b + i]: the window's contribution to the time-mean maps
+// (fme/ace/aggregator/inference/time_mean.py:103-124: tensor[:, time_slice].sum(dim=time).sum(dim=sample) added to a running
+// fp32 map).  The window sum is formed in fp64 and rounded once before it joins the fp32 running sum.
+__global__ void __launch_bounds__(kT) time_sum_kernel(const float* __restrict__ x, int na, long long stride_a, int nb,
+                                                     long long stride_b, long long n, float* __restrict__ acc) {
+  for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < n; i += (long long)gridDim.x * kT) {
+    double s = 0.0;
+    for (int a = 0; a < na; ++a) {
+      const float* xa = x + a * stride_a + i;
+      double sa = 0.0;
+      for (int b = 0; b < nb; ++b) sa += (double)__ldg(xa + b * stride_b);
+      s += sa;
+    }
+    acc[i] += (float)s;
+  }
+}
+
 }  // namespace
 }  // namespace ace
 
 using namespace ace;
+
+extern "C" int ace_time_sum(const float* x_dev, int n_outer, long long stride_outer, int n_inner, long long stride_inner,
+                            long long n_elems, float* acc_dev, void* stream) {
+  ACE_API_BEGIN
+  ACE_REQUIRE(x_dev && acc_dev && n_outer > 0 && n_inner > 0 && n_elems > 0, "ace_time_sum: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  ProfileScope prof("time_sum", s);
+  const int grid = (int)std::min<long long>((n_elems + kT - 1) / kT, 148 * 8);
+  time_sum_kernel<<<grid, kT, 0, s>>>(x_dev, n_outer, stride_outer, n_inner, stride_inner, n_elems, acc_dev);
+  after_launch("time_sum");
+  ACE_API_END
+}
 
 extern "C" int ace_weighted_moments(const float* x_dev, const float* t_dev, const float* weights_dev, long long nfields,
                                     long long hw, double* out_dev, void* stream) {

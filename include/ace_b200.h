@@ -297,6 +297,12 @@ int ace_hpx_inverse(ace_sht_plan* plan, int nside, const float* coeffs_dev, floa
  * zero weight contribute nothing even if NaN (metrics.py:56-58). */
 int ace_weighted_moments(const float* x_dev, const float* t_dev, const float* weights_dev, long long nfields,
                          long long hw, double* out_dev, void* stream);
+/* Time-mean maps (fme/ace/aggregator/inference/time_mean.py:103-124 `_add_or_initialize_time_mean`): one pass over a
+ * window adds its sum over two leading axes (sample, time) to a running fp32 map:
+ *   acc_dev[i] += sum_{a < n_outer, b < n_inner} x_dev[a * stride_outer + b * stride_inner + i],   i < n_elems
+ * (strides in elements; for a window tensor [sample][time][field][H][W]: n_elems = fields * H * W). */
+int ace_time_sum(const float* x_dev, int n_outer, long long stride_outer, int n_inner, long long stride_inner,
+                 long long n_elems, float* acc_dev, void* stream);
 /* zonal mean (mean over longitude; gridded_ops.py:313-315): x_dev float32 [nfields][h][w] -> out_dev [nfields][h] */
 int ace_zonal_mean(const float* x_dev, long long nfields, int h, int w, float* out_dev, void* stream);
 /* fme/core/metrics.py:388-408 spherical_power_spectrum: complex64 [nfields][lmax][mmax] -> float32 [nfields][lmax] */

@@ -66,3 +66,44 @@ def test_power_spectrum_matches_oracle():
     ref = om.spherical_power_spectrum(x, osht.RealSHT(48, 96, grid="legendre-gauss"))
     assert got.shape == ref.shape == (3, 5, 48)
     torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-5 * float(ref.max()))
+
+
+def test_window_aggregators_match_oracle():
+    """Row f3: time-mean maps and per-step reduced metrics accumulated over three windows on the device vs the oracle
+    restatement of fme/ace/aggregator/inference/{time_mean,reduced}.py (itself pinned to the reference's own class bodies)."""
+    from ace_b200 import metrics as bm
+    from oracle import aggregator as oa
+
+    names = ["b", "a", "c"]
+    B, T, H, W = 2, 4, 18, 36
+    g = torch.Generator().manual_seed(7)
+    lat = torch.linspace(-85, 85, H)
+    w = torch.cos(torch.deg2rad(lat))[:, None].expand(H, W).contiguous()
+    ops = bm.LatLonOperations(w)
+    tm_dev, tm_ref = bm.TimeMeanAggregator(names), oa.TimeMean()
+    ma_dev = bm.MeanAggregator(ops, names, n_timesteps=3 * T)
+    refs = {k: oa.ReducedMetric(fn, 3 * T) for k, fn in oa.mean_aggregator_metrics(w).items()}
+    for k in range(3):
+        gen = torch.randn(B, T, len(names), H, W, generator=g) * 3.0 + 1.5
+        tgt = gen + 0.3 * torch.randn(B, T, len(names), H, W, generator=g)
+        tm_dev.record_batch(gen.cuda(), i_time_start=k * T)
+        ma_dev.record_batch(tgt.cuda(), gen.cuda(), i_time_start=k * T)
+        gd = {n: gen[:, :, i] for i, n in enumerate(names)}
+        td = {n: tgt[:, :, i] for i, n in enumerate(names)}
+        tm_ref.record_batch(gd, k * T)
+        for r in refs.values():
+            r.record(td, gd, k * T)
+    got, want = tm_dev.get_data(), tm_ref.get_data()
+    assert list(got) == list(want) == sorted(names)
+    for n in names:
+        torch.testing.assert_close(got[n].cpu(), want[n], rtol=2e-6, atol=2e-6)
+    series = ma_dev.get()
+    assert set(series) == set(refs)
+    for m, r in refs.items():
+        ref = r.get()
+        for n in names:
+            torch.testing.assert_close(series[m][n].cpu(), ref[n], rtol=5e-6, atol=5e-6)
+    import ace_b200
+
+    with pytest.raises(ace_b200.AceError):
+        tm_dev.record_batch(torch.zeros(B, T, len(names), H, W))  # CPU tensor: no fallback
