@@ -221,6 +221,29 @@ class _SpectralConvS2(nn.Module):
         """True when ``weight`` already is the dense [1, L, C, C, 2] operator the device library takes."""
         return self.num_groups == 1 and self.lora_rank == 0 and not self.preserve_global_mean and self.pre_proj is None
 
+    @property
+    def is_grouped_native(self):
+        """True when the grouped operator is multiplied as its diagonal blocks on the device (1 / G of the dense operator's weight
+        bytes and multiplications -- the property the reference's only in-tree performance assertion checks,
+        fme/core/models/conditional_sfno/test_sfnonet.py:262-284): groups of 64 or 128 channels, no channel bottleneck."""
+        return self.num_groups > 1 and self.pre_proj is None and (self.spectral_channels // self.num_groups) in (64, 128)
+
+    def grouped_weight(self):
+        """[G, L, C/G, C/G, 2] fp32: the diagonal blocks with the LoRA update merged (per group) and, for
+        ``preserve_global_mean``, the l = 0 blocks replaced by the identity."""
+        with torch.no_grad():
+            w = self.weight.detach()
+            if self.lora_rank > 0:
+                a = torch.view_as_complex(self.lora_A.double().contiguous())
+                b = torch.view_as_complex(self.lora_B.double().contiguous())
+                w = torch.view_as_real(torch.view_as_complex(w.double().contiguous()) + self.lora_scaling * torch.einsum("gxor,gxri->gxoi", b, a))
+            w = w.float().clone() if w.data_ptr() == self.weight.data_ptr() else w.float()
+            if self.preserve_global_mean:
+                cg = w.shape[2]
+                w[:, 0] = 0.0
+                w[:, 0, :, :, 0] = torch.eye(cg, device=w.device)
+            return w.contiguous()
+
     def sources(self):
         return [p for p in (self.weight, self.lora_A, self.lora_B, getattr(self.pre_proj, "weight", None),
                             getattr(self.post_proj, "weight", None)) if p is not None]
@@ -416,7 +439,7 @@ class SphericalFourierNeuralOperatorNet(nn.Module):
                 derived[prefix + ".weight"] = (mod.sources(), mod.effective_weight)
                 hidden.update((prefix + ".lora_down.weight", prefix + ".lora_up.weight"))
             elif isinstance(mod, _SpectralConvS2) and not mod.is_plain:
-                derived[prefix + ".weight"] = (mod.sources(), mod.effective_weight)
+                derived[prefix + ".weight"] = (mod.sources(), mod.grouped_weight if mod.is_grouped_native else mod.effective_weight)
                 hidden.update(prefix + "." + n for n in ("lora_A", "lora_B", "pre_proj.weight", "post_proj.weight"))
         out = []
         for name, prm in self.named_parameters():

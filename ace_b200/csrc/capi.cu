@@ -20,6 +20,9 @@ Options& options() {
   static Options o = [] {
     Options x;
     if (const char* e = getenv("ACE_B200_PDL")) x.pdl = atoi(e) ? 1 : 0;
+    // every GEMM on the SIMT kernel: for compute-sanitizer racecheck / synccheck runs (tools/sanitize.sh), which do not model
+    // the asynchronous tcgen05 / TMA proxies
+    if (const char* e = getenv("ACE_B200_FORCE_SIMT")) x.force_simt = atoi(e) ? 1 : 0;
     return x;
   }();
   return o;
@@ -84,6 +87,8 @@ extern "C" int ace_set_option(const char* key, int value) {
     options().pdl = value ? 1 : 0;
   } else if (!strcmp(key, "dbg")) {
     options().dbg = value;
+  } else if (!strcmp(key, "l2_persist")) {
+    options().l2_persist = value ? 1 : 0;
   } else if (!strcmp(key, "inv2")) {
     options().inv2 = value ? 1 : 0;
   } else if (!strcmp(key, "tile_list")) {

@@ -57,8 +57,9 @@ struct RtBuf {
 
 struct CBlockW {
   ClnW n0, n1;
-  DevBuf spec;  // planes [L][2 (re, im)][C][Cp]
+  DevBuf spec;  // planes [L][2 (re, im)][C][Cp]; grouped (groups > 1): [L][2][C][cgp], row o holds its group's C / groups inputs
   long long spec_plane = 0;
+  int groups = 1;
   DevBuf fbias, skip_total;
   ConvW skip, fc1, fc2;
 };
@@ -321,7 +322,10 @@ void forward(ace_csfno& n, const float* x, const float* scalar, const float* lab
       resid = n.rr.as<bf16>();
     }
     // complex GEMM per degree l over the orders m <= l (s2convolutions.py:118-136)
-    run_gemm(dhconv_op(n.c1.as<bf16>(), P_c1, w.spec.as<bf16>(), w.spec_plane, pf, C, C, B, n.c2.as<bf16>(), P_c2), s);
+    if (w.groups > 1)
+      run_gemm(dhconv_grouped_op(n.c1.as<bf16>(), P_c1, w.spec.as<bf16>(), w.spec_plane, pf, C, w.groups, B, n.c2.as<bf16>(), P_c2), s);
+    else
+      run_gemm(dhconv_op(n.c1.as<bf16>(), P_c1, w.spec.as<bf16>(), w.spec_plane, pf, C, C, B, n.c2.as<bf16>(), P_c2), s);
     if (options().inv2) {
       run_gemm(sht_op_legendre_inv2(pi, n.c2.as<bf16>(), P_c2, C, B, n.g2.as<bf16>(), n.p_g2), s);
       run_gemm(sht_op_dft_inv2(pi, n.g2.as<bf16>(), n.p_g2, C, B, n.T.as<float>(), act_b), s);
@@ -479,12 +483,25 @@ extern "C" int ace_csfno_set_param(ace_csfno* net, const char* name, const float
       ACE_REQUIRE(set_cln_param(b.n1, c, rest.substr(6), data_dev, numel, name, s), "ace_csfno_set_param: unhandled parameter '%s'", name);
     } else if (rest == "filter.filter.bias") vecC(b.fbias);
     else if (rest == "filter.filter.weight") {
-      // [G = 1][L][O][I][2]  (s2convolutions.py:229-236)
-      ACE_REQUIRE(numel == (long long)C * C * c.lmax * 2, "%s: expected %lld elements, got %lld", name, (long long)C * C * c.lmax * 2, numel);
-      const int Cp = (int)round_up(C, 8);
-      b.spec_plane = (long long)c.lmax * 2 * C * Cp;
-      b.spec.ensure(2 * (size_t)b.spec_plane * sizeof(bf16));
-      launch_prep_dhconv_cplx_strided(data_dev, C, C, c.lmax, (long long)C * C, C, 1, Cp, b.spec.as<bf16>(), b.spec_plane, s);
+      // [G][L][O / G][I / G][2]  (s2convolutions.py:229-236); G = 1: the dense operator, G > 1: the diagonal blocks of a grouped one
+      const long long dense = (long long)C * C * c.lmax * 2;
+      const int G = (numel > 0 && dense % numel == 0) ? (int)(dense / numel) : 0;
+      ACE_REQUIRE(G >= 1 && C % G == 0, "%s: expected %lld elements (or 1/G of it for a grouped filter), got %lld", name, dense, numel);
+      if (G == 1) {
+        const int Cp = (int)round_up(C, 8);
+        b.spec_plane = (long long)c.lmax * 2 * C * Cp;
+        b.spec.ensure(2 * (size_t)b.spec_plane * sizeof(bf16));
+        launch_prep_dhconv_cplx_strided(data_dev, C, C, c.lmax, (long long)C * C, C, 1, Cp, b.spec.as<bf16>(), b.spec_plane, s);
+      } else {
+        const int cg = C / G, cgp = (int)round_up(cg, 8);
+        ACE_REQUIRE(cg == 64 || cg == 128, "%s: grouped filters are multiplied natively for 64 or 128 channels per group (got %d); fold "
+                    "other group sizes into the dense operator", name, cg);
+        b.spec_plane = (long long)c.lmax * 2 * C * cgp;
+        b.spec.release();  // the grouped planes are 1/G of the dense ones: do not keep a dense-sized buffer around
+        b.spec.ensure(2 * (size_t)b.spec_plane * sizeof(bf16));
+        launch_prep_dhconv_grouped(data_dev, G, cg, c.lmax, cgp, b.spec.as<bf16>(), b.spec_plane, s);
+      }
+      b.groups = G;
     } else if (rest == "inner_skip.weight") set_conv_w(b.skip, data_dev, numel, name, s);
     else if (rest == "inner_skip.bias") set_conv_b(b.skip, data_dev, numel, name, s);
     else if (rest == "mlp.fwd.0.weight") set_conv_w(b.fc1, data_dev, numel, name, s);

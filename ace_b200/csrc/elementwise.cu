@@ -98,6 +98,27 @@ __global__ void __launch_bounds__(kThreads) prep_dhconv_cplx_kernel(const float*
   }
 }
 
+// grouped dhconv weights [G][L][cg (o')][cg (i')][2] fp32 -> planes [L][2][C = G cg][cgp]: row o = g cg + o' keeps its own group's inputs
+__global__ void __launch_bounds__(kThreads) prep_dhconv_grouped_kernel(const float* __restrict__ w, int G, int cg, int L, int cgp,
+                                                                      bf16* __restrict__ dst, long long plane) {
+  const int C = G * cg;
+  const long long total = (long long)L * 2 * C * cgp;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    int i = (int)(idx % cgp);
+    long long t = idx / cgp;
+    int o = (int)(t % C);
+    t /= C;
+    int part = (int)(t & 1);
+    int l = (int)(t >> 1);
+    const int g = o / cg, o2 = o - g * cg;
+    float v = (i < cg) ? w[(((((long long)g * L + l) * cg + o2) * cg) + i) * 2 + part] : 0.f;
+    bf16 h, lo;
+    split_bf16(v, h, lo);
+    dst[idx] = h;
+    dst[idx + plane] = lo;
+  }
+}
+
 // one thread per (b, l, m, o); x is broadcast across the o threads of a warp
 __global__ void __launch_bounds__(kThreads) diagonal_contract_kernel(const bf16* __restrict__ c1, long long c1_plane,
                                                                     const float* __restrict__ w, int B, int C, int L,
@@ -132,40 +153,60 @@ __global__ void __launch_bounds__(kThreads) diagonal_contract_kernel(const bf16*
   }
 }
 
-__global__ void __launch_bounds__(kThreads) spec_planes_to_complex_kernel(const bf16* __restrict__ c1, long long plane,
-                                                                         int C, int L, int M, float* __restrict__ out) {
-  // out[c][l][m][2]; consecutive threads walk c (coalesced plane reads); writes are strided but the
-  // standalone transform API is not on the network hot path.
-  const long long total = (long long)L * M * C;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(idx % C);
-    long long lm = idx / C;
-    const bf16* p = c1 + lm * 2 * C;
-    float re = __bfloat162float(p[c]) + __bfloat162float(p[c + plane]);
-    float im = __bfloat162float(p[C + c]) + __bfloat162float(p[C + c + plane]);
-    float2* o = reinterpret_cast<float2*>(out) + (long long)c * L * M + lm;
-    *o = make_float2(re, im);
+// Layout converters of the standalone transform API: 32 x 32 tiles transposed through shared memory so that both the plane
+// side (channel contiguous) and the complex side (order m contiguous) are accessed in 128-256 byte runs.
+// c1 planes [L*M][2C] -> out complex64 [C][L*M]
+__global__ void __launch_bounds__(256) spec_planes_to_complex_kernel(const bf16* __restrict__ c1, long long plane, int C,
+                                                                    long long LM, float* __restrict__ out) {
+  __shared__ float2 tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long lm0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = ty; i < 32; i += 8) {
+    const long long lm = lm0 + i;
+    const int c = c0 + tx;
+    float2 v = make_float2(0.f, 0.f);
+    if (lm < LM && c < C) {
+      const bf16* p = c1 + lm * 2 * C;
+      v.x = __bfloat162float(p[c]) + __bfloat162float(p[c + plane]);
+      v.y = __bfloat162float(p[C + c]) + __bfloat162float(p[C + c + plane]);
+    }
+    tile[i][tx] = v;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i;
+    const long long lm = lm0 + tx;
+    if (c < C && lm < LM) reinterpret_cast<float2*>(out)[(long long)c * LM + lm] = tile[tx][i];
   }
 }
 
-__global__ void __launch_bounds__(kThreads) spec_complex_to_planes_kernel(const float* __restrict__ in, int C, int L,
-                                                                         int M, int Lp, bf16* __restrict__ c2,
-                                                                         long long plane) {
-  const long long total = (long long)M * L * C;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(idx % C);
-    long long t = idx / C;
-    int l = (int)(t % L);
-    int m = (int)(t / L);
-    float2 v = reinterpret_cast<const float2*>(in)[((long long)c * L + l) * M + m];
-    bf16* y = c2 + ((long long)m * Lp + l) * 2 * C;
-    bf16 h, lo;
-    split_bf16(v.x, h, lo);
-    y[c] = h;
-    y[c + plane] = lo;
-    split_bf16(v.y, h, lo);
-    y[C + c] = h;
-    y[C + c + plane] = lo;
+// in complex64 [C][L][M] -> c2 planes [M][Lp][2C]; grid (M tiles, C tiles, L)
+__global__ void __launch_bounds__(256) spec_complex_to_planes_kernel(const float* __restrict__ in, int C, int L, int M, int Lp,
+                                                                    bf16* __restrict__ c2, long long plane) {
+  __shared__ float2 tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int m0 = blockIdx.x * 32, c0 = blockIdx.y * 32, l = blockIdx.z;
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, m = m0 + tx;
+    float2 v = make_float2(0.f, 0.f);
+    if (c < C && m < M) v = reinterpret_cast<const float2*>(in)[((long long)c * L + l) * M + m];
+    tile[i][tx] = v;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int m = m0 + i, c = c0 + tx;
+    if (m < M && c < C) {
+      const float2 v = tile[tx][i];
+      bf16* y = c2 + ((long long)m * Lp + l) * 2 * C;
+      bf16 h, lo;
+      split_bf16(v.x, h, lo);
+      y[c] = h;
+      y[c + plane] = lo;
+      split_bf16(v.y, h, lo);
+      y[C + c] = h;
+      y[C + c + plane] = lo;
+    }
   }
 }
 
@@ -373,6 +414,12 @@ void launch_prep_dhconv_cplx_strided(const float* w, int Cin, int Cout, int L, l
   after_launch("prep_dhconv_cplx");
 }
 
+void launch_prep_dhconv_grouped(const float* w, int G, int cg, int L, int cgp, bf16* dst, long long plane, cudaStream_t stream) {
+  ProfileScope prof("prep_dhconv", stream);
+  prep_dhconv_grouped_kernel<<<grid_for((long long)L * 2 * G * cg * cgp, kThreads), kThreads, 0, stream>>>(w, G, cg, L, cgp, dst, plane);
+  after_launch("prep_dhconv_grouped");
+}
+
 void launch_diagonal_contract(const bf16* c1, long long c1_plane, const float* w, int B, int C, int L, int M, int Lp,
                               bf16* c2, long long c2_plane, cudaStream_t stream) {
   ProfileScope prof("diagonal_contract", stream);
@@ -382,13 +429,15 @@ void launch_diagonal_contract(const bf16* c1, long long c1_plane, const float* w
 
 void launch_spec_planes_to_complex(const bf16* c1, long long plane, int C, int L, int M, float* out, cudaStream_t stream) {
   ProfileScope prof("spec_planes_to_complex", stream);
-  spec_planes_to_complex_kernel<<<grid_for((long long)L * M * C, kThreads), kThreads, 0, stream>>>(c1, plane, C, L, M, out);
+  const long long LM = (long long)L * M;
+  spec_planes_to_complex_kernel<<<dim3((unsigned)((LM + 31) / 32), (unsigned)((C + 31) / 32)), 256, 0, stream>>>(c1, plane, C, LM, out);
   after_launch("spec_planes_to_complex");
 }
 
 void launch_spec_complex_to_planes(const float* in, int C, int L, int M, int Lp, bf16* c2, long long plane, cudaStream_t stream) {
   ProfileScope prof("spec_complex_to_planes", stream);
-  spec_complex_to_planes_kernel<<<grid_for((long long)L * M * C, kThreads), kThreads, 0, stream>>>(in, C, L, M, Lp, c2, plane);
+  ACE_REQUIRE(L <= 65535 && (C + 31) / 32 <= 65535, "spec_complex_to_planes: extent too large");
+  spec_complex_to_planes_kernel<<<dim3((unsigned)((M + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)L), 256, 0, stream>>>(in, C, L, M, Lp, c2, plane);
   after_launch("spec_complex_to_planes");
 }
 

@@ -88,8 +88,13 @@ struct GemmOp {
   //   A holds [Ar | Ai] along its k axis (K + K columns), B holds two real matrices Br, Bi of N x K each (Bi = B + b_part
   //   elements), and the op computes the M x 2N real result   D[:, 0:N] = Ar Br - Ai Bi,   D[:, N:2N] = Ar Bi + Ai Br
   //   (column n of the imaginary part is stored at column index n + N).
+  //   Grouped form (group_n > 0, dhconv with filter_num_groups > 1): the N columns are split into groups of group_n
+  //   columns and group g only contracts the k range [g * group_n, g * group_n + K) of each part of A (K = inputs per
+  //   group; the imaginary part of A starts a_part_k columns after the real part instead of K): a block-diagonal
+  //   operator stored and multiplied as its diagonal blocks.
   int cplx;
   long long a_part, b_part;
+  int group_n, a_part_k;
   // Butterfly mode (inverse longitude DFT of an even-length grid, sht.cu): the k axis is split at k_split,
   //   E[m][n] = sum_{k < k_split} A[m][k] B[n][k],   O[m][n] = sum_{k >= k_split} A[m][k] B[n][k],     n in [0, N)
   //   D[m][n] = E + O,   D[m][n + N] = E - O

@@ -49,7 +49,13 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const __grid_constant__ G
       int m = m0 + mm, k = k0 + kk;
       float v = 0.f;
       if (m < op.M && k < op.K && k >= k_lo) {
-        if (op.cplx != 1) {
+        if (op.cplx == 2 && op.group_n) {
+          // grouped: this tile's columns belong to group g, which contracts k range [g * group_n, + Kh) of each part
+          const int Nh = op.N >> 1, Kh = op.K >> 1;
+          const int g = (n0 % Nh) / op.group_n, ri = k >= Kh, i2 = k - ri * Kh;
+          const bf16* p = A + (long long)m * op.A.s_row + ((long long)ri * op.a_part_k + (long long)g * op.group_n + i2) * op.A.s_k;
+          v = __bfloat162float(p[0]) + __bfloat162float(p[op.A.plane]);
+        } else if (op.cplx != 1) {
           // (cplx == 2: A is [Ar | Ai] along k, i.e. a plain matrix of the doubled K extent)
           const bf16* p = A + (long long)m * op.A.s_row + (long long)k * op.A.s_k;
           v = __bfloat162float(p[0]) + __bfloat162float(p[op.A.plane]);
@@ -138,6 +144,8 @@ void run_gemm_simt(const GemmOp& op_in, cudaStream_t stream) {
       op.M *= 2;
     } else {
       ACE_REQUIRE(!op.n_lo_z1 && !op.n_hi_z1, "gemm %s: complex mode 2 takes no triangular N range", op.name);
+      ACE_REQUIRE(op.group_n == 0 || (op.group_n % BN == 0 && op.N % op.group_n == 0 && op.K <= op.group_n),
+                  "gemm %s: grouped complex mode needs groups of a multiple of %d columns", op.name, BN);
       op.N *= 2;
     }
     op.K *= 2;

@@ -108,7 +108,7 @@ struct Cfg {
 };
 
 struct Tile {
-  int m0, n_begin, n_count, n_end, z1, z2, k_begin, num_kc;
+  int m0, n_begin, n_count, n_end, z1, z2, k_begin, num_kc, tn;
 };
 
 template <int BN, int BK, int TILE_M = 128>
@@ -137,6 +137,7 @@ __device__ __forceinline__ bool decode_tile(const UmmaParams& p, long long t, Ti
   const int n_lo = op.n_lo_z1 ? ti.z1 : 0;
   const int n_hi = op.n_hi_z1 ? min(op.N, ti.z1 + 1) : op.N;
   const int k_lo = op.k_lo_z1 ? ti.z1 : 0;
+  ti.tn = tn;
   ti.m0 = tm * TILE_M;  // pair mode: the caller adds 128 * cluster rank
   ti.n_begin = max(tn * BN, (n_lo / 16) * 16);
   ti.n_end = min(tn * BN + BN, n_hi);
@@ -668,7 +669,9 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
 #pragma unroll
                 for (int pl = 0; pl < 2; ++pl) {
                   if constexpr (C::CT) {
-                    ptx::tma_load_5d(sA + (2 * part + pl) * C::A_PLANE, &p.tmA, fb, k0 + part * op.K, ti.m0, az1, az2, pl);
+                    // grouped form: n tile = group (BN == group_n), which contracts its own k range of each part of A
+                    const int ka = k0 + part * (op.group_n ? op.a_part_k : op.K) + (op.group_n ? ti.tn * op.group_n : 0);
+                    ptx::tma_load_5d(sA + (2 * part + pl) * C::A_PLANE, &p.tmA, fb, ka, ti.m0, az1, az2, pl);
                     ptx::tma_load_5d(sBc + (2 * part + pl) * C::B_PLANE, &p.tmB, fb, k0, ti.n_begin, bz1, part, pl);
                   } else {
                     ptx::tma_load_5d(sA + (2 * part + pl) * C::A_PLANE, &p.tmA, fb, k0, ti.m0, az1, part, pl);
@@ -960,7 +963,8 @@ void launch(const GemmOp& op, cudaStream_t stream) {
   const CUtensorMapSwizzle kswz = (C::BK == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   if (C::CT) {
     // [Ar | Ai] along k: one map over 2K columns; {Br, Bi}: the part index rides on the z2 axis of the B map
-    make_tmap(&p.tmA, op.A, false, op.M, 2LL * op.K, op.Z1, op.Z2, C::BK, 128, kswz, &p.a_z1_on, &p.a_z2_on, op.name);
+    make_tmap(&p.tmA, op.A, false, op.M, op.group_n ? 2LL * op.a_part_k : 2LL * op.K, op.Z1, op.Z2, C::BK, 128, kswz, &p.a_z1_on, &p.a_z2_on,
+              op.name);
     Operand b = op.B;
     b.s_z2 = op.b_part;
     make_tmap(&p.tmB, b, false, op.N, op.K, op.Z1, 2, C::BK, C::BN, kswz, &p.b_z1_on, &p.b_z2_on, op.name);
@@ -994,17 +998,39 @@ void launch(const GemmOp& op, cudaStream_t stream) {
   cfg.blockDim = dim3(kThreadsUmma);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[3];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = (options().pdl && !C::PAIR) ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   if (C::PAIR) {
-    attr[1].id = cudaLaunchAttributeClusterDimension;
-    attr[1].val.clusterDim.x = 2;
-    attr[1].val.clusterDim.y = 1;
-    attr[1].val.clusterDim.z = 1;
-    cfg.numAttrs = 2;
+    attr[cfg.numAttrs].id = cudaLaunchAttributeClusterDimension;
+    attr[cfg.numAttrs].val.clusterDim.x = 2;
+    attr[cfg.numAttrs].val.clusterDim.y = 1;
+    attr[cfg.numAttrs].val.clusterDim.z = 1;
+    ++cfg.numAttrs;
+  }
+  if (options().l2_persist && (op.epi.flags & EPI_OUT_PLANES) && op.epi.out_plane > 0) {
+    // Experiment for the "no intermediate tensor in HBM" question: mark the split-plane OUTPUT of this
+    // GEMM (an intermediate the next kernel consumes) as persisting in the L2 set-aside, everything else as streaming.
+    static size_t max_win = 0, set_aside = 0;
+    if (!max_win) {
+      int dev = 0, v = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&v, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+      max_win = (size_t)std::max(v, 1);
+      cudaDeviceGetAttribute(&v, cudaDevAttrMaxPersistingL2CacheSize, dev);
+      set_aside = (size_t)std::max(v, 0);
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside);
+    }
+    const size_t bytes = std::min<size_t>(max_win, 2 * (size_t)op.epi.out_plane * sizeof(bf16));
+    attr[cfg.numAttrs].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[cfg.numAttrs].val.accessPolicyWindow.base_ptr = (void*)op.epi.out;
+    attr[cfg.numAttrs].val.accessPolicyWindow.num_bytes = bytes;
+    attr[cfg.numAttrs].val.accessPolicyWindow.hitRatio = bytes ? std::min(1.0f, (float)set_aside / (float)bytes) : 0.f;
+    attr[cfg.numAttrs].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[cfg.numAttrs].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    ++cfg.numAttrs;
   }
   ACE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_umma_kernel<C>, p));
   after_launch(op.name);
@@ -1051,6 +1077,8 @@ bool classify(const GemmOp& op, Variant& v, const char** why) {
     if (e.o_n != 1 || !aligned4(op.N) || !aligned4(e.o_m0) || !aligned4(e.o_z1) || !aligned4(e.o_z2) || !aligned4(e.out_plane) || (((uintptr_t)e.out) & 7))
       return fail("complex mode 2: plane output not 8B-vectorisable");
     if (op.B.s_z2 != 0) return fail("complex mode 2: B must not vary along z2 (the axis carries the {re, im} index)");
+    if (op.group_n && ((op.group_n != 64 && op.group_n != 128) || op.N % op.group_n || op.K > op.group_n || op.a_part_k < op.N))
+      return fail("grouped complex mode: groups of 64 or 128 columns");
     v.a_mn = v.b_mn = false;
     v.nc = true;
     v.scalar = false;
@@ -1213,7 +1241,9 @@ bool dispatch(const GemmOp& op, bool dry, cudaStream_t s, const char** why) {
     return true;
   }
   if (op.cplx == 2) {
-    if (!dry) launch<Cfg<128, false, false, P, true, 32, true>>(op, s);
+    if (dry) return true;
+    if (op.group_n == 64) launch<Cfg<64, false, false, P, true, 32, true>>(op, s);
+    else launch<Cfg<128, false, false, P, true, 32, true>>(op, s);
     return true;
   }
   if (op.cplx) {

@@ -91,6 +91,7 @@ void launch_concat_ctx(const float* noise, int En, const float* pos, int Epos, i
 void launch_build_cln_w2(const float* ws_n, const float* wb_n, int En, const float* ws_p, const float* wb_p, int Epos, int C, int Ep, float* w2,
                          cudaStream_t stream);
 // dhconv weight with element (l, o, i, part) at w[(l*s_l + o*s_o + i*s_i)*2 + part] -> planes [L][2 (re, im)][Cout][Cinp]
+void launch_prep_dhconv_grouped(const float* w, int G, int cg, int L, int cgp, bf16* dst, long long plane, cudaStream_t stream);
 void launch_prep_dhconv_cplx_strided(const float* w, int Cin, int Cout, int L, long long s_l, long long s_o, long long s_i, int Cinp, bf16* dst,
                                      long long plane, cudaStream_t stream);
 

@@ -130,6 +130,35 @@ inline GemmOp dhconv_op(const bf16* c1, long long c1_plane, const bf16* w, long 
   return op;
 }
 
+// dhconv with filter_num_groups = G > 1 (fme/core/models/conditional_sfno/s2convolutions.py:119-135): the per-degree operator is
+// block diagonal.  Weights: planes [L][2][C][cgp] -- row o = g * cg + o' holds the cg inputs of ITS group only (1/G of the
+// dense operator's bytes and multiplications); the GEMM is the grouped complex mode of gemm.cuh (orders on the rows).
+inline GemmOp dhconv_grouped_op(const bf16* c1, long long c1_plane, const bf16* w, long long w_plane, const ace_sht_plan& p, int C, int G,
+                                int B, bf16* c2, long long c2_plane) {
+  GemmOp op = make_gemm_op("dhconv");
+  const int cg = C / G, cgp = (int)round_up(cg, 8);
+  op.cplx = 2;
+  op.group_n = cg;
+  op.a_part_k = C;
+  op.M = p.M;
+  op.N = C;
+  op.K = cg;
+  op.Z1 = p.L;
+  op.Z2 = B;
+  op.m_hi_z1 = 1;
+  op.A = {c1, c1_plane, 2LL * C, 1, (long long)p.M * 2 * C, (long long)p.L * p.M * 2 * C};
+  op.B = {w, w_plane, (long long)cgp, 1, 2LL * C * cgp, 0};
+  op.b_part = (long long)C * cgp;
+  op.epi.flags = EPI_OUT_PLANES;
+  op.epi.out = c2;
+  op.epi.out_plane = c2_plane;
+  op.epi.o_z2 = (long long)p.M * p.Lp * 2 * C;
+  op.epi.o_z1 = 2LL * C;
+  op.epi.o_m0 = (long long)p.Lp * 2 * C;
+  op.epi.o_n = 1;
+  return op;
+}
+
 inline void row_stats(GemmOp& op, double* stats, int C) {
   op.epi.flags |= EPI_ROW_STATS;
   op.epi.stats = stats;

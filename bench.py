@@ -472,7 +472,7 @@ def run_b200(args):
     from ace_b200 import legendre as _leg
     from ace_b200.metrics import LatLonOperations
 
-    _, wq, _ = _leg.nodes_and_weights("legendre-gauss", H)
+    _, wq, _ = _leg.grid_nodes("legendre-gauss", H)
     area = torch.as_tensor(wq, dtype=torch.float32)[:, None].expand(H, Wd).contiguous()
     ops = LatLonOperations(area)
     WINDOW = 40

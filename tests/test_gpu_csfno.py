@@ -75,7 +75,10 @@ def test_matches_oracle_tcgen05_path(img, embed, noise, pos, grid):
 
 
 @pytest.mark.parametrize("img,embed,grid,extra", [
-    ((48, 96), 128, "legendre-gauss", dict(filter_num_groups=8)),                                      # the reference's 8-group benchmark option
+    ((48, 96), 128, "legendre-gauss", dict(filter_num_groups=8)),                                      # 16 channels per group: folded into the dense operator
+    ((48, 96), 128, "legendre-gauss", dict(filter_num_groups=2)),                                      # 64 per group: multiplied natively as diagonal blocks
+    ((40, 80), 256, "legendre-gauss", dict(filter_num_groups=2, filter_preserves_global_mean=True, spectral_lora_rank=3)),  # 128 per group, LoRA merged per group
+    ((48, 96), 512, "legendre-gauss", dict(filter_num_groups=8, num_layers=1)),                        # the reference's 8-group benchmark option (C = 512)
     ((48, 96), 64, "legendre-gauss", dict(filter_num_groups=2, filter_preserves_global_mean=True, spectral_lora_rank=4, lora_rank=4)),
     ((32, 64), 64, "legendre-gauss", dict(spectral_ratio=0.5, filter_num_groups=2, spectral_lora_rank=2)),
     ((48, 96), 64, "legendre-gauss", dict(filter_residual=True, filter_output=True)),                  # round trips on the tcgen05 path
@@ -113,6 +116,44 @@ def test_folded_and_filtered_options_match_oracle(img, embed, grid, extra):
             ref2 = onet(x, oc.Context(**ctx))
         assert field_rel_err(ref2, ref) > 1e-3  # the edit matters ...
         assert field_rel_err(net(x.cuda(), _cuda_ctx(ctx)).cpu(), ref2) < 1e-4  # ... and is followed
+
+
+def test_grouped_filter_is_faster_and_smaller():
+    """The reference's only in-tree performance assertion (fme/core/models/conditional_sfno/test_sfnonet.py:262-284
+    ``test_block_speed``: the 8-group dhconv block must be faster and use less memory than the ungrouped one), at its benchmark's
+    width (C = 512, B = 2; fme/core/models/conditional_sfno/benchmark.py:29-46) on a 90x180 grid, through the one-block network."""
+    import ace_b200
+    from ace_b200 import csfno as bc
+
+    img, B = (90, 180), 2
+    res = {}
+    for G in (1, 8):
+        torch.manual_seed(3)
+        net = bc.get_lat_lon_sfnonet(bc.SFNONetConfig(embed_dim=512, num_layers=1, filter_num_groups=G), in_chans=4, out_chans=4, img_shape=img,
+                                     data_grid="legendre-gauss", context_config=bc.ContextConfig(embed_dim_noise=8)).cuda().eval().requires_grad_(False)
+        x = torch.randn(B, 4, *img, device="cuda")
+        ctx = bc.Context(noise=torch.randn(B, 8, *img, device="cuda"))
+        torch.cuda.synchronize()
+        torch.cuda.reset_peak_memory_stats()
+        m0 = torch.cuda.memory_allocated()
+        for _ in range(2):
+            net(x, ctx)  # warm-up: parameter upload, workspaces
+        torch.cuda.synchronize()
+        ace_b200.set_option("profile", 1)
+        ace_b200._lib.profile_report()
+        for _ in range(5):
+            net(x, ctx)
+        rep = ace_b200._lib.profile_report()
+        ace_b200.set_option("profile", 0)
+        res[G] = dict(dhconv_us=rep["dhconv"][1] / rep["dhconv"][0] * 1e3, total_ms=sum(t for _, t in rep.values()) / 5,
+                      torch_bytes=torch.cuda.max_memory_allocated() - m0,
+                      filter_params=sum(p.numel() for k, p in net.named_parameters() if k.endswith("filter.weight")))
+        del net
+        torch.cuda.empty_cache()
+    assert res[8]["filter_params"] * 8 == res[1]["filter_params"]
+    assert res[8]["dhconv_us"] < res[1]["dhconv_us"], res        # grouped dhconv faster ...
+    assert res[8]["total_ms"] < res[1]["total_ms"], res          # ... so is the block around it ...
+    assert res[8]["torch_bytes"] < res[1]["torch_bytes"], res    # ... and it holds 1/8 of the filter weights
 
 
 def test_clip_latent_global_means():

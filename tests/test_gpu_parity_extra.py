@@ -6,7 +6,7 @@
       near zero crossings exceed a 1e-5 * max absolute tolerance with split-bf16 operands).
 (ii)  latent channels with |mean| / std in {10, 100}: bounds the un-centred bf16 split of the deferred InstanceNorm.
 (iii) a 40-step rollout at 180x360 (reduced width) against the oracle with a FIXED bound.
-(iv)  configs[3]'s grid, 721x1440, at reduced width against the oracle.
+(iv)  configs[3]'s grid, 721x1440, at reduced width against a committed oracle fixture.
 """
 import json
 import os
@@ -79,10 +79,11 @@ def test_elementwise_criterion_at_baseline_configs(cin, cout, tag):
     _record(tag, {"max_field_rel_err": err, "elementwise_pass_fraction_rtol1e-4_atol1e-5max": frac,
                   "worst_field_pass_fraction": worst_field, "elementwise_pass_fraction_rtol1e-4_atol5e-5max": frac5})
     assert err < 1e-4, err
-    # stated bounds (measured r02: see DESIGN.md section 6): the survey's element-wise criterion holds for the bulk of the
-    # elements; with a 5e-5 * max absolute floor it holds everywhere
-    assert frac >= 0.90, frac
-    assert frac5 >= 0.999, frac5
+    # stated bounds: the survey's element-wise criterion holds for all but ~1e-5 of the elements (those
+    # sit at zero crossings, where the 1e-5 * max absolute floor is below the 2e-5 * max error of split-bf16 operands); with
+    # a 5e-5 * max floor it holds everywhere
+    assert frac >= 0.9999, frac  # measured r02: 0.999992 (configs[0]) / 0.999997 (configs[1]); worst field 0.99997
+    assert frac5 == 1.0, frac5
 
 
 @pytest.mark.parametrize("ratio", [10.0, 100.0])
@@ -114,7 +115,7 @@ def test_large_mean_latent_channels(ratio):
 @pytest.mark.timeout(1800)
 def test_rollout_40_steps_at_benchmark_grid():
     """40 autoregressive steps at 180x360 (embed 32, 2 blocks) through FusedStepper (CUDA graph) vs the oracle loop; fixed bound
-    3e-4 on every field of every step (errors grow with the Lipschitz constant of the random-init net, not linearly in t)."""
+    1e-4 on every field of every step (the same bound as a single step)."""
     import ace_b200
     from tests.test_gpu_stepper import _oracle_step
 
@@ -145,23 +146,40 @@ def test_rollout_40_steps_at_benchmark_grid():
         worst.append(field_rel_err((outs[t] - mo) / so, (ref_t - mo) / so))
         state = {n: out[n] for n in st.prognostic_names}
     _record("rollout_40_steps_180x360", {"max_field_rel_err_per_step": worst})
-    assert max(worst) < 3e-4, worst
+    assert max(worst) < 1e-4, worst  # measured r02: 1.0e-5 ... 1.3e-5 at every step, no growth
 
 
-@pytest.mark.timeout(2400)
+@pytest.mark.timeout(1200)
 def test_quarter_degree_grid_reduced_width():
     """BASELINE configs[3]'s grid (721x1440: odd nlat, L = M = 721) at embed 8, one block, against the oracle: every GEMM on
-    the tcgen05 kernel (the odd-nlat element-wise store variants of the forward stages, the padded inverse pair)."""
-    from ace_b200 import _lib
+    the tcgen05 kernel (the odd-nlat element-wise store variants of the forward stages, the padded inverse pair).
+    The oracle output is a committed fixture (oracle/make_golden_quarter_degree.py: building the oracle's four Legendre tables at
+    L = 721 takes minutes of host time); weights and input are rebuilt from the same seeds and checked by checksum."""
+    import numpy as np
 
-    onet, net, g = _nets((721, 1440), 3, 3, 8, 1, seed=61)
-    x = torch.randn(1, 3, 721, 1440, generator=g)
+    import ace_b200
+    from ace_b200 import _lib
+    from oracle.make_golden_quarter_degree import CIN, COUT, EMBED, IMG, LAYERS, SEED, seeded_weights_
+    from tests.util import GOLDEN_DIR
+
+    fx = np.load(os.path.join(GOLDEN_DIR, "oracle_quarter_degree_721x1440_embed8.npz"))
+    fields = dict(embed_dim=EMBED, num_layers=LAYERS, operator_type="dhconv", data_grid="legendre-gauss")
+    torch.manual_seed(SEED)  # same parameter creation order and initialisers as the oracle / reference net (tests/test_registry.py)
+    net = ace_b200.ModuleSelector(type="B200SphericalFourierNeuralOperatorNet", config=fields).build(
+        CIN, COUT, ace_b200.DatasetInfo(img_shape=IMG)).torch_module
+    g = seeded_weights_(net, SEED)
+    x = torch.randn(1, CIN, *IMG, generator=g)
+    assert abs(float(x.double().sum()) - float(fx["x_checksum"])) < 1e-6 * max(1.0, abs(float(fx["x_checksum"])))
+    wsum = float(sum(p.double().sum() for p in net.parameters()))
+    assert abs(wsum - float(fx["w_checksum"])) < 1e-6 * max(1.0, abs(float(fx["w_checksum"]))), "seeded weights differ from the fixture's"
+    net = net.cuda().eval().requires_grad_(False)
     s0 = _lib.get_option("count_simt")
-    torch.set_num_threads(min(16, torch.get_num_threads()))
     with torch.no_grad():
         y = net(x.cuda()).cpu()
-        ref = onet(x)
     assert _lib.get_option("count_simt") == s0, "a GEMM fell back to the SIMT kernel at 721x1440"
-    err = field_rel_err(y, ref)
-    _record("quarter_degree_721x1440_embed8", {"max_field_rel_err": err})
+    sub = y[:, :, torch.as_tensor(fx["lat_idx"])][..., ::int(fx["lon_stride"])].double()
+    ref = torch.from_numpy(fx["ref_sub"]).double()
+    err = float(((sub - ref).abs().amax(dim=(-2, -1)) / torch.from_numpy(fx["ref_absmax"]).double()).max())
+    assert torch.isfinite(y).all()
+    _record("quarter_degree_721x1440_embed8", {"max_field_rel_err_on_fixture_subsample": err})
     assert err < 1e-4, err
