@@ -349,19 +349,22 @@ __device__ __forceinline__ void epilogue_nc_chunk(const EpiParams& e, float (&v)
   const int fr = lane >> 2, fp = lane & 3;  // fp32 pass: rows it*8 + fr (it < 4), 16-byte piece fp
   const int pr = lane >> 3, pp = lane & 7;  // plane pass: rows it*4 + pr (it < 8), 8-byte piece pp
 
-  // (the operands were L2-prefetched before the accumulator barrier, so one pass of loads in flight is enough)
+  // All global loads of the chunk are issued before the first one is consumed (one L2 round trip per chunk instead of one per
+  // 16-column half / per plane: the epilogue warps are latency-bound, three of them share a scheduler).
   if (EF & EPI_ADD_F32) {
+    uint4 t[2][4];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      uint4 t[4];
+    for (int h = 0; h < 2; ++h)
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
-        t[it] = make_uint4(0u, 0u, 0u, 0u);
+        t[h][it] = make_uint4(0u, 0u, 0u, 0u);
         if (FULL || (16 * h + fp * 4 < nvalid && it * 8 + fr < rows_valid))
-          t[it] = __ldg(reinterpret_cast<const uint4*>(g_add + (long long)(it * 8) * e.add_m0 + 16 * h));
+          t[h][it] = __ldg(reinterpret_cast<const uint4*>(g_add + (long long)(it * 8) * e.add_m0 + 16 * h));
       }
 #pragma unroll
-      for (int it = 0; it < 4; ++it) s16[swz16(it * 8 + fr, fp)] = t[it];
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+      for (int it = 0; it < 4; ++it) s16[swz16(it * 8 + fr, fp)] = t[h][it];
       __syncwarp();
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -376,17 +379,19 @@ __device__ __forceinline__ void epilogue_nc_chunk(const EpiParams& e, float (&v)
   }
   if (EF & EPI_RES_PLANES) {
     const f2 ra2 = mk2(res_a, res_a);
+    uint2 t[2][8];
 #pragma unroll
-    for (int pl = 0; pl < 2; ++pl) {
-      uint2 t[8];
+    for (int pl = 0; pl < 2; ++pl)
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
-        t[it] = make_uint2(0u, 0u);
+        t[pl][it] = make_uint2(0u, 0u);
         if (FULL || (pp * 4 < nvalid && it * 4 + pr < rows_valid))
-          t[it] = __ldg(reinterpret_cast<const uint2*>(g_res + (long long)(it * 4) * e.res_m0 + (pl ? e.res_plane : 0)));
+          t[pl][it] = __ldg(reinterpret_cast<const uint2*>(g_res + (long long)(it * 4) * e.res_m0 + (pl ? e.res_plane : 0)));
       }
 #pragma unroll
-      for (int it = 0; it < 8; ++it) s8[swz8(it * 4 + pr, pp)] = t[it];
+    for (int pl = 0; pl < 2; ++pl) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) s8[swz8(it * 4 + pr, pp)] = t[pl][it];
       __syncwarp();
 #pragma unroll
       for (int k = 0; k < 8; ++k) {

@@ -126,34 +126,36 @@ def test_grouped_filter_is_faster_and_smaller():
     from ace_b200 import csfno as bc
 
     img, B = (90, 180), 2
-    res = {}
+    res, nets = {}, {}
+    x = torch.randn(B, 4, *img, device="cuda")
+    ctx = bc.Context(noise=torch.randn(B, 8, *img, device="cuda"))
     for G in (1, 8):
         torch.manual_seed(3)
+        torch.cuda.synchronize()
+        m0 = torch.cuda.memory_allocated()
         net = bc.get_lat_lon_sfnonet(bc.SFNONetConfig(embed_dim=512, num_layers=1, filter_num_groups=G), in_chans=4, out_chans=4, img_shape=img,
                                      data_grid="legendre-gauss", context_config=bc.ContextConfig(embed_dim_noise=8)).cuda().eval().requires_grad_(False)
-        x = torch.randn(B, 4, *img, device="cuda")
-        ctx = bc.Context(noise=torch.randn(B, 8, *img, device="cuda"))
-        torch.cuda.synchronize()
-        torch.cuda.reset_peak_memory_stats()
-        m0 = torch.cuda.memory_allocated()
         for _ in range(2):
             net(x, ctx)  # warm-up: parameter upload, workspaces
         torch.cuda.synchronize()
-        ace_b200.set_option("profile", 1)
-        ace_b200._lib.profile_report()
-        for _ in range(5):
-            net(x, ctx)
-        rep = ace_b200._lib.profile_report()
-        ace_b200.set_option("profile", 0)
-        res[G] = dict(dhconv_us=rep["dhconv"][1] / rep["dhconv"][0] * 1e3, total_ms=sum(t for _, t in rep.values()) / 5,
-                      torch_bytes=torch.cuda.max_memory_allocated() - m0,
+        nets[G] = net
+        res[G] = dict(torch_bytes=torch.cuda.memory_allocated() - m0, dhconv_us=[], total_ms=[],
                       filter_params=sum(p.numel() for k, p in net.named_parameters() if k.endswith("filter.weight")))
-        del net
-        torch.cuda.empty_cache()
+    # alternate the two configurations (clock / power state drifts between back-to-back blocks of launches) and keep the best
+    for _ in range(4):
+        for G in (1, 8):
+            ace_b200.set_option("profile", 1)
+            ace_b200._lib.profile_report()
+            for _ in range(3):
+                nets[G](x, ctx)
+            rep = ace_b200._lib.profile_report()
+            ace_b200.set_option("profile", 0)
+            res[G]["dhconv_us"].append(rep["dhconv"][1] / rep["dhconv"][0] * 1e3)
+            res[G]["total_ms"].append(sum(t for _, t in rep.values()) / 3)
     assert res[8]["filter_params"] * 8 == res[1]["filter_params"]
-    assert res[8]["dhconv_us"] < res[1]["dhconv_us"], res        # grouped dhconv faster ...
-    assert res[8]["total_ms"] < res[1]["total_ms"], res          # ... so is the block around it ...
-    assert res[8]["torch_bytes"] < res[1]["torch_bytes"], res    # ... and it holds 1/8 of the filter weights
+    assert min(res[8]["dhconv_us"]) < 0.7 * min(res[1]["dhconv_us"]), res  # grouped dhconv faster (measured r02: 39 vs 85 us) ...
+    assert min(res[8]["total_ms"]) < min(res[1]["total_ms"]), res          # ... so is the block around it ...
+    assert res[8]["torch_bytes"] < res[1]["torch_bytes"], res              # ... and it holds 1/8 of the filter weights
 
 
 def test_clip_latent_global_means():
