@@ -87,8 +87,6 @@ extern "C" int ace_set_option(const char* key, int value) {
     options().pdl = value ? 1 : 0;
   } else if (!strcmp(key, "dbg")) {
     options().dbg = value;
-  } else if (!strcmp(key, "mc3")) {
-    options().mc3 = value ? 1 : 0;
   } else if (!strcmp(key, "l2_persist")) {
     options().l2_persist = value ? 1 : 0;
   } else if (!strcmp(key, "inv2")) {
@@ -120,7 +118,6 @@ extern "C" int ace_get_option(const char* key) {
   if (!strcmp(key, "dhconv_t")) return options().dhconv_t;
   if (!strcmp(key, "tile_list")) return options().tile_list;
   if (!strcmp(key, "inv2")) return options().inv2;
-  if (!strcmp(key, "mc3")) return options().mc3;
   return -1;
 }
 

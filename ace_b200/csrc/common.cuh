@@ -93,7 +93,6 @@ struct Options {
   int dbg = 0;       // development switches of the tcgen05 kernel (results are wrong when non-zero)
   int umma_bk = 0;   // K extent per pipeline stage of the ROWC (forward SHT / dhconv) variants: 0 = per-op hint, 32, 64
   int tile_list = 1; // triangular GEMMs walk a host-built list of their non-empty tiles, heaviest first (0: implicit round-robin walk of the full tile box)
-  int mc3 = 1;         // 1x1 convolutions with 257..384 output channels: clusters of three CTAs, activation tile multicast by TMA (gemm_umma.cu, MC3)
   int l2_persist = 0;  // experiment: L2 persisting access-policy window over the split-plane output of every tcgen05 GEMM
   int inv2 = 1;      // networks use the padded / parity-split inverse Legendre stage + butterfly inverse DFT (sht.cuh); 0: first-generation pair
   int dhconv_t = 0;  // dhconv orientation: 0 = weights on the rows, the l + 1 orders on the columns (fewest multiplications: measured 83 vs 89 us);

@@ -65,8 +65,7 @@ constexpr int kThreadsUmma = 32 * (4 + kEpiWarps);
 constexpr int kStgBytesPerWarp = 2048;
 constexpr int kMaxSmem = 232448;  // 227 KB opt-in limit per CTA
 
-template <int BN_, bool A_MN_, bool B_MN_, uint32_t EF_, bool NC_, int BK_ = 32, bool CPLX_ = false, bool PAIR_ = false, bool BFLY_ = false,
-          bool MC3_ = false>
+template <int BN_, bool A_MN_, bool B_MN_, uint32_t EF_, bool NC_, int BK_ = 32, bool CPLX_ = false, bool PAIR_ = false, bool BFLY_ = false>
 struct Cfg {
   static constexpr int BM = 128, BN = BN_, BK = BK_;
   static constexpr bool A_MN = A_MN_, B_MN = B_MN_, NC = NC_, CPLX = CPLX_;
@@ -77,13 +76,6 @@ struct Cfg {
   // rows of A and HALF of the B tile (the tensor cores read the other half from the peer), which cuts the shared-memory
   // and L2->SM operand traffic per SM by a third for a 256-wide tile
   static constexpr bool PAIR = PAIR_;
-  // MC3: a cluster of three CTAs computes the three 128-row tiles of a 384-row problem for the SAME columns.  Each CTA
-  // loads its own A tile and ONE third of the B tile (a 64-column atom) which TMA multicasts into all three CTAs: the
-  // activation operand crosses the L2 -> SM fabric once instead of three times (fc2 moved 1.1 GB per launch for 0.4 GB of
-  // operands, profiles/r02_ncu_block_default_vs_l2persist.json).  cta_group::1 MMAs; a stage is released to the producers
-  // when the MMAs of all three CTAs have consumed it (multicast commit).
-  static constexpr bool MC3 = MC3_;
-  static_assert(!MC3 || (B_MN_ && !A_MN_ && BN_ == 192 && !PAIR_ && !CPLX_ && !BFLY_ && NC_), "MC3: 1x1 convolution variants, BN = 192");
   static constexpr int BNL = PAIR ? BN / 2 : BN;  // B columns staged by this CTA
   static constexpr int TILE_M = PAIR ? 256 : 128;
   // butterfly mode (GemmOp::bfly): K-chunks below / from k_split accumulate into two accumulators E, O; the epilogue stores
@@ -585,8 +577,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GemmOp& op = p.op;
   constexpr bool PAIR = C::PAIR;
-  constexpr bool MC3 = C::MC3;
-  const uint32_t crank = (PAIR || MC3) ? ptx::cluster_ctarank() : 0u;  // pair: 0 = leader (issues the MMAs), 1 = peer; MC3: row tile
+  const uint32_t crank = PAIR ? ptx::cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs), 1 = peer
   constexpr int NCTA = PAIR ? 2 : 1;
 
   if (warp == 0 && lane == 0) {
@@ -596,7 +587,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(full_bar(s), NCTA);  // pair: one arrive per CTA's producer, all bytes credited to the leader
-      ptx::mbar_init(empty_bar(s), MC3 ? 3 : 1);  // MC3: the MMA warps of all three CTAs release a stage together
+      ptx::mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(tfull_bar(a), 1);
@@ -614,7 +605,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
     }
   }
   ptx::tc_fence_before();
-  if constexpr (PAIR || MC3) ptx::cluster_sync();  // barriers of every CTA exist before any remote arrive / multicast
+  if constexpr (PAIR) ptx::cluster_sync();  // barriers of both CTAs exist before any remote arrive / multicast commit
   else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
@@ -623,11 +614,8 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-  // MC3: the host passes tiles_m = 1 (the row tile is the cluster rank), so a tile index enumerates (column tile, batch)
   const long long total = p.tiles ? p.n_listed : (long long)p.tiles_m * p.tiles_n * op.Z1 * op.Z2;
-  const long long t_first = PAIR ? (blockIdx.x >> 1) : MC3 ? (blockIdx.x / 3) : blockIdx.x;
-  const long long t_step = PAIR ? (gridDim.x >> 1) : MC3 ? (gridDim.x / 3) : gridDim.x;
-  const int mc_m0 = MC3 ? 128 * (int)crank : 0;
+  const long long t_first = PAIR ? (blockIdx.x >> 1) : blockIdx.x, t_step = PAIR ? (gridDim.x >> 1) : gridDim.x;
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp walks the loop, one elected lane issues) =====================
@@ -698,7 +686,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
 #pragma unroll
             for (int pl = 0; pl < 2; ++pl) {
               if (!C::A_MN) {
-                ptx::tma_load_5d(sA + pl * C::A_PLANE, &p.tmA, fb, k0, ti.m0 + mc_m0, az1, az2, pl);
+                ptx::tma_load_5d(sA + pl * C::A_PLANE, &p.tmA, fb, k0, ti.m0, az1, az2, pl);
               } else {
                 // 64-wide MN atoms, each [BK rows][128 B]
 #pragma unroll
@@ -707,11 +695,6 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
               }
               if (!C::B_MN) {
                 ptx::tma_load_5d(sB + pl * C::B_PLANE, &p.tmB, fb, k0, ti.n_begin, bz1, bz2, pl);
-              } else if constexpr (MC3) {
-                // this CTA's third of the B tile, multicast into the same slot of all three CTAs (each CTA's full barrier
-                // is credited with all three thirds)
-                const int a = (int)crank;
-                ptx::tma_load_5d_mc(sB + pl * C::B_PLANE + a * BK * 128, &p.tmB, fb, ti.n_begin + 64 * a, k0, bz1, bz2, pl, (uint16_t)7);
               } else {
 #pragma unroll
                 for (int a = 0; a < BN / 64; ++a)
@@ -724,7 +707,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 1 && (crank == 0 || MC3)) {
+  } else if (warp == 1 && crank == 0) {
     // ===================== MMA issuer (warp-uniform control flow keeps the descriptors in uniform registers) ==========
     // K-major (64B swizzle for BK = 32, 128B for BK = 64): rows of 2*BK bytes, 8-row groups SBO apart; a K-step is
     // 32 bytes inside the swizzled row.  MN-major (128B swizzle): [k][64 mn] atoms, 8-k groups SBO = 1024 B apart, the next
@@ -798,7 +781,6 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
             }
           }
           if constexpr (PAIR) ptx::umma_commit_2sm(empty_bar(stage));  // frees the slot in both CTAs
-          else if constexpr (MC3) ptx::umma_commit_mc(empty_bar(stage), (uint16_t)7);  // one of the three releases, in every CTA
           else ptx::umma_commit(empty_bar(stage));                     // frees the smem slot when these MMAs retire
         }
         __syncwarp();
@@ -821,7 +803,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
     for (long long t = t_first; t < total; t += t_step) {
       if (!decode_tile<BN, BK, C::TILE_M>(p, t, ti)) continue;
       const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
-      ti.m0 += 128 * (int)crank;  // pair mode: this CTA owns the second 128 rows of the 256-row tile; MC3: its row tile
+      ti.m0 += 128 * (int)crank;  // pair mode: this CTA owns the second 128 rows of the 256-row tile
       if constexpr (C::NC) epilogue_nc_prefetch<C>(p, ti, q, sub, lane);
       ptx::mbar_wait(tfull_bar(as), aph);
       ptx::tc_fence_after();
@@ -841,7 +823,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
   }
 
   ptx::tc_fence_before();
-  if constexpr (PAIR || MC3) ptx::cluster_sync();  // a peer may still read this CTA's B half / signal its barriers
+  if constexpr (PAIR) ptx::cluster_sync();  // the peer may still read this CTA's B half / signal its barriers
   else __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
@@ -974,7 +956,7 @@ void launch(const GemmOp& op, cudaStream_t stream) {
   }
   UmmaParams p;
   p.op = op;
-  p.tiles_m = C::MC3 ? 1 : (op.M + C::TILE_M - 1) / C::TILE_M;  // MC3: the row tile is the cluster rank
+  p.tiles_m = (op.M + C::TILE_M - 1) / C::TILE_M;
   p.tiles_n = (op.N + C::BN - 1) / C::BN;
   p.nterms = options().split_terms;
   p.dbg = options().dbg;
@@ -1014,9 +996,7 @@ void launch(const GemmOp& op, cudaStream_t stream) {
     p.tiles = tl.buf.as<int4>();
     p.n_listed = total = tl.n;
   }
-  int grid = C::PAIR ? 2 * (int)std::min<long long>(total, sm_count() / 2)
-             : C::MC3 ? 3 * (int)std::min<long long>(total, sm_count() / 3)
-                      : (int)std::min<long long>(total, sm_count());
+  int grid = C::PAIR ? 2 * (int)std::min<long long>(total, sm_count() / 2) : (int)std::min<long long>(total, sm_count());
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kThreadsUmma);
@@ -1024,12 +1004,12 @@ void launch(const GemmOp& op, cudaStream_t stream) {
   cfg.stream = stream;
   cudaLaunchAttribute attr[3];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = (options().pdl && !C::PAIR && !C::MC3) ? 1 : 0;
+  attr[0].val.programmaticStreamSerializationAllowed = (options().pdl && !C::PAIR) ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (C::PAIR || C::MC3) {
+  if (C::PAIR) {
     attr[cfg.numAttrs].id = cudaLaunchAttributeClusterDimension;
-    attr[cfg.numAttrs].val.clusterDim.x = C::MC3 ? 3 : 2;
+    attr[cfg.numAttrs].val.clusterDim.x = 2;
     attr[cfg.numAttrs].val.clusterDim.y = 1;
     attr[cfg.numAttrs].val.clusterDim.z = 1;
     ++cfg.numAttrs;
@@ -1234,20 +1214,8 @@ bool launch_conv_bn(const GemmOp& op, const Variant& v, cudaStream_t s) {
     default: return false;
   }
 }
-// M in (256, 384]: clusters of three CTAs share the activation tile by TMA multicast
-bool launch_conv_mc3(const GemmOp& op, const Variant& v, cudaStream_t s) {
-  switch (v.ef) {
-    case G | P: launch<Cfg<192, false, true, G | P, true, 32, false, false, false, true>>(op, s); return true;
-    case AD | P: launch<Cfg<192, false, true, AD | P, true, 32, false, false, false, true>>(op, s); return true;
-    case AD | G | P: launch<Cfg<192, false, true, AD | G | P, true, 32, false, false, false, true>>(op, s); return true;
-    case RS | P: launch<Cfg<192, false, true, RS | P, true, 32, false, false, false, true>>(op, s); return true;
-    case P: launch<Cfg<192, false, true, P, true, 32, false, false, false, true>>(op, s); return true;
-    default: return false;
-  }
-}
 bool launch_conv(const GemmOp& op, const Variant& v, cudaStream_t s) {
   if (!v.nc || v.a_mn || !v.b_mn) return false;
-  if (options().mc3 && op.M > 256 && op.M <= 384 && !v.scalar && launch_conv_mc3(op, v, s)) return true;
   // CTA pairs pay off when no half tile is wasted (measured: fc1 M=768 111 -> 95 us; M=384 ops gain nothing)
   const bool want_pair = options().pair == 1 ? op.M > 128 : (options().pair < 0 && op.M % 256 == 0);
   if (want_pair && launch_conv_pair(op, v, s)) return true;
