@@ -95,6 +95,14 @@ extern "C" int ace_set_option(const char* key, int value) {
     options().tile_list = value ? 1 : 0;
   } else if (!strcmp(key, "dhconv_t")) {
     options().dhconv_t = value ? 1 : 0;
+  } else if (!strcmp(key, "group_order")) {
+    options().group_order = value ? 1 : 0;
+  } else if (!strcmp(key, "mma_batch")) {
+    options().mma_batch = value ? 1 : 0;
+  } else if (!strcmp(key, "sp")) {
+    options().sp = value;  // 0 off, 1 where it pays, 2 wherever eligible
+  } else if (!strcmp(key, "trace")) {
+    options().trace = value ? 1 : 0;
   } else if (!strcmp(key, "umma_bk")) {
     ACE_REQUIRE(value == 0 || value == 32 || value == 64, "umma_bk must be 0, 32 or 64");
     options().umma_bk = value;

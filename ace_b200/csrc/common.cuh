@@ -97,6 +97,10 @@ struct Options {
   int inv2 = 1;      // networks use the padded / parity-split inverse Legendre stage + butterfly inverse DFT (sht.cuh); 0: first-generation pair
   int dhconv_t = 0;  // dhconv orientation: 0 = weights on the rows, the l + 1 orders on the columns (fewest multiplications: measured 83 vs 89 us);
                      // 1 = orders on the rows / output channels on the columns (128 x 128 MMAs, NC epilogue)
+  int group_order = 1;  // dense ops with several N tiles: a worker takes all N tiles of its M tile back to back (0: implicit round-robin walk)
+  int mma_batch = 1;  // tcgen05 kernel: MMAs of two ring slots per barrier round when both have landed (0: one slot per round)
+  int sp = 1;        // 1x1 convolutions with >= 128 output channels run with the spatial positions on the accumulator rows (gemm_umma.cu, Cfg::SP)
+  int trace = 0;     // development: per-tile clock samples of the tcgen05 kernel's roles appended to $ACE_B200_TRACE_FILE (tools/trace_report.py)
   int umma_bn = 0;   // 0 = choose per op; otherwise force the N tile of the K-major x K-major variants (192 / 256)
 };
 Options& options();

@@ -57,7 +57,20 @@ struct UmmaParams {
   // kernel) and gives every CTA a different amount of work when the tile cost depends on z1 (Legendre stages).
   const int4* tiles;
   long long n_listed;
+  // development trace (option "trace"): [CTA][tile iteration < kTraceIters][kTraceSlots] clock64 samples of the three roles
+  long long* trace;
+  int mma_batch;  // option "mma_batch": the MMA warp issues two ring slots per barrier round when both have landed
 };
+
+constexpr int kTraceIters = 41, kTraceSlots = 16;
+__device__ __forceinline__ long long globaltimer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void trace_put(const UmmaParams& p, uint32_t it, int slot, long long v) {
+  if (p.trace && it < (uint32_t)kTraceIters) p.trace[((long long)blockIdx.x * kTraceIters + it) * kTraceSlots + slot] = v;
+}
 
 constexpr uint32_t EF_MASK = EPI_ADD_F32 | EPI_RES_PLANES | EPI_GELU | EPI_OUT_PLANES | EPI_OUT_F32;
 constexpr int kEpiWarps = 12;
@@ -65,8 +78,16 @@ constexpr int kThreadsUmma = 32 * (4 + kEpiWarps);
 constexpr int kStgBytesPerWarp = 2048;
 constexpr int kMaxSmem = 232448;  // 227 KB opt-in limit per CTA
 
-template <int BN_, bool A_MN_, bool B_MN_, uint32_t EF_, bool NC_, int BK_ = 32, bool CPLX_ = false, bool PAIR_ = false, bool BFLY_ = false>
+template <int BN_, bool A_MN_, bool B_MN_, uint32_t EF_, bool NC_, int BK_ = 32, bool CPLX_ = false, bool PAIR_ = false, bool BFLY_ = false,
+          bool SP_ = false>
 struct Cfg {
+  // SP ("space on the rows"): a 1x1 convolution executed with the operand roles exchanged -- A = activations (MN-major, 256
+  // spatial positions per CTA pair), B = weights (K-major, the output channels on the accumulator columns).  A thread of the
+  // epilogue then owns ONE spatial position, and for every channel the 32 lanes of a warp touch 32 consecutive positions of
+  // that channel's row: the fp32 addend, the split-plane residual and the output are read / written straight from registers
+  // with coalesced accesses, no shared-memory transposition (the convolutions are shared-memory-bandwidth bound otherwise:
+  // MMA operand reads + TMA fills + epilogue staging ~ 120 B/clk of the SM's 128 B/clk).
+  static constexpr bool SP = SP_;
   static constexpr int BM = 128, BN = BN_, BK = BK_;
   static constexpr bool A_MN = A_MN_, B_MN = B_MN_, NC = NC_, CPLX = CPLX_;
   // complex mode with the NC epilogue = GemmOp::cplx == 2: [Ar | Ai] along the k axis of A, {Br, Bi} as two matrices, the
@@ -86,8 +107,10 @@ struct Cfg {
   static constexpr int UMMA_K = 16;
   static constexpr int A_PLANE = BM * BK * 2;  // bytes
   static constexpr int B_PLANE = BNL * BK * 2;
+  static constexpr int MN_ATOM = 2 * BK * 128;  // MN-major tiles: one 64-wide atom = [plane][BK k-rows][128 B]; the lo plane sits BK * 128 B after the hi plane
+  static constexpr int A_LO = A_MN ? BK * 128 : A_PLANE, B_LO = B_MN ? BK * 128 : B_PLANE;  // byte offset of the lo plane inside the tile
   static constexpr int STAGE = 2 * (CPLX ? 2 : 1) * (A_PLANE + B_PLANE);  // complex mode: {Ar, Ai} x {hi, lo}, then {Br, Bi} x {hi, lo}
-  static constexpr int STG_BYTES = kEpiWarps * kStgBytesPerWarp;
+  static constexpr int STG_BYTES = SP ? 4096 : kEpiWarps * kStgBytesPerWarp;  // SP: per-channel statistics of the tile only
   static constexpr int MAX_STAGES = 8;
   static constexpr int BAR_BYTES = (2 * MAX_STAGES + 4) * 8 + 16;
   static constexpr int STAGES_RAW = (kMaxSmem - 1024 - STG_BYTES - BAR_BYTES) / STAGE;
@@ -96,7 +119,8 @@ struct Cfg {
   static_assert(2 * NACC * BN <= 512, "TMEM budget");
   static_assert(!CPLX || (!A_MN && !B_MN), "complex mode: K-major operands");
   static_assert(!CT || EF_ == EPI_OUT_PLANES, "complex mode with the NC epilogue: plain split-plane output");
-  static_assert(!PAIR || (!CPLX && BNL % 64 == 0), "pair mode");
+  static_assert(!PAIR || (!CPLX && (B_MN_ ? BNL % 64 == 0 : BNL % 16 == 0)), "pair mode");
+  static_assert(!SP || (PAIR && A_MN_ && !B_MN_ && !NC_ && !CPLX_ && !BFLY_), "SP mode: CTA pairs, MN-major activations x K-major weights");
   static constexpr int SMEM_BYTES = STAGES * STAGE + STG_BYTES + BAR_BYTES + 1024;  // + alignment slack
   static_assert(BN % (B_MN_ ? 64 : 32) == 0 && BN <= 256, "BN");
   static_assert(!BFLY || (NC && !CPLX && !PAIR && !B_MN), "butterfly mode: NC epilogue, K-major B");
@@ -558,6 +582,173 @@ __device__ __forceinline__ void epilogue_nc(const UmmaParams& p, const Tile& ti,
   }
 }
 
+// ---- epilogue: SP (thread = spatial position, accumulator columns = output channels; see Cfg::SP) ----
+// EpiParams keep the caller's meaning (row m = channel, column n = spatial position); p.op is the exchanged op (op.M = positions,
+// op.N = channels).
+
+// sum over the 32 lanes of each of 32 per-lane values in 31 shuffles: on return lane l holds the total of element l
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) {
+    const bool up = (lane & w) != 0;
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      const float send = up ? v[i] : v[i + w];
+      const float keep = up ? v[i + w] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+    }
+  }
+  return v[0];
+}
+
+template <class C, bool FULL>
+__device__ __forceinline__ void epilogue_sp_chunk(const EpiParams& e, float (&v)[32], int nvalid, bool sp_ok, int lane, const float* g_add,
+                                                  const uint32_t* g_res, bool odd, float* g_f32, unsigned short* g_pl, const float* bias,
+                                                  const float* res_a, const float* res_s, bool do_stats, float* s_stats) {
+  constexpr uint32_t EF = C::EF;
+  const long long res_m0w = e.res_m0 >> 1, res_planew = e.res_plane >> 1;  // in 32-bit words (both even: sp_eligible)
+  // operands of 16 channels at a time: every load of the half is issued before the first one is used
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    if (EF & EPI_ADD_F32) {
+      float a[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) a[j] = (FULL || 16 * h + j < nvalid) ? __ldg(g_add + (long long)(16 * h + j) * e.add_m0) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[16 * h + j] += a[j];
+    }
+    if (EF & EPI_RES_PLANES) {
+      // 32-bit loads of the word that holds this lane's element (lane pairs share a word; 16-bit non-coherent loads run at a
+      // fraction of the rate) through the coherent path: fc2 reads its residual from the buffer it overwrites in place
+      uint32_t rh[16], rl[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const bool ok = FULL || 16 * h + j < nvalid;
+        const uint32_t* r = g_res + (long long)(16 * h + j) * res_m0w;
+        rh[j] = ok ? *r : 0u;
+        rl[j] = ok ? r[res_planew] : 0u;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float r = __uint_as_float(odd ? (rh[j] & 0xffff0000u) : (rh[j] << 16)) + __uint_as_float(odd ? (rl[j] & 0xffff0000u) : (rl[j] << 16));
+        if (res_a) v[16 * h + j] += fmaf(__ldg(res_a + 16 * h + j), r, __ldg(res_s + 16 * h + j));
+        else v[16 * h + j] += r;
+      }
+    }
+  }
+  if (bias) {
+    float4 b4[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) b4[k] = __ldg(reinterpret_cast<const float4*>(bias) + k);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += reinterpret_cast<const float*>(b4)[j];
+  }
+  if (EF & EPI_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) gelu2(v[j], v[j + 1]);
+  }
+  if (EF & EPI_OUT_F32) {
+    if (sp_ok) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (FULL || j < nvalid) g_f32[(long long)j * e.f_m0] = v[j];
+    }
+  }
+  if (EF & EPI_OUT_PLANES) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      uint32_t hw, lw;
+      split2(v[j], v[j + 1], hw, lw);
+      if (sp_ok) {
+        if (FULL || j < nvalid) {
+          unsigned short* d = g_pl + (long long)j * e.o_m0;
+          d[0] = (unsigned short)hw;
+          d[e.out_plane] = (unsigned short)lw;
+        }
+        if (FULL || j + 1 < nvalid) {
+          unsigned short* d = g_pl + (long long)(j + 1) * e.o_m0;
+          d[0] = (unsigned short)(hw >> 16);
+          d[e.out_plane] = (unsigned short)(lw >> 16);
+        }
+      }
+    }
+  }
+  if (do_stats) {
+    // per-channel sums over this warp's 32 positions (rows beyond the image contribute nothing), then one shared-memory atomic
+    // per channel and warp; the tile's totals go to the fp64 accumulators once per tile (epilogue_sp_flush)
+    float w[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      v[j] = sp_ok ? v[j] : 0.f;
+      w[j] = v[j] * v[j];
+    }
+    const float sq = warp_colsum32(w, lane);
+    const float sm = warp_colsum32(v, lane);
+    if (FULL || lane < nvalid) {
+      atomicAdd(s_stats + 2 * lane, sm);
+      atomicAdd(s_stats + 2 * lane + 1, sq);
+    }
+  }
+}
+
+template <class C>
+__device__ __forceinline__ void epilogue_sp(const UmmaParams& p, const Tile& ti, uint32_t tacc, int q, int sub, int lane, float* s_stats) {
+  constexpr uint32_t EF = C::EF;
+  const GemmOp& op = p.op;
+  const EpiParams& e = op.epi;
+  const int sp = ti.m0 + 32 * q + lane;
+  const bool sp_ok = sp < op.M;
+  const long long spc = sp_ok ? sp : op.M - 1;  // loads of the lanes beyond the image stay in bounds (their results are never stored)
+  const bool do_stats = (e.flags & EPI_ROW_STATS) != 0;
+  const long long cb = ti.n_begin;  // first channel of the tile
+  const float* g_add = nullptr;
+  const uint32_t* g_res = nullptr;  // the 32-bit word that holds position spc (rows start on even elements: sp_eligible)
+  float* g_f32 = nullptr;
+  unsigned short* g_pl = nullptr;
+  const bool odd = (spc & 1) != 0;
+  if (EF & EPI_ADD_F32) g_add = e.add + (long long)ti.z2 * e.add_z2 + cb * e.add_m0 + spc;
+  if (EF & EPI_RES_PLANES) g_res = reinterpret_cast<const uint32_t*>(e.res + (long long)ti.z2 * e.res_z2 + cb * e.res_m0) + (spc >> 1);
+  if (EF & EPI_OUT_F32) g_f32 = e.outf + (long long)ti.z2 * e.f_z2 + cb * e.f_m0 + spc;
+  if (EF & EPI_OUT_PLANES) g_pl = reinterpret_cast<unsigned short*>(e.out) + (long long)ti.z2 * e.o_z2 + cb * e.o_m0 + spc;
+  const float* bias = (e.flags & EPI_ROW_BIAS) ? e.row_bias + (long long)ti.z2 * e.rb_z2 + cb : nullptr;
+  const bool raff = (EF & EPI_RES_PLANES) && (e.flags & EPI_RES_AFFINE);
+  const float* res_a = raff ? e.res_a + (long long)ti.z2 * e.rsa_z2 + cb : nullptr;
+  const float* res_s = raff ? e.res_s + (long long)ti.z2 * e.rsa_z2 + cb : nullptr;
+  const int nch = (ti.n_count + 31) >> 5;
+  for (int c = sub; c < nch; c += kEpiWarps / 4) {
+    const int nvalid = min(32, ti.n_count - c * 32);
+    float v[32];
+    ptx::tmem_ld_32x32(tacc + c * 32, v);
+    ptx::tmem_ld_wait();
+    const long long co = (long long)c * 32;
+    if (nvalid == 32)
+      epilogue_sp_chunk<C, true>(e, v, nvalid, sp_ok, lane, g_add + co * e.add_m0, g_res + co * (e.res_m0 >> 1), odd, g_f32 + co * e.f_m0, g_pl + co * e.o_m0,
+                                 bias ? bias + co : nullptr, res_a ? res_a + co : nullptr, res_s ? res_s + co : nullptr, do_stats,
+                                 s_stats + 2 * co);
+    else
+      epilogue_sp_chunk<C, false>(e, v, nvalid, sp_ok, lane, g_add + co * e.add_m0, g_res + co * (e.res_m0 >> 1), odd, g_f32 + co * e.f_m0, g_pl + co * e.o_m0,
+                                  bias ? bias + co : nullptr, res_a ? res_a + co : nullptr, res_s ? res_s + co : nullptr, do_stats,
+                                  s_stats + 2 * co);
+  }
+}
+
+// the tile's per-channel sums (all twelve epilogue warps have added theirs) -> fp64 accumulators; the staging array is zero again
+// afterwards.  Named barrier 1 = the 384 epilogue threads.
+template <class C>
+__device__ __forceinline__ void epilogue_sp_flush(const UmmaParams& p, const Tile& ti, float* s_stats) {
+  const EpiParams& e = p.op.epi;
+  asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+  for (int i = (int)threadIdx.x - 128; i < 2 * C::BN; i += 32 * kEpiWarps) {
+    const int col = i >> 1;
+    if (col < ti.n_count) {
+      const float val = s_stats[i];
+      s_stats[i] = 0.f;
+      atomicAdd(e.stats + ((long long)ti.z2 * e.stats_z2 + ti.n_begin + col) * 2 + (i & 1), (double)val);
+    }
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+}
+
 template <class C>
 __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid_constant__ UmmaParams p) {
   constexpr int BN = C::BN, BK = C::BK, STAGES = C::STAGES;
@@ -577,6 +768,11 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GemmOp& op = p.op;
   constexpr bool PAIR = C::PAIR;
+  // trace header row (iteration kTraceIters - 1): {globaltimer, clock64} at kernel entry / after the set-up / at the end
+  if (p.trace && threadIdx.x == 0) {
+    trace_put(p, kTraceIters - 1, 0, globaltimer_ns());
+    trace_put(p, kTraceIters - 1, 1, clock64());
+  }
   const uint32_t crank = PAIR ? ptx::cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs), 1 = peer
   constexpr int NCTA = PAIR ? 2 : 1;
 
@@ -594,6 +790,9 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
       ptx::mbar_init(tempty_bar(a), NCTA * kEpiWarps);  // one arrive per epilogue warp (of both CTAs)
     }
     ptx::fence_barrier_init();
+  }
+  if constexpr (C::SP) {
+    for (int i = threadIdx.x; i < 2 * BN; i += kThreadsUmma) reinterpret_cast<float*>(stg_all)[i] = 0.f;
   }
   if (warp == 2) {
     if constexpr (PAIR) {
@@ -613,6 +812,10 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
   // results (and the buffers it was still reading) may only be touched after this point
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (p.trace && threadIdx.x == 0) {
+    trace_put(p, kTraceIters - 1, 2, globaltimer_ns());
+    trace_put(p, kTraceIters - 1, 3, clock64());
+  }
 
   const long long total = p.tiles ? p.n_listed : (long long)p.tiles_m * p.tiles_n * op.Z1 * op.Z2;
   const long long t_first = PAIR ? (blockIdx.x >> 1) : blockIdx.x, t_step = PAIR ? (gridDim.x >> 1) : gridDim.x;
@@ -621,11 +824,19 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
     // ===================== TMA producer (whole warp walks the loop, one elected lane issues) =====================
     int stage = 0;
     uint32_t phase = 0;
+    uint32_t it = 0;
     Tile ti;
     for (long long t = t_first; t < total; t += t_step) {
       if (!decode_tile<BN, BK, C::TILE_M>(p, t, ti)) continue;
       const int az1 = ti.z1 * p.a_z1_on, az2 = ti.z2 * p.a_z2_on, bz1 = ti.z1 * p.b_z1_on, bz2 = ti.z2 * p.b_z2_on;
+      long long tr_wait = 0;
+      if (p.trace && lane == 0) trace_put(p, it, 4, clock64());
       for (int kc = 0; kc < ti.num_kc; ++kc) {
+        if (p.trace) {
+          const long long c0 = clock64();
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          tr_wait += clock64() - c0;
+        } else
         ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
         if (ptx::elect_one()) {
           const uint32_t fb = full_bar(stage);
@@ -640,22 +851,18 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
             // the MMA takes the first N/2 accumulator columns from the leader's B tile and the rest from the peer's
             const int n_eff = (ti.n_count + 15) & ~15;
             const int mrow = ti.m0 + 128 * (int)crank, ncol = ti.n_begin + (n_eff >> 1) * (int)crank;
+            // one box carries both planes; MN-major tiles are stored [64-wide atom][plane][k][64]
+            if (!C::A_MN) {
+              ptx::tma_load_5d_2sm(sA, &p.tmA, fb, k0, mrow, az1, az2, 0);
+            } else {
 #pragma unroll
-            for (int pl = 0; pl < 2; ++pl) {
-              if (!C::A_MN) {
-                ptx::tma_load_5d_2sm(sA + pl * C::A_PLANE, &p.tmA, fb, k0, mrow, az1, az2, pl);
-              } else {
+              for (int a = 0; a < 2; ++a) ptx::tma_load_5d_2sm(sA + a * C::MN_ATOM, &p.tmA, fb, mrow + 64 * a, k0, az1, az2, 0);
+            }
+            if (!C::B_MN) {
+              ptx::tma_load_5d_2sm(sB, &p.tmB, fb, k0, ncol, bz1, bz2, 0);
+            } else {
 #pragma unroll
-                for (int a = 0; a < 2; ++a)
-                  ptx::tma_load_5d_2sm(sA + pl * C::A_PLANE + a * BK * 128, &p.tmA, fb, mrow + 64 * a, k0, az1, az2, pl);
-              }
-              if (!C::B_MN) {
-                ptx::tma_load_5d_2sm(sB + pl * C::B_PLANE, &p.tmB, fb, k0, ncol, bz1, bz2, pl);
-              } else {
-#pragma unroll
-                for (int a = 0; a < C::BNL / 64; ++a)
-                  ptx::tma_load_5d_2sm(sB + pl * C::B_PLANE + a * BK * 128, &p.tmB, fb, ncol + 64 * a, k0, bz1, bz2, pl);
-              }
+              for (int a = 0; a < C::BNL / 64; ++a) ptx::tma_load_5d_2sm(sB + a * C::MN_ATOM, &p.tmB, fb, ncol + 64 * a, k0, bz1, bz2, 0);
             }
           } else if (p.dbg & 2) {
             ptx::mbar_arrive(fb);
@@ -669,36 +876,30 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
               // is a K offset of op.K on the B map
               const uint32_t sBc = sA + 4 * C::A_PLANE;
 #pragma unroll
-              for (int part = 0; part < 2; ++part)
-#pragma unroll
-                for (int pl = 0; pl < 2; ++pl) {
-                  if constexpr (C::CT) {
-                    // grouped form: n tile = group (BN == group_n), which contracts its own k range of each part of A
-                    const int ka = k0 + part * (op.group_n ? op.a_part_k : op.K) + (op.group_n ? ti.tn * op.group_n : 0);
-                    ptx::tma_load_5d(sA + (2 * part + pl) * C::A_PLANE, &p.tmA, fb, ka, ti.m0, az1, az2, pl);
-                    ptx::tma_load_5d(sBc + (2 * part + pl) * C::B_PLANE, &p.tmB, fb, k0, ti.n_begin, bz1, part, pl);
-                  } else {
-                    ptx::tma_load_5d(sA + (2 * part + pl) * C::A_PLANE, &p.tmA, fb, k0, ti.m0, az1, part, pl);
-                    ptx::tma_load_5d(sBc + (2 * part + pl) * C::B_PLANE, &p.tmB, fb, k0 + part * op.K, ti.n_begin, bz1, bz2, pl);
-                  }
+              for (int part = 0; part < 2; ++part) {
+                if constexpr (C::CT) {
+                  // grouped form: n tile = group (BN == group_n), which contracts its own k range of each part of A
+                  const int ka = k0 + part * (op.group_n ? op.a_part_k : op.K) + (op.group_n ? ti.tn * op.group_n : 0);
+                  ptx::tma_load_5d(sA + 2 * part * C::A_PLANE, &p.tmA, fb, ka, ti.m0, az1, az2, 0);
+                  ptx::tma_load_5d(sBc + 2 * part * C::B_PLANE, &p.tmB, fb, k0, ti.n_begin, bz1, part, 0);
+                } else {
+                  ptx::tma_load_5d(sA + 2 * part * C::A_PLANE, &p.tmA, fb, k0, ti.m0, az1, part, 0);
+                  ptx::tma_load_5d(sBc + 2 * part * C::B_PLANE, &p.tmB, fb, k0 + part * op.K, ti.n_begin, bz1, bz2, 0);
                 }
-            } else
-#pragma unroll
-            for (int pl = 0; pl < 2; ++pl) {
+              }
+            } else {
               if (!C::A_MN) {
-                ptx::tma_load_5d(sA + pl * C::A_PLANE, &p.tmA, fb, k0, ti.m0, az1, az2, pl);
+                ptx::tma_load_5d(sA, &p.tmA, fb, k0, ti.m0, az1, az2, 0);
               } else {
-                // 64-wide MN atoms, each [BK rows][128 B]
+                // 64-wide MN atoms, each [plane][BK rows][128 B]
 #pragma unroll
-                for (int a = 0; a < 2; ++a)
-                  ptx::tma_load_5d(sA + pl * C::A_PLANE + a * BK * 128, &p.tmA, fb, ti.m0 + 64 * a, k0, az1, az2, pl);
+                for (int a = 0; a < 2; ++a) ptx::tma_load_5d(sA + a * C::MN_ATOM, &p.tmA, fb, ti.m0 + 64 * a, k0, az1, az2, 0);
               }
               if (!C::B_MN) {
-                ptx::tma_load_5d(sB + pl * C::B_PLANE, &p.tmB, fb, k0, ti.n_begin, bz1, bz2, pl);
+                ptx::tma_load_5d(sB, &p.tmB, fb, k0, ti.n_begin, bz1, bz2, 0);
               } else {
 #pragma unroll
-                for (int a = 0; a < BN / 64; ++a)
-                  ptx::tma_load_5d(sB + pl * C::B_PLANE + a * BK * 128, &p.tmB, fb, ti.n_begin + 64 * a, k0, bz1, bz2, pl);
+                for (int a = 0; a < BN / 64; ++a) ptx::tma_load_5d(sB + a * C::MN_ATOM, &p.tmB, fb, ti.n_begin + 64 * a, k0, bz1, bz2, 0);
               }
             }
           }
@@ -706,98 +907,143 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
+      if (p.trace && lane == 0) {
+        trace_put(p, it, 5, tr_wait);
+        trace_put(p, it, 6, clock64());
+      }
+      ++it;
     }
   } else if (warp == 1 && crank == 0) {
     // ===================== MMA issuer (warp-uniform control flow keeps the descriptors in uniform registers) ==========
     // K-major (64B swizzle for BK = 32, 128B for BK = 64): rows of 2*BK bytes, 8-row groups SBO apart; a K-step is
     // 32 bytes inside the swizzled row.  MN-major (128B swizzle): [k][64 mn] atoms, 8-k groups SBO = 1024 B apart, the next
     // 64-mn atom LBO = BK*128 B away; a K-step is 16 k-rows = 2048 B.  Descriptor address fields are in 16-byte units.
-    const uint64_t descA0 = C::A_MN ? ptx::smem_desc(0, BK * 128, 1024, 2u) : ptx::smem_desc(0, 0, 8 * BK * 2, C::K_LAYOUT);
-    const uint64_t descB0 = C::B_MN ? ptx::smem_desc(0, BK * 128, 1024, 2u) : ptx::smem_desc(0, 0, 8 * BK * 2, C::K_LAYOUT);
+    const uint64_t descA0 = C::A_MN ? ptx::smem_desc(0, C::MN_ATOM, 1024, 2u) : ptx::smem_desc(0, 0, 8 * BK * 2, C::K_LAYOUT);
+    const uint64_t descB0 = C::B_MN ? ptx::smem_desc(0, C::MN_ATOM, 1024, 2u) : ptx::smem_desc(0, 0, 8 * BK * 2, C::K_LAYOUT);
     constexpr uint32_t kstepA = (C::A_MN ? 2048 : 32) >> 4, kstepB = (C::B_MN ? 2048 : 32) >> 4;
     int stage = 0;
     uint32_t phase = 0;
     uint32_t it = 0;
     Tile ti;
+    const int dbg = p.dbg, nterms = p.nterms, op_K = op.K, op_ksplit = op.k_split;
+    const bool tracing = p.trace != nullptr, batch2 = p.mma_batch != 0;
     for (long long t = t_first; t < total; t += t_step) {
       if (!decode_tile<BN, BK, C::TILE_M>(p, t, ti)) continue;
       const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
+      if (p.trace && lane == 0) trace_put(p, it, 0, clock64());
       ptx::mbar_wait(tempty_bar(as), aph ^ 1u);
       ptx::tc_fence_after();
+      long long tr_wait = 0;
+      if (p.trace && lane == 0) {
+        trace_put(p, it, 1, clock64());
+        trace_put(p, it, 13, ((long long)ti.num_kc << 32) | (uint32_t)ti.n_count);
+      }
       const int n_eff = (ti.n_count + 15) & ~15;
       const uint32_t idesc = ptx::instr_desc_bf16(C::TILE_M, n_eff, C::A_MN ? 1 : 0, C::B_MN ? 1 : 0);
       const uint32_t tmem_d = tmem_base + as * (C::NACC * BN);
-      for (int kc = 0; kc < ti.num_kc; ++kc) {
-        ptx::mbar_wait(full_bar(stage), phase);
-        ptx::tc_fence_after();
-        if (ptx::elect_one()) {
-          const uint32_t sA = sbase + stage * C::STAGE;
-          const uint64_t a_hi = descA0 + (uint64_t)(sA >> 4), a_lo = a_hi + (uint64_t)(C::A_PLANE >> 4);
-          const uint64_t b_hi = a_hi - descA0 + descB0 + (uint64_t)((2 * C::A_PLANE) >> 4), b_lo = b_hi + (uint64_t)(C::B_PLANE >> 4);
-          if constexpr (C::CPLX) {
-            // planes in the stage: Ar_hi Ar_lo Ai_hi Ai_lo | Br_hi Br_lo Bi_hi Bi_lo
-            constexpr uint64_t AP = C::A_PLANE >> 4, BP = C::B_PLANE >> 4;
-            const uint64_t b0 = a_hi - descA0 + descB0 + 4 * AP;
-            const uint32_t tmem_r = tmem_base + as * (2 * BN), tmem_i = tmem_r + BN;
-            const uint32_t ineg = idesc | (1u << 13);  // negate A: -Ai * Bi
+      // all MMAs of the K-chunk kc (operands in ring slot st) + the commit that frees the slot; called by the elected lane
+      auto issue_stage = [&](int st, int kc) {
+        const uint32_t sA = sbase + st * C::STAGE;
+        const uint64_t a_hi = descA0 + (uint64_t)(sA >> 4), a_lo = a_hi + (uint64_t)(C::A_LO >> 4);
+        const uint64_t b_hi = a_hi - descA0 + descB0 + (uint64_t)((2 * C::A_PLANE) >> 4), b_lo = b_hi + (uint64_t)(C::B_LO >> 4);
+        if constexpr (C::CPLX) {
+          // planes in the stage: Ar_hi Ar_lo Ai_hi Ai_lo | Br_hi Br_lo Bi_hi Bi_lo
+          constexpr uint64_t AP = C::A_PLANE >> 4, BP = C::B_PLANE >> 4;
+          const uint64_t b0 = a_hi - descA0 + descB0 + 4 * AP;
+          const uint32_t tmem_r = tmem_base + as * (2 * BN), tmem_i = tmem_r + BN;
+          const uint32_t ineg = idesc | (1u << 13);  // negate A: -Ai * Bi
 #pragma unroll
-            for (int kk = 0; kk < BK / 16; ++kk) {
-              const uint64_t ar_h = a_hi + kk * kstepA, ar_l = ar_h + AP, ai_h = ar_h + 2 * AP, ai_l = ar_h + 3 * AP;
-              const uint64_t br_h = b0 + kk * kstepB, br_l = br_h + BP, bi_h = br_h + 2 * BP, bi_l = br_h + 3 * BP;
-              const uint32_t first = (kc | kk) != 0 ? 1u : 0u;
-              ptx::umma_bf16(tmem_r, ar_h, br_h, idesc, first);
-              ptx::umma_bf16(tmem_r, ar_h, br_l, idesc, 1u);
-              ptx::umma_bf16(tmem_r, ar_l, br_h, idesc, 1u);
-              ptx::umma_bf16(tmem_r, ai_h, bi_h, ineg, 1u);
-              ptx::umma_bf16(tmem_r, ai_h, bi_l, ineg, 1u);
-              ptx::umma_bf16(tmem_r, ai_l, bi_h, ineg, 1u);
-              ptx::umma_bf16(tmem_i, ai_h, br_h, idesc, first);
-              ptx::umma_bf16(tmem_i, ai_h, br_l, idesc, 1u);
-              ptx::umma_bf16(tmem_i, ai_l, br_h, idesc, 1u);
-              ptx::umma_bf16(tmem_i, ar_h, bi_h, idesc, 1u);
-              ptx::umma_bf16(tmem_i, ar_h, bi_l, idesc, 1u);
-              ptx::umma_bf16(tmem_i, ar_l, bi_h, idesc, 1u);
-            }
-          } else if constexpr (PAIR) {
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t ar_h = a_hi + kk * kstepA, ar_l = ar_h + AP, ai_h = ar_h + 2 * AP, ai_l = ar_h + 3 * AP;
+            const uint64_t br_h = b0 + kk * kstepB, br_l = br_h + BP, bi_h = br_h + 2 * BP, bi_l = br_h + 3 * BP;
+            const uint32_t first = (kc | kk) != 0 ? 1u : 0u;
+            ptx::umma_bf16(tmem_r, ar_h, br_h, idesc, first);
+            ptx::umma_bf16(tmem_r, ar_h, br_l, idesc, 1u);
+            ptx::umma_bf16(tmem_r, ar_l, br_h, idesc, 1u);
+            ptx::umma_bf16(tmem_r, ai_h, bi_h, ineg, 1u);
+            ptx::umma_bf16(tmem_r, ai_h, bi_l, ineg, 1u);
+            ptx::umma_bf16(tmem_r, ai_l, bi_h, ineg, 1u);
+            ptx::umma_bf16(tmem_i, ai_h, br_h, idesc, first);
+            ptx::umma_bf16(tmem_i, ai_h, br_l, idesc, 1u);
+            ptx::umma_bf16(tmem_i, ai_l, br_h, idesc, 1u);
+            ptx::umma_bf16(tmem_i, ar_h, bi_h, idesc, 1u);
+            ptx::umma_bf16(tmem_i, ar_h, bi_l, idesc, 1u);
+            ptx::umma_bf16(tmem_i, ar_l, bi_h, idesc, 1u);
+          }
+        } else if constexpr (PAIR) {
+          // K-steps that lie entirely beyond K (zero-filled by TMA) are not issued (forward DFT: K = 360 -> 23 of 24)
+          const int kk_n = min(BK / 16, (op_K - (ti.k_begin + kc * BK) + 15) >> 4);
 #pragma unroll
-            for (int kk = 0; kk < BK / 16; ++kk) {
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            if (kk < kk_n) {
               ptx::umma_bf16_2sm(tmem_d, a_hi + kk * kstepA, b_hi + kk * kstepB, idesc, (kc | kk) != 0 ? 1u : 0u);
               ptx::umma_bf16_2sm(tmem_d, a_hi + kk * kstepA, b_lo + kk * kstepB, idesc, 1u);
               ptx::umma_bf16_2sm(tmem_d, a_lo + kk * kstepA, b_hi + kk * kstepB, idesc, 1u);
             }
-          } else if (!(p.dbg & 4)) {
-            // butterfly mode: the chunks from k_split on go to the second accumulator (k_split is a multiple of BK)
-            const int k0 = ti.k_begin + kc * BK;
-            const bool second = C::BFLY && k0 >= op.k_split;
-            const uint32_t tmem_t = tmem_d + (second ? BN : 0);
-            const bool fresh = kc == 0 || (C::BFLY && k0 == op.k_split);
+          }
+        } else if (!(dbg & 4)) {
+          // butterfly mode: the chunks from k_split on go to the second accumulator (k_split is a multiple of BK)
+          const int k0 = ti.k_begin + kc * BK;
+          const bool second = C::BFLY && k0 >= op_ksplit;
+          const uint32_t tmem_t = tmem_d + (second ? BN : 0);
+          const bool fresh = kc == 0 || (C::BFLY && k0 == op_ksplit);
+          const int kk_n = min(BK / 16, (op_K - k0 + 15) >> 4);  // K-steps entirely beyond K are not issued
 #pragma unroll
-            for (int kk = 0; kk < BK / 16; ++kk) {
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            if (kk < kk_n) {
               ptx::umma_bf16(tmem_t, a_hi + kk * kstepA, b_hi + kk * kstepB, idesc, (fresh && kk == 0) ? 0u : 1u);
-              if (p.nterms == 3) {
+              if (nterms == 3) {
                 ptx::umma_bf16(tmem_t, a_hi + kk * kstepA, b_lo + kk * kstepB, idesc, 1u);
                 ptx::umma_bf16(tmem_t, a_lo + kk * kstepA, b_hi + kk * kstepB, idesc, 1u);
               }
             }
           }
-          if constexpr (PAIR) ptx::umma_commit_2sm(empty_bar(stage));  // frees the slot in both CTAs
-          else ptx::umma_commit(empty_bar(stage));                     // frees the smem slot when these MMAs retire
+        }
+        if constexpr (PAIR) ptx::umma_commit_2sm(empty_bar(st));  // frees the slot in both CTAs
+        else ptx::umma_commit(empty_bar(st));                     // frees the smem slot when these MMAs retire
+      };
+      for (int kc = 0; kc < ti.num_kc;) {
+        if (tracing) {
+          const long long c0 = clock64();
+          ptx::mbar_wait(full_bar(stage), phase);
+          tr_wait += clock64() - c0;
+        } else {
+          ptx::mbar_wait(full_bar(stage), phase);
+        }
+        // The barrier round trip (wait, fence, election, commit, re-convergence) is ~250 clocks of serial latency per ring slot,
+        // which the tensor pipe's short queue does not hide when a slot holds only 6 MMAs of <= 96 clocks: when the NEXT slot
+        // has landed too (non-blocking test), its MMAs are issued in the same round.
+        const int stage2 = (stage + 1 == STAGES) ? 0 : stage + 1;
+        const uint32_t phase2 = (stage + 1 == STAGES) ? (phase ^ 1u) : phase;
+        bool two = false;
+        if (batch2 && kc + 1 < ti.num_kc) two = __all_sync(0xffffffffu, ptx::mbar_test_wait(full_bar(stage2), phase2));
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          issue_stage(stage, kc);
+          if (two) issue_stage(stage2, kc + 1);
         }
         __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        const int adv = two ? 2 : 1;
+        kc += adv;
+        stage += adv;
+        if (stage >= STAGES) { stage -= STAGES; phase ^= 1u; }
       }
       if (ptx::elect_one()) {  // accumulator ready for the epilogue (of both CTAs)
         if constexpr (PAIR) ptx::umma_commit_2sm(tfull_bar(as));
         else ptx::umma_commit(tfull_bar(as));
       }
       __syncwarp();
+      if (p.trace && lane == 0) {
+        trace_put(p, it, 2, tr_wait);
+        trace_put(p, it, 3, clock64());
+      }
       ++it;
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int q = warp & 3;           // TMEM lane quarter this warp may access (warp id % 4)
     const int sub = (warp - 4) >> 2;  // which of the kEpiWarps/4 warps of the quarter
-    uint8_t* stg = stg_all + (warp - 4) * kStgBytesPerWarp;
+    uint8_t* stg = C::SP ? stg_all : stg_all + (warp - 4) * kStgBytesPerWarp;
     uint32_t it = 0;
     Tile ti;
     for (long long t = t_first; t < total; t += t_step) {
@@ -805,18 +1051,27 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
       const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
       ti.m0 += 128 * (int)crank;  // pair mode: this CTA owns the second 128 rows of the 256-row tile
       if constexpr (C::NC) epilogue_nc_prefetch<C>(p, ti, q, sub, lane);
+      const bool tr = p.trace && lane == 0 && (warp == 4 || warp == 15);
+      const int trs = warp == 4 ? 7 : 10;
+      if (tr) trace_put(p, it, trs, clock64());
       ptx::mbar_wait(tfull_bar(as), aph);
       ptx::tc_fence_after();
+      if (tr) trace_put(p, it, trs + 1, clock64());
       const uint32_t tacc = tmem_base + as * (C::NACC * BN) + ((uint32_t)(32 * q) << 16);
       if (!(p.dbg & 1)) {
-        if constexpr (C::NC) epilogue_nc<C>(p, ti, tacc, q, sub, lane, stg);
+        if constexpr (C::SP) epilogue_sp<C>(p, ti, tacc, q, sub, lane, reinterpret_cast<float*>(stg_all));
+        else if constexpr (C::NC) epilogue_nc<C>(p, ti, tacc, q, sub, lane, stg);
         else epilogue_rowc<C>(p, ti, tacc, q, sub, lane, stg);
       }
       ptx::tc_fence_before();
       __syncwarp();
+      if (tr) trace_put(p, it, trs + 2, clock64());
       if (lane == 0) {
         if constexpr (PAIR) ptx::mbar_arrive_leader(tempty_bar(as));
         else ptx::mbar_arrive(tempty_bar(as));
+      }
+      if constexpr (C::SP) {
+        if ((op.epi.flags & EPI_ROW_STATS) && !(p.dbg & 1)) epilogue_sp_flush<C>(p, ti, reinterpret_cast<float*>(stg_all));
       }
       ++it;
     }
@@ -825,6 +1080,10 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
   ptx::tc_fence_before();
   if constexpr (PAIR) ptx::cluster_sync();  // the peer may still read this CTA's B half / signal its barriers
   else __syncthreads();
+  if (p.trace && threadIdx.x == 0) {
+    trace_put(p, kTraceIters - 1, 4, globaltimer_ns());
+    trace_put(p, kTraceIters - 1, 5, clock64());
+  }
   if (warp == 2) {
     ptx::tc_fence_after();
     if constexpr (PAIR) ptx::tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
@@ -866,7 +1125,8 @@ int sm_count() {
 void make_tmap(CUtensorMap* tm, const Operand& o, bool mn_major, long long rows, long long kext, int Z1, int Z2,
                int box_inner, int box_outer, CUtensorMapSwizzle swz, int* z1_on, int* z2_on, const char* name) {
   cuuint64_t dims[5], strides[4];
-  cuuint32_t box[5] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer, 1, 1, 1}, estr[5] = {1, 1, 1, 1, 1};
+  // one box = the tile of BOTH planes (hi, lo): half the TMA instructions per stage (the producer warp is issue-bound otherwise)
+  cuuint32_t box[5] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer, 1, 1, 2}, estr[5] = {1, 1, 1, 1, 1};
   if (!mn_major) {
     dims[0] = (cuuint64_t)kext;
     dims[1] = (cuuint64_t)rows;
@@ -900,13 +1160,52 @@ thread_local int t_scalar_store = 0;  // set by dispatch() for the launch it is 
 
 // ---- tile lists of the triangular ops (see UmmaParams::tiles) ----
 struct TileKey {
-  int M, N, K, Z1, Z2, flags, tile_m, bn, bk, m_fastest;
+  int M, N, K, Z1, Z2, flags, tile_m, bn, bk, m_fastest, workers;
   bool operator<(const TileKey& o) const { return memcmp(this, &o, sizeof(TileKey)) < 0; }
 };
 struct TileList {
   DevBuf buf;
   long long n = 0;
 };
+
+// Dense ops with several N tiles per M tile (forward DFT: N = 2 mmax = 362 -> a 256-wide and a 112-wide tile): the implicit walk
+// gives worker w the tiles w, w + G, ... and with an even G every worker only ever sees ONE of the two N tiles, i.e. half the
+// workers do 2.3x the MMA work of the others.  Listed order instead: worker w takes every N tile of M tile w, then of M tile
+// w + G, ... (the second read of the A tile hits L2 right after the first); slots beyond the last M tile are empty entries.
+const TileList& grouped_tile_list(const GemmOp& op, int tile_m, int bn, int workers) {
+  static std::mutex mu;
+  static std::map<TileKey, TileList> cache;
+  TileKey key;
+  memset(&key, 0, sizeof(key));
+  key.M = op.M; key.N = op.N; key.K = op.K; key.Z1 = op.Z1; key.Z2 = op.Z2;
+  key.flags = 16; key.tile_m = tile_m; key.bn = bn; key.workers = workers;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  const int tiles_m = (op.M + tile_m - 1) / tile_m, tiles_n = (op.N + bn - 1) / bn;
+  const long long groups = (long long)tiles_m * op.Z1 * op.Z2;
+  const long long rounds = (groups + workers - 1) / workers;
+  std::vector<int4> host;
+  host.reserve((size_t)(rounds * tiles_n * workers));
+  for (long long r = 0; r < rounds; ++r)
+    for (int tn = 0; tn < tiles_n; ++tn)
+      for (int w = 0; w < workers; ++w) {
+        const long long g = r * workers + w;
+        if (g >= groups) {
+          host.push_back(make_int4(0, tiles_n, 0, 0));  // empty slot: decode_tile() rejects it (no columns)
+          continue;
+        }
+        const int tm = (int)(g % tiles_m);
+        const long long z = g / tiles_m;
+        host.push_back(make_int4(tm, tn, (int)(z / op.Z2), (int)(z % op.Z2)));
+      }
+  while (!host.empty() && host.back().y == tiles_n) host.pop_back();
+  TileList& tl = cache[key];
+  tl.n = (long long)host.size();
+  tl.buf.ensure(std::max<size_t>(16, host.size() * sizeof(int4)));
+  if (!host.empty()) ACE_CHECK_CUDA(cudaMemcpy(tl.buf.p, host.data(), host.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  return tl;
+}
 
 const TileList& tile_list(const GemmOp& op, int tile_m, int bn, int bk, int m_fastest) {
   static std::mutex mu;
@@ -947,8 +1246,19 @@ const TileList& tile_list(const GemmOp& op, int tile_m, int bn, int bk, int m_fa
   return tl;
 }
 
+// SP variants run the caller's op with the operand roles exchanged (the epilogue parameters keep the caller's meaning)
+inline GemmOp exchanged(const GemmOp& o) {
+  GemmOp x = o;
+  x.M = o.N;
+  x.N = o.M;
+  x.A = o.B;
+  x.B = o.A;
+  return x;
+}
+
 template <class C>
-void launch(const GemmOp& op, cudaStream_t stream) {
+void launch(const GemmOp& op_in, cudaStream_t stream) {
+  const GemmOp op = C::SP ? exchanged(op_in) : op_in;
   static bool attr_set = false;
   if (!attr_set) {
     ACE_CHECK_CUDA(cudaFuncSetAttribute(gemm_umma_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -960,6 +1270,7 @@ void launch(const GemmOp& op, cudaStream_t stream) {
   p.tiles_n = (op.N + C::BN - 1) / C::BN;
   p.nterms = options().split_terms;
   p.dbg = options().dbg;
+  p.mma_batch = options().mma_batch;
   p.scalar_store = t_scalar_store;
   // the operand that is re-read by neighbouring tiles should be the small one: keep the big streaming operand's
   // tile shared by consecutive CTAs (they run concurrently, so the second reader hits L2)
@@ -995,6 +1306,14 @@ void launch(const GemmOp& op, cudaStream_t stream) {
     if (tl.n == 0) return;  // nothing to compute
     p.tiles = tl.buf.as<int4>();
     p.n_listed = total = tl.n;
+  } else if (!p.m_fastest && p.tiles_n > 1 && options().tile_list && options().group_order &&
+             4 * (op.N - (p.tiles_n - 1) * C::BN) < 3 * C::BN) {  // a last N tile much narrower than the others (measured: -5 us forward DFT; +6 us inverse DFT, whose two tiles are 96 and 84 wide)
+    const int workers = C::PAIR ? sm_count() / 2 : sm_count();
+    if ((long long)p.tiles_m * op.Z1 * op.Z2 >= workers) {
+      const TileList& tl = grouped_tile_list(op, C::TILE_M, C::BN, workers);
+      p.tiles = tl.buf.as<int4>();
+      p.n_listed = total = tl.n;
+    }
   }
   int grid = C::PAIR ? 2 * (int)std::min<long long>(total, sm_count() / 2) : (int)std::min<long long>(total, sm_count());
   cudaLaunchConfig_t cfg = {};
@@ -1036,7 +1355,31 @@ void launch(const GemmOp& op, cudaStream_t stream) {
     attr[cfg.numAttrs].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
     ++cfg.numAttrs;
   }
+  p.trace = nullptr;
+  static DevBuf trace_buf;
+  const size_t trace_bytes = (size_t)grid * kTraceIters * kTraceSlots * sizeof(long long);
+  const char* trace_path = options().trace ? getenv("ACE_B200_TRACE_FILE") : nullptr;
+  if (trace_path) {
+    trace_buf.ensure((size_t)sm_count() * kTraceIters * kTraceSlots * sizeof(long long));
+    ACE_CHECK_CUDA(cudaMemsetAsync(trace_buf.p, 0, trace_bytes, stream));
+    p.trace = trace_buf.as<long long>();
+  }
   ACE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_umma_kernel<C>, p));
+  if (trace_path) {
+    // development only (never under graph capture): record = {char name[64], int grid, iters, slots, stages, tile_m, bn, bk, pair} + samples
+    std::vector<long long> host(trace_bytes / sizeof(long long));
+    ACE_CHECK_CUDA(cudaStreamSynchronize(stream));
+    ACE_CHECK_CUDA(cudaMemcpy(host.data(), trace_buf.p, trace_bytes, cudaMemcpyDeviceToHost));
+    if (FILE* f = fopen(trace_path, "ab")) {
+      char name[64] = {0};
+      strncpy(name, op.name ? op.name : "?", 63);
+      const int hdr[8] = {grid, kTraceIters, kTraceSlots, C::STAGES, C::TILE_M, C::BN, C::BK, C::PAIR ? 1 : 0};
+      fwrite(name, 1, 64, f);
+      fwrite(hdr, sizeof(int), 8, f);
+      fwrite(host.data(), 1, trace_bytes, f);
+      fclose(f);
+    }
+  }
   after_launch(op.name);
   g_umma_count.fetch_add(1, std::memory_order_relaxed);
 }
@@ -1214,8 +1557,45 @@ bool launch_conv_bn(const GemmOp& op, const Variant& v, cudaStream_t s) {
     default: return false;
   }
 }
+// SP variants (Cfg::SP): channels on the accumulator columns, N tile 256 when the channel count is a multiple of it, else 192
+template <int BN>
+bool launch_conv_sp_bn(const GemmOp& op, const Variant& v, cudaStream_t s) {
+  switch (v.ef) {
+    case G | P: launch<Cfg<BN, true, false, G | P, false, 32, false, true, false, true>>(op, s); return true;
+    case AD | P: launch<Cfg<BN, true, false, AD | P, false, 32, false, true, false, true>>(op, s); return true;
+    case AD | G | P: launch<Cfg<BN, true, false, AD | G | P, false, 32, false, true, false, true>>(op, s); return true;
+    case RS | P: launch<Cfg<BN, true, false, RS | P, false, 32, false, true, false, true>>(op, s); return true;
+    case P: launch<Cfg<BN, true, false, P, false, 32, false, true, false, true>>(op, s); return true;
+    case F: launch<Cfg<BN, true, false, F, false, 32, false, true, false, true>>(op, s); return true;
+    default: return false;
+  }
+}
+bool sp_eligible(const GemmOp& op, const Variant& v) {
+  const EpiParams& e = op.epi;
+  if (!v.nc || v.a_mn || !v.b_mn || op.M < 128 || (op.M & 31) || e.mdiv < op.M || op.Z1 != 1) return false;  // whole 32-channel chunks
+  // the per-channel vectors are read 16 bytes at a time from a 32-channel boundary
+  auto vec_ok = [](const float* p, long long z2) { return p && (((uintptr_t)p) & 15) == 0 && (z2 & 3) == 0; };
+  if ((e.flags & EPI_ROW_BIAS) && !vec_ok(e.row_bias, e.rb_z2)) return false;
+  if ((e.flags & EPI_RES_AFFINE) && !(vec_ok(e.res_a, e.rsa_z2) && vec_ok(e.res_s, e.rsa_z2))) return false;
+  if (e.flags & EPI_ROW_AFFINE) return false;
+  if ((op.epi.flags & EPI_RES_PLANES) && ((e.res_m0 | e.res_plane | e.res_z2) & 1 || (((uintptr_t)e.res) & 3))) return false;  // residual read as 32-bit words
+  // Where it pays (measured at ACE2 size, profiles/r02_sp_probe.jsonl): the exchanged main loop runs at the MMA-only time
+  // (no shared-memory contention), but its epilogue spends more instructions per element (2-byte stores, shuffle-reduced
+  // statistics), so it wins when the main loop is long (K >= 512: fc2) or the epilogue light (no addend / statistics), and
+  // never against the 256-row CTA-pair variants that channel counts of a multiple of 256 already use.
+  if (options().sp != 2) {
+    if (op.M % 256 == 0 || op.K < 256) return false;
+    if (e.flags & (EPI_ROW_STATS | EPI_ADD_F32 | EPI_RES_PLANES)) return false;
+  }
+  return true;
+}
+bool launch_conv_sp(const GemmOp& op, const Variant& v, cudaStream_t s) {
+  return (op.M % 256 == 0) ? launch_conv_sp_bn<256>(op, v, s) : launch_conv_sp_bn<192>(op, v, s);
+}
+
 bool launch_conv(const GemmOp& op, const Variant& v, cudaStream_t s) {
   if (!v.nc || v.a_mn || !v.b_mn) return false;
+  if (options().sp && sp_eligible(op, v) && launch_conv_sp(op, v, s)) return true;
   // CTA pairs pay off when no half tile is wasted (measured: fc1 M=768 111 -> 95 us; M=384 ops gain nothing)
   const bool want_pair = options().pair == 1 ? op.M > 128 : (options().pair < 0 && op.M % 256 == 0);
   if (want_pair && launch_conv_pair(op, v, s)) return true;

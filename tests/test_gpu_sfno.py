@@ -40,6 +40,8 @@ def test_net_matches_reference_vectors(name):
         ((64, 128), 5, 3, 64, 2, 3),
         ((48, 96), 4, 4, 128, 2, 2),     # mlp hidden 256 -> fc1 runs on the CTA-pair (cta_group::2) variant
         ((45, 96), 5, 3, 32, 2, 1),      # odd nlat (as 721x1440): element-wise store variants, still no SIMT fallback
+        ((45, 96), 5, 3, 128, 1, 2),     # odd nlat with the space-on-rows convolution variants (ragged last position tile)
+        ((36, 72), 3, 5, 384, 2, 2),     # ACE2 width: 192-channel column tiles, per-sample folded weights of two members
     ],
 )
 def test_net_tcgen05_path_vs_oracle(img, cin, cout, embed, layers, batch):
