@@ -101,6 +101,12 @@ extern "C" int ace_set_option(const char* key, int value) {
     options().mma_batch = value ? 1 : 0;
   } else if (!strcmp(key, "sp")) {
     options().sp = value;  // 0 off, 1 where it pays, 2 wherever eligible
+  } else if (!strcmp(key, "sp_tma")) {
+    options().sp_tma = value ? 1 : 0;
+  } else if (!strcmp(key, "bfly_pair")) {
+    options().bfly_pair = value ? 1 : 0;
+  } else if (!strcmp(key, "tile_serpentine")) {
+    options().tile_serpentine = value ? 1 : 0;
   } else if (!strcmp(key, "trace")) {
     options().trace = value ? 1 : 0;
   } else if (!strcmp(key, "umma_bk")) {

@@ -100,6 +100,9 @@ struct Options {
   int group_order = 1;  // dense ops with several N tiles: a worker takes all N tiles of its M tile back to back (0: implicit round-robin walk)
   int mma_batch = 1;  // tcgen05 kernel: MMAs of two ring slots per barrier round when both have landed (0: one slot per round)
   int sp = 1;        // 1x1 convolutions with >= 128 output channels run with the spatial positions on the accumulator rows (gemm_umma.cu, Cfg::SP)
+  int sp_tma = 1;    // SP variants store their split-plane output by TMA from a shared-memory tile (0: element-wise stores from registers)
+  int bfly_pair = 1; // butterfly inverse DFT on CTA pairs when the row count is a multiple of 256
+  int tile_serpentine = 1;  // tile lists of the triangular GEMMs: odd strata reversed so every worker's tile costs sum to about the same
   int trace = 0;     // development: per-tile clock samples of the tcgen05 kernel's roles appended to $ACE_B200_TRACE_FILE (tools/trace_report.py)
   int umma_bn = 0;   // 0 = choose per op; otherwise force the N tile of the K-major x K-major variants (192 / 256)
 };

@@ -59,6 +59,10 @@ struct UmmaParams {
   long long n_listed;
   // development trace (option "trace"): [CTA][tile iteration < kTraceIters][kTraceSlots] clock64 samples of the three roles
   long long* trace;
+  // SP variants with split-plane output: 4-D map (position, channel, sample, plane) of the output for the epilogue's TMA stores
+  // (sp_tma = 0: strides not 16-byte aligned -> element-wise stores from registers)
+  CUtensorMap tmO;
+  int sp_tma;
   int mma_batch;  // option "mma_batch": the MMA warp issues two ring slots per barrier round when both have landed
 };
 
@@ -79,7 +83,7 @@ constexpr int kStgBytesPerWarp = 2048;
 constexpr int kMaxSmem = 232448;  // 227 KB opt-in limit per CTA
 
 template <int BN_, bool A_MN_, bool B_MN_, uint32_t EF_, bool NC_, int BK_ = 32, bool CPLX_ = false, bool PAIR_ = false, bool BFLY_ = false,
-          bool SP_ = false>
+          bool SP_ = false, int SP_STAGES_ = 8>
 struct Cfg {
   // SP ("space on the rows"): a 1x1 convolution executed with the operand roles exchanged -- A = activations (MN-major, 256
   // spatial positions per CTA pair), B = weights (K-major, the output channels on the accumulator columns).  A thread of the
@@ -110,8 +114,14 @@ struct Cfg {
   static constexpr int MN_ATOM = 2 * BK * 128;  // MN-major tiles: one 64-wide atom = [plane][BK k-rows][128 B]; the lo plane sits BK * 128 B after the hi plane
   static constexpr int A_LO = A_MN ? BK * 128 : A_PLANE, B_LO = B_MN ? BK * 128 : B_PLANE;  // byte offset of the lo plane inside the tile
   static constexpr int STAGE = 2 * (CPLX ? 2 : 1) * (A_PLANE + B_PLANE);  // complex mode: {Ar, Ai} x {hi, lo}, then {Br, Bi} x {hi, lo}
-  static constexpr int STG_BYTES = SP ? 4096 : kEpiWarps * kStgBytesPerWarp;  // SP: per-channel statistics of the tile only
-  static constexpr int MAX_STAGES = 8;
+  // SP: per warp group (the four lane-quarter warps that share a 32-channel chunk) a [plane][32 channels][128 positions] bf16
+  // tile the output is stored from by TMA, then the per-channel statistics of the tile
+  static constexpr int SP_TILE = 2 * 32 * 128 * 2, SP_STATS = (kEpiWarps / 4) * SP_TILE;
+  static constexpr int STG_BYTES = SP ? SP_STATS + 2048 : kEpiWarps * kStgBytesPerWarp;
+  // SP: the epilogue reads its addend / residual with ordinary global loads, which need L1 lines to land in; with the whole
+  // 227 KB configured as shared memory hardly any are left (measured: those loads cost 24 - 37 us per launch).  Four ring
+  // slots keep the kernel inside the 164 KB carve-out, i.e. 64 KB of L1.
+  static constexpr int MAX_STAGES = SP_ ? SP_STAGES_ : 8;
   static constexpr int BAR_BYTES = (2 * MAX_STAGES + 4) * 8 + 16;
   static constexpr int STAGES_RAW = (kMaxSmem - 1024 - STG_BYTES - BAR_BYTES) / STAGE;
   static constexpr int STAGES = STAGES_RAW > MAX_STAGES ? MAX_STAGES : STAGES_RAW;
@@ -123,7 +133,7 @@ struct Cfg {
   static_assert(!SP || (PAIR && A_MN_ && !B_MN_ && !NC_ && !CPLX_ && !BFLY_), "SP mode: CTA pairs, MN-major activations x K-major weights");
   static constexpr int SMEM_BYTES = STAGES * STAGE + STG_BYTES + BAR_BYTES + 1024;  // + alignment slack
   static_assert(BN % (B_MN_ ? 64 : 32) == 0 && BN <= 256, "BN");
-  static_assert(!BFLY || (NC && !CPLX && !PAIR && !B_MN), "butterfly mode: NC epilogue, K-major B");
+  static_assert(!BFLY || (NC && !CPLX && !B_MN), "butterfly mode: NC epilogue, K-major B");
   static constexpr uint32_t K_LAYOUT = (BK == 64) ? 2u : 4u;  // K-major tiles: 128B swizzle (BK = 64) or 64B (BK = 32)
   static_assert(BK == 32 || BK == 64, "BK");
   static_assert(STAGES >= 2, "pipeline too shallow");
@@ -601,41 +611,55 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
-template <class C, bool FULL>
-__device__ __forceinline__ void epilogue_sp_chunk(const EpiParams& e, float (&v)[32], int nvalid, bool sp_ok, int lane, const float* g_add,
-                                                  const uint32_t* g_res, bool odd, float* g_f32, unsigned short* g_pl, const float* bias,
-                                                  const float* res_a, const float* res_s, bool do_stats, float* s_stats) {
-  constexpr uint32_t EF = C::EF;
-  const long long res_m0w = e.res_m0 >> 1, res_planew = e.res_plane >> 1;  // in 32-bit words (both even: sp_eligible)
-  // operands of 16 channels at a time: every load of the half is issued before the first one is used
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
+// operands of one 32-channel chunk for this thread's position, loaded into registers (issued a whole chunk ahead of their use:
+// before the accumulator barrier for the first chunk of a tile, before the previous chunk's arithmetic for the others)
+template <class C>
+struct SpOperands {
+  static constexpr uint32_t EF = C::EF;
+  static constexpr int NA = (EF & EPI_ADD_F32) ? 32 : 1, NR = (EF & EPI_RES_PLANES) ? 32 : 1;
+  float add[NA];
+  uint32_t rh[NR], rl[NR];  // the 32-bit words that hold this position's hi / lo residual element
+  __device__ __forceinline__ void load(const EpiParams& e, const float* g_add, const uint32_t* g_res, int nvalid) {
     if (EF & EPI_ADD_F32) {
-      float a[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) a[j] = (FULL || 16 * h + j < nvalid) ? __ldg(g_add + (long long)(16 * h + j) * e.add_m0) : 0.f;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[16 * h + j] += a[j];
+      for (int j = 0; j < NA; ++j) add[j] = (j < nvalid) ? __ldg(g_add + (long long)j * e.add_m0) : 0.f;
     }
     if (EF & EPI_RES_PLANES) {
-      // 32-bit loads of the word that holds this lane's element (lane pairs share a word; 16-bit non-coherent loads run at a
-      // fraction of the rate) through the coherent path: fc2 reads its residual from the buffer it overwrites in place
-      uint32_t rh[16], rl[16];
+      // 32-bit loads (lane pairs share a word; 16-bit non-coherent loads run at a fraction of the rate) through the coherent
+      // path: fc2 reads its residual from the buffer it overwrites in place
+      const long long m0w = e.res_m0 >> 1, planew = e.res_plane >> 1;  // in words (both even: sp_eligible)
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const bool ok = FULL || 16 * h + j < nvalid;
-        const uint32_t* r = g_res + (long long)(16 * h + j) * res_m0w;
-        rh[j] = ok ? *r : 0u;
-        rl[j] = ok ? r[res_planew] : 0u;
-      }
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float r = __uint_as_float(odd ? (rh[j] & 0xffff0000u) : (rh[j] << 16)) + __uint_as_float(odd ? (rl[j] & 0xffff0000u) : (rl[j] << 16));
-        if (res_a) v[16 * h + j] += fmaf(__ldg(res_a + 16 * h + j), r, __ldg(res_s + 16 * h + j));
-        else v[16 * h + j] += r;
+      for (int j = 0; j < NR; ++j) {
+        const uint32_t* r = g_res + (long long)j * m0w;
+        rh[j] = (j < nvalid) ? *r : 0u;
+        rl[j] = (j < nvalid) ? r[planew] : 0u;
       }
     }
   }
+  __device__ __forceinline__ void apply(float (&v)[32], bool odd, const float* res_a, const float* res_s) const {
+    if (EF & EPI_ADD_F32) {
+#pragma unroll
+      for (int j = 0; j < NA; ++j) v[j] += add[j];
+    }
+    if (EF & EPI_RES_PLANES) {
+#pragma unroll
+      for (int j = 0; j < NR; ++j) {
+        const float r = __uint_as_float(odd ? (rh[j] & 0xffff0000u) : (rh[j] << 16)) + __uint_as_float(odd ? (rl[j] & 0xffff0000u) : (rl[j] << 16));
+        if (res_a) v[j] += fmaf(__ldg(res_a + j), r, __ldg(res_s + j));
+        else v[j] += r;
+      }
+    }
+  }
+};
+
+// everything after the operands: bias, GELU, stores (staging tile or element-wise), statistics
+template <class C, bool FULL>
+__device__ __forceinline__ void epilogue_sp_chunk(const EpiParams& e, float (&v)[32], int nvalid, bool sp_ok, int lane, float* g_f32,
+                                                  unsigned short* g_pl, const float* bias, bool do_stats, float* s_stats,
+                                                  unsigned short* s_tile, int dbg) {
+  constexpr uint32_t EF = C::EF;
+  if (dbg & 8) do_stats = false;
+  if (dbg & 32) bias = nullptr;
   if (bias) {
     float4 b4[8];
 #pragma unroll
@@ -654,7 +678,20 @@ __device__ __forceinline__ void epilogue_sp_chunk(const EpiParams& e, float (&v)
         if (FULL || j < nvalid) g_f32[(long long)j * e.f_m0] = v[j];
     }
   }
-  if (EF & EPI_OUT_PLANES) {
+  if (dbg & 64) {
+  } else if ((EF & EPI_OUT_PLANES) && s_tile) {
+    // staging tile [plane][channel][128 positions] (s_tile points at this thread's position): a warp writes 64 contiguous
+    // bytes per channel and plane; the tile leaves by TMA (epilogue_sp)
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      uint32_t hw, lw;
+      split2(v[j], v[j + 1], hw, lw);
+      s_tile[j * 128] = (unsigned short)hw;
+      s_tile[(j + 1) * 128] = (unsigned short)(hw >> 16);
+      s_tile[32 * 128 + j * 128] = (unsigned short)lw;
+      s_tile[32 * 128 + (j + 1) * 128] = (unsigned short)(lw >> 16);
+    }
+  } else if (EF & EPI_OUT_PLANES) {
 #pragma unroll
     for (int j = 0; j < 32; j += 2) {
       uint32_t hw, lw;
@@ -691,8 +728,10 @@ __device__ __forceinline__ void epilogue_sp_chunk(const EpiParams& e, float (&v)
   }
 }
 
+// waits for the tile's accumulator itself (tfull barrier) so that the first chunk's operand loads are in flight meanwhile
 template <class C>
-__device__ __forceinline__ void epilogue_sp(const UmmaParams& p, const Tile& ti, uint32_t tacc, int q, int sub, int lane, float* s_stats) {
+__device__ __forceinline__ void epilogue_sp(const UmmaParams& p, const Tile& ti, uint32_t tacc, int q, int sub, int lane, uint8_t* stg_tiles,
+                                            float* s_stats, uint32_t tfull, uint32_t tfull_parity) {
   constexpr uint32_t EF = C::EF;
   const GemmOp& op = p.op;
   const EpiParams& e = op.epi;
@@ -715,20 +754,58 @@ __device__ __forceinline__ void epilogue_sp(const UmmaParams& p, const Tile& ti,
   const float* res_a = raff ? e.res_a + (long long)ti.z2 * e.rsa_z2 + cb : nullptr;
   const float* res_s = raff ? e.res_s + (long long)ti.z2 * e.rsa_z2 + cb : nullptr;
   const int nch = (ti.n_count + 31) >> 5;
+  const long long res_m0w = e.res_m0 >> 1;
+  // TMA-stored output: the four warps (lane quarters q) that share the chunk index `sub` fill one staging tile; named barrier
+  // 2 + sub synchronises them, the first lane of quarter 0 issues the store and waits for it before the tile is written again
+  const bool staged = (EF & EPI_OUT_PLANES) && p.sp_tma;
+  unsigned short* tile = reinterpret_cast<unsigned short*>(stg_tiles + sub * C::SP_TILE);
+  const bool issuer = q == 0 && lane == 0;
+  const bool skip = (p.dbg & 1) != 0;
+  // addend: prefetched a chunk ahead (32 registers); residual planes: loaded and applied 16 channels at a time inside the chunk
+  // (64 registers of prefetched words spill)
+  constexpr bool PREFETCH = (EF & EPI_ADD_F32) && !(EF & EPI_RES_PLANES);
+  SpOperands<C> ops;
+  if (PREFETCH && sub < nch && !skip && !(p.dbg & 16))
+    ops.load(e, g_add + (long long)sub * 32 * e.add_m0, g_res + (long long)sub * 32 * res_m0w, min(32, ti.n_count - sub * 32));
+  ptx::mbar_wait(tfull, tfull_parity);
+  ptx::tc_fence_after();
+  if (skip) return;
   for (int c = sub; c < nch; c += kEpiWarps / 4) {
     const int nvalid = min(32, ti.n_count - c * 32);
     float v[32];
     ptx::tmem_ld_32x32(tacc + c * 32, v);
     ptx::tmem_ld_wait();
     const long long co = (long long)c * 32;
+    if (!(p.dbg & 16)) {
+      if (PREFETCH) {
+        ops.apply(v, odd, nullptr, nullptr);
+        const int cn = c + kEpiWarps / 4;
+        if (cn < nch) ops.load(e, g_add + (long long)cn * 32 * e.add_m0, g_res + (long long)cn * 32 * res_m0w, min(32, ti.n_count - cn * 32));
+      } else if (EF & (EPI_ADD_F32 | EPI_RES_PLANES)) {
+        ops.load(e, g_add + co * e.add_m0, g_res + co * res_m0w, nvalid);
+        ops.apply(v, odd, (p.dbg & 32) ? nullptr : (res_a ? res_a + co : nullptr), res_s ? res_s + co : nullptr);
+      }
+    }
+    if (staged) {
+      if (issuer) ptx::bulk_wait_read0();  // the previous store has finished reading the tile
+      ptx::named_bar_sync(2 + sub, 128);
+    }
+    unsigned short* s_tile = staged ? tile + 32 * q + lane : nullptr;
     if (nvalid == 32)
-      epilogue_sp_chunk<C, true>(e, v, nvalid, sp_ok, lane, g_add + co * e.add_m0, g_res + co * (e.res_m0 >> 1), odd, g_f32 + co * e.f_m0, g_pl + co * e.o_m0,
-                                 bias ? bias + co : nullptr, res_a ? res_a + co : nullptr, res_s ? res_s + co : nullptr, do_stats,
-                                 s_stats + 2 * co);
+      epilogue_sp_chunk<C, true>(e, v, nvalid, sp_ok, lane, g_f32 + co * e.f_m0, g_pl + co * e.o_m0, bias ? bias + co : nullptr, do_stats,
+                                 s_stats + 2 * co, s_tile, p.dbg);
     else
-      epilogue_sp_chunk<C, false>(e, v, nvalid, sp_ok, lane, g_add + co * e.add_m0, g_res + co * (e.res_m0 >> 1), odd, g_f32 + co * e.f_m0, g_pl + co * e.o_m0,
-                                  bias ? bias + co : nullptr, res_a ? res_a + co : nullptr, res_s ? res_s + co : nullptr, do_stats,
-                                  s_stats + 2 * co);
+      epilogue_sp_chunk<C, false>(e, v, nvalid, sp_ok, lane, g_f32 + co * e.f_m0, g_pl + co * e.o_m0, bias ? bias + co : nullptr, do_stats,
+                                  s_stats + 2 * co, s_tile, p.dbg);
+    if (staged) {
+      ptx::fence_proxy_async_smem();  // the tile was written through the generic proxy, TMA reads it through the async proxy
+      ptx::named_bar_sync(2 + sub, 128);
+      if (issuer) {
+        // rows beyond the image and channels beyond the tensor are clipped by TMA
+        ptx::tma_store_4d(&p.tmO, ptx::smem_u32(tile), ti.m0, ti.n_begin + c * 32, ti.z2, 0);
+        ptx::bulk_commit();
+      }
+    }
   }
 }
 
@@ -792,7 +869,8 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
     ptx::fence_barrier_init();
   }
   if constexpr (C::SP) {
-    for (int i = threadIdx.x; i < 2 * BN; i += kThreadsUmma) reinterpret_cast<float*>(stg_all)[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * BN; i += kThreadsUmma) reinterpret_cast<float*>(stg_all + C::SP_STATS)[i] = 0.f;
+    if (warp == 0 && lane == 0) ptx::prefetch_tensormap(&p.tmO);
   }
   if (warp == 2) {
     if constexpr (PAIR) {
@@ -972,13 +1050,18 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
           }
         } else if constexpr (PAIR) {
           // K-steps that lie entirely beyond K (zero-filled by TMA) are not issued (forward DFT: K = 360 -> 23 of 24)
-          const int kk_n = min(BK / 16, (op_K - (ti.k_begin + kc * BK) + 15) >> 4);
+          const int k0 = ti.k_begin + kc * BK;
+          const int kk_n = min(BK / 16, (op_K - k0 + 15) >> 4);
+          // butterfly mode: the chunks from k_split on go to the second accumulator (k_split is a multiple of BK)
+          const bool second = C::BFLY && k0 >= op_ksplit;
+          const uint32_t tmem_t = tmem_d + (second ? BN : 0);
+          const bool fresh = kc == 0 || (C::BFLY && k0 == op_ksplit);
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk) {
             if (kk < kk_n) {
-              ptx::umma_bf16_2sm(tmem_d, a_hi + kk * kstepA, b_hi + kk * kstepB, idesc, (kc | kk) != 0 ? 1u : 0u);
-              ptx::umma_bf16_2sm(tmem_d, a_hi + kk * kstepA, b_lo + kk * kstepB, idesc, 1u);
-              ptx::umma_bf16_2sm(tmem_d, a_lo + kk * kstepA, b_hi + kk * kstepB, idesc, 1u);
+              ptx::umma_bf16_2sm(tmem_t, a_hi + kk * kstepA, b_hi + kk * kstepB, idesc, (fresh && kk == 0) ? 0u : 1u);
+              ptx::umma_bf16_2sm(tmem_t, a_hi + kk * kstepA, b_lo + kk * kstepB, idesc, 1u);
+              ptx::umma_bf16_2sm(tmem_t, a_lo + kk * kstepA, b_hi + kk * kstepB, idesc, 1u);
             }
           }
         } else if (!(dbg & 4)) {
@@ -1054,14 +1137,18 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
       const bool tr = p.trace && lane == 0 && (warp == 4 || warp == 15);
       const int trs = warp == 4 ? 7 : 10;
       if (tr) trace_put(p, it, trs, clock64());
-      ptx::mbar_wait(tfull_bar(as), aph);
-      ptx::tc_fence_after();
-      if (tr) trace_put(p, it, trs + 1, clock64());
       const uint32_t tacc = tmem_base + as * (C::NACC * BN) + ((uint32_t)(32 * q) << 16);
-      if (!(p.dbg & 1)) {
-        if constexpr (C::SP) epilogue_sp<C>(p, ti, tacc, q, sub, lane, reinterpret_cast<float*>(stg_all));
-        else if constexpr (C::NC) epilogue_nc<C>(p, ti, tacc, q, sub, lane, stg);
-        else epilogue_rowc<C>(p, ti, tacc, q, sub, lane, stg);
+      if constexpr (C::SP) {
+        if (tr) trace_put(p, it, trs + 1, clock64());  // (the wait is inside: work = wait + chunks for this variant)
+        epilogue_sp<C>(p, ti, tacc, q, sub, lane, stg_all, reinterpret_cast<float*>(stg_all + C::SP_STATS), tfull_bar(as), aph);
+      } else {
+        ptx::mbar_wait(tfull_bar(as), aph);
+        ptx::tc_fence_after();
+        if (tr) trace_put(p, it, trs + 1, clock64());
+        if (!(p.dbg & 1)) {
+          if constexpr (C::NC) epilogue_nc<C>(p, ti, tacc, q, sub, lane, stg);
+          else epilogue_rowc<C>(p, ti, tacc, q, sub, lane, stg);
+        }
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -1071,10 +1158,11 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
         else ptx::mbar_arrive(tempty_bar(as));
       }
       if constexpr (C::SP) {
-        if ((op.epi.flags & EPI_ROW_STATS) && !(p.dbg & 1)) epilogue_sp_flush<C>(p, ti, reinterpret_cast<float*>(stg_all));
+        if ((op.epi.flags & EPI_ROW_STATS) && !(p.dbg & 1)) epilogue_sp_flush<C>(p, ti, reinterpret_cast<float*>(stg_all + C::SP_STATS));
       }
       ++it;
     }
+    if constexpr (C::SP) ptx::bulk_wait0();  // this thread's TMA stores have completed (only the issuing lanes have any)
   }
 
   ptx::tc_fence_before();
@@ -1156,6 +1244,9 @@ void make_tmap(CUtensorMap* tm, const Operand& o, bool mn_major, long long rows,
                           box[0], box[1]));
 }
 
+inline bool aligned8(long long v) { return (v & 7) == 0; }
+inline bool aligned4(long long v) { return (v & 3) == 0; }
+
 thread_local int t_scalar_store = 0;  // set by dispatch() for the launch it is about to make
 
 // ---- tile lists of the triangular ops (see UmmaParams::tiles) ----
@@ -1207,7 +1298,7 @@ const TileList& grouped_tile_list(const GemmOp& op, int tile_m, int bn, int work
   return tl;
 }
 
-const TileList& tile_list(const GemmOp& op, int tile_m, int bn, int bk, int m_fastest) {
+const TileList& tile_list(const GemmOp& op, int tile_m, int bn, int bk, int m_fastest, int workers) {
   static std::mutex mu;
   static std::map<TileKey, TileList> cache;
   TileKey key;
@@ -1215,6 +1306,7 @@ const TileList& tile_list(const GemmOp& op, int tile_m, int bn, int bk, int m_fa
   key.M = op.M; key.N = op.N; key.K = op.K; key.Z1 = op.Z1; key.Z2 = op.Z2;
   key.flags = (op.n_lo_z1 ? 1 : 0) | (op.n_hi_z1 ? 2 : 0) | (op.k_lo_z1 ? 4 : 0) | (op.m_hi_z1 ? 8 : 0);
   key.tile_m = tile_m; key.bn = bn; key.bk = bk; key.m_fastest = m_fastest;
+  key.workers = options().tile_serpentine ? workers : 0;
   std::lock_guard<std::mutex> lock(mu);
   auto it = cache.find(key);
   if (it != cache.end()) return it->second;
@@ -1237,6 +1329,12 @@ const TileList& tile_list(const GemmOp& op, int tile_m, int bn, int bk, int m_fa
         ents.push_back({make_int4(tm, tn, z1, z2), n_eff * num_kc, order++});
       }
   std::stable_sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b) { return a.cost > b.cost; });
+  // worker w takes entries w, w + G, w + 2G, ...: with every stratum of G entries in descending order worker 0 would get the
+  // heaviest tile of each stratum and worker G - 1 the lightest; odd strata are reversed (serpentine) so the sums even out
+  if (workers > 0 && options().tile_serpentine) {
+    for (size_t b = (size_t)workers; b < ents.size(); b += 2 * (size_t)workers)
+      std::reverse(ents.begin() + b, ents.begin() + std::min(ents.size(), b + (size_t)workers));
+  }
   TileList& tl = cache[key];
   tl.n = (long long)ents.size();
   std::vector<int4> host(ents.size());
@@ -1302,7 +1400,7 @@ void launch(const GemmOp& op_in, cudaStream_t stream) {
   p.tiles = nullptr;
   p.n_listed = 0;
   if ((op.n_lo_z1 || op.n_hi_z1 || op.k_lo_z1 || op.m_hi_z1) && options().tile_list) {
-    const TileList& tl = tile_list(op, C::TILE_M, C::BN, C::BK, p.m_fastest);
+    const TileList& tl = tile_list(op, C::TILE_M, C::BN, C::BK, p.m_fastest, C::PAIR ? sm_count() / 2 : sm_count());
     if (tl.n == 0) return;  // nothing to compute
     p.tiles = tl.buf.as<int4>();
     p.n_listed = total = tl.n;
@@ -1355,6 +1453,20 @@ void launch(const GemmOp& op_in, cudaStream_t stream) {
     attr[cfg.numAttrs].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
     ++cfg.numAttrs;
   }
+  p.sp_tma = 0;
+  if constexpr (C::SP) {
+    const EpiParams& e = op.epi;
+    if ((C::EF & EPI_OUT_PLANES) && options().sp_tma && aligned8(e.o_m0) && aligned8(e.o_z2) && aligned8(e.out_plane) && !(((uintptr_t)e.out) & 15)) {
+      // (position, channel, sample, plane); one store = [2 planes][32 channels][128 positions] from the staging tile
+      cuuint64_t dims[4] = {(cuuint64_t)op.M, (cuuint64_t)op.N, (cuuint64_t)std::max(1, op.Z2), 2};
+      cuuint64_t strides[3] = {(cuuint64_t)e.o_m0 * 2, (cuuint64_t)(op.Z2 > 1 ? e.o_z2 : e.o_m0 * (long long)op.N) * 2, (cuuint64_t)e.out_plane * 2};
+      cuuint32_t box[4] = {128, 32, 1, 2}, estr[4] = {1, 1, 1, 1};
+      CUresult r = encode_fn()(&p.tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)e.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      p.sp_tma = (r == CUDA_SUCCESS) ? 1 : 0;
+    }
+    if (!p.sp_tma) memcpy(&p.tmO, &p.tmA, sizeof(CUtensorMap));  // a valid descriptor for the prefetch
+  }
   p.trace = nullptr;
   static DevBuf trace_buf;
   const size_t trace_bytes = (size_t)grid * kTraceIters * kTraceSlots * sizeof(long long);
@@ -1383,9 +1495,6 @@ void launch(const GemmOp& op_in, cudaStream_t stream) {
   after_launch(op.name);
   g_umma_count.fetch_add(1, std::memory_order_relaxed);
 }
-
-bool aligned8(long long v) { return (v & 7) == 0; }
-bool aligned4(long long v) { return (v & 3) == 0; }
 
 // ---- which compiled variant (if any) serves this op ----
 struct Variant {
@@ -1637,7 +1746,11 @@ bool dispatch(const GemmOp& op, bool dry, cudaStream_t s, const char** why) {
   }
   if (op.bfly) {
     if (!(v.nc && v.a_mn && v.ef == F)) { if (why) *why = "butterfly mode is compiled for MN-major A with fp32 output"; return false; }
-    if (!dry) launch<Cfg<96, true, false, F, true, 32, false, false, true>>(op, s);
+    if (dry) return true;
+    // CTA pairs: the small-N MMAs of this stage are bound by their shared-memory operand reads (4 KB of A per 96-column MMA);
+    // a pair halves the B bytes each CTA stages and reads
+    if (options().pair != 0 && options().bfly_pair && op.M % 256 == 0) launch<Cfg<96, true, false, F, true, 32, false, true, true>>(op, s);
+    else launch<Cfg<96, true, false, F, true, 32, false, false, true>>(op, s);
     return true;
   }
   const bool ok = (!v.nc && !v.a_mn) || (v.nc && (v.ef == P || v.ef == F));

@@ -131,3 +131,27 @@ def test_umma_pair_gemm_matches_fp64(shape, layout):
         _lib.set_option("pair", -1)
     err = (d1.double().cpu() - truth).abs().max() / truth.abs().max()
     assert err < TOL, float(err)
+
+
+@pytest.mark.parametrize(
+    "shape",
+    [
+        (128, 128, 256, 1),     # one position tile, one channel chunk group
+        (384, 8104, 48, 2),     # 192-channel column tiles, ragged last position tile, batch
+        (768, 2000, 96, 1),     # 256-channel column tiles
+        (160, 4100, 320, 1),    # ragged channel chunk (160 = 5 x 32), position count not a multiple of 4 tiles
+    ],
+)
+def test_umma_space_on_rows_variant(shape):
+    """Cfg::SP: a 1x1-convolution-shaped product (activations MN-major) executed with the operand roles exchanged, CTA pairs."""
+    from ace_b200 import _lib
+
+    m, n, k, nb = shape
+    a, b, truth = _case(m, n, k, nb, 2, seed=7)
+    _lib.set_option("sp", 2)
+    try:
+        d1 = _gemm(a, b, m, n, k, nb, 2, impl=1)
+    finally:
+        _lib.set_option("sp", 1)
+    err = (d1.double().cpu() - truth).abs().max() / truth.abs().max()
+    assert err < TOL, float(err)
