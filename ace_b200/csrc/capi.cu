@@ -107,6 +107,8 @@ extern "C" int ace_set_option(const char* key, int value) {
     options().bfly_pair = value ? 1 : 0;
   } else if (!strcmp(key, "tile_serpentine")) {
     options().tile_serpentine = value ? 1 : 0;
+  } else if (!strcmp(key, "sp_tmx")) {
+    options().sp_tmx = value ? 1 : 0;
   } else if (!strcmp(key, "trace")) {
     options().trace = value ? 1 : 0;
   } else if (!strcmp(key, "umma_bk")) {

@@ -103,6 +103,7 @@ struct Options {
   int sp_tma = 1;    // SP variants store their split-plane output by TMA from a shared-memory tile (0: element-wise stores from registers)
   int bfly_pair = 1; // butterfly inverse DFT on CTA pairs when the row count is a multiple of 256
   int tile_serpentine = 1;  // tile lists of the triangular GEMMs: odd strata reversed so every worker's tile costs sum to about the same
+  int sp_tmx = 1;    // SP variants fetch the epilogue's addend / residual tile by TMA (0: loads from the epilogue threads)
   int trace = 0;     // development: per-tile clock samples of the tcgen05 kernel's roles appended to $ACE_B200_TRACE_FILE (tools/trace_report.py)
   int umma_bn = 0;   // 0 = choose per op; otherwise force the N tile of the K-major x K-major variants (192 / 256)
 };

@@ -63,6 +63,9 @@ struct UmmaParams {
   // (sp_tma = 0: strides not 16-byte aligned -> element-wise stores from registers)
   CUtensorMap tmO;
   int sp_tma;
+  // ... and of the epilogue operand (fp32 addend, 3-D + a unit axis, or split-plane residual) for its TMA loads
+  CUtensorMap tmX;
+  int sp_tmx;
   int mma_batch;  // option "mma_batch": the MMA warp issues two ring slots per barrier round when both have landed
 };
 
@@ -116,13 +119,21 @@ struct Cfg {
   static constexpr int STAGE = 2 * (CPLX ? 2 : 1) * (A_PLANE + B_PLANE);  // complex mode: {Ar, Ai} x {hi, lo}, then {Br, Bi} x {hi, lo}
   // SP: per warp group (the four lane-quarter warps that share a 32-channel chunk) a [plane][32 channels][128 positions] bf16
   // tile the output is stored from by TMA, then the per-channel statistics of the tile
-  static constexpr int SP_TILE = 2 * 32 * 128 * 2, SP_STATS = (kEpiWarps / 4) * SP_TILE;
-  static constexpr int STG_BYTES = SP ? SP_STATS + 2048 : kEpiWarps * kStgBytesPerWarp;
+  // (SP_X: a second tile per group that TMA loads the addend [32][128] fp32 / the residual [plane][32][128] bf16 into;
+  //  SP_VEC: per warp the bias / residual scale / residual shift of the chunk's 32 channels)
+  static constexpr int SP_TILE = 2 * 32 * 128 * 2, SP_NG = kEpiWarps / 4;
+  //  a split-plane residual has the layout of the output tile and is loaded into the Y tile itself (SP_SHARED): a thread reads and
+  //  later overwrites exactly its own elements, and the two extra ring slots are worth more than the chunk of load latency)
+  static constexpr bool SP_OPND = (EF_ & (EPI_ADD_F32 | EPI_RES_PLANES)) != 0;
+  static constexpr bool SP_SHARED = SP_OPND;  // (the fp32 addend tile has the same size; barrier A separates its reads from the output writes)
+  static constexpr int SP_X = SP_SHARED ? 0 : SP_NG * SP_TILE;
+  static constexpr int SP_STATS = SP_NG * SP_TILE + ((SP_OPND && !SP_SHARED) ? SP_NG * SP_TILE : 0), SP_VEC = SP_STATS + 2048;
+  static constexpr int STG_BYTES = SP ? SP_VEC + kEpiWarps * 3 * 32 * 4 : kEpiWarps * kStgBytesPerWarp;
   // SP: the epilogue reads its addend / residual with ordinary global loads, which need L1 lines to land in; with the whole
   // 227 KB configured as shared memory hardly any are left (measured: those loads cost 24 - 37 us per launch).  Four ring
   // slots keep the kernel inside the 164 KB carve-out, i.e. 64 KB of L1.
   static constexpr int MAX_STAGES = SP_ ? SP_STAGES_ : 8;
-  static constexpr int BAR_BYTES = (2 * MAX_STAGES + 4) * 8 + 16;
+  static constexpr int BAR_BYTES = (2 * MAX_STAGES + 4) * 8 + 16 + 32;  // ring, accumulator, TMEM slot, SP operand-tile barriers
   static constexpr int STAGES_RAW = (kMaxSmem - 1024 - STG_BYTES - BAR_BYTES) / STAGE;
   static constexpr int STAGES = STAGES_RAW > MAX_STAGES ? MAX_STAGES : STAGES_RAW;
   static constexpr int TMEM_COLS = (2 * NACC * BN <= 256) ? 256 : 512;
@@ -659,13 +670,16 @@ __device__ __forceinline__ void epilogue_sp_chunk(const EpiParams& e, float (&v)
                                                   unsigned short* s_tile, int dbg) {
   constexpr uint32_t EF = C::EF;
   if (dbg & 8) do_stats = false;
-  if (dbg & 32) bias = nullptr;
-  if (bias) {
-    float4 b4[8];
+  {
+    // `bias` = this warp's shared-memory copy of the chunk's 32 biases (zeros without a bias)
 #pragma unroll
-    for (int k = 0; k < 8; ++k) b4[k] = __ldg(reinterpret_cast<const float4*>(bias) + k);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] += reinterpret_cast<const float*>(b4)[j];
+    for (int k = 0; k < 8; ++k) {
+      const float4 b = *reinterpret_cast<const float4*>(bias + 4 * k);
+      v[4 * k] += b.x;
+      v[4 * k + 1] += b.y;
+      v[4 * k + 2] += b.z;
+      v[4 * k + 3] += b.w;
+    }
   }
   if (EF & EPI_GELU) {
 #pragma unroll
@@ -728,10 +742,14 @@ __device__ __forceinline__ void epilogue_sp_chunk(const EpiParams& e, float (&v)
   }
 }
 
-// waits for the tile's accumulator itself (tfull barrier) so that the first chunk's operand loads are in flight meanwhile
+// waits for the tile's accumulator itself (tfull barrier) so that the first chunk's operand tile is in flight meanwhile.
+// Per group of four warps (lane quarters q = 0..3 of the same chunk index `sub`) and chunk of 32 channels:
+//   X tile <- TMA load of the addend / residual of the chunk (issued a chunk ahead by the group's first lane, mbarrier xbar)
+//   v <- accumulator + X (shared-memory reads, thread = position: conflict free) ; barrier A: X consumed, Y free again
+//   bias, GELU, statistics ; Y tile <- split planes ; barrier B ; TMA store of Y
 template <class C>
 __device__ __forceinline__ void epilogue_sp(const UmmaParams& p, const Tile& ti, uint32_t tacc, int q, int sub, int lane, uint8_t* stg_tiles,
-                                            float* s_stats, uint32_t tfull, uint32_t tfull_parity) {
+                                            float* s_stats, float* s_vec, uint32_t xbar, uint32_t& xphase, uint32_t tfull, uint32_t tfull_parity) {
   constexpr uint32_t EF = C::EF;
   const GemmOp& op = p.op;
   const EpiParams& e = op.epi;
@@ -755,55 +773,93 @@ __device__ __forceinline__ void epilogue_sp(const UmmaParams& p, const Tile& ti,
   const float* res_s = raff ? e.res_s + (long long)ti.z2 * e.rsa_z2 + cb : nullptr;
   const int nch = (ti.n_count + 31) >> 5;
   const long long res_m0w = e.res_m0 >> 1;
-  // TMA-stored output: the four warps (lane quarters q) that share the chunk index `sub` fill one staging tile; named barrier
-  // 2 + sub synchronises them, the first lane of quarter 0 issues the store and waits for it before the tile is written again
   const bool staged = (EF & EPI_OUT_PLANES) && p.sp_tma;
+  const bool xtile = C::SP_OPND && p.sp_tmx && staged && !(p.dbg & 16);  // operands by TMA (else: loads from registers' side, SpOperands)
   unsigned short* tile = reinterpret_cast<unsigned short*>(stg_tiles + sub * C::SP_TILE);
+  uint8_t* xt = C::SP_SHARED ? reinterpret_cast<uint8_t*>(tile) : stg_tiles + C::SP_X + sub * C::SP_TILE;
   const bool issuer = q == 0 && lane == 0;
   const bool skip = (p.dbg & 1) != 0;
-  // addend: prefetched a chunk ahead (32 registers); residual planes: loaded and applied 16 channels at a time inside the chunk
-  // (64 registers of prefetched words spill)
-  constexpr bool PREFETCH = (EF & EPI_ADD_F32) && !(EF & EPI_RES_PLANES);
-  SpOperands<C> ops;
-  if (PREFETCH && sub < nch && !skip && !(p.dbg & 16))
-    ops.load(e, g_add + (long long)sub * 32 * e.add_m0, g_res + (long long)sub * 32 * res_m0w, min(32, ti.n_count - sub * 32));
+  auto load_x = [&](int c) {  // (issuer only) the X tile is free: every thread of the group has passed barrier A of the previous chunk
+    ptx::mbar_arrive_expect_tx(xbar, (uint32_t)C::SP_TILE);
+    ptx::tma_load_4d(ptx::smem_u32(xt), &p.tmX, xbar, ti.m0, ti.n_begin + c * 32, ti.z2, 0);
+  };
+  // (SP_SHARED: the issuer waited for the previous store's shared-memory reads right after issuing it)
+  if (xtile && issuer && sub < nch && !skip) load_x(sub);
   ptx::mbar_wait(tfull, tfull_parity);
   ptx::tc_fence_after();
   if (skip) return;
+  float* vec = s_vec + ((sub * 4 + q) * 3) * 32;  // this warp's [bias | residual scale | residual shift] of the chunk
   for (int c = sub; c < nch; c += kEpiWarps / 4) {
     const int nvalid = min(32, ti.n_count - c * 32);
     float v[32];
     ptx::tmem_ld_32x32(tacc + c * 32, v);
-    ptx::tmem_ld_wait();
     const long long co = (long long)c * 32;
-    if (!(p.dbg & 16)) {
-      if (PREFETCH) {
-        ops.apply(v, odd, nullptr, nullptr);
-        const int cn = c + kEpiWarps / 4;
-        if (cn < nch) ops.load(e, g_add + (long long)cn * 32 * e.add_m0, g_res + (long long)cn * 32 * res_m0w, min(32, ti.n_count - cn * 32));
-      } else if (EF & (EPI_ADD_F32 | EPI_RES_PLANES)) {
-        ops.load(e, g_add + co * e.add_m0, g_res + co * res_m0w, nvalid);
-        ops.apply(v, odd, (p.dbg & 32) ? nullptr : (res_a ? res_a + co : nullptr), res_s ? res_s + co : nullptr);
+    // the chunk's per-channel vectors: one coalesced load per vector and warp instead of broadcast loads per channel (with
+    // the whole shared-memory carve-out in use there is no L1 to serve those)
+    if (!(p.dbg & 32)) {
+      const bool ok = lane < nvalid;
+      vec[lane] = (bias && ok) ? __ldg(bias + co + lane) : 0.f;
+      if (EF & EPI_RES_PLANES) {
+        vec[32 + lane] = (res_a && ok) ? __ldg(res_a + co + lane) : 1.f;
+        vec[64 + lane] = (res_s && ok) ? __ldg(res_s + co + lane) : 0.f;
       }
+    } else {
+      vec[lane] = 0.f;
+      vec[32 + lane] = 1.f;
+      vec[64 + lane] = 0.f;
+    }
+    __syncwarp();
+    ptx::tmem_ld_wait();
+    if (xtile) {
+      ptx::mbar_wait(xbar, xphase);
+      xphase ^= 1u;
+      if (EF & EPI_ADD_F32) {
+        const float* xa = reinterpret_cast<const float*>(xt) + 32 * q + lane;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += xa[j * 128];
+      }
+      if (EF & EPI_RES_PLANES) {
+        const unsigned short* xr = reinterpret_cast<const unsigned short*>(xt) + 32 * q + lane;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 ra = *reinterpret_cast<const float4*>(vec + 32 + j), rs = *reinterpret_cast<const float4*>(vec + 64 + j);
+          const float a4[4] = {ra.x, ra.y, ra.z, ra.w}, s4[4] = {rs.x, rs.y, rs.z, rs.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float r = __uint_as_float((uint32_t)xr[(j + k) * 128] << 16) + __uint_as_float((uint32_t)xr[32 * 128 + (j + k) * 128] << 16);
+            v[j + k] += fmaf(a4[k], r, s4[k]);
+          }
+        }
+      }
+    } else if ((EF & (EPI_ADD_F32 | EPI_RES_PLANES)) && !(p.dbg & 16)) {
+      SpOperands<C> ops;
+      ops.load(e, g_add + co * e.add_m0, g_res + co * res_m0w, nvalid);
+      ops.apply(v, odd, res_a ? res_a + co : nullptr, res_s ? res_s + co : nullptr);
     }
     if (staged) {
-      if (issuer) ptx::bulk_wait_read0();  // the previous store has finished reading the tile
-      ptx::named_bar_sync(2 + sub, 128);
+      if (issuer && !(C::SP_SHARED && xtile)) ptx::bulk_wait_read0();  // the previous store has finished reading the Y tile
+      ptx::named_bar_sync(2 + sub, 128);   // barrier A
+      const int cn = c + kEpiWarps / 4;
+      if (!C::SP_SHARED && xtile && issuer && cn < nch) load_x(cn);
     }
     unsigned short* s_tile = staged ? tile + 32 * q + lane : nullptr;
     if (nvalid == 32)
-      epilogue_sp_chunk<C, true>(e, v, nvalid, sp_ok, lane, g_f32 + co * e.f_m0, g_pl + co * e.o_m0, bias ? bias + co : nullptr, do_stats,
-                                 s_stats + 2 * co, s_tile, p.dbg);
+      epilogue_sp_chunk<C, true>(e, v, nvalid, sp_ok, lane, g_f32 + co * e.f_m0, g_pl + co * e.o_m0, vec, do_stats, s_stats + 2 * co, s_tile, p.dbg);
     else
-      epilogue_sp_chunk<C, false>(e, v, nvalid, sp_ok, lane, g_f32 + co * e.f_m0, g_pl + co * e.o_m0, bias ? bias + co : nullptr, do_stats,
-                                  s_stats + 2 * co, s_tile, p.dbg);
+      epilogue_sp_chunk<C, false>(e, v, nvalid, sp_ok, lane, g_f32 + co * e.f_m0, g_pl + co * e.o_m0, vec, do_stats, s_stats + 2 * co, s_tile, p.dbg);
     if (staged) {
       ptx::fence_proxy_async_smem();  // the tile was written through the generic proxy, TMA reads it through the async proxy
-      ptx::named_bar_sync(2 + sub, 128);
+      ptx::named_bar_sync(2 + sub, 128);  // barrier B
       if (issuer) {
         // rows beyond the image and channels beyond the tensor are clipped by TMA
         ptx::tma_store_4d(&p.tmO, ptx::smem_u32(tile), ti.m0, ti.n_begin + c * 32, ti.z2, 0);
         ptx::bulk_commit();
+        if (C::SP_SHARED && xtile) {
+          // the next residual tile lands in the tile this store reads from
+          ptx::bulk_wait_read0();
+          const int cn = c + kEpiWarps / 4;
+          if (cn < nch) load_x(cn);
+        }
       }
     }
   }
@@ -841,6 +897,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
   auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 + a); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 2 * STAGES + 4);
+  auto x_bar = [&](int g) { return bar0 + 8u * (2 * STAGES + 6 + g); };  // SP: operand tile of epilogue group g has landed
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GemmOp& op = p.op;
@@ -862,6 +919,9 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
       ptx::mbar_init(full_bar(s), NCTA);  // pair: one arrive per CTA's producer, all bytes credited to the leader
       ptx::mbar_init(empty_bar(s), 1);
     }
+    if constexpr (C::SP) {
+      for (int g = 0; g < kEpiWarps / 4; ++g) ptx::mbar_init(x_bar(g), 1);
+    }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(tfull_bar(a), 1);
       ptx::mbar_init(tempty_bar(a), NCTA * kEpiWarps);  // one arrive per epilogue warp (of both CTAs)
@@ -870,7 +930,10 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
   }
   if constexpr (C::SP) {
     for (int i = threadIdx.x; i < 2 * BN; i += kThreadsUmma) reinterpret_cast<float*>(stg_all + C::SP_STATS)[i] = 0.f;
-    if (warp == 0 && lane == 0) ptx::prefetch_tensormap(&p.tmO);
+    if (warp == 0 && lane == 0) {
+      ptx::prefetch_tensormap(&p.tmO);
+      ptx::prefetch_tensormap(&p.tmX);
+    }
   }
   if (warp == 2) {
     if constexpr (PAIR) {
@@ -1128,6 +1191,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
     const int sub = (warp - 4) >> 2;  // which of the kEpiWarps/4 warps of the quarter
     uint8_t* stg = C::SP ? stg_all : stg_all + (warp - 4) * kStgBytesPerWarp;
     uint32_t it = 0;
+    uint32_t xphase = 0;  // SP: parity of the group's operand-tile barrier
     Tile ti;
     for (long long t = t_first; t < total; t += t_step) {
       if (!decode_tile<BN, BK, C::TILE_M>(p, t, ti)) continue;
@@ -1140,7 +1204,8 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
       const uint32_t tacc = tmem_base + as * (C::NACC * BN) + ((uint32_t)(32 * q) << 16);
       if constexpr (C::SP) {
         if (tr) trace_put(p, it, trs + 1, clock64());  // (the wait is inside: work = wait + chunks for this variant)
-        epilogue_sp<C>(p, ti, tacc, q, sub, lane, stg_all, reinterpret_cast<float*>(stg_all + C::SP_STATS), tfull_bar(as), aph);
+        epilogue_sp<C>(p, ti, tacc, q, sub, lane, stg_all, reinterpret_cast<float*>(stg_all + C::SP_STATS),
+                       reinterpret_cast<float*>(stg_all + C::SP_VEC), x_bar(sub), xphase, tfull_bar(as), aph);
       } else {
         ptx::mbar_wait(tfull_bar(as), aph);
         ptx::tc_fence_after();
@@ -1466,6 +1531,27 @@ void launch(const GemmOp& op_in, cudaStream_t stream) {
       p.sp_tma = (r == CUDA_SUCCESS) ? 1 : 0;
     }
     if (!p.sp_tma) memcpy(&p.tmO, &p.tmA, sizeof(CUtensorMap));  // a valid descriptor for the prefetch
+    p.sp_tmx = 0;
+    if (p.sp_tma && C::SP_OPND && options().sp_tmx) {
+      CUresult r = CUDA_ERROR_INVALID_VALUE;
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      if ((C::EF & EPI_RES_PLANES) && aligned8(e.res_m0) && aligned8(e.res_z2) && aligned8(e.res_plane) && !(((uintptr_t)e.res) & 15)) {
+        cuuint64_t dims[4] = {(cuuint64_t)op.M, (cuuint64_t)op.N, (cuuint64_t)std::max(1, op.Z2), 2};
+        cuuint64_t strides[3] = {(cuuint64_t)e.res_m0 * 2, (cuuint64_t)(op.Z2 > 1 ? e.res_z2 : e.res_m0 * (long long)op.N) * 2, (cuuint64_t)e.res_plane * 2};
+        cuuint32_t box[4] = {128, 32, 1, 2};
+        r = encode_fn()(&p.tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)e.res, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      } else if ((C::EF & EPI_ADD_F32) && aligned4(e.add_m0) && aligned4(e.add_z2) && !(((uintptr_t)e.add) & 15)) {
+        const cuuint64_t per_sample = (cuuint64_t)(op.Z2 > 1 ? e.add_z2 : e.add_m0 * (long long)op.N) * 4;
+        cuuint64_t dims[4] = {(cuuint64_t)op.M, (cuuint64_t)op.N, (cuuint64_t)std::max(1, op.Z2), 1};
+        cuuint64_t strides[3] = {(cuuint64_t)e.add_m0 * 4, per_sample, per_sample * (cuuint64_t)std::max(1, op.Z2)};
+        cuuint32_t box[4] = {128, 32, 1, 1};
+        r = encode_fn()(&p.tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)e.add, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      }
+      p.sp_tmx = (r == CUDA_SUCCESS) ? 1 : 0;
+    }
+    if (!p.sp_tmx) memcpy(&p.tmX, &p.tmA, sizeof(CUtensorMap));
   }
   p.trace = nullptr;
   static DevBuf trace_buf;
@@ -1694,7 +1780,9 @@ bool sp_eligible(const GemmOp& op, const Variant& v) {
   // never against the 256-row CTA-pair variants that channel counts of a multiple of 256 already use.
   if (options().sp != 2) {
     if (op.M % 256 == 0 || op.K < 256) return false;
-    if (e.flags & (EPI_ROW_STATS | EPI_ADD_F32 | EPI_RES_PLANES)) return false;
+    // (an addend tile loaded a chunk at a time leaves its latency exposed on the short K = 384 tiles: inner_skip 91 vs 76.5 us)
+    if (e.flags & EPI_ADD_F32) return false;
+    if (!(options().sp_tma && options().sp_tmx) && (e.flags & (EPI_ROW_STATS | EPI_RES_PLANES))) return false;
   }
   return true;
 }

@@ -89,6 +89,12 @@ __device__ __forceinline__ void tma_load_5d(uint32_t smem_dst, const void* desc,
       : "memory");
 }
 
+// 4-D tiled load global -> shared (this CTA), completion on an mbarrier
+__device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const void* desc, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_dst),
+               "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 // 4-D tiled store shared -> global (bulk async group of the issuing thread); out-of-range parts of the box are not written
 __device__ __forceinline__ void tma_store_4d(const void* desc, uint32_t smem_src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(reinterpret_cast<uint64_t>(desc)),

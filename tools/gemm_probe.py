@@ -30,7 +30,7 @@ if __name__ == "__main__":
 
     if len(sys.argv) > 2:
         variants = [json.loads(a) for a in sys.argv[2:]]
-    base = dict(split_terms=3, umma_bn=0, umma_bk=0, dbg=0, conv_bn=0, pair=-1, dhconv_t=0, inv2=1, tile_list=1, l2_persist=0, group_order=1, trace=0, mma_batch=1, sp=1, sp_tma=1, bfly_pair=1, tile_serpentine=1)
+    base = dict(split_terms=3, umma_bn=0, umma_bk=0, dbg=0, conv_bn=0, pair=-1, dhconv_t=0, inv2=1, tile_list=1, l2_persist=0, group_order=1, trace=0, mma_batch=1, sp=1, sp_tma=1, bfly_pair=1, tile_serpentine=1, sp_tmx=1)
     for k, val in base.items(): _lib.set_option(k, val)
     with torch.no_grad():
         y_ref = net(x).clone()  # default options: the configuration the GPU test-suite validates against the oracle
