@@ -19,7 +19,7 @@ void set_last_error(const char* msg) { t_last_error = msg ? msg : ""; }
 Options& options() {
   static Options o = [] {
     Options x;
-    if (const char* e = getenv("ACE_B200_PDL")) x.pdl = atoi(e) ? 1 : 0;
+    if (const char* e = getenv("ACE_B200_PDL")) x.pdl = atoi(e);
     // every GEMM on the SIMT kernel: for compute-sanitizer racecheck / synccheck runs (tools/sanitize.sh), which do not model
     // the asynchronous tcgen05 / TMA proxies
     if (const char* e = getenv("ACE_B200_FORCE_SIMT")) x.force_simt = atoi(e) ? 1 : 0;
@@ -84,7 +84,7 @@ extern "C" int ace_set_option(const char* key, int value) {
     ACE_REQUIRE(value == 0 || value == 192 || value == 256, "conv_bn must be 0, 192 or 256");
     options().conv_bn = value;
   } else if (!strcmp(key, "pdl")) {
-    options().pdl = value ? 1 : 0;
+    options().pdl = value;
   } else if (!strcmp(key, "dbg")) {
     options().dbg = value;
   } else if (!strcmp(key, "l2_persist")) {

@@ -1486,7 +1486,7 @@ void launch(const GemmOp& op_in, cudaStream_t stream) {
   cfg.stream = stream;
   cudaLaunchAttribute attr[3];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = (options().pdl && !C::PAIR) ? 1 : 0;
+  attr[0].val.programmaticStreamSerializationAllowed = (options().pdl == 2 || (options().pdl && !C::PAIR)) ? 1 : 0;  // (2: cluster launches too)
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   if (C::PAIR) {
