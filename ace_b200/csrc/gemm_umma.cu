@@ -389,14 +389,15 @@ template <class C, bool FULL>
 __device__ __forceinline__ void epilogue_nc_chunk(const EpiParams& e, float (&v)[32], int nvalid, int rows_valid, int lane,
                                                   uint4* s16, uint2* s8, const float* g_add, const bf16* g_res,
                                                   float* g_f32, bf16* g_pl, float rbias, float res_a, float res_s, bool do_stats,
-                                                  f2& ssum, f2& ssq, bool scalar_store) {
+                                                  f2& ssum, f2& ssq, bool scalar_store, int dbg = 0) {
   constexpr uint32_t EF = C::EF;
   const int fr = lane >> 2, fp = lane & 3;  // fp32 pass: rows it*8 + fr (it < 4), 16-byte piece fp
   const int pr = lane >> 3, pp = lane & 7;  // plane pass: rows it*4 + pr (it < 8), 8-byte piece pp
+  if (dbg & 8) do_stats = false;  // development switches (option "dbg"): 8 no statistics, 16 no addend / residual, 64 no stores
 
   // All global loads of the chunk are issued before the first one is consumed (one L2 round trip per chunk instead of one per
   // 16-column half / per plane: the epilogue warps are latency-bound, three of them share a scheduler).
-  if (EF & EPI_ADD_F32) {
+  if ((EF & EPI_ADD_F32) && !(dbg & 16)) {
     uint4 t[2][4];
 #pragma unroll
     for (int h = 0; h < 2; ++h)
@@ -422,7 +423,7 @@ __device__ __forceinline__ void epilogue_nc_chunk(const EpiParams& e, float (&v)
       __syncwarp();
     }
   }
-  if (EF & EPI_RES_PLANES) {
+  if ((EF & EPI_RES_PLANES) && !(dbg & 16)) {
     // (one plane at a time: holding both planes' loads in registers spills in the RS | P variant and measured slower, fc2 114 -> 118 us)
     const f2 ra2 = mk2(res_a, res_a);
 #pragma unroll
@@ -467,6 +468,7 @@ __device__ __forceinline__ void epilogue_nc_chunk(const EpiParams& e, float (&v)
     }
   }
 
+  if (dbg & 64) return;
   if (EF & EPI_OUT_F32) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -588,10 +590,10 @@ __device__ __forceinline__ void epilogue_nc(const UmmaParams& p, const Tile& ti,
     const int co = c * 32 + part * op.N;
     if (nvalid == 32 && rows_valid >= 32 && !p.scalar_store)
       epilogue_nc_chunk<C, true>(e, v, nvalid, rows_valid, lane, s16, s8, g_add + co, g_res + co, g_f32 + co, g_pl + co, rbias,
-                                 res_a, res_s, do_stats, ssum, ssq, false);
+                                 res_a, res_s, do_stats, ssum, ssq, false, p.dbg);
     else
       epilogue_nc_chunk<C, false>(e, v, nvalid, rows_valid, lane, s16, s8, g_add + co, g_res + co, g_f32 + co, g_pl + co, rbias,
-                                  res_a, res_s, do_stats && row_ok, ssum, ssq, p.scalar_store != 0);
+                                  res_a, res_s, do_stats && row_ok, ssum, ssq, p.scalar_store != 0, p.dbg);
   }
   if (do_stats && row_ok) {
     float s0, s1, q0, q1;

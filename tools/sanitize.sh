@@ -8,16 +8,20 @@
 set -u
 cd "${GRAFT_REPO_ROOT:-.}"
 mkdir -p gpurun_out
-SKIP='not full_size and not baseline_configs and not quarter_degree and not rollout_40 and not test_block_speed and not (test_net_tcgen05_path_vs_oracle and 180)'
+SKIP='not full_size and not baseline_configs and not quarter_degree and not rollout_40 and not test_block_speed and not faster_and_smaller and not (test_net_tcgen05_path_vs_oracle and 180)'
 T1=${ACE_SAN_MEMCHECK_S:-700}
 T2=${ACE_SAN_RACE_S:-300}
+TOOLS=${ACE_SAN_TOOLS:-memcheck racecheck synccheck}
+if [[ " $TOOLS " == *" memcheck "* ]]; then
 timeout $T1 compute-sanitizer --tool memcheck --target-processes all --print-limit 20 --error-exitcode 9 \
-  python -m pytest tests -m gpu -q -x -p no:cacheprovider -k "$SKIP" > gpurun_out/r02_sanitizer_memcheck.log 2>&1
+  python -m pytest tests -m gpu -q -p no:cacheprovider -k "$SKIP" > gpurun_out/r02_sanitizer_memcheck.log 2>&1
 echo "memcheck exit $?" >> gpurun_out/r02_sanitizer_memcheck.log
+fi
 RTESTS="tests/test_gpu_corrector.py tests/test_gpu_metrics.py tests/test_gpu_healpix.py tests/test_gpu_sfno.py::test_net_matches_reference_vectors tests/test_gpu_csfno.py::test_reference_goldens tests/test_gpu_stepper.py::test_step_matches_oracle"
 for tool in racecheck synccheck; do
+  [[ " $TOOLS " == *" $tool "* ]] || continue
   ACE_B200_FORCE_SIMT=1 timeout $T2 compute-sanitizer --tool $tool --target-processes all --print-limit 20 --error-exitcode 9 \
     python -m pytest $RTESTS -q -p no:cacheprovider -k "not 180" > gpurun_out/r02_sanitizer_$tool.log 2>&1
   echo "$tool exit $?" >> gpurun_out/r02_sanitizer_$tool.log
 done
-for t in memcheck racecheck synccheck; do echo "== $t"; grep -E "ERROR SUMMARY|passed|failed|exit|RACECHECK SUMMARY" gpurun_out/r02_sanitizer_$t.log | tail -6; done
+for t in $TOOLS; do echo "== $t"; grep -E "ERROR SUMMARY|passed|failed|exit|RACECHECK SUMMARY" gpurun_out/r02_sanitizer_$t.log | tail -6; done
