@@ -21,6 +21,7 @@ GPU (cuFFT + cuBLAS + ATen: the oracle port moved to CUDA, TF32 off and on) -- S
 
 --workload sht / inverse_sht: the reference's own micro-benchmark shapes (fme/sht_fix.py:232-327: 1024 fields of
 180x360, default lobatto grid) through ace_b200.RealSHT / InverseRealSHT, reported as HBM GB/s against the roofline.
+--workload quarter_degree: BASELINE configs[3] (721x1440, 44 in / 50 out, embed 384, 8 blocks) network forward on one GPU.
 
 --impl reference times the reference algorithm's CPU path (the oracle port of the reference modules;
 the reference is pure Python and `import fme` is impossible in this image) on the host
@@ -405,6 +406,89 @@ def run_sht_workload(args):
     print(json.dumps(line), flush=True)
 
 
+def run_quarter_degree(args):
+    """BASELINE configs[3]: ACE 0.25 degree (721x1440, 44 in / 50 out, embed 384, 8 blocks, dhconv), one member on one B200,
+    device-resident forward passes of the network (the step wrapper adds three elementwise kernels).  No CPU baseline leg: the
+    reference algorithm needs minutes per Legendre table at L = 721 on the host."""
+    import torch
+
+    import ace_b200
+    from ace_b200 import _lib
+
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    img = (721, 1440)
+    fields = dict(embed_dim=384, num_layers=8, operator_type="dhconv", data_grid="legendre-gauss")
+    torch.manual_seed(0)
+    with torch.device(dev):
+        net = ace_b200.ModuleSelector(type="B200SphericalFourierNeuralOperatorNet", config=fields).build(
+            44, 50, ace_b200.DatasetInfo(img_shape=img)).torch_module
+    net = net.eval().requires_grad_(False)
+    x = torch.randn(1, 44, *img, device=dev)
+    K, Wm = args.steps, max(args.warmup, 3)
+    s0 = _lib.get_option("count_simt")
+    with torch.no_grad():
+        for _ in range(Wm):
+            y = net(x)
+        torch.cuda.synchronize()
+        l0 = _lib.launch_count()
+        net(x)
+        launches = _lib.launch_count() - l0
+        sampler = ClockSampler(dev.index)
+        sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        samples = []
+        for _ in range(max(1, args.repeats)):
+            torch.cuda.synchronize()
+            ev0.record()
+            for _ in range(K):
+                y = net(x)
+            ev1.record()
+            torch.cuda.synchronize()
+            samples.append(ev0.elapsed_time(ev1) / K)
+        clocks = sampler.stop()
+        _lib.set_option("profile", 1)
+        _lib.profile_report()
+        net(x)
+        rep = _lib.profile_report()
+        _lib.set_option("profile", 0)
+        # e2e: host input in, host output out
+        xh = x.cpu().pin_memory()
+        yh = torch.empty_like(y, device="cpu").pin_memory()
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(3):
+            yh.copy_(net(xh.to(dev, non_blocking=True)), non_blocking=True)
+        ev1.record()
+        torch.cuda.synchronize()
+        e2e_ms = ev0.elapsed_time(ev1) / 3
+    assert _lib.get_option("count_simt") == s0, "a GEMM fell back to the SIMT kernel"
+    ms = sorted(samples)[len(samples) // 2]
+    C, Kl, W, L, M = 384, img[0], img[1], img[0], img[0]
+    sht_bytes = C * (Kl * W * 4 + L * M * 8) + M * L * Kl * 4
+    kus = {k: round(t / c * 1e3, 1) for k, (c, t) in rep.items()}
+    fwd, inv = (kus["sht.dft_fwd"] + kus["sht.legendre_fwd"]) * 1e-6, (kus["sht.dft_inv"] + kus["sht.legendre_inv"]) * 1e-6
+    pk = peaks()
+    syd = lambda t_ms: 86400.0 / (t_ms * 1e-3) / STEPS_PER_YEAR
+    print(json.dumps({
+        "metric": "simulated_years_per_day", "value": syd(ms), "unit": "sim-years/day", "n_gpus": 1, "steps": K, "warmup": Wm,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16x3 (split-bf16 3-term products, fp32 accumulate; fp32 I/O)", "data": "synthetic",
+        "config": {"workload": "ACE 0.25deg (BASELINE configs[3]): 721x1440, 44in/50out, embed 384, 8 SFNO blocks (dhconv, instance_norm), B=1, network forward",
+                   "weights": "random init (reference initialisation, seed 0)", "l2": "inputs larger than L2 (1.6 GB per activation tensor)"},
+        "e2e": {"value": syd(e2e_ms), "unit": "sim-years/day", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(xh.numel() * 4), "d2h_bytes_per_step": int(yh.numel() * 4)},
+        "gpu_launches": int(launches * K), "launches_per_step": int(launches), "clocks": clocks,
+        "repeats": {"n": len(samples), "ms_per_step": [round(v, 3) for v in samples]},
+        "roofline": {"kernel": "sht (forward / inverse)", "bound": "hbm", "achieved": sht_bytes / max(fwd, inv) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                     "frac": sht_bytes / max(fwd, inv) / 1e9 / pk["hbm_gbs"], "traffic": None, "algorithmic_bytes": sht_bytes,
+                     "forward_us": fwd * 1e6, "inverse_us": inv * 1e6, "note": "slower of the two transforms; peak of " + pk["source"]},
+        "kernels_us": kus, "mem_allocated_GB": round(torch.cuda.max_memory_allocated() / 1e9, 1), "outputs_finite": bool(torch.isfinite(y).all()),
+        "cpu_baseline": None,
+    }), flush=True)
+
+
 # --------------------------------------------------------------------------------------------- B200 arm
 def run_b200(args):
     import torch
@@ -683,12 +767,14 @@ def main():
     ap.add_argument("--no-gpu-eager-baseline", action="store_true")
     ap.add_argument("--repeats", type=int, default=3, help="repeats of the K-step timed region (median reported)")
     ap.add_argument("--sustained-steps", type=int, default=STEPS_PER_YEAR, help="length of the sustained leg (0 = skip)")
-    ap.add_argument("--workload", default="rollout", choices=["rollout", "sht", "inverse_sht"])
+    ap.add_argument("--workload", default="rollout", choices=["rollout", "sht", "inverse_sht", "quarter_degree"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
     elif args.workload in ("sht", "inverse_sht"):
         run_sht_workload(args)
+    elif args.workload == "quarter_degree":
+        run_quarter_degree(args)
     else:
         run_b200(args)
 
