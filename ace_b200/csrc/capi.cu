@@ -109,6 +109,8 @@ extern "C" int ace_set_option(const char* key, int value) {
     options().tile_serpentine = value ? 1 : 0;
   } else if (!strcmp(key, "sp_tmx")) {
     options().sp_tmx = value ? 1 : 0;
+  } else if (!strcmp(key, "cln_gemm")) {
+    options().cln_gemm = value ? 1 : 0;
   } else if (!strcmp(key, "trace")) {
     options().trace = value ? 1 : 0;
   } else if (!strcmp(key, "umma_bk")) {

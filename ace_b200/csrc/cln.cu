@@ -328,7 +328,111 @@ __global__ void build_cln_w2_kernel(const float* __restrict__ ws_n, const float*
   }
 }
 
+// ---- helpers of the tensor-core ConditionalLayerNorm (GemmOp::cln, gemm.cuh) ----
+
+// {mean, rstd} over the channel axis per pixel (pass 1 of cond_layer_norm_kernel2 on its own): musr[b][p]
+__global__ void __launch_bounds__(kWarps * 32) cln_stats_kernel(const bf16* __restrict__ x, long long x_plane, long long x_b, int C, long long HW,
+                                                               float eps, float2* __restrict__ musr) {
+  __shared__ double red[kWarps][32][4];
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long p = (long long)blockIdx.x * kPix2 + 2 * lane;
+  const bool live = p < HW;
+  const bf16* xb = x + (long long)b * x_b + p;
+  double s0 = 0, q0 = 0, s1 = 0, q1 = 0;
+  if (live) {
+#pragma unroll 8
+    for (int c = warp; c < C; c += kWarps) {
+      float v0, v1;
+      load_pair(xb + (long long)c * HW, x_plane, v0, v1);
+      s0 += (double)v0;
+      q0 += (double)v0 * (double)v0;
+      s1 += (double)v1;
+      q1 += (double)v1 * (double)v1;
+    }
+  }
+  red[warp][lane][0] = s0;
+  red[warp][lane][1] = q0;
+  red[warp][lane][2] = s1;
+  red[warp][lane][3] = q1;
+  __syncthreads();
+  if (warp != 0 || !live) return;
+  s0 = q0 = s1 = q1 = 0;
+#pragma unroll
+  for (int w = 0; w < kWarps; ++w) {
+    s0 += red[w][lane][0];
+    q0 += red[w][lane][1];
+    s1 += red[w][lane][2];
+    q1 += red[w][lane][3];
+  }
+  const double m0 = s0 / C, m1 = s1 / C;
+  const float r0 = rsqrtf((float)fmax(q0 / C - m0 * m0, 0.0) + eps), r1 = rsqrtf((float)fmax(q1 / C - m1 * m1, 0.0) + eps);
+  *reinterpret_cast<float4*>(musr + (long long)b * HW + p) = make_float4((float)m0, r0, (float)m1, r1);
+}
+
+// ctx [B][Ep][HW] fp32 -> K-major B operand planes [B][HW][2 Ep]: the Ep context channels twice along k (the first half meets
+// the scale weights, the second half the bias weights); a 32-pixel x Ep tile is transposed through shared memory
+template <int EP>
+__global__ void __launch_bounds__(256) cln_ctx_planes_kernel(const float* __restrict__ ctx, long long HW, bf16* __restrict__ out, long long plane) {
+  __shared__ float tile[EP][33];
+  const int b = blockIdx.y;
+  const long long p0 = (long long)blockIdx.x * 32;
+  for (int i = threadIdx.x; i < EP * 32; i += 256) {
+    const int e = i >> 5, j = i & 31;
+    tile[e][j] = (p0 + j < HW) ? ctx[((long long)b * EP + e) * HW + p0 + j] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * EP; i += 256) {
+    const int j = i / EP, e = i % EP;
+    if (p0 + j >= HW) continue;
+    bf16 h, l;
+    split_bf16(tile[e][j], h, l);
+    bf16* o = out + ((long long)b * HW + p0 + j) * (2 * EP) + e;
+    o[0] = h;
+    o[EP] = h;
+    o[plane] = l;
+    o[plane + EP] = l;
+  }
+}
+
+// w2 [C][Ep][2] -> K-major A operand planes [C][2 Ep] = [scale weights | bias weights]
+__global__ void cln_w_planes_kernel(const float* __restrict__ w2, int C, int Ep, bf16* __restrict__ out, long long plane) {
+  const long long total = (long long)C * Ep;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long c = idx / Ep;
+    const int e = (int)(idx % Ep);
+    bf16 h, l;
+    split_bf16(w2[idx * 2], h, l);
+    out[c * 2 * Ep + e] = h;
+    out[c * 2 * Ep + e + plane] = l;
+    split_bf16(w2[idx * 2 + 1], h, l);
+    out[c * 2 * Ep + Ep + e] = h;
+    out[c * 2 * Ep + Ep + e + plane] = l;
+  }
+}
+
 }  // namespace
+
+void launch_cln_stats(const bf16* x, long long x_plane, long long x_b, int B, int C, long long HW, float eps, float* musr, cudaStream_t stream) {
+  ProfileScope prof("cln_stats", stream);
+  cln_stats_kernel<<<dim3((unsigned)((HW + kPix2 - 1) / kPix2), (unsigned)B), kWarps * 32, 0, stream>>>(x, x_plane, x_b, C, HW, eps,
+                                                                                                    reinterpret_cast<float2*>(musr));
+  after_launch("cln_stats");
+}
+
+void launch_cln_ctx_planes(const float* ctx, int B, int Ep, long long HW, bf16* out, long long plane, cudaStream_t stream) {
+  ProfileScope prof("cln_ctx_planes", stream);
+  const dim3 grid((unsigned)((HW + 31) / 32), (unsigned)B);
+  if (Ep == 32) cln_ctx_planes_kernel<32><<<grid, 256, 0, stream>>>(ctx, HW, out, plane);
+  else if (Ep == 64) cln_ctx_planes_kernel<64><<<grid, 256, 0, stream>>>(ctx, HW, out, plane);
+  else throw Error(ACE_ERR_INVALID, "cln_ctx_planes: padded context width must be 32 or 64");
+  after_launch("cln_ctx_planes");
+}
+
+void launch_cln_w_planes(const float* w2, int C, int Ep, bf16* out, long long plane, cudaStream_t stream) {
+  const long long total = (long long)C * Ep;
+  cln_w_planes_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, 148 * 8), 256, 0, stream>>>(w2, C, Ep, out, plane);
+  after_launch("cln_w_planes");
+}
 
 int cln_padded_context(int E) {
   if (E <= 0) return 0;

@@ -35,6 +35,8 @@ struct ClnW {
   DevBuf Ws, bs, Wb, bb, Wsl, bsl, Wbl, bbl;  // Linear layers on the scalar embedding / labels
   DevBuf ws_n, wb_n, ws_p, wb_p;            // 1x1-conv weights on the noise / positional context, fp32 as given
   DevBuf w2;                                // [C][Ep][2] built by finalize
+  DevBuf wP;                                // planes [C][2 Ep] = [scale | bias] weights: A operand of the tensor-core path
+  long long wP_plane = 0;
 };
 
 // buffers of one outer-grid SHT round trip at a fixed channel count (the never-written l < m region of c1 must stay zero, so
@@ -81,6 +83,8 @@ struct ace_csfno {
 
   int wsB = 0;
   DevBuf xin, hcat, e1, hP, xn, rr, x1, c1, c2, g, g2, T, tP, tn, hmid, d1, ctx, sb0;
+  DevBuf ctxP, musr;  // tensor-core ConditionalLayerNorm: context as K-major planes [B][HW][2 Ep]; per-pixel {mean, rstd}
+  long long p_ctxP = 0;
   long long p_xin, p_hcat, p_act, p_x1, p_c1, p_c2, p_g, p_g2, p_hmid;
   RtBuf rt_in, rt_out;  // filter_residual on the big skip (in_chans wide) / filter_output (out_chans wide)
   DevBuf xrt, yP;       // planes [B][in_chans][HW]: filtered input ahead of norm_big_skip; [B][out_chans][HW]: unfiltered output
@@ -170,6 +174,11 @@ void finalize_cln(ace_csfno& n, ClnW& w, cudaStream_t s) {
   w.w2.ensure((size_t)w.C * n.Ep * 2 * sizeof(float));
   launch_build_cln_w2(w.ws_n.as<float>(), w.wb_n.as<float>(), n.cfg.embed_dim_noise, w.ws_p.as<float>(), w.wb_p.as<float>(), n.cfg.embed_dim_pos,
                       w.C, n.Ep, w.w2.as<float>(), s);
+  if (n.Ep == 32 || n.Ep == 64) {
+    w.wP_plane = (long long)w.C * 2 * n.Ep;
+    w.wP.ensure(2 * (size_t)w.wP_plane * sizeof(bf16));
+    launch_cln_w_planes(w.w2.as<float>(), w.C, n.Ep, w.wP.as<bf16>(), w.wP_plane, s);
+  }
 }
 
 void ensure_ws(ace_csfno& n, int B) {
@@ -199,6 +208,11 @@ void ensure_ws(ace_csfno& n, int B) {
   n.T.ensure((size_t)n.p_act * sizeof(float));
   n.hmid.ensure(2 * (size_t)n.p_hmid * e);
   if (n.Ep > 0) n.ctx.ensure((size_t)B * n.Ep * HW * sizeof(float));
+  if (n.Ep == 32 || n.Ep == 64) {
+    n.p_ctxP = (long long)B * HW * 2 * n.Ep;
+    n.ctxP.ensure(2 * (size_t)n.p_ctxP * sizeof(bf16));
+    n.musr.ensure((size_t)B * HW * 2 * sizeof(float));
+  }
   if (c.big_skip && c.filter_residual) {
     n.rt_in.ensure(*n.outer, c.in_chans, B);
     if (c.normalize_big_skip) n.xrt.ensure(2 * (size_t)n.p_xin * e);
@@ -222,6 +236,42 @@ void run_cln(ace_csfno& n, const ClnW& w, const bf16* x, long long x_plane, long
                             w.bb.as<float>(), w.Wsl.as<float>(), w.bsl.as<float>(), w.Wbl.as<float>(), w.bbl.as<float>(), B, w.C,
                             n.sb0.as<float>(), s);
     sb0 = n.sb0.as<float>();
+  }
+  // tensor-core path (GemmOp::cln): a statistics pass, then ONE GEMM whose two accumulators are the scale / bias modulation
+  // (K = 2 Ep) and whose epilogue normalises x and applies them (the streaming kernel below is bound by its 2 Ep FMAs per
+  // element on the FMA pipe: 200 us per norm at C = 512, 1 degree)
+  if (options().cln_gemm && (n.Ep == 32 || n.Ep == 64) && w.C >= 128 && w.wP.p && n.HW % 4 == 0 && !options().force_simt) {
+    GemmOp op = make_gemm_op("cond_layer_norm");
+    op.cln = 1;
+    op.M = w.C;
+    op.N = (int)n.HW;
+    op.K = 2 * n.Ep;
+    op.k_split = n.Ep;
+    op.Z2 = B;
+    op.A = {w.wP.as<bf16>(), w.wP_plane, 2LL * n.Ep, 1, 0, 0};
+    op.B = {n.ctxP.as<bf16>(), n.p_ctxP, 2LL * n.Ep, 1, 0, n.HW * 2LL * n.Ep};
+    op.epi.flags = EPI_RES_PLANES | EPI_OUT_PLANES;
+    op.epi.res = x;
+    op.epi.res_plane = x_plane;
+    op.epi.res_z2 = x_b;
+    op.epi.res_m0 = n.HW;
+    op.epi.res_n = 1;
+    op.epi.out = out;
+    op.epi.out_plane = o_plane;
+    op.epi.o_z2 = o_b;
+    op.epi.o_m0 = n.HW;
+    op.epi.o_n = 1;
+    op.epi.cln_musr = reinterpret_cast<const float2*>(n.musr.as<float>());
+    op.epi.cln_musr_z2 = n.HW;
+    op.epi.cln_lnw = c.affine_norms ? w.lnw.as<float>() : nullptr;
+    op.epi.cln_lnb = c.affine_norms ? w.lnb.as<float>() : nullptr;
+    op.epi.cln_sb0 = sb0;
+    op.epi.cln_sb0_z2 = w.C;
+    launch_cln_stats(x, x_plane, x_b, B, w.C, n.HW, c.norm_eps, n.musr.as<float>(), s);
+    {
+      ProfileScope prof("cond_layer_norm", s);
+      if (run_gemm_cln(op, s)) return;
+    }
   }
   launch_cond_layer_norm(x, x_plane, x_b, B, w.C, n.HW, c.affine_norms ? w.lnw.as<float>() : nullptr, c.affine_norms ? w.lnb.as<float>() : nullptr,
                          sb0, n.Ep > 0 ? w.w2.as<float>() : nullptr, n.Ep > 0 ? n.ctx.as<float>() : nullptr, n.Ep, c.norm_eps, out, o_plane,
@@ -251,6 +301,8 @@ void forward(ace_csfno& n, const float* x, const float* scalar, const float* lab
   const long long act_b = (long long)C * HW, cat_b = (long long)n.Ctot * HW, in_b = (long long)Cin * HW;
 
   if (n.Ep > 0) launch_concat_ctx(noise, c.embed_dim_noise, posctx, c.embed_dim_pos, B, HW, n.Ep, n.ctx.as<float>(), s);
+  if (options().cln_gemm && (n.Ep == 32 || n.Ep == 64) && !options().force_simt)
+    launch_cln_ctx_planes(n.ctx.as<float>(), B, n.Ep, HW, n.ctxP.as<bf16>(), n.p_ctxP, s);
 
   // network input -> split planes; the big skip is the (optionally conditionally normalised) input, stored in the tail channels
   // of the concat buffer (sfnonet.py:775-778)

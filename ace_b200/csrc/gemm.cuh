@@ -72,6 +72,14 @@ struct EpiParams {
   long long o_z1b;
   float* outf;
   long long f_z1, f_z2, f_m1, f_m0, f_n;
+  // ConditionalLayerNorm mode (GemmOp::cln): per-column {mean, rstd} of the channel LayerNorm, per-row affine of that norm and
+  // the per-(sample, row) {scale0, bias0} of the Linear context terms (null: 1, 0)
+  const float2* cln_musr;
+  long long cln_musr_z2;
+  const float* cln_lnw;
+  const float* cln_lnb;
+  const float* cln_sb0;
+  long long cln_sb0_z2;
 };
 
 struct GemmOp {
@@ -101,6 +109,11 @@ struct GemmOp {
   // B holds 2N rows; rows [N, 2N) equal rows [0, N) with the k >= k_split part negated, so the op is the plain GEMM with
   // 2N columns at half the multiplications (run_gemm falls back to exactly that when the butterfly kernel is not eligible).
   int bfly, k_split;
+  // ConditionalLayerNorm mode (fme/core/models/conditional_sfno/layers.py:285-320; tcgen05 kernel only, csfno.cu falls back to the
+  // streaming kernel of cln.cu otherwise): A = [W_scale | W_bias] along k (k_split = K / 2), B = the per-pixel context with its
+  // channels twice along k, so the two accumulators are S = W_scale ctx and T = W_bias ctx; the epilogue reads the norm's input x
+  // from epi.res (split planes) and stores  y = ((x - mean_n) rstd_n lnw_m + lnb_m) (scale0_m + S) + bias0_m + T  as split planes.
+  int cln;
   int bk_hint;  // 0 = kernel default (32); 64 = K extent per pipeline stage for K-major x K-major ops whose A streams from HBM
   EpiParams epi;
   const char* name;  // for error messages / profiling
@@ -172,5 +185,6 @@ void run_gemm_simt(const GemmOp& op, cudaStream_t stream);
 // returns false (with reason) if the op cannot run on the tcgen05 kernel
 bool umma_eligible(const GemmOp& op, const char** why);
 void run_gemm_umma(const GemmOp& op, cudaStream_t stream);
+bool run_gemm_cln(const GemmOp& op, cudaStream_t stream);  // ConditionalLayerNorm mode (GemmOp::cln); false = not eligible
 
 }  // namespace ace

@@ -86,8 +86,9 @@ constexpr int kStgBytesPerWarp = 2048;
 constexpr int kMaxSmem = 232448;  // 227 KB opt-in limit per CTA
 
 template <int BN_, bool A_MN_, bool B_MN_, uint32_t EF_, bool NC_, int BK_ = 32, bool CPLX_ = false, bool PAIR_ = false, bool BFLY_ = false,
-          bool SP_ = false, int SP_STAGES_ = 8>
+          bool SP_ = false, int SP_STAGES_ = 8, bool CLN_ = false>
 struct Cfg {
+  static constexpr bool CLN = CLN_;  // ConditionalLayerNorm mode (GemmOp::cln): two accumulators split along k like the butterfly mode
   // SP ("space on the rows"): a 1x1 convolution executed with the operand roles exchanged -- A = activations (MN-major, 256
   // spatial positions per CTA pair), B = weights (K-major, the output channels on the accumulator columns).  A thread of the
   // epilogue then owns ONE spatial position, and for every channel the 32 lanes of a warp touch 32 consecutive positions of
@@ -109,7 +110,7 @@ struct Cfg {
   // butterfly mode (GemmOp::bfly): K-chunks below / from k_split accumulate into two accumulators E, O; the epilogue stores
   // E + O at column n and E - O at column n + N
   static constexpr bool BFLY = BFLY_;
-  static constexpr int NACC = (CPLX || BFLY) ? 2 : 1;  // accumulators per tile (complex mode: real and imaginary part)
+  static constexpr int NACC = (CPLX || BFLY || CLN_) ? 2 : 1;  // accumulators per tile (complex mode: real and imaginary part)
   static constexpr uint32_t EF = EF_;
   static constexpr int UMMA_K = 16;
   static constexpr int A_PLANE = BM * BK * 2;  // bytes
@@ -128,7 +129,8 @@ struct Cfg {
   static constexpr bool SP_SHARED = SP_OPND;  // (the fp32 addend tile has the same size; barrier A separates its reads from the output writes)
   static constexpr int SP_X = SP_SHARED ? 0 : SP_NG * SP_TILE;
   static constexpr int SP_STATS = SP_NG * SP_TILE + ((SP_OPND && !SP_SHARED) ? SP_NG * SP_TILE : 0), SP_VEC = SP_STATS + 2048;
-  static constexpr int STG_BYTES = SP ? SP_VEC + kEpiWarps * 3 * 32 * 4 : kEpiWarps * kStgBytesPerWarp;
+  static constexpr int CLN_COLS = kEpiWarps * kStgBytesPerWarp;  // CLN: per warp the {mean, rstd} of the chunk's 32 columns (256 B)
+  static constexpr int STG_BYTES = SP ? SP_VEC + kEpiWarps * 3 * 32 * 4 : kEpiWarps * kStgBytesPerWarp + (CLN_ ? kEpiWarps * 256 : 0);
   // SP: the epilogue reads its addend / residual with ordinary global loads, which need L1 lines to land in; with the whole
   // 227 KB configured as shared memory hardly any are left (measured: those loads cost 24 - 37 us per launch).  Four ring
   // slots keep the kernel inside the 164 KB carve-out, i.e. 64 KB of L1.
@@ -145,6 +147,7 @@ struct Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE + STG_BYTES + BAR_BYTES + 1024;  // + alignment slack
   static_assert(BN % (B_MN_ ? 64 : 32) == 0 && BN <= 256, "BN");
   static_assert(!BFLY || (NC && !CPLX && !B_MN), "butterfly mode: NC epilogue, K-major B");
+  static_assert(!CLN_ || (NC_ && !CPLX_ && !PAIR_ && !BFLY_ && !SP_ && !A_MN_ && !B_MN_ && EF_ == (EPI_RES_PLANES | EPI_OUT_PLANES)), "CLN mode");
   static constexpr uint32_t K_LAYOUT = (BK == 64) ? 2u : 4u;  // K-major tiles: 128B swizzle (BK = 64) or 64B (BK = 32)
   static_assert(BK == 32 || BK == 64, "BK");
   static_assert(STAGES >= 2, "pipeline too shallow");
@@ -602,6 +605,109 @@ __device__ __forceinline__ void epilogue_nc(const UmmaParams& p, const Tile& ti,
     double* st = e.stats + ((long long)ti.z2 * e.stats_z2 + row) * 2;
     atomicAdd(st, (double)(s0 + s1));
     atomicAdd(st + 1, (double)(q0 + q1));
+  }
+}
+
+// ---- epilogue: CLN (ConditionalLayerNorm mode; thread = row = channel, columns = pixels, contiguous in memory) ----
+//   acc0 = S (scale modulation), acc1 = T (bias modulation);  y = x a + o  with  a = rstd_n lnw_m (scale0_m + S),
+//   o = lnb_m (scale0_m + S) - mean_n a + bias0_m + T;  x (the norm's input) is read plane by plane through the staging tile like
+//   the residual of the NC epilogue, y leaves as split planes the same way.
+template <class C>
+__device__ __forceinline__ void epilogue_cln(const UmmaParams& p, const Tile& ti, uint32_t tacc, int q, int sub, int lane, uint8_t* stg_raw,
+                                             float2* s_cols) {
+  const GemmOp& op = p.op;
+  const EpiParams& e = op.epi;
+  uint2* s8 = reinterpret_cast<uint2*>(stg_raw);
+  const int row0 = ti.m0 + 32 * q, row = row0 + lane;
+  const bool row_ok = row < op.M;
+  const int rows_valid = op.M - row0;
+  if (rows_valid <= 0) return;
+  const int rowc = row_ok ? row : op.M - 1;
+  const float lnw = e.cln_lnw ? __ldg(e.cln_lnw + rowc) : 1.f, lnb = e.cln_lnb ? __ldg(e.cln_lnb + rowc) : 0.f;
+  float sc0 = 1.f, bi0 = 0.f;
+  if (e.cln_sb0) {
+    const float2 sb = __ldg(reinterpret_cast<const float2*>(e.cln_sb0 + ((long long)ti.z2 * e.cln_sb0_z2 + rowc) * 2));
+    sc0 = sb.x;
+    bi0 = sb.y;
+  }
+  const int pr = lane >> 3, pp = lane & 7;  // plane pass: rows it*4 + pr (it < 8), 8-byte piece pp
+  const bf16* g_res = e.res + (long long)ti.z2 * e.res_z2 + (long long)(row0 + pr) * e.res_m0 + ti.n_begin + pp * 4;
+  bf16* g_pl = e.out + (long long)ti.z2 * e.o_z2 + (long long)(row0 + pr) * e.o_m0 + ti.n_begin + pp * 4;
+  const float2* g_cols = e.cln_musr + (long long)ti.z2 * e.cln_musr_z2 + ti.n_begin;
+  const int nch = (ti.n_count + 31) >> 5;
+  for (int c = sub; c < nch; c += kEpiWarps / 4) {
+    const int nvalid = min(32, ti.n_count - c * 32);  // multiple of 4 (host-checked)
+    const bool full = nvalid == 32 && rows_valid >= 32;
+    float a[32], o[32];
+    ptx::tmem_ld_32x32(tacc + c * 32, a);
+    ptx::tmem_ld_32x32(tacc + C::BN + c * 32, o);
+    // the chunk's column statistics: one coalesced load, then warp-uniform shared-memory reads
+    s_cols[lane] = (lane < nvalid) ? __ldg(g_cols + c * 32 + lane) : make_float2(0.f, 0.f);
+    __syncwarp();
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      const float4 mr = *reinterpret_cast<const float4*>(s_cols + j);  // {mean_j, rstd_j, mean_j+1, rstd_j+1}
+      const float t0 = sc0 + a[j], t1 = sc0 + a[j + 1];
+      a[j] = mr.y * lnw * t0;
+      a[j + 1] = mr.w * lnw * t1;
+      o[j] = fmaf(lnb, t0, bi0 + o[j]) - mr.x * a[j];
+      o[j + 1] = fmaf(lnb, t1, bi0 + o[j + 1]) - mr.z * a[j + 1];
+    }
+    // x planes: o += a * (hi + lo) through the staging tile; the loads of both planes are in flight together
+    const bf16* gr = g_res + c * 32;
+    uint2 t[2][8];
+#pragma unroll
+    for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        t[pl][it] = make_uint2(0u, 0u);
+        if (full || (pp * 4 < nvalid && it * 4 + pr < rows_valid))
+          t[pl][it] = __ldg(reinterpret_cast<const uint2*>(gr + (long long)(it * 4) * e.res_m0 + (pl ? e.res_plane : 0)));
+      }
+#pragma unroll
+    for (int pl = 0; pl < 2; ++pl) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) s8[swz8(it * 4 + pr, pp)] = t[pl][it];
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const uint2 w = s8[swz8(lane, k)];
+        o[4 * k] = fmaf(a[4 * k], __uint_as_float(w.x << 16), o[4 * k]);
+        o[4 * k + 1] = fmaf(a[4 * k + 1], __uint_as_float(w.x & 0xffff0000u), o[4 * k + 1]);
+        o[4 * k + 2] = fmaf(a[4 * k + 2], __uint_as_float(w.y << 16), o[4 * k + 2]);
+        o[4 * k + 3] = fmaf(a[4 * k + 3], __uint_as_float(w.y & 0xffff0000u), o[4 * k + 3]);
+      }
+      __syncwarp();
+    }
+    // split-plane store of o (pass 0: hi plane, residuals stay in o; pass 1: lo plane)
+    bf16* gp = g_pl + c * 32;
+#pragma unroll
+    for (int pl = 0; pl < 2; ++pl) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        uint32_t w[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          float& x0 = o[4 * k + 2 * i];
+          float& x1 = o[4 * k + 2 * i + 1];
+          w[i] = pack_bf16x2(x0, x1);
+          if (pl == 0) {
+            x0 -= __uint_as_float(w[i] << 16);
+            x1 -= __uint_as_float(w[i] & 0xffff0000u);
+          }
+        }
+        s8[swz8(lane, k)] = make_uint2(w[0], w[1]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const uint2 w = s8[swz8(it * 4 + pr, pp)];
+        if (full || (pp * 4 < nvalid && it * 4 + pr < rows_valid))
+          *reinterpret_cast<uint2*>(gp + (long long)(it * 4) * e.o_m0 + (pl ? e.out_plane : 0)) = w;
+      }
+      __syncwarp();
+    }
   }
 }
 
@@ -1132,9 +1238,9 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
         } else if (!(dbg & 4)) {
           // butterfly mode: the chunks from k_split on go to the second accumulator (k_split is a multiple of BK)
           const int k0 = ti.k_begin + kc * BK;
-          const bool second = C::BFLY && k0 >= op_ksplit;
+          const bool second = (C::BFLY || C::CLN) && k0 >= op_ksplit;
           const uint32_t tmem_t = tmem_d + (second ? BN : 0);
-          const bool fresh = kc == 0 || (C::BFLY && k0 == op_ksplit);
+          const bool fresh = kc == 0 || ((C::BFLY || C::CLN) && k0 == op_ksplit);
           const int kk_n = min(BK / 16, (op_K - k0 + 15) >> 4);  // K-steps entirely beyond K are not issued
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk) {
@@ -1213,7 +1319,8 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) gemm_umma_kernel(const __grid
         ptx::tc_fence_after();
         if (tr) trace_put(p, it, trs + 1, clock64());
         if (!(p.dbg & 1)) {
-          if constexpr (C::NC) epilogue_nc<C>(p, ti, tacc, q, sub, lane, stg);
+          if constexpr (C::CLN) epilogue_cln<C>(p, ti, tacc, q, sub, lane, stg, reinterpret_cast<float2*>(stg_all + C::CLN_COLS + (warp - 4) * 256));
+          else if constexpr (C::NC) epilogue_nc<C>(p, ti, tacc, q, sub, lane, stg);
           else epilogue_rowc<C>(p, ti, tacc, q, sub, lane, stg);
         }
       }
@@ -1862,6 +1969,22 @@ bool dispatch(const GemmOp& op, bool dry, cudaStream_t s, const char** why) {
 }  // namespace
 
 bool umma_eligible(const GemmOp& op, const char** why) { return dispatch(op, true, nullptr, why); }
+
+// ConditionalLayerNorm mode: returns false when the op is outside the compiled variant (the caller then uses cln.cu's kernel)
+bool run_gemm_cln(const GemmOp& op, cudaStream_t stream) {
+  const EpiParams& e = op.epi;
+  const bool ok = op.cln && op.A.s_k == 1 && op.B.s_k == 1 && aligned8(op.A.s_row) && aligned8(op.B.s_row) && aligned8(op.A.plane) &&
+                  aligned8(op.B.plane) && aligned8(op.A.s_z2) && aligned8(op.B.s_z2) && !(((uintptr_t)op.A.ptr) & 15) &&
+                  !(((uintptr_t)op.B.ptr) & 15) && op.K % 64 == 0 && op.k_split * 2 == op.K && op.Z1 == 1 && aligned4(op.N) &&
+                  e.flags == (EPI_RES_PLANES | EPI_OUT_PLANES) && e.res_n == 1 && e.o_n == 1 && aligned4(e.res_m0) && aligned4(e.res_z2) &&
+                  aligned4(e.res_plane) && !(((uintptr_t)e.res) & 7) && aligned4(e.o_m0) && aligned4(e.o_z2) && aligned4(e.out_plane) &&
+                  !(((uintptr_t)e.out) & 7) && e.cln_musr && !(((uintptr_t)e.cln_musr) & 15) && (e.cln_musr_z2 & 1) == 0 && op.M >= 1 &&
+                  e.mdiv >= op.M;
+  if (!ok) return false;
+  t_scalar_store = 0;
+  launch<Cfg<128, false, false, RS | P, true, 32, false, false, false, false, 8, true>>(op, stream);
+  return true;
+}
 
 void run_gemm_umma(const GemmOp& op, cudaStream_t stream) {
   const char* why = nullptr;

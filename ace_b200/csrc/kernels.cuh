@@ -79,6 +79,11 @@ namespace ace {
 void launch_cond_layer_norm(const bf16* x, long long x_plane, long long x_b, int B, int C, long long HW, const float* lnw, const float* lnb,
                             const float* sb0, const float* w2, const float* ctx, int Ep, float eps, bf16* out, long long o_plane,
                             long long o_b, cudaStream_t stream);
+// helpers of the tensor-core ConditionalLayerNorm (GemmOp::cln): per-pixel {mean, rstd} [B][HW][2]; the context as K-major
+// planes [B][HW][2 Ep] (channels twice along k); the weights as K-major planes [C][2 Ep] = [scale | bias]
+void launch_cln_stats(const bf16* x, long long x_plane, long long x_b, int B, int C, long long HW, float eps, float* musr, cudaStream_t stream);
+void launch_cln_ctx_planes(const float* ctx, int B, int Ep, long long HW, bf16* out, long long plane, cudaStream_t stream);
+void launch_cln_w_planes(const float* w2, int C, int Ep, bf16* out, long long plane, cudaStream_t stream);
 // smallest supported padded context width >= E, or -1
 int cln_padded_context(int E);
 // sb0 [B][C][2]: the Linear maps of the per-sample context vectors (scalar embedding, labels) incl. their biases

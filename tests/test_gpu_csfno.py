@@ -345,3 +345,38 @@ def test_fused_stepper_drives_noise_conditioned_network():
     assert not torch.equal(o1, o3)
     assert not torch.equal(o1[:, 0], o1[:, 1])
     assert torch.isfinite(o1).all()
+
+
+@pytest.mark.parametrize("img,embed,noise,pos,affine", [
+    ((48, 96), 128, 32, 0, True),     # Ep = 32 (the ERA5 baseline's context width)
+    ((36, 72), 256, 40, 20, True),    # noise + positional context padded to 64, per-sample label / scalar terms
+    ((30, 60), 160, 24, 8, False),    # a ragged last channel tile (160 = 128 + 32), pixel count not a multiple of the 128-wide tile
+])
+def test_conditional_layer_norm_tensor_core_path(img, embed, noise, pos, affine):
+    """GemmOp::cln: the ConditionalLayerNorm as a statistics pass + one tcgen05 GEMM whose epilogue normalises and modulates, against
+    the oracle and against the default streaming kernel (the GEMM path is an option: it measured slower)."""
+    import ace_b200
+    from oracle import csfno as oc
+
+    dims = dict(embed_dim_noise=noise, embed_dim_pos=pos, embed_dim_labels=3, embed_dim_scalar=2)
+    onet, net = _oracle_and_b200(img, 7, 6, dims, "legendre-gauss", 21, embed_dim=embed, num_layers=2, affine_norms=affine, normalize_big_skip=True)
+    B = 2
+    x = torch.randn(B, 7, *img)
+    ctx = dict(noise=torch.randn(B, noise, *img), embedding_pos=torch.randn(B, pos, *img) if pos else None, labels=torch.randn(B, 3),
+               embedding_scalar=torch.randn(B, 2))
+    with torch.no_grad():
+        ref = onet(x, oc.Context(**ctx))
+    out0 = net(x.cuda(), _cuda_ctx(ctx)).cpu()  # default: the streaming kernel
+    assert field_rel_err(out0, ref) < 1e-4
+    ace_b200.set_option("cln_gemm", 1)
+    ace_b200.set_option("profile", 1)
+    ace_b200._lib.profile_report()
+    try:
+        out = net(x.cuda(), _cuda_ctx(ctx)).cpu()
+        rep = ace_b200._lib.profile_report()
+    finally:
+        ace_b200.set_option("profile", 0)
+        ace_b200.set_option("cln_gemm", 0)
+    assert "cln_stats" in rep, "the tensor-core ConditionalLayerNorm path did not run"
+    assert field_rel_err(out, ref) < 1e-4, field_rel_err(out, ref)
+    assert field_rel_err(out, out0) < 3e-5, field_rel_err(out, out0)
