@@ -1891,7 +1891,12 @@ bool sp_eligible(const GemmOp& op, const Variant& v) {
     if (op.M % 256 == 0 || op.K < 256) return false;
     // (an addend tile loaded a chunk at a time leaves its latency exposed on the short K = 384 tiles: inner_skip 91 vs 76.5 us)
     if (e.flags & EPI_ADD_F32) return false;
-    if (!(options().sp_tma && options().sp_tmx) && (e.flags & (EPI_ROW_STATS | EPI_RES_PLANES))) return false;
+    if (e.flags & (EPI_ROW_STATS | EPI_RES_PLANES)) {
+      // only with the TMA-stored output / TMA-loaded residual tile (16-byte aligned strides); element-wise accesses lose
+      if (!(options().sp_tma && options().sp_tmx)) return false;
+      if (!(aligned8(e.o_m0) && aligned8(e.o_z2) && aligned8(e.out_plane) && !(((uintptr_t)e.out) & 15))) return false;
+      if ((e.flags & EPI_RES_PLANES) && !(aligned8(e.res_m0) && aligned8(e.res_z2) && aligned8(e.res_plane) && !(((uintptr_t)e.res) & 15))) return false;
+    }
   }
   return true;
 }
