@@ -136,6 +136,18 @@ extern "C" int ace_get_option(const char* key) {
   if (!strcmp(key, "dhconv_t")) return options().dhconv_t;
   if (!strcmp(key, "tile_list")) return options().tile_list;
   if (!strcmp(key, "inv2")) return options().inv2;
+  if (!strcmp(key, "sp")) return options().sp;
+  if (!strcmp(key, "sp_tma")) return options().sp_tma;
+  if (!strcmp(key, "sp_tmx")) return options().sp_tmx;
+  if (!strcmp(key, "mma_batch")) return options().mma_batch;
+  if (!strcmp(key, "bfly_pair")) return options().bfly_pair;
+  if (!strcmp(key, "group_order")) return options().group_order;
+  if (!strcmp(key, "tile_serpentine")) return options().tile_serpentine;
+  if (!strcmp(key, "cln_gemm")) return options().cln_gemm;
+  if (!strcmp(key, "pdl")) return options().pdl;
+  if (!strcmp(key, "trace")) return options().trace;
+  if (!strcmp(key, "conv_bn")) return options().conv_bn;
+  if (!strcmp(key, "dbg")) return options().dbg;
   return -1;
 }
 

@@ -80,3 +80,18 @@ def test_header_is_plain_c_and_links_from_a_c_host(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
     assert int(out.stdout.strip()) >= 100
+
+
+def test_runtime_options_round_trip_without_gpu():
+    """Every development / selection switch of the tcgen05 kernel is settable and readable through the C ABI (no GPU needed), and
+    the defaults are the measured winners."""
+    from ace_b200 import _lib
+
+    defaults = {"sp": 1, "sp_tma": 1, "sp_tmx": 1, "mma_batch": 1, "bfly_pair": 1, "group_order": 1, "tile_serpentine": 1, "cln_gemm": 0,
+                "pdl": 0, "trace": 0, "tile_list": 1, "inv2": 1, "dhconv_t": 0}
+    for key, want in defaults.items():
+        assert _lib.get_option(key) == want, key
+        _lib.set_option(key, 1 - want)
+        assert _lib.get_option(key) == 1 - want, key
+        _lib.set_option(key, want)
+        assert _lib.get_option(key) == want, key

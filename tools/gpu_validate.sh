@@ -5,7 +5,7 @@
 set -u
 cd "${GRAFT_REPO_ROOT:-.}"
 mkdir -p gpurun_out
-timeout ${ACE_VALIDATE_PYTEST_S:-600} python -m pytest tests -m gpu -q -n ${ACE_VALIDATE_WORKERS:-4} -p no:cacheprovider --timeout 400 -rf --durations=8 > gpurun_out/tests_gpu.log 2>&1
+timeout ${ACE_VALIDATE_PYTEST_S:-600} python -m pytest tests -m gpu -q -p no:cacheprovider --timeout 400 -rf --durations=8 > gpurun_out/tests_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/tests_gpu.log
 tail -4 gpurun_out/tests_gpu.log
 timeout 60 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
