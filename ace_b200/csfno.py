@@ -32,7 +32,7 @@ checkpoint, sfnonet.py:792-812; the envelope itself is only updated by training,
 Unsupported reference options raise ``NotImplementedError`` at construction (no fallback): ``filter_type`` other than
 ``"linear"``, ``global_layer_norm``, local (DISCO) blocks, ``spectral_ratio < 1`` together with a round-trip residual
 (``filter_residual`` or a non-Gaussian data grid), ``use_mlp=False``, ``encoder_layers != 1``,
-dropout, activation other than GELU, noise + positional context wider than 64 channels.
+dropout, activation other than GELU.
 """
 import ctypes
 import dataclasses
@@ -351,8 +351,6 @@ class SphericalFourierNeuralOperatorNet(nn.Module):
             if p.activation_function not in ("relu", "silu"):
                 raise ValueError(f"Unknown activation function {p.activation_function}")
             unsupported.append(f"activation_function={p.activation_function!r}")
-        if context_config.embed_dim_noise + context_config.embed_dim_pos > 64:
-            unsupported.append("noise + positional context wider than 64 channels")
         if unsupported:
             raise NotImplementedError("ace_b200 NoiseConditionedSFNO does not implement: " + ", ".join(unsupported))
         self.params, self.context_config, self.data_grid = p, context_config, data_grid

@@ -370,27 +370,103 @@ __global__ void __launch_bounds__(kWarps * 32) cln_stats_kernel(const bf16* __re
 }
 
 // ctx [B][Ep][HW] fp32 -> K-major B operand planes [B][HW][2 Ep]: the Ep context channels twice along k (the first half meets
-// the scale weights, the second half the bias weights); a 32-pixel x Ep tile is transposed through shared memory
-template <int EP>
-__global__ void __launch_bounds__(256) cln_ctx_planes_kernel(const float* __restrict__ ctx, long long HW, bf16* __restrict__ out, long long plane) {
-  __shared__ float tile[EP][33];
+// the scale weights, the second half the bias weights); 32-pixel x 64-channel tiles are transposed through shared memory
+// (any Ep: the channel axis is walked 64 at a time)
+__global__ void __launch_bounds__(256) cln_ctx_planes_kernel(const float* __restrict__ ctx, int EP, long long HW, bf16* __restrict__ out,
+                                                            long long plane) {
+  __shared__ float tile[64][33];
   const int b = blockIdx.y;
   const long long p0 = (long long)blockIdx.x * 32;
-  for (int i = threadIdx.x; i < EP * 32; i += 256) {
-    const int e = i >> 5, j = i & 31;
-    tile[e][j] = (p0 + j < HW) ? ctx[((long long)b * EP + e) * HW + p0 + j] : 0.f;
+  for (int e0 = 0; e0 < EP; e0 += 64) {
+    const int ne = min(64, EP - e0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < ne * 32; i += 256) {
+      const int e = i >> 5, j = i & 31;
+      tile[e][j] = (p0 + j < HW) ? ctx[((long long)b * EP + e0 + e) * HW + p0 + j] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * ne; i += 256) {
+      const int j = i / ne, e = i % ne;
+      if (p0 + j >= HW) continue;
+      bf16 h, l;
+      split_bf16(tile[e][j], h, l);
+      bf16* o = out + ((long long)b * HW + p0 + j) * (2 * EP) + e0 + e;
+      o[0] = h;
+      o[EP] = h;
+      o[plane] = l;
+      o[plane + EP] = l;
+    }
   }
+}
+
+// Context wider than 64 channels where the tensor-core path (GemmOp::cln) does not apply (fewer than 128 channels: the
+// conditionally normalised big skip of the network input; pixel counts that are not a multiple of 4): any E, the pixel's context
+// values are re-read per channel through L1 (E * 64 pixels * 4 B per block) instead of living in registers.  A block owns 64
+// pixels; its four thread groups of two warps take the channels c = group (mod 4).
+constexpr int kPixW = 64, kGroupsW = 4;
+__global__ void __launch_bounds__(kPixW * kGroupsW) cond_layer_norm_wide_kernel(const bf16* __restrict__ x, long long x_plane, long long x_b, int C,
+                                                                              long long HW, const float* __restrict__ lnw,
+                                                                              const float* __restrict__ lnb, const float* __restrict__ sb0,
+                                                                              const float* __restrict__ w2, const float* __restrict__ ctx, int E,
+                                                                              float eps, bf16* __restrict__ out, long long o_plane, long long o_b) {
+  __shared__ double red[kGroupsW][kPixW][2];
+  const int b = blockIdx.y, pix = threadIdx.x % kPixW, grp = threadIdx.x / kPixW;
+  const long long p = (long long)blockIdx.x * kPixW + pix;
+  const bool live = p < HW;
+  const bf16* xb = x + (long long)b * x_b + p;
+  double s = 0.0, q = 0.0;
+  if (live) {
+    for (int c = grp; c < C; c += kGroupsW) {
+      const float v = __bfloat162float(xb[(long long)c * HW]) + __bfloat162float(xb[(long long)c * HW + x_plane]);
+      s += (double)v;
+      q += (double)v * (double)v;
+    }
+  }
+  red[grp][pix][0] = s;
+  red[grp][pix][1] = q;
   __syncthreads();
-  for (int i = threadIdx.x; i < 32 * EP; i += 256) {
-    const int j = i / EP, e = i % EP;
-    if (p0 + j >= HW) continue;
-    bf16 h, l;
-    split_bf16(tile[e][j], h, l);
-    bf16* o = out + ((long long)b * HW + p0 + j) * (2 * EP) + e;
-    o[0] = h;
-    o[EP] = h;
-    o[plane] = l;
-    o[plane + EP] = l;
+  if (!live) return;
+  s = q = 0.0;
+#pragma unroll
+  for (int g = 0; g < kGroupsW; ++g) {
+    s += red[g][pix][0];
+    q += red[g][pix][1];
+  }
+  const double mean_d = s / C;
+  const float mean = (float)mean_d;
+  const float rstd = rsqrtf((float)fmax(q / C - mean_d * mean_d, 0.0) + eps);
+  const float* cp = ctx + (long long)b * E * HW + p;
+  bf16* ob = out + (long long)b * o_b + p;
+  for (int c = grp; c < C; c += kGroupsW) {
+    float sc = sb0 ? __ldg(sb0 + ((long long)b * C + c) * 2) : 1.f;
+    float bi = sb0 ? __ldg(sb0 + ((long long)b * C + c) * 2 + 1) : 0.f;
+    const float2* wp = reinterpret_cast<const float2*>(w2) + (long long)c * E;
+    float sc1 = 0.f, bi1 = 0.f;  // two independent chains per accumulator
+    int e = 0;
+    for (; e + 1 < E; e += 2) {
+      const float2 wa = __ldg(wp + e), wb = __ldg(wp + e + 1);
+      const float va = __ldg(cp + (long long)e * HW), vb = __ldg(cp + (long long)(e + 1) * HW);
+      sc = fmaf(wa.x, va, sc);
+      bi = fmaf(wa.y, va, bi);
+      sc1 = fmaf(wb.x, vb, sc1);
+      bi1 = fmaf(wb.y, vb, bi1);
+    }
+    if (e < E) {
+      const float2 wa = __ldg(wp + e);
+      const float va = __ldg(cp + (long long)e * HW);
+      sc = fmaf(wa.x, va, sc);
+      bi = fmaf(wa.y, va, bi);
+    }
+    sc += sc1;
+    bi += bi1;
+    const float v = __bfloat162float(xb[(long long)c * HW]) + __bfloat162float(xb[(long long)c * HW + x_plane]);
+    float y = (v - mean) * rstd;
+    if (lnw) y = fmaf(y, __ldg(lnw + c), __ldg(lnb + c));
+    y = fmaf(y, sc, bi);
+    bf16 hi, lo;
+    split_bf16(y, hi, lo);
+    ob[(long long)c * HW] = hi;
+    ob[(long long)c * HW + o_plane] = lo;
   }
 }
 
@@ -422,9 +498,8 @@ void launch_cln_stats(const bf16* x, long long x_plane, long long x_b, int B, in
 void launch_cln_ctx_planes(const float* ctx, int B, int Ep, long long HW, bf16* out, long long plane, cudaStream_t stream) {
   ProfileScope prof("cln_ctx_planes", stream);
   const dim3 grid((unsigned)((HW + 31) / 32), (unsigned)B);
-  if (Ep == 32) cln_ctx_planes_kernel<32><<<grid, 256, 0, stream>>>(ctx, HW, out, plane);
-  else if (Ep == 64) cln_ctx_planes_kernel<64><<<grid, 256, 0, stream>>>(ctx, HW, out, plane);
-  else throw Error(ACE_ERR_INVALID, "cln_ctx_planes: padded context width must be 32 or 64");
+  if (Ep <= 0 || Ep % 32 != 0) throw Error(ACE_ERR_INVALID, "cln_ctx_planes: padded context width must be a positive multiple of 32");
+  cln_ctx_planes_kernel<<<grid, 256, 0, stream>>>(ctx, Ep, HW, out, plane);
   after_launch("cln_ctx_planes");
 }
 
@@ -440,7 +515,7 @@ int cln_padded_context(int E) {
   if (E <= 16) return 16;
   if (E <= 32) return 32;
   if (E <= 64) return 64;
-  return -1;
+  return (E + 31) / 32 * 32;  // wider: the tensor-core path (GemmOp::cln, K = 2 Ep) or cond_layer_norm_wide_kernel
 }
 
 void launch_cond_layer_norm(const bf16* x, long long x_plane, long long x_b, int B, int C, long long HW, const float* lnw, const float* lnb,
@@ -464,7 +539,10 @@ void launch_cond_layer_norm(const bf16* x, long long x_plane, long long x_b, int
     case 16: ACE_CLN(16); break;
     case 32: ACE_CLN(32); break;
     case 64: ACE_CLN(64); break;
-    default: throw Error(ACE_ERR_INVALID, "cond_layer_norm: padded context width must be 0, 8, 16, 32 or 64");
+    default:
+      if (Ep < 0) throw Error(ACE_ERR_INVALID, "cond_layer_norm: negative context width");
+      cond_layer_norm_wide_kernel<<<dim3((unsigned)((HW + kPixW - 1) / kPixW), (unsigned)B), kPixW * kGroupsW, 0, stream>>>(
+          x, x_plane, x_b, C, HW, lnw, lnb, sb0, w2, ctx, Ep, eps, out, o_plane, o_b);
   }
 #undef ACE_CLN
   after_launch("cond_layer_norm");

@@ -174,7 +174,7 @@ void finalize_cln(ace_csfno& n, ClnW& w, cudaStream_t s) {
   w.w2.ensure((size_t)w.C * n.Ep * 2 * sizeof(float));
   launch_build_cln_w2(w.ws_n.as<float>(), w.wb_n.as<float>(), n.cfg.embed_dim_noise, w.ws_p.as<float>(), w.wb_p.as<float>(), n.cfg.embed_dim_pos,
                       w.C, n.Ep, w.w2.as<float>(), s);
-  if (n.Ep == 32 || n.Ep == 64) {
+  if (n.Ep % 32 == 0) {
     w.wP_plane = (long long)w.C * 2 * n.Ep;
     w.wP.ensure(2 * (size_t)w.wP_plane * sizeof(bf16));
     launch_cln_w_planes(w.w2.as<float>(), w.C, n.Ep, w.wP.as<bf16>(), w.wP_plane, s);
@@ -208,7 +208,7 @@ void ensure_ws(ace_csfno& n, int B) {
   n.T.ensure((size_t)n.p_act * sizeof(float));
   n.hmid.ensure(2 * (size_t)n.p_hmid * e);
   if (n.Ep > 0) n.ctx.ensure((size_t)B * n.Ep * HW * sizeof(float));
-  if (n.Ep == 32 || n.Ep == 64) {
+  if (n.Ep > 0 && n.Ep % 32 == 0) {
     n.p_ctxP = (long long)B * HW * 2 * n.Ep;
     n.ctxP.ensure(2 * (size_t)n.p_ctxP * sizeof(bf16));
     n.musr.ensure((size_t)B * HW * 2 * sizeof(float));
@@ -227,6 +227,14 @@ void ensure_ws(ace_csfno& n, int B) {
   n.wsB = B;
 }
 
+// The tensor-core ConditionalLayerNorm (GemmOp::cln) is an option for the context widths the streaming kernel holds in registers
+// (Ep = 32 / 64: measured slower there) and the default beyond them, where 2 Ep FMAs per element on the FMA
+// pipe would cost more than the rest of the block
+bool cln_on_tensor_cores(const ace_csfno& n) {
+  if (options().force_simt || n.Ep <= 0 || n.Ep % 32 != 0) return false;
+  return n.Ep > 64 || options().cln_gemm;
+}
+
 void run_cln(ace_csfno& n, const ClnW& w, const bf16* x, long long x_plane, long long x_b, const float* scalar, const float* labels, int B, bf16* out,
              long long o_plane, long long o_b, cudaStream_t s) {
   const ace_csfno_config& c = n.cfg;
@@ -240,7 +248,7 @@ void run_cln(ace_csfno& n, const ClnW& w, const bf16* x, long long x_plane, long
   // tensor-core path (GemmOp::cln): a statistics pass, then ONE GEMM whose two accumulators are the scale / bias modulation
   // (K = 2 Ep) and whose epilogue normalises x and applies them (the streaming kernel below is bound by its 2 Ep FMAs per
   // element on the FMA pipe: 200 us per norm at C = 512, 1 degree)
-  if (options().cln_gemm && (n.Ep == 32 || n.Ep == 64) && w.C >= 128 && w.wP.p && n.HW % 4 == 0 && !options().force_simt) {
+  if (cln_on_tensor_cores(n) && w.C >= 128 && w.wP.p && n.HW % 4 == 0) {
     GemmOp op = make_gemm_op("cond_layer_norm");
     op.cln = 1;
     op.M = w.C;
@@ -301,7 +309,7 @@ void forward(ace_csfno& n, const float* x, const float* scalar, const float* lab
   const long long act_b = (long long)C * HW, cat_b = (long long)n.Ctot * HW, in_b = (long long)Cin * HW;
 
   if (n.Ep > 0) launch_concat_ctx(noise, c.embed_dim_noise, posctx, c.embed_dim_pos, B, HW, n.Ep, n.ctx.as<float>(), s);
-  if (options().cln_gemm && (n.Ep == 32 || n.Ep == 64) && !options().force_simt)
+  if (cln_on_tensor_cores(n))
     launch_cln_ctx_planes(n.ctx.as<float>(), B, n.Ep, HW, n.ctxP.as<bf16>(), n.p_ctxP, s);
 
   // network input -> split planes; the big skip is the (optionally conditionally normalised) input, stored in the tail channels
@@ -447,7 +455,6 @@ extern "C" int ace_csfno_create(const ace_csfno_config* cfg, ace_sht_plan* plan_
               "ace_csfno_create: negative context width");
   const int E2 = c.embed_dim_noise + c.embed_dim_pos;
   const int Ep = cln_padded_context(E2);
-  ACE_REQUIRE(Ep >= 0, "ace_csfno_create: noise + positional context of %d channels exceeds the supported 64", E2);
   for (ace_sht_plan* p : {plan_outer, plan_inner})
     ACE_REQUIRE(p->K == c.img_h && p->W == c.img_w && p->L == c.lmax && p->M == c.mmax,
                 "ace_csfno_create: plan (%d,%d,%d,%d) does not match config (%d,%d,%d,%d)", p->K, p->W, p->L, p->M, c.img_h,

@@ -196,10 +196,9 @@ REFERENCE_NOISE_TYPE_NAME = "NoiseConditionedSFNO"
 @ModuleSelector.register(B200_NOISE_TYPE_NAME)
 @dataclasses.dataclass
 class B200NoiseConditionedSFNOBuilder(ModuleConfig):
-    """Same fields and defaults as ``NoiseConditionedSFNOBuilder`` (fme/ace/registry/stochastic_sfno.py:181-397).
-
-    One documented limit: ``noise_embed_dim + context_pos_embed_dim <= 64`` (``__post_init__`` raises otherwise; the reference's
-    default ``noise_embed_dim = 256`` therefore has to be overridden -- every released baseline config sets 32)."""
+    """Same fields and defaults as ``NoiseConditionedSFNOBuilder`` (fme/ace/registry/stochastic_sfno.py:181-397), including the
+    default ``noise_embed_dim = 256``: up to 64 channels of noise + positional context the ConditionalLayerNorm is one streaming
+    kernel, beyond that a statistics pass + one tcgen05 GEMM whose epilogue normalises and modulates (csrc/cln.cu, GemmOp::cln)."""
 
     spectral_transform: str = "sht"
     filter_type: str = "linear"
@@ -250,15 +249,6 @@ class B200NoiseConditionedSFNOBuilder(ModuleConfig):
             raise ValueError("The 'separable' parameter is no longer supported.")
         if self.operator_type != "dhconv":
             raise ValueError("Only 'dhconv' operator_type is supported for NoiseConditionedSFNO models.")
-        # LIMIT of this implementation (not of the reference): the ConditionalLayerNorm kernel keeps a pixel's context vector in
-        # registers, at most 64 channels of noise + positional context.  The reference builder's default noise_embed_dim is 256,
-        # so a config that relies on that default cannot be built here -- fail at configuration time with the reason instead
-        # of at the first forward (the released ERA5 / stochastic baselines use noise_embed_dim 32).
-        if self.noise_embed_dim + self.context_pos_embed_dim > 64:
-            raise ValueError(
-                f"B200NoiseConditionedSFNO supports at most 64 channels of noise + positional context (got noise_embed_dim="
-                f"{self.noise_embed_dim} + context_pos_embed_dim={self.context_pos_embed_dim}); set noise_embed_dim explicitly "
-                "(the released baselines use 32) or use the reference builder for this configuration")
 
     def build(self, n_in_channels: int, n_out_channels: int, dataset_info):
         from .csfno import ContextConfig, NoiseConditionedModel, SFNONetConfig, get_lat_lon_sfnonet  # noqa: PLC0415

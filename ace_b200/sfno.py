@@ -218,6 +218,7 @@ class SphericalFourierNeuralOperatorNet(nn.Module):
         self._net_device = None
         self._plans = None
         self._uploaded = {}       # param name -> (data_ptr, version) last sent to the library
+        self._offloaded = False   # offload_parameters(): the torch parameters live on the host, the library's copies on the GPU
 
     # ------------------------------------------------------------------ device object management
     def _config(self):
@@ -263,8 +264,12 @@ class SphericalFourierNeuralOperatorNet(nn.Module):
             if self._uploaded.get(name) == key:
                 continue
             if prm.device != self._net_device:
-                raise _lib.AceError(f"parameter {name} is on {prm.device}, input is on {self._net_device}")
-            t = prm.detach()
+                if not (self._offloaded and prm.device.type == "cpu"):
+                    raise _lib.AceError(f"parameter {name} is on {prm.device}, input is on {self._net_device}")
+                # offload_parameters(): the edited host copy is staged through a temporary device tensor (stream-ordered free)
+                t = prm.detach().to(self._net_device)
+            else:
+                t = prm.detach()
             if t.dtype != torch.float32 or not t.is_contiguous():
                 t = t.float().contiguous()
             _lib.check(lib.ace_sfno_set_param(self._net, name.encode(), ctypes.c_void_p(t.data_ptr()), t.numel(), stream))
@@ -272,6 +277,22 @@ class SphericalFourierNeuralOperatorNet(nn.Module):
             dirty = True
         if dirty:
             _lib.check(lib.ace_sfno_finalize(self._net))
+
+    def offload_parameters(self):
+        """Single weight residency on the GPU: after the parameters have reached the device library (split-bf16 planes, the form
+        every kernel reads), move the torch fp32 parameters to host memory.  ``state_dict`` / ``load_state_dict`` / in-place edits keep
+        working on the host copies (an edited parameter is re-uploaded before the next forward); ``.cuda()`` brings them back.
+        Frees the fp32 parameter bytes on the device: 1.8 GB at ACE2 1 degree, 6.9 GB at 0.25 degree."""
+        if self._net is None:
+            raise _lib.AceError("offload_parameters(): run one forward first (the device library has no parameters yet)")
+        with torch.cuda.device(self._net_device):
+            self._sync_params(_lib.current_stream_ptr())
+            torch.cuda.current_stream().synchronize()
+        for name, prm in self.named_parameters():
+            prm.data = prm.data.cpu()
+            self._uploaded[name] = (prm.data_ptr(), prm._version)
+        self._offloaded = True
+        return self
 
     # ------------------------------------------------------------------ forward
     def forward(self, x):

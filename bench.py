@@ -21,6 +21,8 @@ GPU (cuFFT + cuBLAS + ATen: the oracle port moved to CUDA, TF32 off and on) -- S
 
 --workload sht / inverse_sht: the reference's own micro-benchmark shapes (fme/sht_fix.py:232-327: 1024 fields of
 180x360, default lobatto grid) through ace_b200.RealSHT / InverseRealSHT, reported as HBM GB/s against the roofline.
+--workload csfno_block / csfno_block_8_groups: the reference's conditional-SFNO block micro-benchmarks
+(fme/core/models/conditional_sfno/benchmark.py:29-46).
 --workload quarter_degree: BASELINE configs[3] (721x1440, 44 in / 50 out, embed 384, 8 blocks) network forward on one GPU.
 
 --impl reference times the reference algorithm's CPU path (the oracle port of the reference modules;
@@ -489,6 +491,122 @@ def run_quarter_degree(args):
     }), flush=True)
 
 
+def run_csfno_block(args):
+    """The reference's `csfno_block` / `csfno_block_8_groups` micro-benchmarks (fme/core/models/conditional_sfno/benchmark.py:29-46:
+    one conditional FourierNeuralOperatorBlock, B = 2, C = 512, 180x360, 64 noise + 32 positional context channels + 3 labels,
+    filter_num_groups 1 or 8).  The C ABI exposes networks, not blocks: the block runs as the single block of a network with an
+    8-channel encoder / decoder, and `value` is the block's own kernels (norm0, SHT, dhconv, inverse SHT, inner_skip + GELU, norm1,
+    MLP, plus the per-forward context preparation) summed from the per-kernel CUDA-event profile; the whole forward is reported too."""
+    import torch
+
+    import ace_b200
+    from ace_b200 import _lib
+    from ace_b200 import csfno as bc
+
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    G = 8 if args.workload.endswith("8_groups") else 1
+    B, C, img, cio = 2, 512, IMG, 8
+    dims = dict(embed_dim_noise=64, embed_dim_pos=32, embed_dim_labels=3)
+    torch.manual_seed(0)
+    net = bc.get_lat_lon_sfnonet(bc.SFNONetConfig(embed_dim=C, num_layers=1, filter_num_groups=G), in_chans=cio, out_chans=cio, img_shape=img,
+                                 data_grid="legendre-gauss", context_config=bc.ContextConfig(**dims)).to(dev).eval().requires_grad_(False)
+    with torch.no_grad():
+        for k, p in net.named_parameters():
+            if "W_scale" in k or "W_bias" in k:
+                p.add_(0.1 * torch.randn_like(p))
+    x = torch.randn(B, cio, *img, device=dev)
+    ctx = bc.Context(noise=torch.randn(B, 64, *img, device=dev), embedding_pos=torch.randn(B, 32, *img, device=dev),
+                     labels=torch.randn(B, 3, device=dev))
+    K, Wm = args.steps, max(args.warmup, 3)
+    for _ in range(Wm):
+        y = net(x, ctx)
+    torch.cuda.synchronize()
+    l0 = _lib.launch_count()
+    net(x, ctx)
+    launches = _lib.launch_count() - l0
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    samples = []
+    for _ in range(max(1, args.repeats)):
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(K):
+            y = net(x, ctx)
+        ev1.record()
+        torch.cuda.synchronize()
+        samples.append(ev0.elapsed_time(ev1) / K)
+    clocks = sampler.stop()
+    _lib.set_option("profile", 1)
+    _lib.profile_report()
+    for _ in range(3):
+        net(x, ctx)
+    rep = _lib.profile_report()
+    _lib.set_option("profile", 0)
+    kus = {k: {"n": c // 3, "us": round(t / c * 1e3, 1)} for k, (c, t) in sorted(rep.items(), key=lambda kv: -kv[1][1])}
+    outside = ("encoder", "decoder", "norm_split", "split_input", "big_skip")
+    block_ms = sum(t for k, (c, t) in rep.items() if not k.startswith(outside)) / 3
+    # e2e: host tensors in (input + per-pixel context), host output out
+    host = [t.cpu().pin_memory() for t in (x, ctx.noise, ctx.embedding_pos, ctx.labels)]
+    yh = torch.empty_like(y, device="cpu").pin_memory()
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(3):
+        xd, nd, pd, ld = (t.to(dev, non_blocking=True) for t in host)
+        yh.copy_(net(xd, bc.Context(noise=nd, embedding_pos=pd, labels=ld)), non_blocking=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    e2e_ms = ev0.elapsed_time(ev1) / 3
+    # the reference block (oracle port of the fme modules) as PyTorch eager on this GPU
+    eager = None
+    try:
+        from oracle import csfno as oc
+        from oracle import sht as osht
+
+        blk = oc.FourierNeuralOperatorBlock(osht.RealSHT(*img), osht.InverseRealSHT(*img), C, img, oc.ContextConfig(**dims), filter_num_groups=G,
+                                            outer_skip=None).to(dev).eval()
+        xb = torch.randn(B, C, *img, device=dev)
+        octx = oc.Context(noise=ctx.noise, embedding_pos=ctx.embedding_pos, labels=ctx.labels)
+        eager = {}
+        old = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+        try:
+            for label, tf32 in (("fp32", False), ("tf32", True)):
+                torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = tf32
+                with torch.no_grad():
+                    for _ in range(2):
+                        blk(xb, octx)
+                    torch.cuda.synchronize()
+                    ev0.record()
+                    for _ in range(5):
+                        blk(xb, octx)
+                    ev1.record()
+                torch.cuda.synchronize()
+                eager[label] = {"ms": ev0.elapsed_time(ev1) / 5}
+        finally:
+            torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    except Exception as e:  # the eager leg is a reported baseline, not the measurement
+        eager = {"error": repr(e)[:200]}
+    ms = sorted(samples)[len(samples) // 2]
+    print(json.dumps({
+        "metric": "csfno_block_ms", "value": block_ms, "unit": "ms", "n_gpus": 1, "steps": K, "warmup": Wm, "ms_per_step": ms,
+        "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16x3 (split-bf16 3-term products, fp32 accumulate; fp32 I/O)", "data": "synthetic",
+        "config": {"workload": f"reference micro-benchmark `{args.workload}` (fme/core/models/conditional_sfno/benchmark.py:29-46): one conditional "
+                               f"SFNO block, B=2, C=512, 180x360, context 64 noise + 32 positional + 3 labels, filter_num_groups={G}",
+                   "value_is": "sum of the block's kernels (CUDA-event profile); ms_per_step = the whole one-block network forward",
+                   "l2": "inputs larger than L2 (265 MB per activation tensor)"},
+        "e2e": {"value": e2e_ms, "unit": "ms", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(sum(t.numel() * 4 for t in host)),
+                "d2h_bytes_per_step": int(yh.numel() * 4), "path": "one-block network forward, host tensors in / out"},
+        "gpu_launches": int(launches * K), "launches_per_step": int(launches), "clocks": clocks,
+        "repeats": {"n": len(samples), "ms_per_step": [round(v, 4) for v in samples]},
+        "kernels_us": kus, "gpu_eager_baseline": eager, "roofline": None, "cpu_baseline": None,
+        "outputs_finite": bool(torch.isfinite(y).all()),
+    }), flush=True)
+
+
 # --------------------------------------------------------------------------------------------- B200 arm
 def run_b200(args):
     import torch
@@ -767,7 +885,7 @@ def main():
     ap.add_argument("--no-gpu-eager-baseline", action="store_true")
     ap.add_argument("--repeats", type=int, default=3, help="repeats of the K-step timed region (median reported)")
     ap.add_argument("--sustained-steps", type=int, default=STEPS_PER_YEAR, help="length of the sustained leg (0 = skip)")
-    ap.add_argument("--workload", default="rollout", choices=["rollout", "sht", "inverse_sht", "quarter_degree"])
+    ap.add_argument("--workload", default="rollout", choices=["rollout", "sht", "inverse_sht", "quarter_degree", "csfno_block", "csfno_block_8_groups"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -775,6 +893,8 @@ def main():
         run_sht_workload(args)
     elif args.workload == "quarter_degree":
         run_quarter_degree(args)
+    elif args.workload.startswith("csfno_block"):
+        run_csfno_block(args)
     else:
         run_b200(args)
 

@@ -97,10 +97,10 @@ class ConditionalLayerNorm(nn.Module):
     def forward(self, x, context):
         vec = lambda t: t.unsqueeze(-1).unsqueeze(-1)  # noqa: E731
         shape = list(x.shape[:-2]) + [1, 1]
-        scale = vec(self.W_scale(context.embedding_scalar)) if self.W_scale is not None else torch.ones(shape, dtype=x.dtype)
+        scale = vec(self.W_scale(context.embedding_scalar)) if self.W_scale is not None else torch.ones(shape, dtype=x.dtype, device=x.device)
         if self.W_scale_2d is not None:
             scale = scale + self.W_scale_2d(context.noise)
-        bias = vec(self.W_bias(context.embedding_scalar)) if self.W_bias is not None else torch.zeros(shape, dtype=x.dtype)
+        bias = vec(self.W_bias(context.embedding_scalar)) if self.W_bias is not None else torch.zeros(shape, dtype=x.dtype, device=x.device)
         if self.W_scale_labels is not None:
             scale = scale + vec(self.W_scale_labels(context.labels))
         if self.W_bias_labels is not None:

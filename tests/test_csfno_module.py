@@ -118,8 +118,10 @@ def test_unsupported_options_raise_and_cpu_input_is_rejected():
                dict(use_mlp=False), dict(activation_function="relu")):
         with pytest.raises(NotImplementedError):
             bc.get_lat_lon_sfnonet(bc.SFNONetConfig(embed_dim=8, num_layers=1, **kw), 2, 2, (8, 16))
-    with pytest.raises(NotImplementedError):
-        bc.get_lat_lon_sfnonet(bc.SFNONetConfig(embed_dim=8, num_layers=1), 2, 2, (8, 16), context_config=bc.ContextConfig(embed_dim_noise=65))
+    # context wider than 64 channels is supported (the reference builder's default noise_embed_dim = 256 builds)
+    bc.get_lat_lon_sfnonet(bc.SFNONetConfig(embed_dim=8, num_layers=1), 2, 2, (8, 16), context_config=bc.ContextConfig(embed_dim_noise=65))
+    sel = ace_b200.ModuleSelector(type="B200NoiseConditionedSFNO", config=dict(embed_dim=8, num_layers=1))
+    assert sel.build(2, 2, ace_b200.DatasetInfo(img_shape=(8, 16))).torch_module.embed_dim == 256
     with pytest.raises(ValueError):
         ace_b200.ModuleSelector(type="B200NoiseConditionedSFNO", config=dict(context_pos_embed_dim=4))  # with pos_embed=True
     net = bc.get_lat_lon_sfnonet(bc.SFNONetConfig(embed_dim=8, num_layers=1), 2, 2, (8, 16)).requires_grad_(False)

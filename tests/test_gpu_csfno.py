@@ -380,3 +380,42 @@ def test_conditional_layer_norm_tensor_core_path(img, embed, noise, pos, affine)
     assert "cln_stats" in rep, "the tensor-core ConditionalLayerNorm path did not run"
     assert field_rel_err(out, ref) < 1e-4, field_rel_err(out, ref)
     assert field_rel_err(out, out0) < 3e-5, field_rel_err(out, out0)
+
+
+@pytest.mark.parametrize("img,embed,noise,pos,tensor_core", [
+    ((36, 72), 128, 64, 32, True),    # the context widths of the reference's block benchmark (conditional_sfno/benchmark.py:34-36): Ep = 96
+    ((30, 60), 64, 256, 0, False),    # the reference builder's default noise_embed_dim = 256 on a 64-channel latent: streaming wide kernel
+    ((27, 54), 128, 70, 0, False),    # pixel count not a multiple of 4 (no tensor-core path), 70 channels padded to 96
+])
+def test_context_wider_than_64_channels(img, embed, noise, pos, tensor_core):
+    """Noise + positional context beyond the 64 channels the streaming kernel holds in registers: the block norms go to the
+    tensor-core ConditionalLayerNorm (GemmOp::cln) by default, the conditionally normalised big skip (7 channels) and shapes
+    outside the GEMM variant to cond_layer_norm_wide_kernel."""
+    import ace_b200
+    from oracle import csfno as oc
+
+    dims = dict(embed_dim_noise=noise, embed_dim_pos=pos, embed_dim_labels=3, embed_dim_scalar=0)
+    onet, net = _oracle_and_b200(img, 7, 6, dims, "legendre-gauss", 23, embed_dim=embed, num_layers=2, affine_norms=True, normalize_big_skip=True)
+    B = 2
+    x = torch.randn(B, 7, *img)
+    ctx = dict(noise=torch.randn(B, noise, *img), embedding_pos=torch.randn(B, pos, *img) if pos else None, labels=torch.randn(B, 3),
+               embedding_scalar=None)
+    with torch.no_grad():
+        ref = onet(x, oc.Context(**ctx))
+    ace_b200.set_option("profile", 1)
+    ace_b200._lib.profile_report()
+    try:
+        out = net(x.cuda(), _cuda_ctx(ctx)).cpu()
+        rep = ace_b200._lib.profile_report()
+    finally:
+        ace_b200.set_option("profile", 0)
+    assert ("cln_stats" in rep) == tensor_core, sorted(rep)
+    assert field_rel_err(out, ref) < 1e-4, field_rel_err(out, ref)
+    # the streaming wide kernel alone reproduces the tensor-core result
+    if tensor_core:
+        ace_b200.set_option("force_simt", 1)
+        try:
+            out_simt = net(x.cuda(), _cuda_ctx(ctx)).cpu()
+        finally:
+            ace_b200.set_option("force_simt", 0)
+        assert field_rel_err(out_simt, ref) < 1e-4, field_rel_err(out_simt, ref)

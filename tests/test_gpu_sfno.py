@@ -149,6 +149,33 @@ def test_module_contract():
             net(torch.zeros(1, 5, 16, 32, device="cuda"))
 
 
+def test_offload_parameters_single_weight_residency():
+    """``offload_parameters()``: the fp32 torch parameters leave the GPU (the library's split planes are the only device copy),
+    the forward is unchanged bit for bit, and edits of the host copies are re-uploaded."""
+    import ace_b200
+
+    net = _b200_net((32, 64), 3, 4, dict(embed_dim=64, num_layers=2, operator_type="dhconv")).cuda().eval().requires_grad_(False)
+    with pytest.raises(ace_b200.AceError):
+        net.offload_parameters()  # nothing uploaded yet
+    x = torch.randn(2, 3, 32, 64, device="cuda")
+    y1 = net(x)
+    torch.cuda.synchronize()
+    n_param_bytes = sum(p.numel() * 4 for p in net.parameters())
+    m0 = torch.cuda.memory_allocated()
+    net.offload_parameters()
+    assert all(p.device.type == "cpu" for p in net.parameters())
+    assert m0 - torch.cuda.memory_allocated() >= 0.95 * n_param_bytes
+    assert torch.equal(net(x), y1)
+    net.decoder[2].weight.mul_(2.0)  # host-side edit
+    torch.testing.assert_close(net(x), 2 * y1, rtol=1e-4, atol=1e-6)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    sd["decoder.2.weight"] = sd["decoder.2.weight"] / 2
+    net.load_state_dict(sd)
+    assert torch.equal(net(x), y1)
+    net.cuda()  # and back
+    assert torch.equal(net(x), y1)
+
+
 @pytest.mark.timeout(900)
 def test_baseline_config_full_size_parity():
     """BASELINE.json configs[1] at full size: ACE2 1 degree (180x360, 44 in / 50 out, embed 384, 8 blocks, dhconv,
