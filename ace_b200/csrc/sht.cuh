@@ -32,6 +32,8 @@ struct ace_sht_plan {
   long long wt_plane, pinv_plane, fdft_plane, idft_plane;
   // lazily grown workspace of the standalone transform API
   ace::DevBuf ws_x, ws_x1, ws_c1, ws_c2, ws_g;
+  ace::DevBuf ws_g2;    // HEALPix inverse: the padded, parity-split g2 layout (the lat-lon standalone API uses ws_g)
+  ace::DevBuf ws_hpx;   // HEALPix ring stage (healpix.cu): [fields][rings][M] complex fp32 between the ring DFT and the plane layouts
   long long ws_fields = 0;         // capacity
   long long ws_fields_layout = 0;  // field count the c1/c2 zero regions are currently valid for
 
