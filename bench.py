@@ -23,6 +23,7 @@ GPU (cuFFT + cuBLAS + ATen: the oracle port moved to CUDA, TF32 off and on) -- S
 180x360, default lobatto grid) through ace_b200.RealSHT / InverseRealSHT, reported as HBM GB/s against the roofline.
 --workload csfno_block / csfno_block_8_groups: the reference's conditional-SFNO block micro-benchmarks
 (fme/core/models/conditional_sfno/benchmark.py:29-46).
+--workload healpix: BASELINE configs[4] as SURVEY.md maps it (HEALPix SHT pair, nside 64, 4 x 50 fields split over the ranks).
 --workload quarter_degree: BASELINE configs[3] (721x1440, 44 in / 50 out, embed 384, 8 blocks) network forward on one GPU.
 
 --impl reference times the reference algorithm's CPU path (the oracle port of the reference modules;
@@ -607,6 +608,109 @@ def run_csfno_block(args):
     }), flush=True)
 
 
+def run_healpix(args):
+    """BASELINE configs[4] as SURVEY.md section 0 / 8(d) maps it: the HEALPix SHT pair of fme/core/cuhpx/sht.py:32-153 at nside 64
+    (lmax = mmax = 127, 49 152 ring-ordered pixels), input randn(4, 50, npix) (seed 0), the 4 samples split over the ranks
+    (1 sample per GPU on 4 GPUs; every rank keeps at least one).  A step = one forward + one inverse transform of the rank's fields
+    through ace_b200.HealpixSHT / HealpixISHT (C ABI ace_hpx_forward / ace_hpx_inverse)."""
+    import torch
+
+    import ace_b200
+    from ace_b200 import _lib, parallel
+
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    rank, world, local_rank = parallel.init_from_env(backend="nccl", device=dev)
+    nside, lmax, nch, nsamp = 64, 127, 50, 4
+    npix = 12 * nside**2
+    per_rank = max(1, nsamp // world)
+    K, Wm = args.steps, max(args.warmup, 3)
+    fwd = ace_b200.HealpixSHT(nside, lmax=lmax, mmax=lmax, quad_weights="none")
+    inv = ace_b200.HealpixISHT(nside, lmax=lmax, mmax=lmax)
+    torch.manual_seed(0)
+    x_all = torch.randn(nsamp, nch, npix)
+    x = x_all[(rank * per_rank) % nsamp:][:per_rank].to(dev)
+
+    def barrier():
+        parallel.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(Wm):
+        c = fwd(x)
+        y = inv(c)
+    torch.cuda.synchronize(dev)
+    l0 = _lib.launch_count()
+    inv(fwd(x))
+    launches = _lib.launch_count() - l0
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    samples = []
+    for _ in range(max(1, args.repeats)):
+        barrier()
+        ev0.record()
+        for _ in range(K):
+            y = inv(fwd(x))
+        ev1.record()
+        barrier()
+        samples.append(parallel.max_over_ranks(ev0.elapsed_time(ev1), device=dev) / K)
+    clocks = sampler.stop()
+    ms = sorted(samples)[len(samples) // 2]
+    # end to end: host pixels in, host pixels out
+    xh = x.cpu().pin_memory()
+    yh = torch.empty_like(xh).pin_memory()
+    barrier()
+    ev0.record()
+    for _ in range(5):
+        yh.copy_(inv(fwd(xh.to(dev, non_blocking=True))), non_blocking=True)
+    ev1.record()
+    barrier()
+    e2e_ms = parallel.max_over_ranks(ev0.elapsed_time(ev1), device=dev) / 5
+    if rank != 0:
+        return
+    _lib.set_option("profile", 1)
+    _lib.profile_report()
+    for _ in range(3):
+        inv(fwd(x))
+    rep = _lib.profile_report()
+    _lib.set_option("profile", 0)
+    kus = {k: round(t / n * 1e3, 1) for k, (n, t) in rep.items()}
+    nf = per_rank * nch
+    L = M = lmax
+    T = 4 * nside - 1
+    by = 2 * (nf * (npix * 4 + L * M * 8) + M * L * T * 4)  # per rank and step: pixels + coefficients + one Legendre table, both directions
+    gbps = lambda t_ms: world * by / (t_ms * 1e-3) / 1e9
+    pk = peaks()
+    # reference algorithm on the host (oracle port of the cuhpx classes: a Python loop of 255 torch.fft calls per direction)
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import healpix as oh
+
+        o_f, o_i = oh.SHT(nside, lmax, lmax, oh.uniform_weights(nside)), oh.iSHT(nside, lmax, lmax)
+        xs = x_all[:1]
+        o_i(o_f(xs))
+        t0 = time.time()
+        o_i(o_f(xs))
+        dt = time.time() - t0
+        cpu = {"value": (2 * (nch * (npix * 4 + L * M * 8) + M * L * T * 4)) / dt / 1e9, "unit": "GB/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"one forward + inverse pair of 1 x {nch} fields, oracle port of fme/core/cuhpx (torch CPU), {dt * 1e3:.0f} ms"}
+    print(json.dumps({
+        "metric": "healpix_sht_hbm_gbps", "value": gbps(ms), "unit": "GB/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "strong" if world <= nsamp else "weak", "vs_baseline": None,
+        "dtype": "bf16x3 Legendre stage (split-bf16, fp32 accumulate), fp32 ring DFT; fp32 / complex64 I/O", "data": "synthetic",
+        "config": {"workload": f"HEALPix SHT pair (BASELINE configs[4] per SURVEY section 0): nside {nside}, lmax = mmax = {lmax}, {nsamp} x {nch} fields "
+                               f"split {per_rank} sample(s) per GPU; step = forward + inverse transform", "l2": "no flush: 39 MB of pixels + 26 MB of "
+                               "coefficients per rank fit the L2; the transform is compute / latency bound (see kernels_us)"},
+        "e2e": {"value": gbps(e2e_ms), "unit": "GB/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(xh.numel() * 4), "d2h_bytes_per_step": int(yh.numel() * 4)},
+        "gpu_launches": int(launches * K), "launches_per_step": int(launches), "clocks": clocks,
+        "repeats": {"n": len(samples), "ms_per_step": [round(v, 4) for v in samples]},
+        "roofline": {"bound": "hbm", "achieved": by / (ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": by / (ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                     "traffic": None, "algorithmic_bytes": by, "note": "per GPU, whole pair (8 kernels); peak of " + pk["source"]},
+        "kernels_us": kus, "cpu_baseline": cpu, "outputs_finite": bool(torch.isfinite(y).all()),
+    }), flush=True)
+
+
 # --------------------------------------------------------------------------------------------- B200 arm
 def run_b200(args):
     import torch
@@ -885,7 +989,7 @@ def main():
     ap.add_argument("--no-gpu-eager-baseline", action="store_true")
     ap.add_argument("--repeats", type=int, default=3, help="repeats of the K-step timed region (median reported)")
     ap.add_argument("--sustained-steps", type=int, default=STEPS_PER_YEAR, help="length of the sustained leg (0 = skip)")
-    ap.add_argument("--workload", default="rollout", choices=["rollout", "sht", "inverse_sht", "quarter_degree", "csfno_block", "csfno_block_8_groups"])
+    ap.add_argument("--workload", default="rollout", choices=["rollout", "sht", "inverse_sht", "quarter_degree", "csfno_block", "csfno_block_8_groups", "healpix"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -895,6 +999,8 @@ def main():
         run_quarter_degree(args)
     elif args.workload.startswith("csfno_block"):
         run_csfno_block(args)
+    elif args.workload == "healpix":
+        run_healpix(args)
     else:
         run_b200(args)
 
