@@ -40,82 +40,160 @@ __host__ __device__ inline Ring ring_of(int t, int nside) {
 
 // Ring stage, forward:  X[m] = e^{-i m phi0} sum_j x[j] e^{-2 pi i j m / nphi}  for m < min(nphi/2 + 1, M), zero beyond
 // (tools.py:44-55).  Two kernels:
-//   hpx_ring_dft_fwd_kernel   x [C][npix] fp32 -> tmp [C][K rings][M] complex fp32.  A block owns one ring and kFT = 8 fields; the
-//       ring's samples sit in shared memory as [j][8 fields] (two warp-uniform 16-byte reads per j), a thread owns one order m and
-//       keeps the 8 fields' (re, im) sums in registers: 16 FMAs per twiddle read instead of 2.  Stores are contiguous along m.
+//   hpx_ring_dft_fwd_kernel   x [C][npix] fp32 -> tmp [C][K rings][M] complex fp32.  A block is ONE warp that owns one ring and
+//       kFT = 8 fields.  The ring's samples sit in shared memory as [j][8 fields], folded for the real-input symmetry (slot j keeps
+//       e = x[j] + x[n-j], slot n - j keeps o = x[j] - x[n-j]: Re = sum_j e cos, Im = -sum_j o sin, half the multiplications).
+//       A lane owns kMT = 4 orders m = lane + 32 i and keeps their 8 fields' (re, im) sums in registers: 64 FMAs per j against
+//       64 bytes of samples and ONE per-lane twiddle read -- the other three twiddles are that one times the warp-uniform
+//       e^{-2 pi i 32 j / n}.  (The shared-memory return path moves 128 B/clk per SM whether or not the lanes read the same
+//       address: the version with one order per lane needed 4.5 B per FMA and ran at a fifth of the FMA rate.)
 //   hpx_tmp_to_x1_kernel      tmp -> X1 planes [(2m + reim)][C][Kp] (ring index contiguous, the Legendre GEMM's A operand):
 //       32 x 32 tiles transposed through shared memory, so the 2-byte plane stores come in 64-byte runs instead of one sector per
-//       element (a block of the one-kernel version owned ONE ring, i.e. one column of X1).
-// grid (rings, ceil(C / kFT)), 128 threads.
-__global__ void __launch_bounds__(128) hpx_ring_dft_fwd_kernel(const float* __restrict__ x, int C, int nside, int K, int M,
-                                                              float2* __restrict__ tmp) {
-  __shared__ float4 sx[kMaxPhi][kFT / 4];
-  __shared__ float2 tw[kMaxPhi];
-  const int t = blockIdx.x, c0 = blockIdx.y * kFT;
-  const Ring r = ring_of(t, nside);
-  const long long npix = 12LL * nside * nside;
-  for (int i = threadIdx.x; i < r.nphi; i += blockDim.x) {
-    double s, c;
-    sincospi(2.0 * (double)i / (double)r.nphi, &s, &c);
-    tw[i] = make_float2((float)c, (float)s);
-  }
-  float* sxf = reinterpret_cast<float*>(sx);
-  for (int i = threadIdx.x; i < kFT * r.nphi; i += blockDim.x) {
-    const int f = i / r.nphi, j = i - f * r.nphi;
-    sxf[j * kFT + f] = (c0 + f < C) ? x[(long long)(c0 + f) * npix + r.start + j] : 0.f;
-  }
-  __syncthreads();
-  // real input: fold x[j] and x[nphi - j] (same cosine, opposite sine) in place -- slot j keeps e = x[j] + x[n-j], slot n - j
-  // o = x[j] - x[n-j] for 0 < j < n/2 -- which halves the multiplications: Re = sum_j e cos, Im = -sum_j o sin
-  const int half = r.nphi / 2;  // nphi is a multiple of 4
-  for (int i = threadIdx.x; i < kFT * (half - 1); i += blockDim.x) {
-    const int f = i % kFT, j = 1 + i / kFT;
-    const float a = sxf[j * kFT + f], b = sxf[(r.nphi - j) * kFT + f];
-    sxf[j * kFT + f] = a + b;
-    sxf[(r.nphi - j) * kFT + f] = a - b;
-  }
-  __syncthreads();
-  const int nm = min(half + 1, M);
-  for (int m = threadIdx.x; m < M; m += blockDim.x) {
-    float re[kFT], im[kFT];
+//       element (a block of the ring kernel owns ONE ring, i.e. one column of X1).
+// grid (rings, ceil(C / kFT)), 32 threads, dynamic shared memory hpx_fwd_smem(nside).
+constexpr int kMT = 4;  // orders (forward) / pixel pairs (inverse) per lane at most
+__host__ __device__ inline size_t hpx_fwd_smem(int nside) { return (size_t)4 * nside * (kFT * sizeof(float) + sizeof(float2)); }
+__host__ __device__ inline size_t hpx_inv_smem(int nside) { return (size_t)(2 * nside + 1) * kFT * sizeof(float2) + (size_t)4 * nside * sizeof(float2); }
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+// packed fp32 pairs (fma.rn.f32x2, SASS FFMA2): one issue slot per two FMAs -- the loops below are issue-bound otherwise
+struct f2 {
+  unsigned long long u;
+};
+__device__ __forceinline__ f2 mk2(float a, float b) {
+  f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.u) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void un2(f2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v.u)); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+  f2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d.u) : "l"(a.u), "l"(b.u), "l"(c.u));
+  return d;
+}
+
+// the orders m = m0 + lane + 32 i, i < MT, of one ring and 8 fields (MT by ring length: short polar rings have few orders)
+template <int MT>
+__device__ __forceinline__ void hpx_fwd_orders(const float4* sx, const float2* tw, int n, int nm, int m0, int lane, int M, int C, int c0, int K, int t,
+                                               double phi0, float2* __restrict__ tmp) {
+  const int half = n / 2;
+  f2 re[MT][kFT / 2], im[MT][kFT / 2];
+  {  // j = 0 and j = n/2: cosine 1 and (-1)^m, no sine term
+    const float4 a = sx[0], b = sx[1], c = sx[half * 2], d = sx[half * 2 + 1];
+    const f2 v0[kFT / 2] = {mk2(a.x, a.y), mk2(a.z, a.w), mk2(b.x, b.y), mk2(b.z, b.w)};
+    const f2 vh[kFT / 2] = {mk2(c.x, c.y), mk2(c.z, c.w), mk2(d.x, d.y), mk2(d.z, d.w)};
 #pragma unroll
-    for (int f = 0; f < kFT; ++f) re[f] = im[f] = 0.f;
-    if (m < nm) {
-      {  // j = 0 and j = n/2: cosine 1 and (-1)^m, no sine term
-        const float4 a = sx[0][0], b = sx[0][1], c = sx[half][0], d = sx[half][1];
-        const float sg = (m & 1) ? -1.f : 1.f;
-        const float v0[kFT] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}, vh[kFT] = {c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
+    for (int i = 0; i < MT; ++i) {
+      const float sg = ((m0 + lane + 32 * i) & 1) ? -1.f : 1.f;
+      const f2 sg2 = mk2(sg, sg);
 #pragma unroll
-        for (int f = 0; f < kFT; ++f) re[f] = fmaf(vh[f], sg, v0[f]);
-      }
-      int q = m;  // (j * m) mod nphi
-#pragma unroll 2
-      for (int j = 1; j < half; ++j) {
-        const float2 w = tw[q];
-        const float4 a = sx[j][0], b = sx[j][1], c = sx[r.nphi - j][0], d = sx[r.nphi - j][1];
-        const float e[kFT] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}, o[kFT] = {c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
-#pragma unroll
-        for (int f = 0; f < kFT; ++f) {
-          re[f] = fmaf(e[f], w.x, re[f]);
-          im[f] = fmaf(-o[f], w.y, im[f]);
-        }
-        q += m;
-        if (q >= r.nphi) q -= r.nphi;
-      }
-      double ps, pc;
-      sincos(-(double)m * r.phi0, &ps, &pc);
-      const float fc = (float)pc, fs = (float)ps;
-#pragma unroll
-      for (int f = 0; f < kFT; ++f) {
-        const float a = re[f] * fc - im[f] * fs, b = re[f] * fs + im[f] * fc;
-        re[f] = a;
-        im[f] = b;
+      for (int h = 0; h < kFT / 2; ++h) {
+        re[i][h] = fma2(vh[h], sg2, v0[h]);
+        im[i][h] = mk2(0.f, 0.f);
       }
     }
-#pragma unroll
-    for (int f = 0; f < kFT; ++f)
-      if (c0 + f < C) tmp[((long long)(c0 + f) * K + t) * M + m] = make_float2(re[f], im[f]);
   }
+  const int mstep = (m0 + lane) % n, ustep = 32 % n;
+  int q = mstep, qu = ustep;  // (j * m) mod n for this lane's first order; (j * 32) mod n
+  for (int j = 1; j < half; ++j) {
+    float2 w[MT];
+    w[0] = tw[q];
+    if (MT > 1) {
+      const float2 u = tw[qu];
+#pragma unroll
+      for (int i = 1; i < MT; ++i) w[i] = cmul(w[i - 1], u);
+    }
+    const float4 a = sx[2 * j], b = sx[2 * j + 1], c = sx[2 * (n - j)], d = sx[2 * (n - j) + 1];
+    const f2 e[kFT / 2] = {mk2(a.x, a.y), mk2(a.z, a.w), mk2(b.x, b.y), mk2(b.z, b.w)};
+    const f2 o[kFT / 2] = {mk2(c.x, c.y), mk2(c.z, c.w), mk2(d.x, d.y), mk2(d.z, d.w)};
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+      const f2 wc = mk2(w[i].x, w[i].x), ws = mk2(-w[i].y, -w[i].y);
+#pragma unroll
+      for (int h = 0; h < kFT / 2; ++h) {
+        re[i][h] = fma2(e[h], wc, re[i][h]);
+        im[i][h] = fma2(o[h], ws, im[i][h]);
+      }
+    }
+    q += mstep;
+    if (q >= n) q -= n;
+    qu += ustep;
+    if (qu >= n) qu -= n;
+  }
+#pragma unroll
+  for (int i = 0; i < MT; ++i) {
+    const int m = m0 + lane + 32 * i;
+    if (m >= M) continue;
+    float fc = 0.f, fs = 0.f;
+    const bool on = m < nm;
+    if (on) {
+      double ps, pc;
+      sincos(-(double)m * phi0, &ps, &pc);
+      fc = (float)pc;
+      fs = (float)ps;
+    }
+#pragma unroll
+    for (int h = 0; h < kFT / 2; ++h) {
+      float r0, r1, i0, i1;
+      un2(re[i][h], r0, r1);
+      un2(im[i][h], i0, i1);
+      const int f = 2 * h;
+      if (c0 + f < C) tmp[((long long)(c0 + f) * K + t) * M + m] = on ? make_float2(r0 * fc - i0 * fs, r0 * fs + i0 * fc) : make_float2(0.f, 0.f);
+      if (c0 + f + 1 < C)
+        tmp[((long long)(c0 + f + 1) * K + t) * M + m] = on ? make_float2(r1 * fc - i1 * fs, r1 * fs + i1 * fc) : make_float2(0.f, 0.f);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(32) hpx_ring_dft_fwd_kernel(const float* __restrict__ x, int C, int nside, int K, int M,
+                                                             float2* __restrict__ tmp) {
+  extern __shared__ float4 hpx_smem[];
+  const int cap = 4 * nside;
+  float4* sx = hpx_smem;                                     // [cap][kFT / 4]
+  float2* tw = reinterpret_cast<float2*>(hpx_smem + cap * (kFT / 4));  // [cap]
+  const int t = blockIdx.x, c0 = blockIdx.y * kFT, lane = threadIdx.x;
+  const Ring r = ring_of(t, nside);
+  const int n = r.nphi, half = n / 2;  // n is a multiple of 4
+  const long long npix = 12LL * nside * nside;
+  for (int i = lane; i < n; i += 32) {
+    float sn, cs;
+    sincospif(2.f * (float)i / (float)n, &sn, &cs);
+    tw[i] = make_float2(cs, sn);
+  }
+  float* sxf = reinterpret_cast<float*>(sx);
+  for (int f = 0; f < kFT; ++f) {
+    const bool live = c0 + f < C;
+    const float* xr = x + (long long)(c0 + f) * npix + r.start;
+    for (int j = lane; j < n; j += 32) sxf[j * kFT + f] = live ? xr[j] : 0.f;
+  }
+  __syncwarp();
+  for (int i = lane; i < kFT * (half - 1); i += 32) {
+    const int f = i % kFT, j = 1 + i / kFT;
+    const float a = sxf[j * kFT + f], b = sxf[(n - j) * kFT + f];
+    sxf[j * kFT + f] = a + b;
+    sxf[(n - j) * kFT + f] = a - b;
+  }
+  __syncwarp();
+  const int nm = min(half + 1, M);
+  int m0 = 0;
+  // warp-uniform dispatch: as many orders per lane as the ring has left
+  for (; m0 < nm; ) {
+    const int left = nm - m0;
+    if (left > 64) {
+      hpx_fwd_orders<4>(sx, tw, n, nm, m0, lane, M, C, c0, K, t, r.phi0, tmp);
+      m0 += 128;
+    } else if (left > 32) {
+      hpx_fwd_orders<2>(sx, tw, n, nm, m0, lane, M, C, c0, K, t, r.phi0, tmp);
+      m0 += 64;
+    } else {
+      hpx_fwd_orders<1>(sx, tw, n, nm, m0, lane, M, C, c0, K, t, r.phi0, tmp);
+      m0 += 32;
+    }
+  }
+  // orders the ring does not resolve: zero
+  for (int m = m0 + lane; m < M; m += 32)
+    for (int f = 0; f < kFT; ++f)
+      if (c0 + f < C) tmp[((long long)(c0 + f) * K + t) * M + m] = make_float2(0.f, 0.f);
 }
 
 // tmp [C][K][2M] fp32 (2M = interleaved re / im of the orders) -> X1 planes [(2m + reim)][C][Kp]; grid (C, ceil(2M/32), ceil(K/32))
@@ -170,66 +248,134 @@ __global__ void __launch_bounds__(256) hpx_g_to_tmp_kernel(const bf16* __restric
   }
 }
 
-__global__ void __launch_bounds__(256) hpx_ring_dft_inv_kernel(const float2* __restrict__ tmp, int C, int nside, int K, int M,
-                                                              float* __restrict__ y) {
-  __shared__ float4 sg[kMaxPhi / 2 + 1][kFT / 2];  // [m][field pair] = (re, im, re, im)
-  __shared__ float2 tw[kMaxPhi];
-  const int t = blockIdx.x, c0 = blockIdx.y * kFT;
-  const Ring r = ring_of(t, nside);
-  const long long npix = 12LL * nside * nside;
-  const int nyq = r.nphi / 2;
-  const int nm = min(nyq + 1, M);
-  for (int i = threadIdx.x; i < r.nphi; i += blockDim.x) {
-    double s, c;
-    sincospi(2.0 * (double)i / (double)r.nphi, &s, &c);
-    tw[i] = make_float2((float)c, (float)s);
-  }
-  float2* sg2 = reinterpret_cast<float2*>(sg);
-  for (int i = threadIdx.x; i < kFT * nm; i += blockDim.x) {
-    const int f = i / nm, m = i - f * nm;
-    float2 v = make_float2(0.f, 0.f);
-    if (c0 + f < C) {
-      const float2 gc = tmp[((long long)(c0 + f) * K + t) * M + m];
-      double ps, pc;
-      sincos((double)m * r.phi0, &ps, &pc);
-      v.x = gc.x * (float)pc - gc.y * (float)ps;
-      v.y = gc.x * (float)ps + gc.y * (float)pc;
-      // Hermitian weights of the c2r transform
-      const float wgt = (m == 0 || m == nyq) ? 1.f : 2.f;
-      v.x *= wgt;
-      v.y = (m == 0 || m == nyq) ? 0.f : v.y * wgt;
-    }
-    sg2[m * kFT + f] = v;
-  }
-  __syncthreads();
-  // real output: y[j] and y[nphi - j] share sum_m vr cos (A) and differ in the sign of sum_m vi sin (S): a thread owns the pair
-  for (int j = threadIdx.x; j <= nyq; j += blockDim.x) {
-    float A[kFT], S[kFT];
+// One warp per (ring, 8 fields): a lane owns up to kMT = 4 pixel pairs (j, n - j), j = j0 + lane + 32 i, and their 8 fields' cosine /
+// sine sums (64 FMAs, issued as 32 FFMA2, per order m against 64 bytes of coefficients and one per-lane twiddle read, like the
+// forward kernel); the Nyquist pixel j = n/2 (cosine (-1)^m, no sine) is a warp reduction.
+// grid (rings, ceil(C / kFT)), 32 threads, hpx_inv_smem(nside) bytes.
+template <int MT>
+__device__ __forceinline__ void hpx_inv_pixels(const float4* sg, const float2* tw, int n, int nm, int j0, int lane, int C, int c0, float* __restrict__ yr0,
+                                               long long npix) {
+  const int nyq = n / 2;
+  f2 A[MT][kFT / 2], S[MT][kFT / 2];
 #pragma unroll
-    for (int f = 0; f < kFT; ++f) A[f] = S[f] = 0.f;
-    int q = 0;  // (j * m) mod nphi
-#pragma unroll 2
-    for (int m = 0; m < nm; ++m) {
-      const float2 w = tw[q];
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int h = 0; h < kFT / 2; ++h) A[i][h] = S[i][h] = mk2(0.f, 0.f);
+  const int jstep = (j0 + lane) % n, ustep = 32 % n;
+  int q = 0, qu = 0;  // (m * j) mod n for this lane's first pixel; (m * 32) mod n
+  for (int m = 0; m < nm; ++m) {
+    float2 w[MT];
+    w[0] = tw[q];
+    if (MT > 1) {
+      const float2 u = tw[qu];
+#pragma unroll
+      for (int i = 1; i < MT; ++i) w[i] = cmul(w[i - 1], u);
+    }
+    const float4 a = sg[4 * m], b = sg[4 * m + 1], c = sg[4 * m + 2], d = sg[4 * m + 3];  // row m: 8 real parts, then 8 imaginary parts
+    const f2 vr[kFT / 2] = {mk2(a.x, a.y), mk2(a.z, a.w), mk2(b.x, b.y), mk2(b.z, b.w)};
+    const f2 vi[kFT / 2] = {mk2(c.x, c.y), mk2(c.z, c.w), mk2(d.x, d.y), mk2(d.z, d.w)};
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+      const f2 wc = mk2(w[i].x, w[i].x), ws = mk2(w[i].y, w[i].y);
 #pragma unroll
       for (int h = 0; h < kFT / 2; ++h) {
-        const float4 v = sg[m][h];
-        A[2 * h] = fmaf(v.x, w.x, A[2 * h]);
-        S[2 * h] = fmaf(v.y, w.y, S[2 * h]);
-        A[2 * h + 1] = fmaf(v.z, w.x, A[2 * h + 1]);
-        S[2 * h + 1] = fmaf(v.w, w.y, S[2 * h + 1]);
+        A[i][h] = fma2(vr[h], wc, A[i][h]);
+        S[i][h] = fma2(vi[h], ws, S[i][h]);
       }
-      q += j;
-      if (q >= r.nphi) q -= r.nphi;
     }
-    const bool mirror = j > 0 && j < nyq;
+    q += jstep;
+    if (q >= n) q -= n;
+    qu += ustep;
+    if (qu >= n) qu -= n;
+  }
 #pragma unroll
-    for (int f = 0; f < kFT; ++f)
+  for (int i = 0; i < MT; ++i) {
+    const int j = j0 + lane + 32 * i;
+    if (j >= nyq) continue;
+#pragma unroll
+    for (int h = 0; h < kFT / 2; ++h) {
+      float a0, a1, s0, s1;
+      un2(A[i][h], a0, a1);
+      un2(S[i][h], s0, s1);
+      const int f = 2 * h;
       if (c0 + f < C) {
-        float* yr = y + (long long)(c0 + f) * npix + r.start;
-        yr[j] = A[f] - S[f];
-        if (mirror) yr[r.nphi - j] = A[f] + S[f];
+        float* yr = yr0 + (long long)f * npix;
+        yr[j] = a0 - s0;
+        if (j > 0) yr[n - j] = a0 + s0;
       }
+      if (c0 + f + 1 < C) {
+        float* yr = yr0 + (long long)(f + 1) * npix;
+        yr[j] = a1 - s1;
+        if (j > 0) yr[n - j] = a1 + s1;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(32) hpx_ring_dft_inv_kernel(const float2* __restrict__ tmp, int C, int nside, int K, int M,
+                                                             float* __restrict__ y) {
+  extern __shared__ float4 hpx_smem[];
+  float4* sg = hpx_smem;                                                        // [2 nside + 1][4] = 8 real parts, 8 imaginary parts
+  float2* tw = reinterpret_cast<float2*>(hpx_smem + (2 * nside + 1) * (kFT / 2));  // [4 nside]
+  const int t = blockIdx.x, c0 = blockIdx.y * kFT, lane = threadIdx.x;
+  const Ring r = ring_of(t, nside);
+  const long long npix = 12LL * nside * nside;
+  const int n = r.nphi, nyq = n / 2;
+  const int nm = min(nyq + 1, M);
+  for (int i = lane; i < n; i += 32) {
+    float sn, cs;
+    sincospif(2.f * (float)i / (float)n, &sn, &cs);
+    tw[i] = make_float2(cs, sn);
+  }
+  float* sgf = reinterpret_cast<float*>(sg);
+  for (int m = lane; m < nm; m += 32) {
+    double ps, pc;
+    sincos((double)m * r.phi0, &ps, &pc);
+    const float fc = (float)pc, fs = (float)ps;
+    const bool edge = (m == 0 || m == nyq);
+    // Hermitian weights of the c2r transform; the imaginary parts of m = 0 and of the Nyquist mode are ignored
+    const float wgt = edge ? 1.f : 2.f;
+    for (int f = 0; f < kFT; ++f) {
+      float2 v = make_float2(0.f, 0.f);
+      if (c0 + f < C) {
+        const float2 gc = tmp[((long long)(c0 + f) * K + t) * M + m];
+        v.x = (gc.x * fc - gc.y * fs) * wgt;
+        v.y = edge ? 0.f : (gc.x * fs + gc.y * fc) * wgt;
+      }
+      sgf[m * 2 * kFT + f] = v.x;
+      sgf[m * 2 * kFT + kFT + f] = v.y;
+    }
+  }
+  __syncwarp();
+  float* yr0 = y + (long long)c0 * npix + r.start;
+  for (int j0 = 0; j0 < nyq;) {  // warp-uniform dispatch: as many pixel pairs per lane as the ring has left
+    const int left = nyq - j0;
+    if (left > 64) {
+      hpx_inv_pixels<4>(sg, tw, n, nm, j0, lane, C, c0, yr0, npix);
+      j0 += 128;
+    } else if (left > 32) {
+      hpx_inv_pixels<2>(sg, tw, n, nm, j0, lane, C, c0, yr0, npix);
+      j0 += 64;
+    } else {
+      hpx_inv_pixels<1>(sg, tw, n, nm, j0, lane, C, c0, yr0, npix);
+      j0 += 32;
+    }
+  }
+  {  // Nyquist pixel j = n/2: y = sum_m vr[m] (-1)^m
+    float acc[kFT];
+#pragma unroll
+    for (int f = 0; f < kFT; ++f) acc[f] = 0.f;
+    for (int m = lane; m < nm; m += 32) {
+      const float sgn = (m & 1) ? -1.f : 1.f;
+#pragma unroll
+      for (int f = 0; f < kFT; ++f) acc[f] = fmaf(sgf[m * 2 * kFT + f], sgn, acc[f]);
+    }
+#pragma unroll
+    for (int f = 0; f < kFT; ++f) {
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) acc[f] += __shfl_xor_sync(0xffffffffu, acc[f], d);
+      if (lane == 0 && c0 + f < C) yr0[(long long)f * npix + nyq] = acc[f];
+    }
   }
 }
 
@@ -263,7 +409,7 @@ extern "C" int ace_hpx_forward(ace_sht_plan* plan, int nside, const float* x_dev
   {
     ProfileScope prof("hpx.ring_dft_fwd", s);
     dim3 grid(p.K, (C + kFT - 1) / kFT);
-    hpx_ring_dft_fwd_kernel<<<grid, 128, 0, s>>>(x_dev, C, nside, p.K, p.M, p.ws_hpx.as<float2>());
+    hpx_ring_dft_fwd_kernel<<<grid, 32, hpx_fwd_smem(nside), s>>>(x_dev, C, nside, p.K, p.M, p.ws_hpx.as<float2>());
     after_launch("hpx_ring_dft_fwd");
   }
   {
@@ -300,8 +446,7 @@ extern "C" int ace_hpx_inverse(ace_sht_plan* plan, int nside, const float* coeff
   {
     ProfileScope prof("hpx.ring_dft_inv", s);
     dim3 grid(p.K, (C + kFT - 1) / kFT);
-    hpx_ring_dft_inv_kernel<<<grid, 160, 0, s>>>  // nphi/2 + 1 <= 129 pixel pairs per equatorial ring at nside 64
-       (p.ws_hpx.as<float2>(), C, nside, p.K, p.M, x_dev);
+    hpx_ring_dft_inv_kernel<<<grid, 32, hpx_inv_smem(nside), s>>>(p.ws_hpx.as<float2>(), C, nside, p.K, p.M, x_dev);
     after_launch("hpx_ring_dft_inv");
   }
   ACE_API_END

@@ -409,6 +409,8 @@ def test_context_wider_than_64_channels(img, embed, noise, pos, tensor_core):
         rep = ace_b200._lib.profile_report()
     finally:
         ace_b200.set_option("profile", 0)
+    if ace_b200.get_option("force_simt"):  # ACE_B200_FORCE_SIMT=1 (sanitizer runs): every norm on the streaming kernels
+        tensor_core = False
     assert ("cln_stats" in rep) == tensor_core, sorted(rep)
     assert field_rel_err(out, ref) < 1e-4, field_rel_err(out, ref)
     # the streaming wide kernel alone reproduces the tensor-core result
