@@ -2,7 +2,7 @@
 // Legendre contraction as the lat-lon transform (tcgen05 GEMMs of sht.cu) over the 4*nside - 1 iso-latitude rings.
 //
 // Replaces /root/reference/fme/core/cuhpx/sht.py:32-153 (SHT / iSHT) with tools.py:34-83 (healpix_rfft_torch /
-// healpix_irfft_torch: a Python loop of 4*nside - 1 torch.fft calls) by ONE kernel per direction for the ring stage.
+// healpix_irfft_torch: a Python loop of 4*nside - 1 torch.fft calls) by a ring-DFT kernel + a tile transposition per direction.
 // Pixels are in RING order; the Legendre tables (no Condon-Shortley sign, ring quadrature weights folded in) come from
 // the host exactly like the lat-lon plan's (ace_sht_plan_create with nlat = 4*nside - 1).
 #include "kernels.cuh"

@@ -9,7 +9,7 @@ Mirrors the object contract of the reference's vendored cuHPX Python transform
 * ``HealpixISHT(nside, lmax, mmax)``: the inverse.
 
 The per-ring FFT loop of the reference (4*nside - 1 ``torch.fft`` calls + phase shifts,
-``fme/core/cuhpx/tools.py:34-83``) is one CUDA kernel per direction; the Legendre contraction reuses the tcgen05 GEMMs
+``fme/core/cuhpx/tools.py:34-83``) is a ring-DFT kernel plus a tile transposition per direction; the Legendre contraction reuses the tcgen05 GEMMs
 of the lat-lon transform.  Unlike the reference's loop -- which takes the ring count from ``ftm.shape[0]`` and is
 therefore only correct for unbatched 1-D input -- any leading batch dims are transformed field by field.
 
