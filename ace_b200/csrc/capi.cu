@@ -5,6 +5,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: the injection library is looked up at run time, nothing to link
+
 #include "gemm.cuh"
 #include "kernels.cuh"
 
@@ -23,6 +25,7 @@ Options& options() {
     // every GEMM on the SIMT kernel: for compute-sanitizer racecheck / synccheck runs (tools/sanitize.sh), which do not model
     // the asynchronous tcgen05 / TMA proxies
     if (const char* e = getenv("ACE_B200_FORCE_SIMT")) x.force_simt = atoi(e) ? 1 : 0;
+    if (const char* e = getenv("ACE_B200_NVTX")) x.nvtx = atoi(e) ? 1 : 0;
     return x;
   }();
   return o;
@@ -37,6 +40,10 @@ std::vector<ProfRec> g_prof;
 }  // namespace
 
 ProfileScope::ProfileScope(const char* n, cudaStream_t s) : name(n), stream(s) {
+  if (options().nvtx) {  // the reference names its timed regions (Timer.child, fme/core/benchmark/timer.py); here: one range per operator
+    nvtxRangePushA(n);
+    ranged = true;
+  }
   if (!options().profile) return;
   if (cudaEventCreate(&start) != cudaSuccess || cudaEventCreate(&stop) != cudaSuccess) {
     start = stop = nullptr;
@@ -45,6 +52,7 @@ ProfileScope::ProfileScope(const char* n, cudaStream_t s) : name(n), stream(s) {
   cudaEventRecord(start, stream);
 }
 ProfileScope::~ProfileScope() {
+  if (ranged) nvtxRangePop();
   if (!start) return;
   cudaEventRecord(stop, stream);
   g_prof.push_back({name, start, stop});
@@ -75,6 +83,7 @@ extern "C" int ace_set_option(const char* key, int value) {
   ACE_REQUIRE(key != nullptr, "ace_set_option: null key");
   if (!strcmp(key, "force_simt")) options().force_simt = value;
   else if (!strcmp(key, "profile")) options().profile = value;
+  else if (!strcmp(key, "nvtx")) options().nvtx = value ? 1 : 0;
   else if (!strcmp(key, "split_terms")) {
     ACE_REQUIRE(value == 1 || value == 3, "split_terms must be 1 or 3");
     options().split_terms = value;
@@ -127,6 +136,7 @@ extern "C" int ace_get_option(const char* key) {
   if (!key) return -1;
   if (!strcmp(key, "force_simt")) return options().force_simt;
   if (!strcmp(key, "profile")) return options().profile;
+  if (!strcmp(key, "nvtx")) return options().nvtx;
   if (!strcmp(key, "split_terms")) return options().split_terms;
   if (!strcmp(key, "count_umma")) return (int)g_umma_count.load();
   if (!strcmp(key, "count_simt")) return (int)g_simt_count.load();

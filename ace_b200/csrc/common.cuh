@@ -78,6 +78,7 @@ struct ProfileScope {
   const char* name;
   cudaStream_t stream;
   cudaEvent_t start = nullptr, stop = nullptr;
+  bool ranged = false;  // an NVTX range is open (option "nvtx")
   ProfileScope(const char* name, cudaStream_t stream);
   ~ProfileScope();
 };
@@ -85,6 +86,7 @@ struct ProfileScope {
 // runtime options
 struct Options {
   int profile = 0;
+  int nvtx = 0;      // NVTX range per operator launch, named like the profile report (nsys / `ncu --nvtx --nvtx-include "dhconv/"`); env ACE_B200_NVTX
   int force_simt = 0;
   int split_terms = 3;
   int pair = -1;     // CTA-pair (cta_group::2, 256 x 256 tiles) variants: -1 = per-op choice (convolutions with M % 256 == 0), 0 = never, 1 = wherever compiled

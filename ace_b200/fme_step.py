@@ -206,6 +206,12 @@ def install_step_into_fme(override: bool = False, name: str = STEP_TYPE_NAME):
     from fme.core.step.single_module import SingleModuleStepConfig  # noqa: PLC0415
     from fme.core.step.step import StepABC, StepSelector  # noqa: PLC0415
 
+    from .registry import disabled_by_env  # noqa: PLC0415
+
+    if disabled_by_env():  # ACE_B200_DISABLE=1: A/B kill switch -- `name` becomes an alias of the reference's single-module step
+        StepSelector.register(name)(SingleModuleStepConfig)
+        return SingleModuleStepConfig
+
     try:
         from fme.core.corrector.state import CorrectorState  # noqa: PLC0415
         from fme.core.stepper_state import StepperState  # noqa: PLC0415

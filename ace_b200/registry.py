@@ -20,6 +20,7 @@ semantics: strict ``from_state`` (unknown keys raise, like dacite strict mode), 
 normalised to include defaults, labels rejected for unconditional builders.
 """
 import dataclasses
+import os
 from typing import Any, Callable, ClassVar, Literal, Mapping
 
 import torch
@@ -165,10 +166,31 @@ class B200SphericalFourierNeuralOperatorBuilder(ModuleConfig):
         )
 
 
+def disabled_by_env() -> bool:
+    """``ACE_B200_DISABLE=1``: the A/B kill switch.  The install functions then leave the reference's builders / transforms / step in
+    place and register the ``B200...`` type names as ALIASES of the reference classes, so the same config file runs on the reference
+    path (for a parity or timing comparison) without editing it."""
+    return os.environ.get("ACE_B200_DISABLE", "0") not in ("", "0")
+
+
+def _fme_registered(selector, name):
+    """The class the fme selector has registered under ``name`` (``Registry._types``, fme/core/registry/registry.py)."""
+    reg = getattr(selector, "registry", None)
+    types = getattr(reg, "_types", None)
+    if types is None or name not in types:
+        raise RuntimeError(f"ACE_B200_DISABLE: the reference type '{name}' is not registered; import its module before installing")
+    return types[name]
+
+
 def install_into_fme(override: bool = False):
     """Register the B200 builder with the real fme registry (needs ``fme`` importable)."""
     from fme.ace.registry.registry import ModuleConfig as FmeModuleConfig  # noqa: PLC0415
     from fme.ace.registry.registry import ModuleSelector as FmeModuleSelector  # noqa: PLC0415
+
+    if disabled_by_env():
+        for alias, ref in ((B200_TYPE_NAME, REFERENCE_TYPE_NAME), (B200_NOISE_TYPE_NAME, REFERENCE_NOISE_TYPE_NAME)):
+            FmeModuleSelector.register(alias)(_fme_registered(FmeModuleSelector, ref))
+        return None
 
     fields = [(f.name, f.type, f) for f in dataclasses.fields(B200SphericalFourierNeuralOperatorBuilder)]
     cls = dataclasses.make_dataclass(

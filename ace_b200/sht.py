@@ -119,5 +119,9 @@ def patch_torch_harmonics():
     """Install these classes the way fme does (fme/sht_fix.py:228-229) if torch_harmonics is importable."""
     import torch_harmonics  # noqa: PLC0415
 
+    from .registry import disabled_by_env  # noqa: PLC0415
+
+    if disabled_by_env():  # ACE_B200_DISABLE=1: A/B kill switch, the reference transforms stay in place
+        return
     torch_harmonics.RealSHT = RealSHT
     torch_harmonics.InverseRealSHT = InverseRealSHT

@@ -80,6 +80,43 @@ def test_patch_torch_harmonics():
             sht(torch.zeros(1, 9, 18))  # CPU tensor: no fallback
 
 
+def test_kill_switch_leaves_the_reference_in_place(monkeypatch):
+    """ACE_B200_DISABLE=1 (A/B against the reference with an unchanged config): the install functions register the ``B200...`` names as
+    aliases of whatever the reference registered and override nothing."""
+    monkeypatch.setenv("ACE_B200_DISABLE", "1")
+    with fake_fme.installed() as mods:
+        FmeSelector = mods["fme.ace.registry.registry"].ModuleSelector
+        FmeConfig = mods["fme.ace.registry.registry"].ModuleConfig
+
+        @dataclasses.dataclass
+        class RefNet(FmeConfig):
+            embed_dim: int = 4
+
+            def build(self, n_in_channels, n_out_channels, dataset_info):
+                return torch.nn.Conv2d(n_in_channels, n_out_channels, 1)
+
+        @dataclasses.dataclass
+        class RefNoise(RefNet):
+            pass
+
+        FmeSelector.register("SphericalFourierNeuralOperatorNet")(RefNet)
+        FmeSelector.register("NoiseConditionedSFNO")(RefNoise)
+        assert ace_b200.install_into_fme(override=True) is None
+        reg = FmeSelector.registry._types
+        assert reg["SphericalFourierNeuralOperatorNet"] is RefNet and reg["B200SphericalFourierNeuralOperatorNet"] is RefNet
+        assert reg["NoiseConditionedSFNO"] is RefNoise and reg["B200NoiseConditionedSFNO"] is RefNoise
+        th = mods["torch_harmonics"]
+        before = (th.RealSHT, th.InverseRealSHT)
+        ace_b200.patch_torch_harmonics()
+        assert (th.RealSHT, th.InverseRealSHT) == before
+        ref_step = mods["fme.core.step.single_module"].SingleModuleStepConfig
+        StepSelector = mods["fme.core.step.step"].StepSelector
+        names_before = {n: c for n, c in StepSelector.registry._types.items()}
+        assert ace_b200.install_step_into_fme(override=True) is ref_step
+        after = StepSelector.registry._types
+        assert after["b200_single_module"] is ref_step and all(after[n] is c for n, c in names_before.items())
+
+
 def _oracle_like(net):
     from oracle import sfno as osfno
 
