@@ -50,7 +50,7 @@ __host__ __device__ inline Ring ring_of(int t, int nside) {
 //   hpx_tmp_to_x1_kernel      tmp -> X1 planes [(2m + reim)][C][Kp] (ring index contiguous, the Legendre GEMM's A operand):
 //       32 x 32 tiles transposed through shared memory, so the 2-byte plane stores come in 64-byte runs instead of one sector per
 //       element (a block of the ring kernel owns ONE ring, i.e. one column of X1).
-// grid (rings, ceil(C / kFT)), 32 threads, dynamic shared memory hpx_fwd_smem(nside).
+// grid (ceil(C / kFT), rings), 32 threads, dynamic shared memory hpx_fwd_smem(nside).
 constexpr int kMT = 4;  // orders (forward) / pixel pairs (inverse) per lane at most
 __host__ __device__ inline size_t hpx_fwd_smem(int nside) { return (size_t)4 * nside * (kFT * sizeof(float) + sizeof(float2)); }
 __host__ __device__ inline size_t hpx_inv_smem(int nside) { return (size_t)(2 * nside + 1) * kFT * sizeof(float2) + (size_t)4 * nside * sizeof(float2); }
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(32) hpx_ring_dft_fwd_kernel(const float* __res
   const int cap = 4 * nside;
   float4* sx = hpx_smem;                                     // [cap][kFT / 4]
   float2* tw = reinterpret_cast<float2*>(hpx_smem + cap * (kFT / 4));  // [cap]
-  const int t = blockIdx.x, c0 = blockIdx.y * kFT, lane = threadIdx.x;
+  const int t = blockIdx.y, c0 = blockIdx.x * kFT, lane = threadIdx.x;
   const Ring r = ring_of(t, nside);
   const int n = r.nphi, half = n / 2;  // n is a multiple of 4
   const long long npix = 12LL * nside * nside;
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(256) hpx_g_to_tmp_kernel(const bf16* __restric
 // One warp per (ring, 8 fields): a lane owns up to kMT = 4 pixel pairs (j, n - j), j = j0 + lane + 32 i, and their 8 fields' cosine /
 // sine sums (64 FMAs, issued as 32 FFMA2, per order m against 64 bytes of coefficients and one per-lane twiddle read, like the
 // forward kernel); the Nyquist pixel j = n/2 (cosine (-1)^m, no sine) is a warp reduction.
-// grid (rings, ceil(C / kFT)), 32 threads, hpx_inv_smem(nside) bytes.
+// grid (ceil(C / kFT), rings), 32 threads, hpx_inv_smem(nside) bytes.
 template <int MT>
 __device__ __forceinline__ void hpx_inv_pixels(const float4* sg, const float2* tw, int n, int nm, int j0, int lane, int C, int c0, float* __restrict__ yr0,
                                                long long npix) {
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(32) hpx_ring_dft_inv_kernel(const float2* __re
   extern __shared__ float4 hpx_smem[];
   float4* sg = hpx_smem;                                                        // [2 nside + 1][4] = 8 real parts, 8 imaginary parts
   float2* tw = reinterpret_cast<float2*>(hpx_smem + (2 * nside + 1) * (kFT / 2));  // [4 nside]
-  const int t = blockIdx.x, c0 = blockIdx.y * kFT, lane = threadIdx.x;
+  const int t = blockIdx.y, c0 = blockIdx.x * kFT, lane = threadIdx.x;
   const Ring r = ring_of(t, nside);
   const long long npix = 12LL * nside * nside;
   const int n = r.nphi, nyq = n / 2;
@@ -408,7 +408,7 @@ extern "C" int ace_hpx_forward(ace_sht_plan* plan, int nside, const float* x_dev
   p.ws_hpx.ensure((size_t)C * p.K * p.M * sizeof(float2));
   {
     ProfileScope prof("hpx.ring_dft_fwd", s);
-    dim3 grid(p.K, (C + kFT - 1) / kFT);
+    dim3 grid((C + kFT - 1) / kFT, p.K);  // field groups on x (no 65 535 limit), rings on y
     hpx_ring_dft_fwd_kernel<<<grid, 32, hpx_fwd_smem(nside), s>>>(x_dev, C, nside, p.K, p.M, p.ws_hpx.as<float2>());
     after_launch("hpx_ring_dft_fwd");
   }
@@ -445,7 +445,7 @@ extern "C" int ace_hpx_inverse(ace_sht_plan* plan, int nside, const float* coeff
   }
   {
     ProfileScope prof("hpx.ring_dft_inv", s);
-    dim3 grid(p.K, (C + kFT - 1) / kFT);
+    dim3 grid((C + kFT - 1) / kFT, p.K);  // field groups on x (no 65 535 limit), rings on y
     hpx_ring_dft_inv_kernel<<<grid, 32, hpx_inv_smem(nside), s>>>(p.ws_hpx.as<float2>(), C, nside, p.K, p.M, x_dev);
     after_launch("hpx_ring_dft_inv");
   }

@@ -52,6 +52,30 @@ def test_config5_shape_vs_oracle_and_round_trip():
     assert rms < 1e-3
 
 
+@pytest.mark.parametrize("nside,lmax,mmax,fields", [
+    (1, 2, 2, 3),      # three rings of four pixels: the shortest rings (half = 2: the main loop of the ring kernels is empty)
+    (2, 4, 5, 11),     # mmax = nlon / 2 + 1 (the module default): the Nyquist order of the equatorial rings
+    (3, 6, 6, 9),      # ring lengths that are not powers of two, a ragged field group
+    (40, 81, 70, 10),  # 160-pixel equatorial rings: 2 orders per lane in one pass + 1 in the next, polar rings on the 1-order path
+])
+def test_ring_length_dispatch_vs_oracle(nside, lmax, mmax, fields):
+    """Every branch of the ring kernels' orders-per-lane dispatch and the shortest rings, against the oracle port of the
+    reference's ring loop (fme/core/cuhpx/tools.py:34-83)."""
+    import ace_b200
+    from oracle import healpix as oh
+
+    fwd = ace_b200.HealpixSHT(nside, lmax=lmax, mmax=mmax, quad_weights="none")
+    inv = ace_b200.HealpixISHT(nside, lmax=lmax, mmax=mmax)
+    torch.manual_seed(nside)
+    x = torch.randn(fields, 12 * nside**2)
+    co = oh.SHT(nside, lmax, mmax, oh.uniform_weights(nside))(x)
+    c = fwd(x.cuda())
+    assert tuple(c.shape) == (fields, lmax, mmax)
+    assert _rel(torch.view_as_real(c).cpu(), torch.view_as_real(co)) < RTOL
+    spec = torch.randn(fields, lmax, mmax, dtype=torch.complex64)
+    assert _rel(inv(spec.cuda()).cpu(), oh.iSHT(nside, lmax, mmax)(spec)) < RTOL
+
+
 def test_contract():
     import ace_b200
 
