@@ -210,6 +210,65 @@ __global__ void __launch_bounds__(256) spec_complex_to_planes_kernel(const float
   }
 }
 
+// The same converters for an even channel count (and even plane offsets): 64 channels x 32 spectral positions per block, a lane
+// owns two adjacent channels on the plane side (bf16x2: 128 bytes per warp and row instead of 64)
+__global__ void __launch_bounds__(256) spec_planes_to_complex2_kernel(const bf16* __restrict__ c1, long long plane, int C,
+                                                                     long long LM, float* __restrict__ out) {
+  __shared__ float2 tile[32][65];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long lm0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 64;
+  const int c = c0 + 2 * tx;
+  for (int i = ty; i < 32; i += 8) {
+    const long long lm = lm0 + i;
+    float2 v0 = make_float2(0.f, 0.f), v1 = v0;
+    if (lm < LM && c < C) {
+      const bf16* p = c1 + lm * 2 * C + c;
+      const __nv_bfloat162 rh = *reinterpret_cast<const __nv_bfloat162*>(p), rl = *reinterpret_cast<const __nv_bfloat162*>(p + plane);
+      const __nv_bfloat162 ih = *reinterpret_cast<const __nv_bfloat162*>(p + C), il = *reinterpret_cast<const __nv_bfloat162*>(p + C + plane);
+      v0 = make_float2(__low2float(rh) + __low2float(rl), __low2float(ih) + __low2float(il));
+      v1 = make_float2(__high2float(rh) + __high2float(rl), __high2float(ih) + __high2float(il));
+    }
+    tile[i][2 * tx] = v0;
+    tile[i][2 * tx + 1] = v1;
+  }
+  __syncthreads();
+  for (int i = ty; i < 64; i += 8) {
+    const int cc = c0 + i;
+    const long long lm = lm0 + tx;
+    if (cc < C && lm < LM) reinterpret_cast<float2*>(out)[(long long)cc * LM + lm] = tile[tx][i];
+  }
+}
+
+__global__ void __launch_bounds__(256) spec_complex_to_planes2_kernel(const float* __restrict__ in, int C, int L, int M, int Lp,
+                                                                     bf16* __restrict__ c2, long long plane) {
+  __shared__ float2 tile[64][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int m0 = blockIdx.x * 32, c0 = blockIdx.y * 64, l = blockIdx.z;
+  for (int i = ty; i < 64; i += 8) {
+    const int c = c0 + i, m = m0 + tx;
+    float2 v = make_float2(0.f, 0.f);
+    if (c < C && m < M) v = reinterpret_cast<const float2*>(in)[((long long)c * L + l) * M + m];
+    tile[i][tx] = v;
+  }
+  __syncthreads();
+  const int c = c0 + 2 * tx;
+  if (c >= C) return;
+  for (int i = ty; i < 32; i += 8) {
+    const int m = m0 + i;
+    if (m >= M) break;
+    const float2 v0 = tile[2 * tx][i], v1 = tile[2 * tx + 1][i];
+    bf16* y = c2 + ((long long)m * Lp + l) * 2 * C + c;
+    const __nv_bfloat162 rh = __floats2bfloat162_rn(v0.x, v1.x), ih = __floats2bfloat162_rn(v0.y, v1.y);
+    const __nv_bfloat162 rl = __floats2bfloat162_rn(v0.x - __low2float(rh), v1.x - __high2float(rh));
+    const __nv_bfloat162 il = __floats2bfloat162_rn(v0.y - __low2float(ih), v1.y - __high2float(ih));
+    *reinterpret_cast<__nv_bfloat162*>(y) = rh;
+    *reinterpret_cast<__nv_bfloat162*>(y + plane) = rl;
+    *reinterpret_cast<__nv_bfloat162*>(y + C) = ih;
+    *reinterpret_cast<__nv_bfloat162*>(y + C + plane) = il;
+  }
+}
+
 // Deferred InstanceNorm.  From the (sum, sum of squares) statistics of h[B][C][HW], per sample b:
 //   a[c] = gamma[c] / sqrt(var_c + eps),   s[c] = beta[c] - mean_c * a[c]        (a*h + s is the normalised tensor)
 // and fold them into the 1x1 convolution that consumes it:  W (a*h + s) + bias = (W diag(a)) h + (bias + W s):
@@ -430,14 +489,20 @@ void launch_diagonal_contract(const bf16* c1, long long c1_plane, const float* w
 void launch_spec_planes_to_complex(const bf16* c1, long long plane, int C, int L, int M, float* out, cudaStream_t stream) {
   ProfileScope prof("spec_planes_to_complex", stream);
   const long long LM = (long long)L * M;
-  spec_planes_to_complex_kernel<<<dim3((unsigned)((LM + 31) / 32), (unsigned)((C + 31) / 32)), 256, 0, stream>>>(c1, plane, C, LM, out);
+  if (C % 2 == 0 && plane % 2 == 0 && ((uintptr_t)c1 & 3) == 0)
+    spec_planes_to_complex2_kernel<<<dim3((unsigned)((LM + 31) / 32), (unsigned)((C + 63) / 64)), 256, 0, stream>>>(c1, plane, C, LM, out);
+  else
+    spec_planes_to_complex_kernel<<<dim3((unsigned)((LM + 31) / 32), (unsigned)((C + 31) / 32)), 256, 0, stream>>>(c1, plane, C, LM, out);
   after_launch("spec_planes_to_complex");
 }
 
 void launch_spec_complex_to_planes(const float* in, int C, int L, int M, int Lp, bf16* c2, long long plane, cudaStream_t stream) {
   ProfileScope prof("spec_complex_to_planes", stream);
   ACE_REQUIRE(L <= 65535 && (C + 31) / 32 <= 65535, "spec_complex_to_planes: extent too large");
-  spec_complex_to_planes_kernel<<<dim3((unsigned)((M + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)L), 256, 0, stream>>>(in, C, L, M, Lp, c2, plane);
+  if (C % 2 == 0 && plane % 2 == 0 && ((uintptr_t)c2 & 3) == 0)
+    spec_complex_to_planes2_kernel<<<dim3((unsigned)((M + 31) / 32), (unsigned)((C + 63) / 64), (unsigned)L), 256, 0, stream>>>(in, C, L, M, Lp, c2, plane);
+  else
+    spec_complex_to_planes_kernel<<<dim3((unsigned)((M + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)L), 256, 0, stream>>>(in, C, L, M, Lp, c2, plane);
   after_launch("spec_complex_to_planes");
 }
 

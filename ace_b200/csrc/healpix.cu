@@ -196,26 +196,30 @@ __global__ void __launch_bounds__(32) hpx_ring_dft_fwd_kernel(const float* __res
       if (c0 + f < C) tmp[((long long)(c0 + f) * K + t) * M + m] = make_float2(0.f, 0.f);
 }
 
-// tmp [C][K][2M] fp32 (2M = interleaved re / im of the orders) -> X1 planes [(2m + reim)][C][Kp]; grid (C, ceil(2M/32), ceil(K/32))
+// tmp [C][K][2M] fp32 (2M = interleaved re / im of the orders) -> X1 planes [(2m + reim)][C][Kp]; 64 (rings) x 32 (rows) tiles, two
+// rings per lane on the store side (bf16x2: 128 bytes per warp and plane row; Kp is even, the pad column K of an odd ring count
+// receives zero).  grid (C, ceil(2M/32), ceil(K/64))
 __global__ void __launch_bounds__(256) hpx_tmp_to_x1_kernel(const float* __restrict__ tmp, int C, int K, int M2, int Kp,
                                                            bf16* __restrict__ x1, long long plane) {
-  __shared__ float tile[32][33];
-  const int t0 = blockIdx.z * 32, r0 = blockIdx.y * 32, f = blockIdx.x;
+  __shared__ float tile[64][33];
+  const int t0 = blockIdx.z * 64, r0 = blockIdx.y * 32, f = blockIdx.x;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int i = ty; i < 32; i += 8) {
+  for (int i = ty; i < 64; i += 8) {
     const int t = t0 + i, mr = r0 + tx;
     tile[i][tx] = (t < K && mr < M2) ? tmp[((long long)f * K + t) * M2 + mr] : 0.f;
   }
   __syncthreads();
+  const int t = t0 + 2 * tx;
+  if (t >= Kp) return;
   for (int i = ty; i < 32; i += 8) {
-    const int mr = r0 + i, t = t0 + tx;
-    if (mr < M2 && t < K) {
-      bf16 h, l;
-      split_bf16(tile[tx][i], h, l);
-      bf16* d = x1 + ((long long)mr * C + f) * Kp + t;
-      d[0] = h;
-      d[plane] = l;
-    }
+    const int mr = r0 + i;
+    if (mr >= M2) break;
+    const float v0 = tile[2 * tx][i], v1 = tile[2 * tx + 1][i];
+    const __nv_bfloat162 hi = __floats2bfloat162_rn(v0, v1);
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(v0 - __low2float(hi), v1 - __high2float(hi));
+    bf16* d = x1 + ((long long)mr * C + f) * Kp + t;
+    *reinterpret_cast<__nv_bfloat162*>(d) = hi;
+    *reinterpret_cast<__nv_bfloat162*>(d + plane) = lo;
   }
 }
 
@@ -228,21 +232,24 @@ __global__ void __launch_bounds__(256) hpx_tmp_to_x1_kernel(const float* __restr
 //       coefficients sit in shared memory as [m][8 fields], a thread owns one pixel and the 8 fields' sums.
 __global__ void __launch_bounds__(256) hpx_g_to_tmp_kernel(const bf16* __restrict__ g, long long plane, int C, int K, int M2, int Kg, int Ke,
                                                           float* __restrict__ tmp) {
-  __shared__ float tile[32][33];
-  const int t0 = blockIdx.z * 32, r0 = blockIdx.y * 32, f = blockIdx.x;
+  __shared__ float tile[32][65];
+  const int t0 = blockIdx.z * 64, r0 = blockIdx.y * 32, f = blockIdx.x;  // 64 rings x 32 rows per block; Kg is a multiple of 64
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   for (int i = ty; i < 32; i += 8) {
-    const int mr = r0 + i, t = t0 + tx;
-    float v = 0.f;
-    if (mr < M2 && t < K) {
+    const int mr = r0 + i;
+    float v0 = 0.f, v1 = 0.f;
+    if (mr < M2) {
       const int row = (((mr >> 1) & 1) ? Ke : 0) + 2 * (mr >> 2) + (mr & 1);  // order m = mr / 2, reim = mr & 1
-      const bf16* s = g + ((long long)row * C + f) * Kg + t;
-      v = __bfloat162float(s[0]) + __bfloat162float(s[plane]);
+      const bf16* s = g + ((long long)row * C + f) * Kg + t0 + 2 * tx;        // two rings per lane (bf16x2)
+      const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(s), l = *reinterpret_cast<const __nv_bfloat162*>(s + plane);
+      v0 = __low2float(h) + __low2float(l);
+      v1 = __high2float(h) + __high2float(l);
     }
-    tile[i][tx] = v;
+    tile[i][2 * tx] = v0;
+    tile[i][2 * tx + 1] = v1;
   }
   __syncthreads();
-  for (int i = ty; i < 32; i += 8) {
+  for (int i = ty; i < 64; i += 8) {
     const int t = t0 + i, mr = r0 + tx;
     if (t < K && mr < M2) tmp[((long long)f * K + t) * M2 + mr] = tile[tx][i];
   }
@@ -414,7 +421,7 @@ extern "C" int ace_hpx_forward(ace_sht_plan* plan, int nside, const float* x_dev
   }
   {
     ProfileScope prof("hpx.tmp_to_x1", s);
-    dim3 grid(C, (2 * p.M + 31) / 32, (p.K + 31) / 32);
+    dim3 grid(C, (2 * p.M + 31) / 32, (p.K + 63) / 64);
     hpx_tmp_to_x1_kernel<<<grid, 256, 0, s>>>(p.ws_hpx.as<float>(), C, p.K, 2 * p.M, p.Kp, p.ws_x1.as<bf16>(), x1p);
     after_launch("hpx_tmp_to_x1");
   }
@@ -439,7 +446,7 @@ extern "C" int ace_hpx_inverse(ace_sht_plan* plan, int nside, const float* coeff
   p.ws_hpx.ensure((size_t)C * p.K * p.M * sizeof(float2));
   {
     ProfileScope prof("hpx.g_to_tmp", s);
-    dim3 grid(C, (2 * p.M + 31) / 32, (p.K + 31) / 32);
+    dim3 grid(C, (2 * p.M + 31) / 32, (p.K + 63) / 64);
     hpx_g_to_tmp_kernel<<<grid, 256, 0, s>>>(p.ws_g2.as<bf16>(), gp, C, p.K, 2 * p.M, p.Kg, p.Ke, p.ws_hpx.as<float>());
     after_launch("hpx_g_to_tmp");
   }
