@@ -26,6 +26,7 @@ from .fme_step import install_step_into_fme  # noqa: F401
 from .corrector import AtmosphereCorrector  # noqa: F401
 from . import parallel  # noqa: F401
 from . import metrics  # noqa: F401
+from . import timing  # noqa: F401
 from .healpix import HealpixISHT, HealpixSHT  # noqa: F401
 
 __version__ = "0.1.0"

@@ -101,6 +101,8 @@ SIGNATURES = {
     "ace_get_option": (_I, [_CP]),
     "ace_launch_count": (_LL, []),
     "ace_profile_report": (_I, [ctypes.c_char_p, _I]),
+    "ace_set_scope_callback": (_I, [_VP, _VP]),
+    "ace_debug_scope": (_I, [_CP]),
     "ace_sht_plan_create": (_I, [_I, _I, _I, _I, _VP, _VP, ctypes.POINTER(_VP)]),
     "ace_sht_plan_destroy": (None, [_VP]),
     "ace_sht_forward": (_I, [_VP, _VP, _VP, _LL, _VP]),

@@ -39,7 +39,16 @@ struct ProfRec {
 std::vector<ProfRec> g_prof;
 }  // namespace
 
+namespace {
+ace_scope_callback g_scope_cb = nullptr;
+void* g_scope_user = nullptr;
+}  // namespace
+
 ProfileScope::ProfileScope(const char* n, cudaStream_t s) : name(n), stream(s) {
+  if (g_scope_cb) {
+    g_scope_cb(n, 1, g_scope_user);
+    hooked = true;
+  }
   if (options().nvtx) {  // the reference names its timed regions (Timer.child, fme/core/benchmark/timer.py); here: one range per operator
     nvtxRangePushA(n);
     ranged = true;
@@ -53,9 +62,11 @@ ProfileScope::ProfileScope(const char* n, cudaStream_t s) : name(n), stream(s) {
 }
 ProfileScope::~ProfileScope() {
   if (ranged) nvtxRangePop();
-  if (!start) return;
-  cudaEventRecord(stop, stream);
-  g_prof.push_back({name, start, stop});
+  if (start) {
+    cudaEventRecord(stop, stream);
+    g_prof.push_back({name, start, stop});
+  }
+  if (hooked && g_scope_cb) g_scope_cb(name, 0, g_scope_user);
 }
 
 void run_gemm(const GemmOp& op, cudaStream_t stream) {
@@ -159,6 +170,21 @@ extern "C" int ace_get_option(const char* key) {
   if (!strcmp(key, "conv_bn")) return options().conv_bn;
   if (!strcmp(key, "dbg")) return options().dbg;
   return -1;
+}
+
+extern "C" int ace_set_scope_callback(ace_scope_callback cb, void* user) {
+  g_scope_cb = cb;
+  g_scope_user = user;
+  return ACE_OK;
+}
+
+extern "C" int ace_debug_scope(const char* name) {
+  ACE_API_BEGIN
+  ACE_REQUIRE(name != nullptr, "ace_debug_scope: null name");
+  static std::string held;  // the scope keeps the pointer until it closes
+  held = name;
+  { ProfileScope scope(held.c_str(), nullptr); }
+  ACE_API_END
 }
 
 extern "C" long long ace_launch_count(void) { return g_launch_count.load(); }

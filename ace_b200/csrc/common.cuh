@@ -79,6 +79,7 @@ struct ProfileScope {
   cudaStream_t stream;
   cudaEvent_t start = nullptr, stop = nullptr;
   bool ranged = false;  // an NVTX range is open (option "nvtx")
+  bool hooked = false;  // the host's scope callback was told about the begin (ace_set_scope_callback)
   ProfileScope(const char* name, cudaStream_t stream);
   ~ProfileScope();
 };

@@ -58,6 +58,7 @@ const char* ace_last_error(void);
  *                 instead of the tcgen05 kernel (both are CUDA; there is no CPU path)
  *   "split_terms" 3 (default) or 1 = plain bf16 products (fast, ~1e-2 accurate)
  *   "profile"     1 = time every launch with CUDA events (see ace_profile_report)
+ *   "nvtx"        1 = one NVTX range per operator launch (default 0; env ACE_B200_NVTX)
  *   "umma_bn"     0 (default: per-op choice) or 128 / 192 / 256: N tile of the tcgen05 kernel (SHT stages)
  *   "umma_bk"     0 (default: per-op hint) or 32 / 64: K extent per pipeline stage of the forward SHT stages
  *   "conv_bn"     0 (default: per-op choice by wave quantisation) or 192 / 256: N tile of the 1x1-conv GEMMs
@@ -74,6 +75,15 @@ long long ace_launch_count(void);
  * synchronises, writes one "name count total_ms" line per kernel name into buf, clears the
  * records and returns the number of bytes written. */
 int ace_profile_report(char* buf, int buflen);
+/* Scope hook: `cb(name, 1, user)` is called on the host before an operator's kernels are enqueued and `cb(name, 0, user)` after
+ * (same names as ace_profile_report); NULL removes it.  A host records its own CUDA events / ranges there: ace_b200.timing
+ * drives the reference's hierarchical Timer protocol with it (fme/core/benchmark/timer.py:48-51; the conditional SFNO block
+ * threads `timer.child("filter")`, ... through its forward, fme/core/models/conditional_sfno/sfnonet.py:388-437).
+ * With option "nvtx" = 1 (env ACE_B200_NVTX) every scope is also an NVTX range. */
+typedef void (*ace_scope_callback)(const char* name, int begin, void* user);
+int ace_set_scope_callback(ace_scope_callback cb, void* user);
+/* Opens and closes the scope `name` without launching anything (tests of the hook / NVTX plumbing; no GPU needed). */
+int ace_debug_scope(const char* name);
 
 /* ---- spherical harmonic transforms ---------------------------------------------------
  * legendre_fwd_host / legendre_inv_host: float64 [mmax][lmax][nlat], the tables of

@@ -421,3 +421,57 @@ def test_context_wider_than_64_channels(img, embed, noise, pos, tensor_core):
         finally:
             ace_b200.set_option("force_simt", 0)
         assert field_rel_err(out_simt, ref) < 1e-4, field_rel_err(out_simt, ref)
+
+
+def test_reference_timer_protocol_over_a_block():
+    """The reference's block benchmark threads a hierarchical CUDA-event Timer through the block's forward
+    (fme/core/benchmark/timer.py:103-164, conditional_sfno/sfnonet.py:388-437); ``ace_b200.timing.timer_scopes`` produces the same
+    children from the library's operator scopes while the network runs as one library call."""
+    import collections
+
+    from ace_b200 import csfno as bc
+    from ace_b200 import timing
+
+    class CudaTimer:  # the reference CUDATimer's behaviour: an event pair on the current stream per entry
+        def __init__(self):
+            self.children, self.pairs, self.entered = collections.defaultdict(CudaTimer), [], False
+
+        def child(self, name):
+            assert self.entered
+            return self.children[name]
+
+        def __enter__(self):
+            assert not self.entered
+            self.entered = True
+            self.pairs.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
+            self.pairs[-1][0].record(torch.cuda.current_stream())
+            return self
+
+        def __exit__(self, *exc):
+            self.pairs[-1][1].record(torch.cuda.current_stream())
+            self.entered = False
+            return False
+
+        def ms(self):
+            torch.cuda.synchronize()
+            return sum(a.elapsed_time(b) for a, b in self.pairs)
+
+    img, B = (90, 180), 2
+    torch.manual_seed(5)
+    net = bc.get_lat_lon_sfnonet(bc.SFNONetConfig(embed_dim=256, num_layers=2), in_chans=4, out_chans=4, img_shape=img, data_grid="legendre-gauss",
+                                 context_config=bc.ContextConfig(embed_dim_noise=8, embed_dim_labels=3)).cuda().eval().requires_grad_(False)
+    x = torch.randn(B, 4, *img, device="cuda")
+    ctx = bc.Context(noise=torch.randn(B, 8, *img, device="cuda"), labels=torch.randn(B, 3, device="cuda"))
+    y0 = net(x, ctx)
+    timer = CudaTimer()
+    with timer, timing.timer_scopes(timer):
+        y1 = net(x, ctx)
+    assert torch.equal(y0, y1)
+    assert {"norm0", "filter", "inner_skip", "norm1", "mlp"} <= set(timer.children)
+    assert set(timer.children["filter"].children) == {"forward_transform", "dhconv", "inverse_transform"}
+    assert all(len(timer.children[k].pairs) == 2 for k in ("norm0", "filter", "inner_skip", "norm1", "mlp"))  # two blocks
+    total = timer.ms()
+    parts = {k: c.ms() for k, c in timer.children.items()}
+    assert all(v > 0 for v in parts.values()) and sum(parts.values()) <= total * 1.001, (total, parts)
+    f = timer.children["filter"]
+    assert sum(c.ms() for c in f.children.values()) <= f.ms() * 1.001
