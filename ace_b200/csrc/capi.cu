@@ -26,6 +26,7 @@ Options& options() {
     // the asynchronous tcgen05 / TMA proxies
     if (const char* e = getenv("ACE_B200_FORCE_SIMT")) x.force_simt = atoi(e) ? 1 : 0;
     if (const char* e = getenv("ACE_B200_NVTX")) x.nvtx = atoi(e) ? 1 : 0;
+    if (const char* e = getenv("ACE_B200_CLN_GEMM")) x.cln_gemm = atoi(e) ? 1 : 0;
     return x;
   }();
   return o;

@@ -369,6 +369,54 @@ __global__ void __launch_bounds__(kWarps * 32) cln_stats_kernel(const bf16* __re
   *reinterpret_cast<float4*>(musr + (long long)b * HW + p) = make_float4((float)m0, r0, (float)m1, r1);
 }
 
+// The same statistics with four pixels per lane (8-byte loads: a warp covers 128 pixels of a channel row per request instead of 64,
+// twice the bytes in flight per thread) -- needs HW % 4 == 0 and 8-byte aligned channel rows, which the tensor-core path has anyway
+constexpr int kPix4 = 128;
+__global__ void __launch_bounds__(kWarps * 32) cln_stats4_kernel(const bf16* __restrict__ x, long long x_plane, long long x_b, int C, long long HW,
+                                                                float eps, float2* __restrict__ musr) {
+  __shared__ double red[kWarps][32][8];
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long p = (long long)blockIdx.x * kPix4 + 4 * lane;
+  const bool live = p < HW;  // HW % 4 == 0: a quad is live or dead as a whole
+  const bf16* xb = x + (long long)b * x_b + p;
+  double s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+  if (live) {
+#pragma unroll 4
+    for (int c = warp; c < C; c += kWarps) {
+      const uint2 h = __ldg(reinterpret_cast<const uint2*>(xb + (long long)c * HW));
+      const uint2 l = __ldg(reinterpret_cast<const uint2*>(xb + (long long)c * HW + x_plane));
+      const float v[4] = {__uint_as_float(h.x << 16) + __uint_as_float(l.x << 16), __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u),
+                          __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16), __uint_as_float(h.y & 0xffff0000u) + __uint_as_float(l.y & 0xffff0000u)};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const double d = (double)v[i];
+        s[i] += d;
+        q[i] = fma(d, d, q[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    red[warp][lane][2 * i] = s[i];
+    red[warp][lane][2 * i + 1] = q[i];
+  }
+  __syncthreads();
+  // 32 lanes x 4 pixels = 128 results: thread t < 128 finishes pixel t (lane t / 4, slot t % 4)
+  const int t = threadIdx.x;
+  if (t >= kPix4) return;
+  const int ln = t >> 2, i = t & 3;
+  const long long pp = (long long)blockIdx.x * kPix4 + t;
+  if (pp >= HW) return;
+  double ss = 0, qq = 0;
+#pragma unroll
+  for (int w = 0; w < kWarps; ++w) {
+    ss += red[w][ln][2 * i];
+    qq += red[w][ln][2 * i + 1];
+  }
+  const double m = ss / C;
+  musr[(long long)b * HW + pp] = make_float2((float)m, rsqrtf((float)fmax(qq / C - m * m, 0.0) + eps));
+}
+
 // ctx [B][Ep][HW] fp32 -> K-major B operand planes [B][HW][2 Ep]: the Ep context channels twice along k (the first half meets
 // the scale weights, the second half the bias weights); 32-pixel x 64-channel tiles are transposed through shared memory
 // (any Ep: the channel axis is walked 64 at a time)
@@ -490,8 +538,12 @@ __global__ void cln_w_planes_kernel(const float* __restrict__ w2, int C, int Ep,
 
 void launch_cln_stats(const bf16* x, long long x_plane, long long x_b, int B, int C, long long HW, float eps, float* musr, cudaStream_t stream) {
   ProfileScope prof("cln_stats", stream);
-  cln_stats_kernel<<<dim3((unsigned)((HW + kPix2 - 1) / kPix2), (unsigned)B), kWarps * 32, 0, stream>>>(x, x_plane, x_b, C, HW, eps,
-                                                                                                    reinterpret_cast<float2*>(musr));
+  if (HW % 4 == 0 && x_plane % 4 == 0 && x_b % 4 == 0 && ((uintptr_t)x & 7) == 0)
+    cln_stats4_kernel<<<dim3((unsigned)((HW + kPix4 - 1) / kPix4), (unsigned)B), kWarps * 32, 0, stream>>>(x, x_plane, x_b, C, HW, eps,
+                                                                                                      reinterpret_cast<float2*>(musr));
+  else
+    cln_stats_kernel<<<dim3((unsigned)((HW + kPix2 - 1) / kPix2), (unsigned)B), kWarps * 32, 0, stream>>>(x, x_plane, x_b, C, HW, eps,
+                                                                                                      reinterpret_cast<float2*>(musr));
   after_launch("cln_stats");
 }
 
