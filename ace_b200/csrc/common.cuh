@@ -107,9 +107,10 @@ struct Options {
   int bfly_pair = 1; // butterfly inverse DFT on CTA pairs when the row count is a multiple of 256
   int tile_serpentine = 1;  // tile lists of the triangular GEMMs: odd strata reversed so every worker's tile costs sum to about the same
   int sp_tmx = 1;    // SP variants fetch the epilogue's addend / residual tile by TMA (0: loads from the epilogue threads)
-  int cln_gemm = 0;  // 1: ConditionalLayerNorm of the noise-conditioned SFNO on the tcgen05 kernel (GemmOp::cln) where eligible. Parity green, but
-                     // measured 158 us (GEMM, bound by its epilogue: 12 warps per SM as a streaming engine) + 53 us (statistics) against 200 us of
-                     // the streaming kernel (profiles/r02_csfno_probe_cln_gemm.json): not the default
+  int cln_gemm = 1;  // ConditionalLayerNorm of the noise-conditioned SFNO on the tcgen05 kernel (GemmOp::cln: statistics pass + one GEMM whose
+                     // epilogue normalises and modulates) where eligible (>= 128 channels, pixel count % 4 == 0, context padded to a multiple
+                     // of 32); 0: the streaming kernel up to 64 context channels.  A/B on the ERA5-baseline network: 10.54 vs 10.71 ms per
+                     // forward (profiles/r02c_cln_ab.json); env ACE_B200_CLN_GEMM
   int trace = 0;     // development: per-tile clock samples of the tcgen05 kernel's roles appended to $ACE_B200_TRACE_FILE (tools/trace_report.py)
   int umma_bn = 0;   // 0 = choose per op; otherwise force the N tile of the K-major x K-major variants (192 / 256)
 };

@@ -17,7 +17,7 @@
 //
 // Unlike the InstanceNorm of the deterministic SFNO (sfno.cu), the conditional layer norm is per PIXEL over channels with a
 // per-pixel, per-channel affine map (functions of the noise field), so it cannot be folded into the neighbouring GEMMs'
-// per-row epilogues; it is one streaming kernel per norm (cln.cu).
+// per-row epilogues; it is a statistics pass + one GEMM with a normalising epilogue, or one streaming kernel, per norm (cln.cu).
 #include <map>
 #include <string>
 #include <vector>
@@ -227,9 +227,9 @@ void ensure_ws(ace_csfno& n, int B) {
   n.wsB = B;
 }
 
-// The tensor-core ConditionalLayerNorm (GemmOp::cln) is an option for the context widths the streaming kernel holds in registers
-// (Ep = 32 / 64: measured slower there) and the default beyond them, where 2 Ep FMAs per element on the FMA
-// pipe would cost more than the rest of the block
+// The tensor-core ConditionalLayerNorm (GemmOp::cln) is the default wherever the context is padded to a multiple of 32 (option
+// cln_gemm: 1.6 % of the ERA5-baseline forward at Ep = 32) and the only fast path beyond 64 context channels,
+// where the 2 Ep FMAs per element of the streaming kernel would cost more than the rest of the block
 bool cln_on_tensor_cores(const ace_csfno& n) {
   if (options().force_simt || n.Ep <= 0 || n.Ep % 32 != 0) return false;
   return n.Ep > 64 || options().cln_gemm;

@@ -87,7 +87,7 @@ def test_runtime_options_round_trip_without_gpu():
     the defaults are the measured winners."""
     from ace_b200 import _lib
 
-    defaults = {"sp": 1, "sp_tma": 1, "sp_tmx": 1, "mma_batch": 1, "bfly_pair": 1, "group_order": 1, "tile_serpentine": 1, "cln_gemm": 0,
+    defaults = {"sp": 1, "sp_tma": 1, "sp_tmx": 1, "mma_batch": 1, "bfly_pair": 1, "group_order": 1, "tile_serpentine": 1, "cln_gemm": 1,
                 "pdl": 0, "trace": 0, "tile_list": 1, "inv2": 1, "dhconv_t": 0, "nvtx": 0}
     for key, want in defaults.items():
         assert _lib.get_option(key) == want, key
