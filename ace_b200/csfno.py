@@ -459,16 +459,35 @@ class SphericalFourierNeuralOperatorNet(nn.Module):
             if self._uploaded.get(name) == key:
                 continue
             for p in sources:
-                if p.device != self._net_device:
+                if p.device != self._net_device and not (getattr(self, "_offloaded", False) and p.device.type == "cpu"):
                     raise _lib.AceError(f"parameter {name} is on {p.device}, input is on {self._net_device}")
             t = sources[0].detach() if build is None else build()
             if t.dtype != torch.float32 or not t.is_contiguous():
                 t = t.float().contiguous()
+            if t.device != self._net_device:  # offload_parameters(): an edited host copy, staged through a temporary device tensor
+                t = t.to(self._net_device)
             _lib.check(lib.ace_csfno_set_param(self._net, name.encode(), ctypes.c_void_p(t.data_ptr()), t.numel(), stream))
             self._uploaded[name] = key
             dirty = True
         if dirty:
             _lib.check(lib.ace_csfno_finalize(self._net, stream))
+
+    def offload_parameters(self):
+        """Single weight residency on the GPU (same contract as the deterministic network's ``offload_parameters``): once the device
+        library holds its split-plane copies, the torch fp32 parameters of this network move to host memory (-3 GB for the ERA5
+        baseline).  ``state_dict`` / ``load_state_dict`` / in-place edits keep working on the host copies; an edited parameter (or a
+        fold that depends on it) is rebuilt and re-uploaded before the next forward.  The envelope buffers stay on the device."""
+        if self._net is None:
+            raise _lib.AceError("offload_parameters(): run one forward first (the device library has no parameters yet)")
+        with torch.cuda.device(self._net_device):
+            self._sync_params(_lib.current_stream_ptr())
+            torch.cuda.current_stream().synchronize()
+        for prm in self.parameters():
+            prm.data = prm.data.cpu()
+        for name, sources, _ in self.device_parameters():
+            self._uploaded[name] = tuple((p.data_ptr(), p._version) for p in sources)
+        self._offloaded = True
+        return self
 
     # ------------------------------------------------------------------ forward
     def forward(self, x: torch.Tensor, context: Context):

@@ -483,3 +483,41 @@ def test_reference_timer_protocol_over_a_block():
     assert all(v > 0 for v in parts.values()) and sum(parts.values()) <= total * 1.001, (total, parts)
     f = timer.children["filter"]
     assert sum(c.ms() for c in f.children.values()) <= f.ms() * 1.001
+
+
+def test_offload_parameters_of_the_conditional_network():
+    """``offload_parameters()`` on the noise-conditioned network (a spectral LoRA fold included): torch parameters on the host, same
+    output bit for bit, host-side edits of a plain and of a folded parameter re-uploaded."""
+    from ace_b200 import csfno as bc
+
+    img, B = (32, 64), 2
+    torch.manual_seed(9)
+    net = bc.get_lat_lon_sfnonet(bc.SFNONetConfig(embed_dim=32, num_layers=2, spectral_lora_rank=2, affine_norms=True), in_chans=4, out_chans=3,
+                                 img_shape=img, data_grid="legendre-gauss", context_config=bc.ContextConfig(embed_dim_noise=8)).cuda().eval().requires_grad_(False)
+    with torch.no_grad():
+        for k, p in net.named_parameters():
+            if "lora" in k or "W_scale" in k or "W_bias" in k:
+                p.add_(0.1 * torch.randn_like(p))
+    x = torch.randn(B, 4, *img, device="cuda")
+    ctx = bc.Context(noise=torch.randn(B, 8, *img, device="cuda"))
+    y1 = net(x, ctx)
+    torch.cuda.synchronize()
+    nbytes = sum(p.numel() * 4 for p in net.parameters())
+    m0 = torch.cuda.memory_allocated()
+    net.offload_parameters()
+    assert all(p.device.type == "cpu" for p in net.parameters())
+    assert m0 - torch.cuda.memory_allocated() >= 0.9 * nbytes
+    assert torch.equal(net(x, ctx), y1)
+    net.decoder[2].weight.mul_(2.0)  # plain parameter, host-side edit
+    torch.testing.assert_close(net(x, ctx), 2 * y1, rtol=1e-4, atol=1e-6)
+    net.decoder[2].weight.mul_(0.5)
+    assert torch.equal(net(x, ctx), y1)
+    lu = net.blocks[0].filter.filter.lora_B  # a source of a FOLDED parameter (W_l + (alpha / r) B_l A_l)
+    lu.mul_(2.0)
+    assert not torch.equal(net(x, ctx), y1)
+    lu.mul_(0.5)
+    assert torch.equal(net(x, ctx), y1)
+    net.load_state_dict({k: v.clone() for k, v in net.state_dict().items()})  # everything is folded and uploaded again from the host copies
+    assert torch.equal(net(x, ctx), y1)
+    net.cuda()
+    assert torch.equal(net(x, ctx), y1)
