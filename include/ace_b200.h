@@ -134,7 +134,8 @@ int ace_sfno_query(ace_sfno* net, int* in_chans, int* out_chans, long long* hw);
  * "linear" (dhconv weights [1][L][O][I][2]), one filter group, scale_factor 1, encoder_layers 1, GELU, MLP, identity outer
  * skip, ConditionalLayerNorm (layers.py:143-320, channel LayerNorm per pixel, eps 1e-5) conditioned on any of: a scalar
  * embedding [batch][embed_dim_scalar], labels [batch][embed_dim_labels], a noise field [batch][embed_dim_noise][H][W], a
- * positional embedding [batch][embed_dim_pos][H][W].  embed_dim_noise + embed_dim_pos <= 64. */
+ * positional embedding [batch][embed_dim_pos][H][W] (any width: up to 64 channels one streaming kernel per norm or -- the
+ * default from 32 padded channels on -- a statistics pass + one tcgen05 GEMM; beyond 64 only the latter). */
 typedef struct ace_csfno_config {
   int img_h, img_w;
   int in_chans, out_chans;
